@@ -1,0 +1,178 @@
+"""ctypes bindings for the CPU oracle (oracle/liboracle.so) and for oracle/_ref/libref.so (the reference's own
+sources compiled from /root/reference).  TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs -- never by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from realtimepathtracingresearchframework_b200 import types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+f32p = C.POINTER(C.c_float)
+
+
+class OracleRenderArgs(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("camera", T.RenderCameraParams), ("params", T.RenderParams),
+                ("lighting", T.LightSamplingConfig), ("scene_params", T.SceneParams), ("frame_offset", C.c_uint32),
+                ("first_sample", C.c_uint32), ("n_samples", C.c_int32), ("x0", C.c_int32), ("y0", C.c_int32),
+                ("x1", C.c_int32), ("y1", C.c_int32), ("transmission", C.c_int32), ("n_threads", C.c_int32)]
+
+
+def build(force=False):
+    """make -C oracle (liboracle.so, and oracle/_ref when /root/reference is present)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    if force or not os.path.exists(so) or os.path.exists("/root/reference/rendering"):
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=subprocess.DEVNULL)
+    return so
+
+
+def _fp(a):
+    return a.ctypes.data_as(f32p)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.oracle_scene_create.restype = C.c_void_p
+        L.oracle_scene_create.argtypes = [C.POINTER(T.SceneDesc), C.POINTER(T.LightSamplingConfig)]
+        L.oracle_scene_destroy.argtypes = [C.c_void_p]
+        L.oracle_scene_num_tris.restype = C.c_int64
+        L.oracle_scene_num_tris.argtypes = [C.c_void_p]
+        L.oracle_scene_num_lights.argtypes = [C.c_void_p]
+        L.oracle_scene_get_lights.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_view_params.argtypes = [C.POINTER(T.RenderCameraParams), C.c_int32, C.c_int32, f32p]
+        L.oracle_render.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), f32p, C.POINTER(C.c_uint64)]
+        L.oracle_render_sample.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_uint32, f32p]
+        for n in ("oracle_trace_closest", "oracle_trace_closest_bruteforce"):
+            getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_int32, f32p, f32p]
+        L.oracle_lcg_seed.restype = C.c_uint32
+        L.oracle_lcg_seed.argtypes = [C.c_uint32] * 3
+        L.oracle_lcg_randomf.restype = C.c_float
+        L.oracle_lcg_randomf.argtypes = [C.POINTER(C.c_uint32)]
+        L.oracle_sincos.argtypes = [C.c_float, f32p, f32p]
+        for n in ("oracle_exp", "oracle_acos", "oracle_fast_positive_atan"):
+            getattr(L, n).restype = C.c_float
+            getattr(L, n).argtypes = [C.c_float]
+        L.oracle_gltf_wpdf.restype = C.c_float
+        L.oracle_hit_attributes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, f32p]
+        L.oracle_sky_illum.argtypes = [C.POINTER(T.SceneParams), f32p, C.c_float, f32p]
+        L.oracle_dequantize_position.argtypes = [C.c_uint64, f32p, f32p, f32p]
+        L.oracle_dequantize_normal.argtypes = [C.c_uint32, f32p]
+        L.oracle_dequantize_uv.argtypes = [C.c_uint32, f32p]
+        _lib = L
+    return _lib
+
+
+def ref():
+    """oracle/_ref/libref.so or None when it has not been built (it needs /root/reference at build time)."""
+    global _ref
+    if _ref is None:
+        so = os.path.join(_HERE, "_ref", "libref.so")
+        if not os.path.exists(so):
+            return None
+        R = C.CDLL(so)
+        R.ref_lcg_seed.restype = C.c_uint32
+        R.ref_lcg_seed.argtypes = [C.c_uint32] * 3
+        R.ref_lcg_randomf.restype = C.c_float
+        R.ref_lcg_randomf.argtypes = [C.POINTER(C.c_uint32)]
+        R.ref_fast_positive_atan.restype = C.c_float
+        R.ref_fast_positive_atan.argtypes = [C.c_float]
+        R.ref_gltf_wpdf.restype = C.c_float
+        R.ref_quantize_position.restype = C.c_uint64
+        R.ref_quantize_normal.restype = C.c_uint32
+        R.ref_quantize_uv.restype = C.c_uint32
+        R.ref_dequantize_position.argtypes = [C.c_uint64, f32p, f32p, f32p]
+        R.ref_dequantize_normal.argtypes = [C.c_uint32, f32p]
+        R.ref_dequantize_uv.argtypes = [C.c_uint32, f32p]
+        R.ref_sky_fit.argtypes = [C.POINTER(T.SceneConfig), C.POINTER(T.SceneParams)]
+        _ref = R
+    return _ref
+
+
+class OracleScene:
+    def __init__(self, scene, lighting=None):
+        self.scene = scene
+        self.lighting = lighting or T.LightSamplingConfig()
+        d = scene.desc()
+        self.h = lib().oracle_scene_create(C.byref(d), C.byref(self.lighting))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_scene_destroy(self.h)
+            self.h = None
+
+    @property
+    def num_tris(self):
+        return lib().oracle_scene_num_tris(self.h)
+
+    def lights(self):
+        n = lib().oracle_scene_num_lights(self.h)
+        arr = (T.TriLightData * max(n, 1))()
+        lib().oracle_scene_get_lights(self.h, arr)
+        return np.frombuffer(arr, dtype=np.float32).reshape(-1, 12)[:n].copy()
+
+    def _args(self, width, height, camera, scene_params, params=None, frame_offset=0, first_sample=0, n_samples=1,
+              region=None, transmission=0, n_threads=0):
+        a = OracleRenderArgs()
+        a.width, a.height = width, height
+        a.camera = camera
+        a.params = params or T.RenderParams()
+        a.lighting = self.lighting
+        a.scene_params = scene_params
+        a.frame_offset, a.first_sample, a.n_samples = frame_offset, first_sample, n_samples
+        x0, y0, x1, y1 = region or (0, 0, width, height)
+        a.x0, a.y0, a.x1, a.y1 = x0, y0, x1, y1
+        a.transmission, a.n_threads = transmission, n_threads
+        return a
+
+    def render(self, width, height, camera, scene_params, spp, out=None, **kw):
+        """Running mean over `spp` frames of batch_spp=1 -> (H, W, 4) float32, plus (closest, shadow, vertices) counters."""
+        a = self._args(width, height, camera, scene_params, n_samples=spp, **kw)
+        img = np.zeros((height, width, 4), np.float32) if out is None else out
+        stats = (C.c_uint64 * 3)()
+        lib().oracle_render(self.h, C.byref(a), _fp(img), stats)
+        return img, tuple(int(x) for x in stats)
+
+    def render_sample(self, width, height, camera, scene_params, sample_index, **kw):
+        a = self._args(width, height, camera, scene_params, **kw)
+        img = np.zeros((height, width, 4), np.float32)
+        lib().oracle_render_sample(self.h, C.byref(a), sample_index, _fp(img))
+        return img
+
+    def trace_closest(self, queries, bruteforce=False):
+        """queries: structured (n, 8) float32 view of RenderRayQuery -> (results (n,4) float32 bits, t (n,))."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, 8)
+        n = q.shape[0]
+        res = np.zeros((n, 4), np.float32)
+        t = np.zeros(n, np.float32)
+        fn = lib().oracle_trace_closest_bruteforce if bruteforce else lib().oracle_trace_closest
+        fn(self.h, q.ctypes.data, n, _fp(res), _fp(t))
+        return res, t
+
+
+def view_params(camera, w, h):
+    out = np.zeros(9, np.float32)
+    lib().oracle_view_params(C.byref(camera), w, h, _fp(out))
+    return out
+
+
+def sky_fit(config=None):
+    """update_sky_light through the reference's own sky_model.cpp (needs oracle/_ref)."""
+    R = ref()
+    if R is None:
+        raise RuntimeError("oracle/_ref/libref.so is not built (needs /root/reference at build time)")
+    cfg = config or T.SceneConfig()
+    sp = T.SceneParams()
+    R.ref_sky_fit(C.byref(cfg), C.byref(sp))
+    return sp

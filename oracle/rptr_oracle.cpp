@@ -1,0 +1,1184 @@
+// oracle/rptr_oracle.cpp -- TEST INFRASTRUCTURE. CPU restatement of the reference's per-pixel-sample path
+// tracing loop (PT_MEGAKERNEL with the LCG sampler).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library; the product (librptr_cuda.so) never does.
+//
+// PARITY STATUS: the reference ships no golden vectors, scenes or images for this path, and
+// its traversal/intersection and GLSL built-ins live in the Vulkan driver.  The functions the reference can
+// execute as C++ (BSDF, LCG, triangle lights, hit attributes, sky fit, light binning) are pinned against
+// oracle/_ref (the reference's own sources compiled from /root/reference, see oracle/Makefile) in
+// tests/test_oracle_vs_ref.py and through tests/golden/.  The GLSL-only driver loop below (pt_megakernel.glsl,
+// shade_base_material.glsl, nee.glsl) and the ray/triangle routine are restatements: "parity unpinned" for those.
+//
+// Structure follows the reference megakernel (one sequential loop per pixel sample), NOT the CUDA wavefront.
+#include "shading_oracle.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// scene: instances flattened to world-space triangles (the closest-hit contract of SURVEY 8a-4: Moeller-Trumbore
+// on world-space (v0, e1, e2), no culling, hit iff tmin < t < tmax, ties -> lowest flattened triangle id)
+// ------------------------------------------------------------------------------------------------------------
+struct GeomInst { // one entry of the reference's instanced_geometry[] (rendering/rt/geometry.h.glsl:72-98)
+    const uint64_t *qverts;
+    const uint64_t *qnuv;
+    float scale[3], offset[3];
+    int n_tris;
+    bool has_normals, has_uvs;
+    int material_id;         // >= 0: constant; < 0: -1 - material_offset with per-triangle ids
+    const uint8_t *tri_mat;  // per-triangle ids of this geometry (already offset by primOffset)
+    uint32_t flags;
+    int instance;
+    float o2w[12];  // object-to-world rows
+    V3 w2o_row[3];  // rows of inverse(mat3(o2w)): columns of normals_to_world = transpose(world_to_object)
+    int64_t first_tri;
+};
+struct Tri {
+    V3 v0, e1, e2;
+    int geom_inst, prim;
+};
+struct Node {
+    float bmin[3], bmax[3];
+    int left, right; // inner: children; leaf: left = -1 - first, right = count
+};
+
+static inline V3 xfm_point(const float *m, V3 v) {
+    return v3(fmaf(m[0], v.x, fmaf(m[1], v.y, fmaf(m[2], v.z, m[3]))), fmaf(m[4], v.x, fmaf(m[5], v.y, fmaf(m[6], v.z, m[7]))),
+              fmaf(m[8], v.x, fmaf(m[9], v.y, fmaf(m[10], v.z, m[11]))));
+}
+
+struct Scene {
+    std::vector<GeomInst> ginst;
+    std::vector<Tri> tris;
+    std::vector<int> tri_order; // bvh leaf order -> triangle id
+    std::vector<Node> nodes;
+    std::vector<rptr_base_material> materials;
+    std::vector<rptr_tri_light_data> lights;
+    bool any_non_opaque = false;
+    // owned copies of the input streams (the caller's Scene dies after set_scene, app.cpp:151-175)
+    std::vector<std::vector<uint64_t>> own_qv, own_qn;
+    std::vector<std::vector<uint8_t>> own_tm;
+};
+
+// --- binned SAH BVH2 over padded triangle boxes ---------------------------------------------------------------
+struct BuildPrim { float bmin[3], bmax[3], c[3]; int id; };
+
+static void tri_bounds(const Tri &t, float *mn, float *mx) {
+    V3 a = t.v0, b = t.v0 + t.e1, c = t.v0 + t.e2;
+    float pa[3][3] = {{a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}};
+    for (int k = 0; k < 3; ++k) {
+        mn[k] = fminf(pa[0][k], fminf(pa[1][k], pa[2][k]));
+        mx[k] = fmaxf(pa[0][k], fmaxf(pa[1][k], pa[2][k]));
+        // conservative padding so that box culling never rejects a hit the triangle routine accepts
+        float pad = 1.52587890625e-05f * fmaxf(fabsf(mn[k]), fabsf(mx[k])) + 1e-30f;
+        mn[k] -= pad;
+        mx[k] += pad;
+    }
+}
+
+static int build_rec(Scene &s, std::vector<BuildPrim> &p, int lo, int hi) {
+    int idx = (int)s.nodes.size();
+    s.nodes.push_back(Node());
+    float bmin[3] = {1e30f, 1e30f, 1e30f}, bmax[3] = {-1e30f, -1e30f, -1e30f}, cmin[3] = {1e30f, 1e30f, 1e30f},
+          cmax[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = lo; i < hi; ++i)
+        for (int k = 0; k < 3; ++k) {
+            bmin[k] = fminf(bmin[k], p[i].bmin[k]);
+            bmax[k] = fmaxf(bmax[k], p[i].bmax[k]);
+            cmin[k] = fminf(cmin[k], p[i].c[k]);
+            cmax[k] = fmaxf(cmax[k], p[i].c[k]);
+        }
+    for (int k = 0; k < 3; ++k) {
+        s.nodes[idx].bmin[k] = bmin[k];
+        s.nodes[idx].bmax[k] = bmax[k];
+    }
+    int n = hi - lo;
+    auto make_leaf = [&]() {
+        s.nodes[idx].left = -1 - (int)s.tri_order.size();
+        s.nodes[idx].right = n;
+        for (int i = lo; i < hi; ++i) s.tri_order.push_back(p[i].id);
+        return idx;
+    };
+    if (n <= 2) return make_leaf();
+    const int NB = 16;
+    int best_axis = -1, best_bin = -1;
+    float best_cost = 1e30f;
+    auto area = [](const float *mn, const float *mx) {
+        float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    for (int ax = 0; ax < 3; ++ax) {
+        float ext = cmax[ax] - cmin[ax];
+        if (!(ext > 0.0f)) continue;
+        float bmn[NB][3], bmx[NB][3];
+        int cnt[NB];
+        for (int b = 0; b < NB; ++b) {
+            cnt[b] = 0;
+            for (int k = 0; k < 3; ++k) { bmn[b][k] = 1e30f; bmx[b][k] = -1e30f; }
+        }
+        float sc = (float)NB / ext;
+        for (int i = lo; i < hi; ++i) {
+            int b = std::min(NB - 1, std::max(0, (int)((p[i].c[ax] - cmin[ax]) * sc)));
+            cnt[b]++;
+            for (int k = 0; k < 3; ++k) {
+                bmn[b][k] = fminf(bmn[b][k], p[i].bmin[k]);
+                bmx[b][k] = fmaxf(bmx[b][k], p[i].bmax[k]);
+            }
+        }
+        float ra[NB];
+        int rc[NB];
+        float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+        int c = 0;
+        for (int b = NB - 1; b > 0; --b) {
+            for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], bmn[b][k]); mx[k] = fmaxf(mx[k], bmx[b][k]); }
+            c += cnt[b];
+            ra[b] = c ? area(mn, mx) : 0.0f;
+            rc[b] = c;
+        }
+        for (int k = 0; k < 3; ++k) { mn[k] = 1e30f; mx[k] = -1e30f; }
+        c = 0;
+        for (int b = 0; b < NB - 1; ++b) {
+            for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], bmn[b][k]); mx[k] = fmaxf(mx[k], bmx[b][k]); }
+            c += cnt[b];
+            if (c == 0 || rc[b + 1] == 0) continue;
+            float cost = area(mn, mx) * (float)c + ra[b + 1] * (float)rc[b + 1];
+            if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; }
+        }
+    }
+    int mid;
+    if (best_axis < 0) {
+        if (n <= 8) return make_leaf();
+        mid = lo + n / 2;
+    } else {
+        float leaf_cost = area(bmin, bmax) * (float)n;
+        if (n <= 4 && leaf_cost <= best_cost + area(bmin, bmax)) return make_leaf();
+        float ext = cmax[best_axis] - cmin[best_axis];
+        float sc = (float)NB / ext;
+        float cm = cmin[best_axis];
+        int ax = best_axis, bb = best_bin;
+        auto it = std::partition(p.begin() + lo, p.begin() + hi, [&](const BuildPrim &q) {
+            int b = std::min(NB - 1, std::max(0, (int)((q.c[ax] - cm) * sc)));
+            return b <= bb;
+        });
+        mid = (int)(it - p.begin());
+        if (mid == lo || mid == hi) mid = lo + n / 2;
+    }
+    int l = build_rec(s, p, lo, mid);
+    int r = build_rec(s, p, mid, hi);
+    s.nodes[idx].left = l;
+    s.nodes[idx].right = r;
+    return idx;
+}
+
+static void build_bvh(Scene &s) {
+    s.nodes.clear();
+    s.tri_order.clear();
+    std::vector<BuildPrim> p(s.tris.size());
+    for (size_t i = 0; i < s.tris.size(); ++i) {
+        tri_bounds(s.tris[i], p[i].bmin, p[i].bmax);
+        for (int k = 0; k < 3; ++k) p[i].c[k] = 0.5f * (p[i].bmin[k] + p[i].bmax[k]);
+        p[i].id = (int)i;
+    }
+    if (p.empty()) return;
+    s.nodes.reserve(p.size());
+    build_rec(s, p, 0, (int)p.size());
+}
+
+// --- ray/triangle: the shared closest-hit contract -------------------------------------------------------------
+struct Hit { float t, u, v; int tri; };
+
+static inline bool intersect_tri(const Tri &tr, V3 o, V3 d, float &t, float &u, float &v) {
+    V3 p = cross(d, tr.e2);
+    float det = dot(tr.e1, p);
+    if (det == 0.0f) return false;
+    float inv = 1.0f / det;
+    V3 s = o - tr.v0;
+    u = dot(s, p) * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    V3 q = cross(s, tr.e1);
+    v = dot(d, q) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+    t = dot(tr.e2, q) * inv;
+    return true;
+}
+
+static inline bool slab(const Node &n, V3 o, V3 inv, float tmin, float tmax) {
+    float t0 = (n.bmin[0] - o.x) * inv.x, t1 = (n.bmax[0] - o.x) * inv.x;
+    float tn = fminf(t0, t1), tf = fmaxf(t0, t1);
+    t0 = (n.bmin[1] - o.y) * inv.y; t1 = (n.bmax[1] - o.y) * inv.y;
+    tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
+    t0 = (n.bmin[2] - o.z) * inv.z; t1 = (n.bmax[2] - o.z) * inv.z;
+    tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
+    tf *= 1.0000004f; // keep the slab test conservative against rounding
+    return tn <= tf && tf >= tmin && tn <= tmax;
+}
+
+// after = (t0, id0): only hits strictly after that key in (t, id) order qualify (used to continue past
+// alpha-rejected candidates front to back).  Pass t0 = tmin, id0 = INT_MAX for a plain query.
+static bool closest_hit(const Scene &s, V3 o, V3 d, float tmin, float tmax, float after_t, int after_id, Hit &best) {
+    best.tri = -1;
+    best.t = tmax;
+    if (s.nodes.empty()) return false;
+    V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[128];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+        const Node &n = s.nodes[stack[--sp]];
+        if (!slab(n, o, inv, tmin, best.t)) continue;
+        if (n.left < 0) {
+            int first = -1 - n.left;
+            for (int i = 0; i < n.right; ++i) {
+                int id = s.tri_order[first + i];
+                float t, u, v;
+                if (!intersect_tri(s.tris[id], o, d, t, u, v)) continue;
+                if (!(t > tmin && t < tmax)) continue;
+                if (!(t > after_t || (t == after_t && id > after_id))) continue;
+                if (best.tri < 0 || t < best.t || (t == best.t && id < best.tri)) {
+                    best.t = t; best.u = u; best.v = v; best.tri = id;
+                }
+            }
+        } else {
+            stack[sp++] = n.left;
+            stack[sp++] = n.right;
+        }
+    }
+    return best.tri >= 0;
+}
+
+// calls f(tri id, t, u, v) for every triangle hit in (tmin, tmax) until it returns true (= occluded)
+template <class F>
+static bool any_hit(const Scene &s, V3 o, V3 d, float tmin, float tmax, F &&f) {
+    if (s.nodes.empty()) return false;
+    V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[128];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+        const Node &n = s.nodes[stack[--sp]];
+        if (!slab(n, o, inv, tmin, tmax)) continue;
+        if (n.left < 0) {
+            int first = -1 - n.left;
+            for (int i = 0; i < n.right; ++i) {
+                int id = s.tri_order[first + i];
+                float t, u, v;
+                if (!intersect_tri(s.tris[id], o, d, t, u, v)) continue;
+                if (!(t > tmin && t < tmax)) continue;
+                if (f(id, t, u, v)) return true;
+            }
+        } else {
+            stack[sp++] = n.left;
+            stack[sp++] = n.right;
+        }
+    }
+    return false;
+}
+
+// --- hit attributes: rendering/rt/hit.glsl:49-128,162-203 -------------------------------------------------------
+struct RTHit {
+    V3 normal; float dist; V3 geo_normal; int material_id; V3 tangent; float bitangent_l; V2 uv;
+};
+
+static inline int calc_hit_material_id(const GeomInst &g, uint32_t prim) { // hit.glsl:49-56
+    if (g.material_id < 0) return (int)g.tri_mat[prim] - g.material_id - 1;
+    return g.material_id;
+}
+
+static RTHit calc_hit_attributes(const GeomInst &g, float ray_t, uint32_t prim, float ax, float ay) {
+    RTHit h;
+    h.dist = ray_t;
+    V3 p0 = dequantize_position(g.qverts[3 * (size_t)prim + 0], g.scale, g.offset);
+    V3 p1 = dequantize_position(g.qverts[3 * (size_t)prim + 1], g.scale, g.offset);
+    V3 p2 = dequantize_position(g.qverts[3 * (size_t)prim + 2], g.scale, g.offset);
+    V3 gn = cross(p1 - p0, p2 - p0);
+    V3 bary = v3(1.0f - ax - ay, ax, ay);
+    V3 n = gn;
+    uint64_t qa = 0, qb = 0, qc = 0;
+    if (g.has_normals || g.has_uvs) {
+        qa = g.qnuv[3 * (size_t)prim + 0];
+        qb = g.qnuv[3 * (size_t)prim + 1];
+        qc = g.qnuv[3 * (size_t)prim + 2];
+    }
+    if (g.has_normals) {
+        n = mat_mul(dequantize_normal((uint32_t)qa), dequantize_normal((uint32_t)qb), dequantize_normal((uint32_t)qc), bary);
+        if (dot(n, gn) < 0.0f) gn = -gn;
+    }
+    h.geo_normal = gn * 0.5f;
+    h.normal = n;
+    V2 uva{0, 0}, uvb{0, 0}, uvc{0, 0};
+    h.uv = V2{0.0f, 0.0f};
+    if (g.has_uvs) {
+        uva = dequantize_uv((uint32_t)(qa >> 32));
+        uvb = dequantize_uv((uint32_t)(qb >> 32));
+        uvc = dequantize_uv((uint32_t)(qc >> 32));
+        h.uv = V2{fmaf(uvc.x, bary.z, fmaf(uvb.x, bary.y, uva.x * bary.x)), fmaf(uvc.y, bary.z, fmaf(uvb.y, bary.y, uva.y * bary.x))};
+    }
+    h.material_id = calc_hit_material_id(g, prim);
+    const V3 *r = g.w2o_row;
+    h.geo_normal = mat_mul(r[0], r[1], r[2], h.geo_normal);
+    h.normal = normalize(mat_mul(r[0], r[1], r[2], h.normal));
+    bool requires_tangent = true;
+    if (g.has_uvs) {
+        float det = length(gn);
+        V3 frame_n = gn / (det * det);
+        V3 dp2perp = cross(p2 - p0, frame_n);
+        V3 dp1perp = cross(frame_n, p1 - p0);
+        V2 duv1{uvb.x - uva.x, uvb.y - uva.y}, duv2{uvc.x - uva.x, uvc.y - uva.y};
+        V3 T = dp2perp * duv1.x + dp1perp * duv2.x;
+        V3 B = dp2perp * duv1.y + dp1perp * duv2.y;
+        T = mat_mul(r[0], r[1], r[2], T);
+        B = mat_mul(r[0], r[1], r[2], B);
+        float Tlen = length(T);
+        if (Tlen > 0.0f && !std::isinf(Tlen) && !std::isnan(Tlen)) {
+            h.tangent = T;
+            h.bitangent_l = dot(normalize(cross(h.geo_normal, T)), B);
+            requires_tangent = false;
+        }
+    }
+    if (requires_tangent) {
+        h.tangent = normalize(mat_mul(r[0], r[1], r[2], cross(p2 - p0, gn)));
+        h.bitangent_l = 1.0f;
+    }
+    return h;
+}
+
+// --- host pre-passes --------------------------------------------------------------------------------------------
+static inline float halton2(unsigned index) { // util/compute_util.h:19-33
+    index = (index << 16) | (index >> 16);
+    index = ((index & 0x00ff00ffu) << 8) | ((index & 0xff00ff00u) >> 8);
+    index = ((index & 0x0f0f0f0fu) << 4) | ((index & 0xf0f0f0f0u) >> 4);
+    index = ((index & 0x33333333u) << 2) | ((index & 0xccccccccu) >> 2);
+    index = ((index & 0x55555555u) << 1) | ((index & 0xaaaaaaaau) >> 1);
+    return u2f(0x3f800000u | (index >> 9)) - 1.0f;
+}
+
+struct Emitter { V3 v0, v1, v2, radiance; };
+
+static inline float host_luminance(V3 c) { return 0.2126f * c.x + 0.7152f * c.y + 0.0722f * c.z; } // util/util.cpp:293-296
+
+// librender/lights.cpp:131-166 (host variant: libm atan, not the shader polynomial)
+static float host_triangle_solid_angle(V3 v0, V3 v1, V3 v2) {
+    V3 prm;
+    float tangent = half_tri_solid_angle_tan(v0, v1, v2, prm);
+    float off = (tangent < 0.0f) ? (float)M_PI : 0.0f;
+    return 2.0f * (atanf(tangent) + off);
+}
+
+// librender/lights.cpp:169-203
+static std::vector<float> estimate_normalized_radiance(const std::vector<Emitter> &em, float min_dist) {
+    std::vector<float> rad(em.size());
+    for (size_t i = 0; i < em.size(); ++i) {
+        const Emitter &l = em[i];
+        V3 n = normalize(cross(l.v1 - l.v0, l.v2 - l.v0));
+        if (!(fabsf(length(n) - 1.0f) < 0.05f)) { rad[i] = 0.0f; continue; }
+        V3 c = (l.v0 + l.v1 + l.v2) / 3.0f;
+        V3 o = n * min_dist;
+        float sa = host_triangle_solid_angle(normalize(l.v0 - c - o), normalize(l.v1 - c - o), normalize(l.v2 - c - o));
+        rad[i] = (float)((double)host_luminance(l.radiance) * ((double)sa / M_2_PI)); // sic: M_2_PI = 2/pi
+    }
+    return rad;
+}
+
+// librender/lights.cpp:220-349
+static void equalize_emitter_bins(std::vector<Emitter> &emitters, std::vector<float> &radiances, int bin_size) {
+    if (bin_size <= 1 || radiances.empty()) return;
+    int n0 = (int)radiances.size();
+    int original_bin_count = (n0 + (bin_size - 1)) / bin_size;
+    float average_weight = 0.0f;
+    for (int i = 0; i < n0; ++i) average_weight += radiances[i];
+    average_weight /= (float)radiances.size();
+    struct Bin { float radiance; int source_idx; int split_count; };
+    std::vector<Bin> bins;
+    bins.reserve(2 * radiances.size());
+    for (int i = 0; i < n0; ++i) {
+        float w = radiances[i];
+        int clones = (int)std::max((unsigned)std::min(w / average_weight, (float)original_bin_count), 1u);
+        for (int j = 0; j < clones; ++j) bins.push_back(Bin{radiances[i] / (float)clones, i, clones});
+    }
+    std::vector<Bin> shuffled;
+    auto reshuffle = [&]() {
+        shuffled.resize(bins.size());
+        for (int index = 0, count = (int)bins.size(); index < count; ++index) {
+            int src = (int)(unsigned)(halton2((unsigned)index) * (float)(unsigned)count);
+            for (;;) {
+                if (src >= count) src = 0;
+                if (bins[src].source_idx == ~0) ++src;
+                else break;
+            }
+            shuffled[index] = bins[src];
+            bins[src].source_idx = ~0;
+        }
+        bins = std::move(shuffled);
+        shuffled.clear();
+    };
+    reshuffle();
+    auto measure = [bin_size](const std::vector<Bin> &b) {
+        float mn = 2.0e32f, mx = 0.0f;
+        for (int i = 0, ie = (int)b.size(); i < ie;) {
+            float tot = 0.0f;
+            for (int j = 0; j < bin_size && i < ie; ++i, ++j) tot += b[i].radiance;
+            mn = std::min(tot, mn);
+            mx = std::max(tot, mx);
+        }
+        return std::min(mn / mx, 1.0f);
+    };
+    float equality = measure(bins);
+    std::vector<Bin> postfix;
+    for (int retries = 0; equality < 0.6f && retries < 2; ++retries) {
+        postfix.resize(bins.size());
+        Bin acc = bins[0];
+        postfix[0] = acc;
+        for (size_t i = 1; i < bins.size(); ++i) {
+            acc = Bin{acc.radiance + bins[i].radiance, bins[i].source_idx, 1};
+            postfix[i] = acc;
+        }
+        postfix.front().split_count = 1;
+        float sum = postfix.back().radiance;
+        for (auto &it : postfix) it.radiance /= sum;
+        int prev_elements = (int)bins.size();
+        int prev_bin_count = (prev_elements + (bin_size - 1)) / bin_size;
+        int padded = (prev_bin_count + 1) * bin_size;
+        unsigned hidx = 0;
+        while ((int)bins.size() < padded) {
+            float u = halton2(hidx++);
+            auto it = std::upper_bound(postfix.begin(), postfix.end(), u, [](float bound, const Bin &b) { return bound < b.radiance; });
+            if (it == postfix.end()) it = postfix.end() - 1;
+            ++it->split_count;
+            bins.push_back(Bin{it->radiance, (int)(it - postfix.begin()), 0});
+        }
+        for (int i = prev_elements; i < padded; ++i) {
+            Bin &clone = bins[i];
+            Bin &orig = bins[clone.source_idx];
+            int &counter = postfix[clone.source_idx].split_count;
+            if (counter > 1) {
+                orig.radiance /= (float)counter;
+                orig.split_count *= counter;
+                counter = 1;
+            }
+            clone.radiance = orig.radiance;
+            clone.source_idx = orig.source_idx;
+            clone.split_count = orig.split_count;
+        }
+        reshuffle();
+        equality = measure(bins);
+    }
+    std::vector<Emitter> out(bins.size());
+    radiances.resize(bins.size());
+    for (size_t i = 0; i < bins.size(); ++i) {
+        radiances[i] = bins[i].radiance;
+        out[i] = emitters[bins[i].source_idx];
+        out[i].radiance = out[i].radiance / (float)bins[i].split_count;
+    }
+    emitters = std::move(out);
+}
+
+} // namespace
+
+// ================================================================================================================
+// C API (ctypes-callable)
+// ================================================================================================================
+extern "C" {
+
+typedef struct oracle_render_args {
+    int32_t width, height;
+    rptr_camera_params camera;
+    rptr_render_params params;
+    rptr_light_sampling_config lighting;
+    rptr_scene_params scene_params; // sun_radiance[3] as produced by the sky fit BEFORE the light-count rule
+    uint32_t frame_offset;
+    uint32_t first_sample;  // frame_id of the first frame
+    int32_t n_samples;      // number of frames (batch_spp = 1 each)
+    int32_t x0, y0, x1, y1; // pixel region to render (x1/y1 exclusive)
+    int32_t transmission;   // 0 = megakernel build (no GLTF_SUPPORT_TRANSMISSION)
+    int32_t n_threads;      // 0 = all
+} oracle_render_args;
+
+struct oracle_scene { Scene s; };
+
+// Host inverse of the 3x3 part, rows of the inverse = cross products of columns / det.
+static void inverse_rows(const float *m, V3 *rows) {
+    V3 c0 = v3(m[0], m[4], m[8]), c1 = v3(m[1], m[5], m[9]), c2 = v3(m[2], m[6], m[10]);
+    V3 r0 = cross(c1, c2), r1 = cross(c2, c0), r2 = cross(c0, c1);
+    float det = dot(c0, r0);
+    float inv = 1.0f / det;
+    rows[0] = r0 * inv;
+    rows[1] = r1 * inv;
+    rows[2] = r2 * inv;
+}
+
+oracle_scene *oracle_scene_create(const rptr_scene_desc *d, const rptr_light_sampling_config *ls) {
+    oracle_scene *os = new oracle_scene();
+    Scene &s = os->s;
+    s.materials.assign(d->materials, d->materials + d->n_materials);
+    // copy the streams
+    s.own_qv.resize(d->n_geometries);
+    s.own_qn.resize(d->n_geometries);
+    for (int g = 0; g < d->n_geometries; ++g) {
+        const rptr_geometry_desc &gd = d->geometries[g];
+        s.own_qv[g].assign(gd.qverts, gd.qverts + 3 * (size_t)gd.n_tris);
+        if (gd.qnormal_uv && (gd.has_normals || gd.has_uvs)) s.own_qn[g].assign(gd.qnormal_uv, gd.qnormal_uv + 3 * (size_t)gd.n_tris);
+    }
+    s.own_tm.resize(d->n_pmeshes);
+    for (int p = 0; p < d->n_pmeshes; ++p)
+        if (d->pmeshes[p].tri_material_ids)
+            s.own_tm[p].assign(d->pmeshes[p].tri_material_ids, d->pmeshes[p].tri_material_ids + d->pmeshes[p].n_tri_material_ids);
+
+    std::vector<Emitter> emitters;
+    std::vector<char> pmesh_nonemissive(d->n_pmeshes, 0);
+    for (int i = 0; i < d->n_instances; ++i) {
+        const rptr_instance_desc &inst = d->instances[i];
+        const rptr_pmesh_desc &pm = d->pmeshes[inst.pmesh_id];
+        const rptr_mesh_desc &mesh = d->meshes[pm.mesh_id];
+        bool per_tri = pm.tri_material_ids != nullptr;
+        // vulkan/render_vulkan.cpp:1116-1131: pmesh no_alpha = all its materials are NOALPHA
+        int64_t prim_offset = 0;
+        std::vector<Emitter> next;
+        for (int j = 0; j < mesh.n_geometries; ++j) {
+            int g = mesh.first_geometry + j;
+            const rptr_geometry_desc &gd = d->geometries[g];
+            GeomInst gi;
+            gi.qverts = s.own_qv[g].data();
+            gi.qnuv = s.own_qn[g].empty() ? nullptr : s.own_qn[g].data();
+            for (int k = 0; k < 3; ++k) { gi.scale[k] = gd.quantized_scaling[k]; gi.offset[k] = gd.quantized_offset[k]; }
+            gi.n_tris = gd.n_tris;
+            gi.has_normals = gd.has_normals && gi.qnuv;
+            gi.has_uvs = gd.has_uvs && gi.qnuv;
+            int mat_off = pm.n_material_offsets ? pm.material_offsets[j] : 0;
+            gi.flags = RPTR_GEOMETRY_FLAGS_IMPLICIT_INDICES;
+            gi.tri_mat = nullptr;
+            bool no_alpha;
+            if (per_tri) { // render_vulkan.cpp:2812-2818
+                gi.material_id = -1 - mat_off;
+                gi.tri_mat = s.own_tm[inst.pmesh_id].data() + prim_offset;
+                gi.flags |= RPTR_GEOMETRY_FLAGS_EXTENDED_SHADER;
+                no_alpha = true;
+                for (int t = 0; t < gd.n_tris; ++t)
+                    if (!(s.materials[mat_off + gi.tri_mat[t]].flags & RPTR_BASE_MATERIAL_NOALPHA)) { no_alpha = false; break; }
+            } else {
+                gi.material_id = mat_off;
+                no_alpha = (s.materials[mat_off].flags & RPTR_BASE_MATERIAL_NOALPHA) != 0;
+                if (s.materials[mat_off].flags & RPTR_BASE_MATERIAL_EXTENDED) gi.flags |= RPTR_GEOMETRY_FLAGS_EXTENDED_SHADER;
+                if (!(s.materials[mat_off].flags & RPTR_BASE_MATERIAL_ONESIDED)) gi.flags |= RPTR_GEOMETRY_FLAGS_THIN;
+            }
+            if (no_alpha) gi.flags |= RPTR_GEOMETRY_FLAGS_NOALPHA;
+            else s.any_non_opaque = true;
+            gi.instance = i;
+            std::memcpy(gi.o2w, inst.transform, sizeof(gi.o2w));
+            inverse_rows(gi.o2w, gi.w2o_row);
+            gi.first_tri = (int64_t)s.tris.size();
+            int gidx = (int)s.ginst.size();
+            for (int t = 0; t < gd.n_tris; ++t) {
+                V3 a = xfm_point(gi.o2w, dequantize_position(gi.qverts[3 * (size_t)t + 0], gi.scale, gi.offset));
+                V3 b = xfm_point(gi.o2w, dequantize_position(gi.qverts[3 * (size_t)t + 1], gi.scale, gi.offset));
+                V3 c = xfm_point(gi.o2w, dequantize_position(gi.qverts[3 * (size_t)t + 2], gi.scale, gi.offset));
+                s.tris.push_back(Tri{a, b - a, c - a, gidx, t});
+                // collect_emitters (librender/lights.cpp:33-73)
+                if (!pmesh_nonemissive[inst.pmesh_id]) {
+                    int mid = per_tri ? mat_off + gi.tri_mat[t] : mat_off;
+                    const rptr_base_material &m = s.materials[mid];
+                    if (m.emission_intensity > 0.0f) {
+                        V3 rad = v3(m.base_color[0], m.base_color[1], m.base_color[2]) * m.emission_intensity;
+                        next.push_back(Emitter{a, b, c, rad});
+                    }
+                }
+            }
+            s.ginst.push_back(gi);
+            prim_offset += gd.n_tris;
+        }
+        if (!pmesh_nonemissive[inst.pmesh_id]) { // lights.cpp:17-30: new emitters are PREPENDED
+            if (!next.empty()) emitters.insert(emitters.begin(), next.begin(), next.end());
+            else pmesh_nonemissive[inst.pmesh_id] = 1;
+        }
+    }
+    if (d->binned_lights) {
+        s.lights.assign(d->binned_lights, d->binned_lights + d->n_binned_lights);
+    } else if (!emitters.empty()) { // update_light_sampling, lights.cpp:75-90
+        std::vector<float> rad = estimate_normalized_radiance(emitters, ls->min_perceived_receiver_dist);
+        if (ls->min_radiance > 0.0f) {
+            size_t n = 0;
+            for (size_t i = 0; i < emitters.size(); ++i)
+                if (rad[i] >= ls->min_radiance) { emitters[n] = emitters[i]; rad[n] = rad[i]; ++n; }
+            emitters.resize(n);
+            rad.resize(n);
+        }
+        equalize_emitter_bins(emitters, rad, ls->bin_size);
+        for (const Emitter &e : emitters) {
+            rptr_tri_light_data t;
+            t.v0[0] = e.v0.x; t.v0[1] = e.v0.y; t.v0[2] = e.v0.z;
+            t.v1[0] = e.v1.x; t.v1[1] = e.v1.y; t.v1[2] = e.v1.z;
+            t.v2[0] = e.v2.x; t.v2[1] = e.v2.y; t.v2[2] = e.v2.z;
+            t.radiance[0] = e.radiance.x; t.radiance[1] = e.radiance.y; t.radiance[2] = e.radiance.z;
+            s.lights.push_back(t);
+        }
+    }
+    build_bvh(s);
+    return os;
+}
+
+void oracle_scene_destroy(oracle_scene *s) { delete s; }
+int64_t oracle_scene_num_tris(const oracle_scene *s) { return (int64_t)s->s.tris.size(); }
+int32_t oracle_scene_num_lights(const oracle_scene *s) { return (int32_t)s->s.lights.size(); }
+void oracle_scene_get_lights(const oracle_scene *s, rptr_tri_light_data *out) {
+    std::memcpy(out, s->s.lights.data(), s->s.lights.size() * sizeof(rptr_tri_light_data));
+}
+
+// vulkan/render_vulkan.cpp:2880-2894 -> out = du(3), dv(3), top_left(3)
+void oracle_view_params(const rptr_camera_params *cam, int32_t w, int32_t h, float *out) {
+    V3 dir = v3(cam->dir[0], cam->dir[1], cam->dir[2]), up = v3(cam->up[0], cam->up[1], cam->up[2]);
+    float py = 2.0f * tanf(0.5f * cam->fovy * 0.01745329251994329576923690768489f);
+    float aspect = (float)w / (float)h;
+    float px = py * aspect;
+    V3 du = normalize(cross(dir, up)) * px;
+    V3 dv = -normalize(cross(du, dir)) * py;
+    V3 tl = dir - du * 0.5f - dv * 0.5f;
+    out[0] = du.x; out[1] = du.y; out[2] = du.z;
+    out[3] = dv.x; out[4] = dv.y; out[5] = dv.z;
+    out[6] = tl.x; out[7] = tl.y; out[8] = tl.z;
+}
+
+} // extern "C"
+
+namespace {
+
+struct Frame {
+    const Scene *s;
+    const oracle_render_args *a;
+    rptr_scene_params sp; // with the light-count rule applied to sun_radiance.w
+    V3 cam_pos, du, dv, tl;
+    int n_lights, n_bins;
+    bool tr;
+};
+
+// counters for the roofline bookkeeping the bench reports (path vertices / shadow rays per sample)
+struct Counters { uint64_t closest_rays = 0, shadow_rays = 0, vertices = 0; };
+
+// sample_tri_lights: rendering/mc/lights_linear.glsl:19-127 (BINNED_LIGHTS_BIN_MAX_SIZE = 16)
+static V3 sample_tri_lights(const Frame &f, V3 hit_p, V3 hit_n, V2 dir_sample, V2 sel, V3 &light_dir, float &light_dist,
+                            float &pdf, float &mis_wpdf) {
+    int num_lights = f.n_lights;
+    int num_bins = f.n_bins;
+    int bin_size = f.a->lighting.bin_size;
+    sel.x *= (float)num_bins;
+    int bin_id = (int)(uint32_t)sel.x;
+    bin_id = std::min(bin_id, num_bins - 1);
+    float sel_p = 1.0f / (float)num_bins;
+    sel.x -= (float)bin_id;
+    float contribs[RPTR_BINNED_LIGHTS_BIN_MAX_SIZE];
+    float total = 0.0f;
+    const float MIN_IRRADIANCE = 6.2e-4f * 0.001f;
+    int bin_end = std::min(bin_size * (bin_id + 1), num_lights);
+    for (int i = 0; i < RPTR_BINNED_LIGHTS_BIN_MAX_SIZE; ++i) {
+        int light_id = bin_size * bin_id + i;
+        if (!(light_id < bin_end)) break;
+        const rptr_tri_light_data &L = f.s->lights[light_id];
+        V3 a = v3(L.v0[0], L.v0[1], L.v0[2]) - hit_p, b = v3(L.v1[0], L.v1[1], L.v1[2]) - hit_p, c = v3(L.v2[0], L.v2[1], L.v2[2]) - hit_p;
+        bool front = dot(cross(a, b), c) < 0.0f; // is_tri_facing_forward, lights/tri.glsl:23-25
+        float contrib = luminance(v3(L.radiance[0], L.radiance[1], L.radiance[2]));
+        if ((dot(a, hit_n) > 0.0f || dot(b, hit_n) > 0.0f || dot(c, hit_n) > 0.0f) && front) {
+            V3 prm;
+            contrib *= triangle_solid_angle(normalize(a), normalize(b), normalize(c), prm);
+        } else
+            contrib = 0.0f;
+        contrib += MIN_IRRADIANCE;
+        contribs[i] = contrib;
+        total += contrib;
+    }
+    float p = 0.0f, t = 0.0f;
+    int light_id = 0;
+    for (int i = 0; i < RPTR_BINNED_LIGHTS_BIN_MAX_SIZE; ++i) {
+        light_id = bin_size * bin_id + i;
+        if (!(light_id < bin_end)) break;
+        p = contribs[i] / total;
+        t += p;
+        if (sel.y < t) break;
+    }
+    // note: when the loop runs off the end of the bin, the reference indexes one light past it; with the bin
+    // padded by equalize_emitter_bins this cannot go out of bounds except in the last bin -> clamp there.
+    light_id = std::min(light_id, num_lights - 1);
+    sel_p *= p;
+    const rptr_tri_light_data &L = f.s->lights[light_id];
+    V3 v0 = v3(L.v0[0], L.v0[1], L.v0[2]), v1 = v3(L.v1[0], L.v1[1], L.v1[2]), v2 = v3(L.v2[0], L.v2[1], L.v2[2]);
+    V3 d0 = normalize(v0 - hit_p), d1 = normalize(v1 - hit_p), d2 = normalize(v2 - hit_p);
+    V3 prm;
+    float omega = triangle_solid_angle(d0, d1, d2, prm);
+    light_dir = sample_solid_angle_polygon(d0, d1, d2, omega, prm, dir_sample);
+    pdf = 1.0f / omega;
+    V3 e_n = cross(v1 - v0, v2 - v0);
+    light_dist = dot(v0 - hit_p, e_n) / dot(light_dir, e_n);
+    mis_wpdf = 2.0f * light_dist * light_dist / fabsf(dot(light_dir, e_n));
+    pdf *= sel_p;
+    mis_wpdf /= (float)num_bins;
+    return v3(L.radiance[0], L.radiance[1], L.radiance[2]) / pdf;
+}
+
+static inline float geometry_scale_to_tmin(V3 orig, float scale) { return (length(orig) + scale) * 0.000005f; } // vulkan/geometry.glsl:76-78
+
+// alpha of a candidate: constants only -> 1 (textured alpha arrives with the texture path)
+static inline float material_alpha(const rptr_base_material &) { return 1.0f; }
+
+// raytrace_test_visibility: vulkan/pt_megakernel.glsl:216-272
+static bool test_visibility(const Frame &f, V3 from, V3 dir, float dist, float geometry_scale, uint32_t pixel_linear,
+                            uint32_t frame_id, Counters &cnt) {
+    float eps = geometry_scale_to_tmin(from, geometry_scale);
+    if (dist - 2.0f * eps > 0.0f) {
+        cnt.shadow_rays++;
+        const Scene &s = *f.s;
+        bool occluded = any_hit(s, from, dir, eps, dist - eps, [&](int id, float, float, float) {
+            const Tri &tr = s.tris[id];
+            const GeomInst &g = s.ginst[tr.geom_inst];
+            if (g.flags & RPTR_GEOMETRY_FLAGS_NOALPHA) return true;
+            const rptr_base_material &m = s.materials[calc_hit_material_id(g, (uint32_t)tr.prim)];
+            if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) return true;
+            Lcg arng = lcg_seed((uint32_t)tr.prim ^ frame_id, (uint32_t)g.instance ^ f.a->frame_offset, pixel_linear);
+            float alpha = material_alpha(m);
+            if (!(alpha > 0.0f) || (alpha < 1.0f && lcg_randomf(arng) > alpha)) return false;
+            return true;
+        });
+        return !occluded;
+    }
+    return true;
+}
+
+// main_spp: vulkan/pt_megakernel.glsl:310-737, shade_base_material (rendering/mc/shade_base_material.glsl:14-96),
+// sample_direct_light (rendering/mc/nee.glsl:32-90).  Returns vec4(illum, bounce == 0 ? 0 : 1).
+static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, Counters &cnt) {
+    const oracle_render_args &a = *f.a;
+    const Scene &s = *f.s;
+    const rptr_scene_params &sp = f.sp;
+    uint32_t linear = (uint32_t)px + (uint32_t)py * (uint32_t)a.width;
+    Lcg rng = lcg_seed(sample_index, a.frame_offset, linear);
+    float ptx = (float)px + 0.5f, pty = (float)py + 0.5f;
+    if (a.params.enable_raster_taa == 0) {
+        float ux = lcg_randomf(rng);
+        float uy = lcg_randomf(rng);
+        ptx += ux - 0.5f;
+        pty += uy - 0.5f;
+    }
+    ptx /= (float)a.width;
+    pty /= (float)a.height;
+    V3 ray_origin = f.cam_pos;
+    V3 ray_dir = normalize(f.du * ptx + f.dv * pty + f.tl);
+    float t_min = 0.0f, t_max = 2.e32f;
+    float total_t = 0.0f;
+    V3 illum = v3(0.0f), throughput = v3(1.0f);
+    int bounce = 0;
+    float prev_bounce_pdf = 2.e16f;
+    const float p_sun = sp.sun_radiance[3];
+    V3 sun_dir = v3(sp.sun_dir[0], sp.sun_dir[1], sp.sun_dir[2]);
+    V3 sun_rgb = v3(sp.sun_radiance[0], sp.sun_radiance[1], sp.sun_radiance[2]);
+
+    for (int v = 0; v < a.params.max_path_depth; ++v) {
+        // closest hit with front-to-back stochastic alpha (pt_megakernel.glsl:440-478,153-211)
+        Hit hit;
+        cnt.closest_rays++;
+        float after_t = t_min;
+        int after_id = 0x7fffffff;
+        bool found;
+        for (;;) {
+            found = closest_hit(s, ray_origin, ray_dir, t_min, t_max, after_t, after_id, hit);
+            if (!found) break;
+            const Tri &tr = s.tris[hit.tri];
+            const GeomInst &g = s.ginst[tr.geom_inst];
+            if (g.flags & RPTR_GEOMETRY_FLAGS_NOALPHA) break;
+            const rptr_base_material &m = s.materials[calc_hit_material_id(g, (uint32_t)tr.prim)];
+            if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) break;
+            float alpha = material_alpha(m);
+            if (!(alpha > 0.0f) || (alpha < 1.0f && lcg_randomf(rng) > alpha)) {
+                after_t = hit.t;
+                after_id = hit.tri;
+                continue;
+            }
+            break;
+        }
+        if (!found) { // :480-489
+            illum = illum + throughput * compute_sky_illum(sp, ray_dir, prev_bounce_pdf);
+            break;
+        }
+        cnt.vertices++;
+        const Tri &tr = s.tris[hit.tri];
+        const GeomInst &g = s.ginst[tr.geom_inst];
+        RTHit h = calc_hit_attributes(g, hit.t, (uint32_t)tr.prim, hit.u, hit.v);
+
+        float approx_sa = length(h.geo_normal); // :578-580
+        h.geo_normal = h.geo_normal / approx_sa;
+        approx_sa *= fabsf(dot(h.geo_normal, ray_dir)) / (h.dist * h.dist);
+        total_t += h.dist; // :585
+        float geometry_scale = total_t;
+
+        V3 w_o = -ray_dir;
+        V3 ip = ray_origin + ray_dir * h.dist; // :613
+        V3 ign = h.geo_normal, in_ = h.normal;
+        const rptr_base_material &mp = s.materials[h.material_id];
+        if (dot(w_o, ign) < 0.0f) { // :622-633
+            if (mp.flags & RPTR_BASE_MATERIAL_VOLUME) {
+                ip = ray_origin;
+                h.dist = 0.0f;
+            } else if (!(mp.flags & RPTR_BASE_MATERIAL_ONESIDED)) {
+                in_ = -in_;
+                ign = -ign;
+            }
+        }
+        // normal mapping needs textures: normal_map must be -1 on this path (checked at scene creation)
+        { // :657-668
+            float nw = dot(w_o, in_), gnw = dot(w_o, ign);
+            if (nw * gnw <= 0.0f) {
+                float blend = gnw / (gnw - nw);
+                in_ = normalize(mix(ign, in_, blend - 0.0001f));
+            }
+        }
+        V3 v_y = normalize(cross(in_, h.tangent)); // :677-678
+        V3 v_x = cross(v_y, in_);
+
+        // ---- shade_base_material ----
+        GltfMat mat;
+        V3 emit;
+        unpack_material(mat, emit, mp, f.tr);
+        if (a.params.output_channel == 0 && !is_zero(emit)) { // :33-39
+            float light_pdf = (1.0f - p_sun) * (1.0f / ((float)f.n_bins * approx_sa));
+            float w = nee_mis_heuristic(1.0f, prev_bounce_pdf, 1.0f, light_pdf);
+            illum = illum + throughput * w * emit;
+        }
+        if (a.params.output_channel != 0) { // AOV channels, :42-53; pow(0.25, bounce) is an exact power of two
+            float reliability = u2f((uint32_t)(127 - 2 * bounce) << 23);
+            if (a.params.output_channel == 1) illum = illum + throughput * mat.base_color * reliability;
+            else if (a.params.output_channel == 2) illum = illum + in_ * reliability;
+            else if (a.params.output_channel == 3) illum = illum + ip * reliability;
+        }
+        if (bounce + 1 >= a.params.max_path_depth) break; // :56-57
+        if (a.params.output_channel == 0) { // :59-65, nee.glsl:32-90
+            V2 dir_sample, sel_sample;
+            dir_sample.x = lcg_randomf(rng);
+            dir_sample.y = lcg_randomf(rng);
+            sel_sample.x = lcg_randomf(rng);
+            sel_sample.y = lcg_randomf(rng);
+            V3 li = v3(0.0f), light_dir = v3(0.0f);
+            float light_dist = 2.e16f, light_pdf = 0.0f, mis_pdf = 0.0f;
+            if (sel_sample.x <= p_sun) {
+                sel_sample.x /= p_sun;
+                // sample_sun_light: mc/lights_sun.glsl:8-17, lights/sun.glsl:9-20
+                float sn, cs;
+                sincos_pos(TWO_PI_F * dir_sample.x, sn, cs);
+                float cosT = mix(1.0f, sp.sun_cos_angle, dir_sample.y);
+                float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
+                V3 fx, fy;
+                ortho_basis(fx, fy, sun_dir);
+                light_dir = mat_mul(fx, fy, sun_dir, v3(sinT * cs, sinT * sn, cosT));
+                float pdf = 1.0f / (TWO_PI_F * (1.0f - sp.sun_cos_angle));
+                li = li + (v3(1.0f) / pdf) * (sun_rgb / p_sun);
+                light_pdf = pdf * p_sun;
+                mis_pdf = light_pdf;
+            } else {
+                sel_sample.x = (sel_sample.x - p_sun) / (1.0f - p_sun);
+                float tri_mis = 0.0f;
+                li = li + sample_tri_lights(f, ip, in_, dir_sample, sel_sample, light_dir, light_dist, light_pdf, tri_mis) / (1.0f - p_sun);
+                light_pdf *= 1.0f - p_sun;
+                mis_pdf = tri_mis * (1.0f - p_sun);
+            }
+            V3 contrib = v3(0.0f);
+            if (light_pdf > 0.0f && dot(light_dir, ign) * dot(light_dir, in_) > 0.0f) {
+                bool vis = test_visibility(f, ip, light_dir, light_dist, geometry_scale, linear, sample_index, cnt);
+                float bsdf_pdf = gltf_wpdf(mat, in_, w_o, light_dir, f.tr);
+                if (bsdf_pdf >= 0.0f && vis) {
+                    V3 bsdf = gltf_bsdf(mat, in_, w_o, light_dir, f.tr);
+                    float w = nee_mis_heuristic(1.0f, mis_pdf, 1.0f, bsdf_pdf);
+                    contrib = li * (bsdf * (w * fabsf(dot(light_dir, in_))));
+                }
+            }
+            illum = illum + throughput * contrib;
+        }
+        if (a.params.glossy_only_mode != 0 && !(mat.roughness < RPTR_GLOSSY_MODE_ROUGHNESS_THRESHOLD && mat.ior != 1.0f)) break;
+        V2 lobe, dirs;
+        lobe.x = lcg_randomf(rng);
+        lobe.y = lcg_randomf(rng);
+        dirs.x = lcg_randomf(rng);
+        dirs.y = lcg_randomf(rng);
+        V3 w_i;
+        float sampling_pdf = 0.0f, mis_wpdf = 0.0f;
+        V3 bsdf = sample_gltf_brdf(mat, in_, w_o, w_i, sampling_pdf, mis_wpdf, dirs, lobe, v_x, v_y, f.tr);
+        ++bounce;
+        if (mis_wpdf == 0.0f || is_zero(bsdf) || !(dot(w_i, in_) * dot(w_i, ign) > 0.0f)) break;
+        throughput = throughput * bsdf;
+        prev_bounce_pdf = mis_wpdf;
+        // next ray: pt_megakernel.glsl:703-709
+        ray_dir = w_i;
+        ray_origin = ip;
+        t_min = geometry_scale_to_tmin(ray_origin, total_t);
+        t_max = 1e20f;
+        // Russian roulette: :715-729
+        if (bounce >= a.params.rr_path_depth) {
+            float prefix = fmaxf(throughput.x, fmaxf(throughput.y, throughput.z));
+            float rr_prob = prefix;
+            float rr_sample = lcg_randomf(rng);
+            if (bounce > 6) rr_prob = fminf(0.95f, rr_prob);
+            else rr_prob = fminf(1.0f, rr_prob);
+            if (rr_sample < rr_prob) throughput = throughput / rr_prob;
+            else break;
+        }
+    }
+    return V4{illum.x, illum.y, illum.z, bounce == 0 ? 0.0f : 1.0f};
+}
+
+static Frame make_frame(const oracle_scene *os, const oracle_render_args *a) {
+    Frame f;
+    f.s = &os->s;
+    f.a = a;
+    f.sp = a->scene_params;
+    f.n_lights = (int)os->s.lights.size();
+    int bs = a->lighting.bin_size;
+    f.n_bins = bs > 0 ? (f.n_lights + (bs - 1)) / bs : 0;
+    // vulkan/render_sky.cpp:67-70
+    if (f.n_lights > 0) f.sp.sun_radiance[3] *= 0.5f;
+    else f.sp.sun_radiance[3] = 1.0f;
+    float vp[9];
+    oracle_view_params(&a->camera, a->width, a->height, vp);
+    f.cam_pos = v3(a->camera.pos[0], a->camera.pos[1], a->camera.pos[2]);
+    f.du = v3(vp[0], vp[1], vp[2]);
+    f.dv = v3(vp[3], vp[4], vp[5]);
+    f.tl = v3(vp[6], vp[7], vp[8]);
+    f.tr = a->transmission != 0;
+    return f;
+}
+
+} // namespace
+
+extern "C" {
+
+// Renders n_samples frames of batch_spp = 1 into rgba (W*H*4 floats, row-major, top row first), replaying
+// accumulate.glsl:68-73 + process_samples.comp:116-129: frame 0 stores x, frame k folds m += (x - m)/float(k+1).
+// If first_sample > 0 the buffer must hold the running mean of the previous frames.
+// stats (optional, 3 x uint64): closest rays, shadow rays, path vertices.
+int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rgba, uint64_t *stats) {
+    Frame f = make_frame(os, a);
+    int nt = a->n_threads;
+#ifdef _OPENMP
+    if (nt <= 0) nt = omp_get_max_threads();
+#else
+    nt = 1;
+#endif
+    uint64_t c0 = 0, c1 = 0, c2 = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(+ : c0, c1, c2)
+    for (int y = a->y0; y < a->y1; ++y) {
+        Counters cnt;
+        for (int x = a->x0; x < a->x1; ++x) {
+            float *px = rgba + 4 * ((size_t)y * a->width + x);
+            for (int k = 0; k < a->n_samples; ++k) {
+                uint32_t frame_id = a->first_sample + (uint32_t)k;
+                V4 c = main_spp(f, x, y, frame_id, cnt);
+                float xs[4] = {c.x, c.y, c.z, c.w};
+                if (frame_id > 0) {
+                    float denom = (float)(frame_id + 1u);
+                    for (int j = 0; j < 4; ++j) {
+                        float m = px[j];
+                        m += (xs[j] - m) / denom;
+                        px[j] = m;
+                    }
+                } else
+                    for (int j = 0; j < 4; ++j) px[j] = xs[j];
+            }
+        }
+        c0 += cnt.closest_rays; c1 += cnt.shadow_rays; c2 += cnt.vertices;
+    }
+    if (stats) { stats[0] = c0; stats[1] = c1; stats[2] = c2; }
+    return 0;
+}
+
+// One un-averaged sample layer (the vec4 main_spp returns) for every pixel of the region: sample_rgba is W*H*4.
+int oracle_render_sample(const oracle_scene *os, const oracle_render_args *a, uint32_t sample_index, float *sample_rgba) {
+    Frame f = make_frame(os, a);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = a->y0; y < a->y1; ++y) {
+        Counters cnt;
+        for (int x = a->x0; x < a->x1; ++x) {
+            V4 c = main_spp(f, x, y, sample_index, cnt);
+            float *px = sample_rgba + 4 * ((size_t)y * a->width + x);
+            px[0] = c.x; px[1] = c.y; px[2] = c.z; px[3] = c.w;
+        }
+    }
+    return 0;
+}
+
+// RQ_CLOSEST semantics (vulkan/rt_intersect.comp:28-68): result = (bary.x, bary.y, bits(instance+geometry), bits(prim)),
+// miss -> (0,0,bits(-1),bits(-1)); extra_t (optional) receives t.
+int oracle_trace_closest(const oracle_scene *os, const rptr_render_ray_query *q, int32_t n, float *results, float *extra_t) {
+    const Scene &s = os->s;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; ++i) {
+        Hit h;
+        V3 o = v3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), d = v3(q[i].dir[0], q[i].dir[1], q[i].dir[2]);
+        bool ok = closest_hit(s, o, d, 0.0f, q[i].t_max, 0.0f, 0x7fffffff, h);
+        int32_t gi = -1, prim = -1;
+        float u = 0.0f, v = 0.0f;
+        if (ok) { gi = s.tris[h.tri].geom_inst; prim = s.tris[h.tri].prim; u = h.u; v = h.v; }
+        results[4 * i + 0] = u;
+        results[4 * i + 1] = v;
+        std::memcpy(&results[4 * i + 2], &gi, 4);
+        std::memcpy(&results[4 * i + 3], &prim, 4);
+        if (extra_t) extra_t[i] = ok ? h.t : -1.0f;
+    }
+    return 0;
+}
+
+// Brute-force variant (no BVH): pins the BVH culling itself on small scenes.
+int oracle_trace_closest_bruteforce(const oracle_scene *os, const rptr_render_ray_query *q, int32_t n, float *results, float *extra_t) {
+    const Scene &s = os->s;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < n; ++i) {
+        V3 o = v3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), d = v3(q[i].dir[0], q[i].dir[1], q[i].dir[2]);
+        int best = -1;
+        float bt = q[i].t_max, bu = 0.0f, bv = 0.0f;
+        for (int id = 0; id < (int)s.tris.size(); ++id) {
+            float t, u, v;
+            if (!intersect_tri(s.tris[id], o, d, t, u, v)) continue;
+            if (!(t > 0.0f && t < q[i].t_max)) continue;
+            if (best < 0 || t < bt) { best = id; bt = t; bu = u; bv = v; }
+        }
+        int32_t gi = -1, prim = -1;
+        if (best >= 0) { gi = s.tris[best].geom_inst; prim = s.tris[best].prim; }
+        results[4 * i + 0] = best >= 0 ? bu : 0.0f;
+        results[4 * i + 1] = best >= 0 ? bv : 0.0f;
+        std::memcpy(&results[4 * i + 2], &gi, 4);
+        std::memcpy(&results[4 * i + 3], &prim, 4);
+        if (extra_t) extra_t[i] = best >= 0 ? bt : -1.0f;
+    }
+    return 0;
+}
+
+// ---- unit entry points used to pin the restatement against oracle/_ref and tests/golden -------------------------
+uint32_t oracle_lcg_seed(uint32_t index, uint32_t frame, uint32_t linear) { return lcg_seed(index, frame, linear).state; }
+float oracle_lcg_randomf(uint32_t *state) {
+    Lcg r{*state};
+    float f = lcg_randomf(r);
+    *state = r.state;
+    return f;
+}
+void oracle_sincos(float x, float *s, float *c) { sincos_pos(x, *s, *c); }
+float oracle_exp(float x) { return exp_f(x); }
+float oracle_acos(float x) { return acos_f(x); }
+float oracle_fast_positive_atan(float y) { return fast_positive_atan(y); }
+
+static GltfMat mat_from(const rptr_base_material *p, int tr) {
+    GltfMat m;
+    V3 e;
+    unpack_material(m, e, *p, tr != 0);
+    return m;
+}
+void oracle_gltf_bsdf(const rptr_base_material *p, const float *n, const float *wo, const float *wi, int tr, float *out) {
+    V3 r = gltf_bsdf(mat_from(p, tr), v3(n[0], n[1], n[2]), v3(wo[0], wo[1], wo[2]), v3(wi[0], wi[1], wi[2]), tr != 0);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+float oracle_gltf_wpdf(const rptr_base_material *p, const float *n, const float *wo, const float *wi, int tr) {
+    return gltf_wpdf(mat_from(p, tr), v3(n[0], n[1], n[2]), v3(wo[0], wo[1], wo[2]), v3(wi[0], wi[1], wi[2]), tr != 0);
+}
+// out = weight(3), w_i(3), pdf, mis_wpdf
+void oracle_gltf_sample(const rptr_base_material *p, const float *n, const float *wo, const float *vx, const float *vy,
+                        const float *rng_sample, const float *fresnel_sample, int tr, float *out) {
+    V3 wi;
+    float pdf = 0.0f, mis = 0.0f;
+    V3 w = sample_gltf_brdf(mat_from(p, tr), v3(n[0], n[1], n[2]), v3(wo[0], wo[1], wo[2]), wi, pdf, mis,
+                            V2{rng_sample[0], rng_sample[1]}, V2{fresnel_sample[0], fresnel_sample[1]}, v3(vx[0], vx[1], vx[2]),
+                            v3(vy[0], vy[1], vy[2]), tr != 0);
+    out[0] = w.x; out[1] = w.y; out[2] = w.z;
+    out[3] = wi.x; out[4] = wi.y; out[5] = wi.z;
+    out[6] = pdf; out[7] = mis;
+}
+void oracle_ortho_basis(const float *n, float *vx, float *vy) {
+    V3 a, b;
+    ortho_basis(a, b, v3(n[0], n[1], n[2]));
+    vx[0] = a.x; vx[1] = a.y; vx[2] = a.z;
+    vy[0] = b.x; vy[1] = b.y; vy[2] = b.z;
+}
+// out = solid angle, params(3)
+void oracle_triangle_solid_angle(const float *v0, const float *v1, const float *v2, float *out) {
+    V3 prm;
+    out[0] = triangle_solid_angle(v3(v0[0], v0[1], v0[2]), v3(v1[0], v1[1], v1[2]), v3(v2[0], v2[1], v2[2]), prm);
+    out[1] = prm.x; out[2] = prm.y; out[3] = prm.z;
+}
+void oracle_sample_solid_angle_polygon(const float *v0, const float *v1, const float *v2, const float *rnd, float *out) {
+    V3 a = v3(v0[0], v0[1], v0[2]), b = v3(v1[0], v1[1], v1[2]), c = v3(v2[0], v2[1], v2[2]);
+    V3 prm;
+    float omega = triangle_solid_angle(a, b, c, prm);
+    V3 d = sample_solid_angle_polygon(a, b, c, omega, prm, V2{rnd[0], rnd[1]});
+    out[0] = d.x; out[1] = d.y; out[2] = d.z;
+}
+// sample_tri_lights on an explicit light list; out = L(3), light_dir(3), light_dist, pdf, mis_wpdf
+void oracle_sample_tri_lights(const rptr_tri_light_data *lights, int32_t n_lights, int32_t bin_size, const float *hit_p,
+                              const float *hit_n, const float *dir_sample, const float *sel_sample, float *out) {
+    oracle_scene os;
+    os.s.lights.assign(lights, lights + n_lights);
+    oracle_render_args a;
+    std::memset(&a, 0, sizeof(a));
+    a.lighting.bin_size = bin_size;
+    Frame f;
+    f.s = &os.s;
+    f.a = &a;
+    f.n_lights = n_lights;
+    f.n_bins = (n_lights + bin_size - 1) / bin_size;
+    V3 ld;
+    float dist, pdf, mis;
+    V3 L = sample_tri_lights(f, v3(hit_p[0], hit_p[1], hit_p[2]), v3(hit_n[0], hit_n[1], hit_n[2]), V2{dir_sample[0], dir_sample[1]},
+                             V2{sel_sample[0], sel_sample[1]}, ld, dist, pdf, mis);
+    out[0] = L.x; out[1] = L.y; out[2] = L.z;
+    out[3] = ld.x; out[4] = ld.y; out[5] = ld.z;
+    out[6] = dist; out[7] = pdf; out[8] = mis;
+}
+void oracle_sky_illum(const rptr_scene_params *sp, const float *dir, float prev_pdf, float *out) {
+    V3 r = compute_sky_illum(*sp, v3(dir[0], dir[1], dir[2]), prev_pdf);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+// calc_hit_attributes for triangle `prim` of flattened geometry-instance gi; out = normal(3), dist, geo_normal(3),
+// material_id (as float), tangent(3), bitangent_l, uv(2)
+void oracle_hit_attributes(const oracle_scene *os, int32_t gi, int32_t prim, float t, float u, float v, float *out) {
+    RTHit h = calc_hit_attributes(os->s.ginst[gi], t, (uint32_t)prim, u, v);
+    out[0] = h.normal.x; out[1] = h.normal.y; out[2] = h.normal.z; out[3] = h.dist;
+    out[4] = h.geo_normal.x; out[5] = h.geo_normal.y; out[6] = h.geo_normal.z; out[7] = (float)h.material_id;
+    out[8] = h.tangent.x; out[9] = h.tangent.y; out[10] = h.tangent.z; out[11] = h.bitangent_l;
+    out[12] = h.uv.x; out[13] = h.uv.y;
+}
+void oracle_dequantize_position(uint64_t q, const float *scale, const float *offset, float *out) {
+    V3 p = dequantize_position(q, scale, offset);
+    out[0] = p.x; out[1] = p.y; out[2] = p.z;
+}
+void oracle_dequantize_normal(uint32_t w, float *out) {
+    V3 n = dequantize_normal(w);
+    out[0] = n.x; out[1] = n.y; out[2] = n.z;
+}
+void oracle_dequantize_uv(uint32_t w, float *out) {
+    V2 uv = dequantize_uv(w);
+    out[0] = uv.x; out[1] = uv.y;
+}
+// librender/lights.cpp pre-pass on an explicit emitter list; returns the binned count (out sized >= 2*n + 2*bin)
+int32_t oracle_bin_emitters(const rptr_tri_light_data *in, int32_t n, const rptr_light_sampling_config *ls, rptr_tri_light_data *out, int32_t max_out) {
+    std::vector<Emitter> em(n);
+    for (int i = 0; i < n; ++i)
+        em[i] = Emitter{v3(in[i].v0[0], in[i].v0[1], in[i].v0[2]), v3(in[i].v1[0], in[i].v1[1], in[i].v1[2]),
+                        v3(in[i].v2[0], in[i].v2[1], in[i].v2[2]), v3(in[i].radiance[0], in[i].radiance[1], in[i].radiance[2])};
+    std::vector<float> rad = estimate_normalized_radiance(em, ls->min_perceived_receiver_dist);
+    equalize_emitter_bins(em, rad, ls->bin_size);
+    if ((int)em.size() > max_out) return -(int)em.size();
+    for (size_t i = 0; i < em.size(); ++i) {
+        out[i].v0[0] = em[i].v0.x; out[i].v0[1] = em[i].v0.y; out[i].v0[2] = em[i].v0.z;
+        out[i].v1[0] = em[i].v1.x; out[i].v1[1] = em[i].v1.y; out[i].v1[2] = em[i].v1.z;
+        out[i].v2[0] = em[i].v2.x; out[i].v2[1] = em[i].v2.y; out[i].v2[2] = em[i].v2.z;
+        out[i].radiance[0] = em[i].radiance.x; out[i].radiance[1] = em[i].radiance.y; out[i].radiance[2] = em[i].radiance.z;
+    }
+    return (int32_t)em.size();
+}
+int32_t oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+} // extern "C"

@@ -1,0 +1,249 @@
+"""Procedural scenes for BASELINE.json's configs, built directly as the reference's in-memory
+scene model: quantised unrolled vertex streams per Geometry, Mesh / ParameterizedMesh / Instance tables and
+BaseMaterial blocks (librender/mesh.h:10-129, librender/scene.h:48-72).
+
+Positions are generated ON the 21-bit grid with a power-of-two quantized_scaling so that the float vertices the BVH
+sees and the ones the shader re-dequantises (rendering/rt/hit.glsl:41-46) are the same numbers (hard part 5).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import types as T
+
+_MASK21 = np.uint64(0x1FFFFF)
+
+
+def pack_qverts(grid):
+    """grid: (..., 3) integer array of 21-bit coordinates -> uint64 words (librender/quantize.h:7-11)."""
+    g = np.asarray(grid).astype(np.uint64)
+    return (g[..., 0] & _MASK21) | ((g[..., 1] & _MASK21) << np.uint64(21)) | ((g[..., 2] & _MASK21) << np.uint64(42))
+
+
+def quantize_normal(n):
+    """float normals (..., 3) -> uint32 oct encoding (librender/quantize.h:21-35), float32 arithmetic."""
+    n = np.asarray(n, dtype=np.float32)
+    nl1 = np.abs(n[..., 0]) + np.abs(n[..., 1]) + np.abs(n[..., 2])
+    pn = n[..., :2] / nl1[..., None]
+    neg = n[..., 2] <= 0
+    sx = np.where(pn[..., 0] >= 0, np.float32(1), np.float32(-1))
+    sy = np.where(pn[..., 1] >= 0, np.float32(1), np.float32(-1))
+    fx = (np.float32(1) - np.abs(pn[..., 1])) * sx
+    fy = (np.float32(1) - np.abs(pn[..., 0])) * sy
+    px = np.where(neg, fx, pn[..., 0]) * np.float32(0x8000)
+    py = np.where(neg, fy, pn[..., 1]) * np.float32(0x8000)
+    ix = np.clip(px.astype(np.int32), -0x7FFF, 0x7FFF)
+    iy = np.clip(py.astype(np.int32), -0x7FFF, 0x7FFF)
+    ux = (ix + 0x8000).astype(np.uint32)
+    uy = (iy + 0x8000).astype(np.uint32)
+    return ux | (uy << np.uint32(16))
+
+
+def quantize_uv(uv):
+    """uv (..., 2) -> uint32 (librender/quantize.h:38-42 with a zero safety offset)."""
+    uv = np.asarray(uv, dtype=np.float32)
+    s = np.float32(0xFFFF) / np.float32(8.0)
+    a = (np.float32(0) + uv[..., 0]) * s
+    b = ((np.float32(1) + np.float32(0)) - uv[..., 1]) * s
+    ux = (np.float32(0.5) + a).astype(np.int64).astype(np.uint32) & np.uint32(0xFFFF)
+    uy = (np.float32(0.5) + b).astype(np.int64).astype(np.uint32) & np.uint32(0xFFFF)
+    return ux | (uy << np.uint32(16))
+
+
+class Geometry:
+    def __init__(self, qverts, scaling, offset, qnormal_uv=None, has_normals=False, has_uvs=False):
+        self.qverts = np.ascontiguousarray(qverts, dtype=np.uint64).reshape(-1)
+        assert self.qverts.size % 3 == 0
+        self.qnormal_uv = None if qnormal_uv is None else np.ascontiguousarray(qnormal_uv, dtype=np.uint64).reshape(-1)
+        self.scaling = tuple(float(x) for x in scaling)
+        self.offset = tuple(float(x) for x in offset)
+        self.has_normals, self.has_uvs = bool(has_normals), bool(has_uvs)
+
+    @property
+    def n_tris(self):
+        return self.qverts.size // 3
+
+    def positions(self):
+        """Dequantised float32 vertices, (n_tris, 3, 3) (librender/dequantize.glsl:8-21)."""
+        q = self.qverts
+        u = np.stack([q & _MASK21, (q >> np.uint64(21)) & _MASK21, (q >> np.uint64(42)) & _MASK21], -1).astype(np.float32)
+        p = u * np.asarray(self.scaling, np.float32) + np.asarray(self.offset, np.float32)
+        return p.reshape(-1, 3, 3)
+
+
+class Scene:
+    """In-memory scene; `desc()` yields the rptr_scene_desc consumed by rptr_cuda_set_scene (and by the oracle)."""
+
+    def __init__(self):
+        self.geometries = []   # Geometry
+        self.meshes = []       # (first_geometry, n_geometries)
+        self.pmeshes = []      # dict(mesh_id, material_offsets, tri_material_ids)
+        self.instances = []    # (pmesh_id, 3x4 row-major transform)
+        self.materials = []    # T.BaseMaterial
+        self.binned_lights = None
+        self._keep = []
+
+    def add_mesh(self, geometries):
+        first = len(self.geometries)
+        self.geometries.extend(geometries)
+        self.meshes.append((first, len(geometries)))
+        return len(self.meshes) - 1
+
+    def add_pmesh(self, mesh_id, material_offsets, tri_material_ids=None):
+        tm = None if tri_material_ids is None else np.ascontiguousarray(tri_material_ids, dtype=np.uint8)
+        self.pmeshes.append(dict(mesh_id=mesh_id, material_offsets=np.ascontiguousarray(material_offsets, dtype=np.int32),
+                                 tri_material_ids=tm))
+        return len(self.pmeshes) - 1
+
+    def add_instance(self, pmesh_id, transform=None):
+        t = np.eye(4, dtype=np.float32)[:3] if transform is None else np.asarray(transform, dtype=np.float32).reshape(3, 4)
+        self.instances.append((pmesh_id, np.ascontiguousarray(t)))
+        return len(self.instances) - 1
+
+    def total_tris(self):
+        n = 0
+        for pm_id, _ in self.instances:
+            first, cnt = self.meshes[self.pmeshes[pm_id]["mesh_id"]]
+            n += sum(g.n_tris for g in self.geometries[first:first + cnt])
+        return n
+
+    def desc(self):
+        keep = []
+        geoms = (T.GeometryDesc * max(1, len(self.geometries)))()
+        for i, g in enumerate(self.geometries):
+            geoms[i].qverts = g.qverts.ctypes.data
+            geoms[i].qnormal_uv = None if g.qnormal_uv is None else g.qnormal_uv.ctypes.data
+            for k in range(3):
+                geoms[i].quantized_scaling[k] = g.scaling[k]
+                geoms[i].quantized_offset[k] = g.offset[k]
+            geoms[i].n_tris = g.n_tris
+            geoms[i].has_normals = int(g.has_normals)
+            geoms[i].has_uvs = int(g.has_uvs)
+        meshes = (T.MeshDesc * max(1, len(self.meshes)))()
+        for i, (f, n) in enumerate(self.meshes):
+            meshes[i].first_geometry, meshes[i].n_geometries = f, n
+        pms = (T.PMeshDesc * max(1, len(self.pmeshes)))()
+        for i, pm in enumerate(self.pmeshes):
+            pms[i].mesh_id = pm["mesh_id"]
+            pms[i].n_material_offsets = pm["material_offsets"].size
+            pms[i].material_offsets = pm["material_offsets"].ctypes.data
+            tm = pm["tri_material_ids"]
+            pms[i].tri_material_ids = None if tm is None else tm.ctypes.data
+            pms[i].n_tri_material_ids = 0 if tm is None else tm.size
+        insts = (T.InstanceDesc * max(1, len(self.instances)))()
+        for i, (pm, t) in enumerate(self.instances):
+            insts[i].pmesh_id = pm
+            for k, x in enumerate(t.reshape(-1)):
+                insts[i].transform[k] = float(x)
+        mats = (T.BaseMaterial * max(1, len(self.materials)))(*self.materials)
+        d = T.SceneDesc()
+        d.geometries, d.n_geometries = geoms, len(self.geometries)
+        d.meshes, d.n_meshes = meshes, len(self.meshes)
+        d.pmeshes, d.n_pmeshes = pms, len(self.pmeshes)
+        d.instances, d.n_instances = insts, len(self.instances)
+        d.materials, d.n_materials = mats, len(self.materials)
+        if self.binned_lights is not None:
+            bl = (T.TriLightData * len(self.binned_lights))(*self.binned_lights)
+            d.binned_lights, d.n_binned_lights = bl, len(self.binned_lights)
+            keep.append(bl)
+        keep += [geoms, meshes, pms, insts, mats]
+        self._keep = keep  # ctypes arrays must outlive the descriptor
+        return d
+
+
+def look_at_camera(eye, center, up=(0.0, 1.0, 0.0), fovy=65.0):
+    """RenderCameraParams{eye, normalised view direction, up, fovy} as app.cpp:357 hands it to the backend."""
+    eye = np.asarray(eye, np.float32)
+    d = np.asarray(center, np.float32) - eye
+    d = d / np.float32(np.sqrt(np.float32(np.dot(d, d))))
+    return T.RenderCameraParams(pos=tuple(eye), dir=tuple(d), up=tuple(up), fovy=fovy)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C1: Cornell-style box, 12 triangles (SURVEY 8d "C1 synthetic input")
+# ---------------------------------------------------------------------------------------------------------------
+def _quad(a, b, c, d):
+    """two triangles (a,b,c), (a,c,d)"""
+    return [a, b, c, a, c, d]
+
+
+def cornell_box():
+    s = Scene()
+    base = np.array([-1.0, 0.0, -1.0])
+    scale = 2.0 ** -20
+
+    def grid(points):
+        g = np.floor((np.asarray(points, np.float64) - base) / scale)
+        return np.clip(g, 0, 0x1FFFFF).astype(np.int64)
+
+    offset = tuple(base + 2.0 ** -21)
+    floor = _quad((-1, 0, -1), (-1, 0, 1), (1, 0, 1), (1, 0, -1))
+    ceil = _quad((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1))
+    back = _quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1))
+    left = _quad((-1, 0, -1), (-1, 2, -1), (-1, 2, 1), (-1, 0, 1))
+    right = _quad((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1))
+    # light quad just under the ceiling, wound so that cross(v1-v0, v2-v0) points down (-y): tri lights only
+    # illuminate points they face (is_tri_facing_forward, rendering/lights/tri.glsl:23-25)
+    light = _quad((-0.25, 1.998, -0.25), (0.25, 1.998, -0.25), (0.25, 1.998, 0.25), (-0.25, 1.998, 0.25))
+    groups = [floor + ceil + back, left, right, light]
+    geoms = [Geometry(pack_qverts(grid(g)), (scale,) * 3, offset) for g in groups]
+    mesh = s.add_mesh(geoms)
+    noalpha = T.BASE_MATERIAL_NOALPHA
+    lam = dict(ior=1.0, roughness=1.0, metallic=0.0, flags=noalpha)
+    s.materials = [T.BaseMaterial(base_color=(0.73, 0.73, 0.73), **lam), T.BaseMaterial(base_color=(0.63, 0.065, 0.05), **lam),
+                   T.BaseMaterial(base_color=(0.14, 0.45, 0.091), **lam),
+                   T.BaseMaterial(base_color=(1.0, 0.85, 0.6), emission_intensity=17.0, **lam)]
+    pm = s.add_pmesh(mesh, [0, 1, 2, 3])
+    s.add_instance(pm)
+    s.camera = look_at_camera((0, 1, 3.4), (0, 1, 0), fovy=40.0)
+    s.name = "cornell12"
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C2/C3/C5: N random triangles (default 1 000 000) in 16 geometries, diffuse + GGX, sun + sky only
+# ---------------------------------------------------------------------------------------------------------------
+_PALETTE = [(0.80, 0.80, 0.80), (0.90, 0.35, 0.25), (0.25, 0.65, 0.90), (0.95, 0.85, 0.35), (0.35, 0.80, 0.45), (0.75, 0.40, 0.85),
+            (0.95, 0.60, 0.20), (0.30, 0.35, 0.85), (0.60, 0.60, 0.60), (0.85, 0.25, 0.45), (0.20, 0.75, 0.75), (0.70, 0.75, 0.30),
+            (0.90, 0.90, 0.95), (0.55, 0.35, 0.25), (0.40, 0.55, 0.35), (0.50, 0.50, 0.70)]
+
+
+def splitmix64_uniform(seed, n):
+    """n doubles in [0,1): the i-th value is the splitmix64 output for state seed + (i+1)*golden, top 53 bits."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def random_triangle_grid(n_tris, seed=0x5EED1A7B200, box=10.0, edge=0.15, scale=2.0 ** -16, base=-16.0):
+    u = splitmix64_uniform(seed, n_tris * 9).reshape(n_tris, 9)
+    c = (u[:, 0:3] * 2.0 - 1.0) * box
+    e1 = (u[:, 3:6] * 2.0 - 1.0) * edge
+    e2 = (u[:, 6:9] * 2.0 - 1.0) * edge
+    v = np.stack([c, c + e1, c + e2], 1)
+    return np.clip(np.floor((v - base) / scale), 0, 0x1FFFFF).astype(np.int64)  # (n, 3, 3)
+
+
+def random_triangles(n_tris=1_000_000, n_geometries=16, seed=0x5EED1A7B200):
+    s = Scene()
+    scale, base = 2.0 ** -16, -16.0
+    g = random_triangle_grid(n_tris, seed, scale=scale, base=base)
+    per = (n_tris + n_geometries - 1) // n_geometries
+    offset = (base + 2.0 ** -17,) * 3
+    geoms = []
+    for j in range(n_geometries):
+        part = g[j * per:(j + 1) * per]
+        if len(part) == 0:
+            break
+        geoms.append(Geometry(pack_qverts(part.reshape(-1, 3)), (scale,) * 3, offset))
+    mesh = s.add_mesh(geoms)
+    s.materials = [T.BaseMaterial(base_color=_PALETTE[j % 16], roughness=0.1 + 0.05 * (j % 16), metallic=float(j & 1), ior=1.5,
+                                  specular=0.5, flags=T.BASE_MATERIAL_NOALPHA) for j in range(len(geoms))]
+    pm = s.add_pmesh(mesh, list(range(len(geoms))))
+    s.add_instance(pm)
+    s.camera = look_at_camera((0, 0, 30), (0, 0, 0), fovy=65.0)
+    s.name = "random%d" % n_tris
+    return s
