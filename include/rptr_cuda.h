@@ -1,0 +1,116 @@
+/* rptr_cuda.h -- C ABI of librptr_cuda.so, the B200 (sm_100a) wavefront path tracer that sits behind the
+ * reference's RenderBackend / RaytraceBackend plugin surface (`rptr --backend cuda`).
+ *
+ * Every entry point is what the reference-side adapter `RenderCuda : RenderBackend, RaytraceBackend`
+ * binds; the comment on each names the reference interface it replaces (paths relative to the reference tree).
+ * Conventions: plain pointers and sizes only; int return, 0 = ok, non-zero = error with a message available from
+ * rptr_cuda_last_error(); nothing throws across the boundary (the adapter turns errors into throw_error(),
+ * util/error_io.h:27-30).  All host pointers are borrowed for the duration of the call only (the reference destroys
+ * its Scene right after set_scene, app.cpp:151-175).  One context = one GPU; calls on a context must come from one
+ * thread at a time (the reference's render thread, SURVEY 8b "Threading").
+ */
+#ifndef RPTR_CUDA_H
+#define RPTR_CUDA_H
+
+#include "rptr_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rptr_ctx rptr_ctx;
+
+/* Device counters accumulated since the last rptr_cuda_reset_counters(): the inputs of the roofline formula in
+ * DESIGN.md section 7 (the reference's REPORT_RAY_STATS counters are commented out, vulkan/render_vulkan.cpp:2191-2225). */
+typedef struct rptr_counters {
+    uint64_t samples;          /* pixel samples completed */
+    uint64_t closest_rays;     /* closest-hit rays traced */
+    uint64_t shadow_rays;      /* any-hit rays traced */
+    uint64_t shaded_vertices;  /* path vertices shaded (hits) */
+    uint64_t closest_nodes;    /* BVH nodes fetched by closest-hit rays */
+    uint64_t closest_tris;     /* triangles tested by closest-hit rays */
+    uint64_t shadow_nodes;
+    uint64_t shadow_tris;
+    uint64_t launches;         /* kernels launched by this library */
+    double ms_trace;           /* device time (CUDA events) in the closest-hit stage; needs option "stage_timing" */
+    double ms_shadow;
+    double ms_shade;
+    double ms_other;           /* raygen + resolve */
+    uint64_t trace_launches;   /* number of closest-hit kernel launches timed in ms_trace */
+} rptr_counters;
+
+/* create_cuda_backend(Display&) / ~RenderBackend  (librender/render_backend.h:118-119, main.cpp:273-285).
+ * Fails (non-zero, *out = NULL) when no CUDA device is usable: there is no CPU fallback. */
+int rptr_cuda_create(int device_ordinal, rptr_ctx **out);
+void rptr_cuda_destroy(rptr_ctx *ctx);
+/* last error message of ctx (or of the failed rptr_cuda_create when ctx == NULL) */
+const char *rptr_cuda_last_error(const rptr_ctx *ctx);
+/* RenderBackend::name() (librender/render_backend.h:79) */
+const char *rptr_cuda_name(void);
+
+/* RenderBackend::initialize(fb_width, fb_height) (librender/render_backend.h:86; vulkan/render_vulkan.cpp:245-249):
+ * (re)allocates the RGBA32F accumulator, zeroes frame_id and frame_offset. */
+int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height);
+
+/* RenderBackend::set_scene(const Scene&) + RenderExtension::update_scene_from_backend of the binned-lights extension
+ * (librender/render_backend.h:92; vulkan/render_vulkan.cpp:1554-1644; vulkan/light_sampling/render_binned_lights.cpp:68-149).
+ * Copies everything to the device, builds the BVH, collects+bins emitters unless desc->binned_lights is given. */
+int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_light_sampling_config *lighting);
+/* binned TriLightData[] in NEE order (the LIGHTS_BIND_POINT buffer); returns the count, copies up to max_lights */
+int32_t rptr_cuda_get_lights(rptr_ctx *ctx, rptr_tri_light_data *out, int32_t max_lights);
+
+/* RenderBackend::update_config(SceneConfig) after the host-side sky fit (vulkan/render_vulkan.cpp:2954-2959,
+ * vulkan/render_sky.cpp:25-72).  sun_radiance[3] is 1 (sun up) or 0 as the fit leaves it; the light-count rule of
+ * render_sky.cpp:67-70 is applied by the backend. */
+int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *params);
+
+/* Backend options that are compile-time switches or host options in the reference:
+ *   "transmission"  0/1  GLTF_SUPPORT_TRANSMISSION[_ROUGHNESS] (off in the megakernel build, rendering/bsdfs/gltf_bsdf.glsl:10-13)
+ *   "wave_paths"    max paths in flight per wavefront pass (memory/occupancy knob)
+ *   "stage_timing"  0/1  time each stage with CUDA events into rptr_counters.ms_*
+ *   "tile_rank", "tile_world", "tile_rows": screen-space sharding across GPUs (interleaved bands of tile_rows rows)
+ */
+int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value);
+
+/* RenderBackend::begin_frame / draw_frame / end_frame (librender/render_backend.h:97-99;
+ * vulkan/render_vulkan.cpp:1919-2002, 2157-2178, 2017-2155).  begin_frame applies the counter protocol
+ * (reset: frame_offset += frame_id unless frozen, frame_id = 0) and update_view_parameters (:2880-2941);
+ * draw_frame renders params.batch_spp sample layers; end_frame resolves and advances frame_id. Asynchronous. */
+int rptr_cuda_begin_frame(rptr_ctx *ctx, const rptr_camera_params *camera, const rptr_render_params *params,
+                          const rptr_light_sampling_config *lighting, int32_t reset_accumulation, int32_t freeze_frame, double time);
+int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant);
+int rptr_cuda_end_frame(rptr_ctx *ctx, int32_t variant);
+
+/* RenderBackend::stats() / flush_pipeline() (librender/render_backend.h:109-110; vulkan/render_vulkan.cpp:2229-2248). Synchronise. */
+int rptr_cuda_stats(rptr_ctx *ctx, rptr_render_stats *out);
+int rptr_cuda_flush(rptr_ctx *ctx);
+int rptr_cuda_get_counters(rptr_ctx *ctx, rptr_counters *out);
+int rptr_cuda_reset_counters(rptr_ctx *ctx);
+/* frame_id / frame_offset / accumulated_spp as the reference keeps them (vulkan/render_vulkan.h:166-168) */
+int rptr_cuda_frame_state(rptr_ctx *ctx, uint32_t *frame_id, uint32_t *frame_offset, uint32_t *accumulated_spp);
+
+/* RenderGraphic::get_framebuffer_size / readback_framebuffer(float*) / (unsigned char*)
+ * (util/display/render_graphic.h:27-37; vulkan/render_vulkan.cpp:2250-2287): RGBA, row-major, top row first.
+ * Return the number of elements written (width*height*4) or 0 when the buffer is too small. */
+int rptr_cuda_framebuffer_size(rptr_ctx *ctx, uint32_t *width, uint32_t *height, uint32_t *channels);
+size_t rptr_cuda_readback_f32(rptr_ctx *ctx, size_t n_elems, float *dst);
+size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst);
+/* device address of the RGBA32F accumulator (for the multi-GPU reduce over NCCL); valid until initialize/destroy */
+int rptr_cuda_framebuffer_device_ptr(rptr_ctx *ctx, void **ptr);
+/* the cudaStream_t all work of this context is enqueued on (CommandStream of util/device_backend.h:14-22): lets a
+ * caller bracket frames with its own events or order a collective after end_frame without a host sync */
+int rptr_cuda_stream_handle(rptr_ctx *ctx, void **stream);
+
+/* RaytraceBackend::trace_ray / RQ_CLOSEST (librender/raytrace_backend.h:18; vulkan/rt_intersect.comp:28-68):
+ * results[i] = (bary.x, bary.y, bits(instance+geometry index), bits(primitive index)); miss = (0, 0, bits(-1), bits(-1)).
+ * hit_t (optional) receives the hit distance or -1.  Host buffers. */
+int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, int32_t n, float *results, float *hit_t);
+
+/* util/write_image.cpp:34-66 (WriteImage::write_pfm): "<prefix>.pfm", RGB, bottom row first, little-endian.
+ * Pure host helper so validation mode (libapp/app_state.cpp:362-388) can be replayed without the app. */
+int rptr_write_pfm(const char *prefix, uint32_t width, uint32_t height, uint32_t channels, const float *pixels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPTR_CUDA_H */

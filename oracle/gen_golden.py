@@ -1,0 +1,166 @@
+"""Generates the committed fixtures from the reference's OWN sources (through oracle/_ref/libref.so, built from
+/root/reference by oracle/Makefile).  Run in the authoring container:  python oracle/gen_golden.py
+
+  realtimepathtracingresearchframework_b200/data/sky_fits.json   update_sky_light fits for the SceneConfigs used by tests/bench
+  tests/golden/ref_vectors.npz                                   input/output vectors of the reference's shading functions
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+from realtimepathtracingresearchframework_b200 import types as T  # noqa: E402
+
+SKY_CONFIGS = [
+    dict(),                                                        # SceneConfig defaults (render_params.glsl.h:157-162)
+    dict(sun_dir=(0.35, 0.8, 0.45)),
+    dict(sun_dir=(1.0, 0.25, 0.3), turbidity=5.0, albedo=(0.3, 0.3, 0.3)),
+    dict(sun_dir=(0.0, -0.2, 1.0)),                                # sun below the horizon
+]
+
+
+def fa(*v):
+    return (C.c_float * len(v))(*v)
+
+
+def sky_key(cfg):
+    return "%.6g|%.6g,%.6g,%.6g|%.6g|%.6g,%.6g,%.6g" % (cfg.bump_scale, *cfg.sun_dir, cfg.turbidity, *cfg.albedo)
+
+
+def gen_sky():
+    table = {}
+    for kw in SKY_CONFIGS:
+        cfg = T.SceneConfig(**kw)
+        sp = po.sky_fit(cfg)
+        table[sky_key(cfg)] = dict(sky_configs=[[float(x) for x in row] for row in sp.sky_configs], sky_radiances=[float(x) for x in sp.sky_radiances],
+                                   sun_dir=[float(x) for x in sp.sun_dir], sun_cos_angle=float(sp.sun_cos_angle),
+                                   sun_radiance=[float(x) for x in sp.sun_radiance], normal_z_scale=float(sp.normal_z_scale))
+    path = os.path.join(ROOT, "realtimepathtracingresearchframework_b200", "data", "sky_fits.json")
+    with open(path, "w") as f:
+        json.dump(table, f, indent=1)
+    print("wrote", path, len(table), "fits")
+
+
+def unit(v):
+    return v / np.linalg.norm(v, axis=-1, keepdims=True)
+
+
+def gen_vectors(n=512, seed=1234):
+    R = po.ref()
+    rng = np.random.default_rng(seed)
+    out = {}
+    # --- LCG / murmur: integer exact ---
+    idx = rng.integers(0, 2 ** 32, (n, 3), dtype=np.uint64).astype(np.uint32)
+    seeds = np.array([R.ref_lcg_seed(int(a), int(b), int(c)) for a, b, c in idx], np.uint32)
+    draws = np.zeros((n, 4), np.float32)
+    states = np.zeros((n, 4), np.uint32)
+    for i in range(n):
+        st = C.c_uint32(int(seeds[i]))
+        for k in range(4):
+            draws[i, k] = R.ref_lcg_randomf(C.byref(st))
+            states[i, k] = st.value
+    out.update(lcg_in=idx, lcg_seed=seeds, lcg_draws=draws, lcg_states=states)
+    # --- glTF BSDF ---
+    mats = np.zeros((n, 20), np.float32)  # BaseMaterial as 20 words
+    mviews = mats.view(np.uint32)
+    nrm = unit(rng.normal(size=(n, 3))).astype(np.float32)
+    wo = unit(nrm + 0.9 * unit(rng.normal(size=(n, 3)))).astype(np.float32)
+    wi = unit(nrm + 0.9 * unit(rng.normal(size=(n, 3)))).astype(np.float32)
+    flip = rng.random(n) < 0.25
+    wi[flip] = (wi[flip] - 2 * nrm[flip] * np.sum(wi[flip] * nrm[flip], -1, keepdims=True)).astype(np.float32)
+    u4 = rng.random((n, 4)).astype(np.float32)
+    res = {k: [] for k in ("bsdf", "wpdf", "sample", "bsdf_tr", "wpdf_tr", "sample_tr", "vx", "vy")}
+    for i in range(n):
+        m = T.BaseMaterial(base_color=tuple(rng.random(3)), roughness=float(rng.random()), metallic=float(rng.random() < 0.3) * float(rng.random()),
+                           ior=float(1.0 if rng.random() < 0.15 else 1.05 + rng.random()), specular=0.5,
+                           specular_transmission=float(rng.random() < 0.5) * float(rng.random()), clearcoat_gloss=float(rng.random()),
+                           flags=int(rng.integers(0, 4)))
+        mats[i] = np.frombuffer(bytes(m), np.float32)
+        vx, vy = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        R.ref_ortho_basis(fa(*nrm[i]), vx.ctypes.data_as(po.f32p), vy.ctypes.data_as(po.f32p))
+        res["vx"].append(vx), res["vy"].append(vy)
+        for tr, suf in ((0, ""), (1, "_tr")):
+            o3 = np.zeros(3, np.float32)
+            R.ref_gltf_bsdf(C.byref(m), fa(*nrm[i]), fa(*wo[i]), fa(*wi[i]), tr, o3.ctypes.data_as(po.f32p))
+            res["bsdf" + suf].append(o3)
+            res["wpdf" + suf].append(R.ref_gltf_wpdf(C.byref(m), fa(*nrm[i]), fa(*wo[i]), fa(*wi[i]), tr))
+            o8 = np.zeros(8, np.float32)
+            R.ref_gltf_sample(C.byref(m), fa(*nrm[i]), fa(*wo[i]), fa(*vx), fa(*vy), fa(*u4[i, :2]), fa(*u4[i, 2:]), tr, o8.ctypes.data_as(po.f32p))
+            res["sample" + suf].append(o8)
+    out.update(mat=mviews.copy(), n=nrm, wo=wo, wi=wi, u4=u4, **{"gltf_" + k: np.array(v, np.float32) for k, v in res.items()})
+    # --- triangle lights ---
+    tri = (rng.normal(size=(n, 3, 3)) + rng.normal(size=(n, 1, 3)) * 2).astype(np.float32)
+    d = unit(tri).astype(np.float32)
+    sa = np.zeros((n, 4), np.float32)
+    smp = np.zeros((n, 3), np.float32)
+    u2 = rng.random((n, 2)).astype(np.float32)
+    for i in range(n):
+        R.ref_triangle_solid_angle(fa(*d[i, 0]), fa(*d[i, 1]), fa(*d[i, 2]), sa[i].ctypes.data_as(po.f32p))
+        R.ref_sample_solid_angle_polygon(fa(*d[i, 0]), fa(*d[i, 1]), fa(*d[i, 2]), fa(*u2[i]), smp[i].ctypes.data_as(po.f32p))
+    atan_in = np.concatenate([rng.normal(size=n // 2) * 3, rng.random(n // 2) * 40]).astype(np.float32)
+    atan_out = np.array([R.ref_fast_positive_atan(float(x)) for x in atan_in], np.float32)
+    out.update(tri_dirs=d, tri_solid_angle=sa, tri_sample=smp, tri_u2=u2, atan_in=atan_in, atan_out=atan_out)
+    # binned RIS light selection
+    n_l = 40
+    lights = np.zeros((n_l, 12), np.float32)
+    c = rng.normal(size=(n_l, 1, 3)) * 3 + np.array([0, 4, 0])
+    lights[:, :9] = (c + rng.normal(size=(n_l, 3, 3)) * 0.5).reshape(n_l, 9)
+    lights[:, 9:] = rng.random((n_l, 3)) * 10
+    larr = (T.TriLightData * n_l).from_buffer_copy(lights.tobytes())
+    hp = (rng.normal(size=(n, 3)) * 2).astype(np.float32)
+    hn = unit(rng.normal(size=(n, 3))).astype(np.float32)
+    ris = np.zeros((n, 9), np.float32)
+    for i in range(n):
+        R.ref_sample_tri_lights(larr, n_l, 16, fa(*hp[i]), fa(*hn[i]), fa(*u4[i, :2]), fa(*u4[i, 2:]), ris[i].ctypes.data_as(po.f32p))
+    out.update(ris_lights=lights, ris_p=hp, ris_n=hn, ris_out=ris)
+    # --- quantisation + hit attributes ---
+    qv = rng.integers(0, 2 ** 63, (n, 3), dtype=np.uint64)
+    qn = rng.integers(0, 2 ** 63, (n, 3), dtype=np.uint64)
+    scale = np.array([2.0 ** -16, 2.0 ** -15, 3e-5], np.float32)
+    offs = np.array([-16.0, 1.5, 0.25], np.float32)
+    deq = np.zeros((n, 3, 3), np.float32)
+    dn = np.zeros((n, 3, 3), np.float32)
+    duv = np.zeros((n, 3, 2), np.float32)
+    hit = np.zeros((n, 2, 14), np.float32)
+    w2o = np.array([0.5, 0.1, 0, -0.1, 0.6, 0.2, 0.05, -0.2, 0.7], np.float32)
+    bary = rng.random((n, 2)).astype(np.float32) * 0.5
+    id4 = rng.integers(0, 2 ** 32, 4, dtype=np.uint64).astype(np.uint32)
+    for i in range(n):
+        for k in range(3):
+            R.ref_dequantize_position(C.c_uint64(int(qv[i, k])), fa(*scale), fa(*offs), deq[i, k].ctypes.data_as(po.f32p))
+            R.ref_dequantize_normal(C.c_uint32(int(qn[i, k] & 0xFFFFFFFF)), dn[i, k].ctypes.data_as(po.f32p))
+            R.ref_dequantize_uv(C.c_uint32(int(qn[i, k] >> 32)), duv[i, k].ctypes.data_as(po.f32p))
+        qva = (C.c_uint64 * 3)(*[int(x) for x in qv[i]])
+        qna = (C.c_uint64 * 3)(*[int(x) for x in qn[i]])
+        for j, (hn_, hu_, mid) in enumerate(((0, 0, 3), (1, 1, -2))):
+            R.ref_hit_attributes(qva, qna, fa(*scale), fa(*offs), hn_, hu_, fa(*w2o), mid, id4.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(i % 16),
+                                 C.c_float(1.5), C.c_float(float(bary[i, 0])), C.c_float(float(bary[i, 1])), hit[i, j].ctypes.data_as(po.f32p))
+    out.update(q_verts=qv, q_nuv=qn, q_scale=scale, q_offset=offs, deq_pos=deq, deq_normal=dn, deq_uv=duv, hit_w2o=w2o, hit_bary=bary,
+               hit_id4=id4, hit_out=hit)
+    # --- host light binning ---
+    for tag, cnt in (("small", 2), ("mid", 37), ("big", 300)):
+        em = np.zeros((cnt, 12), np.float32)
+        cc = rng.normal(size=(cnt, 1, 3)) * 4
+        em[:, :9] = (cc + rng.normal(size=(cnt, 3, 3)) * rng.random((cnt, 1, 1)) * 1.5).reshape(cnt, 9)
+        em[:, 9:] = rng.random((cnt, 3)) * (10.0 ** rng.uniform(-1, 2, (cnt, 1)))
+        ls = T.LightSamplingConfig()
+        outl = (T.TriLightData * (2 * cnt + 64))()
+        m = R.ref_bin_emitters((T.TriLightData * cnt).from_buffer_copy(em.tobytes()), cnt, C.byref(ls), outl, 2 * cnt + 64)
+        assert m > 0
+        out["bin_%s_in" % tag] = em
+        out["bin_%s_out" % tag] = np.frombuffer(outl, np.float32).reshape(-1, 12)[:m].copy()
+    path = os.path.join(ROOT, "tests", "golden", "ref_vectors.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    if po.ref() is None:
+        sys.exit("oracle/_ref/libref.so missing: run `make -C oracle` in a container that has /root/reference")
+    gen_sky()
+    gen_vectors()

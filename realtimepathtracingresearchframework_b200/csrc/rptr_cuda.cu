@@ -1,0 +1,860 @@
+// rptr_cuda.cu -- librptr_cuda.so: the wavefront path tracer and its C ABI (include/rptr_cuda.h).
+//
+// One frame = for each wave of sample layers:  raygen -> [ trace -> shade -> shadow ] x max_path_depth -> resolve.
+// Path state lives in HBM as 16-byte SoA records indexed by path slot (slot = layer * local_pixels + local_pixel, so
+// neighbouring threads hold neighbouring pixels); queues of live path slots and of shadow rays are compacted with
+// warp-aggregated atomics; every kernel is a persistent grid (a multiple of the SM count) that strides over a
+// device-resident count, so a whole frame is enqueued without a host round trip.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (RPTR-FP contract, see rptr_math.cuh).
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rptr_cuda.h"
+#include "rptr_host.hpp"
+
+using namespace rp;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// device-side buffers
+// ---------------------------------------------------------------------------------------------------------------------
+struct Wave {
+    float4 *ray_o;  // origin.xyz, tmin
+    float4 *ray_d;  // dir.xyz, tmax
+    float4 *hit;    // t, u, v, bits(leaf triangle index | -1)
+    float4 *thr;    // throughput.rgb, prev_bounce_pdf
+    float4 *illum;  // illum.rgb, total_t
+    uint2 *rngb;    // lcg state, bounce
+    float4 *sh_o;   // shadow queue: origin.xyz, tmin
+    float4 *sh_d;   //               dir.xyz, tmax
+    float4 *sh_c;   //               contribution.rgb, bits(path slot)
+    uint32_t *queue[2];
+    uint32_t *counts; // [2*d] = live paths entering bounce d, [2*d+1] = shadow rays of bounce d
+};
+
+struct TileMap {
+    int32_t width, height;
+    int32_t rank, world, rows; // interleaved bands of `rows` rows: band b belongs to rank b % world
+    int32_t local_rows;
+    int32_t local_pixels;
+};
+
+__host__ __device__ inline int32_t local_row_to_global(const TileMap &t, int32_t lr) {
+    int32_t band = lr / t.rows;
+    return (band * t.world + t.rank) * t.rows + lr % t.rows;
+}
+
+struct DevCounters {
+    unsigned long long closest_rays, shadow_rays, shaded_vertices, closest_nodes, closest_tris, shadow_nodes, shadow_tris, samples;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
+    // warp-aggregated atomic: one atomicAdd per warp, returns this lane's slot (valid when pred)
+    const unsigned mask = __ballot_sync(__activemask(), pred);
+    if (!pred) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1));
+}
+
+__device__ __forceinline__ void flush_counter(unsigned long long *dst, unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
+}
+
+// raygen (vulkan/pt_megakernel.glsl:310-365): one thread per path slot of the wave
+__global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave w, int32_t first_layer, int32_t n_layers) {
+    const uint32_t n = (uint32_t)n_layers * (uint32_t)tm.local_pixels;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        const int32_t layer = (int32_t)(slot / (uint32_t)tm.local_pixels);
+        const int32_t lp = (int32_t)(slot % (uint32_t)tm.local_pixels);
+        const int32_t px = lp % tm.width;
+        const int32_t py = local_row_to_global(tm, lp / tm.width);
+        PathState ps;
+        generate_primary(fp, px, py, fp.first_sample + (uint32_t)(first_layer + layer), ps);
+        w.ray_o[slot] = f4(ps.o.x, ps.o.y, ps.o.z, ps.tmin);
+        w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
+        w.thr[slot] = f4(1.0f, 1.0f, 1.0f, ps.prev_pdf);
+        w.illum[slot] = f4(0.0f, 0.0f, 0.0f, 0.0f);
+        w.rngb[slot] = make_uint2(ps.rng, 0u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[0] = n;
+}
+
+// closest hit for the live paths of bounce d
+__global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_t *queue, const uint32_t *count, DevCounters *dc) {
+    const uint32_t n = *count;
+    TraceCounters cnt{0, 0};
+    unsigned long long rays = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = queue ? queue[i] : i;
+        const float4 o = w.ray_o[slot], d = w.ray_d[slot];
+        HitRec h;
+        trace_ray<false>(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h, cnt);
+        w.hit[slot] = f4(h.t, h.u, h.v, __int_as_float(h.tri));
+        rays++;
+    }
+    flush_counter(&dc->closest_rays, rays);
+    flush_counter(&dc->closest_nodes, cnt.nodes);
+    flush_counter(&dc->closest_tris, cnt.tris);
+}
+
+// shade the vertices found by k_trace; emits shadow rays and the next bounce's queue
+__global__ void __launch_bounds__(128) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
+                                               const uint32_t *count, uint32_t *next_queue, uint32_t *next_count,
+                                               uint32_t *shadow_count, DevCounters *dc) {
+    const uint32_t n = *count;
+    unsigned long long verts = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // all lanes of a warp iterate together so that the ballots in warp_append see a converged warp
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t i = base + (threadIdx.x & 31);
+        const bool active = i < n;
+        bool cont = false, shadow = false;
+        uint32_t slot = 0;
+        ShadowRay sh;
+        sh.tmax = -1.0f;
+        if (active) {
+            slot = queue ? queue[i] : i;
+            const float4 o = w.ray_o[slot], d = w.ray_d[slot], hit = w.hit[slot], thr = w.thr[slot], il = w.illum[slot];
+            const uint2 rb = w.rngb[slot];
+            PathState ps;
+            ps.o = f3(o.x, o.y, o.z); ps.tmin = o.w;
+            ps.d = f3(d.x, d.y, d.z); ps.tmax = d.w;
+            ps.thr = f3(thr.x, thr.y, thr.z); ps.prev_pdf = thr.w;
+            ps.illum = f3(il.x, il.y, il.z); ps.total_t = il.w;
+            ps.rng = rb.x; ps.bounce = (int)rb.y;
+            const int tri = __float_as_int(hit.w);
+            if (tri >= 0) verts++;
+            ShadeResult r = shade_vertex(fp, sc, ps, hit.x, hit.y, hit.z, tri >= 0 ? &bvh.tris[tri] : nullptr, sh);
+            cont = r == SHADE_CONTINUE;
+            shadow = sh.tmax > 0.0f;
+            w.illum[slot] = f4(ps.illum.x, ps.illum.y, ps.illum.z, ps.total_t);
+            w.rngb[slot] = make_uint2(ps.rng, (uint32_t)ps.bounce);
+            if (cont) {
+                w.ray_o[slot] = f4(ps.o.x, ps.o.y, ps.o.z, ps.tmin);
+                w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
+                w.thr[slot] = f4(ps.thr.x, ps.thr.y, ps.thr.z, ps.prev_pdf);
+            }
+        }
+        __syncwarp();
+        const uint32_t qi = warp_append(next_count, cont);
+        if (cont) next_queue[qi] = slot;
+        const uint32_t si = warp_append(shadow_count, shadow);
+        if (shadow) {
+            w.sh_o[si] = f4(sh.o.x, sh.o.y, sh.o.z, sh.tmin);
+            w.sh_d[si] = f4(sh.d.x, sh.d.y, sh.d.z, sh.tmax);
+            w.sh_c[si] = f4(sh.contrib.x, sh.contrib.y, sh.contrib.z, __uint_as_float(slot));
+        }
+    }
+    flush_counter(&dc->shaded_vertices, verts);
+}
+
+// any-hit visibility for the NEE samples of bounce d (vulkan/pt_megakernel.glsl:216-272); unoccluded -> illum += contrib
+__global__ void __launch_bounds__(128) k_shadow(BvhDev bvh, Wave w, const uint32_t *count, DevCounters *dc) {
+    const uint32_t n = *count;
+    TraceCounters cnt{0, 0};
+    unsigned long long rays = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o = w.sh_o[i], d = w.sh_d[i];
+        HitRec h;
+        const bool occluded = trace_ray<true>(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h, cnt);
+        rays++;
+        if (!occluded) {
+            const float4 c = w.sh_c[i];
+            const uint32_t slot = __float_as_uint(c.w);
+            float4 il = w.illum[slot];
+            il.x = il.x + c.x; il.y = il.y + c.y; il.z = il.z + c.z;
+            w.illum[slot] = il;
+        }
+    }
+    flush_counter(&dc->shadow_rays, rays);
+    flush_counter(&dc->shadow_nodes, cnt.nodes);
+    flush_counter(&dc->shadow_tris, cnt.tris);
+}
+
+// accumulate.glsl:68-73 + process_samples.comp:116-129 replayed in sample order for the layers of this wave:
+// sample k (0-based since the last reset) is stored when k == 0 and folded as m += (x - m) / float(k + 1) otherwise.
+__global__ void __launch_bounds__(256) k_resolve(TileMap tm, Wave w, float4 *accum, uint32_t first_sample, int32_t n_layers, DevCounters *dc) {
+    unsigned long long samples = 0;
+    for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < (uint32_t)tm.local_pixels; lp += gridDim.x * blockDim.x) {
+        const int32_t px = (int32_t)(lp % (uint32_t)tm.width);
+        const int32_t py = local_row_to_global(tm, (int32_t)(lp / (uint32_t)tm.width));
+        float4 *dst = accum + (size_t)py * tm.width + px;
+        float4 m = *dst;
+        for (int32_t l = 0; l < n_layers; ++l) {
+            const uint32_t slot = (uint32_t)l * (uint32_t)tm.local_pixels + lp;
+            const float4 il = w.illum[slot];
+            const float alpha = w.rngb[slot].y == 0u ? 0.0f : 1.0f;
+            const uint32_t k = first_sample + (uint32_t)l;
+            if (k > 0) {
+                const float denom = (float)(k + 1u);
+                m.x += (il.x - m.x) / denom;
+                m.y += (il.y - m.y) / denom;
+                m.z += (il.z - m.z) / denom;
+                m.w += (alpha - m.w) / denom;
+            } else
+                m = f4(il.x, il.y, il.z, alpha);
+            samples++;
+        }
+        *dst = m;
+    }
+    flush_counter(&dc->samples, samples);
+}
+
+// RQ_CLOSEST (vulkan/rt_intersect.comp:28-68)
+__global__ void __launch_bounds__(128) k_ray_queries(BvhDev bvh, const rptr_render_ray_query *q, int32_t n, float4 *results, float *hit_t) {
+    TraceCounters cnt{0, 0};
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        HitRec h;
+        const bool ok = trace_ray<false>(bvh, f3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), f3(q[i].dir[0], q[i].dir[1], q[i].dir[2]), 0.0f, q[i].t_max, h, cnt);
+        int32_t gi = -1, prim = -1;
+        if (ok) { gi = bvh.tris[h.tri].geom_inst; prim = bvh.tris[h.tri].prim; }
+        results[i] = f4(ok ? h.u : 0.0f, ok ? h.v : 0.0f, __int_as_float(gi), __int_as_float(prim));
+        if (hit_t) hit_t[i] = ok ? h.t : -1.0f;
+    }
+}
+
+// display path only (process_samples.comp:138-200 without tonemapping operators): exposure + sRGB, not part of .pfm parity
+__global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, uchar4 *out, uint32_t n, float exposure_scale) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 c = accum[i];
+        float v[3] = {c.x * exposure_scale, c.y * exposure_scale, c.z * exposure_scale};
+        unsigned char o[3];
+        for (int k = 0; k < 3; ++k) {
+            float x = v[k];
+            float s = (x <= 0.0031308f) ? 12.92f * x : 1.055f * powf(fmaxf(fabsf(x), 1.192092896e-07f), 1.0f / 2.4f) - 0.055f;
+            o[k] = (unsigned char)(fminf(fmaxf(s, 0.0f), 1.0f) * 255.0f + 0.5f);
+        }
+        out[i] = make_uchar4(o[0], o[1], o[2], (unsigned char)(fminf(fmaxf(c.w, 0.0f), 1.0f) * 255.0f + 0.5f));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+struct rptr_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    // framebuffer
+    int32_t width = 0, height = 0;
+    float4 *accum = nullptr;
+    uchar4 *ldr = nullptr;
+    // counters protocol (vulkan/render_vulkan.h:166-168)
+    uint32_t frame_id = 0, frame_offset = 0, accumulated_spp = 0;
+    bool freeze_frame = false;
+    // scene
+    bool has_scene = false;
+    std::vector<void *> scene_allocs;
+    SceneDev scene{};
+    BvhDev bvh{};
+    int32_t n_lights = 0;
+    std::vector<rptr_tri_light_data> lights_host;
+    rptr_scene_params scene_params{};
+    bool has_scene_params = false;
+    // frame
+    rptr_camera_params camera{};
+    rptr_render_params params{};
+    rptr_light_sampling_config lighting{};
+    bool in_frame = false;
+    // options
+    int transmission = 0;
+    int64_t wave_paths = 8ll << 20;
+    int stage_timing = 0;
+    int tile_rank = 0, tile_world = 1, tile_rows = 8;
+    // wave
+    Wave wave{};
+    size_t wave_capacity = 0;
+    int wave_depth = 0;
+    std::vector<void *> wave_allocs;
+    DevCounters *dcounters = nullptr;
+    // stats
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bool frame_timed = false;
+    float last_render_ms = 0.0f;
+    uint64_t launches = 0, trace_launches = 0;
+    double ms_trace = 0, ms_shadow = 0, ms_shade = 0, ms_other = 0;
+    struct Timed { cudaEvent_t a, b; int stage; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> event_pool;
+    size_t bytes_now = 0, bytes_max = 0, bytes_total = 0;
+};
+
+static int fail(rptr_ctx *ctx, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    else g_create_error = buf;
+    return 1;
+}
+
+#define CU(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T> static cudaError_t dev_alloc(rptr_ctx *ctx, T **p, size_t n, std::vector<void *> &owner) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess) {
+        owner.push_back(*p);
+        ctx->bytes_now += n * sizeof(T);
+        ctx->bytes_total += n * sizeof(T);
+        if (ctx->bytes_now > ctx->bytes_max) ctx->bytes_max = ctx->bytes_now;
+    }
+    return e;
+}
+static void free_all(rptr_ctx *ctx, std::vector<void *> &owner) {
+    for (void *p : owner) cudaFree(p);
+    owner.clear();
+    (void)ctx;
+}
+
+static TileMap make_tilemap(const rptr_ctx *ctx) {
+    TileMap t;
+    t.width = ctx->width; t.height = ctx->height;
+    t.rank = ctx->tile_rank; t.world = ctx->tile_world; t.rows = ctx->tile_rows;
+    int32_t rows = 0;
+    for (int32_t y = 0; y < ctx->height; ++y)
+        if ((y / t.rows) % t.world == t.rank) rows++;
+    t.local_rows = rows;
+    t.local_pixels = rows * ctx->width;
+    return t;
+}
+
+static int grid_for(const rptr_ctx *ctx, int blocks_per_sm) { return ctx->num_sms * blocks_per_sm; }
+
+static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
+    if (paths <= ctx->wave_capacity && depth <= ctx->wave_depth) return 0;
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (void *p : ctx->wave_allocs) cudaFree(p);
+    ctx->wave_allocs.clear();
+    Wave &w = ctx->wave;
+    const size_t n = paths;
+    CU(dev_alloc(ctx, &w.ray_o, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.ray_d, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.hit, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.thr, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.illum, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.rngb, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.sh_o, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.sh_d, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.sh_c, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.queue[0], n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.queue[1], n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.counts, (size_t)2 * (depth + 2), ctx->wave_allocs));
+    ctx->wave_capacity = paths;
+    ctx->wave_depth = depth;
+    return 0;
+}
+
+static cudaEvent_t get_event(rptr_ctx *ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct StageTimer {
+    rptr_ctx *ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int stage;
+    StageTimer(rptr_ctx *c, int s) : ctx(c), stage(s) {
+        if (ctx->stage_timing) {
+            a = get_event(ctx);
+            b = get_event(ctx);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~StageTimer() {
+        if (a) {
+            cudaEventRecord(b, ctx->stream);
+            ctx->timed.push_back({a, b, stage});
+        }
+    }
+};
+static void collect_timers(rptr_ctx *ctx) {
+    for (auto &t : ctx->timed) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            if (t.stage == 0) { ctx->ms_trace += ms; ctx->trace_launches++; }
+            else if (t.stage == 1) ctx->ms_shade += ms;
+            else if (t.stage == 2) ctx->ms_shadow += ms;
+            else ctx->ms_other += ms;
+        }
+        ctx->event_pool.push_back(t.a);
+        ctx->event_pool.push_back(t.b);
+    }
+    ctx->timed.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *rptr_cuda_name(void) { return "CUDA wavefront path tracer (sm_100a)"; }
+
+int rptr_cuda_create(int device_ordinal, rptr_ctx **out) {
+    rptr_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, "rptr_cuda_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, "no usable CUDA device (%s); this backend has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(nullptr, "device ordinal %d out of range (%d devices)", device_ordinal, n);
+    e = cudaSetDevice(device_ordinal);
+    if (e != cudaSuccess) return fail(nullptr, "cudaSetDevice(%d): %s", device_ordinal, cudaGetErrorString(e));
+    ctx = new rptr_ctx();
+    ctx->device = device_ordinal;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device_ordinal);
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev_begin) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_end) != cudaSuccess || cudaMalloc((void **)&ctx->dcounters, sizeof(DevCounters)) != cudaSuccess) {
+        fail(nullptr, "CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return 1;
+    }
+    cudaMemset(ctx->dcounters, 0, sizeof(DevCounters));
+    *out = ctx;
+    return 0;
+}
+
+void rptr_cuda_destroy(rptr_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    collect_timers(ctx);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    free_all(ctx, ctx->scene_allocs);
+    free_all(ctx, ctx->wave_allocs);
+    cudaFree(ctx->accum);
+    cudaFree(ctx->ldr);
+    cudaFree(ctx->dcounters);
+    cudaEventDestroy(ctx->ev_begin);
+    cudaEventDestroy(ctx->ev_end);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *rptr_cuda_last_error(const rptr_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height) {
+    if (!ctx) return 1;
+    if (width <= 0 || height <= 0 || (int64_t)width * height > (1ll << 28)) return fail(ctx, "invalid framebuffer size %dx%d", width, height);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->accum);
+    cudaFree(ctx->ldr);
+    ctx->accum = nullptr;
+    ctx->ldr = nullptr;
+    ctx->width = width;
+    ctx->height = height;
+    const size_t n = (size_t)width * height;
+    CU(cudaMalloc((void **)&ctx->accum, n * sizeof(float4)));
+    CU(cudaMalloc((void **)&ctx->ldr, n * sizeof(uchar4)));
+    CU(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
+    ctx->frame_id = 0; // vulkan/render_vulkan.cpp:245-249
+    ctx->frame_offset = 0;
+    ctx->accumulated_spp = 0;
+    ctx->in_frame = false;
+    return 0;
+}
+
+int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_light_sampling_config *lighting) {
+    if (!ctx) return 1;
+    if (!desc) return fail(ctx, "set_scene: desc is NULL");
+    CU(cudaSetDevice(ctx->device));
+    rptr_light_sampling_config ls;
+    if (lighting) ls = *lighting;
+    else { ls.light_mis_angle = 0.0f; ls.bin_size = 16; ls.min_perceived_receiver_dist = 15.0f; ls.min_radiance = 0.0f; }
+    HostScene hs;
+    try {
+        build_host_scene(*desc, ls, hs);
+    } catch (const std::exception &e) {
+        return fail(ctx, "set_scene: %s", e.what());
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_all(ctx, ctx->scene_allocs);
+    ctx->has_scene = false;
+    std::vector<uint64_t *> d_qv(hs.qverts.size(), nullptr), d_qn(hs.qnuv.size(), nullptr);
+    std::vector<uint8_t *> d_tm(hs.tri_mat.size(), nullptr);
+    for (size_t g = 0; g < hs.qverts.size(); ++g) {
+        CU(dev_alloc(ctx, &d_qv[g], hs.qverts[g].size(), ctx->scene_allocs));
+        CU(cudaMemcpy(d_qv[g], hs.qverts[g].data(), hs.qverts[g].size() * 8, cudaMemcpyHostToDevice));
+        if (!hs.qnuv[g].empty()) {
+            CU(dev_alloc(ctx, &d_qn[g], hs.qnuv[g].size(), ctx->scene_allocs));
+            CU(cudaMemcpy(d_qn[g], hs.qnuv[g].data(), hs.qnuv[g].size() * 8, cudaMemcpyHostToDevice));
+        }
+    }
+    for (size_t p = 0; p < hs.tri_mat.size(); ++p)
+        if (!hs.tri_mat[p].empty()) {
+            CU(dev_alloc(ctx, &d_tm[p], hs.tri_mat[p].size(), ctx->scene_allocs));
+            CU(cudaMemcpy(d_tm[p], hs.tri_mat[p].data(), hs.tri_mat[p].size(), cudaMemcpyHostToDevice));
+        }
+    std::vector<GeomInst> gi(hs.ginst.size());
+    for (size_t i = 0; i < hs.ginst.size(); ++i) {
+        gi[i] = hs.ginst[i].g;
+        gi[i].qverts = d_qv[hs.ginst[i].geometry];
+        gi[i].qnuv = d_qn[hs.ginst[i].geometry];
+        gi[i].tri_mat = d_tm[hs.ginst[i].pmesh] ? d_tm[hs.ginst[i].pmesh] + hs.ginst[i].prim_offset : nullptr;
+    }
+    GeomInst *d_gi;
+    rptr_base_material *d_mat;
+    rptr_tri_light_data *d_lights;
+    BvhNode *d_nodes;
+    Tri *d_tris;
+    CU(dev_alloc(ctx, &d_gi, gi.size(), ctx->scene_allocs));
+    CU(cudaMemcpy(d_gi, gi.data(), gi.size() * sizeof(GeomInst), cudaMemcpyHostToDevice));
+    CU(dev_alloc(ctx, &d_mat, hs.materials.size(), ctx->scene_allocs));
+    CU(cudaMemcpy(d_mat, hs.materials.data(), hs.materials.size() * sizeof(rptr_base_material), cudaMemcpyHostToDevice));
+    CU(dev_alloc(ctx, &d_lights, hs.lights.size(), ctx->scene_allocs));
+    if (!hs.lights.empty()) CU(cudaMemcpy(d_lights, hs.lights.data(), hs.lights.size() * sizeof(rptr_tri_light_data), cudaMemcpyHostToDevice));
+    CU(dev_alloc(ctx, &d_nodes, hs.nodes.size(), ctx->scene_allocs));
+    if (!hs.nodes.empty()) CU(cudaMemcpy(d_nodes, hs.nodes.data(), hs.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+    CU(dev_alloc(ctx, &d_tris, hs.leaf_tris.size(), ctx->scene_allocs));
+    if (!hs.leaf_tris.empty()) CU(cudaMemcpy(d_tris, hs.leaf_tris.data(), hs.leaf_tris.size() * sizeof(Tri), cudaMemcpyHostToDevice));
+    ctx->scene = SceneDev{d_gi, d_mat, d_lights};
+    ctx->bvh = BvhDev{d_nodes, d_tris, (int32_t)hs.nodes.size(), (int32_t)hs.leaf_tris.size()};
+    ctx->n_lights = (int32_t)hs.lights.size();
+    ctx->lights_host = hs.lights;
+    ctx->has_scene = true;
+    ctx->frame_id = 0; // vulkan/render_vulkan.cpp:1556
+    return 0;
+}
+
+int32_t rptr_cuda_get_lights(rptr_ctx *ctx, rptr_tri_light_data *out, int32_t max_lights) {
+    if (!ctx) return -1;
+    const int32_t n = (int32_t)ctx->lights_host.size();
+    if (out) memcpy(out, ctx->lights_host.data(), sizeof(rptr_tri_light_data) * (size_t)(n < max_lights ? n : max_lights));
+    return n;
+}
+
+int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *p) {
+    if (!ctx) return 1;
+    if (!p) return fail(ctx, "set_scene_params: params is NULL");
+    ctx->scene_params = *p;
+    ctx->has_scene_params = true;
+    return 0;
+}
+
+int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx) return 1;
+    if (!name) return fail(ctx, "set_option: name is NULL");
+    if (ctx->in_frame) return fail(ctx, "set_option(%s) inside begin_frame/end_frame", name);
+    const std::string n(name);
+    if (n == "transmission") ctx->transmission = value != 0;
+    else if (n == "wave_paths") {
+        if (value < 1024) return fail(ctx, "wave_paths must be >= 1024");
+        ctx->wave_paths = value;
+    } else if (n == "stage_timing") ctx->stage_timing = value != 0;
+    else if (n == "tile_rank") ctx->tile_rank = (int)value;
+    else if (n == "tile_world") ctx->tile_world = (int)value;
+    else if (n == "tile_rows") ctx->tile_rows = (int)value;
+    else return fail(ctx, "unknown option '%s'", name);
+    if (ctx->tile_world < 1 || ctx->tile_rows < 1) return fail(ctx, "tile_world and tile_rows must be >= 1");
+    return 0;
+}
+
+int rptr_cuda_begin_frame(rptr_ctx *ctx, const rptr_camera_params *camera, const rptr_render_params *params,
+                          const rptr_light_sampling_config *lighting, int32_t reset_accumulation, int32_t freeze_frame, double time) {
+    (void)time;
+    if (!ctx) return 1;
+    if (!camera || !params) return fail(ctx, "begin_frame: camera/params is NULL");
+    if (!ctx->accum) return fail(ctx, "begin_frame before initialize");
+    if (!ctx->has_scene) return fail(ctx, "begin_frame before set_scene");
+    if (!ctx->has_scene_params) return fail(ctx, "begin_frame before set_scene_params (update_config)");
+    if (ctx->in_frame) return fail(ctx, "begin_frame called twice without end_frame");
+    if (params->batch_spp < 1) return fail(ctx, "batch_spp must be >= 1");
+    if (params->max_path_depth < 1 || params->max_path_depth > 64) return fail(ctx, "max_path_depth out of range");
+    if (ctx->tile_rank < 0 || ctx->tile_rank >= ctx->tile_world) return fail(ctx, "tile_rank %d outside tile_world %d", ctx->tile_rank, ctx->tile_world);
+    ctx->camera = *camera;
+    ctx->params = *params;
+    if (lighting) ctx->lighting = *lighting;
+    else { ctx->lighting.light_mis_angle = 0.0f; ctx->lighting.bin_size = 16; ctx->lighting.min_perceived_receiver_dist = 15.0f; ctx->lighting.min_radiance = 0.0f; }
+    if (ctx->lighting.bin_size < 1 || ctx->lighting.bin_size > RPTR_BINNED_LIGHTS_BIN_MAX_SIZE) return fail(ctx, "bin_size must be in [1, %d]", RPTR_BINNED_LIGHTS_BIN_MAX_SIZE);
+    ctx->freeze_frame = freeze_frame != 0;
+    if (reset_accumulation) { // vulkan/render_vulkan.cpp:1937-1941
+        if (!freeze_frame) ctx->frame_offset += ctx->frame_id;
+        ctx->frame_id = 0;
+    }
+    ctx->in_frame = true;
+    return 0;
+}
+
+static FrameParams make_frame_params(const rptr_ctx *ctx) {
+    FrameParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.width = ctx->width; fp.height = ctx->height;
+    memcpy(fp.cam_pos, ctx->camera.pos, sizeof(fp.cam_pos));
+    view_params(ctx->camera, ctx->width, ctx->height, fp.du, fp.dv, fp.tl);
+    fp.frame_offset = ctx->frame_offset;
+    fp.first_sample = ctx->frame_id;
+    fp.batch = ctx->params.batch_spp;
+    fp.max_path_depth = ctx->params.max_path_depth;
+    fp.rr_path_depth = ctx->params.rr_path_depth;
+    fp.output_channel = ctx->params.output_channel;
+    fp.glossy_only_mode = ctx->params.glossy_only_mode;
+    fp.enable_raster_taa = ctx->params.enable_raster_taa;
+    fp.n_lights = ctx->n_lights;
+    fp.bin_size = ctx->lighting.bin_size;
+    fp.n_bins = (ctx->n_lights + fp.bin_size - 1) / fp.bin_size; // vulkan/pt_megakernel.glsl:102-103
+    fp.transmission = ctx->transmission;
+    fp.sp = ctx->scene_params;
+    if (ctx->n_lights > 0) fp.sp.sun_radiance[3] *= 0.5f; // vulkan/render_sky.cpp:67-70
+    else fp.sp.sun_radiance[3] = 1.0f;
+    return fp;
+}
+
+int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
+    (void)variant;
+    if (!ctx) return 1;
+    if (!ctx->in_frame) return fail(ctx, "draw_frame outside begin_frame/end_frame");
+    CU(cudaSetDevice(ctx->device));
+    const TileMap tm = make_tilemap(ctx);
+    FrameParams fp = make_frame_params(ctx);
+    const int depth = fp.max_path_depth;
+    CU(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    if (tm.local_pixels > 0) {
+        int64_t layers_per_wave = ctx->wave_paths / tm.local_pixels;
+        if (layers_per_wave < 1) layers_per_wave = 1;
+        if (layers_per_wave > fp.batch) layers_per_wave = fp.batch;
+        if (ensure_wave(ctx, (size_t)layers_per_wave * tm.local_pixels, depth)) return 1;
+        Wave &w = ctx->wave;
+        const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4);
+        for (int32_t first = 0; first < fp.batch; first += (int32_t)layers_per_wave) {
+            const int32_t nl = (int32_t)((fp.batch - first) < layers_per_wave ? (fp.batch - first) : layers_per_wave);
+            CU(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * 2 * (depth + 2), ctx->stream));
+            {
+                StageTimer t(ctx, 3);
+                k_raygen<<<g_light, 256, 0, ctx->stream>>>(fp, tm, w, first, nl);
+                ctx->launches++;
+            }
+            for (int d = 0; d < depth; ++d) {
+                const uint32_t *q = d == 0 ? nullptr : w.queue[d & 1];
+                uint32_t *nq = w.queue[(d + 1) & 1];
+                {
+                    StageTimer t(ctx, 0);
+                    k_trace<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, q, w.counts + 2 * d, ctx->dcounters);
+                    ctx->launches++;
+                }
+                {
+                    StageTimer t(ctx, 1);
+                    k_shade<<<g_trace, 128, 0, ctx->stream>>>(fp, ctx->scene, ctx->bvh, w, q, w.counts + 2 * d, nq, w.counts + 2 * (d + 1),
+                                                             w.counts + 2 * d + 1, ctx->dcounters);
+                    ctx->launches++;
+                }
+                if (fp.output_channel == 0 && d + 1 < depth) {
+                    StageTimer t(ctx, 2);
+                    k_shadow<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, w.counts + 2 * d + 1, ctx->dcounters);
+                    ctx->launches++;
+                }
+            }
+            {
+                StageTimer t(ctx, 3);
+                k_resolve<<<g_light, 256, 0, ctx->stream>>>(tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters);
+                ctx->launches++;
+            }
+        }
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int rptr_cuda_end_frame(rptr_ctx *ctx, int32_t variant) {
+    (void)variant;
+    if (!ctx) return 1;
+    if (!ctx->in_frame) return fail(ctx, "end_frame without begin_frame");
+    CU(cudaEventRecord(ctx->ev_end, ctx->stream));
+    ctx->frame_timed = true;
+    ctx->accumulated_spp = ctx->frame_id + (uint32_t)ctx->params.batch_spp; // vulkan/render_vulkan.cpp:2152-2154
+    if (!ctx->freeze_frame) ctx->frame_id += (uint32_t)ctx->params.batch_spp;
+    ctx->in_frame = false;
+    return 0;
+}
+
+int rptr_cuda_flush(rptr_ctx *ctx) {
+    if (!ctx) return 1;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    collect_timers(ctx);
+    return 0;
+}
+
+int rptr_cuda_stats(rptr_ctx *ctx, rptr_render_stats *out) {
+    if (!ctx || !out) return 1;
+    if (rptr_cuda_flush(ctx)) return 1;
+    memset(out, 0, sizeof(*out));
+    if (ctx->frame_timed) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) ctx->last_render_ms = ms;
+    }
+    out->has_valid_frame_stats = ctx->last_render_ms != 0.0f;
+    out->render_time = ctx->last_render_ms;
+    out->rays_per_second = -1.0f;
+    out->frame_stats_delay = 0;
+    out->spp = (int32_t)ctx->accumulated_spp;
+    out->total_device_bytes_allocated = ctx->bytes_total;
+    out->max_device_bytes_allocated = ctx->bytes_max;
+    out->device_bytes_currently_allocated = ctx->bytes_now;
+    return 0;
+}
+
+int rptr_cuda_get_counters(rptr_ctx *ctx, rptr_counters *out) {
+    if (!ctx || !out) return 1;
+    if (rptr_cuda_flush(ctx)) return 1;
+    DevCounters dc;
+    CU(cudaMemcpy(&dc, ctx->dcounters, sizeof(dc), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->samples = dc.samples;
+    out->closest_rays = dc.closest_rays;
+    out->shadow_rays = dc.shadow_rays;
+    out->shaded_vertices = dc.shaded_vertices;
+    out->closest_nodes = dc.closest_nodes;
+    out->closest_tris = dc.closest_tris;
+    out->shadow_nodes = dc.shadow_nodes;
+    out->shadow_tris = dc.shadow_tris;
+    out->launches = ctx->launches;
+    out->ms_trace = ctx->ms_trace;
+    out->ms_shadow = ctx->ms_shadow;
+    out->ms_shade = ctx->ms_shade;
+    out->ms_other = ctx->ms_other;
+    out->trace_launches = ctx->trace_launches;
+    return 0;
+}
+
+int rptr_cuda_reset_counters(rptr_ctx *ctx) {
+    if (!ctx) return 1;
+    if (rptr_cuda_flush(ctx)) return 1;
+    CU(cudaMemset(ctx->dcounters, 0, sizeof(DevCounters)));
+    ctx->launches = 0;
+    ctx->trace_launches = 0;
+    ctx->ms_trace = ctx->ms_shadow = ctx->ms_shade = ctx->ms_other = 0.0;
+    return 0;
+}
+
+int rptr_cuda_frame_state(rptr_ctx *ctx, uint32_t *frame_id, uint32_t *frame_offset, uint32_t *accumulated_spp) {
+    if (!ctx) return 1;
+    if (frame_id) *frame_id = ctx->frame_id;
+    if (frame_offset) *frame_offset = ctx->frame_offset;
+    if (accumulated_spp) *accumulated_spp = ctx->accumulated_spp;
+    return 0;
+}
+
+int rptr_cuda_framebuffer_size(rptr_ctx *ctx, uint32_t *width, uint32_t *height, uint32_t *channels) {
+    if (!ctx) return 1;
+    if (width) *width = (uint32_t)ctx->width;
+    if (height) *height = (uint32_t)ctx->height;
+    if (channels) *channels = 4;
+    return 0;
+}
+
+size_t rptr_cuda_readback_f32(rptr_ctx *ctx, size_t n_elems, float *dst) {
+    if (!ctx || !dst || !ctx->accum) return 0;
+    const size_t size = (size_t)ctx->width * ctx->height * 4;
+    if (n_elems < size) return 0; // vulkan/render_vulkan.cpp:2262-2263
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+    if (cudaMemcpyAsync(dst, ctx->accum, size * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        fail(ctx, "readback failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    return size;
+}
+
+size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst) {
+    if (!ctx || !dst || !ctx->accum) return 0;
+    const size_t size = (size_t)ctx->width * ctx->height * 4;
+    if (n_elems < size) return 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+    const float scale = exp2f(ctx->params.exposure);
+    k_to_srgb8<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->accum, ctx->ldr, (uint32_t)(size / 4), scale);
+    ctx->launches++;
+    if (cudaMemcpyAsync(dst, ctx->ldr, size, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
+    return size;
+}
+
+int rptr_cuda_framebuffer_device_ptr(rptr_ctx *ctx, void **ptr) {
+    if (!ctx || !ptr) return 1;
+    if (!ctx->accum) return fail(ctx, "framebuffer_device_ptr before initialize");
+    if (rptr_cuda_flush(ctx)) return 1;
+    *ptr = ctx->accum;
+    return 0;
+}
+
+int rptr_cuda_stream_handle(rptr_ctx *ctx, void **stream) {
+    if (!ctx || !stream) return 1;
+    *stream = (void *)ctx->stream;
+    return 0;
+}
+
+int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, int32_t n, float *results, float *hit_t) {
+    if (!ctx) return 1;
+    if (!ctx->has_scene) return fail(ctx, "trace_rays before set_scene");
+    if (n < 0 || (n > 0 && (!queries || !results))) return fail(ctx, "trace_rays: invalid arguments");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    rptr_render_ray_query *dq = nullptr;
+    float4 *dr = nullptr;
+    float *dt = nullptr;
+    CU(cudaMalloc((void **)&dq, sizeof(rptr_render_ray_query) * (size_t)n));
+    CU(cudaMalloc((void **)&dr, sizeof(float4) * (size_t)n));
+    CU(cudaMalloc((void **)&dt, sizeof(float) * (size_t)n));
+    CU(cudaMemcpyAsync(dq, queries, sizeof(rptr_render_ray_query) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    k_ray_queries<<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->bvh, dq, n, dr, dt);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(results, dr, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hit_t) CU(cudaMemcpyAsync(hit_t, dt, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dq);
+    cudaFree(dr);
+    cudaFree(dt);
+    return 0;
+}
+
+int rptr_write_pfm(const char *prefix, uint32_t width, uint32_t height, uint32_t channels, const float *pixels) {
+    if (!prefix || width == 0 || height == 0 || channels < 3 || !pixels) return 1;
+    std::string path = std::string(prefix) + ".pfm";
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return 1;
+    fprintf(f, "PF\n%i %i\n-1.0\n", (int)width, (int)height);
+    std::vector<float> row((size_t)width * 3);
+    for (uint32_t y = 0; y < height; ++y) { // bottom row first
+        const float *src = pixels + (size_t)(height - y - 1) * width * channels;
+        for (uint32_t x = 0; x < width; ++x)
+            for (uint32_t j = 0; j < 3; ++j) row[(size_t)x * 3 + j] = src[(size_t)x * channels + j];
+        fwrite(row.data(), sizeof(float), row.size(), f);
+    }
+    fclose(f);
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,454 @@
+// rptr_host.cpp -- host-side scene ingestion: instance flattening, per-geometry parameter blocks, emitter
+// collection + bin equalisation, and the SAH BVH build that stands in for the driver's BLAS/TLAS build.
+#include "rptr_host.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <stdexcept>
+
+namespace rp {
+
+// ---- small host helpers ------------------------------------------------------------------------------------------------
+static inline float3 xfm_point(const float *m, float3 v) {
+    return f3(fmaf(m[0], v.x, fmaf(m[1], v.y, fmaf(m[2], v.z, m[3]))), fmaf(m[4], v.x, fmaf(m[5], v.y, fmaf(m[6], v.z, m[7]))),
+              fmaf(m[8], v.x, fmaf(m[9], v.y, fmaf(m[10], v.z, m[11]))));
+}
+
+// rows of inverse(mat3(m)) = cross products of the columns / determinant
+static void inverse_rows(const float *m, float *rows9) {
+    float3 c0 = f3(m[0], m[4], m[8]), c1 = f3(m[1], m[5], m[9]), c2 = f3(m[2], m[6], m[10]);
+    float3 r0 = cross(c1, c2), r1 = cross(c2, c0), r2 = cross(c0, c1);
+    float det = dot(c0, r0);
+    if (!(det != 0.0f)) throw std::runtime_error("instance transform is singular");
+    float inv = 1.0f / det;
+    r0 = r0 * inv; r1 = r1 * inv; r2 = r2 * inv;
+    rows9[0] = r0.x; rows9[1] = r0.y; rows9[2] = r0.z;
+    rows9[3] = r1.x; rows9[4] = r1.y; rows9[5] = r1.z;
+    rows9[6] = r2.x; rows9[7] = r2.y; rows9[8] = r2.z;
+}
+
+void view_params(const rptr_camera_params &cam, int w, int h, float *du_, float *dv_, float *tl_) {
+    float3 dir = ld3(cam.dir), up = ld3(cam.up);
+    float py = 2.0f * tanf(0.5f * cam.fovy * 0.01745329251994329576923690768489f);
+    float aspect = (float)w / (float)h;
+    float px = py * aspect;
+    float3 du = normalize(cross(dir, up)) * px;
+    float3 dv = -normalize(cross(du, dir)) * py;
+    float3 tl = dir - du * 0.5f - dv * 0.5f;
+    du_[0] = du.x; du_[1] = du.y; du_[2] = du.z;
+    dv_[0] = dv.x; dv_[1] = dv.y; dv_[2] = dv.z;
+    tl_[0] = tl.x; tl_[1] = tl.y; tl_[2] = tl.z;
+}
+
+// ---- emitters: librender/lights.cpp ---------------------------------------------------------------------------------------
+namespace {
+
+struct Emitter { float3 v0, v1, v2, radiance; };
+
+inline float halton2(unsigned index) { // util/compute_util.h:19-33
+    index = (index << 16) | (index >> 16);
+    index = ((index & 0x00ff00ffu) << 8) | ((index & 0xff00ff00u) >> 8);
+    index = ((index & 0x0f0f0f0fu) << 4) | ((index & 0xf0f0f0f0u) >> 4);
+    index = ((index & 0x33333333u) << 2) | ((index & 0xccccccccu) >> 2);
+    index = ((index & 0x55555555u) << 1) | ((index & 0xaaaaaaaau) >> 1);
+    return u2f(0x3f800000u | (index >> 9)) - 1.0f;
+}
+
+// lights.cpp:169-203; the host variant uses libm atan (lights.cpp:122-129) and divides by M_2_PI (sic, :195)
+std::vector<float> estimate_normalized_radiance(const std::vector<Emitter> &em, float min_dist) {
+    std::vector<float> rad(em.size());
+    for (size_t i = 0; i < em.size(); ++i) {
+        const Emitter &l = em[i];
+        float3 n = normalize(cross(l.v1 - l.v0, l.v2 - l.v0));
+        if (!(fabsf(length(n) - 1.0f) < 0.05f)) { rad[i] = 0.0f; continue; }
+        float3 c = (l.v0 + l.v1 + l.v2) / 3.0f;
+        float3 o = n * min_dist;
+        float3 prm;
+        float tangent = half_tri_solid_angle_tan(normalize(l.v0 - c - o), normalize(l.v1 - c - o), normalize(l.v2 - c - o), prm);
+        float sa = 2.0f * (atanf(tangent) + ((tangent < 0.0f) ? (float)M_PI : 0.0f));
+        float lum = 0.2126f * l.radiance.x + 0.7152f * l.radiance.y + 0.0722f * l.radiance.z; // util/util.cpp:293-296
+        rad[i] = (float)((double)lum * ((double)sa / M_2_PI));
+    }
+    return rad;
+}
+
+struct Slot { float radiance; int source; int splits; };
+
+void halton_shuffle(std::vector<Slot> &slots) { // lights.cpp:246-263
+    std::vector<Slot> out(slots.size());
+    const int count = (int)slots.size();
+    for (int i = 0; i < count; ++i) {
+        int src = (int)(unsigned)(halton2((unsigned)i) * (float)(unsigned)count);
+        for (;;) {
+            if (src >= count) src = 0;
+            if (slots[src].source == ~0) ++src;
+            else break;
+        }
+        out[i] = slots[src];
+        slots[src].source = ~0;
+    }
+    slots.swap(out);
+}
+
+float bin_equality(const std::vector<Slot> &slots, int bin_size) { // lights.cpp:266-279
+    float lo = 2.0e32f, hi = 0.0f;
+    for (int i = 0, n = (int)slots.size(); i < n;) {
+        float total = 0.0f;
+        for (int j = 0; j < bin_size && i < n; ++i, ++j) total += slots[i].radiance;
+        lo = std::min(total, lo);
+        hi = std::max(total, hi);
+    }
+    return std::min(lo / hi, 1.0f);
+}
+
+// lights.cpp:220-349
+void equalize_emitter_bins(std::vector<Emitter> &emitters, std::vector<float> &radiances, int bin_size) {
+    if (bin_size <= 1 || radiances.empty()) return;
+    const int n0 = (int)radiances.size();
+    const int bins0 = (n0 + (bin_size - 1)) / bin_size;
+    float avg = 0.0f;
+    for (float r : radiances) avg += r;
+    avg /= (float)radiances.size();
+    std::vector<Slot> slots;
+    slots.reserve(2 * radiances.size());
+    for (int i = 0; i < n0; ++i) {
+        int clones = (int)std::max((unsigned)std::min(radiances[i] / avg, (float)bins0), 1u);
+        for (int j = 0; j < clones; ++j) slots.push_back(Slot{radiances[i] / (float)clones, i, clones});
+    }
+    halton_shuffle(slots);
+    float equality = bin_equality(slots, bin_size);
+    std::vector<Slot> cdf;
+    for (int retry = 0; equality < 0.6f && retry < 2; ++retry) {
+        cdf.resize(slots.size());
+        Slot acc = slots[0];
+        cdf[0] = acc;
+        for (size_t i = 1; i < slots.size(); ++i) {
+            acc = Slot{acc.radiance + slots[i].radiance, slots[i].source, 1};
+            cdf[i] = acc;
+        }
+        cdf.front().splits = 1;
+        const float sum = cdf.back().radiance;
+        for (Slot &c : cdf) c.radiance /= sum;
+        const int prev = (int)slots.size();
+        const int padded = ((prev + (bin_size - 1)) / bin_size + 1) * bin_size;
+        unsigned h = 0;
+        while ((int)slots.size() < padded) {
+            float u = halton2(h++);
+            auto it = std::upper_bound(cdf.begin(), cdf.end(), u, [](float bound, const Slot &s) { return bound < s.radiance; });
+            if (it == cdf.end()) it = cdf.end() - 1;
+            ++it->splits;
+            slots.push_back(Slot{it->radiance, (int)(it - cdf.begin()), 0});
+        }
+        for (int i = prev; i < padded; ++i) {
+            Slot &clone = slots[i];
+            Slot &orig = slots[clone.source];
+            int &counter = cdf[clone.source].splits;
+            if (counter > 1) {
+                orig.radiance /= (float)counter;
+                orig.splits *= counter;
+                counter = 1;
+            }
+            clone.radiance = orig.radiance;
+            clone.source = orig.source;
+            clone.splits = orig.splits;
+        }
+        halton_shuffle(slots);
+        equality = bin_equality(slots, bin_size);
+    }
+    std::vector<Emitter> out(slots.size());
+    radiances.resize(slots.size());
+    for (size_t i = 0; i < slots.size(); ++i) {
+        radiances[i] = slots[i].radiance;
+        out[i] = emitters[slots[i].source];
+        out[i].radiance = out[i].radiance / (float)slots[i].splits;
+    }
+    emitters.swap(out);
+}
+
+} // namespace
+
+// ---- scene flattening ---------------------------------------------------------------------------------------------------
+void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config &ls, HostScene &s) {
+    s = HostScene();
+    if (d.n_materials <= 0 || !d.materials) throw std::runtime_error("scene has no materials");
+    s.materials.assign(d.materials, d.materials + d.n_materials);
+    for (const rptr_base_material &m : s.materials) {
+        const float scal[] = {m.base_color[0], m.roughness, m.specular, m.metallic, m.ior, m.specular_transmission, m.clearcoat_gloss};
+        for (float v : scal)
+            if (f2u(v) & 0x80000000u) throw std::runtime_error("textured material parameters are not supported by this backend yet (constants only)");
+        if (m.normal_map != -1) throw std::runtime_error("normal maps are not supported by this backend yet (normal_map must be -1)");
+    }
+    s.qverts.resize(d.n_geometries);
+    s.qnuv.resize(d.n_geometries);
+    for (int g = 0; g < d.n_geometries; ++g) {
+        const rptr_geometry_desc &gd = d.geometries[g];
+        if (gd.n_tris < 0 || (gd.n_tris > 0 && !gd.qverts)) throw std::runtime_error("geometry without vertices");
+        s.qverts[g].assign(gd.qverts, gd.qverts + 3 * (size_t)gd.n_tris);
+        if (gd.qnormal_uv && (gd.has_normals || gd.has_uvs)) s.qnuv[g].assign(gd.qnormal_uv, gd.qnormal_uv + 3 * (size_t)gd.n_tris);
+    }
+    s.tri_mat.resize(d.n_pmeshes);
+    for (int p = 0; p < d.n_pmeshes; ++p) {
+        const rptr_pmesh_desc &pm = d.pmeshes[p];
+        if (pm.mesh_id < 0 || pm.mesh_id >= d.n_meshes) throw std::runtime_error("parameterized mesh refers to a missing mesh");
+        if (pm.tri_material_ids) s.tri_mat[p].assign(pm.tri_material_ids, pm.tri_material_ids + pm.n_tri_material_ids);
+    }
+    size_t total = 0;
+    for (int i = 0; i < d.n_instances; ++i) {
+        const rptr_instance_desc &inst = d.instances[i];
+        if (inst.pmesh_id < 0 || inst.pmesh_id >= d.n_pmeshes) throw std::runtime_error("instance refers to a missing parameterized mesh");
+        const rptr_mesh_desc &mesh = d.meshes[d.pmeshes[inst.pmesh_id].mesh_id];
+        for (int j = 0; j < mesh.n_geometries; ++j) total += (size_t)d.geometries[mesh.first_geometry + j].n_tris;
+    }
+    if (total > 0x7ffffff0u) throw std::runtime_error("too many triangles after instancing");
+    s.tris.reserve(total);
+
+    std::vector<Emitter> emitters;
+    std::vector<char> nonemissive(d.n_pmeshes, 0);
+    for (int i = 0; i < d.n_instances; ++i) {
+        const rptr_instance_desc &inst = d.instances[i];
+        const rptr_pmesh_desc &pm = d.pmeshes[inst.pmesh_id];
+        const rptr_mesh_desc &mesh = d.meshes[pm.mesh_id];
+        const bool per_tri = !s.tri_mat[inst.pmesh_id].empty();
+        int64_t prim_offset = 0;
+        std::vector<Emitter> found;
+        for (int j = 0; j < mesh.n_geometries; ++j) {
+            const int gidx = mesh.first_geometry + j;
+            const rptr_geometry_desc &gd = d.geometries[gidx];
+            HostGeomInst hg;
+            memset(&hg, 0, sizeof(hg));
+            hg.geometry = gidx;
+            hg.pmesh = inst.pmesh_id;
+            hg.prim_offset = prim_offset;
+            GeomInst &g = hg.g;
+            for (int k = 0; k < 3; ++k) { g.scale[k] = gd.quantized_scaling[k]; g.offset[k] = gd.quantized_offset[k]; }
+            g.has_normals = gd.has_normals && !s.qnuv[gidx].empty();
+            g.has_uvs = gd.has_uvs && !s.qnuv[gidx].empty();
+            const int mat_off = pm.n_material_offsets ? pm.material_offsets[j] : 0;
+            g.flags = RPTR_GEOMETRY_FLAGS_IMPLICIT_INDICES;
+            const uint8_t *tm = per_tri ? s.tri_mat[inst.pmesh_id].data() + prim_offset : nullptr;
+            bool no_alpha;
+            if (per_tri) { // render_vulkan.cpp:2812-2818
+                if (prim_offset + gd.n_tris > (int64_t)s.tri_mat[inst.pmesh_id].size()) throw std::runtime_error("per-triangle material ids too short");
+                g.material_id = -1 - mat_off;
+                g.flags |= RPTR_GEOMETRY_FLAGS_EXTENDED_SHADER;
+                no_alpha = true;
+                for (int t = 0; t < gd.n_tris; ++t) {
+                    int mid = mat_off + tm[t];
+                    if (mid >= d.n_materials) throw std::runtime_error("per-triangle material id out of range");
+                    if (!(s.materials[mid].flags & RPTR_BASE_MATERIAL_NOALPHA)) no_alpha = false;
+                }
+            } else {
+                if (mat_off < 0 || mat_off >= d.n_materials) throw std::runtime_error("material offset out of range");
+                g.material_id = mat_off;
+                no_alpha = (s.materials[mat_off].flags & RPTR_BASE_MATERIAL_NOALPHA) != 0;
+                if (s.materials[mat_off].flags & RPTR_BASE_MATERIAL_EXTENDED) g.flags |= RPTR_GEOMETRY_FLAGS_EXTENDED_SHADER;
+                if (!(s.materials[mat_off].flags & RPTR_BASE_MATERIAL_ONESIDED)) g.flags |= RPTR_GEOMETRY_FLAGS_THIN;
+            }
+            if (no_alpha) g.flags |= RPTR_GEOMETRY_FLAGS_NOALPHA;
+            else s.any_non_opaque = true;
+            g.instance = i;
+            memcpy(hg.o2w, inst.transform, sizeof(hg.o2w));
+            inverse_rows(hg.o2w, g.w2o);
+            const int gi = (int)s.ginst.size();
+            const uint64_t *qv = s.qverts[gidx].data();
+            for (int t = 0; t < gd.n_tris; ++t) {
+                float3 a = xfm_point(hg.o2w, dequantize_position(qv[3 * (size_t)t + 0], g.scale, g.offset));
+                float3 b = xfm_point(hg.o2w, dequantize_position(qv[3 * (size_t)t + 1], g.scale, g.offset));
+                float3 c = xfm_point(hg.o2w, dequantize_position(qv[3 * (size_t)t + 2], g.scale, g.offset));
+                float3 e1 = b - a, e2 = c - a;
+                Tri tr;
+                tr.v0x = a.x; tr.v0y = a.y; tr.v0z = a.z;
+                tr.e1x = e1.x; tr.e1y = e1.y; tr.e1z = e1.z;
+                tr.e2x = e2.x; tr.e2y = e2.y; tr.e2z = e2.z;
+                tr.id = (int32_t)s.tris.size();
+                tr.geom_inst = gi;
+                tr.prim = t;
+                s.tris.push_back(tr);
+                if (!nonemissive[inst.pmesh_id]) { // collect_emitters, lights.cpp:33-73
+                    const rptr_base_material &m = s.materials[per_tri ? mat_off + tm[t] : mat_off];
+                    if (m.emission_intensity > 0.0f) found.push_back(Emitter{a, b, c, ld3(m.base_color) * m.emission_intensity});
+                }
+            }
+            s.ginst.push_back(hg);
+            prim_offset += gd.n_tris;
+        }
+        if (!nonemissive[inst.pmesh_id]) { // lights.cpp:17-30: each instance's emitters are prepended
+            if (!found.empty()) emitters.insert(emitters.begin(), found.begin(), found.end());
+            else nonemissive[inst.pmesh_id] = 1;
+        }
+    }
+    if (d.binned_lights && d.n_binned_lights > 0) {
+        s.lights.assign(d.binned_lights, d.binned_lights + d.n_binned_lights);
+    } else if (!emitters.empty()) { // update_light_sampling, lights.cpp:75-90
+        std::vector<float> rad = estimate_normalized_radiance(emitters, ls.min_perceived_receiver_dist);
+        if (ls.min_radiance > 0.0f) { // trim_dim_emitters, lights.cpp:205-218
+            size_t n = 0;
+            for (size_t i = 0; i < emitters.size(); ++i)
+                if (rad[i] >= ls.min_radiance) { emitters[n] = emitters[i]; rad[n] = rad[i]; ++n; }
+            emitters.resize(n);
+            rad.resize(n);
+        }
+        equalize_emitter_bins(emitters, rad, ls.bin_size);
+        s.lights.reserve(emitters.size());
+        for (const Emitter &e : emitters) {
+            rptr_tri_light_data t;
+            t.v0[0] = e.v0.x; t.v0[1] = e.v0.y; t.v0[2] = e.v0.z;
+            t.v1[0] = e.v1.x; t.v1[1] = e.v1.y; t.v1[2] = e.v1.z;
+            t.v2[0] = e.v2.x; t.v2[1] = e.v2.y; t.v2[2] = e.v2.z;
+            t.radiance[0] = e.radiance.x; t.radiance[1] = e.radiance.y; t.radiance[2] = e.radiance.z;
+            s.lights.push_back(t);
+        }
+    }
+    build_bvh(s);
+}
+
+// ---- binned-SAH BVH2 build -----------------------------------------------------------------------------------------------
+namespace {
+
+struct Prim { float lo[3], hi[3], c[3]; int32_t id; };
+struct ChildRef { int32_t c, n; float lo[3], hi[3]; };
+struct Builder {
+    HostScene &s;
+    std::vector<Prim> prims;
+    static constexpr int NB = 16;
+    static constexpr int MAX_LEAF = 4;
+    static float half_area(const float *lo, const float *hi) {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    ChildRef build(int lo, int hi, int depth) {
+        ChildRef r;
+        float cmin[3], cmax[3];
+        for (int k = 0; k < 3; ++k) { r.lo[k] = 1e30f; r.hi[k] = -1e30f; cmin[k] = 1e30f; cmax[k] = -1e30f; }
+        for (int i = lo; i < hi; ++i)
+            for (int k = 0; k < 3; ++k) {
+                r.lo[k] = fminf(r.lo[k], prims[i].lo[k]);
+                r.hi[k] = fmaxf(r.hi[k], prims[i].hi[k]);
+                cmin[k] = fminf(cmin[k], prims[i].c[k]);
+                cmax[k] = fmaxf(cmax[k], prims[i].c[k]);
+            }
+        const int n = hi - lo;
+        auto leaf = [&]() {
+            r.c = ~(int32_t)s.leaf_tris.size();
+            r.n = n;
+            for (int i = lo; i < hi; ++i) s.leaf_tris.push_back(s.tris[prims[i].id]);
+            return r;
+        };
+        if (n == 1) return leaf();
+        int best_axis = -1, best_bin = -1;
+        float best_cost = 1e30f;
+        if (depth < 48) {
+            for (int ax = 0; ax < 3; ++ax) {
+                const float ext = cmax[ax] - cmin[ax];
+                if (!(ext > 0.0f)) continue;
+                float blo[NB][3], bhi[NB][3];
+                int cnt[NB];
+                for (int b = 0; b < NB; ++b) {
+                    cnt[b] = 0;
+                    for (int k = 0; k < 3; ++k) { blo[b][k] = 1e30f; bhi[b][k] = -1e30f; }
+                }
+                const float sc = (float)NB / ext;
+                for (int i = lo; i < hi; ++i) {
+                    int b = std::min(NB - 1, std::max(0, (int)((prims[i].c[ax] - cmin[ax]) * sc)));
+                    cnt[b]++;
+                    for (int k = 0; k < 3; ++k) {
+                        blo[b][k] = fminf(blo[b][k], prims[i].lo[k]);
+                        bhi[b][k] = fmaxf(bhi[b][k], prims[i].hi[k]);
+                    }
+                }
+                float ra[NB];
+                int rc[NB];
+                float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+                int c = 0;
+                for (int b = NB - 1; b > 0; --b) {
+                    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], blo[b][k]); mx[k] = fmaxf(mx[k], bhi[b][k]); }
+                    c += cnt[b];
+                    ra[b] = c ? half_area(mn, mx) : 0.0f;
+                    rc[b] = c;
+                }
+                for (int k = 0; k < 3; ++k) { mn[k] = 1e30f; mx[k] = -1e30f; }
+                c = 0;
+                for (int b = 0; b < NB - 1; ++b) {
+                    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], blo[b][k]); mx[k] = fmaxf(mx[k], bhi[b][k]); }
+                    c += cnt[b];
+                    if (c == 0 || rc[b + 1] == 0) continue;
+                    float cost = half_area(mn, mx) * (float)c + ra[b + 1] * (float)rc[b + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; }
+                }
+            }
+        }
+        int mid;
+        if (best_axis < 0) {
+            if (n <= MAX_LEAF) return leaf();
+            mid = lo + n / 2; // coincident centroids or depth cap: median split in current order
+        } else {
+            const float parent = half_area(r.lo, r.hi);
+            // SAH termination: traversal step cost 1.2 box-pair tests vs 1 per triangle
+            if (n <= MAX_LEAF && (float)n * parent <= 1.2f * parent + best_cost) return leaf();
+            const float sc = (float)NB / (cmax[best_axis] - cmin[best_axis]);
+            const float cm = cmin[best_axis];
+            const int ax = best_axis, bb = best_bin;
+            auto it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const Prim &q) {
+                return std::min(NB - 1, std::max(0, (int)((q.c[ax] - cm) * sc))) <= bb;
+            });
+            mid = (int)(it - prims.begin());
+            if (mid == lo || mid == hi) mid = lo + n / 2;
+        }
+        const int32_t idx = (int32_t)s.nodes.size();
+        s.nodes.push_back(BvhNode());
+        ChildRef a = build(lo, mid, depth + 1);
+        ChildRef b = build(mid, hi, depth + 1);
+        BvhNode &nd = s.nodes[idx];
+        for (int k = 0; k < 3; ++k) {
+            nd.c0min[k] = a.lo[k]; nd.c0max[k] = a.hi[k];
+            nd.c1min[k] = b.lo[k]; nd.c1max[k] = b.hi[k];
+        }
+        nd.c0 = a.c; nd.n0 = a.n;
+        nd.c1 = b.c; nd.n1 = b.n;
+        s.sah_cost += half_area(r.lo, r.hi);
+        r.c = idx;
+        r.n = 0;
+        return r;
+    }
+};
+
+} // namespace
+
+void build_bvh(HostScene &s) {
+    auto t0 = std::chrono::steady_clock::now();
+    s.nodes.clear();
+    s.leaf_tris.clear();
+    s.sah_cost = 0.0f;
+    if (s.tris.empty()) return;
+    Builder b{s, {}};
+    b.prims.resize(s.tris.size());
+    for (size_t i = 0; i < s.tris.size(); ++i) {
+        const Tri &t = s.tris[i];
+        Prim &p = b.prims[i];
+        const float v[3][3] = {{t.v0x, t.v0y, t.v0z}, {t.v0x + t.e1x, t.v0y + t.e1y, t.v0z + t.e1z}, {t.v0x + t.e2x, t.v0y + t.e2y, t.v0z + t.e2z}};
+        for (int k = 0; k < 3; ++k) {
+            float lo = fminf(v[0][k], fminf(v[1][k], v[2][k])), hi = fmaxf(v[0][k], fmaxf(v[1][k], v[2][k]));
+            // conservative padding (2^-16 relative): box culling may never reject what intersect_tri accepts
+            float pad = 1.52587890625e-05f * fmaxf(fabsf(lo), fabsf(hi)) + 1e-30f;
+            p.lo[k] = lo - pad;
+            p.hi[k] = hi + pad;
+            p.c[k] = 0.5f * (p.lo[k] + p.hi[k]);
+        }
+        p.id = (int32_t)i;
+    }
+    s.nodes.reserve(s.tris.size());
+    s.leaf_tris.reserve(s.tris.size());
+    ChildRef root = b.build(0, (int)b.prims.size(), 0);
+    if (root.c < 0) { // a single leaf: wrap it into a root node with an empty second child
+        BvhNode nd;
+        memset(&nd, 0, sizeof(nd));
+        for (int k = 0; k < 3; ++k) { nd.c0min[k] = root.lo[k]; nd.c0max[k] = root.hi[k]; nd.c1min[k] = 1e30f; nd.c1max[k] = -1e30f; }
+        nd.c0 = root.c; nd.n0 = root.n;
+        nd.c1 = 0; nd.n1 = -1;
+        s.nodes.push_back(nd);
+    }
+    s.bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+} // namespace rp

@@ -1,0 +1,42 @@
+// rptr_host.hpp -- host-side scene ingestion for the CUDA backend: what RenderVulkan::set_scene and the binned-lights
+// extension do on the CPU before anything reaches the GPU (vulkan/render_vulkan.cpp:1554-1644,2748-2850;
+// vulkan/light_sampling/render_binned_lights.cpp:68-149; librender/lights.cpp:14-349).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "rptr_bvh.cuh"
+
+namespace rp {
+
+struct HostGeomInst {
+    GeomInst g;       // pointers are indices-to-be-patched: see stream ids below
+    int32_t geometry; // index into the scene's geometry streams
+    int32_t pmesh;    // for tri_mat
+    int64_t prim_offset;
+    float o2w[12];
+};
+
+struct HostScene {
+    // owned copies of the input streams (the caller's Scene is only borrowed for set_scene, app.cpp:151-175)
+    std::vector<std::vector<uint64_t>> qverts, qnuv;
+    std::vector<std::vector<uint8_t>> tri_mat;
+    std::vector<HostGeomInst> ginst;
+    std::vector<rptr_base_material> materials;
+    std::vector<rptr_tri_light_data> lights;
+    std::vector<Tri> tris;      // flattened (instance, geometry, primitive) order; Tri::id == index
+    std::vector<BvhNode> nodes; // node 0 = root
+    std::vector<Tri> leaf_tris; // leaf order
+    bool any_non_opaque = false;
+    double bvh_build_ms = 0.0;
+    float sah_cost = 0.0f;
+};
+
+// Throws std::runtime_error with a readable message on invalid input.
+void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config &ls, HostScene &out);
+void build_bvh(HostScene &s);
+
+// update_view_parameters (vulkan/render_vulkan.cpp:2880-2894): out = du, dv, top_left
+void view_params(const rptr_camera_params &cam, int w, int h, float *du, float *dv, float *tl);
+
+} // namespace rp

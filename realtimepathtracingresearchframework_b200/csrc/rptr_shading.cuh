@@ -1,0 +1,838 @@
+// rptr_shading.cuh -- per-vertex shading of the wavefront path tracer (hit attributes, material unpack, emitter MIS,
+// next-event estimation, glTF BSDF sampling, Russian roulette, sky on miss), written against rptr_math.cuh.
+// Replaces, as one stage of the wavefront, what the reference runs inside its megakernel thread:
+//   vulkan/pt_megakernel.glsl:113-149,578-731 + rendering/mc/{shade_base_material,nee,lights_linear}.glsl +
+//   rendering/bsdfs/gltf_bsdf.glsl + rendering/lights/{tri,sun}.glsl + rendering/rt/hit.glsl.
+#pragma once
+#include "rptr_math.cuh"
+#include "../../include/rptr_types.h"
+
+namespace rp {
+
+// ---- device-side scene --------------------------------------------------------------------------------------------
+struct GeomInst { // the reference's instanced_geometry[] entry (rendering/rt/geometry.h.glsl:72-98), one per (instance, geometry)
+    const uint64_t *qverts;
+    const uint64_t *qnuv;
+    const uint8_t *tri_mat;
+    float scale[3], offset[3];
+    float w2o[9]; // rows of inverse(mat3(object_to_world))
+    int32_t material_id;
+    uint32_t flags;
+    int32_t instance;
+    int32_t has_normals, has_uvs;
+    int32_t _pad;
+};
+
+struct Tri { // 48 B traversal record, world space
+    float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
+    int32_t id;        // flattened (instance, geometry, primitive) index: the closest-hit tie-break key
+    int32_t geom_inst; // index into GeomInst[]
+    int32_t prim;
+};
+
+struct SceneDev {
+    const GeomInst *ginst;
+    const rptr_base_material *materials;
+    const rptr_tri_light_data *lights;
+};
+
+struct FrameParams {
+    int32_t width, height;
+    float cam_pos[3], du[3], dv[3], tl[3];
+    uint32_t frame_offset;
+    uint32_t first_sample; // frame_id of layer 0 of this batch
+    int32_t batch;
+    int32_t max_path_depth, rr_path_depth, output_channel, glossy_only_mode, enable_raster_taa;
+    int32_t n_lights, n_bins, bin_size;
+    int32_t transmission;
+    rptr_scene_params sp; // sun_radiance[3] already carries the light-count rule (vulkan/render_sky.cpp:67-70)
+};
+
+// ---- RNG: rendering/pointsets/hashing.glsl:11-39, lcg_rng.glsl:15-39 ------------------------------------------------
+RPTR_HD uint32_t murmur_mix(uint32_t hash, uint32_t k) {
+    k *= 0xcc9e2d51u;
+    k = (k << 15) | (k >> 17);
+    k *= 0x1b873593u;
+    hash ^= k;
+    hash = ((hash << 13) | (hash >> 19)) * 5u + 0xe6546b64u;
+    return hash;
+}
+RPTR_HD uint32_t murmur_finalize(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+RPTR_HD uint32_t lcg_seed(uint32_t index, uint32_t frame, uint32_t linear) {
+    uint32_t s = murmur_mix(frame, linear);
+    s = murmur_mix(s, index);
+    return murmur_finalize(s);
+}
+RPTR_HD float lcg_randomf(uint32_t &state) {
+    state = state * 1664525u + 1013904223u;
+    return (float)state * 2.3283064365386963e-10f; // ldexp(float(state), -32)
+}
+
+// ---- rendering/util.glsl:70-92 ---------------------------------------------------------------------------------------
+RPTR_HD void ortho_basis(float3 &vx, float3 &vy, float3 n) {
+    vy = f3(0.0f);
+    if (n.x < 0.6f && n.x > -0.6f) vy.x = 1.0f;
+    else if (n.y < 0.6f && n.y > -0.6f) vy.y = 1.0f;
+    else if (n.z < 0.6f && n.z > -0.6f) vy.z = 1.0f;
+    else vy.x = 1.0f;
+    vx = normalize(cross(vy, n));
+    vy = normalize(cross(n, vx));
+}
+RPTR_HD float cos_half_angle(float c) { return (1.0f + c) / sqrtf(2.0f + 2.0f * c); }
+RPTR_HD float mix_fma(float x, float y, float a) { return fmaf(a, y, fmaf(-a, x, x)); }
+
+// ---- material ----------------------------------------------------------------------------------------------------------
+struct GltfMat {
+    float3 base_color;
+    float metallic, specular, roughness, ior;
+    float specular_transmission, transmission_roughness;
+    float3 transmission_color;
+    uint32_t flags;
+};
+
+// constants-only unpack_material + load_material (rendering/rt/material_textures.glsl:95-135, gltf_bsdf.glsl:38-62)
+RPTR_HD float unpack_material(GltfMat &m, float3 &emit, const rptr_base_material &p, bool transmission) {
+    float alpha = 1.0f;
+    m.base_color = f3(p.base_color[0], p.base_color[1], p.base_color[2]);
+    if (alpha > 0.001f) m.base_color = m.base_color / alpha;
+    m.specular = p.specular;
+    m.roughness = p.roughness;
+    m.metallic = p.metallic;
+    m.ior = p.ior;
+    emit = f3(p.base_color[0], p.base_color[1], p.base_color[2]) * p.emission_intensity;
+    if (p.emission_intensity != 0.0f) m.base_color = f3(0.0f);
+    m.specular_transmission = 0.0f;
+    m.transmission_color = f3(0.0f);
+    m.transmission_roughness = 0.0f;
+    if (transmission) {
+        m.specular_transmission = p.specular_transmission;
+        if (m.specular_transmission > 0.0f) {
+            if (!(m.ior > 1.0f)) {
+                alpha *= 1.0f - m.specular_transmission;
+                m.specular_transmission = 0.0f;
+            } else {
+                m.transmission_color = m.base_color;
+                m.transmission_roughness = m.roughness;
+                m.roughness = sqrtf(p.clearcoat_gloss);
+            }
+        }
+    }
+    m.flags = p.flags;
+    return alpha;
+}
+
+// ---- glTF BSDF (rendering/bsdfs/gltf_bsdf.glsl:172-645) -----------------------------------------------------------------
+RPTR_HD float schlick_weight(float c) {
+    float x = clampf(1.0f - c, 0.0f, 1.0f);
+    float x2 = x * x;
+    return x2 * x2 * x;
+}
+RPTR_HD float gtr_2(float cos_h, float alpha) {
+    float a2 = alpha * alpha;
+    return RPTR_INV_PI * a2 / pow2(1.0f + (a2 - 1.0f) * cos_h * cos_h);
+}
+RPTR_HD float smith_den1(float ndo, float a2) { return fabsf(ndo) + sqrtf(a2 + (1.0f - a2) * ndo * ndo); }
+RPTR_HD float smith_visibility_ggx(float ndo, float ndi, float alpha) {
+    float a = alpha * alpha;
+    return 1.0f / (smith_den1(ndi, a) * smith_den1(ndo, a));
+}
+RPTR_HD float3 to_pipe_sample(float2 u) {
+    float s, c;
+    sincos_pos(RPTR_TWO_PI * u.x, s, c);
+    return f3(c, s, u.y);
+}
+RPTR_HD float3 sample_sphere(float3 up) {
+    float ct = up.z * 2.0f - 1.0f;
+    float st = sqrtf(fmaxf(1.0f - ct * ct, 0.0f));
+    return f3(st * up.x, st * up.y, ct);
+}
+RPTR_HD float3 sample_gtr_2_vndf(float3 wo, float ax, float ay, float3 up) {
+    float3 wi = normalize(f3(ax * wo.x, ay * wo.y, wo.z));
+    float z = fmaf(1.0f - up.z, 1.0f + wi.z, -wi.z);
+    float st = sqrtf(clampf(1.0f - z * z, 0.0f, 1.0f));
+    float3 wm = f3(st * up.x, st * up.y, z) + wi;
+    float3 w = f3(wm.x * ax, wm.y * ay, fmaxf(0.0f, wm.z));
+    return w / length(w);
+}
+RPTR_HD float gtr_2_vndf_pdf(float ndo, float cos_h, float alpha) {
+    return gtr_2(cos_h, alpha) * (0.5f / smith_den1(ndo, alpha * alpha));
+}
+RPTR_HD float3 diffuse_basecolor(const GltfMat &m) { return m.base_color * (1.0f - m.metallic); }
+RPTR_HD float3 specular_basecolor(const GltfMat &m, float ior) {
+    float d = pow2((ior - 1.0f) / (ior + 1.0f));
+    return mix3(f3(d), m.base_color, m.metallic);
+}
+RPTR_HD float specular_alpha(const GltfMat &m) { return fmaxf(m.roughness * m.roughness, 0.002f); }
+RPTR_HD float transmission_alpha(const GltfMat &m) { return fmaxf(m.transmission_roughness * m.transmission_roughness, 0.002f); }
+RPTR_HD float gltf_schlick_weight(float odh, float ior) {
+    float f = schlick_weight(odh);
+    if (ior < 1.0f) {
+        float cc = sqrtf(1.0f - ior * ior);
+        f = mixf(f, 1.0f, fminf((1.0f - odh) / (1.0f - cc), 1.0f));
+    }
+    return f;
+}
+
+RPTR_HD float3 gltf_bsdf(const GltfMat &m, float3 n, float3 wo, float3 wi, bool tr) {
+    float idn = dot(n, wi), odn = dot(n, wo);
+    float ior = odn < 0.0f ? 1.0f / m.ior : m.ior;
+    float3 wh;
+    if (idn * odn < 0.0f) {
+        if (!tr) return f3(0.0f);
+        if (!(m.specular_transmission > 0.0f)) return f3(0.0f);
+        if (m.flags & RPTR_BASE_MATERIAL_ONESIDED) wh = wi * (-ior) - wo;
+        else wh = reflect3(wi, n) + wo;
+        if (!(dot(wh, n) > 0.0f)) return f3(0.0f);
+    } else
+        wh = wi + wo;
+    wh = normalize(wh);
+    float odh = dot(wo, wh), idh = dot(wi, wh);
+    float3 diffuse = diffuse_basecolor(m) * RPTR_INV_PI;
+    float3 specular = f3(0.0f);
+    if (m.ior > 1.0f) {
+        float3 f0 = specular_basecolor(m, m.ior);
+        float sa = specular_alpha(m);
+        if (tr && idn * odn < 0.0f) sa = transmission_alpha(m);
+        float refl = gtr_2(dot(n, wh), sa);
+        refl *= smith_visibility_ggx(odn, idn, sa);
+        float fw = gltf_schlick_weight(fabsf(odh), ior);
+        float3 F = mix3(f0, f3(1.0f), fw);
+        if (tr && idn * odn < 0.0f) {
+            diffuse = f3(0.0f);
+            specular = m.transmission_color * (refl * (1.0f - m.metallic) * m.specular_transmission) * (f3(1.0f) - F);
+            if (m.flags & RPTR_BASE_MATERIAL_ONESIDED) {
+                float ac = 2.0f * odh / (idh * ior + odh);
+                specular = specular * (ac * ac);
+            }
+        } else {
+            if (tr) diffuse = diffuse * (1.0f - m.specular_transmission);
+            diffuse = diffuse * (f3(1.0f) - F);
+            specular = F * refl;
+        }
+    }
+    return diffuse + specular;
+}
+
+struct Components { float w0, w1, w2; };
+RPTR_HD Components component_sampler(const GltfMat &m, float ior, float3 odh, float3 vis, bool tr) {
+    Components c;
+    float sl = luminance(specular_basecolor(m, m.ior));
+    float F0 = mixf(sl, 1.0f, gltf_schlick_weight(odh.x, 1.0f));
+    float F1 = mixf(sl, 1.0f, gltf_schlick_weight(odh.y, 1.0f));
+    c.w0 = (1.0f - F0) * vis.x * (1.0f - m.metallic) * luminance(diffuse_basecolor(m));
+    c.w1 = F1 * vis.y;
+    c.w2 = 0.0f;
+    float sum = 0.0f;
+    if (tr) {
+        float F2 = mixf(sl, 1.0f, gltf_schlick_weight(odh.z, ior));
+        c.w0 *= (1.0f - m.specular_transmission);
+        c.w2 = (1.0f - F2) * vis.z * (1.0f - m.metallic) * m.specular_transmission;
+        sum += c.w0; sum += c.w1; sum += c.w2;
+    } else {
+        sum += c.w0; sum += c.w1;
+    }
+    if (sum > 0.0f) {
+        c.w0 /= sum;
+        c.w1 /= sum;
+        if (tr) c.w2 /= sum;
+    } else
+        c.w0 = 1.0f;
+    return c;
+}
+RPTR_HD int sample_reuse_component(const Components &c, float &rnd, float &prob, bool tr) {
+    int comp = 0;
+    float next_base = 0.0f, base = 0.0f;
+    float w[3] = {c.w0, c.w1, c.w2};
+    int n = tr ? 3 : 2;
+    for (int i = 0; i < n; ++i) {
+        float p = w[i];
+        if (p > 0.0f && rnd >= next_base) {
+            comp = i;
+            prob = p;
+            base = next_base;
+        }
+        next_base += p;
+    }
+    rnd = fminf(1.0f, (rnd - base) / prob);
+    return comp;
+}
+
+RPTR_HD float gltf_wpdf(const GltfMat &m, float3 n, float3 wo, float3 wi, bool tr) {
+    float idn = dot(n, wi), odn = dot(n, wo);
+    float ior = odn < 0.0f ? 1.0f / m.ior : m.ior;
+    float pdf = RPTR_INV_PI * fabsf(idn);
+    if (m.ior > 1.0f) {
+        float3 wh;
+        if (idn * odn < 0.0f) {
+            if (!tr) return 0.0f;
+            if (!(m.specular_transmission > 0.0f)) return 0.0f;
+            if (m.flags & RPTR_BASE_MATERIAL_ONESIDED) wh = wi * (-ior) - wo;
+            else wh = reflect3(wi, n) + wo;
+            if (!(dot(wh, n) > 0.0f)) return 0.0f;
+        } else
+            wh = wi + wo;
+        wh = normalize(wh);
+        float odh = dot(wo, wh), idh = dot(wi, wh);
+        float cth = dot(wh, n);
+        float3 vis = f3(1.0f, 0.0f, 0.0f);
+        float sa = specular_alpha(m);
+        vis.y = 2.0f * fabsf(idn) / smith_den1(idn, sa * sa);
+        float ta = sa;
+        if (tr) {
+            vis.z = vis.y;
+            if (m.specular_transmission > 0.0f) {
+                ta = transmission_alpha(m);
+                vis.z = 2.0f * fabsf(idn) / smith_den1(idn, ta * ta);
+            }
+        }
+        Components c = component_sampler(m, ior, f3(fabsf(odh)), vis, tr);
+        if (tr && idn * odn < 0.0f) sa = ta;
+        float spec = gtr_2_vndf_pdf(odn, cth, sa);
+        if (tr && idn * odn < 0.0f) {
+            if (m.flags & RPTR_BASE_MATERIAL_ONESIDED) {
+                float ac = 2.0f * odh / (idh * ior + odh);
+                spec *= ac * ac;
+            }
+            pdf = spec * c.w2;
+        } else {
+            pdf *= c.w0;
+            pdf += spec * c.w1;
+        }
+    }
+    return pdf;
+}
+
+// returns f*|cos|/pdf; pdf == 0 marks failure (mis_wpdf = 0 then)
+RPTR_HD float3 sample_gltf_brdf(const GltfMat &m, float3 n, float3 wo, float3 &wi, float &pdf, float &mis_wpdf, float2 rng_sample,
+                               float2 fresnel_sample, float3 vx, float3 vy, bool tr) {
+    float3 wol = f3(dot(vx, wo), dot(vy, wo), dot(n, wo));
+    float odn = wol.z;
+    float ior = m.ior;
+    mis_wpdf = 0.0f;
+    wi = f3(0.0f);
+    if (tr) {
+        ior = odn < 0.0f ? 1.0f / m.ior : m.ior;
+        if (odn < 0.0f) wol.z = -wol.z;
+    } else if (odn < 0.0f) {
+        pdf = 0.0f;
+        return f3(0.0f);
+    }
+    float3 up = to_pipe_sample(rng_sample);
+    float3 wid = normalize(n + sample_sphere(up));
+    if (tr && odn < 0.0f) wid = -wid;
+
+    float sa = specular_alpha(m);
+    int comp = 0;
+    float comp_pdf = 0.0f;
+    Components c;
+    c.w0 = c.w1 = c.w2 = 0.0f;
+    float3 whs = f3(0.0f), wht = f3(0.0f);
+    if (m.ior > 1.0f) {
+        float3 odh_all = f3(0.0f), vis_all = f3(0.0f);
+        odh_all.x = cos_half_angle(dot(wo, wid));
+        vis_all.x = 1.0f;
+        whs = sample_gtr_2_vndf(wol, sa, sa, up);
+        odh_all.y = dot(wol, whs);
+        float sidn = reflect3(-wol, whs).z;
+        vis_all.y = sidn > 0.0f ? 2.0f * sidn / smith_den1(sidn, sa * sa) : 0.0f;
+        if (tr) {
+            float ta = sa;
+            wht = whs;
+            odh_all.z = odh_all.y;
+            float tidn = sidn;
+            if (m.specular_transmission > 0.0f) {
+                ta = transmission_alpha(m);
+                wht = sample_gtr_2_vndf(wol, ta, ta, up);
+                odh_all.z = dot(wol, wht);
+                if (m.flags & RPTR_BASE_MATERIAL_ONESIDED) tidn = -refract3(-wol, wht, 1.0f / ior).z;
+                else tidn = reflect3(-wol, wht).z;
+                vis_all.z = tidn > 0.0f ? 2.0f * tidn / smith_den1(tidn, ta * ta) : 0.0f;
+            }
+        }
+        c = component_sampler(m, ior, odh_all, vis_all, tr);
+        comp = sample_reuse_component(c, fresnel_sample.x, comp_pdf, tr);
+    }
+    float cth, idh, odh;
+    if (comp == 0) {
+        wi = wid;
+        float3 wh = normalize(wi + wo);
+        cth = dot(n, wh);
+        idh = odh = dot(wo, wh);
+    } else {
+        if (tr && comp == 2) {
+            sa = transmission_alpha(m);
+            whs = wht;
+        }
+        float3 wh = whs;
+        if (tr && odn < 0.0f) wh.z = -wh.z;
+        cth = wh.z;
+        wh = mat_mul(vx, vy, n, wh);
+        idh = odh = dot(wo, wh);
+        if (tr && comp != 1) {
+            if (m.flags & RPTR_BASE_MATERIAL_ONESIDED) {
+                wi = refract3(-wo, wh, 1.0f / ior);
+                idh = dot(wi, wh);
+            } else
+                wi = reflect3(reflect3(-wo, wh), n);
+        } else
+            wi = reflect3(-wo, wh);
+    }
+    float idn = dot(n, wi);
+    bool bad = tr ? ((idn * odn > 0.0f) != (comp != 2)) : !(idn > 0.0f);
+    if (bad) {
+        pdf = 0.0f;
+        return f3(0.0f);
+    }
+    pdf = RPTR_INV_PI * fabsf(idn);
+    if (m.ior > 1.0f) {
+        pdf *= c.w0;
+        float spec = gtr_2_vndf_pdf(odn, cth, sa);
+        if (tr && idn * odn < 0.0f) {
+            if (m.flags & RPTR_BASE_MATERIAL_ONESIDED) {
+                float ac = 2.0f * odh / (idh * ior + odh);
+                spec *= ac * ac;
+            }
+            pdf = spec * c.w2;
+        } else
+            pdf += spec * c.w1;
+    }
+    if (!(pdf > 0.0f)) return f3(0.0f);
+    float3 f = gltf_bsdf(m, n, wo, wi, tr);
+    mis_wpdf = gltf_wpdf(m, n, wo, wi, tr);
+    return f * fabsf(idn) / pdf;
+}
+
+// ---- triangle lights (rendering/lights/tri.glsl:58-152) ------------------------------------------------------------------
+RPTR_HD float fast_positive_atan(float y) {
+    float ay = fabsf(y);
+    float rx = (ay > 1.0f) ? (1.0f / ay) : ay;
+    float ry = rx * rx;
+    float rz = fmaf(ry, 0.02083509974181652f, -0.08513300120830536f);
+    rz = fmaf(ry, rz, 0.18014100193977356f);
+    rz = fmaf(ry, rz, -0.3302994966506958f);
+    ry = fmaf(ry, rz, 0.9998660087585449f);
+    rz = fmaf(-2.0f * ry, rx, 0.5f * RPTR_PI);
+    rz = (ay > 1.0f) ? rz : 0.0f;
+    rx = fmaf(rx, ry, rz);
+    return (y < 0.0f) ? (RPTR_PI - rx) : rx;
+}
+RPTR_HD float half_tri_solid_angle_tan(float3 v0, float3 v1, float3 v2, float3 &params) {
+    float hs = (v0.x > 0.0f) ? -1.0f : 1.0f;
+    float hk = 1.0f / (fabsf(v0.x) + 1.0f);
+    float hy = v0.y * hk, hz = v0.z * hk;
+    float d01 = dot(v0, v1), d02 = dot(v1, v2), d12 = dot(v0, v2);
+    float dh0 = fmaf(-hs, v1.x, d01);
+    float dh2 = fmaf(-hs, v2.x, d12);
+    float c0x = fmaf(-dh0, hy, v1.y), c0y = fmaf(-dh0, hz, v1.z);
+    float c1x = fmaf(-dh2, hy, v2.y), c1y = fmaf(-dh2, hz, v2.z);
+    float det = c0x * c1y - c1x * c0y;
+    float vol = fabsf(det);
+    float d02p12 = d02 + d12;
+    float opd01 = 1.0f + d01;
+    params = f3(vol, d02p12, opd01);
+    return vol / (opd01 + d02p12);
+}
+RPTR_HD float triangle_solid_angle(float3 v0, float3 v1, float3 v2, float3 &params) {
+    return 2.0f * fast_positive_atan(half_tri_solid_angle_tan(v0, v1, v2, params));
+}
+RPTR_HD float3 sample_solid_angle_polygon(float3 v0, float3 v1, float3 v2, float omega, float3 prm, float2 rnd) {
+    float target = omega * rnd.x;
+    float3 a0 = v1, a1 = v0, a2 = v2;
+    float s, c;
+    sincos_pos(0.5f * target, s, c);
+    float3 offset = a0 * (prm.x * c - prm.y * s) + a2 * (prm.z * s);
+    float k = 2.0f * (dot(a0, offset) / dot(offset, offset));
+    float3 nv2 = f3(fmaf(k, offset.x, -a0.x), fmaf(k, offset.y, -a0.y), fmaf(k, offset.z, -a0.z));
+    float s2 = dot(a1, nv2);
+    float sm = mix_fma(1.0f, s2, rnd.y);
+    float den = fmaf(-s2, s2, 1.0f);
+    float tn = sqrtf(fmaf(-sm, sm, 1.0f) / den);
+    tn = (den > 0.0f) ? tn : rnd.y;
+    return a1 * fmaf(-tn, s2, sm) + nv2 * tn;
+}
+
+RPTR_HD float3 ld3(const float *p) { return f3(p[0], p[1], p[2]); }
+
+// sample_tri_lights (rendering/mc/lights_linear.glsl:19-127), BINNED_LIGHTS_BIN_MAX_SIZE = 16
+RPTR_HD float3 sample_tri_lights(const FrameParams &fp, const rptr_tri_light_data *lights, float3 hit_p, float3 hit_n, float2 dir_sample,
+                                float2 sel, float3 &light_dir, float &light_dist, float &pdf, float &mis_wpdf) {
+    int num_lights = fp.n_lights, num_bins = fp.n_bins, bin_size = fp.bin_size;
+    sel.x *= (float)num_bins;
+    int bin_id = (int)(uint32_t)sel.x;
+    bin_id = bin_id < num_bins - 1 ? bin_id : num_bins - 1;
+    float sel_p = 1.0f / (float)num_bins;
+    float contribs[RPTR_BINNED_LIGHTS_BIN_MAX_SIZE];
+    float total = 0.0f;
+    const float MIN_IRRADIANCE = 6.2e-4f * 0.001f;
+    int bin_end = bin_size * (bin_id + 1);
+    bin_end = bin_end < num_lights ? bin_end : num_lights;
+#pragma unroll 1
+    for (int i = 0; i < RPTR_BINNED_LIGHTS_BIN_MAX_SIZE; ++i) {
+        int light_id = bin_size * bin_id + i;
+        if (!(light_id < bin_end)) break;
+        const rptr_tri_light_data &L = lights[light_id];
+        float3 a = ld3(L.v0) - hit_p, b = ld3(L.v1) - hit_p, c = ld3(L.v2) - hit_p;
+        bool front = dot(cross(a, b), c) < 0.0f;
+        float contrib = luminance(ld3(L.radiance));
+        if ((dot(a, hit_n) > 0.0f || dot(b, hit_n) > 0.0f || dot(c, hit_n) > 0.0f) && front) {
+            float3 prm;
+            contrib *= triangle_solid_angle(normalize(a), normalize(b), normalize(c), prm);
+        } else
+            contrib = 0.0f;
+        contrib += MIN_IRRADIANCE;
+        contribs[i] = contrib;
+        total += contrib;
+    }
+    float p = 0.0f, t = 0.0f;
+    int light_id = 0;
+#pragma unroll 1
+    for (int i = 0; i < RPTR_BINNED_LIGHTS_BIN_MAX_SIZE; ++i) {
+        light_id = bin_size * bin_id + i;
+        if (!(light_id < bin_end)) break;
+        p = contribs[i] / total;
+        t += p;
+        if (sel.y < t) break;
+    }
+    light_id = light_id < num_lights - 1 ? light_id : num_lights - 1;
+    sel_p *= p;
+    const rptr_tri_light_data &L = lights[light_id];
+    float3 v0 = ld3(L.v0), v1 = ld3(L.v1), v2 = ld3(L.v2);
+    float3 d0 = normalize(v0 - hit_p), d1 = normalize(v1 - hit_p), d2 = normalize(v2 - hit_p);
+    float3 prm;
+    float omega = triangle_solid_angle(d0, d1, d2, prm);
+    light_dir = sample_solid_angle_polygon(d0, d1, d2, omega, prm, dir_sample);
+    pdf = 1.0f / omega;
+    float3 e_n = cross(v1 - v0, v2 - v0);
+    light_dist = dot(v0 - hit_p, e_n) / dot(light_dir, e_n);
+    mis_wpdf = 2.0f * light_dist * light_dist / fabsf(dot(light_dir, e_n));
+    pdf *= sel_p;
+    mis_wpdf /= (float)num_bins;
+    return ld3(L.radiance) / pdf;
+}
+
+// ---- sky (rendering/lights/sky_model_arhosek/sky_model.glsl:40-59, vulkan/pt_megakernel.glsl:113-149) -------------------
+RPTR_HD float3 skymodel_radiance(const rptr_scene_params &sp, float3 sun_dir, float3 view) {
+    float ct = clampf(view.y, 0.0f, 1.0f);
+    float cg = clampf(dot(view, sun_dir), -1.0f, 1.0f);
+    float gamma = acos_f(ct);
+    float rayM = cg * cg;
+    float zenith = sqrtf(ct);
+    float out[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float c0 = sp.sky_configs[0][ch], c1 = sp.sky_configs[1][ch], c2 = sp.sky_configs[2][ch], c3 = sp.sky_configs[3][ch],
+                    c4 = sp.sky_configs[4][ch], c5 = sp.sky_configs[5][ch], c6 = sp.sky_configs[6][ch], c7 = sp.sky_configs[7][ch],
+                    c8 = sp.sky_configs[8][ch];
+        float expM = exp_f(c4 * gamma);
+        float b = 1.0f + c8 * c8 - 2.0f * c8 * cg;
+        float mieM = (1.0f + cg * cg) / (b * sqrtf(b));
+        float lhs = 1.0f + c0 * exp_f(c1 / (ct + 0.01f));
+        float rhs = c2 + c3 * expM + c5 * rayM + c6 * mieM + c7 * zenith;
+        out[ch] = lhs * rhs * sp.sky_radiances[ch] * 0.01f;
+    }
+    return f3(out[0], out[1], out[2]);
+}
+RPTR_HD float nee_mis_heuristic(float nf, float pf, float ng, float pg) {
+    float f = nf * pf, g = ng * pg;
+    return f / (f + g);
+}
+RPTR_HD float3 compute_sky_illum(const rptr_scene_params &sp, float3 ray_dir, float prev_bsdf_pdf) {
+    float3 dir = ray_dir;
+    float ocean = 1.0f;
+    if (dir.y <= 0.0f) {
+        dir.y = -dir.y;
+        float b = fmaxf(1.0f - fabsf(dir.y), 0.0f);
+        float b2 = b * b;
+        ocean = 0.7f * (b2 * b2 * b);
+    }
+    float3 sun_dir = ld3(sp.sun_dir);
+    float3 atm = max0(skymodel_radiance(sp, sun_dir, dir)) * ocean;
+    float3 sun = f3(0.0f);
+    if (dot(dir, sun_dir) >= sp.sun_cos_angle) sun = ld3(sp.sun_radiance) * ocean;
+    float3 illum = f3(0.0f);
+    illum = illum + abs3(atm);
+    float light_pdf = sp.sun_radiance[3] * (1.0f / (RPTR_TWO_PI * (1.0f - sp.sun_cos_angle)));
+    float w = nee_mis_heuristic(1.0f, prev_bsdf_pdf, 1.0f, light_pdf);
+    illum = illum + abs3(sun) * w;
+    return illum;
+}
+
+// ---- quantisation (librender/dequantize.glsl:8-48) -----------------------------------------------------------------------
+RPTR_HD float3 dequantize_position(uint64_t q, const float *scale, const float *offset) {
+    float ux = (float)(uint32_t)(q & 0x1FFFFFu);
+    float uy = (float)(uint32_t)((q >> 21) & 0x1FFFFFu);
+    float uz = (float)(uint32_t)((q >> 42) & 0x1FFFFFu);
+    return f3(ux * scale[0] + offset[0], uy * scale[1] + offset[1], uz * scale[2] + offset[2]);
+}
+RPTR_HD float3 dequantize_normal(uint32_t w) {
+    float nx = (float)((int)(w & 0xFFFFu) - 0x8000) / 32767.0f;
+    float ny = (float)((int)(w >> 16) - 0x8000) / 32767.0f;
+    float nl1 = fabsf(nx) + fabsf(ny);
+    if (nl1 >= 1.0f) {
+        float tx = (1.0f - fabsf(ny)) * (nx >= 0.0f ? 1.0f : -1.0f);
+        float ty = (1.0f - fabsf(nx)) * (ny >= 0.0f ? 1.0f : -1.0f);
+        nx = tx;
+        ny = ty;
+    }
+    return normalize(f3(nx, ny, 1.0f - nl1));
+}
+RPTR_HD float2 dequantize_uv(uint32_t w) {
+    float s = 8.0f / 65535.0f;
+    return f2(0.0f + (float)(int)(w & 0xFFFFu) * s, 1.0f + (float)(-(int)(w >> 16)) * s);
+}
+
+// ---- hit attributes (rendering/rt/hit.glsl:49-128,162-203) -----------------------------------------------------------------
+struct RTHit {
+    float3 normal; float dist; float3 geo_normal; int material_id; float3 tangent; float bitangent_l; float2 uv;
+};
+RPTR_HD int calc_hit_material_id(const GeomInst &g, uint32_t prim) {
+    if (g.material_id < 0) return (int)g.tri_mat[prim] - g.material_id - 1;
+    return g.material_id;
+}
+RPTR_HD RTHit calc_hit_attributes(const GeomInst &g, float ray_t, uint32_t prim, float ax, float ay) {
+    RTHit h;
+    h.dist = ray_t;
+    const uint64_t *qv = g.qverts + 3 * (size_t)prim;
+    float3 p0 = dequantize_position(qv[0], g.scale, g.offset);
+    float3 p1 = dequantize_position(qv[1], g.scale, g.offset);
+    float3 p2 = dequantize_position(qv[2], g.scale, g.offset);
+    float3 gn = cross(p1 - p0, p2 - p0);
+    float3 bary = f3(1.0f - ax - ay, ax, ay);
+    float3 n = gn;
+    uint64_t qa = 0, qb = 0, qc = 0;
+    if (g.has_normals || g.has_uvs) {
+        const uint64_t *qn = g.qnuv + 3 * (size_t)prim;
+        qa = qn[0]; qb = qn[1]; qc = qn[2];
+    }
+    if (g.has_normals) {
+        n = mat_mul(dequantize_normal((uint32_t)qa), dequantize_normal((uint32_t)qb), dequantize_normal((uint32_t)qc), bary);
+        if (dot(n, gn) < 0.0f) gn = -gn;
+    }
+    h.geo_normal = gn * 0.5f;
+    h.normal = n;
+    float2 uva = f2(0, 0), uvb = f2(0, 0), uvc = f2(0, 0);
+    h.uv = f2(0.0f, 0.0f);
+    if (g.has_uvs) {
+        uva = dequantize_uv((uint32_t)(qa >> 32));
+        uvb = dequantize_uv((uint32_t)(qb >> 32));
+        uvc = dequantize_uv((uint32_t)(qc >> 32));
+        h.uv = f2(fmaf(uvc.x, bary.z, fmaf(uvb.x, bary.y, uva.x * bary.x)), fmaf(uvc.y, bary.z, fmaf(uvb.y, bary.y, uva.y * bary.x)));
+    }
+    h.material_id = calc_hit_material_id(g, prim);
+    float3 r0 = f3(g.w2o[0], g.w2o[1], g.w2o[2]), r1 = f3(g.w2o[3], g.w2o[4], g.w2o[5]), r2 = f3(g.w2o[6], g.w2o[7], g.w2o[8]);
+    h.geo_normal = mat_mul(r0, r1, r2, h.geo_normal);
+    h.normal = normalize(mat_mul(r0, r1, r2, h.normal));
+    bool requires_tangent = true;
+    if (g.has_uvs) {
+        float det = length(gn);
+        float3 frame_n = gn / (det * det);
+        float3 dp2perp = cross(p2 - p0, frame_n);
+        float3 dp1perp = cross(frame_n, p1 - p0);
+        float2 duv1 = f2(uvb.x - uva.x, uvb.y - uva.y), duv2 = f2(uvc.x - uva.x, uvc.y - uva.y);
+        float3 T = dp2perp * duv1.x + dp1perp * duv2.x;
+        float3 B = dp2perp * duv1.y + dp1perp * duv2.y;
+        T = mat_mul(r0, r1, r2, T);
+        B = mat_mul(r0, r1, r2, B);
+        float Tlen = length(T);
+        if (Tlen > 0.0f && Tlen <= 3.402823466e+38f) { // > 0, not inf, not nan
+            h.tangent = T;
+            h.bitangent_l = dot(normalize(cross(h.geo_normal, T)), B);
+            requires_tangent = false;
+        }
+    }
+    if (requires_tangent) {
+        h.tangent = normalize(mat_mul(r0, r1, r2, cross(p2 - p0, gn)));
+        h.bitangent_l = 1.0f;
+    }
+    return h;
+}
+
+RPTR_HD float geometry_scale_to_tmin(float3 orig, float scale) { return (length(orig) + scale) * 0.000005f; }
+
+// ---- one path vertex ---------------------------------------------------------------------------------------------------------
+struct PathState {
+    float3 o, d;
+    float tmin, tmax;
+    float3 thr;
+    float prev_pdf;
+    float3 illum;
+    float total_t;
+    uint32_t rng;
+    int bounce;
+};
+struct ShadowRay {
+    float3 o, d;
+    float tmin, tmax;
+    float3 contrib; // throughput * L * w * |cos| * f, added to illum iff unoccluded
+};
+enum ShadeResult { SHADE_TERMINATE = 0, SHADE_CONTINUE = 1 };
+
+// primary ray + path state (vulkan/pt_megakernel.glsl:310-365)
+RPTR_HD void generate_primary(const FrameParams &fp, int px, int py, uint32_t sample_index, PathState &ps) {
+    uint32_t linear = (uint32_t)px + (uint32_t)py * (uint32_t)fp.width;
+    ps.rng = lcg_seed(sample_index, fp.frame_offset, linear);
+    float ptx = (float)px + 0.5f, pty = (float)py + 0.5f;
+    if (fp.enable_raster_taa == 0) {
+        float ux = lcg_randomf(ps.rng);
+        float uy = lcg_randomf(ps.rng);
+        ptx += ux - 0.5f;
+        pty += uy - 0.5f;
+    }
+    ptx /= (float)fp.width;
+    pty /= (float)fp.height;
+    ps.o = ld3(fp.cam_pos);
+    ps.d = normalize(ld3(fp.du) * ptx + ld3(fp.dv) * pty + ld3(fp.tl));
+    ps.tmin = 0.0f;
+    ps.tmax = 2.e32f;
+    ps.thr = f3(1.0f);
+    ps.prev_pdf = 2.e16f;
+    ps.illum = f3(0.0f);
+    ps.total_t = 0.0f;
+    ps.bounce = 0;
+}
+
+// Shades the vertex found by the closest-hit stage (tri < 0: miss).  On SHADE_CONTINUE ps holds the next ray.
+// sh.tmax < 0 means "no shadow ray"; sh.tmax == 0 means "visible without tracing" (the contribution is then
+// already added to ps.illum).  Restates pt_megakernel.glsl:480-731 + shade_base_material.glsl:14-96 + nee.glsl:32-90.
+RPTR_HD ShadeResult shade_vertex(const FrameParams &fp, const SceneDev &sc, PathState &ps, float hit_t, float hit_u, float hit_v,
+                                const Tri *tri, ShadowRay &sh) {
+    sh.tmax = -1.0f;
+    const rptr_scene_params &sp = fp.sp;
+    if (!tri) {
+        ps.illum = ps.illum + ps.thr * compute_sky_illum(sp, ps.d, ps.prev_pdf);
+        return SHADE_TERMINATE;
+    }
+    const bool tr = fp.transmission != 0;
+    const GeomInst &g = sc.ginst[tri->geom_inst];
+    RTHit h = calc_hit_attributes(g, hit_t, (uint32_t)tri->prim, hit_u, hit_v);
+    float approx_sa = length(h.geo_normal);
+    h.geo_normal = h.geo_normal / approx_sa;
+    approx_sa *= fabsf(dot(h.geo_normal, ps.d)) / (h.dist * h.dist);
+    ps.total_t += h.dist;
+    float geometry_scale = ps.total_t;
+    float3 w_o = -ps.d;
+    float3 ip = ps.o + ps.d * h.dist;
+    float3 ign = h.geo_normal, in_ = h.normal;
+    const rptr_base_material &mp = sc.materials[h.material_id];
+    if (dot(w_o, ign) < 0.0f) {
+        if (mp.flags & RPTR_BASE_MATERIAL_VOLUME) {
+            ip = ps.o;
+            h.dist = 0.0f;
+        } else if (!(mp.flags & RPTR_BASE_MATERIAL_ONESIDED)) {
+            in_ = -in_;
+            ign = -ign;
+        }
+    }
+    {
+        float nw = dot(w_o, in_), gnw = dot(w_o, ign);
+        if (nw * gnw <= 0.0f) {
+            float blend = gnw / (gnw - nw);
+            in_ = normalize(mix3(ign, in_, blend - 0.0001f));
+        }
+    }
+    float3 v_y = normalize(cross(in_, h.tangent));
+    float3 v_x = cross(v_y, in_);
+
+    GltfMat mat;
+    float3 emit;
+    unpack_material(mat, emit, mp, tr);
+    const float p_sun = sp.sun_radiance[3];
+    if (fp.output_channel == 0 && !is_zero(emit)) {
+        float light_pdf = (1.0f - p_sun) * (1.0f / ((float)fp.n_bins * approx_sa));
+        float w = nee_mis_heuristic(1.0f, ps.prev_pdf, 1.0f, light_pdf);
+        ps.illum = ps.illum + ps.thr * w * emit;
+    }
+    if (fp.output_channel != 0) {
+        float reliability = u2f((uint32_t)(127 - 2 * ps.bounce) << 23); // pow(0.25, bounce)
+        if (fp.output_channel == 1) ps.illum = ps.illum + ps.thr * mat.base_color * reliability;
+        else if (fp.output_channel == 2) ps.illum = ps.illum + in_ * reliability;
+        else if (fp.output_channel == 3) ps.illum = ps.illum + ip * reliability;
+    }
+    if (ps.bounce + 1 >= fp.max_path_depth) return SHADE_TERMINATE;
+    if (fp.output_channel == 0) {
+        float2 dir_sample, sel_sample;
+        dir_sample.x = lcg_randomf(ps.rng);
+        dir_sample.y = lcg_randomf(ps.rng);
+        sel_sample.x = lcg_randomf(ps.rng);
+        sel_sample.y = lcg_randomf(ps.rng);
+        float3 li = f3(0.0f), light_dir = f3(0.0f);
+        float light_dist = 2.e16f, light_pdf = 0.0f, mis_pdf = 0.0f;
+        if (sel_sample.x <= p_sun) {
+            sel_sample.x /= p_sun;
+            float sn, cs;
+            sincos_pos(RPTR_TWO_PI * dir_sample.x, sn, cs);
+            float cosT = mixf(1.0f, sp.sun_cos_angle, dir_sample.y);
+            float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
+            float3 sun_dir = ld3(sp.sun_dir);
+            float3 fx, fy;
+            ortho_basis(fx, fy, sun_dir);
+            light_dir = mat_mul(fx, fy, sun_dir, f3(sinT * cs, sinT * sn, cosT));
+            float pdf = 1.0f / (RPTR_TWO_PI * (1.0f - sp.sun_cos_angle));
+            li = li + (f3(1.0f) / pdf) * (ld3(sp.sun_radiance) / p_sun);
+            light_pdf = pdf * p_sun;
+            mis_pdf = light_pdf;
+        } else {
+            sel_sample.x = (sel_sample.x - p_sun) / (1.0f - p_sun);
+            float tri_mis = 0.0f;
+            li = li + sample_tri_lights(fp, sc.lights, ip, in_, dir_sample, sel_sample, light_dir, light_dist, light_pdf, tri_mis) / (1.0f - p_sun);
+            light_pdf *= 1.0f - p_sun;
+            mis_pdf = tri_mis * (1.0f - p_sun);
+        }
+        if (light_pdf > 0.0f && dot(light_dir, ign) * dot(light_dir, in_) > 0.0f) {
+            float bsdf_pdf = gltf_wpdf(mat, in_, w_o, light_dir, tr);
+            if (bsdf_pdf >= 0.0f) {
+                float3 bsdf = gltf_bsdf(mat, in_, w_o, light_dir, tr);
+                float w = nee_mis_heuristic(1.0f, mis_pdf, 1.0f, bsdf_pdf);
+                float3 contrib = ps.thr * (li * (bsdf * (w * fabsf(dot(light_dir, in_)))));
+                // raytrace_test_visibility (pt_megakernel.glsl:216-272)
+                float eps = geometry_scale_to_tmin(ip, geometry_scale);
+                if (light_dist - 2.0f * eps > 0.0f) {
+                    sh.o = ip;
+                    sh.d = light_dir;
+                    sh.tmin = eps;
+                    sh.tmax = light_dist - eps;
+                    sh.contrib = contrib;
+                } else {
+                    ps.illum = ps.illum + contrib;
+                    sh.tmax = 0.0f;
+                }
+            }
+        }
+    }
+    if (fp.glossy_only_mode != 0 && !(mat.roughness < RPTR_GLOSSY_MODE_ROUGHNESS_THRESHOLD && mat.ior != 1.0f)) return SHADE_TERMINATE;
+    float2 lobe, dirs;
+    lobe.x = lcg_randomf(ps.rng);
+    lobe.y = lcg_randomf(ps.rng);
+    dirs.x = lcg_randomf(ps.rng);
+    dirs.y = lcg_randomf(ps.rng);
+    float3 w_i;
+    float sampling_pdf = 0.0f, mis_wpdf = 0.0f;
+    float3 bsdf = sample_gltf_brdf(mat, in_, w_o, w_i, sampling_pdf, mis_wpdf, dirs, lobe, v_x, v_y, tr);
+    ++ps.bounce;
+    if (mis_wpdf == 0.0f || is_zero(bsdf) || !(dot(w_i, in_) * dot(w_i, ign) > 0.0f)) return SHADE_TERMINATE;
+    ps.thr = ps.thr * bsdf;
+    ps.prev_pdf = mis_wpdf;
+    ps.d = w_i;
+    ps.o = ip;
+    ps.tmin = geometry_scale_to_tmin(ps.o, ps.total_t);
+    ps.tmax = 1e20f;
+    if (ps.bounce >= fp.rr_path_depth) {
+        float prefix = fmaxf(ps.thr.x, fmaxf(ps.thr.y, ps.thr.z));
+        float rr_prob = prefix;
+        float rr_sample = lcg_randomf(ps.rng);
+        if (ps.bounce > 6) rr_prob = fminf(0.95f, rr_prob);
+        else rr_prob = fminf(1.0f, rr_prob);
+        if (rr_sample < rr_prob) ps.thr = ps.thr / rr_prob;
+        else return SHADE_TERMINATE;
+    }
+    return SHADE_CONTINUE;
+}
+
+} // namespace rp

@@ -1,0 +1,102 @@
+// tests/hostsim/hostsim.cpp -- TEST-ONLY harness (never part of librptr_cuda.so).
+// Compiles the product's __host__ __device__ shading / traversal code (csrc/rptr_shading.cuh, rptr_bvh.cuh) and its
+// host scene ingestion (csrc/rptr_host.cpp) with g++ and runs them one sample at a time on the CPU, so that
+// tests/test_hostsim_parity.py can check -- without a GPU -- that the code the kernels execute agrees bit for bit with
+// the independent oracle.  The wavefront kernels themselves (queues, atomics, resolve) are covered by the -m gpu tests.
+#include "../../realtimepathtracingresearchframework_b200/csrc/rptr_host.hpp"
+#include <cstring>
+
+using namespace rp;
+
+extern "C" {
+
+struct hostsim_args { // same layout as oracle_render_args
+    int32_t width, height;
+    rptr_camera_params camera;
+    rptr_render_params params;
+    rptr_light_sampling_config lighting;
+    rptr_scene_params scene_params;
+    uint32_t frame_offset, first_sample;
+    int32_t n_samples;
+    int32_t x0, y0, x1, y1;
+    int32_t transmission, n_threads;
+};
+
+struct hostsim_scene { HostScene hs; std::vector<GeomInst> gi; };
+
+hostsim_scene *hostsim_scene_create(const rptr_scene_desc *d, const rptr_light_sampling_config *ls) {
+    hostsim_scene *s = new hostsim_scene();
+    try {
+        build_host_scene(*d, *ls, s->hs);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "hostsim: %s\n", e.what());
+        delete s;
+        return nullptr;
+    }
+    for (const HostGeomInst &h : s->hs.ginst) {
+        GeomInst g = h.g;
+        g.qverts = s->hs.qverts[h.geometry].data();
+        g.qnuv = s->hs.qnuv[h.geometry].empty() ? nullptr : s->hs.qnuv[h.geometry].data();
+        g.tri_mat = s->hs.tri_mat[h.pmesh].empty() ? nullptr : s->hs.tri_mat[h.pmesh].data() + h.prim_offset;
+        s->gi.push_back(g);
+    }
+    return s;
+}
+void hostsim_scene_destroy(hostsim_scene *s) { delete s; }
+int32_t hostsim_num_lights(const hostsim_scene *s) { return (int32_t)s->hs.lights.size(); }
+void hostsim_get_lights(const hostsim_scene *s, rptr_tri_light_data *out) { memcpy(out, s->hs.lights.data(), s->hs.lights.size() * sizeof(*out)); }
+int32_t hostsim_num_nodes(const hostsim_scene *s) { return (int32_t)s->hs.nodes.size(); }
+
+static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
+    FrameParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.width = a->width; fp.height = a->height;
+    memcpy(fp.cam_pos, a->camera.pos, 12);
+    view_params(a->camera, a->width, a->height, fp.du, fp.dv, fp.tl);
+    fp.frame_offset = a->frame_offset;
+    fp.first_sample = a->first_sample;
+    fp.batch = 1;
+    fp.max_path_depth = a->params.max_path_depth;
+    fp.rr_path_depth = a->params.rr_path_depth;
+    fp.output_channel = a->params.output_channel;
+    fp.glossy_only_mode = a->params.glossy_only_mode;
+    fp.enable_raster_taa = a->params.enable_raster_taa;
+    fp.n_lights = (int)s->hs.lights.size();
+    fp.bin_size = a->lighting.bin_size;
+    fp.n_bins = fp.bin_size > 0 ? (fp.n_lights + fp.bin_size - 1) / fp.bin_size : 0;
+    fp.transmission = a->transmission;
+    fp.sp = a->scene_params;
+    if (fp.n_lights > 0) fp.sp.sun_radiance[3] *= 0.5f;
+    else fp.sp.sun_radiance[3] = 1.0f;
+    return fp;
+}
+
+// un-averaged sample layer `sample_index` for the region; rgba is W*H*4
+int hostsim_render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba) {
+    FrameParams fp = make_frame(s, a);
+    SceneDev sc{s->gi.data(), s->hs.materials.data(), s->hs.lights.data()};
+    BvhDev bvh{s->hs.nodes.data(), s->hs.leaf_tris.data(), (int32_t)s->hs.nodes.size(), (int32_t)s->hs.leaf_tris.size()};
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = a->y0; y < a->y1; ++y)
+        for (int x = a->x0; x < a->x1; ++x) {
+            PathState ps;
+            generate_primary(fp, x, y, sample_index, ps);
+            TraceCounters cnt{0, 0};
+            for (;;) {
+                HitRec h;
+                bool found = trace_ray<false>(bvh, ps.o, ps.d, ps.tmin, ps.tmax, h, cnt);
+                ShadowRay sh;
+                ShadeResult r = shade_vertex(fp, sc, ps, h.t, h.u, h.v, found ? &bvh.tris[h.tri] : nullptr, sh);
+                if (sh.tmax > 0.0f) {
+                    HitRec o;
+                    if (!trace_ray<true>(bvh, sh.o, sh.d, sh.tmin, sh.tmax, o, cnt)) ps.illum = ps.illum + sh.contrib;
+                }
+                if (r == SHADE_TERMINATE) break;
+            }
+            float *px = rgba + 4 * ((size_t)y * a->width + x);
+            px[0] = ps.illum.x; px[1] = ps.illum.y; px[2] = ps.illum.z; px[3] = ps.bounce == 0 ? 0.0f : 1.0f;
+        }
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol that
+include/rptr_cuda.h declares, keeps the reference's POD layouts, and fails loudly (no CPU fallback) when no CUDA
+device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from realtimepathtracingresearchframework_b200 import backend, types as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rptr_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rptr_(?:cuda_)?[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_python_binding_agree():
+    assert declared_symbols() == sorted(backend.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(cuda_lib_path):
+    lib = C.CDLL(cuda_lib_path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), "librptr_cuda.so does not export %s" % name
+
+
+def test_pod_layouts_match_reference_sizes():
+    # sizes stated by the reference headers
+    assert C.sizeof(T.BaseMaterial) == 80
+    assert C.sizeof(T.RenderParams) == 80
+    assert C.sizeof(T.LightSamplingConfig) == 16
+    assert C.sizeof(T.SceneConfig) == 32
+    assert C.sizeof(T.RenderRayQuery) == 32
+    assert C.sizeof(T.TriLightData) == 48
+    assert C.sizeof(T.RenderCameraParams) == 40
+    assert T.BaseMaterial.emission_intensity.offset == 76 and T.BaseMaterial.ior.offset == 48
+    assert T.RenderParams.output_channel.offset == 32 and T.RenderParams.focal_length.offset == 64
+
+
+def test_reference_defaults():
+    p = T.RenderParams()
+    assert (p.batch_spp, p.max_path_depth, p.rr_path_depth, p.pixel_radius, p.output_channel) == (1, 9, 2, 1.0, 0)
+    ls = T.LightSamplingConfig()
+    assert (ls.bin_size, ls.min_perceived_receiver_dist, ls.min_radiance) == (16, 15.0, 0.0)
+    m = T.BaseMaterial()
+    assert m.normal_map == -1 and abs(m.ior - 1.5) < 1e-7 and m.roughness == 1.0
+
+
+def test_no_cpu_fallback(cuda_lib_path):
+    """Without a CUDA device the product must refuse to work rather than fall back to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(backend.RptrError) as e:
+        backend.RenderCuda(device=0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_never_touches_the_oracle():
+    """Only tests/, bench.py and __graft_entry__.smoke may reach into oracle/."""
+    pkg = os.path.join(ROOT, "realtimepathtracingresearchframework_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"(from|import)\s+oracle|oracle/.*\.(h|so|cpp)|liboracle", txt.replace("oracle/gen_golden.py", "")), f
+
+
+def test_write_and_read_pfm_roundtrip(cuda_lib_path, tmp_path):
+    import numpy as np
+    img = np.random.default_rng(0).random((5, 7, 4)).astype(np.float32)
+    backend.write_pfm(tmp_path / "x", img)
+    raw = open(tmp_path / "x.pfm", "rb").read()
+    assert raw.startswith(b"PF\n7 5\n-1.0\n")  # util/write_image.cpp:52
+    body = np.frombuffer(raw[len(b"PF\n7 5\n-1.0\n"):], "<f4").reshape(5, 7, 3)
+    assert np.array_equal(body[0], img[4, :, :3])  # rows bottom to top, alpha dropped
+    assert np.array_equal(backend.read_pfm(tmp_path / "x.pfm"), img[..., :3])

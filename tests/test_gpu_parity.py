@@ -1,0 +1,315 @@
+"""Parity tests proper (-m gpu): the CUDA wavefront, called through the C ABI (RenderCuda -> librptr_cuda.so), against the
+CPU oracle on identical scene / camera / counters.
+
+Bar (BASELINE.json north_star): .pfm within 1e-4 rel-L2.  A path tracer only meets that if essentially every sample
+takes the same discrete decisions (hard part 1), so these tests assert the stronger property the RPTR-FP
+contract gives: the RGBA32F accumulator is BIT-IDENTICAL to the oracle's, and they report rel-L2 (= 0) as well.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from realtimepathtracingresearchframework_b200 import RenderConfiguration, RenderCuda, RptrError, load_sky_fit, scenes, types as T
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_TOL = 1e-4  # north_star tolerance on the .pfm (float RGB)
+
+
+def rel_l2(a, b):
+    a, b = a[..., :3].astype(np.float64), b[..., :3].astype(np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
+
+
+def max_rel_err(a, b):
+    """util/compare_exr.cpp:72-84 style per-channel relative error"""
+    a, b = a[..., :3].astype(np.float64), b[..., :3].astype(np.float64)
+    return float((np.abs(a - b) / np.maximum(np.abs(b), 1e-6)).max())
+
+
+def make_backend(scene, w, h, sky=None, **options):
+    r = RenderCuda(device=0)
+    r.initialize(w, h)
+    for k, v in options.items():
+        r.set_option(k, v)
+    r.set_scene(scene)
+    r.update_config(T.SceneConfig(**(sky or {})))
+    return r
+
+
+def assert_identical(img, ref, what):
+    l2, mre = rel_l2(img, ref), max_rel_err(img, ref)
+    ndiff = int((img.view(np.uint32) != ref.view(np.uint32)).any(-1).sum())
+    assert np.isfinite(ref).all() and ref[..., :3].max() > 0
+    assert l2 <= REL_L2_TOL, "%s: rel-L2 %.3e" % (what, l2)
+    assert ndiff == 0, "%s: %d pixels differ (rel-L2 %.3e, max rel err %.3e)" % (what, ndiff, l2, mre)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_c1_cornell_full_resolution_1spp(oracle, tmp_path):
+    """BASELINE config C1: 12-triangle Cornell box, 1920x1080, 1 spp, Lambert + emissive quad; validation .pfm."""
+    s = scenes.cornell_box()
+    W, H = 1920, 1080
+    r = make_backend(s, W, H)
+    r.render_spp(s.camera, 1)
+    img = r.framebuffer()
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=1)
+    assert_identical(img, ref, "C1")
+    from realtimepathtracingresearchframework_b200 import read_pfm, write_pfm
+    write_pfm(tmp_path / "c1_0001", img)  # <prefix>_<%04d spp>.pfm (libapp/app_state.cpp:467-481)
+    assert np.array_equal(read_pfm(tmp_path / "c1_0001.pfm"), ref[..., :3])
+    assert r.stats().spp == 1
+
+
+@pytest.mark.parametrize("n_tris,spp,sky", [(20000, 4, {}), (200000, 3, dict(sun_dir=(0.35, 0.8, 0.45)))])
+def test_random_triangles_ggx_progressive(oracle, n_tris, spp, sky):
+    """C2-style scene (diffuse + GGX, sun + sky NEE) at reduced size, progressive accumulation over `spp` frames."""
+    s = scenes.random_triangles(n_tris)
+    W, H = 320, 180
+    r = make_backend(s, W, H, sky)
+    r.render_spp(s.camera, spp)
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(T.SceneConfig(**sky)), spp=spp)
+    assert_identical(r.framebuffer(), ref, "random%d" % n_tris)
+
+
+def test_emissive_instanced_scene_tri_light_nee(oracle):
+    """per-triangle material ids, two instances (one transformed), binned RIS over several light bins, p_sun = 0.5"""
+    from test_hostsim_parity import emissive_soup
+    s = emissive_soup()
+    W, H = 256, 144
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    r = make_backend(s, W, H, sky)
+    o = oracle.OracleScene(s)
+    assert np.array_equal(r.lights(), o.lights()), "host light pre-pass (collect + equalize bins) differs"
+    assert len(o.lights()) > 16
+    r.render_spp(s.camera, 3)
+    ref, _ = o.render(W, H, s.camera, load_sky_fit(T.SceneConfig(**sky)), spp=3)
+    assert_identical(r.framebuffer(), ref, "emissive instanced")
+
+
+def test_transmission_option(oracle):
+    s = scenes.random_triangles(4000)
+    for j, m in enumerate(s.materials):
+        if j % 2 == 1:
+            m.specular_transmission, m.metallic = 0.8, 0.0
+            m.flags = T.BASE_MATERIAL_NOALPHA | T.BASE_MATERIAL_EXTENDED | (T.BASE_MATERIAL_ONESIDED if j % 4 == 1 else 0)
+    W, H = 192, 108
+    r = make_backend(s, W, H, transmission=1)
+    r.render_spp(s.camera, 2)
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=2, transmission=1)
+    assert_identical(r.framebuffer(), ref, "transmission")
+
+
+def test_batch_spp_equals_sequential_frames(oracle):
+    """batch_spp = k in one frame is defined as k frames of batch_spp = 1 (the race-free reading of the reference's
+    z-layers, SURVEY 5 'race detection'); also exercises several waves per frame."""
+    s = scenes.random_triangles(20000)
+    W, H = 160, 90
+    a = make_backend(s, W, H)
+    a.render_spp(s.camera, 8, batch_spp=1)
+    b = make_backend(s, W, H, wave_paths=3 * W * H)  # 8 layers in waves of 3 + 3 + 2
+    b.render_spp(s.camera, 8, batch_spp=8)
+    c = make_backend(s, W, H)
+    c.render_spp(s.camera, 8, batch_spp=3)  # 3 + 3 + 2 (next_frame_spp clamps the last frame)
+    fa_, fb, fc = a.framebuffer(), b.framebuffer(), c.framebuffer()
+    assert np.array_equal(fa_.view(np.uint32), fb.view(np.uint32))
+    assert np.array_equal(fa_.view(np.uint32), fc.view(np.uint32))
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=8)
+    assert_identical(fb, ref, "batch 8")
+    assert a.frame_state() == b.frame_state() == (8, 0, 8)
+
+
+def test_frame_counter_protocol(oracle):
+    """begin_frame / end_frame counters seed the RNG (vulkan/render_vulkan.cpp:1937-1941, 2152-2154)."""
+    s = scenes.cornell_box()
+    W, H = 128, 72
+    r = make_backend(s, W, H)
+    assert r.frame_state() == (0, 0, 0)
+    r.render_spp(s.camera, 3)
+    assert r.frame_state() == (3, 0, 3)
+    first = r.framebuffer()
+    # reset: frame_offset += frame_id, frame_id = 0 -> a different random sequence
+    r.render_spp(s.camera, 2)
+    assert r.frame_state() == (2, 3, 2)
+    second = r.framebuffer()
+    assert not np.array_equal(first, second)
+    o = oracle.OracleScene(s)
+    ref, _ = o.render(W, H, s.camera, load_sky_fit(), spp=2, frame_offset=3)
+    assert_identical(second, ref, "after reset")
+    # frozen reset keeps frame_offset
+    cfg = RenderConfiguration(s.camera, reset_accumulation=True, freeze_frame=True)
+    r.begin_frame(None, cfg); r.draw_frame(); r.end_frame()
+    assert r.frame_state() == (0, 3, 1)  # frozen: frame_id does not advance, accumulated_spp = frame_id + batch
+    ref, _ = o.render(W, H, s.camera, load_sky_fit(), spp=1, frame_offset=3)
+    assert_identical(r.framebuffer(), ref, "frozen frame")
+    # set_scene zeroes frame_id only; initialize zeroes both (:1556, :245-249)
+    r.set_scene(s)
+    assert r.frame_state()[:2] == (0, 3)
+    r.initialize(W, H)
+    assert r.frame_state()[:2] == (0, 0)
+
+
+def test_aov_output_channels(oracle):
+    s = scenes.random_triangles(5000)
+    W, H = 128, 72
+    for channel in (1, 2, 3):
+        r = make_backend(s, W, H)
+        r.params.output_channel = channel
+        r.render_spp(s.camera, 2)
+        p = T.RenderParams(output_channel=channel)
+        ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=2, params=p)
+        assert_identical(r.framebuffer(), ref, "output_channel %d" % channel)
+
+
+def test_render_params_depth_and_rr(oracle):
+    s = scenes.random_triangles(5000)
+    W, H = 128, 72
+    for depth, rr in ((1, 2), (3, 0), (5, 9)):
+        r = make_backend(s, W, H)
+        r.params.max_path_depth, r.params.rr_path_depth = depth, rr
+        r.render_spp(s.camera, 2)
+        p = T.RenderParams(max_path_depth=depth, rr_path_depth=rr)
+        ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=2, params=p)
+        assert_identical(r.framebuffer(), ref, "depth %d rr %d" % (depth, rr))
+
+
+def random_queries(n, seed, box=12.0):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((n, 8), np.float32)
+    q[:, 0:3] = rng.uniform(-box, box, (n, 3))
+    d = rng.normal(size=(n, 3))
+    q[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    q[:, 7] = rng.choice([1e20, 5.0, 0.5], n)
+    return q
+
+
+def test_ray_query_service_matches_oracle_and_bruteforce(oracle):
+    """RaytraceBackend::trace_ray / RQ_CLOSEST: (bary, instance+geometry, primitive, t) identical to the oracle's BVH and,
+    on a small scene, to a brute-force loop over all triangles (pins the conservative box culling)."""
+    s = scenes.random_triangles(3000)
+    r = make_backend(s, 64, 64)
+    o = oracle.OracleScene(s)
+    q = random_queries(20000, 5)
+    res, t = r.trace_ray(q)
+    ores, ot = o.trace_closest(q)
+    bres, bt = o.trace_closest(q, bruteforce=True)
+    assert (t >= 0).mean() > 0.05
+    assert np.array_equal(ores.view(np.uint32), bres.view(np.uint32)) and np.array_equal(ot, bt)
+    assert np.array_equal(res.view(np.uint32), ores.view(np.uint32))
+    assert np.array_equal(t, ot)
+    big = scenes.random_triangles(300000)
+    r.set_scene(big)
+    q = random_queries(200000, 6)
+    res, t = r.trace_ray(q)
+    ores, ot = oracle.OracleScene(big).trace_closest(q)
+    assert np.array_equal(res.view(np.uint32), ores.view(np.uint32)) and np.array_equal(t, ot)
+
+
+def test_empty_and_degenerate_inputs(oracle):
+    # a scene whose only geometry has zero-area triangles, plus rays that miss everything: pure sky image
+    s = scenes.Scene()
+    g = np.zeros((4, 3, 3), np.int64) + 1000
+    geo = scenes.Geometry(scenes.pack_qverts(g.reshape(-1, 3)), (2.0 ** -16,) * 3, (-16.0,) * 3)
+    s.materials = [T.BaseMaterial(flags=T.BASE_MATERIAL_NOALPHA)]
+    s.add_instance(s.add_pmesh(s.add_mesh([geo]), [0]))
+    s.camera = scenes.look_at_camera((0, 0, 5), (0, 0.3, 0))
+    W, H = 96, 64
+    r = make_backend(s, W, H)
+    r.render_spp(s.camera, 2)
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=2)
+    img = r.framebuffer()
+    assert_identical(img, ref, "degenerate")
+    assert (img[..., 3] == 0).all()  # alpha = 0 where bounce == 0 (pt_megakernel.glsl:736)
+    res, t = r.trace_ray(random_queries(100, 1))
+    assert (t == -1).all() and (res.view(np.int32)[:, 2:] == -1).all()
+    res, t = r.trace_ray(np.zeros((0, 8), np.float32))
+    assert res.shape == (0, 4)
+
+
+def test_error_behaviour():
+    s = scenes.cornell_box()
+    r = RenderCuda(device=0)
+    cfg = RenderConfiguration(s.camera, reset_accumulation=True)
+    with pytest.raises(RptrError):
+        r.begin_frame(None, cfg)  # before initialize
+    r.initialize(64, 64)
+    with pytest.raises(RptrError):
+        r.begin_frame(None, cfg)  # before set_scene
+    r.set_scene(s)
+    with pytest.raises(RptrError):
+        r.begin_frame(None, cfg)  # before update_config
+    r.update_config()
+    with pytest.raises(RptrError):
+        r.draw_frame()  # outside a frame
+    r.begin_frame(None, cfg)
+    r.draw_frame()
+    r.end_frame()
+    small = np.zeros(64 * 64 * 4 - 1, np.float32)
+    assert r.readback_framebuffer(small) == 0  # vulkan/render_vulkan.cpp:2262-2263
+    full = np.zeros(64 * 64 * 4, np.float32)
+    assert r.readback_framebuffer(full) == full.size
+    ldr = np.zeros(64 * 64 * 4, np.uint8)
+    assert r.readback_framebuffer(ldr) == ldr.size and ldr.max() > 0
+    textured = scenes.cornell_box()
+    textured.materials[0].roughness = float(np.frombuffer(np.uint32(0x80000001).tobytes(), np.float32)[0])
+    with pytest.raises(RptrError):
+        r.set_scene(textured)  # texture handles are not supported yet: fail loudly
+    with pytest.raises(RptrError):
+        r.set_option("no_such_option", 1)
+
+
+def test_screen_tiles_sum_to_the_single_gpu_image():
+    """Multi-GPU sharding (C5) on one device: ranks render interleaved row bands into zero-initialised full-size
+    accumulators; their element-wise sum (what the NCCL reduce computes) is bit-identical to the 1-GPU image."""
+    s = scenes.random_triangles(20000)
+    W, H = 200, 117  # deliberately not a multiple of the band height
+    full = make_backend(s, W, H)
+    full.render_spp(s.camera, 3)
+    ref = full.framebuffer()
+    for world in (2, 3):
+        total = np.zeros_like(ref)
+        owned = np.zeros((H, W), np.int32)
+        for rank in range(world):
+            r = make_backend(s, W, H, tile_world=world, tile_rank=rank, tile_rows=8)
+            r.render_spp(s.camera, 3)
+            part = r.framebuffer()
+            owned += (part[..., :3] != 0).any(-1)
+            total += part
+        assert owned.max() <= 1
+        assert np.array_equal(total.view(np.uint32), ref.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE full sizes (C2: 1M triangles, 1920x1080): size-independent properties + oracle on a region
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2_scene():
+    return scenes.random_triangles(1_000_000)
+
+
+def test_c2_full_size_region_against_oracle_and_determinism(oracle, c2_scene):
+    s = c2_scene
+    W, H = 1920, 1080
+    r = make_backend(s, W, H)
+    r.render_spp(s.camera, 2, batch_spp=2)
+    img = r.framebuffer()
+    c = r.counters()
+    assert c["samples"] == 2 * W * H
+    assert c["closest_rays"] >= c["samples"] and c["shaded_vertices"] > 0 and c["shadow_rays"] > 0
+    # determinism / idempotence: a second context gives the same bits
+    r2 = make_backend(s, W, H)
+    r2.render_spp(s.camera, 2, batch_spp=1)
+    assert np.array_equal(img.view(np.uint32), r2.framebuffer().view(np.uint32))
+    # oracle on a 480 x 96 window in the middle of the frame (full-size camera, same pixel ids)
+    x0, y0, x1, y1 = 720, 492, 1200, 588
+    ref = np.zeros((H, W, 4), np.float32)
+    oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=2, region=(x0, y0, x1, y1), out=ref)
+    assert_identical(img[y0:y1, x0:x1], ref[y0:y1, x0:x1], "C2 window")
+    # checksum of checksums: linearity of the tile decomposition at full size
+    parts = []
+    for rank in range(2):
+        t = make_backend(s, W, H, tile_world=2, tile_rank=rank, tile_rows=32)
+        t.render_spp(s.camera, 2, batch_spp=2)
+        parts.append(t.framebuffer())
+    assert np.array_equal((parts[0] + parts[1]).view(np.uint32), img.view(np.uint32))

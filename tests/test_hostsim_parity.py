@@ -1,0 +1,105 @@
+"""The code the CUDA kernels execute (csrc/rptr_shading.cuh, rptr_bvh.cuh are __host__ __device__; csrc/rptr_host.cpp is
+the product's scene ingestion) compiled for the CPU by tests/hostsim and compared BIT FOR BIT with the independent
+oracle: different source, different BVH, same arithmetic contract.  This is the CPU-runnable half of the parity gate;
+tests/test_gpu_parity.py repeats it on the device through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from realtimepathtracingresearchframework_b200 import load_sky_fit, scenes, types as T
+
+
+@pytest.fixture(scope="module")
+def H(hostsim, oracle):
+    lib = C.CDLL(hostsim)
+    lib.hostsim_scene_create.restype = C.c_void_p
+    lib.hostsim_scene_create.argtypes = [C.POINTER(T.SceneDesc), C.POINTER(T.LightSamplingConfig)]
+    lib.hostsim_scene_destroy.argtypes = [C.c_void_p]
+    lib.hostsim_render_sample.argtypes = [C.c_void_p, C.POINTER(oracle.OracleRenderArgs), C.c_uint32, oracle.f32p]
+    lib.hostsim_get_lights.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hostsim_num_lights.argtypes = [C.c_void_p]
+    return lib
+
+
+def emissive_soup(n=3000):
+    """random triangles with per-triangle material ids, a few emissive -> several light bins + p_sun = 0.5"""
+    s = scenes.Scene()
+    g = scenes.random_triangle_grid(n, seed=77, box=4.0, edge=0.6)
+    scale, base = 2.0 ** -16, -16.0
+    geo = scenes.Geometry(scenes.pack_qverts(g.reshape(-1, 3)), (scale,) * 3, (base + 2.0 ** -17,) * 3)
+    mesh = s.add_mesh([geo])
+    s.materials = [T.BaseMaterial(base_color=(0.7, 0.6, 0.5), roughness=0.4, ior=1.5, flags=T.BASE_MATERIAL_NOALPHA),
+                   T.BaseMaterial(base_color=(0.2, 0.5, 0.8), roughness=0.15, metallic=1.0, flags=T.BASE_MATERIAL_NOALPHA),
+                   T.BaseMaterial(base_color=(1.0, 0.9, 0.7), emission_intensity=25.0, flags=T.BASE_MATERIAL_NOALPHA),
+                   T.BaseMaterial(base_color=(0.4, 0.9, 0.4), emission_intensity=3.0, ior=1.0, flags=T.BASE_MATERIAL_NOALPHA)]
+    ids = (np.arange(n) % 2).astype(np.uint8)
+    ids[::37] = 2
+    ids[5::91] = 3
+    pm = s.add_pmesh(mesh, [0], tri_material_ids=ids)
+    s.add_instance(pm)
+    # a second, transformed instance of the same mesh (non-uniform scale + rotation + translation)
+    t = np.array([[0.8, -0.3, 0.1, 3.0], [0.2, 0.9, 0.0, -1.0], [0.0, 0.1, 1.1, 0.5]], np.float32)
+    s.add_instance(pm, t)
+    s.camera = scenes.look_at_camera((0, 1, 14), (0.5, 0, 0), fovy=50.0)
+    return s
+
+
+CASES = {
+    "cornell": (scenes.cornell_box, dict()),
+    "random20k": (lambda: scenes.random_triangles(20000), dict()),
+    "random20k_slanted_sun": (lambda: scenes.random_triangles(20000), dict(sun_dir=(0.35, 0.8, 0.45))),
+    "emissive_instanced": (emissive_soup, dict(sun_dir=(0.35, 0.8, 0.45))),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_product_code_matches_oracle_bit_for_bit(H, oracle, case):
+    make, sky = CASES[case]
+    s = make()
+    sp = load_sky_fit(T.SceneConfig(**sky))
+    o = oracle.OracleScene(s)
+    ls = T.LightSamplingConfig()
+    d = s.desc()
+    hs = H.hostsim_scene_create(C.byref(d), C.byref(ls))
+    assert hs
+    try:
+        n = H.hostsim_num_lights(hs)
+        arr = (T.TriLightData * max(n, 1))()
+        H.hostsim_get_lights(hs, arr)
+        assert np.array_equal(np.frombuffer(arr, np.float32).reshape(-1, 12)[:n], o.lights()), "binned light buffers differ"
+        W, Hh = 160, 90
+        for sample in (0, 3):
+            ref = o.render_sample(W, Hh, s.camera, sp, sample)
+            a = o._args(W, Hh, s.camera, sp)
+            img = np.zeros((Hh, W, 4), np.float32)
+            H.hostsim_render_sample(hs, C.byref(a), sample, oracle._fp(img))
+            assert np.isfinite(ref).all()
+            assert ref[..., :3].max() > 0
+            assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), "%d pixels differ" % (ref != img).any(-1).sum()
+    finally:
+        H.hostsim_scene_destroy(hs)
+
+
+def test_transmission_build_matches_oracle(H, oracle):
+    """GLTF_SUPPORT_TRANSMISSION[_ROUGHNESS] variant (pipeline_pt hit groups): thick (ONESIDED) + thin glass."""
+    s = scenes.random_triangles(4000)
+    for j, m in enumerate(s.materials):
+        if j % 4 == 1:
+            m.specular_transmission, m.metallic, m.flags = 0.9, 0.0, T.BASE_MATERIAL_NOALPHA | T.BASE_MATERIAL_ONESIDED | T.BASE_MATERIAL_EXTENDED
+        if j % 4 == 3:
+            m.specular_transmission, m.metallic, m.flags = 0.7, 0.0, T.BASE_MATERIAL_NOALPHA | T.BASE_MATERIAL_EXTENDED
+    sp = load_sky_fit(T.SceneConfig(sun_dir=(0.35, 0.8, 0.45)))
+    o = oracle.OracleScene(s)
+    ls = T.LightSamplingConfig()
+    d = s.desc()
+    hs = H.hostsim_scene_create(C.byref(d), C.byref(ls))
+    W, Hh = 128, 72
+    ref = o.render_sample(W, Hh, s.camera, sp, 1, transmission=1)
+    a = o._args(W, Hh, s.camera, sp, transmission=1)
+    img = np.zeros((Hh, W, 4), np.float32)
+    H.hostsim_render_sample(hs, C.byref(a), 1, oracle._fp(img))
+    H.hostsim_scene_destroy(hs)
+    assert np.array_equal(ref.view(np.uint32), img.view(np.uint32))
+    # and transmission really changes the image
+    assert not np.array_equal(ref, o.render_sample(W, Hh, s.camera, sp, 1, transmission=0))
