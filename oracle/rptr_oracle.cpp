@@ -73,6 +73,7 @@ struct Scene {
 // --- binned SAH BVH2 over padded triangle boxes ---------------------------------------------------------------
 struct BuildPrim { float bmin[3], bmax[3], c[3]; int id; };
 
+static float g_abs_pad = 0.0f; // 2^-18 * scene extent, set by build_bvh
 static void tri_bounds(const Tri &t, float *mn, float *mx) {
     V3 a = t.v0, b = t.v0 + t.e1, c = t.v0 + t.e2;
     float pa[3][3] = {{a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}};
@@ -80,7 +81,7 @@ static void tri_bounds(const Tri &t, float *mn, float *mx) {
         mn[k] = fminf(pa[0][k], fminf(pa[1][k], pa[2][k]));
         mx[k] = fmaxf(pa[0][k], fmaxf(pa[1][k], pa[2][k]));
         // conservative padding so that box culling never rejects a hit the triangle routine accepts
-        float pad = 1.52587890625e-05f * fmaxf(fabsf(mn[k]), fabsf(mx[k])) + 1e-30f;
+        float pad = 1.52587890625e-05f * fmaxf(fabsf(mn[k]), fabsf(mx[k])) + g_abs_pad + 1e-30f;
         mn[k] -= pad;
         mx[k] += pad;
     }
@@ -184,6 +185,12 @@ static void build_bvh(Scene &s) {
     s.nodes.clear();
     s.tri_order.clear();
     std::vector<BuildPrim> p(s.tris.size());
+    float extent = 0.0f;
+    for (const Tri &t : s.tris) {
+        V3 b = t.v0 + t.e1, c = t.v0 + t.e2;
+        extent = fmaxf(extent, fmaxf(max3(vabs(t.v0)), fmaxf(max3(vabs(b)), max3(vabs(c)))));
+    }
+    g_abs_pad = 3.814697265625e-06f * extent;
     for (size_t i = 0; i < s.tris.size(); ++i) {
         tri_bounds(s.tris[i], p[i].bmin, p[i].bmax);
         for (int k = 0; k < 3; ++k) p[i].c[k] = 0.5f * (p[i].bmin[k] + p[i].bmax[k]);

@@ -423,14 +423,21 @@ void build_bvh(HostScene &s) {
     if (s.tris.empty()) return;
     Builder b{s, {}};
     b.prims.resize(s.tris.size());
+    float extent = 0.0f; // largest |coordinate| of the scene: scale of the absolute part of the box padding
+    for (const Tri &t : s.tris)
+        extent = fmaxf(extent, fmaxf(fmaxf(fabsf(t.v0x), fabsf(t.v0y)), fabsf(t.v0z)) + fmaxf(fmaxf(fabsf(t.e1x), fabsf(t.e1y)), fabsf(t.e1z)) +
+                                   fmaxf(fmaxf(fabsf(t.e2x), fabsf(t.e2y)), fabsf(t.e2z)));
+    const float abs_pad = 3.814697265625e-06f * extent; // 2^-18 * extent
     for (size_t i = 0; i < s.tris.size(); ++i) {
         const Tri &t = s.tris[i];
         Prim &p = b.prims[i];
         const float v[3][3] = {{t.v0x, t.v0y, t.v0z}, {t.v0x + t.e1x, t.v0y + t.e1y, t.v0z + t.e1z}, {t.v0x + t.e2x, t.v0y + t.e2y, t.v0z + t.e2z}};
         for (int k = 0; k < 3; ++k) {
             float lo = fminf(v[0][k], fminf(v[1][k], v[2][k])), hi = fmaxf(v[0][k], fmaxf(v[1][k], v[2][k]));
-            // conservative padding (2^-16 relative): box culling may never reject what intersect_tri accepts
-            float pad = 1.52587890625e-05f * fmaxf(fabsf(lo), fabsf(hi)) + 1e-30f;
+            // conservative padding: box culling may never reject what intersect_tri accepts.  Both tests round at
+            // ulp(|origin|) ~ 6e-8 |origin|, so the pad has a part relative to the coordinates (2^-16) and a part
+            // relative to the scene extent (2^-18): safe for ray origins within ~16 scene extents.
+            float pad = 1.52587890625e-05f * fmaxf(fabsf(lo), fabsf(hi)) + abs_pad + 1e-30f;
             p.lo[k] = lo - pad;
             p.hi[k] = hi + pad;
             p.c[k] = 0.5f * (p.lo[k] + p.hi[k]);

@@ -227,10 +227,10 @@ def random_triangle_grid(n_tris, seed=0x5EED1A7B200, box=10.0, edge=0.15, scale=
     return np.clip(np.floor((v - base) / scale), 0, 0x1FFFFF).astype(np.int64)  # (n, 3, 3)
 
 
-def random_triangles(n_tris=1_000_000, n_geometries=16, seed=0x5EED1A7B200):
+def random_triangles(n_tris=1_000_000, n_geometries=16, seed=0x5EED1A7B200, box=10.0, edge=0.15):
     s = Scene()
     scale, base = 2.0 ** -16, -16.0
-    g = random_triangle_grid(n_tris, seed, scale=scale, base=base)
+    g = random_triangle_grid(n_tris, seed, box=box, edge=edge, scale=scale, base=base)
     per = (n_tris + n_geometries - 1) // n_geometries
     offset = (base + 2.0 ** -17,) * 3
     geoms = []

@@ -100,3 +100,22 @@ int hostsim_render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_
 }
 
 } // extern "C"
+
+// RQ_CLOSEST through the product's traversal code (tmin = q.mode_or_data reinterpreted as float when any != 0)
+extern "C" int hostsim_trace(const hostsim_scene *s, const rptr_render_ray_query *q, int32_t n, float *results, float *hit_t, int32_t any) {
+    BvhDev bvh{s->hs.nodes.data(), s->hs.leaf_tris.data(), (int32_t)s->hs.nodes.size(), (int32_t)s->hs.leaf_tris.size()};
+    for (int32_t i = 0; i < n; ++i) {
+        HitRec h;
+        TraceCounters cnt{0, 0};
+        float3 o = f3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), d = f3(q[i].dir[0], q[i].dir[1], q[i].dir[2]);
+        bool ok = any ? trace_ray<true>(bvh, o, d, 0.0f, q[i].t_max, h, cnt) : trace_ray<false>(bvh, o, d, 0.0f, q[i].t_max, h, cnt);
+        int32_t gi = -1, prim = -1;
+        if (ok) { gi = bvh.tris[h.tri].geom_inst; prim = bvh.tris[h.tri].prim; }
+        results[4 * i + 0] = ok ? h.u : 0.0f;
+        results[4 * i + 1] = ok ? h.v : 0.0f;
+        memcpy(&results[4 * i + 2], &gi, 4);
+        memcpy(&results[4 * i + 3], &prim, 4);
+        if (hit_t) hit_t[i] = ok ? h.t : -1.0f;
+    }
+    return 0;
+}

@@ -178,7 +178,7 @@ def random_queries(n, seed, box=12.0):
     rng = np.random.default_rng(seed)
     q = np.zeros((n, 8), np.float32)
     q[:, 0:3] = rng.uniform(-box, box, (n, 3))
-    d = rng.normal(size=(n, 3))
+    d = rng.uniform(-0.8 * box, 0.8 * box, (n, 3)) - q[:, 0:3]  # aim into the triangle cloud
     q[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
     q[:, 7] = rng.choice([1e20, 5.0, 0.5], n)
     return q
@@ -187,10 +187,10 @@ def random_queries(n, seed, box=12.0):
 def test_ray_query_service_matches_oracle_and_bruteforce(oracle):
     """RaytraceBackend::trace_ray / RQ_CLOSEST: (bary, instance+geometry, primitive, t) identical to the oracle's BVH and,
     on a small scene, to a brute-force loop over all triangles (pins the conservative box culling)."""
-    s = scenes.random_triangles(3000)
+    s = scenes.random_triangles(3000, box=2.0, edge=0.3)
     r = make_backend(s, 64, 64)
     o = oracle.OracleScene(s)
-    q = random_queries(20000, 5)
+    q = random_queries(20000, 5, box=2.5)
     res, t = r.trace_ray(q)
     ores, ot = o.trace_closest(q)
     bres, bt = o.trace_closest(q, bruteforce=True)

@@ -103,3 +103,42 @@ def test_transmission_build_matches_oracle(H, oracle):
     assert np.array_equal(ref.view(np.uint32), img.view(np.uint32))
     # and transmission really changes the image
     assert not np.array_equal(ref, o.render_sample(W, Hh, s.camera, sp, 1, transmission=0))
+
+
+def test_traversal_edge_rays_against_bruteforce(hostsim, oracle):
+    """The product's BVH traversal (fma slabs, padded boxes) against the oracle's brute-force loop over all triangles:
+    exactly axis-parallel rays (d.k == +-0, what sun shadow rays at the zenith produce), rays starting on surfaces,
+    rays along box faces of axis-aligned walls."""
+    lib = C.CDLL(hostsim)
+    lib.hostsim_scene_create.restype = C.c_void_p
+    lib.hostsim_scene_create.argtypes = [C.POINTER(T.SceneDesc), C.POINTER(T.LightSamplingConfig)]
+    lib.hostsim_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, oracle.f32p, oracle.f32p, C.c_int32]
+    rng = np.random.default_rng(3)
+    for s, box in ((scenes.cornell_box(), 1.0), (scenes.random_triangles(3000, box=2.0, edge=0.4), 2.5)):
+        o = oracle.OracleScene(s)
+        ls = T.LightSamplingConfig()
+        d = s.desc()
+        hs = lib.hostsim_scene_create(C.byref(d), C.byref(ls))
+        n = 6000
+        q = np.zeros((n, 8), np.float32)
+        q[:, 0:3] = rng.uniform(-box, box, (n, 3)) + (np.array([0, 1, 0]) if box == 1.0 else 0)
+        q[:, 7] = 1e20
+        axes = np.eye(3, dtype=np.float32)
+        for i in range(n):
+            k = i % 6
+            v = axes[k % 3] * (1 if k < 3 else -1)
+            if i % 4 == 1:
+                v = v + axes[(k + 1) % 3] * np.float32(rng.uniform(-1, 1))  # parallel to one axis plane only
+            if i % 4 == 2:
+                v = np.where(v == 0, np.float32(-0.0), v)  # negative zeros
+            q[i, 4:7] = v / np.linalg.norm(v)
+        # a third of the origins snapped onto grid planes of the geometry (on walls / box faces)
+        q[::3, 0] = np.round(q[::3, 0])
+        ref, tref = o.trace_closest(q, bruteforce=True)
+        got, tgot = np.zeros((n, 4), np.float32), np.zeros(n, np.float32)
+        lib.hostsim_trace(hs, q.ctypes.data, n, oracle._fp(got), oracle._fp(tgot), 0)
+        assert (tref >= 0).mean() > 0.2
+        assert np.array_equal(tref, tgot) and np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+        # oracle's own BVH too
+        ob, tob = o.trace_closest(q)
+        assert np.array_equal(tref, tob) and np.array_equal(ref.view(np.uint32), ob.view(np.uint32))
