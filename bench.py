@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--wave-paths", type=int, default=0)
+    ap.add_argument("--option", action="append", default=[], help="backend option name=value (rptr_cuda_set_option)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -174,6 +175,9 @@ def run_b200(args):
     r.set_option("stage_timing", 1)
     if args.wave_paths:
         r.set_option("wave_paths", args.wave_paths)
+    for kv in args.option:
+        k, v = kv.split("=")
+        r.set_option(k, int(v))
     if world > 1:
         r.set_option("tile_world", world)
         r.set_option("tile_rank", rank)

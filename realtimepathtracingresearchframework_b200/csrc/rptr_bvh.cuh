@@ -22,11 +22,17 @@ static_assert(sizeof(BvhNode) == 64, "BvhNode must be one 64-byte record");
 static_assert(sizeof(Tri) == 48, "Tri must be three 128-bit words");
 
 struct BvhDev {
-    const BvhNode *nodes;
-    const Tri *tris; // leaf order
+    const BvhNode *nodes; // breadth-first order: node 0 = root
+    const Tri *tris;      // leaf order
     int32_t n_nodes;
     int32_t n_tris;
+    // the first top_k nodes again, with the four 16-byte words of node i stored at word position w ^ ((i >> 1) & 3):
+    // the image a CTA of the trace kernel copies into shared memory (the XOR spreads random nodes over the banks)
+    const BvhNode *top_swizzled;
+    int32_t top_k;
 };
+
+#define RPTR_TOP_NODES_MAX 2048 // 128 KB of shared memory per CTA
 
 struct HitRec {
     float t, u, v;

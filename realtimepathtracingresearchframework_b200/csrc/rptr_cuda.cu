@@ -19,6 +19,7 @@
 
 #include "../../include/rptr_cuda.h"
 #include "rptr_host.hpp"
+#include "rptr_trace_kernels.cuh"
 
 using namespace rp;
 
@@ -36,7 +37,7 @@ struct Wave {
     float4 *sh_d;   //               dir.xyz, tmax
     float4 *sh_c;   //               contribution.rgb, bits(path slot)
     uint32_t *queue[2];
-    uint32_t *counts; // [2*d] = live paths entering bounce d, [2*d+1] = shadow rays of bounce d
+    uint32_t *counts; // per bounce d: [4d] live paths entering it, [4d+1] its shadow rays, [4d+2], [4d+3] fetch cursors
 };
 
 struct TileMap {
@@ -278,6 +279,7 @@ struct rptr_ctx {
     int transmission = 0;
     int64_t wave_paths = 8ll << 20;
     int stage_timing = 0;
+    int trace_kernel = 0; // 0 = persistent while-while (rptr_trace_kernels.cuh), 1 = one ray per thread (A/B reference)
     int tile_rank = 0, tile_world = 1, tile_rows = 8;
     // wave
     Wave wave{};
@@ -364,7 +366,7 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     CU(dev_alloc(ctx, &w.sh_c, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.queue[0], n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.queue[1], n, ctx->wave_allocs));
-    CU(dev_alloc(ctx, &w.counts, (size_t)2 * (depth + 2), ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.counts, (size_t)4 * (depth + 2), ctx->wave_allocs));
     ctx->wave_capacity = paths;
     ctx->wave_depth = depth;
     return 0;
@@ -443,6 +445,13 @@ int rptr_cuda_create(int device_ordinal, rptr_ctx **out) {
         return 1;
     }
     cudaMemset(ctx->dcounters, 0, sizeof(DevCounters));
+    const int top_bytes = RPTR_TOP_NODES_MAX * (int)sizeof(BvhNode);
+    if (cudaFuncSetAttribute(k_trace_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_trace_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess) {
+        fail(nullptr, "cannot reserve %d bytes of shared memory for the trace kernel: %s", top_bytes, cudaGetErrorString(cudaGetLastError()));
+        rptr_cuda_destroy(ctx);
+        return 1;
+    }
     *out = ctx;
     return 0;
 }
@@ -541,8 +550,20 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     if (!hs.nodes.empty()) CU(cudaMemcpy(d_nodes, hs.nodes.data(), hs.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
     CU(dev_alloc(ctx, &d_tris, hs.leaf_tris.size(), ctx->scene_allocs));
     if (!hs.leaf_tris.empty()) CU(cudaMemcpy(d_tris, hs.leaf_tris.data(), hs.leaf_tris.size() * sizeof(Tri), cudaMemcpyHostToDevice));
+    // swizzled image of the top of the (breadth-first ordered) tree for the trace kernel's shared-memory stage
+    const int32_t top_k = (int32_t)std::min<size_t>(hs.nodes.size(), RPTR_TOP_NODES_MAX);
+    std::vector<BvhNode> top(top_k > 0 ? top_k : 1);
+    for (int32_t i = 0; i < top_k; ++i) {
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(&hs.nodes[i]);
+        unsigned char *dst = reinterpret_cast<unsigned char *>(&top[i]);
+        const int sw = (i >> 1) & 3;
+        for (int wd = 0; wd < 4; ++wd) memcpy(dst + ((wd ^ sw) << 4), src + (wd << 4), 16);
+    }
+    BvhNode *d_top;
+    CU(dev_alloc(ctx, &d_top, top.size(), ctx->scene_allocs));
+    CU(cudaMemcpy(d_top, top.data(), top.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
     ctx->scene = SceneDev{d_gi, d_mat, d_lights};
-    ctx->bvh = BvhDev{d_nodes, d_tris, (int32_t)hs.nodes.size(), (int32_t)hs.leaf_tris.size()};
+    ctx->bvh = BvhDev{d_nodes, d_tris, (int32_t)hs.nodes.size(), (int32_t)hs.leaf_tris.size(), d_top, top_k};
     ctx->n_lights = (int32_t)hs.lights.size();
     ctx->lights_host = hs.lights;
     ctx->has_scene = true;
@@ -575,6 +596,7 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
         if (value < 1024) return fail(ctx, "wave_paths must be >= 1024");
         ctx->wave_paths = value;
     } else if (n == "stage_timing") ctx->stage_timing = value != 0;
+    else if (n == "trace_kernel") ctx->trace_kernel = (int)value;
     else if (n == "tile_rank") ctx->tile_rank = (int)value;
     else if (n == "tile_world") ctx->tile_world = (int)value;
     else if (n == "tile_rows") ctx->tile_rows = (int)value;
@@ -648,32 +670,45 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         if (layers_per_wave > fp.batch) layers_per_wave = fp.batch;
         if (ensure_wave(ctx, (size_t)layers_per_wave * tm.local_pixels, depth)) return 1;
         Wave &w = ctx->wave;
-        const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4);
+        // trace: one 1024-thread CTA per SM; dynamic smem = the staged top of the BVH (at least one node's worth)
+        const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4), g_pt = grid_for(ctx, 1);
+        const size_t top_smem = (size_t)(ctx->bvh.top_k > 0 ? ctx->bvh.top_k : 1) * sizeof(BvhNode);
         for (int32_t first = 0; first < fp.batch; first += (int32_t)layers_per_wave) {
             const int32_t nl = (int32_t)((fp.batch - first) < layers_per_wave ? (fp.batch - first) : layers_per_wave);
-            CU(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * 2 * (depth + 2), ctx->stream));
+            CU(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), ctx->stream));
             {
                 StageTimer t(ctx, 3);
                 k_raygen<<<g_light, 256, 0, ctx->stream>>>(fp, tm, w, first, nl);
                 ctx->launches++;
             }
             for (int d = 0; d < depth; ++d) {
+                // counts[4d] = live paths entering bounce d, [4d+1] = its shadow rays, [4d+2], [4d+3] = fetch cursors
                 const uint32_t *q = d == 0 ? nullptr : w.queue[d & 1];
                 uint32_t *nq = w.queue[(d + 1) & 1];
+                uint32_t *cn = w.counts + 4 * d;
                 {
                     StageTimer t(ctx, 0);
-                    k_trace<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, q, w.counts + 2 * d, ctx->dcounters);
+                    if (ctx->trace_kernel == 0) {
+                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, nullptr, nullptr};
+                        k_trace_persistent<false><<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
+                            ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
+                    } else
+                        k_trace<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, q, cn, ctx->dcounters);
                     ctx->launches++;
                 }
                 {
                     StageTimer t(ctx, 1);
-                    k_shade<<<g_trace, 128, 0, ctx->stream>>>(fp, ctx->scene, ctx->bvh, w, q, w.counts + 2 * d, nq, w.counts + 2 * (d + 1),
-                                                             w.counts + 2 * d + 1, ctx->dcounters);
+                    k_shade<<<g_trace, 128, 0, ctx->stream>>>(fp, ctx->scene, ctx->bvh, w, q, cn, nq, cn + 4, cn + 1, ctx->dcounters);
                     ctx->launches++;
                 }
                 if (fp.output_channel == 0 && d + 1 < depth) {
                     StageTimer t(ctx, 2);
-                    k_shadow<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, w.counts + 2 * d + 1, ctx->dcounters);
+                    if (ctx->trace_kernel == 0) {
+                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, w.sh_c, w.illum};
+                        k_trace_persistent<true><<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
+                            ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
+                    } else
+                        k_shadow<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, cn + 1, ctx->dcounters);
                     ctx->launches++;
                 }
             }

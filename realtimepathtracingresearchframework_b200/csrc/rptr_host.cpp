@@ -200,7 +200,7 @@ void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config
         const rptr_mesh_desc &mesh = d.meshes[d.pmeshes[inst.pmesh_id].mesh_id];
         for (int j = 0; j < mesh.n_geometries; ++j) total += (size_t)d.geometries[mesh.first_geometry + j].n_tris;
     }
-    if (total > 0x7ffffff0u) throw std::runtime_error("too many triangles after instancing");
+    if (total > 0x1ffffff0u) throw std::runtime_error("too many triangles after instancing (limit 2^29)");
     s.tris.reserve(total);
 
     std::vector<Emitter> emitters;
@@ -454,6 +454,29 @@ void build_bvh(HostScene &s) {
         nd.c0 = root.c; nd.n0 = root.n;
         nd.c1 = 0; nd.n1 = -1;
         s.nodes.push_back(nd);
+    }
+    // Relabel the nodes breadth-first: the top of the tree becomes the contiguous prefix [0, K) that the trace kernel
+    // stages into shared memory with one TMA bulk copy per CTA (rptr_trace_kernels.cuh).
+    {
+        const int32_t n = (int32_t)s.nodes.size();
+        std::vector<int32_t> order;
+        order.reserve(n);
+        order.push_back(0);
+        for (size_t head = 0; head < order.size(); ++head) {
+            const BvhNode &nd = s.nodes[order[head]];
+            if (nd.c0 >= 0 && nd.n0 == 0) order.push_back(nd.c0);
+            if (nd.c1 >= 0 && nd.n1 == 0) order.push_back(nd.c1);
+        }
+        std::vector<int32_t> new_index(n, -1);
+        for (int32_t i = 0; i < (int32_t)order.size(); ++i) new_index[order[i]] = i;
+        std::vector<BvhNode> bfs(order.size());
+        for (int32_t i = 0; i < (int32_t)order.size(); ++i) {
+            BvhNode nd = s.nodes[order[i]];
+            if (nd.c0 >= 0 && nd.n0 == 0) nd.c0 = new_index[nd.c0];
+            if (nd.c1 >= 0 && nd.n1 == 0) nd.c1 = new_index[nd.c1];
+            bfs[i] = nd;
+        }
+        s.nodes.swap(bfs);
     }
     s.bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }

@@ -1,0 +1,251 @@
+// rptr_trace_kernels.cuh -- the trace stage of the wavefront: persistent-threads BVH traversal.
+//
+// Ray lengths in the target scenes are close to exponentially distributed (a random triangle soup: neighbouring pixels
+// stop at unrelated depths), so a "one ray per thread, wait for the warp" kernel runs at ~14 % SIMD efficiency (ncu:
+// 4.6 active threads per instruction, profiles/r01_trace_v1.txt).  This kernel is a per-lane state machine instead; one
+// trip through its loop is at most one node step and one leaf step for the whole warp:
+//   * every lane owns one ray.  Lanes that have finished are refilled from the ray queue once at least
+//     RPTR_REFILL_LANES of them are idle (warp-aggregated fetch from a per-warp chunk: one global atomic per 256 rays);
+//   * NODE STEP: every lane whose current item is an inner node fetches it (4 x 128-bit words), slab-tests both child
+//     boxes and picks the next item;
+//   * a lane that reaches a leaf parks it in a register and keeps walking inner nodes from its stack (speculative
+//     traversal), so nearly all lanes take part in every node step;
+//   * LEAF STEP: run only when at least RPTR_LEAF_LANES lanes hold a parked leaf (warp ballot) or nobody has inner-node
+//     work left, so the ~4x more expensive triangle code also runs at high lane utilisation.
+// Semantics are those of trace_ray<> in rptr_bvh.cuh (same intersect_tri, same tie-break, order independent), which
+// stays as the host-executable statement of the contract.
+#pragma once
+#include "rptr_bvh.cuh"
+
+namespace rp {
+
+#define RPTR_EMPTY ((int32_t)0x80000000)
+#define RPTR_FETCH_CHUNK 256
+#define RPTR_REFILL_LANES 8
+#define RPTR_LEAF_LANES 16
+
+struct TraceIO {
+    // rays: closest -> Wave ray_o/ray_d indexed by path slot through `queue` (or identity); shadow -> sh_o/sh_d by index
+    const float4 *ray_o;
+    const float4 *ray_d;
+    const uint32_t *queue; // may be nullptr (identity)
+    const uint32_t *count; // number of rays (device resident)
+    uint32_t *work;        // global fetch cursor (zeroed before launch)
+    float4 *hit;           // closest: (t,u,v,bits(tri)) per path slot
+    const float4 *sh_c;    // shadow: (contribution.rgb, bits(path slot))
+    float4 *illum;         // shadow: illum.rgb += contribution when unoccluded
+};
+
+RPTR_HD int32_t leaf_ref(int32_t c, int32_t n) { return ~(((~c) << 2) | (n - 1)); } // c = ~first, n in [1,4]
+
+#if defined(__CUDACC__)
+
+// ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) + mbarrier, raw PTX ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+#define RPTR_TRACE_THREADS 1024 // one CTA per SM: 32 warps share one 128 KB image of the top of the BVH
+#define RPTR_TMA_CHUNK 32768u
+
+template <bool Any>
+__global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhDev bvh, TraceIO io, unsigned long long *c_rays,
+                                                                            unsigned long long *c_nodes, unsigned long long *c_tris) {
+    extern __shared__ __align__(128) unsigned char smem_top[]; // top_k swizzled nodes
+    __shared__ __align__(8) uint64_t top_bar;
+    const uint32_t n = *io.count;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // ---- stage the top of the tree: TMA bulk copies issued by one thread, completion through an mbarrier ----
+    const uint32_t top_bytes = (uint32_t)bvh.top_k * (uint32_t)sizeof(BvhNode);
+    if (threadIdx.x == 0) mbar_init(&top_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && n > 0) {
+        mbar_expect_tx(&top_bar, top_bytes);
+        for (uint32_t off = 0; off < top_bytes; off += RPTR_TMA_CHUNK)
+            tma_bulk_g2s(smem_top + off, reinterpret_cast<const unsigned char *>(bvh.top_swizzled) + off,
+                         min(RPTR_TMA_CHUNK, top_bytes - off), &top_bar);
+    }
+    if (n > 0) mbar_wait(&top_bar, 0);
+    const int32_t top_k = bvh.top_k;
+    uint32_t pool_pos = 0, pool_end = 0; // per-warp pool of ray indices (warp-uniform)
+    bool drained = false;                // the global queue has been exhausted (warp-uniform)
+
+    // per-lane ray state
+    bool have = false;
+    uint32_t ray_index = 0, slot = 0;
+    float3 o = f3(0.0f), d = f3(0.0f), inv = f3(0.0f), ood = f3(0.0f);
+    float tmin = 0.0f, tmax = 0.0f;
+    float best_t = 0.0f, best_u = 0.0f, best_v = 0.0f;
+    int32_t best_tri = -1, best_id = 0x7fffffff;
+    int32_t node = RPTR_EMPTY; // current item: inner node (>= 0), leaf reference (< 0) or RPTR_EMPTY
+    int32_t leaf = 0;          // parked leaf reference (< 0) or 0 = none
+    int32_t stack[64];
+    int sp = 0;
+    uint32_t n_nodes = 0, n_tris = 0, n_rays = 0;
+
+    for (;;) {
+        __syncwarp();
+        // ---- retire + refill --------------------------------------------------------------------------------------
+        const bool done = have && node == RPTR_EMPTY && leaf == 0;
+        const unsigned idle = __ballot_sync(FULL, !have || done);
+        const unsigned inner0 = __ballot_sync(FULL, have && node >= 0);
+        const unsigned parked0 = __ballot_sync(FULL, have && leaf != 0);
+        if (__popc(idle) >= RPTR_REFILL_LANES || (inner0 == 0 && parked0 == 0)) {
+            if (done) {
+                if (Any) {
+                    if (best_tri < 0) { // unoccluded: add the pending NEE contribution (one shadow ray per path and bounce)
+                        const float4 c = io.sh_c[ray_index];
+                        const uint32_t ps = __float_as_uint(c.w);
+                        float4 il = io.illum[ps];
+                        il.x = il.x + c.x; il.y = il.y + c.y; il.z = il.z + c.z;
+                        io.illum[ps] = il;
+                    }
+                } else {
+                    io.hit[slot] = f4(best_t, best_u, best_v, __int_as_float(best_tri));
+                }
+                have = false;
+            }
+            if (pool_pos >= pool_end && !drained) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(io.work, (uint32_t)RPTR_FETCH_CHUNK);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) drained = true;
+                else { pool_pos = base; pool_end = min(base + (uint32_t)RPTR_FETCH_CHUNK, n); }
+            }
+            const uint32_t avail = pool_end > pool_pos ? pool_end - pool_pos : 0u;
+            const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+            if (!have && rank < avail) {
+                ray_index = pool_pos + rank;
+                slot = (Any || !io.queue) ? ray_index : io.queue[ray_index];
+                const float4 ro = io.ray_o[Any ? ray_index : slot], rd = io.ray_d[Any ? ray_index : slot];
+                o = f3(ro.x, ro.y, ro.z); tmin = ro.w;
+                d = f3(rd.x, rd.y, rd.z); tmax = rd.w;
+                inv = f3(1.0f / slab_safe(d.x), 1.0f / slab_safe(d.y), 1.0f / slab_safe(d.z));
+                ood = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+                best_t = tmax; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
+                sp = 0;
+                leaf = 0;
+                node = bvh.n_nodes > 0 ? 0 : RPTR_EMPTY;
+                have = true;
+                n_rays++;
+            }
+            pool_pos += min(avail, (uint32_t)__popc(idle));
+            if (drained && !__any_sync(FULL, have)) break;
+        }
+        // ---- node step ----------------------------------------------------------------------------------------------
+        if (have && node >= 0) {
+            float4 q0, q1, q2, q3;
+            if (node < top_k) { // top of the tree: shared memory (LDS.128), words XOR-swizzled against bank conflicts
+                const unsigned char *sp_ = smem_top + (size_t)node * sizeof(BvhNode);
+                const int sw = (node >> 1) & 3;
+                q0 = *reinterpret_cast<const float4 *>(sp_ + ((0 ^ sw) << 4));
+                q1 = *reinterpret_cast<const float4 *>(sp_ + ((1 ^ sw) << 4));
+                q2 = *reinterpret_cast<const float4 *>(sp_ + ((2 ^ sw) << 4));
+                q3 = *reinterpret_cast<const float4 *>(sp_ + ((3 ^ sw) << 4));
+            } else {
+                const char *np = reinterpret_cast<const char *>(bvh.nodes + node);
+                q0 = ld128(np); q1 = ld128(np + 16); q2 = ld128(np + 32); q3 = ld128(np + 48);
+            }
+            n_nodes++;
+            const int32_t c0 = f2i(q3.x), c1 = f2i(q3.y), n0 = f2i(q3.z), n1 = f2i(q3.w);
+            float tn0, tn1 = 0.0f;
+            const bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, inv, ood, tmin, best_t, tn0);
+            const bool h1 = n1 >= 0 && slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, inv, ood, tmin, best_t, tn1);
+            const int32_t r0 = c0 < 0 ? leaf_ref(c0, n0) : c0;
+            const int32_t r1 = c1 < 0 ? leaf_ref(c1, n1) : c1;
+            if (h0 && h1) { // nearer child first
+                const bool first0 = tn0 <= tn1;
+                node = first0 ? r0 : r1;
+                stack[sp++] = first0 ? r1 : r0;
+            } else if (h0) {
+                node = r0;
+            } else if (h1) {
+                node = r1;
+            } else {
+                node = sp > 0 ? stack[--sp] : RPTR_EMPTY;
+            }
+            // park a leaf and go on with whatever the stack holds (speculative traversal)
+            if (node < 0 && node != RPTR_EMPTY && leaf == 0) {
+                leaf = node;
+                node = sp > 0 ? stack[--sp] : RPTR_EMPTY;
+            }
+        }
+        // ---- leaf step ------------------------------------------------------------------------------------------------
+        const unsigned parked = __ballot_sync(FULL, have && leaf != 0);
+        const unsigned inner = __ballot_sync(FULL, have && node >= 0);
+        if (parked != 0 && (__popc(parked) >= RPTR_LEAF_LANES || inner == 0)) {
+            if (have && leaf != 0) {
+                const int32_t ref = ~leaf;
+                const int32_t first = ref >> 2;
+                const int32_t cnt = (ref & 3) + 1;
+                bool occluded = false;
+                for (int32_t i = 0; i < cnt; ++i) {
+                    const char *tp = reinterpret_cast<const char *>(bvh.tris + first + i);
+                    const float4 a = ld128(tp), b = ld128(tp + 16), c4 = ld128(tp + 32);
+                    n_tris++;
+                    float t, u, v;
+                    if (!intersect_tri(f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c4.x), o, d, t, u, v)) continue;
+                    if (!(t > tmin && t < tmax)) continue;
+                    const int32_t id = f2i(c4.y);
+                    if (Any) {
+                        best_tri = first + i;
+                        occluded = true;
+                        break;
+                    }
+                    if (best_tri < 0 || t < best_t || (t == best_t && id < best_id)) {
+                        best_t = t; best_u = u; best_v = v; best_tri = first + i; best_id = id;
+                    }
+                }
+                leaf = 0;
+                if (Any && occluded) { // drop the rest of the traversal
+                    sp = 0;
+                    node = RPTR_EMPTY;
+                } else if (node < 0 && node != RPTR_EMPTY) { // the current item was a second leaf waiting for the slot
+                    leaf = node;
+                    node = sp > 0 ? stack[--sp] : RPTR_EMPTY;
+                }
+            }
+        }
+    }
+    // ---- counters ----
+    unsigned long long a = n_rays, b = n_nodes, c = n_tris;
+    for (int s = 16; s > 0; s >>= 1) {
+        a += __shfl_down_sync(FULL, a, s);
+        b += __shfl_down_sync(FULL, b, s);
+        c += __shfl_down_sync(FULL, c, s);
+    }
+    if (lane == 0) {
+        if (a) atomicAdd(c_rays, a);
+        if (b) atomicAdd(c_nodes, b);
+        if (c) atomicAdd(c_tris, c);
+    }
+}
+
+#endif // __CUDACC__
+
+} // namespace rp

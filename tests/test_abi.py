@@ -79,3 +79,18 @@ def test_write_and_read_pfm_roundtrip(cuda_lib_path, tmp_path):
     body = np.frombuffer(raw[len(b"PF\n7 5\n-1.0\n"):], "<f4").reshape(5, 7, 3)
     assert np.array_equal(body[0], img[4, :, :3])  # rows bottom to top, alpha dropped
     assert np.array_equal(backend.read_pfm(tmp_path / "x.pfm"), img[..., :3])
+
+
+def test_reference_side_adapter_compiles():
+    """host/render_cuda.{h,cpp} is the file a maintainer drops into the reference tree.  When the
+    reference tree is present (authoring container) check that it really compiles against the reference's own headers."""
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "librender")):
+        pytest.skip("reference tree not present")
+    src = os.path.join(ROOT, "realtimepathtracingresearchframework_b200", "host", "render_cuda.cpp")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++20", "-fsyntax-only", "-w", "-I", os.path.join(ROOT, "oracle", "ref_shim"), "-I", ref + "/util", "-I", ref + "/librender",
+           "-I", ref, "-I", ref + "/util/display", "-I", os.path.join(ROOT, "include"), src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
