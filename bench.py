@@ -264,7 +264,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (closest-hit trace): algorithmic bytes / event-timed duration ----
     peak, peak_src = peaks()
-    node_b, tri_b = 64, 48
+    node_b, tri_b = cnt["node_bytes"], cnt["tri_bytes"]
     trace_bytes = cnt["closest_rays"] * (32 + 32) + cnt["closest_nodes"] * node_b + cnt["closest_tris"] * tri_b
     ach = trace_bytes / (cnt["ms_trace"] * 1e-3) / 1e9 if cnt["ms_trace"] > 0 else None
     stage_ms = {k: cnt[k] for k in ("ms_trace", "ms_shade", "ms_shadow", "ms_other")}
@@ -274,7 +274,7 @@ def run_b200(args):
                 "per_launch": {"launches": cnt["trace_launches"], "avg_ms": cnt["ms_trace"] / max(1, cnt["trace_launches"]),
                                "avg_algorithmic_bytes": trace_bytes / max(1, cnt["trace_launches"])},
                 "per_ray": {"nodes": cnt["closest_nodes"] / max(1, cnt["closest_rays"]), "tris": cnt["closest_tris"] / max(1, cnt["closest_rays"]),
-                            "bytes": trace_bytes / max(1, cnt["closest_rays"])},
+                            "bytes": trace_bytes / max(1, cnt["closest_rays"]), "node_bytes": node_b, "tri_bytes": tri_b},
                 "per_sample": {"closest_rays": cnt["closest_rays"] / spl, "shadow_rays": cnt["shadow_rays"] / spl, "vertices": cnt["shaded_vertices"] / spl},
                 "stage_ms_rank0": stage_ms, "mrays_per_s": (cnt["closest_rays"] + cnt["shadow_rays"]) / (dev_ms * 1e-3) / 1e6 * world}
     line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

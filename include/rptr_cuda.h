@@ -37,6 +37,8 @@ typedef struct rptr_counters {
     double ms_shade;
     double ms_other;           /* raygen + resolve */
     uint64_t trace_launches;   /* number of closest-hit kernel launches timed in ms_trace */
+    uint64_t node_bytes;       /* size of one BVH node record fetched per node visit */
+    uint64_t tri_bytes;        /* size of one traversal triangle record fetched per triangle test */
 } rptr_counters;
 
 /* create_cuda_backend(Display&) / ~RenderBackend  (librender/render_backend.h:118-119, main.cpp:273-285).

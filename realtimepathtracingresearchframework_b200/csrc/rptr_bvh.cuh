@@ -11,28 +11,38 @@
 
 namespace rp {
 
-// 64-byte two-child node (both child boxes in the parent: one fetch decides both descents), read as 4 x 128-bit words:
-//   q0 = (c0min.xyz, c0max.x)  q1 = (c0max.yz, c1min.xy)  q2 = (c1min.z, c1max.xyz)  q3 = (c0, c1, n0, n1)
-struct alignas(64) BvhNode {
-    float c0min[3], c0max[3], c1min[3], c1max[3];
-    int32_t c0, c1; // >= 0: inner node index; < 0: leaf, first triangle = ~c
-    int32_t n0, n1; // triangle count when the child is a leaf, 0 for an inner child, -1 for "no child"
+#define RPTR_EMPTY ((int32_t)0x80000000)
+#define RPTR_BVH_WIDTH 4
+#define RPTR_STACK_SIZE 128
+#define RPTR_MAX_BVH_DEPTH 40 // builder guarantee: 3 pushes per level + 1 < RPTR_STACK_SIZE
+
+// 128-byte four-wide node, child boxes as structure of arrays, read as 7 x 128-bit words (the 8th is padding):
+//   w0 = lo.x[4]  w1 = lo.y[4]  w2 = lo.z[4]  w3 = hi.x[4]  w4 = hi.y[4]  w5 = hi.z[4]  w6 = child[4]
+// child[k] >= 0: inner node index; < 0: leaf reference ~((first_triangle << 2) | (count - 1)), count in [1, 4];
+// RPTR_EMPTY: unused slot (its box is inverted so it can never be hit).
+struct alignas(128) BvhNode {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int32_t child[4];
+    int32_t pad[4];
 };
-static_assert(sizeof(BvhNode) == 64, "BvhNode must be one 64-byte record");
+static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte record");
 static_assert(sizeof(Tri) == 48, "Tri must be three 128-bit words");
+
+RPTR_HD int32_t make_leaf_ref(int32_t first, int32_t count) { return ~((first << 2) | (count - 1)); }
+RPTR_HD bool is_leaf_ref(int32_t r) { return r < 0 && r != RPTR_EMPTY; }
 
 struct BvhDev {
     const BvhNode *nodes; // breadth-first order: node 0 = root
     const Tri *tris;      // leaf order
     int32_t n_nodes;
     int32_t n_tris;
-    // the first top_k nodes again, with the four 16-byte words of node i stored at word position w ^ ((i >> 1) & 3):
+    // the first top_k nodes again, with the eight 16-byte words of node i stored at word position w ^ (i & 7):
     // the image a CTA of the trace kernel copies into shared memory (the XOR spreads random nodes over the banks)
     const BvhNode *top_swizzled;
     int32_t top_k;
 };
 
-#define RPTR_TOP_NODES_MAX 2048 // 128 KB of shared memory per CTA
+#define RPTR_TOP_NODES_MAX 1024 // 128 KB of shared memory per CTA
 
 struct HitRec {
     float t, u, v;
@@ -86,7 +96,10 @@ RPTR_HD bool slab(float lox, float loy, float loz, float hix, float hiy, float h
     return tn <= tf && tf >= tmin && tn <= tmax;
 }
 
-// generic traversal; Any = stop at the first accepted triangle
+RPTR_HD float comp4(const float4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+// Reference traversal (host-executable statement of the contract; the GPU's persistent kernel in
+// rptr_trace_kernels.cuh visits the same tree in a different order with the same result).  Any = stop at the first hit.
 template <bool Any>
 RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float tmax, HitRec &best, TraceCounters &cnt) {
     best.tri = -1;
@@ -95,60 +108,57 @@ RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float 
     best.u = best.v = 0.0f;
     if (bvh.n_nodes == 0) return false;
     // 1/d for the fma slabs, with |d.k| clamped away from zero: an exactly axis-parallel ray (d.k == +-0, common for
-    // sun shadow rays) would otherwise give lo*inf - o*inf = NaN on one side of the slab and a wrong rejection.  With
-    // the clamp the slab interval of such an axis is (-huge, +huge) inside the slab and empty outside, as it should be.
+    // sun shadow rays) would otherwise give lo*inf - o*inf = NaN on one side of the slab and a wrong rejection.
     const float3 inv = f3(1.0f / slab_safe(d.x), 1.0f / slab_safe(d.y), 1.0f / slab_safe(d.z));
     const float3 ood = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-    int32_t stack[64];
+    int32_t stack[RPTR_STACK_SIZE];
     int sp = 0;
     int32_t cur = 0;
     for (;;) {
-        const char *np = reinterpret_cast<const char *>(bvh.nodes + cur);
-        const float4 q0 = ld128(np), q1 = ld128(np + 16), q2 = ld128(np + 32), q3 = ld128(np + 48);
-        cnt.nodes++;
-        const int32_t c0 = f2i(q3.x), c1 = f2i(q3.y), n0 = f2i(q3.z), n1 = f2i(q3.w);
-        float tn0, tn1 = 0.0f;
-        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, inv, ood, tmin, best.t, tn0);
-        bool h1 = n1 >= 0 && slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, inv, ood, tmin, best.t, tn1);
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const bool hs = side == 0 ? h0 : h1;
-            const int32_t c = side == 0 ? c0 : c1;
-            if (hs && c < 0) {
-                const int32_t first = ~c;
-                const int32_t n = side == 0 ? n0 : n1;
-                for (int32_t i = 0; i < n; ++i) {
-                    const char *tp = reinterpret_cast<const char *>(bvh.tris + first + i);
-                    const float4 a = ld128(tp), b = ld128(tp + 16), c4 = ld128(tp + 32);
-                    cnt.tris++;
-                    float t, u, v;
-                    if (!intersect_tri(f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c4.x), o, d, t, u, v)) continue;
-                    if (!(t > tmin && t < tmax)) continue;
-                    const int32_t id = f2i(c4.y);
-                    if (Any) {
-                        best.t = t; best.u = u; best.v = v; best.tri = first + i; best.id = id;
-                        return true;
-                    }
-                    if (best.tri < 0 || t < best.t || (t == best.t && id < best.id)) {
-                        best.t = t; best.u = u; best.v = v; best.tri = first + i; best.id = id;
-                    }
-                }
-                if (side == 0) h0 = false;
-                else h1 = false;
+        if (cur >= 0) {
+            const char *np = reinterpret_cast<const char *>(bvh.nodes + cur);
+            const float4 w0 = ld128(np), w1 = ld128(np + 16), w2 = ld128(np + 32), w3 = ld128(np + 48), w4 = ld128(np + 64),
+                         w5 = ld128(np + 80), w6 = ld128(np + 96);
+            cnt.nodes++;
+            // hit children, nearest first into `cur`, the others onto the stack
+            int32_t near_ref = RPTR_EMPTY;
+            float near_t = 0.0f;
+            for (int k = 0; k < RPTR_BVH_WIDTH; ++k) {
+                const int32_t ref = f2i(comp4(w6, k));
+                float tn;
+                if (ref == RPTR_EMPTY) continue;
+                if (!slab(comp4(w0, k), comp4(w1, k), comp4(w2, k), comp4(w3, k), comp4(w4, k), comp4(w5, k), inv, ood, tmin, best.t, tn)) continue;
+                if (near_ref == RPTR_EMPTY) {
+                    near_ref = ref; near_t = tn;
+                } else if (tn < near_t) {
+                    stack[sp++] = near_ref;
+                    near_ref = ref; near_t = tn;
+                } else
+                    stack[sp++] = ref;
             }
-        }
-        if (h0 && h1) {
-            const bool near0 = tn0 <= tn1;
-            stack[sp++] = near0 ? c1 : c0;
-            cur = near0 ? c0 : c1;
-        } else if (h0) {
-            cur = c0;
-        } else if (h1) {
-            cur = c1;
-        } else {
-            if (sp == 0) break;
-            cur = stack[--sp];
-        }
+            cur = near_ref != RPTR_EMPTY ? near_ref : (sp > 0 ? stack[--sp] : RPTR_EMPTY);
+        } else if (cur != RPTR_EMPTY) {
+            const int32_t ref = ~cur;
+            const int32_t first = ref >> 2, n = (ref & 3) + 1;
+            for (int32_t i = 0; i < n; ++i) {
+                const char *tp = reinterpret_cast<const char *>(bvh.tris + first + i);
+                const float4 a = ld128(tp), b = ld128(tp + 16), c4 = ld128(tp + 32);
+                cnt.tris++;
+                float t, u, v;
+                if (!intersect_tri(f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c4.x), o, d, t, u, v)) continue;
+                if (!(t > tmin && t < tmax)) continue;
+                const int32_t id = f2i(c4.y);
+                if (Any) {
+                    best.t = t; best.u = u; best.v = v; best.tri = first + i; best.id = id;
+                    return true;
+                }
+                if (best.tri < 0 || t < best.t || (t == best.t && id < best.id)) {
+                    best.t = t; best.u = u; best.v = v; best.tri = first + i; best.id = id;
+                }
+            }
+            cur = sp > 0 ? stack[--sp] : RPTR_EMPTY;
+        } else
+            break;
     }
     return best.tri >= 0;
 }

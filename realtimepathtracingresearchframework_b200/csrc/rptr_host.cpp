@@ -303,58 +303,63 @@ void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config
     build_bvh(s);
 }
 
-// ---- binned-SAH BVH2 build -----------------------------------------------------------------------------------------------
+// ---- BVH build: binned-SAH binary tree, collapsed to the 4-wide breadth-first layout of rptr_bvh.cuh ---------------------
 namespace {
 
 struct Prim { float lo[3], hi[3], c[3]; int32_t id; };
-struct ChildRef { int32_t c, n; float lo[3], hi[3]; };
+struct Node2 { // temporary binary node
+    float lo[3], hi[3];
+    int32_t left, right; // inner: child indices; leaf: left = ~first_prim_slot, right = count
+};
 struct Builder {
-    HostScene &s;
     std::vector<Prim> prims;
+    std::vector<Node2> nodes;
+    int sah_depth_limit = 32;
     static constexpr int NB = 16;
     static constexpr int MAX_LEAF = 4;
     static float half_area(const float *lo, const float *hi) {
         float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
         return dx * dy + dy * dz + dz * dx;
     }
-    ChildRef build(int lo, int hi, int depth) {
-        ChildRef r;
-        float cmin[3], cmax[3];
-        for (int k = 0; k < 3; ++k) { r.lo[k] = 1e30f; r.hi[k] = -1e30f; cmin[k] = 1e30f; cmax[k] = -1e30f; }
+    int32_t build(int lo, int hi, int depth) {
+        const int32_t idx = (int32_t)nodes.size();
+        nodes.push_back(Node2());
+        float blo[3], bhi[3], cmin[3], cmax[3];
+        for (int k = 0; k < 3; ++k) { blo[k] = 1e30f; bhi[k] = -1e30f; cmin[k] = 1e30f; cmax[k] = -1e30f; }
         for (int i = lo; i < hi; ++i)
             for (int k = 0; k < 3; ++k) {
-                r.lo[k] = fminf(r.lo[k], prims[i].lo[k]);
-                r.hi[k] = fmaxf(r.hi[k], prims[i].hi[k]);
+                blo[k] = fminf(blo[k], prims[i].lo[k]);
+                bhi[k] = fmaxf(bhi[k], prims[i].hi[k]);
                 cmin[k] = fminf(cmin[k], prims[i].c[k]);
                 cmax[k] = fmaxf(cmax[k], prims[i].c[k]);
             }
+        for (int k = 0; k < 3; ++k) { nodes[idx].lo[k] = blo[k]; nodes[idx].hi[k] = bhi[k]; }
         const int n = hi - lo;
         auto leaf = [&]() {
-            r.c = ~(int32_t)s.leaf_tris.size();
-            r.n = n;
-            for (int i = lo; i < hi; ++i) s.leaf_tris.push_back(s.tris[prims[i].id]);
-            return r;
+            nodes[idx].left = ~lo;
+            nodes[idx].right = n;
+            return idx;
         };
         if (n == 1) return leaf();
         int best_axis = -1, best_bin = -1;
         float best_cost = 1e30f;
-        if (depth < 48) {
+        if (depth < sah_depth_limit) {
             for (int ax = 0; ax < 3; ++ax) {
                 const float ext = cmax[ax] - cmin[ax];
                 if (!(ext > 0.0f)) continue;
-                float blo[NB][3], bhi[NB][3];
+                float bl[NB][3], bh[NB][3];
                 int cnt[NB];
                 for (int b = 0; b < NB; ++b) {
                     cnt[b] = 0;
-                    for (int k = 0; k < 3; ++k) { blo[b][k] = 1e30f; bhi[b][k] = -1e30f; }
+                    for (int k = 0; k < 3; ++k) { bl[b][k] = 1e30f; bh[b][k] = -1e30f; }
                 }
                 const float sc = (float)NB / ext;
                 for (int i = lo; i < hi; ++i) {
                     int b = std::min(NB - 1, std::max(0, (int)((prims[i].c[ax] - cmin[ax]) * sc)));
                     cnt[b]++;
                     for (int k = 0; k < 3; ++k) {
-                        blo[b][k] = fminf(blo[b][k], prims[i].lo[k]);
-                        bhi[b][k] = fmaxf(bhi[b][k], prims[i].hi[k]);
+                        bl[b][k] = fminf(bl[b][k], prims[i].lo[k]);
+                        bh[b][k] = fmaxf(bh[b][k], prims[i].hi[k]);
                     }
                 }
                 float ra[NB];
@@ -362,7 +367,7 @@ struct Builder {
                 float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
                 int c = 0;
                 for (int b = NB - 1; b > 0; --b) {
-                    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], blo[b][k]); mx[k] = fmaxf(mx[k], bhi[b][k]); }
+                    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], bl[b][k]); mx[k] = fmaxf(mx[k], bh[b][k]); }
                     c += cnt[b];
                     ra[b] = c ? half_area(mn, mx) : 0.0f;
                     rc[b] = c;
@@ -370,7 +375,7 @@ struct Builder {
                 for (int k = 0; k < 3; ++k) { mn[k] = 1e30f; mx[k] = -1e30f; }
                 c = 0;
                 for (int b = 0; b < NB - 1; ++b) {
-                    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], blo[b][k]); mx[k] = fmaxf(mx[k], bhi[b][k]); }
+                    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], bl[b][k]); mx[k] = fmaxf(mx[k], bh[b][k]); }
                     c += cnt[b];
                     if (c == 0 || rc[b + 1] == 0) continue;
                     float cost = half_area(mn, mx) * (float)c + ra[b + 1] * (float)rc[b + 1];
@@ -381,10 +386,15 @@ struct Builder {
         int mid;
         if (best_axis < 0) {
             if (n <= MAX_LEAF) return leaf();
-            mid = lo + n / 2; // coincident centroids or depth cap: median split in current order
+            // coincident centroids or past the SAH depth limit: balanced median split along the widest centroid axis
+            int ax = 0;
+            if (cmax[1] - cmin[1] > cmax[ax] - cmin[ax]) ax = 1;
+            if (cmax[2] - cmin[2] > cmax[ax] - cmin[ax]) ax = 2;
+            mid = lo + n / 2;
+            std::nth_element(prims.begin() + lo, prims.begin() + mid, prims.begin() + hi, [ax](const Prim &a, const Prim &b) { return a.c[ax] < b.c[ax]; });
         } else {
-            const float parent = half_area(r.lo, r.hi);
-            // SAH termination: traversal step cost 1.2 box-pair tests vs 1 per triangle
+            const float parent = half_area(blo, bhi);
+            // SAH termination: one traversal step costs about 1.2 triangle tests
             if (n <= MAX_LEAF && (float)n * parent <= 1.2f * parent + best_cost) return leaf();
             const float sc = (float)NB / (cmax[best_axis] - cmin[best_axis]);
             const float cm = cmin[best_axis];
@@ -395,23 +405,78 @@ struct Builder {
             mid = (int)(it - prims.begin());
             if (mid == lo || mid == hi) mid = lo + n / 2;
         }
-        const int32_t idx = (int32_t)s.nodes.size();
-        s.nodes.push_back(BvhNode());
-        ChildRef a = build(lo, mid, depth + 1);
-        ChildRef b = build(mid, hi, depth + 1);
-        BvhNode &nd = s.nodes[idx];
-        for (int k = 0; k < 3; ++k) {
-            nd.c0min[k] = a.lo[k]; nd.c0max[k] = a.hi[k];
-            nd.c1min[k] = b.lo[k]; nd.c1max[k] = b.hi[k];
-        }
-        nd.c0 = a.c; nd.n0 = a.n;
-        nd.c1 = b.c; nd.n1 = b.n;
-        s.sah_cost += half_area(r.lo, r.hi);
-        r.c = idx;
-        r.n = 0;
-        return r;
+        const int32_t l = build(lo, mid, depth + 1);
+        const int32_t r = build(mid, hi, depth + 1);
+        nodes[idx].left = l;
+        nodes[idx].right = r;
+        return idx;
     }
 };
+
+// collapse the binary tree into 4-wide nodes, emitted breadth-first; returns the depth of the wide tree
+int collapse(const Builder &b, HostScene &s) {
+    struct Item { int32_t node2; int32_t depth; };
+    std::vector<Item> queue;
+    s.nodes.clear();
+    s.leaf_tris.clear();
+    s.sah_cost = 0.0f;
+    auto is_leaf2 = [&](int32_t i) { return b.nodes[i].left < 0; };
+    auto area = [&](int32_t i) { return Builder::half_area(b.nodes[i].lo, b.nodes[i].hi); };
+    auto emit_leaf = [&](int32_t i) {
+        const int first_slot = ~b.nodes[i].left, n = b.nodes[i].right;
+        const int32_t first = (int32_t)s.leaf_tris.size();
+        for (int k = 0; k < n; ++k) s.leaf_tris.push_back(s.tris[b.prims[first_slot + k].id]);
+        return make_leaf_ref(first, n);
+    };
+    int max_depth = 0;
+    if (is_leaf2(0)) { // a single leaf: one node with one used slot
+        queue.push_back(Item{-1, 0});
+    } else
+        queue.push_back(Item{0, 0});
+    for (size_t head = 0; head < queue.size(); ++head) {
+        const Item it = queue[head];
+        max_depth = std::max(max_depth, (int)it.depth);
+        int32_t kids[RPTR_BVH_WIDTH];
+        int nk = 0;
+        if (it.node2 < 0) {
+            kids[nk++] = 0;
+        } else {
+            kids[nk++] = b.nodes[it.node2].left;
+            kids[nk++] = b.nodes[it.node2].right;
+            while (nk < RPTR_BVH_WIDTH) { // open the inner child with the largest surface area
+                int pick = -1;
+                float best = -1.0f;
+                for (int k = 0; k < nk; ++k)
+                    if (!is_leaf2(kids[k]) && area(kids[k]) > best) { best = area(kids[k]); pick = k; }
+                if (pick < 0) break;
+                const int32_t open = kids[pick];
+                kids[pick] = b.nodes[open].left;
+                kids[nk++] = b.nodes[open].right;
+            }
+        }
+        BvhNode nd;
+        memset(&nd, 0, sizeof(nd));
+        for (int k = 0; k < RPTR_BVH_WIDTH; ++k) {
+            nd.lox[k] = nd.loy[k] = nd.loz[k] = 1e30f;
+            nd.hix[k] = nd.hiy[k] = nd.hiz[k] = -1e30f;
+            nd.child[k] = RPTR_EMPTY;
+        }
+        // children of the queue items appended so far = index the child node will get
+        for (int k = 0; k < nk; ++k) {
+            const Node2 &c = b.nodes[kids[k]];
+            nd.lox[k] = c.lo[0]; nd.loy[k] = c.lo[1]; nd.loz[k] = c.lo[2];
+            nd.hix[k] = c.hi[0]; nd.hiy[k] = c.hi[1]; nd.hiz[k] = c.hi[2];
+            if (is_leaf2(kids[k])) nd.child[k] = emit_leaf(kids[k]);
+            else {
+                nd.child[k] = (int32_t)queue.size();
+                queue.push_back(Item{kids[k], it.depth + 1});
+            }
+            s.sah_cost += area(kids[k]);
+        }
+        s.nodes.push_back(nd);
+    }
+    return max_depth + 1;
+}
 
 } // namespace
 
@@ -421,7 +486,7 @@ void build_bvh(HostScene &s) {
     s.leaf_tris.clear();
     s.sah_cost = 0.0f;
     if (s.tris.empty()) return;
-    Builder b{s, {}};
+    Builder b;
     b.prims.resize(s.tris.size());
     float extent = 0.0f; // largest |coordinate| of the scene: scale of the absolute part of the box padding
     for (const Tri &t : s.tris)
@@ -444,39 +509,21 @@ void build_bvh(HostScene &s) {
         }
         p.id = (int32_t)i;
     }
-    s.nodes.reserve(s.tris.size());
-    s.leaf_tris.reserve(s.tris.size());
-    ChildRef root = b.build(0, (int)b.prims.size(), 0);
-    if (root.c < 0) { // a single leaf: wrap it into a root node with an empty second child
-        BvhNode nd;
-        memset(&nd, 0, sizeof(nd));
-        for (int k = 0; k < 3; ++k) { nd.c0min[k] = root.lo[k]; nd.c0max[k] = root.hi[k]; nd.c1min[k] = 1e30f; nd.c1max[k] = -1e30f; }
-        nd.c0 = root.c; nd.n0 = root.n;
-        nd.c1 = 0; nd.n1 = -1;
-        s.nodes.push_back(nd);
-    }
-    // Relabel the nodes breadth-first: the top of the tree becomes the contiguous prefix [0, K) that the trace kernel
-    // stages into shared memory with one TMA bulk copy per CTA (rptr_trace_kernels.cuh).
-    {
-        const int32_t n = (int32_t)s.nodes.size();
-        std::vector<int32_t> order;
-        order.reserve(n);
-        order.push_back(0);
-        for (size_t head = 0; head < order.size(); ++head) {
-            const BvhNode &nd = s.nodes[order[head]];
-            if (nd.c0 >= 0 && nd.n0 == 0) order.push_back(nd.c0);
-            if (nd.c1 >= 0 && nd.n1 == 0) order.push_back(nd.c1);
+    // The traversal stack holds RPTR_STACK_SIZE entries (3 pushes per level): rebuild with an earlier switch to balanced
+    // median splits until the wide tree is at most RPTR_MAX_BVH_DEPTH deep (never needed for sane inputs).
+    for (int limit = 32;; limit -= 8) {
+        std::vector<Prim> keep = b.prims;
+        b.nodes.clear();
+        b.nodes.reserve(2 * s.tris.size());
+        b.sah_depth_limit = limit;
+        b.build(0, (int)b.prims.size(), 0);
+        s.leaf_tris.reserve(s.tris.size());
+        const int depth = collapse(b, s);
+        if (depth <= RPTR_MAX_BVH_DEPTH || limit <= 0) {
+            if (depth > RPTR_MAX_BVH_DEPTH) throw std::runtime_error("BVH too deep for the traversal stack");
+            break;
         }
-        std::vector<int32_t> new_index(n, -1);
-        for (int32_t i = 0; i < (int32_t)order.size(); ++i) new_index[order[i]] = i;
-        std::vector<BvhNode> bfs(order.size());
-        for (int32_t i = 0; i < (int32_t)order.size(); ++i) {
-            BvhNode nd = s.nodes[order[i]];
-            if (nd.c0 >= 0 && nd.n0 == 0) nd.c0 = new_index[nd.c0];
-            if (nd.c1 >= 0 && nd.n1 == 0) nd.c1 = new_index[nd.c1];
-            bfs[i] = nd;
-        }
-        s.nodes.swap(bfs);
+        b.prims.swap(keep);
     }
     s.bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }

@@ -19,7 +19,6 @@
 
 namespace rp {
 
-#define RPTR_EMPTY ((int32_t)0x80000000)
 #define RPTR_FETCH_CHUNK 256
 #define RPTR_REFILL_LANES 8
 #define RPTR_LEAF_LANES 16
@@ -36,7 +35,6 @@ struct TraceIO {
     float4 *illum;         // shadow: illum.rgb += contribution when unoccluded
 };
 
-RPTR_HD int32_t leaf_ref(int32_t c, int32_t n) { return ~(((~c) << 2) | (n - 1)); } // c = ~first, n in [1,4]
 
 #if defined(__CUDACC__)
 
@@ -104,7 +102,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     int32_t best_tri = -1, best_id = 0x7fffffff;
     int32_t node = RPTR_EMPTY; // current item: inner node (>= 0), leaf reference (< 0) or RPTR_EMPTY
     int32_t leaf = 0;          // parked leaf reference (< 0) or 0 = none
-    int32_t stack[64];
+    int32_t stack[RPTR_STACK_SIZE];
     int sp = 0;
     uint32_t n_nodes = 0, n_tris = 0, n_rays = 0;
 
@@ -159,36 +157,50 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         }
         // ---- node step ----------------------------------------------------------------------------------------------
         if (have && node >= 0) {
-            float4 q0, q1, q2, q3;
+            float4 w0, w1, w2, w3, w4, w5, w6;
             if (node < top_k) { // top of the tree: shared memory (LDS.128), words XOR-swizzled against bank conflicts
                 const unsigned char *sp_ = smem_top + (size_t)node * sizeof(BvhNode);
-                const int sw = (node >> 1) & 3;
-                q0 = *reinterpret_cast<const float4 *>(sp_ + ((0 ^ sw) << 4));
-                q1 = *reinterpret_cast<const float4 *>(sp_ + ((1 ^ sw) << 4));
-                q2 = *reinterpret_cast<const float4 *>(sp_ + ((2 ^ sw) << 4));
-                q3 = *reinterpret_cast<const float4 *>(sp_ + ((3 ^ sw) << 4));
+                const int sw = node & 7;
+                w0 = *reinterpret_cast<const float4 *>(sp_ + ((0 ^ sw) << 4));
+                w1 = *reinterpret_cast<const float4 *>(sp_ + ((1 ^ sw) << 4));
+                w2 = *reinterpret_cast<const float4 *>(sp_ + ((2 ^ sw) << 4));
+                w3 = *reinterpret_cast<const float4 *>(sp_ + ((3 ^ sw) << 4));
+                w4 = *reinterpret_cast<const float4 *>(sp_ + ((4 ^ sw) << 4));
+                w5 = *reinterpret_cast<const float4 *>(sp_ + ((5 ^ sw) << 4));
+                w6 = *reinterpret_cast<const float4 *>(sp_ + ((6 ^ sw) << 4));
             } else {
                 const char *np = reinterpret_cast<const char *>(bvh.nodes + node);
-                q0 = ld128(np); q1 = ld128(np + 16); q2 = ld128(np + 32); q3 = ld128(np + 48);
+                w0 = ld128(np); w1 = ld128(np + 16); w2 = ld128(np + 32); w3 = ld128(np + 48);
+                w4 = ld128(np + 64); w5 = ld128(np + 80); w6 = ld128(np + 96);
             }
             n_nodes++;
-            const int32_t c0 = f2i(q3.x), c1 = f2i(q3.y), n0 = f2i(q3.z), n1 = f2i(q3.w);
-            float tn0, tn1 = 0.0f;
-            const bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, inv, ood, tmin, best_t, tn0);
-            const bool h1 = n1 >= 0 && slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, inv, ood, tmin, best_t, tn1);
-            const int32_t r0 = c0 < 0 ? leaf_ref(c0, n0) : c0;
-            const int32_t r1 = c1 < 0 ? leaf_ref(c1, n1) : c1;
-            if (h0 && h1) { // nearer child first
-                const bool first0 = tn0 <= tn1;
-                node = first0 ? r0 : r1;
-                stack[sp++] = first0 ? r1 : r0;
-            } else if (h0) {
-                node = r0;
-            } else if (h1) {
-                node = r1;
-            } else {
-                node = sp > 0 ? stack[--sp] : RPTR_EMPTY;
-            }
+            // four slab tests; a missed (or unused: inverted box) child gets key +inf and reference EMPTY
+            const float INF = __int_as_float(0x7f800000);
+            float t0, t1, t2, t3;
+            int32_t r0 = f2i(w6.x), r1 = f2i(w6.y), r2 = f2i(w6.z), r3 = f2i(w6.w);
+            if (!slab(w0.x, w1.x, w2.x, w3.x, w4.x, w5.x, inv, ood, tmin, best_t, t0)) { t0 = INF; r0 = RPTR_EMPTY; }
+            if (!slab(w0.y, w1.y, w2.y, w3.y, w4.y, w5.y, inv, ood, tmin, best_t, t1)) { t1 = INF; r1 = RPTR_EMPTY; }
+            if (!slab(w0.z, w1.z, w2.z, w3.z, w4.z, w5.z, inv, ood, tmin, best_t, t2)) { t2 = INF; r2 = RPTR_EMPTY; }
+            if (!slab(w0.w, w1.w, w2.w, w3.w, w4.w, w5.w, inv, ood, tmin, best_t, t3)) { t3 = INF; r3 = RPTR_EMPTY; }
+            // 5-comparator sorting network on (t, ref): nearest first
+#define RPTR_CSWAP(ta, ra, tb, rb)                                  \
+    {                                                               \
+        const bool sw_ = tb < ta;                                   \
+        const float tl_ = sw_ ? tb : ta, th_ = sw_ ? ta : tb;       \
+        const int32_t rl_ = sw_ ? rb : ra, rh_ = sw_ ? ra : rb;     \
+        ta = tl_; tb = th_; ra = rl_; rb = rh_;                     \
+    }
+            RPTR_CSWAP(t0, r0, t1, r1)
+            RPTR_CSWAP(t2, r2, t3, r3)
+            RPTR_CSWAP(t0, r0, t2, r2)
+            RPTR_CSWAP(t1, r1, t3, r3)
+            RPTR_CSWAP(t1, r1, t2, r2)
+#undef RPTR_CSWAP
+            // continue with the nearest hit, push the others farthest first
+            if (r3 != RPTR_EMPTY) stack[sp++] = r3;
+            if (r2 != RPTR_EMPTY) stack[sp++] = r2;
+            if (r1 != RPTR_EMPTY) stack[sp++] = r1;
+            node = r0 != RPTR_EMPTY ? r0 : (sp > 0 ? stack[--sp] : RPTR_EMPTY);
             // park a leaf and go on with whatever the stack holds (speculative traversal)
             if (node < 0 && node != RPTR_EMPTY && leaf == 0) {
                 leaf = node;
