@@ -52,7 +52,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("RPTR_CUDA_LIB") or LIB_PATH  # RPTR_CUDA_LIB: tuning variants built by tools/sweep.py
     if not os.path.exists(p):
         raise RptrError("librptr_cuda.so is not built (%s); run `python -m realtimepathtracingresearchframework_b200.build`. "
                         "There is no CPU fallback." % p)

@@ -42,7 +42,9 @@ struct BvhDev {
     int32_t top_k;
 };
 
+#ifndef RPTR_TOP_NODES_MAX
 #define RPTR_TOP_NODES_MAX 1024 // 128 KB of shared memory per CTA
+#endif
 
 struct HitRec {
     float t, u, v;

@@ -445,7 +445,7 @@ int rptr_cuda_create(int device_ordinal, rptr_ctx **out) {
         return 1;
     }
     cudaMemset(ctx->dcounters, 0, sizeof(DevCounters));
-    const int top_bytes = RPTR_TOP_NODES_MAX * (int)sizeof(BvhNode);
+    const int top_bytes = (int)RPTR_TRACE_SMEM_BYTES;
     if (cudaFuncSetAttribute(k_trace_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_trace_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess) {
         fail(nullptr, "cannot reserve %d bytes of shared memory for the trace kernel: %s", top_bytes, cudaGetErrorString(cudaGetLastError()));
@@ -672,7 +672,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         Wave &w = ctx->wave;
         // trace: one 1024-thread CTA per SM; dynamic smem = the staged top of the BVH (at least one node's worth)
         const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4), g_pt = grid_for(ctx, 1);
-        const size_t top_smem = (size_t)(ctx->bvh.top_k > 0 ? ctx->bvh.top_k : 1) * sizeof(BvhNode);
+        const size_t top_smem = RPTR_TRACE_SMEM_BYTES; // staged BVH top (128 KB) + shared part of the traversal stacks (64 KB)
         for (int32_t first = 0; first < fp.batch; first += (int32_t)layers_per_wave) {
             const int32_t nl = (int32_t)((fp.batch - first) < layers_per_wave ? (fp.batch - first) : layers_per_wave);
             CU(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), ctx->stream));

@@ -19,9 +19,15 @@
 
 namespace rp {
 
+#ifndef RPTR_FETCH_CHUNK
 #define RPTR_FETCH_CHUNK 256
+#endif
+#ifndef RPTR_REFILL_LANES
 #define RPTR_REFILL_LANES 8
+#endif
+#ifndef RPTR_LEAF_LANES
 #define RPTR_LEAF_LANES 16
+#endif
 
 struct TraceIO {
     // rays: closest -> Wave ray_o/ray_d indexed by path slot through `queue` (or identity); shadow -> sh_o/sh_d by index
@@ -37,6 +43,13 @@ struct TraceIO {
 
 
 #if defined(__CUDACC__)
+
+// 256-bit read-only global load (sm_100: LDG.E.ENL2.256.CONSTANT); p must be 32-byte aligned
+__device__ __forceinline__ void ld256(const void *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
 
 // ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) + mbarrier, raw PTX ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -69,6 +82,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 #define RPTR_TRACE_THREADS 1024 // one CTA per SM: 32 warps share one 128 KB image of the top of the BVH
 #define RPTR_TMA_CHUNK 32768u
+// Traversal stack: the first RPTR_SMEM_STACK entries of every thread live in shared memory, laid out [entry][thread] so
+// that the bank only depends on the lane (any mix of stack depths in a warp is conflict free: one wavefront per push /
+// pop instead of up to 32 sectors through local memory); deeper entries spill to a local-memory array.
+#ifndef RPTR_SMEM_STACK
+#define RPTR_SMEM_STACK 16
+#endif
+#define RPTR_TRACE_SMEM_BYTES ((size_t)RPTR_TOP_NODES_MAX * sizeof(BvhNode) + (size_t)RPTR_SMEM_STACK * RPTR_TRACE_THREADS * sizeof(int32_t))
+#define RPTR_PUSH(v)                                                         \
+    {                                                                        \
+        if (sp < RPTR_SMEM_STACK) sstack[sp * RPTR_TRACE_THREADS] = (v);     \
+        else lstack[sp - RPTR_SMEM_STACK] = (v);                             \
+        ++sp;                                                                \
+    }
+#define RPTR_POP() (sp > 0 ? (--sp, sp < RPTR_SMEM_STACK ? sstack[sp * RPTR_TRACE_THREADS] : lstack[sp - RPTR_SMEM_STACK]) : RPTR_EMPTY)
 
 template <bool Any>
 __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhDev bvh, TraceIO io, unsigned long long *c_rays,
@@ -102,7 +129,8 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     int32_t best_tri = -1, best_id = 0x7fffffff;
     int32_t node = RPTR_EMPTY; // current item: inner node (>= 0), leaf reference (< 0) or RPTR_EMPTY
     int32_t leaf = 0;          // parked leaf reference (< 0) or 0 = none
-    int32_t stack[RPTR_STACK_SIZE];
+    int32_t lstack[RPTR_STACK_SIZE - RPTR_SMEM_STACK]; // overflow part of the traversal stack (local memory)
+    int32_t *sstack = reinterpret_cast<int32_t *>(smem_top + (size_t)RPTR_TOP_NODES_MAX * sizeof(BvhNode)) + threadIdx.x;
     int sp = 0;
     uint32_t n_nodes = 0, n_tris = 0, n_rays = 0;
 
@@ -168,10 +196,12 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 w4 = *reinterpret_cast<const float4 *>(sp_ + ((4 ^ sw) << 4));
                 w5 = *reinterpret_cast<const float4 *>(sp_ + ((5 ^ sw) << 4));
                 w6 = *reinterpret_cast<const float4 *>(sp_ + ((6 ^ sw) << 4));
-            } else {
+            } else { // 3 x 256-bit + 1 x 128-bit loads: every 32-byte sector of the node passes through L1 once
                 const char *np = reinterpret_cast<const char *>(bvh.nodes + node);
-                w0 = ld128(np); w1 = ld128(np + 16); w2 = ld128(np + 32); w3 = ld128(np + 48);
-                w4 = ld128(np + 64); w5 = ld128(np + 80); w6 = ld128(np + 96);
+                ld256(np, w0, w1);
+                ld256(np + 32, w2, w3);
+                ld256(np + 64, w4, w5);
+                w6 = ld128(np + 96);
             }
             n_nodes++;
             // four slab tests; a missed (or unused: inverted box) child gets key +inf and reference EMPTY
@@ -197,14 +227,14 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             RPTR_CSWAP(t1, r1, t2, r2)
 #undef RPTR_CSWAP
             // continue with the nearest hit, push the others farthest first
-            if (r3 != RPTR_EMPTY) stack[sp++] = r3;
-            if (r2 != RPTR_EMPTY) stack[sp++] = r2;
-            if (r1 != RPTR_EMPTY) stack[sp++] = r1;
-            node = r0 != RPTR_EMPTY ? r0 : (sp > 0 ? stack[--sp] : RPTR_EMPTY);
+            if (r3 != RPTR_EMPTY) RPTR_PUSH(r3);
+            if (r2 != RPTR_EMPTY) RPTR_PUSH(r2);
+            if (r1 != RPTR_EMPTY) RPTR_PUSH(r1);
+            node = r0 != RPTR_EMPTY ? r0 : RPTR_POP();
             // park a leaf and go on with whatever the stack holds (speculative traversal)
             if (node < 0 && node != RPTR_EMPTY && leaf == 0) {
                 leaf = node;
-                node = sp > 0 ? stack[--sp] : RPTR_EMPTY;
+                node = RPTR_POP();
             }
         }
         // ---- leaf step ------------------------------------------------------------------------------------------------
@@ -239,7 +269,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                     node = RPTR_EMPTY;
                 } else if (node < 0 && node != RPTR_EMPTY) { // the current item was a second leaf waiting for the slot
                     leaf = node;
-                    node = sp > 0 ? stack[--sp] : RPTR_EMPTY;
+                    node = RPTR_POP();
                 }
             }
         }

@@ -1,3 +1,3 @@
-nvidia-smi --query-gpu=index,name --format=csv,noheader
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 2 --spp 16 > gpurun_out/mg2.json 2> gpurun_out/mg2.err; tail -5 gpurun_out/mg2.err; cat gpurun_out/mg2.json | cut -c1-900
-timeout 300 python bench.py --impl reference --steps 1 --warmup 1 --cpu-seconds 6 > gpurun_out/ref.json 2> gpurun_out/ref.err; tail -2 gpurun_out/ref.err; cat gpurun_out/ref.json | cut -c1-600
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/t.log 2>&1; tail -2 gpurun_out/t.log
+timeout 300 python bench.py --steps 2 --warmup 2 --spp 16 --no-cpu-baseline > gpurun_out/ab_0.json 2> gpurun_out/ab_0.err; tail -2 gpurun_out/ab_0.err
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_trace_persistent -c 2 -o gpurun_out/prof_trace_r1f -f python bench.py --steps 1 --warmup 0 --spp 4 --no-cpu-baseline > gpurun_out/ncu.log 2>&1; tail -1 gpurun_out/ncu.log
