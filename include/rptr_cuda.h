@@ -39,6 +39,8 @@ typedef struct rptr_counters {
     uint64_t trace_launches;   /* number of closest-hit kernel launches timed in ms_trace */
     uint64_t node_bytes;       /* size of one BVH node record fetched per node visit */
     uint64_t tri_bytes;        /* size of one traversal triangle record fetched per triangle test */
+    uint64_t bvh_nodes;        /* number of (4-wide) BVH nodes of the current scene */
+    double bvh_build_ms;       /* wall time of the last BVH build (host SAH or device LBVH) */
 } rptr_counters;
 
 /* create_cuda_backend(Display&) / ~RenderBackend  (librender/render_backend.h:118-119, main.cpp:273-285).
@@ -70,6 +72,9 @@ int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *params);
  *   "transmission"  0/1  GLTF_SUPPORT_TRANSMISSION[_ROUGHNESS] (off in the megakernel build, rendering/bsdfs/gltf_bsdf.glsl:10-13)
  *   "wave_paths"    max paths in flight per wavefront pass (memory/occupancy knob)
  *   "stage_timing"  0/1  time each stage with CUDA events into rptr_counters.ms_*
+ *   "bvh_builder"   0 = binned-SAH build on the host inside set_scene, 1 = LBVH build on the device (both replace the
+ *                   driver's BLAS/TLAS build, vulkan/vulkanrt_utils.cpp:82-167; images are identical either way)
+ *   "trace_kernel"  0 = persistent speculative traversal kernel, 1 = one-ray-per-thread kernel (A/B reference)
  *   "tile_rank", "tile_world", "tile_rows": screen-space sharding across GPUs (interleaved bands of tile_rows rows)
  */
 int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value);

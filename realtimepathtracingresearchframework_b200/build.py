@@ -11,8 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librptr_cuda.so")
-SOURCES = ["rptr_cuda.cu", "rptr_host.cpp"]
-HEADERS = ["rptr_math.cuh", "rptr_shading.cuh", "rptr_bvh.cuh", "rptr_trace_kernels.cuh", "rptr_host.hpp", "../../include/rptr_cuda.h", "../../include/rptr_types.h"]
+SOURCES = ["rptr_cuda.cu", "rptr_bvh_build.cu", "rptr_host.cpp"]
+HEADERS = ["rptr_math.cuh", "rptr_shading.cuh", "rptr_bvh.cuh", "rptr_trace_kernels.cuh", "rptr_host.hpp", "rptr_bvh_build.hpp",
+           "../../include/rptr_cuda.h", "../../include/rptr_types.h"]
 
 # RPTR-FP contract (csrc/rptr_math.cuh): no FMA contraction on either side, IEEE division and square root.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-prec-div=true",

@@ -20,6 +20,7 @@
 #include "../../include/rptr_cuda.h"
 #include "rptr_host.hpp"
 #include "rptr_trace_kernels.cuh"
+#include "rptr_bvh_build.hpp"
 
 using namespace rp;
 
@@ -280,6 +281,8 @@ struct rptr_ctx {
     int64_t wave_paths = 8ll << 20;
     int stage_timing = 0;
     int trace_kernel = 0; // 0 = persistent while-while (rptr_trace_kernels.cuh), 1 = one ray per thread (A/B reference)
+    int bvh_builder = 0;  // 0 = binned SAH on the host (rptr_host.cpp), 1 = LBVH on the device (rptr_bvh_build.cu)
+    double bvh_build_ms = 0.0;
     int tile_rank = 0, tile_world = 1, tile_rows = 8;
     // wave
     Wave wave{};
@@ -506,7 +509,7 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     else { ls.light_mis_angle = 0.0f; ls.bin_size = 16; ls.min_perceived_receiver_dist = 15.0f; ls.min_radiance = 0.0f; }
     HostScene hs;
     try {
-        build_host_scene(*desc, ls, hs);
+        build_host_scene(*desc, ls, hs, /*with_bvh=*/ctx->bvh_builder == 0);
     } catch (const std::exception &e) {
         return fail(ctx, "set_scene: %s", e.what());
     }
@@ -546,6 +549,34 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     CU(cudaMemcpy(d_mat, hs.materials.data(), hs.materials.size() * sizeof(rptr_base_material), cudaMemcpyHostToDevice));
     CU(dev_alloc(ctx, &d_lights, hs.lights.size(), ctx->scene_allocs));
     if (!hs.lights.empty()) CU(cudaMemcpy(d_lights, hs.lights.data(), hs.lights.size() * sizeof(rptr_tri_light_data), cudaMemcpyHostToDevice));
+    if (ctx->bvh_builder == 1) { // device LBVH (rptr_bvh_build.cu)
+        float extent = 0.0f, cmin[3] = {1e30f, 1e30f, 1e30f}, cmax[3] = {-1e30f, -1e30f, -1e30f};
+        for (const Tri &t : hs.tris) {
+            const float v[3][3] = {{t.v0x, t.v0y, t.v0z}, {t.v0x + t.e1x, t.v0y + t.e1y, t.v0z + t.e1z}, {t.v0x + t.e2x, t.v0y + t.e2y, t.v0z + t.e2z}};
+            extent = fmaxf(extent, fmaxf(fmaxf(fabsf(t.v0x), fabsf(t.v0y)), fabsf(t.v0z)) + fmaxf(fmaxf(fabsf(t.e1x), fabsf(t.e1y)), fabsf(t.e1z)) +
+                                       fmaxf(fmaxf(fabsf(t.e2x), fabsf(t.e2y)), fabsf(t.e2z)));
+            for (int k = 0; k < 3; ++k) {
+                const float c = 0.5f * (fminf(v[0][k], fminf(v[1][k], v[2][k])) + fmaxf(v[0][k], fmaxf(v[1][k], v[2][k])));
+                cmin[k] = fminf(cmin[k], c);
+                cmax[k] = fmaxf(cmax[k], c);
+            }
+        }
+        DeviceBvh db;
+        std::string err;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (!build_bvh_device(hs.tris, extent, cmin, cmax, ctx->stream, ctx->num_sms, db, err)) return fail(ctx, "set_scene: %s", err.c_str());
+        ctx->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        for (void *p : {(void *)db.nodes, (void *)db.tris, (void *)db.top})
+            if (p) ctx->scene_allocs.push_back(p);
+        ctx->scene = SceneDev{d_gi, d_mat, d_lights};
+        ctx->bvh = BvhDev{db.nodes, db.tris, db.n_nodes, db.n_tris, db.top, db.top_k};
+        ctx->n_lights = (int32_t)hs.lights.size();
+        ctx->lights_host = hs.lights;
+        ctx->has_scene = true;
+        ctx->frame_id = 0;
+        return 0;
+    }
+    ctx->bvh_build_ms = hs.bvh_build_ms;
     CU(dev_alloc(ctx, &d_nodes, hs.nodes.size(), ctx->scene_allocs));
     if (!hs.nodes.empty()) CU(cudaMemcpy(d_nodes, hs.nodes.data(), hs.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
     CU(dev_alloc(ctx, &d_tris, hs.leaf_tris.size(), ctx->scene_allocs));
@@ -597,6 +628,10 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
         ctx->wave_paths = value;
     } else if (n == "stage_timing") ctx->stage_timing = value != 0;
     else if (n == "trace_kernel") ctx->trace_kernel = (int)value;
+    else if (n == "bvh_builder") {
+        if (value != 0 && value != 1) return fail(ctx, "bvh_builder must be 0 (host SAH) or 1 (device LBVH)");
+        ctx->bvh_builder = (int)value; // takes effect at the next set_scene
+    }
     else if (n == "tile_rank") ctx->tile_rank = (int)value;
     else if (n == "tile_world") ctx->tile_world = (int)value;
     else if (n == "tile_rows") ctx->tile_rows = (int)value;
@@ -784,6 +819,8 @@ int rptr_cuda_get_counters(rptr_ctx *ctx, rptr_counters *out) {
     out->trace_launches = ctx->trace_launches;
     out->node_bytes = sizeof(BvhNode) - 16; // 7 of the 8 words are fetched
     out->tri_bytes = sizeof(Tri);
+    out->bvh_nodes = (uint64_t)ctx->bvh.n_nodes;
+    out->bvh_build_ms = ctx->bvh_build_ms;
     return 0;
 }
 

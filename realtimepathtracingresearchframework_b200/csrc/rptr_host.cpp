@@ -169,7 +169,7 @@ void equalize_emitter_bins(std::vector<Emitter> &emitters, std::vector<float> &r
 } // namespace
 
 // ---- scene flattening ---------------------------------------------------------------------------------------------------
-void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config &ls, HostScene &s) {
+void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config &ls, HostScene &s, bool with_bvh) {
     s = HostScene();
     if (d.n_materials <= 0 || !d.materials) throw std::runtime_error("scene has no materials");
     s.materials.assign(d.materials, d.materials + d.n_materials);
@@ -300,7 +300,7 @@ void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config
             s.lights.push_back(t);
         }
     }
-    build_bvh(s);
+    if (with_bvh) build_bvh(s);
 }
 
 // ---- BVH build: binned-SAH binary tree, collapsed to the 4-wide breadth-first layout of rptr_bvh.cuh ---------------------

@@ -33,7 +33,8 @@ struct HostScene {
 };
 
 // Throws std::runtime_error with a readable message on invalid input.
-void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config &ls, HostScene &out);
+// with_bvh = false leaves nodes / leaf_tris empty (the device builder of rptr_bvh_build.cu takes over from `tris`)
+void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config &ls, HostScene &out, bool with_bvh = true);
 void build_bvh(HostScene &s);
 
 // update_view_parameters (vulkan/render_vulkan.cpp:2880-2894): out = du, dv, top_left
