@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tris", type=int, default=1_000_000)
+    ap.add_argument("--scene", default="c2", choices=["c2", "c4"], help="c2 = headline workload (configs[1]); c4 = configs[3], informational")
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--height", type=int, default=H)
@@ -88,10 +89,15 @@ class ClockSampler:
 
 def make_scene(args):
     from realtimepathtracingresearchframework_b200 import scenes
+    if args.scene == "c4":  # BASELINE configs[3]: 100 k-triangle mesh x 100 instances, full BSDF set + area-light NEE
+        return scenes.instanced_scene(100_000, 100)
     return scenes.random_triangles(args.tris)
 
 
 def workload_name(args):
+    if args.scene == "c4":
+        return "synthetic 10M-triangle instanced scene (100k mesh x 100), %dx%d, %d spp, GGX+transmission+emissive tri-light NEE (BASELINE configs[3])" % (
+            args.width, args.height, args.spp)
     return "synthetic %d random-triangle scene, %dx%d, %d spp, diffuse+GGX, sun+sky NEE (BASELINE configs[1])" % (
         args.tris, args.width, args.height, args.spp)
 
@@ -173,6 +179,9 @@ def run_b200(args):
     r = RenderCuda(device=local)
     r.initialize(args.width, args.height)
     r.set_option("stage_timing", 1)
+    if args.scene == "c4":
+        r.set_option("transmission", 1)
+        r.set_option("bvh_builder", 1)
     if args.wave_paths:
         r.set_option("wave_paths", args.wave_paths)
     for kv in args.option:

@@ -247,3 +247,78 @@ def random_triangles(n_tris=1_000_000, n_geometries=16, seed=0x5EED1A7B200, box=
     s.camera = look_at_camera((0, 0, 30), (0, 0, 0), fovy=65.0)
     s.name = "random%d" % n_tris
     return s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C4: one base mesh instanced many times; GGX + transmission (thick / thin) + emissive per-triangle materials
+# ---------------------------------------------------------------------------------------------------------------------
+def vks_instance_transform(translation, scaling, quat_codes):
+    """The 3x4 object-to-world matrix a .vks instance yields: vkr_dequantize_transform of the 24-byte record
+    (translation 3 x f32, scaling f32, quaternion 4 x u16; ext/libvkr/src/vkr.c:1381-1408) followed by the vks axis
+    flip of AnimationData::dequantize (librender/scene.cpp:22-41).  float32 arithmetic throughout."""
+    f = np.float32
+    q = (np.asarray(quat_codes, np.uint16).astype(np.float32) * (f(2.0) / f(0xffff)) - f(1.0)).astype(np.float32)
+    q[3] = -q[3]
+    xx, xy, xz, xw = q[0] * q[0], q[0] * q[1], q[0] * q[2], q[0] * q[3]
+    yy, yz, yw = q[1] * q[1], q[1] * q[2], q[1] * q[3]
+    zz, zw = q[2] * q[2], q[2] * q[3]
+    m = np.zeros((4, 3), np.float32)  # float matrix[4][3] of vkr.c
+    m[0] = [f(1) - f(2) * (yy + zz), f(2) * (xy - zw), f(2) * (xz + yw)]
+    m[1] = [f(2) * (xy + zw), f(1) - f(2) * (xx + zz), f(2) * (yz - xw)]
+    m[2] = [f(2) * (xz - yw), f(2) * (yz + xw), f(1) - f(2) * (xx + yy)]
+    m[:3] *= f(scaling)
+    m[3] = np.asarray(translation, np.float32)
+    cols = m  # glm::mat4x3: column i = matrix[i][0..2]
+    M = np.zeros((3, 4), np.float32)
+    for c in range(4):
+        M[:, c] = cols[c]
+    flip = np.array([[-1, 0, 0], [0, 0, 1], [0, 1, 0]], np.float32)  # (x, y, z) -> (-x, z, y)
+    return (flip @ M).astype(np.float32)
+
+
+def quantize_quaternion(q):
+    """vkr_quantize_transform's 16-bit quaternion code (ext/libvkr/src/vkr.c:1366-1370)."""
+    q = np.asarray(q, np.float32)
+    return np.floor((q * np.float32(0.5) + np.float32(0.5)) * np.float32(0xffff) - np.float32(0.5)).astype(np.uint16)
+
+
+def instanced_scene(n_base_tris=100_000, n_instances=100, seed=0xC4C4C4, edge=None):
+    """BASELINE configs[3]: the first n_base_tris triangles of the C2 generator scaled x0.1 (edge 0.015 in a +-1 box),
+    instanced on a 5 x 5 x k lattice of pitch 6.  Reduced test sizes keep the surface density by growing the edges."""
+    s = Scene()
+    scale, base = 2.0 ** -19, -2.0
+    if edge is None:
+        edge = min(0.3, 0.015 * (100_000 / n_base_tris) ** 0.5)
+    g = random_triangle_grid(n_base_tris, seed=0x5EED1A7B200, box=1.0, edge=edge, scale=scale, base=base)
+    geo = Geometry(pack_qverts(g.reshape(-1, 3)), (scale,) * 3, (base + 2.0 ** -20,) * 3)
+    mesh = s.add_mesh([geo])
+    na = T.BASE_MATERIAL_NOALPHA
+    mats = []
+    for j in range(8):  # GGX opaque
+        mats.append(T.BaseMaterial(base_color=_PALETTE[j], roughness=0.15 + 0.1 * j, metallic=float(j & 1), ior=1.5, flags=na))
+    for j in range(4):  # transmissive: two thick (ONESIDED), two thin
+        fl = na | T.BASE_MATERIAL_EXTENDED | (T.BASE_MATERIAL_ONESIDED if j < 2 else 0)
+        mats.append(T.BaseMaterial(base_color=_PALETTE[8 + j], roughness=0.05 + 0.1 * j, ior=1.33 + 0.1 * j, specular_transmission=1.0,
+                                   clearcoat_gloss=0.02 + 0.05 * j, flags=fl))
+    for j in range(2):  # stand-ins for the alpha-tested materials (alpha textures arrive with row f2): opaque, not flagged NOALPHA
+        mats.append(T.BaseMaterial(base_color=_PALETTE[12 + j], roughness=0.6, ior=1.5, flags=0))
+    for j in range(2):  # emissive
+        mats.append(T.BaseMaterial(base_color=(1.0, 0.8 - 0.3 * j, 0.5 + 0.4 * j), emission_intensity=20.0, flags=na))
+    s.materials = mats
+    ids = (np.arange(n_base_tris) % 14).astype(np.uint8)
+    n_em = min(64, n_base_tris)
+    ids[:n_em] = 14 + (np.arange(n_em) % 2)
+    pm = s.add_pmesh(mesh, [0], tri_material_ids=ids)
+    u = splitmix64_uniform(seed, n_instances * 8).reshape(n_instances, 8)
+    for i in range(n_instances):
+        cell = np.array([i % 5, (i // 5) % 5, i // 25], np.float32) * np.float32(6.0)
+        scl = np.float32(0.5 + u[i, 0])
+        q = (u[i, 1:5] * 2.0 - 1.0).astype(np.float32)
+        q = q / np.float32(np.sqrt(np.float32(np.dot(q, q))))
+        s.add_instance(pm, vks_instance_transform(cell, scl, quantize_quaternion(q)))
+    pos = np.array([t[:, 3] for _, t in s.instances], np.float32)  # instance origins after the (x, y, z) -> (-x, z, y) flip
+    centre = 0.5 * (pos.min(0) + pos.max(0))
+    radius = float(np.abs(pos - centre).max()) + 3.0
+    s.camera = look_at_camera(centre + np.array([0.0, 0.2 * radius, 2.4 * radius], np.float32), centre, fovy=50.0)
+    s.name = "instanced%dx%d" % (n_base_tris, n_instances)
+    return s

@@ -370,3 +370,36 @@ def test_two_devices_when_available():
         r.render_spp(s.camera, 2)
         total += r.framebuffer()
     assert np.array_equal(total.view(np.uint32), full.framebuffer().view(np.uint32))
+
+
+def test_c4_instanced_transmission_emissive(oracle):
+    """BASELINE configs[3] (instances + full BSDF set + area-light NEE): reduced size against the oracle with both BVH
+    builders, then the full 10 M instanced triangles (device LBVH) through size-independent properties."""
+    s = scenes.instanced_scene(1500, 25)
+    W, H = 240, 135
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(T.SceneConfig(**sky)), spp=3, transmission=1)
+    for builder in (0, 1):
+        r = make_backend(s, W, H, sky, transmission=1, bvh_builder=builder)
+        r.render_spp(s.camera, 3)
+        assert_identical(r.framebuffer(), ref, "C4 reduced, builder %d" % builder)
+
+
+def test_c4_full_size_properties():
+    s = scenes.instanced_scene(100_000, 100)
+    assert s.total_tris() == 10_000_000
+    W, H = 960, 540
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    r = make_backend(s, W, H, sky, transmission=1, bvh_builder=1)
+    assert len(r.lights()) >= 6400
+    r.render_spp(s.camera, 2, batch_spp=2)
+    img = r.framebuffer()
+    assert np.isfinite(img).all() and (img[..., 3] > 0).mean() > 0.01
+    c = r.counters()
+    assert c["samples"] == 2 * W * H and c["shadow_rays"] > 0
+    parts = []
+    for rank in range(2):
+        t = make_backend(s, W, H, sky, transmission=1, bvh_builder=1, tile_world=2, tile_rank=rank)
+        t.render_spp(s.camera, 2, batch_spp=1)
+        parts.append(t.framebuffer())
+    assert np.array_equal((parts[0] + parts[1]).view(np.uint32), img.view(np.uint32))

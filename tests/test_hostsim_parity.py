@@ -142,3 +142,27 @@ def test_traversal_edge_rays_against_bruteforce(hostsim, oracle):
         # oracle's own BVH too
         ob, tob = o.trace_closest(q)
         assert np.array_equal(tref, tob) and np.array_equal(ref.view(np.uint32), ob.view(np.uint32))
+
+
+def test_c4_style_instanced_scene_matches_oracle(H, oracle):
+    """BASELINE configs[3] at reduced size: one mesh instanced 25 times through .vks-style quantised similarity
+    transforms, per-triangle u8 material ids, GGX + thick/thin transmission + emissive triangles -> binned tri-light NEE."""
+    s = scenes.instanced_scene(1500, 25)
+    sp = load_sky_fit(T.SceneConfig(sun_dir=(0.35, 0.8, 0.45)))
+    o = oracle.OracleScene(s)
+    assert len(o.lights()) >= 25 * 64
+    ls = T.LightSamplingConfig()
+    d = s.desc()
+    hs = H.hostsim_scene_create(C.byref(d), C.byref(ls))
+    n = H.hostsim_num_lights(hs)
+    arr = (T.TriLightData * n)()
+    H.hostsim_get_lights(hs, arr)
+    assert np.array_equal(np.frombuffer(arr, np.float32).reshape(-1, 12), o.lights())
+    W, Hh = 200, 112
+    ref = o.render_sample(W, Hh, s.camera, sp, 2, transmission=1)
+    a = o._args(W, Hh, s.camera, sp, transmission=1)
+    img = np.zeros((Hh, W, 4), np.float32)
+    H.hostsim_render_sample(hs, C.byref(a), 2, oracle._fp(img))
+    H.hostsim_scene_destroy(hs)
+    assert (ref[..., 3] > 0).mean() > 0.02
+    assert np.array_equal(ref.view(np.uint32), img.view(np.uint32))
