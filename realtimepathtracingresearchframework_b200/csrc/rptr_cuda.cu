@@ -114,53 +114,103 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
     flush_counter(&dc->closest_tris, cnt.tris);
 }
 
-// shade the vertices found by k_trace; emits shadow rays and the next bounce's queue
-__global__ void __launch_bounds__(128) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
-                                               const uint32_t *count, uint32_t *next_queue, uint32_t *next_count,
-                                               uint32_t *shadow_count, DevCounters *dc) {
+// Shade the vertices found by the trace stage; emits shadow rays and the next bounce's queue.
+// Divergence control: a CTA takes tiles of RPTR_SHADE_TILE queue entries, counting-sorts them in shared memory by
+// (miss | material id) and hands every warp a run of equal keys, so that sky evaluation, Lambert, GGX, transmissive and
+// emissive vertices do not share warps (the reference's megakernel pays that divergence inside every workgroup).
+#define RPTR_SHADE_THREADS 128
+#define RPTR_SHADE_PER_THREAD 4
+#define RPTR_SHADE_TILE (RPTR_SHADE_THREADS * RPTR_SHADE_PER_THREAD)
+#define RPTR_SHADE_KEYS 16
+__global__ void __launch_bounds__(RPTR_SHADE_THREADS) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
+                                                              const uint32_t *count, uint32_t *next_queue, uint32_t *next_count,
+                                                              uint32_t *shadow_count, DevCounters *dc) {
+    __shared__ uint32_t s_hist[RPTR_SHADE_KEYS], s_base[RPTR_SHADE_KEYS];
+    __shared__ uint32_t s_sorted[RPTR_SHADE_TILE];
     const uint32_t n = *count;
     unsigned long long verts = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    // all lanes of a warp iterate together so that the ballots in warp_append see a converged warp
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t i = base + (threadIdx.x & 31);
-        const bool active = i < n;
-        bool cont = false, shadow = false;
-        uint32_t slot = 0;
-        ShadowRay sh;
-        sh.tmax = -1.0f;
-        if (active) {
-            slot = queue ? queue[i] : i;
-            const float4 o = w.ray_o[slot], d = w.ray_d[slot], hit = w.hit[slot], thr = w.thr[slot], il = w.illum[slot];
-            const uint2 rb = w.rngb[slot];
-            PathState ps;
-            ps.o = f3(o.x, o.y, o.z); ps.tmin = o.w;
-            ps.d = f3(d.x, d.y, d.z); ps.tmax = d.w;
-            ps.thr = f3(thr.x, thr.y, thr.z); ps.prev_pdf = thr.w;
-            ps.illum = f3(il.x, il.y, il.z); ps.total_t = il.w;
-            ps.rng = rb.x; ps.bounce = (int)rb.y;
-            const int tri = __float_as_int(hit.w);
-            if (tri >= 0) verts++;
-            ShadeResult r = shade_vertex(fp, sc, ps, hit.x, hit.y, hit.z, tri >= 0 ? &bvh.tris[tri] : nullptr, sh);
-            cont = r == SHADE_CONTINUE;
-            shadow = sh.tmax > 0.0f;
-            w.illum[slot] = f4(ps.illum.x, ps.illum.y, ps.illum.z, ps.total_t);
-            w.rngb[slot] = make_uint2(ps.rng, (uint32_t)ps.bounce);
-            if (cont) {
-                w.ray_o[slot] = f4(ps.o.x, ps.o.y, ps.o.z, ps.tmin);
-                w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
-                w.thr[slot] = f4(ps.thr.x, ps.thr.y, ps.thr.z, ps.prev_pdf);
+    const uint32_t n_tiles = (n + RPTR_SHADE_TILE - 1) / RPTR_SHADE_TILE;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t tile_base = tile * RPTR_SHADE_TILE;
+        const uint32_t tile_count = min((uint32_t)RPTR_SHADE_TILE, n - tile_base);
+        if (threadIdx.x < RPTR_SHADE_KEYS) s_hist[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t my_slot[RPTR_SHADE_PER_THREAD], my_key[RPTR_SHADE_PER_THREAD], my_pos[RPTR_SHADE_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < RPTR_SHADE_PER_THREAD; ++k) {
+            const uint32_t j = k * RPTR_SHADE_THREADS + threadIdx.x;
+            my_key[k] = 0xffffffffu;
+            if (j < tile_count) {
+                const uint32_t slot = queue ? queue[tile_base + j] : tile_base + j;
+                const int tri = __float_as_int(w.hit[slot].w);
+                uint32_t key = 0; // miss
+                if (tri >= 0) {
+                    const Tri *tr = bvh.tris + tri;
+                    const GeomInst &g = sc.ginst[tr->geom_inst];
+                    // key = code path of shade_vertex, not the material itself (keeps neighbouring pixels together):
+                    // Lambert / GGX / thin or thick transmission, plus the emitter-MIS variant of each
+                    const rptr_base_material &m = sc.materials[calc_hit_material_id(g, (uint32_t)tr->prim)];
+                    key = 1u;
+                    if (m.ior > 1.0f) key = 2u;
+                    if (fp.transmission && m.ior > 1.0f && m.specular_transmission > 0.0f) key = (m.flags & RPTR_BASE_MATERIAL_ONESIDED) ? 4u : 3u;
+                    if (m.emission_intensity != 0.0f) key += 5u;
+                }
+                my_slot[k] = slot;
+                my_key[k] = key;
+                my_pos[k] = atomicAdd(&s_hist[key], 1u);
             }
         }
-        __syncwarp();
-        const uint32_t qi = warp_append(next_count, cont);
-        if (cont) next_queue[qi] = slot;
-        const uint32_t si = warp_append(shadow_count, shadow);
-        if (shadow) {
-            w.sh_o[si] = f4(sh.o.x, sh.o.y, sh.o.z, sh.tmin);
-            w.sh_d[si] = f4(sh.d.x, sh.d.y, sh.d.z, sh.tmax);
-            w.sh_c[si] = f4(sh.contrib.x, sh.contrib.y, sh.contrib.z, __uint_as_float(slot));
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int b = 0; b < RPTR_SHADE_KEYS; ++b) { s_base[b] = acc; acc += s_hist[b]; }
         }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RPTR_SHADE_PER_THREAD; ++k)
+            if (my_key[k] != 0xffffffffu) s_sorted[s_base[my_key[k]] + my_pos[k]] = my_slot[k];
+        __syncthreads();
+        for (int k = 0; k < RPTR_SHADE_PER_THREAD; ++k) {
+            const uint32_t j = k * RPTR_SHADE_THREADS + threadIdx.x;
+            const bool active = j < tile_count;
+            bool cont = false, shadow = false;
+            uint32_t slot = 0;
+            ShadowRay sh;
+            sh.tmax = -1.0f;
+            if (active) {
+                slot = s_sorted[j];
+                const float4 o = w.ray_o[slot], d = w.ray_d[slot], hit = w.hit[slot], thr = w.thr[slot], il = w.illum[slot];
+                const uint2 rb = w.rngb[slot];
+                PathState ps;
+                ps.o = f3(o.x, o.y, o.z); ps.tmin = o.w;
+                ps.d = f3(d.x, d.y, d.z); ps.tmax = d.w;
+                ps.thr = f3(thr.x, thr.y, thr.z); ps.prev_pdf = thr.w;
+                ps.illum = f3(il.x, il.y, il.z); ps.total_t = il.w;
+                ps.rng = rb.x; ps.bounce = (int)rb.y;
+                const int tri = __float_as_int(hit.w);
+                if (tri >= 0) verts++;
+                ShadeResult r = shade_vertex(fp, sc, ps, hit.x, hit.y, hit.z, tri >= 0 ? &bvh.tris[tri] : nullptr, sh);
+                cont = r == SHADE_CONTINUE;
+                shadow = sh.tmax > 0.0f;
+                w.illum[slot] = f4(ps.illum.x, ps.illum.y, ps.illum.z, ps.total_t);
+                w.rngb[slot] = make_uint2(ps.rng, (uint32_t)ps.bounce);
+                if (cont) {
+                    w.ray_o[slot] = f4(ps.o.x, ps.o.y, ps.o.z, ps.tmin);
+                    w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
+                    w.thr[slot] = f4(ps.thr.x, ps.thr.y, ps.thr.z, ps.prev_pdf);
+                }
+            }
+            __syncwarp();
+            const uint32_t qi = warp_append(next_count, cont);
+            if (cont) next_queue[qi] = slot;
+            const uint32_t si = warp_append(shadow_count, shadow);
+            if (shadow) {
+                w.sh_o[si] = f4(sh.o.x, sh.o.y, sh.o.z, sh.tmin);
+                w.sh_d[si] = f4(sh.d.x, sh.d.y, sh.d.z, sh.tmax);
+                w.sh_c[si] = f4(sh.contrib.x, sh.contrib.y, sh.contrib.z, __uint_as_float(slot));
+            }
+        }
+        __syncthreads();
     }
     flush_counter(&dc->shaded_vertices, verts);
 }
