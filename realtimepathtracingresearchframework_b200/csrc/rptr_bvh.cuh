@@ -26,7 +26,7 @@ struct alignas(128) BvhNode {
     int32_t pad[4];
 };
 static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte record");
-static_assert(sizeof(Tri) == 48, "Tri must be three 128-bit words");
+static_assert(sizeof(Tri) == 48 || sizeof(Tri) == 64, "Tri must be three 128-bit or two 256-bit words");
 
 RPTR_HD int32_t make_leaf_ref(int32_t first, int32_t count) { return ~((first << 2) | (count - 1)); }
 RPTR_HD bool is_leaf_ref(int32_t r) { return r < 0 && r != RPTR_EMPTY; }
@@ -93,9 +93,11 @@ RPTR_HD bool slab(float lox, float loy, float loz, float hix, float hiy, float h
     tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
     t0 = fmaf(loz, inv.z, -ood.z); t1 = fmaf(hiz, inv.z, -ood.z);
     tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
-    tf *= 1.0000004f;
+    // [tn, tf] x [tmin, tmax] non-empty  <=>  max(tn, tmin) <= min(tf, tmax)
+    tf = fminf(tf * 1.0000004f, tmax);
+    tn = fmaxf(tn, tmin);
     tnear = tn;
-    return tn <= tf && tf >= tmin && tn <= tmax;
+    return tn <= tf;
 }
 
 RPTR_HD float comp4(const float4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }

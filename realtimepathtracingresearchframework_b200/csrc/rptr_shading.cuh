@@ -23,11 +23,18 @@ struct GeomInst { // the reference's instanced_geometry[] entry (rendering/rt/ge
     int32_t _pad;
 };
 
-struct Tri { // 48 B traversal record, world space
+#ifdef RPTR_TRI64
+struct alignas(64) Tri { // 64 B traversal record (two 256-bit loads), world space
+#else
+struct Tri { // 48 B traversal record (three 128-bit loads), world space
+#endif
     float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
     int32_t id;        // flattened (instance, geometry, primitive) index: the closest-hit tie-break key
     int32_t geom_inst; // index into GeomInst[]
     int32_t prim;
+#ifdef RPTR_TRI64
+    int32_t pad[4];
+#endif
 };
 
 struct SceneDev {

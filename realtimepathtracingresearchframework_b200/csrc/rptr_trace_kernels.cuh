@@ -26,7 +26,7 @@ namespace rp {
 #define RPTR_REFILL_LANES 8
 #endif
 #ifndef RPTR_LEAF_LANES
-#define RPTR_LEAF_LANES 16
+#define RPTR_LEAF_LANES 8
 #endif
 
 struct TraceIO {
@@ -80,7 +80,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
-#define RPTR_TRACE_THREADS 1024 // one CTA per SM: 32 warps share one 128 KB image of the top of the BVH
+#ifndef RPTR_TRACE_THREADS
+#define RPTR_TRACE_THREADS 768 // one CTA per SM: 24 warps (80 registers each) share one 128 KB image of the top of the BVH
+#endif
 #define RPTR_TMA_CHUNK 32768u
 // Traversal stack: the first RPTR_SMEM_STACK entries of every thread live in shared memory, laid out [entry][thread] so
 // that the bank only depends on the lane (any mix of stack depths in a warp is conflict free: one wavefront per push /
@@ -183,9 +185,21 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             pool_pos += min(avail, (uint32_t)__popc(idle));
             if (drained && !__any_sync(FULL, have)) break;
         }
-        // ---- node step ----------------------------------------------------------------------------------------------
-        if (have && node >= 0) {
-            float4 w0, w1, w2, w3, w4, w5, w6;
+        // ---- issue every load of this trip up front: the node of lanes with node work AND the first triangle of lanes
+        //      whose parked leaf is processed in this trip, so the two dependent fetches overlap instead of queueing ----
+        const bool leaf_turn = __popc(parked0) >= RPTR_LEAF_LANES || inner0 == 0;
+        const bool do_node = have && node >= 0;
+        const bool do_leaf = leaf_turn && have && leaf != 0;
+        float4 w0, w1, w2, w3, w4, w5, w6, ta, tb, tc;
+        int32_t lf_first = 0, lf_cnt = 0;
+        if (do_leaf) {
+            const int32_t ref = ~leaf;
+            lf_first = ref >> 2;
+            lf_cnt = (ref & 3) + 1;
+            const char *tp = reinterpret_cast<const char *>(bvh.tris + lf_first);
+            ta = ld128(tp); tb = ld128(tp + 16); tc = ld128(tp + 32);
+        }
+        if (do_node) {
             if (node < top_k) { // top of the tree: shared memory (LDS.128), words XOR-swizzled against bank conflicts
                 const unsigned char *sp_ = smem_top + (size_t)node * sizeof(BvhNode);
                 const int sw = node & 7;
@@ -203,6 +217,9 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 ld256(np + 64, w4, w5);
                 w6 = ld128(np + 96);
             }
+        }
+        // ---- node step ----------------------------------------------------------------------------------------------
+        if (do_node) {
             n_nodes++;
             // four slab tests; a missed (or unused: inverted box) child gets key +inf and reference EMPTY
             const float INF = __int_as_float(0x7f800000);
@@ -213,12 +230,12 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             if (!slab(w0.z, w1.z, w2.z, w3.z, w4.z, w5.z, inv, ood, tmin, best_t, t2)) { t2 = INF; r2 = RPTR_EMPTY; }
             if (!slab(w0.w, w1.w, w2.w, w3.w, w4.w, w5.w, inv, ood, tmin, best_t, t3)) { t3 = INF; r3 = RPTR_EMPTY; }
             // 5-comparator sorting network on (t, ref): nearest first
-#define RPTR_CSWAP(ta, ra, tb, rb)                                  \
+#define RPTR_CSWAP(ta_, ra, tb_, rb)                                 \
     {                                                               \
-        const bool sw_ = tb < ta;                                   \
-        const float tl_ = sw_ ? tb : ta, th_ = sw_ ? ta : tb;       \
+        const bool sw_ = tb_ < ta_;                                 \
+        const float tl_ = sw_ ? tb_ : ta_, th_ = sw_ ? ta_ : tb_;   \
         const int32_t rl_ = sw_ ? rb : ra, rh_ = sw_ ? ra : rb;     \
-        ta = tl_; tb = th_; ra = rl_; rb = rh_;                     \
+        ta_ = tl_; tb_ = th_; ra = rl_; rb = rh_;                   \
     }
             RPTR_CSWAP(t0, r0, t1, r1)
             RPTR_CSWAP(t2, r2, t3, r3)
@@ -231,46 +248,43 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             if (r2 != RPTR_EMPTY) RPTR_PUSH(r2);
             if (r1 != RPTR_EMPTY) RPTR_PUSH(r1);
             node = r0 != RPTR_EMPTY ? r0 : RPTR_POP();
-            // park a leaf and go on with whatever the stack holds (speculative traversal)
+            // park a leaf and go on with whatever the stack holds (speculative traversal); when this lane's parked leaf
+            // is being processed in this trip the slot frees up below
             if (node < 0 && node != RPTR_EMPTY && leaf == 0) {
                 leaf = node;
                 node = RPTR_POP();
             }
         }
-        // ---- leaf step ------------------------------------------------------------------------------------------------
-        const unsigned parked = __ballot_sync(FULL, have && leaf != 0);
-        const unsigned inner = __ballot_sync(FULL, have && node >= 0);
-        if (parked != 0 && (__popc(parked) >= RPTR_LEAF_LANES || inner == 0)) {
-            if (have && leaf != 0) {
-                const int32_t ref = ~leaf;
-                const int32_t first = ref >> 2;
-                const int32_t cnt = (ref & 3) + 1;
-                bool occluded = false;
-                for (int32_t i = 0; i < cnt; ++i) {
-                    const char *tp = reinterpret_cast<const char *>(bvh.tris + first + i);
-                    const float4 a = ld128(tp), b = ld128(tp + 16), c4 = ld128(tp + 32);
-                    n_tris++;
-                    float t, u, v;
-                    if (!intersect_tri(f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c4.x), o, d, t, u, v)) continue;
-                    if (!(t > tmin && t < tmax)) continue;
-                    const int32_t id = f2i(c4.y);
-                    if (Any) {
-                        best_tri = first + i;
-                        occluded = true;
-                        break;
-                    }
-                    if (best_tri < 0 || t < best_t || (t == best_t && id < best_id)) {
-                        best_t = t; best_u = u; best_v = v; best_tri = first + i; best_id = id;
-                    }
+        // ---- leaf step: software-pipelined over the (<= 4, contiguous) triangles of the parked leaf ------------------------
+        if (do_leaf) {
+            bool occluded = false;
+            for (int32_t i = 0; i < lf_cnt; ++i) {
+                const float4 a = ta, b = tb, c4 = tc;
+                if (i + 1 < lf_cnt) { // fetch the next triangle while this one is tested
+                    const char *tp = reinterpret_cast<const char *>(bvh.tris + lf_first + i + 1);
+                    ta = ld128(tp); tb = ld128(tp + 16); tc = ld128(tp + 32);
                 }
-                leaf = 0;
-                if (Any && occluded) { // drop the rest of the traversal
-                    sp = 0;
-                    node = RPTR_EMPTY;
-                } else if (node < 0 && node != RPTR_EMPTY) { // the current item was a second leaf waiting for the slot
-                    leaf = node;
-                    node = RPTR_POP();
+                n_tris++;
+                float t, u, v;
+                if (!intersect_tri(f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c4.x), o, d, t, u, v)) continue;
+                if (!(t > tmin && t < tmax)) continue;
+                const int32_t id = f2i(c4.y);
+                if (Any) {
+                    best_tri = lf_first + i;
+                    occluded = true;
+                    break;
                 }
+                if (best_tri < 0 || t < best_t || (t == best_t && id < best_id)) {
+                    best_t = t; best_u = u; best_v = v; best_tri = lf_first + i; best_id = id;
+                }
+            }
+            leaf = 0;
+            if (Any && occluded) { // drop the rest of the traversal
+                sp = 0;
+                node = RPTR_EMPTY;
+            } else if (node < 0 && node != RPTR_EMPTY) { // the current item was a second leaf waiting for the slot
+                leaf = node;
+                node = RPTR_POP();
             }
         }
     }
