@@ -328,7 +328,9 @@ struct rptr_ctx {
     bool in_frame = false;
     // options
     int transmission = 0;
-    int64_t wave_paths = 8ll << 20;
+    // paths per wave: 64 spp of 1920x1080 in one wave (144 B of path state each, 19 GB); every launch of the bounce loop
+    // pays a fixed tail (the longest ray of the queue), so few large waves beat many small ones (profiles/r01_wave_sweep.md)
+    int64_t wave_paths = 128ll << 20;
     int stage_timing = 0;
     int trace_kernel = 0; // 0 = persistent while-while (rptr_trace_kernels.cuh), 1 = one ray per thread (A/B reference)
     int bvh_builder = 0;  // 0 = binned SAH on the host (rptr_host.cpp), 1 = LBVH on the device (rptr_bvh_build.cu)
@@ -755,7 +757,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         if (layers_per_wave > fp.batch) layers_per_wave = fp.batch;
         if (ensure_wave(ctx, (size_t)layers_per_wave * tm.local_pixels, depth)) return 1;
         Wave &w = ctx->wave;
-        // trace: one 1024-thread CTA per SM; dynamic smem = the staged top of the BVH (at least one node's worth)
+        // trace: one RPTR_TRACE_THREADS CTA per SM; dynamic smem = the staged top of the BVH + the shared stack part
         const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4), g_pt = grid_for(ctx, 1);
         const size_t top_smem = RPTR_TRACE_SMEM_BYTES; // staged BVH top (128 KB) + shared part of the traversal stacks (64 KB)
         for (int32_t first = 0; first < fp.batch; first += (int32_t)layers_per_wave) {

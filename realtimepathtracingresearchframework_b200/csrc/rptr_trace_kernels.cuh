@@ -80,6 +80,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
+#ifndef RPTR_CHUNKS_PER_WARP
+#define RPTR_CHUNKS_PER_WARP 4 // target number of queue fetches per warp (tail balance) before the chunk is shortened
+#endif
 #ifndef RPTR_TRACE_THREADS
 #define RPTR_TRACE_THREADS 768 // one CTA per SM: 24 warps (80 registers each) share one 128 KB image of the top of the BVH
 #endif
@@ -119,6 +122,11 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     }
     if (n > 0) mbar_wait(&top_bar, 0);
     const int32_t top_k = bvh.top_k;
+    // Rays per queue fetch: RPTR_FETCH_CHUNK for long queues (few atomics, coherent warps); short queues (late bounces)
+    // are cut finer so that every warp of the grid gets work instead of a few warps walking 256 rays 32 at a time.
+    // Guided self-scheduling: the size is recomputed from what is left of the queue at every fetch.
+    const uint32_t chunk_div = gridDim.x * (RPTR_TRACE_THREADS / 32) * RPTR_CHUNKS_PER_WARP;
+    uint32_t chunk = min((uint32_t)RPTR_FETCH_CHUNK, max(32u, (n / chunk_div) & ~31u));
     uint32_t pool_pos = 0, pool_end = 0; // per-warp pool of ray indices (warp-uniform)
     bool drained = false;                // the global queue has been exhausted (warp-uniform)
 
@@ -160,10 +168,13 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             }
             if (pool_pos >= pool_end && !drained) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(io.work, (uint32_t)RPTR_FETCH_CHUNK);
+                if (lane == 0) base = atomicAdd(io.work, chunk);
                 base = __shfl_sync(FULL, base, 0);
                 if (base >= n) drained = true;
-                else { pool_pos = base; pool_end = min(base + (uint32_t)RPTR_FETCH_CHUNK, n); }
+                else {
+                    pool_pos = base; pool_end = min(base + chunk, n);
+                    chunk = min((uint32_t)RPTR_FETCH_CHUNK, max(32u, ((n - pool_end) / chunk_div) & ~31u));
+                }
             }
             const uint32_t avail = pool_end > pool_pos ? pool_end - pool_pos : 0u;
             const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
