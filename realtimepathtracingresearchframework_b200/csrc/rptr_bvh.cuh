@@ -16,16 +16,27 @@ namespace rp {
 #define RPTR_STACK_SIZE 128
 #define RPTR_MAX_BVH_DEPTH 40 // builder guarantee: 3 pushes per level + 1 < RPTR_STACK_SIZE
 
-// 128-byte four-wide node, child boxes as structure of arrays, read as 7 x 128-bit words (the 8th is padding):
-//   w0 = lo.x[4]  w1 = lo.y[4]  w2 = lo.z[4]  w3 = hi.x[4]  w4 = hi.y[4]  w5 = hi.z[4]  w6 = child[4]
+// 64-byte four-wide node with quantised child boxes (one 128-bit word per line below, two 256-bit loads per node):
+//   w0 = org.x  org.y  org.z  ext.x
+//   w1 = ext.y  ext.z  qlo.x[4]  qlo.y[4]
+//   w2 = qlo.z[4]  qhi.x[4]  qhi.y[4]  qhi.z[4]
+//   w3 = child[4]
+// Child k spans, per axis, [org + f(qlo[k]) * ext, org + f(qhi[k]) * ext] with f(b) = 1 + (b & 127) / 128: every byte is
+// stored as 0x80 | q (q in [0, 127]) so that ONE byte permute builds the float 0x3f000000 | b << 16 = f(b) in [1, 2),
+// and the slab test is t = fma(f, ext * (1/d), (org - o) * (1/d)) -- no integer-to-float conversion, no cancellation
+// against a large bias.  The grid of a node starts at org + ext (<= the lowest child corner) and has 127 steps of
+// ext / 128; encode_node() rounds lo down / hi up in exact arithmetic, so the decoded boxes contain the builder's padded
+// boxes and culling stays conservative (rptr_bvh.cuh header: box tests only prune, the closest-hit contract is untouched).
 // child[k] >= 0: inner node index; < 0: leaf reference ~((first_triangle << 2) | (count - 1)), count in [1, 4];
-// RPTR_EMPTY: unused slot (its box is inverted so it can never be hit).
-struct alignas(128) BvhNode {
-    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+// RPTR_EMPTY: unused slot (tested explicitly, its box bytes are 0x80).
+struct alignas(64) BvhNode {
+    float org[3];
+    float ext[3];
+    uint32_t qlo[3]; // byte k of qlo[a] = 0x80 | quantised lower bound of child k on axis a
+    uint32_t qhi[3];
     int32_t child[4];
-    int32_t pad[4];
 };
-static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte record");
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be one 64-byte record");
 static_assert(sizeof(Tri) == 48 || sizeof(Tri) == 64, "Tri must be three 128-bit or two 256-bit words");
 
 RPTR_HD int32_t make_leaf_ref(int32_t first, int32_t count) { return ~((first << 2) | (count - 1)); }
@@ -36,14 +47,14 @@ struct BvhDev {
     const Tri *tris;      // leaf order
     int32_t n_nodes;
     int32_t n_tris;
-    // the first top_k nodes again, with the eight 16-byte words of node i stored at word position w ^ (i & 7):
+    // the first top_k nodes again, with the four 16-byte words of node i stored at word position w ^ ((i >> 1) & 3):
     // the image a CTA of the trace kernel copies into shared memory (the XOR spreads random nodes over the banks)
     const BvhNode *top_swizzled;
     int32_t top_k;
 };
 
 #ifndef RPTR_TOP_NODES_MAX
-#define RPTR_TOP_NODES_MAX 1024 // 128 KB of shared memory per CTA
+#define RPTR_TOP_NODES_MAX 1024 // 64 KB of shared memory per CTA
 #endif
 
 struct HitRec {
@@ -83,15 +94,41 @@ struct TraceCounters { uint32_t nodes, tris; };
 
 RPTR_HD float slab_safe(float d) { return fabsf(d) > 1e-18f ? d : copysignf(1e-18f, d); }
 
-// Slab test with fma: t = b * inv - o * inv.  Pruning only (conservative: boxes are padded at build time by more than
-// the rounding of this expression for origins within ~16x the scene extent; tfar is widened by 4 ulp).
-RPTR_HD bool slab(float lox, float loy, float loz, float hix, float hiy, float hiz, float3 inv, float3 ood, float tmin, float tmax,
-                  float &tnear) {
-    float t0 = fmaf(lox, inv.x, -ood.x), t1 = fmaf(hix, inv.x, -ood.x);
+RPTR_HD float u2f_(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+// f(b) of child k from a packed word of four bytes: float bits 0x3f000000 | byte << 16 (PRMT on the device)
+RPTR_HD float qfloat(uint32_t word, int k) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(word, 0x3f000000u, 0x7044u | ((uint32_t)k << 8)));
+#else
+    return u2f_(0x3f000000u | (((word >> (8 * k)) & 0xffu) << 16));
+#endif
+}
+
+// Per-node part of the slab test: a = ext / d, b = (org - o) / d  (fma form, |error| ~ 2^-22 of the scene scale, covered
+// by the padding of the builder's boxes for ray origins within ~8 scene extents).
+struct NodeSlab { float ax, ay, az, bx, by, bz; };
+RPTR_HD NodeSlab node_slab(float orgx, float orgy, float orgz, float extx, float exty, float extz, float3 inv, float3 ood) {
+    NodeSlab n;
+    n.ax = extx * inv.x; n.ay = exty * inv.y; n.az = extz * inv.z;
+    n.bx = fmaf(orgx, inv.x, -ood.x); n.by = fmaf(orgy, inv.y, -ood.y); n.bz = fmaf(orgz, inv.z, -ood.z);
+    return n;
+}
+// Slab test of child k (pruning only; tfar is widened by 4 ulp).
+RPTR_HD bool slab_q(const NodeSlab &n, uint32_t qlx, uint32_t qly, uint32_t qlz, uint32_t qhx, uint32_t qhy, uint32_t qhz, int k, float tmin,
+                    float tmax, float &tnear) {
+    float t0 = fmaf(qfloat(qlx, k), n.ax, n.bx), t1 = fmaf(qfloat(qhx, k), n.ax, n.bx);
     float tn = fminf(t0, t1), tf = fmaxf(t0, t1);
-    t0 = fmaf(loy, inv.y, -ood.y); t1 = fmaf(hiy, inv.y, -ood.y);
+    t0 = fmaf(qfloat(qly, k), n.ay, n.by); t1 = fmaf(qfloat(qhy, k), n.ay, n.by);
     tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
-    t0 = fmaf(loz, inv.z, -ood.z); t1 = fmaf(hiz, inv.z, -ood.z);
+    t0 = fmaf(qfloat(qlz, k), n.az, n.bz); t1 = fmaf(qfloat(qhz, k), n.az, n.bz);
     tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
     // [tn, tf] x [tmin, tmax] non-empty  <=>  max(tn, tmin) <= min(tf, tmax)
     tf = fminf(tf * 1.0000004f, tmax);
@@ -100,7 +137,58 @@ RPTR_HD bool slab(float lox, float loy, float loz, float hix, float hiy, float h
     return tn <= tf;
 }
 
-RPTR_HD float comp4(const float4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+// Quantise nk child boxes (lo[k][axis], hi[k][axis]; already padded by the builder) into one node.  Exact arithmetic in
+// double (all operands are floats with <= 8 extra bits): decoded lower bounds never exceed lo, upper bounds never fall
+// short of hi.
+RPTR_HD BvhNode encode_node(const float (*lo)[3], const float (*hi)[3], const int32_t *child, int nk) {
+    BvhNode nd;
+    for (int a = 0; a < 3; ++a) {
+        double L = 1e300, H = -1e300;
+        for (int k = 0; k < nk; ++k) {
+            if (child[k] == RPTR_EMPTY) continue;
+            L = (double)lo[k][a] < L ? (double)lo[k][a] : L;
+            H = (double)hi[k][a] > H ? (double)hi[k][a] : H;
+        }
+        if (L > H) { L = 0.0; H = 0.0; }
+        // ext: 127 steps of ext/128 must cover [L, H] from a grid origin org + ext <= L, with slack for the rounding of org
+        float ext = (float)((H - L) * (128.0 / 127.0) * 1.000001);
+        const float tiny = (float)(fabs(L) + fabs(H)) * 1.1920929e-07f + 1e-30f;
+        if (!(ext > tiny)) ext = tiny;
+        float org;
+        for (;;) {
+            org = (float)(L - (double)ext);
+            if ((double)org + (double)ext > L) org = nextafterf(org, -3.0e38f);
+            if ((double)org + (double)ext * (255.0 / 128.0) >= H) break;
+            ext = ext * 1.0009765625f;
+        }
+        nd.org[a] = org;
+        nd.ext[a] = ext;
+        uint32_t wlo = 0x80808080u, whi = 0x80808080u;
+        for (int k = 0; k < nk; ++k) {
+            if (child[k] == RPTR_EMPTY) continue;
+            const double l = (double)lo[k][a], h = (double)hi[k][a], o = (double)org, e = (double)ext;
+            int ql = (int)floor((l - o - e) / e * 128.0), qh = (int)ceil((h - o - e) / e * 128.0);
+            ql = ql < 0 ? 0 : (ql > 127 ? 127 : ql);
+            qh = qh < 0 ? 0 : (qh > 127 ? 127 : qh);
+            while (ql > 0 && o + e * ((128.0 + ql) / 128.0) > l) --ql;
+            while (qh < 127 && o + e * ((128.0 + qh) / 128.0) < h) ++qh;
+            wlo = (wlo & ~(0xffu << (8 * k))) | ((0x80u | (uint32_t)ql) << (8 * k));
+            whi = (whi & ~(0xffu << (8 * k))) | ((0x80u | (uint32_t)qh) << (8 * k));
+        }
+        nd.qlo[a] = wlo;
+        nd.qhi[a] = whi;
+    }
+    for (int k = 0; k < RPTR_BVH_WIDTH; ++k) nd.child[k] = k < nk ? child[k] : RPTR_EMPTY;
+    return nd;
+}
+
+// Decoded box of child k (tests / validation).
+RPTR_HD void decode_child(const BvhNode &nd, int k, float *lo, float *hi) {
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = (float)((double)nd.org[a] + (double)qfloat(nd.qlo[a], k) * (double)nd.ext[a]);
+        hi[a] = (float)((double)nd.org[a] + (double)qfloat(nd.qhi[a], k) * (double)nd.ext[a]);
+    }
+}
 
 // Reference traversal (host-executable statement of the contract; the GPU's persistent kernel in
 // rptr_trace_kernels.cuh visits the same tree in a different order with the same result).  Any = stop at the first hit.
@@ -120,18 +208,17 @@ RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float 
     int32_t cur = 0;
     for (;;) {
         if (cur >= 0) {
-            const char *np = reinterpret_cast<const char *>(bvh.nodes + cur);
-            const float4 w0 = ld128(np), w1 = ld128(np + 16), w2 = ld128(np + 32), w3 = ld128(np + 48), w4 = ld128(np + 64),
-                         w5 = ld128(np + 80), w6 = ld128(np + 96);
+            const BvhNode &nd = bvh.nodes[cur];
             cnt.nodes++;
+            const NodeSlab ns = node_slab(nd.org[0], nd.org[1], nd.org[2], nd.ext[0], nd.ext[1], nd.ext[2], inv, ood);
             // hit children, nearest first into `cur`, the others onto the stack
             int32_t near_ref = RPTR_EMPTY;
             float near_t = 0.0f;
             for (int k = 0; k < RPTR_BVH_WIDTH; ++k) {
-                const int32_t ref = f2i(comp4(w6, k));
+                const int32_t ref = nd.child[k];
                 float tn;
                 if (ref == RPTR_EMPTY) continue;
-                if (!slab(comp4(w0, k), comp4(w1, k), comp4(w2, k), comp4(w3, k), comp4(w4, k), comp4(w5, k), inv, ood, tmin, best.t, tn)) continue;
+                if (!slab_q(ns, nd.qlo[0], nd.qlo[1], nd.qlo[2], nd.qhi[0], nd.qhi[1], nd.qhi[2], k, tmin, best.t, tn)) continue;
                 if (near_ref == RPTR_EMPTY) {
                     near_ref = ref; near_t = tn;
                 } else if (tn < near_t) {

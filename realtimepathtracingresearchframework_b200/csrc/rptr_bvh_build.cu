@@ -170,13 +170,8 @@ __global__ void k_collapse(const int32_t *cur, int32_t cur_count, int32_t level_
                 kids[nk++] = nodes[open].right;
             }
         }
-        BvhNode nd;
-        for (int k = 0; k < RPTR_BVH_WIDTH; ++k) {
-            nd.lox[k] = nd.loy[k] = nd.loz[k] = 1e30f;
-            nd.hix[k] = nd.hiy[k] = nd.hiz[k] = -1e30f;
-            nd.child[k] = RPTR_EMPTY;
-            nd.pad[k] = 0;
-        }
+        float clo[RPTR_BVH_WIDTH][3], chi[RPTR_BVH_WIDTH][3];
+        int32_t cref[RPTR_BVH_WIDTH];
         for (int k = 0; k < nk; ++k) {
             Box b;
             int32_t ref;
@@ -195,10 +190,10 @@ __global__ void k_collapse(const int32_t *cur, int32_t cur_count, int32_t level_
                     ref = next_base + (int32_t)pos;
                 }
             }
-            nd.lox[k] = b.lo[0]; nd.loy[k] = b.lo[1]; nd.loz[k] = b.lo[2];
-            nd.hix[k] = b.hi[0]; nd.hiy[k] = b.hi[1]; nd.hiz[k] = b.hi[2];
-            nd.child[k] = ref;
+            for (int a = 0; a < 3; ++a) { clo[k][a] = b.lo[a]; chi[k][a] = b.hi[a]; }
+            cref[k] = ref;
         }
+        const BvhNode nd = encode_node(clo, chi, cref, nk);
         out[level_base + i] = nd;
     }
 }
@@ -208,10 +203,10 @@ __global__ void k_gather_tris(const Tri *tris, const uint32_t *sorted, int32_t n
 }
 
 __global__ void k_swizzle_top(const BvhNode *nodes, int32_t top_k, BvhNode *top) {
-    // one thread per 16-byte word: word w of node i goes to word position w ^ (i & 7)
-    for (int32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < top_k * 8; t += gridDim.x * blockDim.x) {
-        const int32_t i = t >> 3, w = t & 7;
-        reinterpret_cast<float4 *>(top + i)[w ^ (i & 7)] = reinterpret_cast<const float4 *>(nodes + i)[w];
+    // one thread per 16-byte word: word w of node i goes to word position w ^ ((i >> 1) & 3)
+    for (int32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < top_k * 4; t += gridDim.x * blockDim.x) {
+        const int32_t i = t >> 2, w = t & 3;
+        reinterpret_cast<float4 *>(top + i)[w ^ ((i >> 1) & 3)] = reinterpret_cast<const float4 *>(nodes + i)[w];
     }
 }
 
@@ -257,7 +252,7 @@ bool build_bvh_device(const std::vector<Tri> &tris, float extent, const float *c
     CUB_OK(cudaMalloc(&d_out, sizeof(BvhNode) * max_nodes));
     CUB_OK(cudaMemcpyAsync(d_tris, tris.data(), sizeof(Tri) * n, cudaMemcpyHostToDevice, stream));
     {
-        const float abs_pad = 3.814697265625e-06f * extent;
+        const float abs_pad = 7.62939453125e-06f * extent;
         float3 mn = make_float3(cmin[0], cmin[1], cmin[2]);
         float3 sc = make_float3(2097152.0f / fmaxf(cmax[0] - cmin[0], 1e-30f), 2097152.0f / fmaxf(cmax[1] - cmin[1], 1e-30f),
                                 2097152.0f / fmaxf(cmax[2] - cmin[2], 1e-30f));

@@ -639,8 +639,8 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     for (int32_t i = 0; i < top_k; ++i) {
         const unsigned char *src = reinterpret_cast<const unsigned char *>(&hs.nodes[i]);
         unsigned char *dst = reinterpret_cast<unsigned char *>(&top[i]);
-        const int sw = i & 7;
-        for (int wd = 0; wd < 8; ++wd) memcpy(dst + ((wd ^ sw) << 4), src + (wd << 4), 16);
+        const int sw = (i >> 1) & 3;
+        for (int wd = 0; wd < 4; ++wd) memcpy(dst + ((wd ^ sw) << 4), src + (wd << 4), 16);
     }
     BvhNode *d_top;
     CU(dev_alloc(ctx, &d_top, top.size(), ctx->scene_allocs));
@@ -869,7 +869,7 @@ int rptr_cuda_get_counters(rptr_ctx *ctx, rptr_counters *out) {
     out->ms_shade = ctx->ms_shade;
     out->ms_other = ctx->ms_other;
     out->trace_launches = ctx->trace_launches;
-    out->node_bytes = sizeof(BvhNode) - 16; // 7 of the 8 words are fetched
+    out->node_bytes = sizeof(BvhNode);
     out->tri_bytes = sizeof(Tri);
     out->bvh_nodes = (uint64_t)ctx->bvh.n_nodes;
     out->bvh_build_ms = ctx->bvh_build_ms;

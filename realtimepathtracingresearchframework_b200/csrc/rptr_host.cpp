@@ -454,25 +454,20 @@ int collapse(const Builder &b, HostScene &s) {
                 kids[nk++] = b.nodes[open].right;
             }
         }
-        BvhNode nd;
-        memset(&nd, 0, sizeof(nd));
-        for (int k = 0; k < RPTR_BVH_WIDTH; ++k) {
-            nd.lox[k] = nd.loy[k] = nd.loz[k] = 1e30f;
-            nd.hix[k] = nd.hiy[k] = nd.hiz[k] = -1e30f;
-            nd.child[k] = RPTR_EMPTY;
-        }
+        float clo[RPTR_BVH_WIDTH][3], chi[RPTR_BVH_WIDTH][3];
+        int32_t cref[RPTR_BVH_WIDTH];
         // children of the queue items appended so far = index the child node will get
         for (int k = 0; k < nk; ++k) {
             const Node2 &c = b.nodes[kids[k]];
-            nd.lox[k] = c.lo[0]; nd.loy[k] = c.lo[1]; nd.loz[k] = c.lo[2];
-            nd.hix[k] = c.hi[0]; nd.hiy[k] = c.hi[1]; nd.hiz[k] = c.hi[2];
-            if (is_leaf2(kids[k])) nd.child[k] = emit_leaf(kids[k]);
+            for (int a = 0; a < 3; ++a) { clo[k][a] = c.lo[a]; chi[k][a] = c.hi[a]; }
+            if (is_leaf2(kids[k])) cref[k] = emit_leaf(kids[k]);
             else {
-                nd.child[k] = (int32_t)queue.size();
+                cref[k] = (int32_t)queue.size();
                 queue.push_back(Item{kids[k], it.depth + 1});
             }
             s.sah_cost += area(kids[k]);
         }
+        const BvhNode nd = encode_node(clo, chi, cref, nk);
         s.nodes.push_back(nd);
     }
     return max_depth + 1;
@@ -492,7 +487,7 @@ void build_bvh(HostScene &s) {
     for (const Tri &t : s.tris)
         extent = fmaxf(extent, fmaxf(fmaxf(fabsf(t.v0x), fabsf(t.v0y)), fabsf(t.v0z)) + fmaxf(fmaxf(fabsf(t.e1x), fabsf(t.e1y)), fabsf(t.e1z)) +
                                    fmaxf(fmaxf(fabsf(t.e2x), fabsf(t.e2y)), fabsf(t.e2z)));
-    const float abs_pad = 3.814697265625e-06f * extent; // 2^-18 * extent
+    const float abs_pad = 7.62939453125e-06f * extent; // 2^-17 * extent
     for (size_t i = 0; i < s.tris.size(); ++i) {
         const Tri &t = s.tris[i];
         Prim &p = b.prims[i];
@@ -501,7 +496,7 @@ void build_bvh(HostScene &s) {
             float lo = fminf(v[0][k], fminf(v[1][k], v[2][k])), hi = fmaxf(v[0][k], fmaxf(v[1][k], v[2][k]));
             // conservative padding: box culling may never reject what intersect_tri accepts.  Both tests round at
             // ulp(|origin|) ~ 6e-8 |origin|, so the pad has a part relative to the coordinates (2^-16) and a part
-            // relative to the scene extent (2^-18): safe for ray origins within ~16 scene extents.
+            // relative to the scene extent (2^-17): safe for ray origins within ~16 scene extents.
             float pad = 1.52587890625e-05f * fmaxf(fabsf(lo), fabsf(hi)) + abs_pad + 1e-30f;
             p.lo[k] = lo - pad;
             p.hi[k] = hi + pad;

@@ -6,8 +6,8 @@
 // trip through its loop is at most one node step and one leaf step for the whole warp:
 //   * every lane owns one ray.  Lanes that have finished are refilled from the ray queue once at least
 //     RPTR_REFILL_LANES of them are idle (warp-aggregated fetch from a per-warp chunk: one global atomic per 256 rays);
-//   * NODE STEP: every lane whose current item is an inner node fetches it (4 x 128-bit words), slab-tests both child
-//     boxes and picks the next item;
+//   * NODE STEP: every lane whose current item is an inner node fetches it (64 bytes: 2 x 256-bit), slab-tests the four
+//     quantised child boxes and picks the next item;
 //   * a lane that reaches a leaf parks it in a register and keeps walking inner nodes from its stack (speculative
 //     traversal), so nearly all lanes take part in every node step;
 //   * LEAF STEP: run only when at least RPTR_LEAF_LANES lanes hold a parked leaf (warp ballot) or nobody has inner-node
@@ -84,7 +84,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #define RPTR_CHUNKS_PER_WARP 4 // target number of queue fetches per warp (tail balance) before the chunk is shortened
 #endif
 #ifndef RPTR_TRACE_THREADS
-#define RPTR_TRACE_THREADS 768 // one CTA per SM: 24 warps (80 registers each) share one 128 KB image of the top of the BVH
+#define RPTR_TRACE_THREADS 896 // one CTA per SM: 28 warps (<= 72 registers each) share one 64 KB image of the top of the BVH
 #endif
 #define RPTR_TMA_CHUNK 32768u
 // Traversal stack: the first RPTR_SMEM_STACK entries of every thread live in shared memory, laid out [entry][thread] so
@@ -94,13 +94,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #define RPTR_SMEM_STACK 16
 #endif
 #define RPTR_TRACE_SMEM_BYTES ((size_t)RPTR_TOP_NODES_MAX * sizeof(BvhNode) + (size_t)RPTR_SMEM_STACK * RPTR_TRACE_THREADS * sizeof(int32_t))
-#define RPTR_PUSH(v)                                                         \
-    {                                                                        \
-        if (sp < RPTR_SMEM_STACK) sstack[sp * RPTR_TRACE_THREADS] = (v);     \
-        else lstack[sp - RPTR_SMEM_STACK] = (v);                             \
-        ++sp;                                                                \
+// shared-window accesses by 32-bit address (a generic pointer would cost a window-base computation per push / pop)
+__device__ __forceinline__ void sts32(uint32_t addr, int32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ int32_t lds32(uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+// byte-permute with the selector as the immediate operand (nvcc otherwise keeps the constant as the immediate and
+// re-materialises every selector in a register)
+template <int K>
+__device__ __forceinline__ float qfloat_k(uint32_t word, uint32_t hi_const) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(hi_const), "n"(0x7044 | (K << 8)));
+    return __uint_as_float(r);
+}
+// slab test of child K against the per-node ray constants, branch free: returns the entry distance, or +inf on a miss.
+// qn* / qf* are the packed bounds on the near / far side of each axis (picked per node from the sign of the direction:
+// fma is monotonic, so this equals the min / max form of slab_q() bit for bit).
+template <int K>
+__device__ __forceinline__ float slab_k(const NodeSlab &n, uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx, uint32_t qfy,
+                                        uint32_t qfz, uint32_t hc, float tmin, float tmax, int32_t ref) {
+    const float nx = fmaf(qfloat_k<K>(qnx, hc), n.ax, n.bx), fx = fmaf(qfloat_k<K>(qfx, hc), n.ax, n.bx);
+    const float ny = fmaf(qfloat_k<K>(qny, hc), n.ay, n.by), fy = fmaf(qfloat_k<K>(qfy, hc), n.ay, n.by);
+    const float nz = fmaf(qfloat_k<K>(qnz, hc), n.az, n.bz), fz = fmaf(qfloat_k<K>(qfz, hc), n.az, n.bz);
+    float tf = fminf(fminf(fx, fy), fz);
+    float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    tf = fminf(tf * 1.0000004f, tmax);
+    return (tn <= tf) & (ref != RPTR_EMPTY) ? tn : __int_as_float(0x7f800000);
+}
+#define RPTR_STACK_STRIDE ((uint32_t)(RPTR_TRACE_THREADS * sizeof(int32_t)))
+#define RPTR_PUSH(v)                                                                  \
+    {                                                                                 \
+        if (sp < RPTR_SMEM_STACK) sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, (v)); \
+        else lstack[sp - RPTR_SMEM_STACK] = (v);                                      \
+        ++sp;                                                                         \
     }
-#define RPTR_POP() (sp > 0 ? (--sp, sp < RPTR_SMEM_STACK ? sstack[sp * RPTR_TRACE_THREADS] : lstack[sp - RPTR_SMEM_STACK]) : RPTR_EMPTY)
+#define RPTR_POP() (sp > 0 ? (--sp, sp < RPTR_SMEM_STACK ? lds32(sst + (uint32_t)sp * RPTR_STACK_STRIDE) : lstack[sp - RPTR_SMEM_STACK]) : RPTR_EMPTY)
 
 template <bool Any>
 __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhDev bvh, TraceIO io, unsigned long long *c_rays,
@@ -140,7 +170,10 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     int32_t node = RPTR_EMPTY; // current item: inner node (>= 0), leaf reference (< 0) or RPTR_EMPTY
     int32_t leaf = 0;          // parked leaf reference (< 0) or 0 = none
     int32_t lstack[RPTR_STACK_SIZE - RPTR_SMEM_STACK]; // overflow part of the traversal stack (local memory)
-    int32_t *sstack = reinterpret_cast<int32_t *>(smem_top + (size_t)RPTR_TOP_NODES_MAX * sizeof(BvhNode)) + threadIdx.x;
+    const uint32_t sst = smem_u32(smem_top + (size_t)RPTR_TOP_NODES_MAX * sizeof(BvhNode)) + threadIdx.x * (uint32_t)sizeof(int32_t);
+    // high bytes of the decoded box coordinates, kept opaque to ptxas so that it stays in a register and the selectors
+    // become immediates (n is never 2^32 - 1)
+    const uint32_t hc = n == 0xffffffffu ? 0u : 0x3f000000u;
     int sp = 0;
     uint32_t n_nodes = 0, n_tris = 0, n_rays = 0;
 
@@ -201,7 +234,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         const bool leaf_turn = __popc(parked0) >= RPTR_LEAF_LANES || inner0 == 0;
         const bool do_node = have && node >= 0;
         const bool do_leaf = leaf_turn && have && leaf != 0;
-        float4 w0, w1, w2, w3, w4, w5, w6, ta, tb, tc;
+        float4 w0, w1, w2, w3, ta, tb, tc;
         int32_t lf_first = 0, lf_cnt = 0;
         if (do_leaf) {
             const int32_t ref = ~leaf;
@@ -213,33 +246,38 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         if (do_node) {
             if (node < top_k) { // top of the tree: shared memory (LDS.128), words XOR-swizzled against bank conflicts
                 const unsigned char *sp_ = smem_top + (size_t)node * sizeof(BvhNode);
-                const int sw = node & 7;
+                const int sw = (node >> 1) & 3;
                 w0 = *reinterpret_cast<const float4 *>(sp_ + ((0 ^ sw) << 4));
                 w1 = *reinterpret_cast<const float4 *>(sp_ + ((1 ^ sw) << 4));
                 w2 = *reinterpret_cast<const float4 *>(sp_ + ((2 ^ sw) << 4));
                 w3 = *reinterpret_cast<const float4 *>(sp_ + ((3 ^ sw) << 4));
-                w4 = *reinterpret_cast<const float4 *>(sp_ + ((4 ^ sw) << 4));
-                w5 = *reinterpret_cast<const float4 *>(sp_ + ((5 ^ sw) << 4));
-                w6 = *reinterpret_cast<const float4 *>(sp_ + ((6 ^ sw) << 4));
-            } else { // 3 x 256-bit + 1 x 128-bit loads: every 32-byte sector of the node passes through L1 once
+            } else { // 2 x 256-bit loads: both 32-byte sectors of the node pass through L1 once
                 const char *np = reinterpret_cast<const char *>(bvh.nodes + node);
                 ld256(np, w0, w1);
                 ld256(np + 32, w2, w3);
-                ld256(np + 64, w4, w5);
-                w6 = ld128(np + 96);
             }
         }
         // ---- node step ----------------------------------------------------------------------------------------------
         if (do_node) {
             n_nodes++;
-            // four slab tests; a missed (or unused: inverted box) child gets key +inf and reference EMPTY
+            // four slab tests on the quantised child boxes; a missed or unused child gets key +inf and reference EMPTY
             const float INF = __int_as_float(0x7f800000);
-            float t0, t1, t2, t3;
-            int32_t r0 = f2i(w6.x), r1 = f2i(w6.y), r2 = f2i(w6.z), r3 = f2i(w6.w);
-            if (!slab(w0.x, w1.x, w2.x, w3.x, w4.x, w5.x, inv, ood, tmin, best_t, t0)) { t0 = INF; r0 = RPTR_EMPTY; }
-            if (!slab(w0.y, w1.y, w2.y, w3.y, w4.y, w5.y, inv, ood, tmin, best_t, t1)) { t1 = INF; r1 = RPTR_EMPTY; }
-            if (!slab(w0.z, w1.z, w2.z, w3.z, w4.z, w5.z, inv, ood, tmin, best_t, t2)) { t2 = INF; r2 = RPTR_EMPTY; }
-            if (!slab(w0.w, w1.w, w2.w, w3.w, w4.w, w5.w, inv, ood, tmin, best_t, t3)) { t3 = INF; r3 = RPTR_EMPTY; }
+            const NodeSlab ns = node_slab(w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, inv, ood);
+            const uint32_t qlx = __float_as_uint(w1.z), qly = __float_as_uint(w1.w), qlz = __float_as_uint(w2.x);
+            const uint32_t qhx = __float_as_uint(w2.y), qhy = __float_as_uint(w2.z), qhz = __float_as_uint(w2.w);
+            const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
+            const uint32_t qnx = sx ? qhx : qlx, qfx = sx ? qlx : qhx;
+            const uint32_t qny = sy ? qhy : qly, qfy = sy ? qly : qhy;
+            const uint32_t qnz = sz ? qhz : qlz, qfz = sz ? qlz : qhz;
+            int32_t r0 = f2i(w3.x), r1 = f2i(w3.y), r2 = f2i(w3.z), r3 = f2i(w3.w);
+            float t0 = slab_k<0>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r0);
+            float t1 = slab_k<1>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r1);
+            float t2 = slab_k<2>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r2);
+            float t3 = slab_k<3>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r3);
+            r0 = t0 < INF ? r0 : RPTR_EMPTY;
+            r1 = t1 < INF ? r1 : RPTR_EMPTY;
+            r2 = t2 < INF ? r2 : RPTR_EMPTY;
+            r3 = t3 < INF ? r3 : RPTR_EMPTY;
             // 5-comparator sorting network on (t, ref): nearest first
 #define RPTR_CSWAP(ta_, ra, tb_, rb)                                 \
     {                                                               \
@@ -255,9 +293,15 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             RPTR_CSWAP(t1, r1, t2, r2)
 #undef RPTR_CSWAP
             // continue with the nearest hit, push the others farthest first
-            if (r3 != RPTR_EMPTY) RPTR_PUSH(r3);
-            if (r2 != RPTR_EMPTY) RPTR_PUSH(r2);
-            if (r1 != RPTR_EMPTY) RPTR_PUSH(r1);
+            if (sp + 3 <= RPTR_SMEM_STACK) { // common case, branch free: store unconditionally, advance when the entry is valid
+                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r3); sp += r3 != RPTR_EMPTY;
+                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r2); sp += r2 != RPTR_EMPTY;
+                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r1); sp += r1 != RPTR_EMPTY;
+            } else {
+                if (r3 != RPTR_EMPTY) RPTR_PUSH(r3);
+                if (r2 != RPTR_EMPTY) RPTR_PUSH(r2);
+                if (r1 != RPTR_EMPTY) RPTR_PUSH(r1);
+            }
             node = r0 != RPTR_EMPTY ? r0 : RPTR_POP();
             // park a leaf and go on with whatever the stack holds (speculative traversal); when this lane's parked leaf
             // is being processed in this trip the slot frees up below
