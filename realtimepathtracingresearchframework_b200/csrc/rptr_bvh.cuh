@@ -47,9 +47,10 @@ struct BvhDev {
     const Tri *tris;      // leaf order
     int32_t n_nodes;
     int32_t n_tris;
-    // the first top_k nodes again, with the four 16-byte words of node i stored at word position w ^ ((i >> 1) & 3):
-    // the image a CTA of the trace kernel copies into shared memory (the XOR spreads random nodes over the banks)
-    const BvhNode *top_swizzled;
+    // the first top_k nodes again, split into four planes of 16-byte words (plane w at byte w * 16 * RPTR_TOP_NODES_MAX
+    // holds word w of node 0, 1, ...): the image a CTA of the trace kernel copies into shared memory.  A warp reading
+    // word w of 32 random nodes then spreads over all banks, and the four addresses differ by immediates.
+    const float4 *top_planes;
     int32_t top_k;
 };
 

@@ -13,7 +13,7 @@
 //   k_refit       bottom-up boxes through atomic arrival counters
 //   k_collapse    level by level: opens the largest child until 4 are held, subtrees of <= 4 triangles become leaves
 //                 (their triangles are contiguous in Morton order, so the leaf triangle array is just the sorted array)
-//   k_gather_tris / k_swizzle_top   leaf-order triangle records, shared-memory image of the first nodes
+//   k_gather_tris / k_top_planes    leaf-order triangle records, shared-memory image of the first nodes
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 
@@ -202,11 +202,11 @@ __global__ void k_gather_tris(const Tri *tris, const uint32_t *sorted, int32_t n
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) leaf_tris[i] = tris[sorted[i]];
 }
 
-__global__ void k_swizzle_top(const BvhNode *nodes, int32_t top_k, BvhNode *top) {
-    // one thread per 16-byte word: word w of node i goes to word position w ^ ((i >> 1) & 3)
+__global__ void k_top_planes(const BvhNode *nodes, int32_t top_k, float4 *planes) {
+    // one thread per 16-byte word: word w of node i goes to plane w, slot i
     for (int32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < top_k * 4; t += gridDim.x * blockDim.x) {
         const int32_t i = t >> 2, w = t & 3;
-        reinterpret_cast<float4 *>(top + i)[w ^ ((i >> 1) & 3)] = reinterpret_cast<const float4 *>(nodes + i)[w];
+        planes[w * RPTR_TOP_NODES_MAX + i] = reinterpret_cast<const float4 *>(nodes + i)[w];
     }
 }
 
@@ -229,7 +229,8 @@ bool build_bvh_device(const std::vector<Tri> &tris, float extent, const float *c
     uint32_t *d_vals = nullptr, *d_sorted = nullptr, *d_arrivals = nullptr, *d_count = nullptr;
     Node2 *d_nodes2 = nullptr;
     int32_t *d_leaf_parent = nullptr, *d_q[2] = {nullptr, nullptr};
-    BvhNode *d_out = nullptr, *d_top = nullptr;
+    BvhNode *d_out = nullptr;
+    float4 *d_top = nullptr;
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
     const int grid = num_sms * 8;
@@ -292,8 +293,9 @@ bool build_bvh_device(const std::vector<Tri> &tris, float extent, const float *c
         out.depth = depth;
     }
     out.top_k = out.n_nodes < RPTR_TOP_NODES_MAX ? out.n_nodes : RPTR_TOP_NODES_MAX;
-    CUB_OK(cudaMalloc(&d_top, sizeof(BvhNode) * (out.top_k > 0 ? out.top_k : 1)));
-    if (out.top_k > 0) k_swizzle_top<<<64, 256, 0, stream>>>(d_out, out.top_k, d_top);
+    CUB_OK(cudaMalloc(&d_top, sizeof(float4) * 4 * RPTR_TOP_NODES_MAX));
+    CUB_OK(cudaMemsetAsync(d_top, 0, sizeof(float4) * 4 * RPTR_TOP_NODES_MAX, stream));
+    if (out.top_k > 0) k_top_planes<<<64, 256, 0, stream>>>(d_out, out.top_k, d_top);
     CUB_OK(cudaStreamSynchronize(stream));
     CUB_OK(cudaGetLastError());
     out.nodes = d_out;

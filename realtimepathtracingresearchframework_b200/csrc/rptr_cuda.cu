@@ -633,18 +633,14 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     if (!hs.nodes.empty()) CU(cudaMemcpy(d_nodes, hs.nodes.data(), hs.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
     CU(dev_alloc(ctx, &d_tris, hs.leaf_tris.size(), ctx->scene_allocs));
     if (!hs.leaf_tris.empty()) CU(cudaMemcpy(d_tris, hs.leaf_tris.data(), hs.leaf_tris.size() * sizeof(Tri), cudaMemcpyHostToDevice));
-    // swizzled image of the top of the (breadth-first ordered) tree for the trace kernel's shared-memory stage
+    // word planes of the top of the (breadth-first ordered) tree for the trace kernel's shared-memory stage
     const int32_t top_k = (int32_t)std::min<size_t>(hs.nodes.size(), RPTR_TOP_NODES_MAX);
-    std::vector<BvhNode> top(top_k > 0 ? top_k : 1);
-    for (int32_t i = 0; i < top_k; ++i) {
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(&hs.nodes[i]);
-        unsigned char *dst = reinterpret_cast<unsigned char *>(&top[i]);
-        const int sw = (i >> 1) & 3;
-        for (int wd = 0; wd < 4; ++wd) memcpy(dst + ((wd ^ sw) << 4), src + (wd << 4), 16);
-    }
-    BvhNode *d_top;
+    std::vector<float4> top(4 * RPTR_TOP_NODES_MAX, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    for (int32_t i = 0; i < top_k; ++i)
+        for (int wd = 0; wd < 4; ++wd) memcpy(&top[(size_t)wd * RPTR_TOP_NODES_MAX + i], reinterpret_cast<const unsigned char *>(&hs.nodes[i]) + (wd << 4), 16);
+    float4 *d_top;
     CU(dev_alloc(ctx, &d_top, top.size(), ctx->scene_allocs));
-    CU(cudaMemcpy(d_top, top.data(), top.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_top, top.data(), top.size() * sizeof(float4), cudaMemcpyHostToDevice));
     ctx->scene = SceneDev{d_gi, d_mat, d_lights};
     ctx->bvh = BvhDev{d_nodes, d_tris, (int32_t)hs.nodes.size(), (int32_t)hs.leaf_tris.size(), d_top, top_k};
     ctx->n_lights = (int32_t)hs.lights.size();

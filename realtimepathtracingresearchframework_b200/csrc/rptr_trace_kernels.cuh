@@ -23,10 +23,10 @@ namespace rp {
 #define RPTR_FETCH_CHUNK 256
 #endif
 #ifndef RPTR_REFILL_LANES
-#define RPTR_REFILL_LANES 8
+#define RPTR_REFILL_LANES 4
 #endif
 #ifndef RPTR_LEAF_LANES
-#define RPTR_LEAF_LANES 8
+#define RPTR_LEAF_LANES 12
 #endif
 
 struct TraceIO {
@@ -86,7 +86,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #ifndef RPTR_TRACE_THREADS
 #define RPTR_TRACE_THREADS 896 // one CTA per SM: 28 warps (<= 72 registers each) share one 64 KB image of the top of the BVH
 #endif
-#define RPTR_TMA_CHUNK 32768u
+#define RPTR_TOP_PLANE_BYTES (RPTR_TOP_NODES_MAX * 16)
 // Traversal stack: the first RPTR_SMEM_STACK entries of every thread live in shared memory, laid out [entry][thread] so
 // that the bank only depends on the lane (any mix of stack depths in a warp is conflict free: one wavefront per push /
 // pop instead of up to 32 sectors through local memory); deeper entries spill to a local-memory array.
@@ -99,6 +99,12 @@ __device__ __forceinline__ void sts32(uint32_t addr, int32_t v) { asm volatile("
 __device__ __forceinline__ int32_t lds32(uint32_t addr) {
     int32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF) : "memory");
     return v;
 }
 // byte-permute with the selector as the immediate operand (nvcc otherwise keeps the constant as the immediate and
@@ -135,23 +141,24 @@ __device__ __forceinline__ float slab_k(const NodeSlab &n, uint32_t qnx, uint32_
 template <bool Any>
 __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhDev bvh, TraceIO io, unsigned long long *c_rays,
                                                                             unsigned long long *c_nodes, unsigned long long *c_tris) {
-    extern __shared__ __align__(128) unsigned char smem_top[]; // top_k swizzled nodes
+    extern __shared__ __align__(128) unsigned char smem_top[]; // four word planes of the top_k first nodes, then the stacks
     __shared__ __align__(8) uint64_t top_bar;
     const uint32_t n = *io.count;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     // ---- stage the top of the tree: TMA bulk copies issued by one thread, completion through an mbarrier ----
-    const uint32_t top_bytes = (uint32_t)bvh.top_k * (uint32_t)sizeof(BvhNode);
+    const uint32_t plane_bytes = (uint32_t)bvh.top_k * 16u; // one 16-byte word of each staged node
     if (threadIdx.x == 0) mbar_init(&top_bar, 1);
     __syncthreads();
-    if (threadIdx.x == 0 && n > 0) {
-        mbar_expect_tx(&top_bar, top_bytes);
-        for (uint32_t off = 0; off < top_bytes; off += RPTR_TMA_CHUNK)
-            tma_bulk_g2s(smem_top + off, reinterpret_cast<const unsigned char *>(bvh.top_swizzled) + off,
-                         min(RPTR_TMA_CHUNK, top_bytes - off), &top_bar);
+    if (threadIdx.x == 0 && n > 0 && plane_bytes > 0) {
+        mbar_expect_tx(&top_bar, 4u * plane_bytes);
+        for (uint32_t w = 0; w < 4; ++w)
+            tma_bulk_g2s(smem_top + w * RPTR_TOP_PLANE_BYTES, reinterpret_cast<const unsigned char *>(bvh.top_planes) + w * RPTR_TOP_PLANE_BYTES,
+                         plane_bytes, &top_bar);
     }
-    if (n > 0) mbar_wait(&top_bar, 0);
+    if (n > 0 && plane_bytes > 0) mbar_wait(&top_bar, 0);
     const int32_t top_k = bvh.top_k;
+    const uint32_t top_base = smem_u32(smem_top);
     // Rays per queue fetch: RPTR_FETCH_CHUNK for long queues (few atomics, coherent warps); short queues (late bounces)
     // are cut finer so that every warp of the grid gets work instead of a few warps walking 256 rays 32 at a time.
     // Guided self-scheduling: the size is recomputed from what is left of the queue at every fetch.
@@ -244,13 +251,10 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             ta = ld128(tp); tb = ld128(tp + 16); tc = ld128(tp + 32);
         }
         if (do_node) {
-            if (node < top_k) { // top of the tree: shared memory (LDS.128), words XOR-swizzled against bank conflicts
-                const unsigned char *sp_ = smem_top + (size_t)node * sizeof(BvhNode);
-                const int sw = (node >> 1) & 3;
-                w0 = *reinterpret_cast<const float4 *>(sp_ + ((0 ^ sw) << 4));
-                w1 = *reinterpret_cast<const float4 *>(sp_ + ((1 ^ sw) << 4));
-                w2 = *reinterpret_cast<const float4 *>(sp_ + ((2 ^ sw) << 4));
-                w3 = *reinterpret_cast<const float4 *>(sp_ + ((3 ^ sw) << 4));
+            if (node < top_k) { // top of the tree: shared memory, one LDS.128 per word plane (address = base + 16 * node)
+                const uint32_t a = top_base + ((uint32_t)node << 4);
+                w0 = lds128<0>(a); w1 = lds128<RPTR_TOP_PLANE_BYTES>(a);
+                w2 = lds128<2 * RPTR_TOP_PLANE_BYTES>(a); w3 = lds128<3 * RPTR_TOP_PLANE_BYTES>(a);
             } else { // 2 x 256-bit loads: both 32-byte sectors of the node pass through L1 once
                 const char *np = reinterpret_cast<const char *>(bvh.nodes + node);
                 ld256(np, w0, w1);
@@ -274,10 +278,6 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             float t1 = slab_k<1>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r1);
             float t2 = slab_k<2>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r2);
             float t3 = slab_k<3>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r3);
-            r0 = t0 < INF ? r0 : RPTR_EMPTY;
-            r1 = t1 < INF ? r1 : RPTR_EMPTY;
-            r2 = t2 < INF ? r2 : RPTR_EMPTY;
-            r3 = t3 < INF ? r3 : RPTR_EMPTY;
             // 5-comparator sorting network on (t, ref): nearest first
 #define RPTR_CSWAP(ta_, ra, tb_, rb)                                 \
     {                                                               \
@@ -292,17 +292,17 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             RPTR_CSWAP(t1, r1, t3, r3)
             RPTR_CSWAP(t1, r1, t2, r2)
 #undef RPTR_CSWAP
-            // continue with the nearest hit, push the others farthest first
+            // continue with the nearest hit, push the others farthest first (a key of +inf marks a missed / unused child)
             if (sp + 3 <= RPTR_SMEM_STACK) { // common case, branch free: store unconditionally, advance when the entry is valid
-                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r3); sp += r3 != RPTR_EMPTY;
-                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r2); sp += r2 != RPTR_EMPTY;
-                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r1); sp += r1 != RPTR_EMPTY;
+                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r3); sp += t3 < INF;
+                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r2); sp += t2 < INF;
+                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r1); sp += t1 < INF;
             } else {
-                if (r3 != RPTR_EMPTY) RPTR_PUSH(r3);
-                if (r2 != RPTR_EMPTY) RPTR_PUSH(r2);
-                if (r1 != RPTR_EMPTY) RPTR_PUSH(r1);
+                if (t3 < INF) RPTR_PUSH(r3);
+                if (t2 < INF) RPTR_PUSH(r2);
+                if (t1 < INF) RPTR_PUSH(r1);
             }
-            node = r0 != RPTR_EMPTY ? r0 : RPTR_POP();
+            node = t0 < INF ? r0 : RPTR_POP();
             // park a leaf and go on with whatever the stack holds (speculative traversal); when this lane's parked leaf
             // is being processed in this trip the slot frees up below
             if (node < 0 && node != RPTR_EMPTY && leaf == 0) {
