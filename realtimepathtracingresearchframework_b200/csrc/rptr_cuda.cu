@@ -122,7 +122,10 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
 #define RPTR_SHADE_PER_THREAD 4
 #define RPTR_SHADE_TILE (RPTR_SHADE_THREADS * RPTR_SHADE_PER_THREAD)
 #define RPTR_SHADE_KEYS 16
-__global__ void __launch_bounds__(RPTR_SHADE_THREADS) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
+#ifndef RPTR_SHADE_MIN_BLOCKS
+#define RPTR_SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
                                                               const uint32_t *count, uint32_t *next_queue, uint32_t *next_count,
                                                               uint32_t *shadow_count, DevCounters *dc) {
     __shared__ uint32_t s_hist[RPTR_SHADE_KEYS], s_base[RPTR_SHADE_KEYS];
@@ -179,25 +182,28 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS) k_shade(FrameParams fp, Sc
             sh.tmax = -1.0f;
             if (active) {
                 slot = s_sorted[j];
-                const float4 o = w.ray_o[slot], d = w.ray_d[slot], hit = w.hit[slot], thr = w.thr[slot], il = w.illum[slot];
-                const uint2 rb = w.rngb[slot];
-                PathState ps;
-                ps.o = f3(o.x, o.y, o.z); ps.tmin = o.w;
-                ps.d = f3(d.x, d.y, d.z); ps.tmax = d.w;
-                ps.thr = f3(thr.x, thr.y, thr.z); ps.prev_pdf = thr.w;
-                ps.illum = f3(il.x, il.y, il.z); ps.total_t = il.w;
-                ps.rng = rb.x; ps.bounce = (int)rb.y;
+                const float4 hit = w.hit[slot];
                 const int tri = __float_as_int(hit.w);
-                if (tri >= 0) verts++;
-                ShadeResult r = shade_vertex(fp, sc, ps, hit.x, hit.y, hit.z, tri >= 0 ? &bvh.tris[tri] : nullptr, sh);
-                cont = r == SHADE_CONTINUE;
-                shadow = sh.tmax > 0.0f;
-                w.illum[slot] = f4(ps.illum.x, ps.illum.y, ps.illum.z, ps.total_t);
-                w.rngb[slot] = make_uint2(ps.rng, (uint32_t)ps.bounce);
-                if (cont) {
-                    w.ray_o[slot] = f4(ps.o.x, ps.o.y, ps.o.z, ps.tmin);
-                    w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
-                    w.thr[slot] = f4(ps.thr.x, ps.thr.y, ps.thr.z, ps.prev_pdf);
+                if (tri >= 0) { // a miss ends the path; its sky term is added by k_resolve from the untouched path state
+                    const float4 o = w.ray_o[slot], d = w.ray_d[slot], thr = w.thr[slot], il = w.illum[slot];
+                    const uint2 rb = w.rngb[slot];
+                    PathState ps;
+                    ps.o = f3(o.x, o.y, o.z); ps.tmin = o.w;
+                    ps.d = f3(d.x, d.y, d.z); ps.tmax = d.w;
+                    ps.thr = f3(thr.x, thr.y, thr.z); ps.prev_pdf = thr.w;
+                    ps.illum = f3(il.x, il.y, il.z); ps.total_t = il.w;
+                    ps.rng = rb.x; ps.bounce = (int)rb.y;
+                    verts++;
+                    ShadeResult r = shade_hit(fp, sc, ps, hit.x, hit.y, hit.z, &bvh.tris[tri], sh);
+                    cont = r == SHADE_CONTINUE;
+                    shadow = sh.tmax > 0.0f;
+                    w.illum[slot] = f4(ps.illum.x, ps.illum.y, ps.illum.z, ps.total_t);
+                    w.rngb[slot] = make_uint2(ps.rng, (uint32_t)ps.bounce);
+                    if (cont) {
+                        w.ray_o[slot] = f4(ps.o.x, ps.o.y, ps.o.z, ps.tmin);
+                        w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
+                        w.thr[slot] = f4(ps.thr.x, ps.thr.y, ps.thr.z, ps.prev_pdf);
+                    }
                 }
             }
             __syncwarp();
@@ -240,7 +246,10 @@ __global__ void __launch_bounds__(128) k_shadow(BvhDev bvh, Wave w, const uint32
 
 // accumulate.glsl:68-73 + process_samples.comp:116-129 replayed in sample order for the layers of this wave:
 // sample k (0-based since the last reset) is stored when k == 0 and folded as m += (x - m) / float(k + 1) otherwise.
-__global__ void __launch_bounds__(256) k_resolve(TileMap tm, Wave w, float4 *accum, uint32_t first_sample, int32_t n_layers, DevCounters *dc) {
+// Paths that ended with a miss (hit record still says "no triangle") get their sky / sun-disc term here, from the ray
+// direction, throughput and previous-bounce pdf they died with (shade_miss).
+__global__ void __launch_bounds__(256) k_resolve(rptr_scene_params sp, TileMap tm, Wave w, float4 *accum, uint32_t first_sample, int32_t n_layers,
+                                                 DevCounters *dc) {
     unsigned long long samples = 0;
     for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < (uint32_t)tm.local_pixels; lp += gridDim.x * blockDim.x) {
         const int32_t px = (int32_t)(lp % (uint32_t)tm.width);
@@ -249,8 +258,13 @@ __global__ void __launch_bounds__(256) k_resolve(TileMap tm, Wave w, float4 *acc
         float4 m = *dst;
         for (int32_t l = 0; l < n_layers; ++l) {
             const uint32_t slot = (uint32_t)l * (uint32_t)tm.local_pixels + lp;
-            const float4 il = w.illum[slot];
+            float4 il = w.illum[slot];
             const float alpha = w.rngb[slot].y == 0u ? 0.0f : 1.0f;
+            if (__float_as_int(w.hit[slot].w) < 0) {
+                const float4 d = w.ray_d[slot], thr = w.thr[slot];
+                const float3 r = shade_miss(sp, f3(il.x, il.y, il.z), f3(thr.x, thr.y, thr.z), f3(d.x, d.y, d.z), thr.w);
+                il.x = r.x; il.y = r.y; il.z = r.z;
+            }
             const uint32_t k = first_sample + (uint32_t)l;
             if (k > 0) {
                 const float denom = (float)(k + 1u);
@@ -797,7 +811,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
             }
             {
                 StageTimer t(ctx, 3);
-                k_resolve<<<g_light, 256, 0, ctx->stream>>>(tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters);
+                k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp.sp, tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters);
                 ctx->launches++;
             }
         }

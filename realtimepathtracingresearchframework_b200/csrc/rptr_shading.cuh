@@ -708,14 +708,16 @@ RPTR_HD void generate_primary(const FrameParams &fp, int px, int py, uint32_t sa
 // Shades the vertex found by the closest-hit stage (tri < 0: miss).  On SHADE_CONTINUE ps holds the next ray.
 // sh.tmax < 0 means "no shadow ray"; sh.tmax == 0 means "visible without tracing" (the contribution is then
 // already added to ps.illum).  Restates pt_megakernel.glsl:480-731 + shade_base_material.glsl:14-96 + nee.glsl:32-90.
-RPTR_HD ShadeResult shade_vertex(const FrameParams &fp, const SceneDev &sc, PathState &ps, float hit_t, float hit_u, float hit_v,
-                                const Tri *tri, ShadowRay &sh) {
+// A path that leaves the scene: sky + sun disc, weighted against the sun's NEE pdf (pt_megakernel.glsl:113-149, 480-489).
+// The wavefront defers this to the resolve kernel (the miss is always the last event of a path, so the sum is the same).
+RPTR_HD float3 shade_miss(const rptr_scene_params &sp, float3 illum, float3 thr, float3 dir, float prev_pdf) {
+    return illum + thr * compute_sky_illum(sp, dir, prev_pdf);
+}
+
+RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathState &ps, float hit_t, float hit_u, float hit_v, const Tri *tri,
+                             ShadowRay &sh) {
     sh.tmax = -1.0f;
     const rptr_scene_params &sp = fp.sp;
-    if (!tri) {
-        ps.illum = ps.illum + ps.thr * compute_sky_illum(sp, ps.d, ps.prev_pdf);
-        return SHADE_TERMINATE;
-    }
     const bool tr = fp.transmission != 0;
     const GeomInst &g = sc.ginst[tri->geom_inst];
     RTHit h = calc_hit_attributes(g, hit_t, (uint32_t)tri->prim, hit_u, hit_v);
@@ -840,6 +842,17 @@ RPTR_HD ShadeResult shade_vertex(const FrameParams &fp, const SceneDev &sc, Path
         else return SHADE_TERMINATE;
     }
     return SHADE_CONTINUE;
+}
+
+// One path vertex (hit or miss) -- the megakernel-order statement used by the host-side simulation and the unit tests.
+RPTR_HD ShadeResult shade_vertex(const FrameParams &fp, const SceneDev &sc, PathState &ps, float hit_t, float hit_u, float hit_v,
+                                const Tri *tri, ShadowRay &sh) {
+    sh.tmax = -1.0f;
+    if (!tri) {
+        ps.illum = shade_miss(fp.sp, ps.illum, ps.thr, ps.d, ps.prev_pdf);
+        return SHADE_TERMINATE;
+    }
+    return shade_hit(fp, sc, ps, hit_t, hit_u, hit_v, tri, sh);
 }
 
 } // namespace rp
