@@ -38,8 +38,8 @@ template <class T> struct tvec3 {
     const T &operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
 };
 template <class T> struct tvec4 {
-    union { T x, r; };
-    union { T y, g; };
+    // .xy is the one GLSL swizzle the Z-order Sobol sampler needs (rendering/pointsets/sobol.glsl:174)
+    union { struct { union { T x, r; }; union { T y, g; }; }; tvec2<T> xy; };
     union { T z, b; };
     union { T w, a; };
     tvec4() : x(0), y(0), z(0), w(0) {}
@@ -97,6 +97,15 @@ template <class T> inline bool operator==(tvec3<T> a, tvec3<T> b) { return a.x =
 template <class T> inline bool operator!=(tvec3<T> a, tvec3<T> b) { return !(a == b); }
 inline uvec3 operator&(uvec3 a, uvec3 b) { return uvec3(a.x & b.x, a.y & b.y, a.z & b.z); }
 inline uvec2 operator&(uvec2 a, uvec2 b) { return uvec2(a.x & b.x, a.y & b.y); }
+// integer built-ins used by rendering/pointsets/{sobol,sample_order}.glsl
+typedef tvec2<bool> bvec2;
+inline int bitCount(uint v) { return __builtin_popcount(v); }
+inline int findMSB(uint v) { return v ? 31 - __builtin_clz(v) : -1; }
+inline ivec2 findMSB(uvec2 v) { return ivec2(findMSB(v.x), findMSB(v.y)); }
+inline bvec2 notEqual(uvec2 a, uvec2 b) { return bvec2(a.x != b.x, a.y != b.y); }
+inline uvec2 operator<<(uvec2 a, ivec2 b) { return uvec2(a.x << b.x, a.y << b.y); }
+inline uvec2 operator<<(uvec2 a, uvec2 b) { return uvec2(a.x << b.x, a.y << b.y); }
+inline uvec4 operator>>(uvec4 a, uint b) { return uvec4(a.x >> b, a.y >> b, a.z >> b, a.w >> b); }
 
 // --- scalar built-ins -------------------------------------------------------------------------------------------
 using std::abs; using std::sqrt; using std::sin; using std::cos; using std::tan; using std::exp; using std::log;

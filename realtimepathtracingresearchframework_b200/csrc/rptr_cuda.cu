@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
 #ifndef RPTR_SHADE_MIN_BLOCKS
 #define RPTR_SHADE_MIN_BLOCKS 4
 #endif
+template <int FEAT>
 __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
                                                               const uint32_t *count, uint32_t *next_queue, uint32_t *next_count,
                                                               uint32_t *shadow_count, DevCounters *dc) {
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                     const rptr_base_material &m = sc.materials[calc_hit_material_id(g, (uint32_t)tr->prim)];
                     key = 1u;
                     if (m.ior > 1.0f) key = 2u;
-                    if (fp.transmission && m.ior > 1.0f && m.specular_transmission > 0.0f) key = (m.flags & RPTR_BASE_MATERIAL_ONESIDED) ? 4u : 3u;
+                    if ((FEAT & RPTR_FEAT_TRANSMISSION) && fp.transmission && m.ior > 1.0f && m.specular_transmission > 0.0f) key = (m.flags & RPTR_BASE_MATERIAL_ONESIDED) ? 4u : 3u;
                     if (m.emission_intensity != 0.0f) key += 5u;
                 }
                 my_slot[k] = slot;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                     ps.illum = f3(il.x, il.y, il.z); ps.total_t = il.w;
                     ps.rng = rb.x; ps.bounce = (int)rb.y;
                     verts++;
-                    ShadeResult r = shade_hit(fp, sc, ps, hit.x, hit.y, hit.z, &bvh.tris[tri], sh);
+                    ShadeResult r = shade_hit<FEAT>(fp, sc, ps, hit.x, hit.y, hit.z, &bvh.tris[tri], sh);
                     cont = r == SHADE_CONTINUE;
                     shadow = sh.tmax > 0.0f;
                     w.illum[slot] = f4(ps.illum.x, ps.illum.y, ps.illum.z, ps.total_t);
@@ -795,7 +796,14 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                 }
                 {
                     StageTimer t(ctx, 1);
-                    k_shade<<<g_trace, 128, 0, ctx->stream>>>(fp, ctx->scene, ctx->bvh, w, q, cn, nq, cn + 4, cn + 1, ctx->dcounters);
+                    // smallest compiled variant that covers the features this frame uses (rptr_shading.cuh, RPTR_FEAT_*)
+                    const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
+                                     (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0);
+#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, q, cn, nq, cn + 4, cn + 1, ctx->dcounters
+                    if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
+                    else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
+                    else k_shade<RPTR_FEAT_ALL><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
+#undef RPTR_SHADE_ARGS
                     ctx->launches++;
                 }
                 if (fp.output_channel == 0 && d + 1 < depth) {

@@ -714,11 +714,19 @@ RPTR_HD float3 shade_miss(const rptr_scene_params &sp, float3 illum, float3 thr,
     return illum + thr * compute_sky_illum(sp, dir, prev_pdf);
 }
 
+// FEAT: code paths compiled in (the reference compiles its shader variants from #defines the same way, e.g.
+// GLTF_SUPPORT_TRANSMISSION); a kernel built without a feature must only be launched when the frame does not use it.
+#define RPTR_FEAT_TRANSMISSION 1 // fp.transmission may be set
+#define RPTR_FEAT_TRI_LIGHTS 2   // the scene has binned triangle lights (p_sun < 1)
+#define RPTR_FEAT_AOV 4          // fp.output_channel may be non-zero
+#define RPTR_FEAT_ALL 7
+template <int FEAT = RPTR_FEAT_ALL>
 RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathState &ps, float hit_t, float hit_u, float hit_v, const Tri *tri,
                              ShadowRay &sh) {
     sh.tmax = -1.0f;
     const rptr_scene_params &sp = fp.sp;
-    const bool tr = fp.transmission != 0;
+    const bool tr = (FEAT & RPTR_FEAT_TRANSMISSION) && fp.transmission != 0;
+    const int output_channel = (FEAT & RPTR_FEAT_AOV) ? fp.output_channel : 0;
     const GeomInst &g = sc.ginst[tri->geom_inst];
     RTHit h = calc_hit_attributes(g, hit_t, (uint32_t)tri->prim, hit_u, hit_v);
     float approx_sa = length(h.geo_normal);
@@ -753,19 +761,19 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
     float3 emit;
     unpack_material(mat, emit, mp, tr);
     const float p_sun = sp.sun_radiance[3];
-    if (fp.output_channel == 0 && !is_zero(emit)) {
+    if (output_channel == 0 && !is_zero(emit)) {
         float light_pdf = (1.0f - p_sun) * (1.0f / ((float)fp.n_bins * approx_sa));
         float w = nee_mis_heuristic(1.0f, ps.prev_pdf, 1.0f, light_pdf);
         ps.illum = ps.illum + ps.thr * w * emit;
     }
-    if (fp.output_channel != 0) {
+    if (output_channel != 0) {
         float reliability = u2f((uint32_t)(127 - 2 * ps.bounce) << 23); // pow(0.25, bounce)
-        if (fp.output_channel == 1) ps.illum = ps.illum + ps.thr * mat.base_color * reliability;
-        else if (fp.output_channel == 2) ps.illum = ps.illum + in_ * reliability;
-        else if (fp.output_channel == 3) ps.illum = ps.illum + ip * reliability;
+        if (output_channel == 1) ps.illum = ps.illum + ps.thr * mat.base_color * reliability;
+        else if (output_channel == 2) ps.illum = ps.illum + in_ * reliability;
+        else if (output_channel == 3) ps.illum = ps.illum + ip * reliability;
     }
     if (ps.bounce + 1 >= fp.max_path_depth) return SHADE_TERMINATE;
-    if (fp.output_channel == 0) {
+    if (output_channel == 0) {
         float2 dir_sample, sel_sample;
         dir_sample.x = lcg_randomf(ps.rng);
         dir_sample.y = lcg_randomf(ps.rng);
@@ -773,7 +781,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
         sel_sample.y = lcg_randomf(ps.rng);
         float3 li = f3(0.0f), light_dir = f3(0.0f);
         float light_dist = 2.e16f, light_pdf = 0.0f, mis_pdf = 0.0f;
-        if (sel_sample.x <= p_sun) {
+        if (!(FEAT & RPTR_FEAT_TRI_LIGHTS) || sel_sample.x <= p_sun) {
             sel_sample.x /= p_sun;
             float sn, cs;
             sincos_pos(RPTR_TWO_PI * dir_sample.x, sn, cs);

@@ -26,7 +26,7 @@ namespace rp {
 #define RPTR_REFILL_LANES 4
 #endif
 #ifndef RPTR_LEAF_LANES
-#define RPTR_LEAF_LANES 12
+#define RPTR_LEAF_LANES 8
 #endif
 
 struct TraceIO {
@@ -80,6 +80,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
+#ifndef RPTR_HC_PER_THREAD
+#define RPTR_HC_PER_THREAD 1
+#endif
+#ifndef RPTR_ANY_UNSORTED
+#define RPTR_ANY_UNSORTED 1 // shadow rays: skip the nearest-first sorting network (any hit terminates the ray)
+#endif
+#ifndef RPTR_LEAF_ONE_PER_TRIP
+#define RPTR_LEAF_ONE_PER_TRIP 1 // leaf step tests one triangle of the parked leaf per trip instead of looping over it
+#endif
 #ifndef RPTR_CHUNKS_PER_WARP
 #define RPTR_CHUNKS_PER_WARP 4 // target number of queue fetches per warp (tail balance) before the chunk is shortened
 #endif
@@ -143,12 +152,16 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                                                                             unsigned long long *c_nodes, unsigned long long *c_tris) {
     extern __shared__ __align__(128) unsigned char smem_top[]; // four word planes of the top_k first nodes, then the stacks
     __shared__ __align__(8) uint64_t top_bar;
+    __shared__ uint32_t hc_word;
     const uint32_t n = *io.count;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     // ---- stage the top of the tree: TMA bulk copies issued by one thread, completion through an mbarrier ----
     const uint32_t plane_bytes = (uint32_t)bvh.top_k * 16u; // one 16-byte word of each staged node
-    if (threadIdx.x == 0) mbar_init(&top_bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(&top_bar, 1);
+        hc_word = 0x3f000000u;
+    }
     __syncthreads();
     if (threadIdx.x == 0 && n > 0 && plane_bytes > 0) {
         mbar_expect_tx(&top_bar, 4u * plane_bytes);
@@ -180,7 +193,13 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     const uint32_t sst = smem_u32(smem_top + (size_t)RPTR_TOP_NODES_MAX * sizeof(BvhNode)) + threadIdx.x * (uint32_t)sizeof(int32_t);
     // high bytes of the decoded box coordinates, kept opaque to ptxas so that it stays in a register and the selectors
     // become immediates (n is never 2^32 - 1)
+#if RPTR_HC_PER_THREAD
+    // read back from shared memory on purpose: a value ptxas can prove constant or warp-uniform takes the immediate /
+    // uniform-register slot of PRMT, and all 24 selectors of a node step are then materialised in registers instead
+    const uint32_t hc = (uint32_t)lds32(smem_u32(&hc_word));
+#else
     const uint32_t hc = n == 0xffffffffu ? 0u : 0x3f000000u;
+#endif
     int sp = 0;
     uint32_t n_nodes = 0, n_tris = 0, n_rays = 0;
 
@@ -286,11 +305,13 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         const int32_t rl_ = sw_ ? rb : ra, rh_ = sw_ ? ra : rb;     \
         ta_ = tl_; tb_ = th_; ra = rl_; rb = rh_;                   \
     }
-            RPTR_CSWAP(t0, r0, t1, r1)
-            RPTR_CSWAP(t2, r2, t3, r3)
-            RPTR_CSWAP(t0, r0, t2, r2)
-            RPTR_CSWAP(t1, r1, t3, r3)
-            RPTR_CSWAP(t1, r1, t2, r2)
+            if (!(Any && RPTR_ANY_UNSORTED)) {
+                RPTR_CSWAP(t0, r0, t1, r1)
+                RPTR_CSWAP(t2, r2, t3, r3)
+                RPTR_CSWAP(t0, r0, t2, r2)
+                RPTR_CSWAP(t1, r1, t3, r3)
+                RPTR_CSWAP(t1, r1, t2, r2)
+            }
 #undef RPTR_CSWAP
             // continue with the nearest hit, push the others farthest first (a key of +inf marks a missed / unused child)
             if (sp + 3 <= RPTR_SMEM_STACK) { // common case, branch free: store unconditionally, advance when the entry is valid
@@ -310,7 +331,35 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 node = RPTR_POP();
             }
         }
-        // ---- leaf step: software-pipelined over the (<= 4, contiguous) triangles of the parked leaf ------------------------
+        // ---- leaf step ------------------------------------------------------------------------------------------------
+#if RPTR_LEAF_ONE_PER_TRIP
+        // one triangle of the parked leaf per trip (its words were requested at the top of the trip); the leaf reference
+        // is advanced in place: ~((first + 1) << 2 | (count - 2)) == leaf - 3
+        if (do_leaf) {
+            bool occluded = false;
+            n_tris++;
+            float t, u, v;
+            if (intersect_tri(f3(ta.x, ta.y, ta.z), f3(ta.w, tb.x, tb.y), f3(tb.z, tb.w, tc.x), o, d, t, u, v) && t > tmin && t < tmax) {
+                const int32_t id = f2i(tc.y);
+                if (Any) {
+                    best_tri = lf_first;
+                    occluded = true;
+                } else if (best_tri < 0 || t < best_t || (t == best_t && id < best_id)) {
+                    best_t = t; best_u = u; best_v = v; best_tri = lf_first; best_id = id;
+                }
+            }
+            leaf = lf_cnt > 1 ? leaf - 3 : 0;
+            if (Any && occluded) { // drop the rest of the traversal
+                sp = 0;
+                leaf = 0;
+                node = RPTR_EMPTY;
+            } else if (leaf == 0 && node < 0 && node != RPTR_EMPTY) { // the current item was a second leaf waiting for the slot
+                leaf = node;
+                node = RPTR_POP();
+            }
+        }
+#else
+        // software-pipelined over the (<= 4, contiguous) triangles of the parked leaf
         if (do_leaf) {
             bool occluded = false;
             for (int32_t i = 0; i < lf_cnt; ++i) {
@@ -342,6 +391,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 node = RPTR_POP();
             }
         }
+#endif
     }
     // ---- counters ----
     unsigned long long a = n_rays, b = n_nodes, c = n_tris;
