@@ -87,6 +87,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(args):
+    """DRAM bytes per closest-hit launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the launches of a
+    frame) from the committed ncu capture of this same command, or None when the workload is not the captured one."""
+    p = os.path.join(ROOT, "profiles", "r01_trace_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        t = json.load(f)
+    w = t["workload"]
+    same = (args.scene == w["scene"] and args.tris == w["tris"] and args.spp == w["spp"] and args.width == w["width"] and
+            args.height == w["height"] and not args.wave_paths and not args.option and args.gpus == 1)
+    return (t["closest"]["avg_dram_bytes_per_launch"], "profiles/r01_trace_traffic.json") if same else (None, None)
+
+
 def make_scene(args):
     from realtimepathtracingresearchframework_b200 import scenes
     if args.scene == "c4":  # BASELINE configs[3]: 100 k-triangle mesh x 100 instances, full BSDF set + area-light NEE
@@ -278,8 +292,9 @@ def run_b200(args):
     ach = trace_bytes / (cnt["ms_trace"] * 1e-3) / 1e9 if cnt["ms_trace"] > 0 else None
     stage_ms = {k: cnt[k] for k in ("ms_trace", "ms_shade", "ms_shadow", "ms_other")}
     spl = max(1, cnt["samples"])
+    traffic, traffic_src = measured_traffic(args)
     roofline = {"bound": "hbm", "kernel": "k_trace (closest hit)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "per_launch": {"launches": cnt["trace_launches"], "avg_ms": cnt["ms_trace"] / max(1, cnt["trace_launches"]),
                                "avg_algorithmic_bytes": trace_bytes / max(1, cnt["trace_launches"])},
                 "per_ray": {"nodes": cnt["closest_nodes"] / max(1, cnt["closest_rays"]), "tris": cnt["closest_tris"] / max(1, cnt["closest_rays"]),

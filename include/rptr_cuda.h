@@ -70,6 +70,8 @@ int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *params);
 
 /* Backend options that are compile-time switches or host options in the reference:
  *   "transmission"  0/1  GLTF_SUPPORT_TRANSMISSION[_ROUGHNESS] (off in the megakernel build, rendering/bsdfs/gltf_bsdf.glsl:10-13)
+ *   "rng_variant"   RenderBackendOptions::rng_variant (librender/render_params.glsl.h:34-37,76): 0 UNIFORM (LCG), 1 BN, 2 SOBOL,
+ *                   3 Z_SBL; 1-3 need their tables (rptr_cuda_set_pointset_table) before the next draw_frame
  *   "wave_paths"    max paths in flight per wavefront pass (memory/occupancy knob)
  *   "stage_timing"  0/1  time each stage with CUDA events into rptr_counters.ms_*
  *   "bvh_builder"   0 = binned-SAH build on the host inside set_scene, 1 = LBVH build on the device (both replace the
@@ -78,6 +80,11 @@ int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *params);
  *   "tile_rank", "tile_world", "tile_rows": screen-space sharding across GPUs (interleaved bands of tile_rows rows)
  */
 int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value);
+
+/* RenderSobolVulkan::update_random_buf / RenderBNPointsVulkan::update_random_buf (vulkan/pointsets/render_sobol.cpp:77-104,
+ * render_bn.cpp:77-126): hands the reference's sampler tables to the backend.  table = RPTR_POINTSET_*; count must be the
+ * table's element count; the data is copied to the device. */
+int rptr_cuda_set_pointset_table(rptr_ctx *ctx, int32_t table, const uint32_t *data, size_t count);
 
 /* RenderBackend::begin_frame / draw_frame / end_frame (librender/render_backend.h:97-99;
  * vulkan/render_vulkan.cpp:1919-2002, 2157-2178, 2017-2155).  begin_frame applies the counter protocol

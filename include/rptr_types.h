@@ -48,8 +48,18 @@ extern "C" {
 #define RPTR_LIGHT_SAMPLING_VARIANT_NONE 0
 #define RPTR_LIGHT_SAMPLING_VARIANT_RIS 1
 
-/* librender/render_params.glsl.h:34-37 (only UNIFORM is on the hot path this round) */
+/* librender/render_params.glsl.h:34-37 */
 #define RPTR_RNG_VARIANT_UNIFORM 0
+#define RPTR_RNG_VARIANT_BN 1
+#define RPTR_RNG_VARIANT_SOBOL 2
+#define RPTR_RNG_VARIANT_Z_SBL 3
+
+/* tables of the low-discrepancy samplers, as the reference holds them (rendering/pointsets/sobol_data.h:13-17,
+ * bn_data.h:12-27; sources rendering/pointsets/sobol_tables.h, bn_tables.h) */
+#define RPTR_POINTSET_SOBOL_MATRIX 0       /* SobolMatrix            uint32[1024 * 32] */
+#define RPTR_POINTSET_SOBOL_TILE_INVERT 1  /* SobolInversion_1_0     uint32[256 * 256] */
+#define RPTR_POINTSET_BN_SOBOL 2           /* sobol_256spp_256d      uint32[256 * 256] */
+#define RPTR_POINTSET_BN_SCRAMBLING_1SPP 3 /* scramblingTile_yx_d_1spp uint32[128 * 128 * 8] */
 
 typedef struct rptr_base_material {
     float base_color[3];

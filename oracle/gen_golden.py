@@ -3,6 +3,8 @@
 
   realtimepathtracingresearchframework_b200/data/sky_fits.json   update_sky_light fits for the SceneConfigs used by tests/bench
   tests/golden/ref_vectors.npz                                   input/output vectors of the reference's shading functions
+  realtimepathtracingresearchframework_b200/data/pointset_tables.npz  the reference's Sobol / blue-noise sampler tables (data)
+  tests/golden/ref_pointsets.npz                                 sampler streams of rendering/pointsets/{sobol,bn_rng,sample_order}.glsl
 """
 import ctypes as C
 import json
@@ -159,8 +161,77 @@ def gen_vectors(n=512, seed=1234):
     print("wrote", path, {k: v.shape for k, v in out.items()})
 
 
+# The sampler calls one path makes (vulkan/pt_megakernel.glsl:314-317,423,719; rendering/mc/shade_base_material.glsl:59-82):
+# op 0 = RANDOM_FLOAT1(rng, arg), 1 = RANDOM_SET_DIM, 2 = RANDOM_SHIFT_DIM
+def path_ops(n_vertices):
+    ops = [(0, 0), (0, 1)]
+    for v in range(n_vertices):
+        ops += [(1, 6 + 8 * v), (0, 2), (0, 3), (0, 0), (0, 1), (2, 4), (0, 2), (0, 3), (0, 0), (0, 1), (2, 4), (0, -1)]
+    return ops
+
+
+def gen_pointsets(n=384, seed=4321):
+    R = po.ref()
+    rng = np.random.default_rng(seed)
+    # --- tables: the reference's data, stored in the smallest exact integer type ---
+    tabs = []
+    for which in range(4):
+        cnt = R.ref_pointset_table(which, None)
+        buf = np.zeros(cnt, np.uint32)
+        R.ref_pointset_table(which, buf.ctypes.data_as(C.POINTER(C.c_uint32)))
+        tabs.append(buf)
+    assert tabs[1].max() < 65536 and tabs[2].max() < 256 and tabs[3].max() < 256
+    path = os.path.join(ROOT, "realtimepathtracingresearchframework_b200", "data", "pointset_tables.npz")
+    np.savez_compressed(path, sobol_matrix=tabs[0], sobol_tile_invert=tabs[1].astype(np.uint16), bn_sobol=tabs[2].astype(np.uint8),
+                        bn_scrambling_1spp=tabs[3].astype(np.uint8))
+    print("wrote", path, os.path.getsize(path), "bytes")
+    # --- sampler streams ---
+    ops = path_ops(4) + [(1, 1019), (0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6), (1, 2047), (0, 1), (0, 2)]
+    op_a = np.array([o for o, _ in ops], np.int32)
+    arg_a = np.array([a for _, a in ops], np.int32)
+    n_draws = int((op_a == 0).sum())
+    out = dict(ops=op_a, args=arg_a)
+    for variant in (1, 2, 3):
+        q = np.zeros((n, 6), np.uint32)  # sample_index, frame_id, frame_offset, px, py, width
+        q[:, 0] = rng.integers(0, 5000, n)
+        q[: n // 8, 0] = rng.integers(0, 65536, n // 8)      # large sample indices (index bits up to 2^32 for Z_SBL)
+        q[:, 1] = rng.integers(0, 5000, n)
+        q[:, 2] = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+        q[: n // 4, 2] = rng.integers(0, 4, n // 4)
+        q[:, 5] = rng.choice([1920, 1280, 256, 3840, 333], n)
+        q[:, 3] = rng.integers(0, 4096, n) % q[:, 5]
+        q[:, 4] = rng.integers(0, 2160, n)
+        draws = np.zeros((n, n_draws), np.float32)
+        state = np.zeros((n, 2), np.uint32)
+        for i in range(n):
+            m = R.ref_pointset_replay(variant, int(q[i, 0]), int(q[i, 1]), int(q[i, 2]), int(q[i, 3]), int(q[i, 4]), int(q[i, 5]), 1080,
+                                      op_a.ctypes.data_as(C.POINTER(C.c_int32)), arg_a.ctypes.data_as(C.POINTER(C.c_int32)), len(ops),
+                                      draws[i].ctypes.data_as(po.f32p), state[i].ctypes.data_as(C.POINTER(C.c_uint32)))
+            assert m == n_draws
+        out["v%d_in" % variant] = q
+        out["v%d_draws" % variant] = draws
+        out["v%d_state" % variant] = state
+    # --- morton_sample_id (sample_order.glsl:21-73) with every flag combination and non-square / non-power-of-two tiles ---
+    mq = np.zeros((n, 7), np.uint32)
+    mq[:, 0] = rng.integers(0, 1000, n)
+    mq[:, 1] = rng.integers(0, 4096, n)
+    mq[:, 2] = rng.integers(0, 4096, n)
+    tiles = np.array([(256, 256), (8, 8), (16, 64), (128, 32), (100, 60), (1920, 1080), (2, 2)], np.uint32)
+    mq[:, 3:5] = tiles[rng.integers(0, len(tiles), n)]
+    mq[:, 5] = rng.integers(0, 2, n)
+    mq[:, 6] = rng.integers(0, 2, n)
+    R.ref_morton_sample_id.restype = C.c_uint32
+    out["morton_in"] = mq
+    out["morton_out"] = np.array([R.ref_morton_sample_id(*[int(x) for x in row]) for row in mq], np.uint32)
+    path = os.path.join(ROOT, "tests", "golden", "ref_pointsets.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if po.ref() is None:
         sys.exit("oracle/_ref/libref.so missing: run `make -C oracle` in a container that has /root/reference")
-    gen_sky()
-    gen_vectors()
+    if "--pointsets-only" not in sys.argv:
+        gen_sky()
+        gen_vectors()
+    gen_pointsets()

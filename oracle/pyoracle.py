@@ -18,7 +18,8 @@ class OracleRenderArgs(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("camera", T.RenderCameraParams), ("params", T.RenderParams),
                 ("lighting", T.LightSamplingConfig), ("scene_params", T.SceneParams), ("frame_offset", C.c_uint32),
                 ("first_sample", C.c_uint32), ("n_samples", C.c_int32), ("x0", C.c_int32), ("y0", C.c_int32),
-                ("x1", C.c_int32), ("y1", C.c_int32), ("transmission", C.c_int32), ("n_threads", C.c_int32)]
+                ("x1", C.c_int32), ("y1", C.c_int32), ("transmission", C.c_int32), ("n_threads", C.c_int32),
+                ("rng_variant", C.c_int32), ("batch_spp", C.c_int32), ("pointset_tables", C.c_void_p * 4)]
 
 
 def build(force=False):
@@ -56,6 +57,10 @@ def lib():
         L.oracle_render_sample.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_uint32, f32p]
         for n in ("oracle_trace_closest", "oracle_trace_closest_bruteforce"):
             getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_int32, f32p, f32p]
+        L.oracle_pointset_replay.argtypes = [C.c_int, C.POINTER(C.c_void_p)] + [C.c_uint32] * 6 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                                                                       C.c_int, f32p, C.POINTER(C.c_uint32)]
+        L.oracle_morton_sample_id.restype = C.c_uint32
+        L.oracle_morton_sample_id.argtypes = [C.c_uint32] * 5 + [C.c_int, C.c_int]
         L.oracle_lcg_seed.restype = C.c_uint32
         L.oracle_lcg_seed.argtypes = [C.c_uint32] * 3
         L.oracle_lcg_randomf.restype = C.c_float
@@ -96,6 +101,11 @@ def ref():
         R.ref_dequantize_normal.argtypes = [C.c_uint32, f32p]
         R.ref_dequantize_uv.argtypes = [C.c_uint32, f32p]
         R.ref_sky_fit.argtypes = [C.POINTER(T.SceneConfig), C.POINTER(T.SceneParams)]
+        R.ref_pointset_table.argtypes = [C.c_int, C.POINTER(C.c_uint32)]
+        R.ref_pointset_replay.argtypes = [C.c_int] + [C.c_uint32] * 7 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, f32p,
+                                                                        C.POINTER(C.c_uint32)]
+        R.ref_morton_sample_id.restype = C.c_uint32
+        R.ref_morton_sample_id.argtypes = [C.c_uint32] * 5 + [C.c_int, C.c_int]
         _ref = R
     return _ref
 
@@ -123,7 +133,7 @@ class OracleScene:
         return np.frombuffer(arr, dtype=np.float32).reshape(-1, 12)[:n].copy()
 
     def _args(self, width, height, camera, scene_params, params=None, frame_offset=0, first_sample=0, n_samples=1,
-              region=None, transmission=0, n_threads=0):
+              region=None, transmission=0, n_threads=0, rng_variant=0, batch_spp=1, pointset_tables=None):
         a = OracleRenderArgs()
         a.width, a.height = width, height
         a.camera = camera
@@ -134,6 +144,13 @@ class OracleScene:
         x0, y0, x1, y1 = region or (0, 0, width, height)
         a.x0, a.y0, a.x1, a.y1 = x0, y0, x1, y1
         a.transmission, a.n_threads = transmission, n_threads
+        a.rng_variant, a.batch_spp = rng_variant, batch_spp
+        if rng_variant != 0:
+            if pointset_tables is None:
+                raise ValueError("rng_variant != 0 needs pointset_tables (four uint32 arrays)")
+            self._tables = [np.ascontiguousarray(t, np.uint32) for t in pointset_tables]  # keep alive during the call
+            for i, t in enumerate(self._tables):
+                a.pointset_tables[i] = t.ctypes.data
         return a
 
     def render(self, width, height, camera, scene_params, spp, out=None, **kw):
@@ -159,6 +176,13 @@ class OracleScene:
         fn = lib().oracle_trace_closest_bruteforce if bruteforce else lib().oracle_trace_closest
         fn(self.h, q.ctypes.data, n, _fp(res), _fp(t))
         return res, t
+
+
+def table_ptrs(tables):
+    """(C array of 4 pointers, keep-alive list) for oracle_pointset_replay."""
+    keep = [np.ascontiguousarray(t, np.uint32) for t in tables]
+    arr = (C.c_void_p * 4)(*[t.ctypes.data for t in keep])
+    return arr, keep
 
 
 def view_params(camera, w, h):

@@ -11,6 +11,7 @@
 //
 // Structure follows the reference megakernel (one sequential loop per pixel sample), NOT the CUDA wavefront.
 #include "shading_oracle.h"
+#include "pointsets_oracle.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -508,6 +509,10 @@ typedef struct oracle_render_args {
     int32_t x0, y0, x1, y1; // pixel region to render (x1/y1 exclusive)
     int32_t transmission;   // 0 = megakernel build (no GLTF_SUPPORT_TRANSMISSION)
     int32_t n_threads;      // 0 = all
+    int32_t rng_variant;    // RenderBackendOptions::rng_variant: 0 UNIFORM, 1 BN, 2 SOBOL, 3 Z_SBL
+    int32_t batch_spp;      // >= 1: view_params.frame_id of sample k is first_sample + (k / batch_spp) * batch_spp (the BN
+                            // sampler seeds from frame_id, not from the sample index: bn_rng.glsl:112)
+    const uint32_t *pointset_tables[4]; // SobolMatrix, SobolInversion_1_0, sobol_256spp_256d, scramblingTile_yx_d_1spp
 } oracle_render_args;
 
 struct oracle_scene { Scene s; };
@@ -758,16 +763,32 @@ static bool test_visibility(const Frame &f, V3 from, V3 dir, float dist, float g
 
 // main_spp: vulkan/pt_megakernel.glsl:310-737, shade_base_material (rendering/mc/shade_base_material.glsl:14-96),
 // sample_direct_light (rendering/mc/nee.glsl:32-90).  Returns vec4(illum, bounce == 0 ? 0 : 1).
-static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, Counters &cnt) {
+// RANDOM_STATE of the selected pointset (rendering/pointsets/selected_rng.glsl) + the separate LCG the megakernel keeps
+// for stochastic alpha when the pointset is not the LCG (pt_megakernel.glsl:354-358)
+struct PathRng {
+    oracle_ps::QmcRng q;
+    Lcg lcg, alpha;
+    bool qmc = false;
+    float draw(int d) { return qmc ? q.draw(d) : lcg_randomf(lcg); }
+    float draw_alpha() { return qmc ? lcg_randomf(alpha) : lcg_randomf(lcg); }
+    void set_dim(int d) { q.set_dim(d); }
+    void shift_dim(int d) { q.shift_dim(d); }
+};
+
+static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32_t view_frame_id, Counters &cnt) {
     const oracle_render_args &a = *f.a;
     const Scene &s = *f.s;
     const rptr_scene_params &sp = f.sp;
     uint32_t linear = (uint32_t)px + (uint32_t)py * (uint32_t)a.width;
-    Lcg rng = lcg_seed(sample_index, a.frame_offset, linear);
+    PathRng rng;
+    rng.lcg = lcg_seed(sample_index, a.frame_offset, linear);
+    rng.alpha = rng.lcg;
+    rng.qmc = a.rng_variant != 0;
+    if (rng.qmc) rng.q.seed(a.rng_variant, a.pointset_tables, sample_index, view_frame_id, a.frame_offset, (uint32_t)px, (uint32_t)py, (uint32_t)a.width);
     float ptx = (float)px + 0.5f, pty = (float)py + 0.5f;
     if (a.params.enable_raster_taa == 0) {
-        float ux = lcg_randomf(rng);
-        float uy = lcg_randomf(rng);
+        float ux = rng.draw(0); // DIM_PIXEL_X, pathspace.h:13-14
+        float uy = rng.draw(1);
         ptx += ux - 0.5f;
         pty += uy - 0.5f;
     }
@@ -785,6 +806,7 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, Counte
     V3 sun_rgb = v3(sp.sun_radiance[0], sp.sun_radiance[1], sp.sun_radiance[2]);
 
     for (int v = 0; v < a.params.max_path_depth; ++v) {
+        rng.set_dim(6 + v * (4 + 4)); // RANDOM_SET_DIM(rng, DIM_CAMERA_END + unrollBounceIdx * (DIM_VERTEX_END + DIM_LIGHT_END)), :423
         // closest hit with front-to-back stochastic alpha (pt_megakernel.glsl:440-478,153-211)
         Hit hit;
         cnt.closest_rays++;
@@ -800,7 +822,7 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, Counte
             const rptr_base_material &m = s.materials[calc_hit_material_id(g, (uint32_t)tr.prim)];
             if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) break;
             float alpha = material_alpha(m);
-            if (!(alpha > 0.0f) || (alpha < 1.0f && lcg_randomf(rng) > alpha)) {
+            if (!(alpha > 0.0f) || (alpha < 1.0f && rng.draw_alpha() > alpha)) {
                 after_t = hit.t;
                 after_id = hit.tri;
                 continue;
@@ -864,10 +886,10 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, Counte
         if (bounce + 1 >= a.params.max_path_depth) break; // :56-57
         if (a.params.output_channel == 0) { // :59-65, nee.glsl:32-90
             V2 dir_sample, sel_sample;
-            dir_sample.x = lcg_randomf(rng);
-            dir_sample.y = lcg_randomf(rng);
-            sel_sample.x = lcg_randomf(rng);
-            sel_sample.y = lcg_randomf(rng);
+            dir_sample.x = rng.draw(2); // DIM_POSITION_X
+            dir_sample.y = rng.draw(3);
+            sel_sample.x = rng.draw(0); // DIM_LIGHT_SEL_1
+            sel_sample.y = rng.draw(1);
             V3 li = v3(0.0f), light_dir = v3(0.0f);
             float light_dist = 2.e16f, light_pdf = 0.0f, mis_pdf = 0.0f;
             if (sel_sample.x <= p_sun) {
@@ -903,15 +925,17 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, Counte
             }
             illum = illum + throughput * contrib;
         }
+        rng.shift_dim(4); // RANDOM_SHIFT_DIM(rng, DIM_LIGHT_END), shade_base_material.glsl:66
         if (a.params.glossy_only_mode != 0 && !(mat.roughness < RPTR_GLOSSY_MODE_ROUGHNESS_THRESHOLD && mat.ior != 1.0f)) break;
         V2 lobe, dirs;
-        lobe.x = lcg_randomf(rng);
-        lobe.y = lcg_randomf(rng);
-        dirs.x = lcg_randomf(rng);
-        dirs.y = lcg_randomf(rng);
+        lobe.x = rng.draw(2); // DIM_LOBE
+        lobe.y = rng.draw(3);
+        dirs.x = rng.draw(0); // DIM_DIRECTION_X
+        dirs.y = rng.draw(1);
         V3 w_i;
         float sampling_pdf = 0.0f, mis_wpdf = 0.0f;
         V3 bsdf = sample_gltf_brdf(mat, in_, w_o, w_i, sampling_pdf, mis_wpdf, dirs, lobe, v_x, v_y, f.tr);
+        rng.shift_dim(4); // DIM_VERTEX_END, :82
         ++bounce;
         if (mis_wpdf == 0.0f || is_zero(bsdf) || !(dot(w_i, in_) * dot(w_i, ign) > 0.0f)) break;
         throughput = throughput * bsdf;
@@ -925,7 +949,7 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, Counte
         if (bounce >= a.params.rr_path_depth) {
             float prefix = fmaxf(throughput.x, fmaxf(throughput.y, throughput.z));
             float rr_prob = prefix;
-            float rr_sample = lcg_randomf(rng);
+            float rr_sample = rng.draw(-1); // DIM_RR = DIM_FREE_PATH - DIM_VERTEX_END
             if (bounce > 6) rr_prob = fminf(0.95f, rr_prob);
             else rr_prob = fminf(1.0f, rr_prob);
             if (rr_sample < rr_prob) throughput = throughput / rr_prob;
@@ -980,7 +1004,8 @@ int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rg
             float *px = rgba + 4 * ((size_t)y * a->width + x);
             for (int k = 0; k < a->n_samples; ++k) {
                 uint32_t frame_id = a->first_sample + (uint32_t)k;
-                V4 c = main_spp(f, x, y, frame_id, cnt);
+                const uint32_t batch = a->batch_spp > 1 ? (uint32_t)a->batch_spp : 1u;
+                V4 c = main_spp(f, x, y, frame_id, a->first_sample + ((uint32_t)k / batch) * batch, cnt);
                 float xs[4] = {c.x, c.y, c.z, c.w};
                 if (frame_id > 0) {
                     float denom = (float)(frame_id + 1u);
@@ -1006,7 +1031,7 @@ int oracle_render_sample(const oracle_scene *os, const oracle_render_args *a, ui
     for (int y = a->y0; y < a->y1; ++y) {
         Counters cnt;
         for (int x = a->x0; x < a->x1; ++x) {
-            V4 c = main_spp(f, x, y, sample_index, cnt);
+            V4 c = main_spp(f, x, y, sample_index, sample_index, cnt);
             float *px = sample_rgba + 4 * ((size_t)y * a->width + x);
             px[0] = c.x; px[1] = c.y; px[2] = c.z; px[3] = c.w;
         }
@@ -1061,6 +1086,26 @@ int oracle_trace_closest_bruteforce(const oracle_scene *os, const rptr_render_ra
 }
 
 // ---- unit entry points used to pin the restatement against oracle/_ref and tests/golden -------------------------
+// replay of sampler calls, same protocol as ref_pointset_replay (oracle/ref_shim/ref_pointsets.cpp)
+int oracle_pointset_replay(int variant, const uint32_t *const *tables, uint32_t sample_index, uint32_t frame_id, uint32_t frame_offset, uint32_t px,
+                           uint32_t py, uint32_t w, const int32_t *ops, const int32_t *args, int n_ops, float *out, uint32_t *state_out) {
+    oracle_ps::QmcRng q;
+    q.seed(variant, tables, sample_index, frame_id, frame_offset, px, py, w);
+    if (state_out) {
+        state_out[0] = variant == oracle_ps::BN ? q.pixel : q.index;
+        state_out[1] = variant == oracle_ps::BN ? q.sample : q.scramble;
+    }
+    int n = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        if (ops[i] == 0) out[n++] = q.draw(args[i]);
+        else if (ops[i] == 1) q.set_dim(args[i]);
+        else q.shift_dim(args[i]);
+    }
+    return n;
+}
+uint32_t oracle_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, uint32_t tw, uint32_t th, int hash_tile, int hash_sample) {
+    return oracle_ps::morton_sample_id(sample_id, px, py, tw, th, hash_tile != 0, hash_sample != 0);
+}
 uint32_t oracle_lcg_seed(uint32_t index, uint32_t frame, uint32_t linear) { return lcg_seed(index, frame, linear).state; }
 float oracle_lcg_randomf(uint32_t *state) {
     Lcg r{*state};

@@ -7,5 +7,5 @@ intel/RealTimePathTracingResearchFramework (`rptr --backend cuda`).
   types.py     ctypes mirrors of the boundary PODs (include/rptr_types.h)
 """
 from . import types  # noqa: F401
-from .backend import (RenderConfiguration, RenderCuda, RptrError, create_cuda_backend, load_library, load_sky_fit,  # noqa: F401
+from .backend import (RenderConfiguration, RenderCuda, RptrError, create_cuda_backend, load_library, load_pointset_tables, load_sky_fit,  # noqa: F401
                       read_pfm, write_pfm)

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "rptr_cuda_begin_frame", "rptr_cuda_draw_frame", "rptr_cuda_end_frame", "rptr_cuda_stats", "rptr_cuda_flush",
     "rptr_cuda_get_counters", "rptr_cuda_reset_counters", "rptr_cuda_frame_state", "rptr_cuda_framebuffer_size",
     "rptr_cuda_readback_f32", "rptr_cuda_readback_u8", "rptr_cuda_framebuffer_device_ptr", "rptr_cuda_stream_handle",
-    "rptr_cuda_trace_rays",
+    "rptr_cuda_trace_rays", "rptr_cuda_set_pointset_table",
     "rptr_write_pfm",
 ]
 
@@ -70,6 +70,7 @@ def load_library(path=None):
     L.rptr_cuda_get_lights.restype = i32
     L.rptr_cuda_set_scene_params.argtypes = [vp, C.POINTER(T.SceneParams)]
     L.rptr_cuda_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.rptr_cuda_set_pointset_table.argtypes = [vp, i32, u32p, C.c_size_t]
     L.rptr_cuda_begin_frame.argtypes = [vp, C.POINTER(T.RenderCameraParams), C.POINTER(T.RenderParams),
                                         C.POINTER(T.LightSamplingConfig), i32, i32, C.c_double]
     L.rptr_cuda_draw_frame.argtypes = [vp, i32]
@@ -131,6 +132,22 @@ class RenderConfiguration:
         self.reset_accumulation, self.freeze_frame = reset_accumulation, freeze_frame
 
 
+POINTSET_TABLE_NAMES = ("sobol_matrix", "sobol_tile_invert", "bn_sobol", "bn_scrambling_1spp")  # RPTR_POINTSET_* order
+
+
+def load_pointset_tables():
+    """The reference's sampler tables (SobolMatrix, SobolInversion_1_0, sobol_256spp_256d, scramblingTile_yx_d_1spp) as four
+    uint32 arrays in RPTR_POINTSET_* order.
+
+    Like the sky fit, the tables stay on the reference's side of the boundary: in the rptr integration the adapter hands
+    rendering/pointsets/{sobol,bn}_tables.h to rptr_cuda_set_pointset_table the way render_sobol.cpp / render_bn.cpp
+    upload them.  Standalone callers get data/pointset_tables.npz, extracted from those headers by oracle/gen_golden.py.
+    """
+    import numpy as np
+    z = np.load(os.path.join(_HERE, "data", "pointset_tables.npz"))
+    return [np.ascontiguousarray(z[k], dtype=np.uint32) for k in POINTSET_TABLE_NAMES]
+
+
 class RenderCuda:
     """`RenderBackend` for `--backend cuda` (one instance = one B200)."""
 
@@ -183,6 +200,22 @@ class RenderCuda:
 
     def set_option(self, name, value):
         self._check(self._L.rptr_cuda_set_option(self._h, name.encode(), int(value)))
+
+    def set_pointset_table(self, table, data):
+        """RenderSobolVulkan / RenderBNPointsVulkan::update_random_buf: table = RPTR_POINTSET_* index, data = uint32 array."""
+        import numpy as np
+        a = np.ascontiguousarray(data, dtype=np.uint32)
+        self._check(self._L.rptr_cuda_set_pointset_table(self._h, int(table), a.ctypes.data_as(C.POINTER(C.c_uint32)), a.size))
+
+    def set_rng_variant(self, variant, tables=None):
+        """options.rng_variant (librender/render_params.glsl.h:34-37,76) + the tables that variant reads."""
+        variant = int(variant)
+        if variant != 0:
+            tabs = tables if tables is not None else load_pointset_tables()
+            for i in {1: (2, 3), 2: (0,), 3: (0, 1)}[variant]:
+                self.set_pointset_table(i, tabs[i])
+        self.set_option("rng_variant", variant)
+        self.options["rng_variant"] = variant
 
     def begin_frame(self, cmd_stream, config):
         self.camera = config.camera

@@ -33,7 +33,8 @@ struct Wave {
     float4 *hit;    // t, u, v, bits(leaf triangle index | -1)
     float4 *thr;    // throughput.rgb, prev_bounce_pdf
     float4 *illum;  // illum.rgb, total_t
-    uint2 *rngb;    // lcg state, bounce
+    uint2 *rngb;    // sampler word that advances with the draws (LCG state), bounce
+    uint32_t *rng2; // second sampler word (Sobol index / BN pixelID); allocated for rng_variant != UNIFORM only
     float4 *sh_o;   // shadow queue: origin.xyz, tmin
     float4 *sh_d;   //               dir.xyz, tmax
     float4 *sh_c;   //               contribution.rgb, bits(path slot)
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave
         w.thr[slot] = f4(1.0f, 1.0f, 1.0f, ps.prev_pdf);
         w.illum[slot] = f4(0.0f, 0.0f, 0.0f, 0.0f);
         w.rngb[slot] = make_uint2(ps.rng, 0u);
+        if (fp.rng_variant != 0) w.rng2[slot] = ps.rng_b;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[0] = n;
 }
@@ -194,6 +196,8 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                     ps.thr = f3(thr.x, thr.y, thr.z); ps.prev_pdf = thr.w;
                     ps.illum = f3(il.x, il.y, il.z); ps.total_t = il.w;
                     ps.rng = rb.x; ps.bounce = (int)rb.y;
+                    ps.rng_b = ((FEAT & RPTR_FEAT_QMC) && fp.rng_variant != 0) ? w.rng2[slot] : 0u;
+                    ps.rng_dim = 0;
                     verts++;
                     ShadeResult r = shade_hit<FEAT>(fp, sc, ps, hit.x, hit.y, hit.z, &bvh.tris[tri], sh);
                     cont = r == SHADE_CONTINUE;
@@ -343,6 +347,8 @@ struct rptr_ctx {
     bool in_frame = false;
     // options
     int transmission = 0;
+    int rng_variant = 0; // RenderBackendOptions::rng_variant
+    uint32_t *pointset_tables[4] = {nullptr, nullptr, nullptr, nullptr}; // device copies, rptr_cuda_set_pointset_table
     // paths per wave: 64 spp of 1920x1080 in one wave (144 B of path state each, 19 GB); every launch of the bounce loop
     // pays a fixed tail (the longest ray of the queue), so few large waves beat many small ones (profiles/r01_wave_sweep.md)
     int64_t wave_paths = 128ll << 20;
@@ -419,7 +425,10 @@ static TileMap make_tilemap(const rptr_ctx *ctx) {
 static int grid_for(const rptr_ctx *ctx, int blocks_per_sm) { return ctx->num_sms * blocks_per_sm; }
 
 static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
-    if (paths <= ctx->wave_capacity && depth <= ctx->wave_depth) return 0;
+    const bool need_rng2 = ctx->rng_variant != 0;
+    if (paths <= ctx->wave_capacity && depth <= ctx->wave_depth && (!need_rng2 || ctx->wave.rng2)) return 0;
+    if (paths < ctx->wave_capacity) paths = ctx->wave_capacity;
+    if (depth < ctx->wave_depth) depth = ctx->wave_depth;
     CU(cudaStreamSynchronize(ctx->stream));
     for (void *p : ctx->wave_allocs) cudaFree(p);
     ctx->wave_allocs.clear();
@@ -431,6 +440,8 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     CU(dev_alloc(ctx, &w.thr, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.illum, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.rngb, n, ctx->wave_allocs));
+    w.rng2 = nullptr;
+    if (need_rng2) CU(dev_alloc(ctx, &w.rng2, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.sh_o, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.sh_d, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.sh_c, n, ctx->wave_allocs));
@@ -534,6 +545,7 @@ void rptr_cuda_destroy(rptr_ctx *ctx) {
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     free_all(ctx, ctx->scene_allocs);
     free_all(ctx, ctx->wave_allocs);
+    for (uint32_t *t : ctx->pointset_tables) cudaFree(t);
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
     cudaFree(ctx->dcounters);
@@ -686,7 +698,10 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
     if (ctx->in_frame) return fail(ctx, "set_option(%s) inside begin_frame/end_frame", name);
     const std::string n(name);
     if (n == "transmission") ctx->transmission = value != 0;
-    else if (n == "wave_paths") {
+    else if (n == "rng_variant") {
+        if (value < 0 || value > 3) return fail(ctx, "rng_variant must be 0 (UNIFORM), 1 (BN), 2 (SOBOL) or 3 (Z_SBL)");
+        ctx->rng_variant = (int)value;
+    } else if (n == "wave_paths") {
         if (value < 1024) return fail(ctx, "wave_paths must be >= 1024");
         ctx->wave_paths = value;
     } else if (n == "stage_timing") ctx->stage_timing = value != 0;
@@ -700,6 +715,22 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
     else if (n == "tile_rows") ctx->tile_rows = (int)value;
     else return fail(ctx, "unknown option '%s'", name);
     if (ctx->tile_world < 1 || ctx->tile_rows < 1) return fail(ctx, "tile_world and tile_rows must be >= 1");
+    return 0;
+}
+
+static const size_t k_pointset_table_size[4] = {(size_t)RPTR_SOBOL_DIMS * RPTR_SOBOL_MATRIX_SIZE, (size_t)RPTR_SOBOL_TILE * RPTR_SOBOL_TILE,
+                                                (size_t)RPTR_BN_SAMPLES * RPTR_BN_DIMS, (size_t)RPTR_BN_TILE * RPTR_BN_TILE * RPTR_BN_SCRAMBLING_DIMS};
+
+int rptr_cuda_set_pointset_table(rptr_ctx *ctx, int32_t table, const uint32_t *data, size_t count) {
+    if (!ctx) return 1;
+    if (table < 0 || table > 3) return fail(ctx, "set_pointset_table: unknown table %d", table);
+    if (!data) return fail(ctx, "set_pointset_table: data is NULL");
+    if (count != k_pointset_table_size[table]) return fail(ctx, "set_pointset_table(%d): expected %zu elements, got %zu", table, k_pointset_table_size[table], count);
+    if (ctx->in_frame) return fail(ctx, "set_pointset_table inside begin_frame/end_frame");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->pointset_tables[table]) CU(cudaMalloc(&ctx->pointset_tables[table], count * sizeof(uint32_t)));
+    CU(cudaMemcpy(ctx->pointset_tables[table], data, count * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -747,6 +778,11 @@ static FrameParams make_frame_params(const rptr_ctx *ctx) {
     fp.bin_size = ctx->lighting.bin_size;
     fp.n_bins = (ctx->n_lights + fp.bin_size - 1) / fp.bin_size; // vulkan/pt_megakernel.glsl:102-103
     fp.transmission = ctx->transmission;
+    fp.rng_variant = ctx->rng_variant;
+    fp.pts.sobol_matrix = ctx->pointset_tables[RPTR_POINTSET_SOBOL_MATRIX];
+    fp.pts.sobol_tile_invert = ctx->pointset_tables[RPTR_POINTSET_SOBOL_TILE_INVERT];
+    fp.pts.bn_sobol = ctx->pointset_tables[RPTR_POINTSET_BN_SOBOL];
+    fp.pts.bn_scrambling = ctx->pointset_tables[RPTR_POINTSET_BN_SCRAMBLING_1SPP];
     fp.sp = ctx->scene_params;
     if (ctx->n_lights > 0) fp.sp.sun_radiance[3] *= 0.5f; // vulkan/render_sky.cpp:67-70
     else fp.sp.sun_radiance[3] = 1.0f;
@@ -757,6 +793,12 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
     (void)variant;
     if (!ctx) return 1;
     if (!ctx->in_frame) return fail(ctx, "draw_frame outside begin_frame/end_frame");
+    {   // the Sobol / blue-noise samplers read the reference's tables (vulkan/pointsets/render_{sobol,bn}.cpp upload them)
+        const int v = ctx->rng_variant;
+        const bool ok = v == 0 || (v == 1 && ctx->pointset_tables[2] && ctx->pointset_tables[3]) || (v == 2 && ctx->pointset_tables[0]) ||
+                        (v == 3 && ctx->pointset_tables[0] && ctx->pointset_tables[1]);
+        if (!ok) return fail(ctx, "rng_variant %d needs its tables: call rptr_cuda_set_pointset_table first", v);
+    }
     CU(cudaSetDevice(ctx->device));
     const TileMap tm = make_tilemap(ctx);
     FrameParams fp = make_frame_params(ctx);
@@ -798,7 +840,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     StageTimer t(ctx, 1);
                     // smallest compiled variant that covers the features this frame uses (rptr_shading.cuh, RPTR_FEAT_*)
                     const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
-                                     (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0);
+                                     (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0);
 #define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, q, cn, nq, cn + 4, cn + 1, ctx->dcounters
                     if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);

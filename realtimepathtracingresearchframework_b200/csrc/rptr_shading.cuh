@@ -5,6 +5,7 @@
 //   rendering/bsdfs/gltf_bsdf.glsl + rendering/lights/{tri,sun}.glsl + rendering/rt/hit.glsl.
 #pragma once
 #include "rptr_math.cuh"
+#include "rptr_pointsets.cuh"
 #include "../../include/rptr_types.h"
 
 namespace rp {
@@ -52,6 +53,8 @@ struct FrameParams {
     int32_t max_path_depth, rr_path_depth, output_channel, glossy_only_mode, enable_raster_taa;
     int32_t n_lights, n_bins, bin_size;
     int32_t transmission;
+    int32_t rng_variant;  // RenderBackendOptions::rng_variant (librender/render_params.glsl.h:34-37)
+    PointsetTables pts;   // tables of the Sobol / blue-noise samplers (null unless rng_variant needs them)
     rptr_scene_params sp; // sun_radiance[3] already carries the light-count rule (vulkan/render_sky.cpp:67-70)
 };
 
@@ -671,8 +674,10 @@ struct PathState {
     float prev_pdf;
     float3 illum;
     float total_t;
-    uint32_t rng;
+    uint32_t rng;     // RANDOM_STATE word that advances with every draw (LCG state; Sobol scramble LCG; BN sampleID)
     int bounce;
+    uint32_t rng_b;   // second word, constant along the path (Sobol index / BN pixelID; unused by the LCG)
+    int32_t rng_dim;  // RANDOM_SET_DIM / RANDOM_SHIFT_DIM cursor
 };
 struct ShadowRay {
     float3 o, d;
@@ -681,14 +686,34 @@ struct ShadowRay {
 };
 enum ShadeResult { SHADE_TERMINATE = 0, SHADE_CONTINUE = 1 };
 
+// FEAT: code paths compiled in (the reference compiles its shader variants from #defines the same way, e.g.
+// GLTF_SUPPORT_TRANSMISSION, RBO_rng_variant); a kernel built without a feature must only be launched when the frame
+// does not use it.
+#define RPTR_FEAT_TRANSMISSION 1 // fp.transmission may be set
+#define RPTR_FEAT_TRI_LIGHTS 2   // the scene has binned triangle lights (p_sun < 1)
+#define RPTR_FEAT_AOV 4          // fp.output_channel may be non-zero
+#define RPTR_FEAT_QMC 8          // fp.rng_variant may select a Sobol / blue-noise sampler
+#define RPTR_FEAT_ALL 15
+// RANDOM_FLOAT1(rng, d) of the selected pointset (rendering/pointsets/selected_rng.glsl, rendering/defaults.glsl:23-28)
+template <int FEAT>
+RPTR_HD float path_rand(const FrameParams &fp, PathState &ps, int d) {
+    if (!(FEAT & RPTR_FEAT_QMC) || fp.rng_variant == 0) return lcg_randomf(ps.rng);
+    Sampler sm;
+    sm.a = ps.rng; sm.b = ps.rng_b; sm.dim = ps.rng_dim;
+    const float r = sampler_next(fp.rng_variant, fp.pts, sm, d);
+    ps.rng = sm.a;
+    return r;
+}
+
 // primary ray + path state (vulkan/pt_megakernel.glsl:310-365)
 RPTR_HD void generate_primary(const FrameParams &fp, int px, int py, uint32_t sample_index, PathState &ps) {
-    uint32_t linear = (uint32_t)px + (uint32_t)py * (uint32_t)fp.width;
-    ps.rng = lcg_seed(sample_index, fp.frame_offset, linear);
+    const Sampler sm = sampler_init(fp.rng_variant, fp.pts, sample_index, fp.first_sample, fp.frame_offset, (uint32_t)px, (uint32_t)py,
+                                    (uint32_t)fp.width);
+    ps.rng = sm.a; ps.rng_b = sm.b; ps.rng_dim = 0;
     float ptx = (float)px + 0.5f, pty = (float)py + 0.5f;
     if (fp.enable_raster_taa == 0) {
-        float ux = lcg_randomf(ps.rng);
-        float uy = lcg_randomf(ps.rng);
+        float ux = path_rand<RPTR_FEAT_ALL>(fp, ps, RPTR_DIM_PIXEL_X);
+        float uy = path_rand<RPTR_FEAT_ALL>(fp, ps, RPTR_DIM_PIXEL_X + 1);
         ptx += ux - 0.5f;
         pty += uy - 0.5f;
     }
@@ -714,12 +739,6 @@ RPTR_HD float3 shade_miss(const rptr_scene_params &sp, float3 illum, float3 thr,
     return illum + thr * compute_sky_illum(sp, dir, prev_pdf);
 }
 
-// FEAT: code paths compiled in (the reference compiles its shader variants from #defines the same way, e.g.
-// GLTF_SUPPORT_TRANSMISSION); a kernel built without a feature must only be launched when the frame does not use it.
-#define RPTR_FEAT_TRANSMISSION 1 // fp.transmission may be set
-#define RPTR_FEAT_TRI_LIGHTS 2   // the scene has binned triangle lights (p_sun < 1)
-#define RPTR_FEAT_AOV 4          // fp.output_channel may be non-zero
-#define RPTR_FEAT_ALL 7
 template <int FEAT = RPTR_FEAT_ALL>
 RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathState &ps, float hit_t, float hit_u, float hit_v, const Tri *tri,
                              ShadowRay &sh) {
@@ -727,6 +746,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
     const rptr_scene_params &sp = fp.sp;
     const bool tr = (FEAT & RPTR_FEAT_TRANSMISSION) && fp.transmission != 0;
     const int output_channel = (FEAT & RPTR_FEAT_AOV) ? fp.output_channel : 0;
+    ps.rng_dim = RPTR_DIM_CAMERA_END + ps.bounce * (RPTR_DIM_VERTEX_END + RPTR_DIM_LIGHT_END); // RANDOM_SET_DIM, pt_megakernel.glsl:423
     const GeomInst &g = sc.ginst[tri->geom_inst];
     RTHit h = calc_hit_attributes(g, hit_t, (uint32_t)tri->prim, hit_u, hit_v);
     float approx_sa = length(h.geo_normal);
@@ -775,10 +795,10 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
     if (ps.bounce + 1 >= fp.max_path_depth) return SHADE_TERMINATE;
     if (output_channel == 0) {
         float2 dir_sample, sel_sample;
-        dir_sample.x = lcg_randomf(ps.rng);
-        dir_sample.y = lcg_randomf(ps.rng);
-        sel_sample.x = lcg_randomf(ps.rng);
-        sel_sample.y = lcg_randomf(ps.rng);
+        dir_sample.x = path_rand<FEAT>(fp, ps, RPTR_DIM_POSITION_X);
+        dir_sample.y = path_rand<FEAT>(fp, ps, RPTR_DIM_POSITION_X + 1);
+        sel_sample.x = path_rand<FEAT>(fp, ps, RPTR_DIM_LIGHT_SEL_1);
+        sel_sample.y = path_rand<FEAT>(fp, ps, RPTR_DIM_LIGHT_SEL_1 + 1);
         float3 li = f3(0.0f), light_dir = f3(0.0f);
         float light_dist = 2.e16f, light_pdf = 0.0f, mis_pdf = 0.0f;
         if (!(FEAT & RPTR_FEAT_TRI_LIGHTS) || sel_sample.x <= p_sun) {
@@ -823,15 +843,17 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
             }
         }
     }
+    ps.rng_dim += RPTR_DIM_LIGHT_END; // RANDOM_SHIFT_DIM, shade_base_material.glsl:66
     if (fp.glossy_only_mode != 0 && !(mat.roughness < RPTR_GLOSSY_MODE_ROUGHNESS_THRESHOLD && mat.ior != 1.0f)) return SHADE_TERMINATE;
     float2 lobe, dirs;
-    lobe.x = lcg_randomf(ps.rng);
-    lobe.y = lcg_randomf(ps.rng);
-    dirs.x = lcg_randomf(ps.rng);
-    dirs.y = lcg_randomf(ps.rng);
+    lobe.x = path_rand<FEAT>(fp, ps, RPTR_DIM_LOBE);
+    lobe.y = path_rand<FEAT>(fp, ps, RPTR_DIM_LOBE + 1);
+    dirs.x = path_rand<FEAT>(fp, ps, RPTR_DIM_DIRECTION_X);
+    dirs.y = path_rand<FEAT>(fp, ps, RPTR_DIM_DIRECTION_X + 1);
     float3 w_i;
     float sampling_pdf = 0.0f, mis_wpdf = 0.0f;
     float3 bsdf = sample_gltf_brdf(mat, in_, w_o, w_i, sampling_pdf, mis_wpdf, dirs, lobe, v_x, v_y, tr);
+    ps.rng_dim += RPTR_DIM_VERTEX_END; // shade_base_material.glsl:82
     ++ps.bounce;
     if (mis_wpdf == 0.0f || is_zero(bsdf) || !(dot(w_i, in_) * dot(w_i, ign) > 0.0f)) return SHADE_TERMINATE;
     ps.thr = ps.thr * bsdf;
@@ -843,7 +865,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
     if (ps.bounce >= fp.rr_path_depth) {
         float prefix = fmaxf(ps.thr.x, fmaxf(ps.thr.y, ps.thr.z));
         float rr_prob = prefix;
-        float rr_sample = lcg_randomf(ps.rng);
+        float rr_sample = path_rand<FEAT>(fp, ps, RPTR_DIM_RR);
         if (ps.bounce > 6) rr_prob = fminf(0.95f, rr_prob);
         else rr_prob = fminf(1.0f, rr_prob);
         if (rr_sample < rr_prob) ps.thr = ps.thr / rr_prob;

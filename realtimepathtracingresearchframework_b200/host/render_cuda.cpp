@@ -7,6 +7,8 @@
 #include "scene.h"         // librender/scene.h
 #include "quantize.h"      // librender/quantize.h
 #include "../rendering/lights/sky_model_arhosek/sky_model.h"
+#include "../rendering/pointsets/sobol_tables.h" // SobolMatrix, SobolInversion_1_0 (vulkan/pointsets/render_sobol.cpp:14)
+#include "../rendering/pointsets/bn_tables.h"    // sobol_256spp_256d, scramblingTile_yx_d_1spp (vulkan/pointsets/render_bn.cpp)
 
 namespace glsl {
 using namespace glm;
@@ -148,7 +150,26 @@ void RenderCuda::update_config(SceneConfig const &config) {
     check(rptr_cuda_set_scene_params(ctx, &sp));
 }
 
+// options.rng_variant (librender/render_params.glsl.h:76) + the tables the reference's pointset extensions upload
+// (RenderSobolVulkan::update_random_buf, RenderBNPointsVulkan::update_random_buf)
+void RenderCuda::apply_rng_variant() {
+    const int v = options.rng_variant;
+    if (v == applied_rng_variant) return;
+    static_assert(sizeof(SobolMatrix[0]) == 4 && sizeof(SobolInversion_1_0[0]) == 4 && sizeof(sobol_256spp_256d[0]) == 4, "table element size");
+    if (v == RNG_VARIANT_SOBOL || v == RNG_VARIANT_Z_SBL) {
+        check(rptr_cuda_set_pointset_table(ctx, RPTR_POINTSET_SOBOL_MATRIX, (const uint32_t *)SobolMatrix, sizeof(SobolMatrix) / 4));
+        check(rptr_cuda_set_pointset_table(ctx, RPTR_POINTSET_SOBOL_TILE_INVERT, (const uint32_t *)SobolInversion_1_0, sizeof(SobolInversion_1_0) / 4));
+    } else if (v == RNG_VARIANT_BN) {
+        check(rptr_cuda_set_pointset_table(ctx, RPTR_POINTSET_BN_SOBOL, (const uint32_t *)sobol_256spp_256d, sizeof(sobol_256spp_256d) / 4));
+        check(rptr_cuda_set_pointset_table(ctx, RPTR_POINTSET_BN_SCRAMBLING_1SPP, (const uint32_t *)scramblingTile_yx_d_1spp,
+                                           sizeof(scramblingTile_yx_d_1spp) / 4));
+    }
+    check(rptr_cuda_set_option(ctx, "rng_variant", v));
+    applied_rng_variant = v;
+}
+
 void RenderCuda::begin_frame(CommandStream *, const RenderConfiguration &config) {
+    apply_rng_variant();
     this->camera = config.camera;
     this->time = config.time;
     this->reset_accumulation = config.reset_accumulation;

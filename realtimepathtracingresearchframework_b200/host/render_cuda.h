@@ -47,6 +47,8 @@ protected:
 
 private:
     void check(int rc) const;
+    void apply_rng_variant();
+    int applied_rng_variant = RNG_VARIANT_UNIFORM;
     rptr_ctx *ctx = nullptr;
     int fb_width = 0, fb_height = 0;
     bool has_lights = false;

@@ -20,6 +20,8 @@ struct hostsim_args { // same layout as oracle_render_args
     int32_t n_samples;
     int32_t x0, y0, x1, y1;
     int32_t transmission, n_threads;
+    int32_t rng_variant, batch_spp;
+    const uint32_t *pointset_tables[4];
 };
 
 struct hostsim_scene { HostScene hs; std::vector<GeomInst> gi; };
@@ -65,6 +67,11 @@ static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
     fp.bin_size = a->lighting.bin_size;
     fp.n_bins = fp.bin_size > 0 ? (fp.n_lights + fp.bin_size - 1) / fp.bin_size : 0;
     fp.transmission = a->transmission;
+    fp.rng_variant = a->rng_variant;
+    fp.pts.sobol_matrix = a->pointset_tables[0];
+    fp.pts.sobol_tile_invert = a->pointset_tables[1];
+    fp.pts.bn_sobol = a->pointset_tables[2];
+    fp.pts.bn_scrambling = a->pointset_tables[3];
     fp.sp = a->scene_params;
     if (fp.n_lights > 0) fp.sp.sun_radiance[3] *= 0.5f;
     else fp.sp.sun_radiance[3] = 1.0f;
@@ -97,6 +104,27 @@ int hostsim_render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_
             px[0] = ps.illum.x; px[1] = ps.illum.y; px[2] = ps.illum.z; px[3] = ps.bounce == 0 ? 0.0f : 1.0f;
         }
     return 0;
+}
+
+// sampler calls replayed through the product's rptr_pointsets.cuh (same protocol as oracle_pointset_replay)
+int hostsim_pointset_replay(int variant, const uint32_t *const *tables, uint32_t sample_index, uint32_t frame_id, uint32_t frame_offset, uint32_t px,
+                            uint32_t py, uint32_t w, const int32_t *ops, const int32_t *args, int n_ops, float *out, uint32_t *state_out) {
+    PointsetTables t{tables[0], tables[1], tables[2], tables[3]};
+    Sampler s = sampler_init(variant, t, sample_index, frame_id, frame_offset, px, py, w);
+    if (state_out) {
+        state_out[0] = s.b;
+        state_out[1] = s.a;
+    }
+    int n = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        if (ops[i] == 0) out[n++] = sampler_next(variant, t, s, args[i]);
+        else if (ops[i] == 1) s.dim = args[i];
+        else s.dim += args[i];
+    }
+    return n;
+}
+uint32_t hostsim_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, uint32_t tw, uint32_t th, int hash_tile, int hash_sample) {
+    return morton_sample_id(sample_id, px, py, tw, th, hash_tile != 0, hash_sample != 0);
 }
 
 } // extern "C"

@@ -403,3 +403,42 @@ def test_c4_full_size_properties():
         t.render_spp(s.camera, 2, batch_spp=1)
         parts.append(t.framebuffer())
     assert np.array_equal((parts[0] + parts[1]).view(np.uint32), img.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [T.RNG_VARIANT_BN, T.RNG_VARIANT_SOBOL, T.RNG_VARIANT_Z_SBL])
+def test_low_discrepancy_samplers(oracle, variant):
+    """options.rng_variant = BN / SOBOL / Z_SBL: the CUDA wavefront with the reference's sampler tables
+    against the oracle (itself pinned to streams executed from rendering/pointsets/*.glsl), progressive over several
+    frames and as one batch; frame wider than a 256-pixel Sobol tile and taller than a 128-pixel blue-noise tile."""
+    from realtimepathtracingresearchframework_b200 import load_pointset_tables
+    tables = load_pointset_tables()
+    s = scenes.random_triangles(20000)
+    W, H = 400, 225
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    sp = load_sky_fit(T.SceneConfig(**sky))
+    o = oracle.OracleScene(s)
+    r = make_backend(s, W, H, sky)
+    with pytest.raises(RptrError):  # tables are the caller's data, like the sky fit: selecting the variant alone must fail loudly
+        r.set_option("rng_variant", variant)
+        r.render_spp(s.camera, 1)
+    r.close()
+    r = make_backend(s, W, H, sky)
+    r.set_rng_variant(variant, tables)
+    r.render_spp(s.camera, 3, batch_spp=1)
+    ref, _ = o.render(W, H, s.camera, sp, spp=3, rng_variant=variant, pointset_tables=tables)
+    assert_identical(r.framebuffer(), ref, "rng_variant %d, 3 frames" % variant)
+    uni, _ = o.render(W, H, s.camera, sp, spp=3)
+    assert not np.array_equal(ref, uni)
+    # one frame of batch_spp = 4 in waves of 3 + 1 layers; BN seeds every layer from the frame's frame_id (bn_rng.glsl:112)
+    b = make_backend(s, W, H, sky, wave_paths=3 * W * H)
+    b.set_rng_variant(variant, tables)
+    b.render_spp(s.camera, 4, batch_spp=4)
+    refb, _ = o.render(W, H, s.camera, sp, spp=4, rng_variant=variant, pointset_tables=tables, batch_spp=4)
+    assert_identical(b.framebuffer(), refb, "rng_variant %d, batch of 4" % variant)
+    # back to the LCG on the same context
+    b.set_rng_variant(0)
+    b.render_spp(s.camera, 2)
+    assert b.frame_state()[1] == 4  # reset_accumulation rolled frame_offset += frame_id (vulkan/render_vulkan.cpp:1937-1941)
+    refu, _ = o.render(W, H, s.camera, sp, spp=2, frame_offset=4)
+    assert_identical(b.framebuffer(), refu, "back to UNIFORM")
