@@ -28,6 +28,16 @@ sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL: "NCCL version ..." from rank 0), so fd 1 is
+# pointed at stderr for everything but our own line.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -171,7 +181,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args)}, "cpu_baseline": base,
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -312,7 +322,7 @@ def run_b200(args):
             "gpu_launches": int(cnt["launches"]), "clocks": clk, "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, scene, args.cpu_seconds)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

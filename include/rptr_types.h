@@ -197,6 +197,24 @@ typedef struct rptr_instance_desc {
     float transform[12];
 } rptr_instance_desc;
 
+/* A texture as the reference's Image holds it (util/image.h:8-27): 8-bit texels, `channels` per pixel, row-major.
+ * This round the backend accepts 1 x 1 textures only ("1x1-texel mode"): a material parameter that carries a
+ * texture handle (rendering/bsdfs/texture_channel_mask.h) then resolves to one texel, UNORM8 -> value / 255, colour
+ * channels of an sRGB texture through the sRGB transfer function.  Larger textures are rejected with an error. */
+#define RPTR_COLOR_SPACE_LINEAR 0
+#define RPTR_COLOR_SPACE_SRGB 1
+typedef struct rptr_texture_desc {
+    int32_t width, height;
+    int32_t channels;    /* 1..4; missing colour channels read 0, missing alpha reads 255 */
+    int32_t color_space; /* RPTR_COLOR_SPACE_* */
+    const uint8_t *texels;
+} rptr_texture_desc;
+
+/* rendering/bsdfs/texture_channel_mask.h:20-27: a float material parameter with the sign bit set is a texture handle */
+#define RPTR_TEXTURED_PARAM_MASK 0x80000000u
+#define RPTR_GET_TEXTURE_CHANNEL(x) (((x) >> 29) & 0x3u)
+#define RPTR_GET_TEXTURE_ID(x) ((x) & 0x1fffffffu)
+
 typedef struct rptr_scene_desc {
     const rptr_geometry_desc *geometries;
     int32_t n_geometries;
@@ -213,6 +231,9 @@ typedef struct rptr_scene_desc {
      * (librender/lights.cpp:14-90). */
     const rptr_tri_light_data *binned_lights;
     int32_t n_binned_lights;
+    /* Scene::textures (librender/scene.h); material parameters refer to them through texture handles. May be NULL. */
+    const rptr_texture_desc *textures;
+    int32_t n_textures;
 } rptr_scene_desc;
 
 #ifdef __cplusplus

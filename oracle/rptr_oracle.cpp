@@ -66,6 +66,10 @@ struct Scene {
     std::vector<rptr_base_material> materials;
     std::vector<rptr_tri_light_data> lights;
     bool any_non_opaque = false;
+    // owned copies of the scene's textures (1 x 1 texel mode)
+    std::vector<rptr_texture_desc> textures;
+    std::vector<std::vector<uint8_t>> own_texels;
+    TextureSet texset;
     // owned copies of the input streams (the caller's Scene dies after set_scene, app.cpp:151-175)
     std::vector<std::vector<uint64_t>> own_qv, own_qn;
     std::vector<std::vector<uint8_t>> own_tm;
@@ -532,6 +536,16 @@ oracle_scene *oracle_scene_create(const rptr_scene_desc *d, const rptr_light_sam
     oracle_scene *os = new oracle_scene();
     Scene &s = os->s;
     s.materials.assign(d->materials, d->materials + d->n_materials);
+    s.own_texels.resize(d->textures ? d->n_textures : 0);
+    for (int t = 0; t < (int)s.own_texels.size(); ++t) {
+        rptr_texture_desc td = d->textures[t];
+        if (td.width != 1 || td.height != 1) { delete os; return nullptr; } // 1x1-texel mode only
+        s.own_texels[t].assign(td.texels, td.texels + td.channels);
+        td.texels = s.own_texels[t].data();
+        s.textures.push_back(td);
+    }
+    s.texset.tex = s.textures.data();
+    s.texset.n = (int)s.textures.size();
     // copy the streams
     s.own_qv.resize(d->n_geometries);
     s.own_qn.resize(d->n_geometries);
@@ -735,8 +749,6 @@ static V3 sample_tri_lights(const Frame &f, V3 hit_p, V3 hit_n, V2 dir_sample, V
 
 static inline float geometry_scale_to_tmin(V3 orig, float scale) { return (length(orig) + scale) * 0.000005f; } // vulkan/geometry.glsl:76-78
 
-// alpha of a candidate: constants only -> 1 (textured alpha arrives with the texture path)
-static inline float material_alpha(const rptr_base_material &) { return 1.0f; }
 
 // raytrace_test_visibility: vulkan/pt_megakernel.glsl:216-272
 static bool test_visibility(const Frame &f, V3 from, V3 dir, float dist, float geometry_scale, uint32_t pixel_linear,
@@ -752,7 +764,7 @@ static bool test_visibility(const Frame &f, V3 from, V3 dir, float dist, float g
             const rptr_base_material &m = s.materials[calc_hit_material_id(g, (uint32_t)tr.prim)];
             if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) return true;
             Lcg arng = lcg_seed((uint32_t)tr.prim ^ frame_id, (uint32_t)g.instance ^ f.a->frame_offset, pixel_linear);
-            float alpha = material_alpha(m);
+            float alpha = material_alpha(s.texset, m);
             if (!(alpha > 0.0f) || (alpha < 1.0f && lcg_randomf(arng) > alpha)) return false;
             return true;
         });
@@ -821,7 +833,7 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
             if (g.flags & RPTR_GEOMETRY_FLAGS_NOALPHA) break;
             const rptr_base_material &m = s.materials[calc_hit_material_id(g, (uint32_t)tr.prim)];
             if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) break;
-            float alpha = material_alpha(m);
+            float alpha = material_alpha(s.texset, m);
             if (!(alpha > 0.0f) || (alpha < 1.0f && rng.draw_alpha() > alpha)) {
                 after_t = hit.t;
                 after_id = hit.tri;
@@ -871,7 +883,7 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         // ---- shade_base_material ----
         GltfMat mat;
         V3 emit;
-        unpack_material(mat, emit, mp, f.tr);
+        unpack_material(mat, emit, mp, f.tr, s.texset);
         if (a.params.output_channel == 0 && !is_zero(emit)) { // :33-39
             float light_pdf = (1.0f - p_sun) * (1.0f / ((float)f.n_bins * approx_sa));
             float w = nee_mis_heuristic(1.0f, prev_bounce_pdf, 1.0f, light_pdf);
@@ -915,7 +927,7 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
             }
             V3 contrib = v3(0.0f);
             if (light_pdf > 0.0f && dot(light_dir, ign) * dot(light_dir, in_) > 0.0f) {
-                bool vis = test_visibility(f, ip, light_dir, light_dist, geometry_scale, linear, sample_index, cnt);
+                bool vis = test_visibility(f, ip, light_dir, light_dist, geometry_scale, linear, view_frame_id, cnt);
                 float bsdf_pdf = gltf_wpdf(mat, in_, w_o, light_dir, f.tr);
                 if (bsdf_pdf >= 0.0f && vis) {
                     V3 bsdf = gltf_bsdf(mat, in_, w_o, light_dir, f.tr);
@@ -1121,7 +1133,7 @@ float oracle_fast_positive_atan(float y) { return fast_positive_atan(y); }
 static GltfMat mat_from(const rptr_base_material *p, int tr) {
     GltfMat m;
     V3 e;
-    unpack_material(m, e, *p, tr != 0);
+    unpack_material(m, e, *p, tr != 0, TextureSet());
     return m;
 }
 void oracle_gltf_bsdf(const rptr_base_material *p, const float *n, const float *wo, const float *wi, int tr, float *out) {

@@ -62,23 +62,64 @@ struct GltfMat {
 };
 static inline bool is_textured(float v) { return (f2u(v) & 0x80000000u) != 0; }
 
-// constants-only unpack (non-unrolled standard-texture semantics, rendering/rt/materials.glsl:42-49); returns alpha
-static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_material &p, bool transmission) {
-    float alpha = 1.0f;
-    m.base_color = v3(p.base_color[0], p.base_color[1], p.base_color[2]);
+// ---- textures: rendering/rt/material_textures.glsl:37-63 in 1x1-texel mode -------------------------------
+// A 1 x 1 texture returns its only texel whatever the uv / LOD.  UNORM8 -> v / 255; colour channels of an sRGB image through
+// the sRGB transfer function, evaluated in double and rounded once (our statement of the texture unit's table).
+struct TextureSet {
+    const rptr_texture_desc *tex = nullptr;
+    int n = 0;
+    struct RGBA { float r, g, b, a; };
+    static float decode(int v, bool srgb) {
+        if (!srgb) return (float)v / 255.0f;
+        double c = (double)v / 255.0;
+        return (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+    }
+    RGBA texel(uint32_t id) const {
+        const rptr_texture_desc &t = tex[id];
+        bool srgb = t.color_space == RPTR_COLOR_SPACE_SRGB;
+        float ch[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+        for (int k = 0; k < t.channels && k < 4; ++k) ch[k] = k == 3 ? (float)t.texels[3] / 255.0f : decode(t.texels[k], srgb);
+        return RGBA{ch[0], ch[1], ch[2], ch[3]};
+    }
+    static bool is_handle(float x) { return (f2u(x) & RPTR_TEXTURED_PARAM_MASK) != 0; }
+    // textured_color_param(vec4(p.base_color, 1), hit)
+    RGBA color_param(const float *rgb) const {
+        if (is_handle(rgb[0])) return texel(RPTR_GET_TEXTURE_ID(f2u(rgb[0])));
+        return RGBA{rgb[0], rgb[1], rgb[2], 1.0f};
+    }
+    // textured_scalar_param(x, hit)
+    float scalar_param(float x) const {
+        if (!is_handle(x)) return x;
+        RGBA t = texel(RPTR_GET_TEXTURE_ID(f2u(x)));
+        const float ch[4] = {t.r, t.g, t.b, t.a};
+        return ch[RPTR_GET_TEXTURE_CHANNEL(f2u(x))];
+    }
+};
+// get_material_alpha (material_textures.glsl:137-145)
+static inline float material_alpha(const TextureSet &ts, const rptr_base_material &p) { return ts.color_param(p.base_color).a; }
+
+// unpack_material (material_textures.glsl:95-135, non-unrolled standard-texture semantics of rendering/rt/materials.glsl:42-49);
+// returns alpha
+static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_material &p, bool transmission, const TextureSet &ts) {
+    TextureSet::RGBA texel = ts.color_param(p.base_color);
+    float alpha = texel.a;
+    m.base_color = v3(texel.r, texel.g, texel.b);
     if (alpha > 0.001f) m.base_color = m.base_color / alpha; // PREMULTIPLIED_BASE_COLOR_ALPHA
-    m.specular = p.specular;
-    m.roughness = p.roughness;
-    m.metallic = p.metallic;
-    m.ior = p.ior;
+    m.specular = ts.scalar_param(p.specular);
+    m.roughness = ts.scalar_param(p.roughness);
+    m.metallic = ts.scalar_param(p.metallic);
+    m.ior = ts.scalar_param(p.ior);
     emit = v3(p.base_color[0], p.base_color[1], p.base_color[2]) * p.emission_intensity;
-    if (p.emission_intensity != 0.0f) m.base_color = v3(0.0f);
+    if (p.emission_intensity != 0.0f) {
+        if (TextureSet::is_handle(p.base_color[0])) emit = m.base_color * p.emission_intensity;
+        m.base_color = v3(0.0f);
+    }
     // load_material (gltf_bsdf.glsl:38-62)
     m.specular_transmission = 0.0f;
     m.transmission_color = v3(0.0f);
     m.transmission_roughness = 0.0f;
     if (transmission) {
-        m.specular_transmission = p.specular_transmission;
+        m.specular_transmission = ts.scalar_param(p.specular_transmission);
         if (m.specular_transmission > 0.0f) {
             if (!(m.ior > 1.0f)) {
                 alpha *= 1.0f - m.specular_transmission;
@@ -86,7 +127,7 @@ static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_materi
             } else {
                 m.transmission_color = m.base_color;
                 m.transmission_roughness = m.roughness;
-                m.roughness = sqrtf(p.clearcoat_gloss);
+                m.roughness = sqrtf(ts.scalar_param(p.clearcoat_gloss));
             }
         }
     }

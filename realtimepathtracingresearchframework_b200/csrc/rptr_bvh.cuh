@@ -93,6 +93,26 @@ RPTR_HD bool intersect_tri(float3 v0, float3 e1, float3 e2, float3 o, float3 d, 
 
 struct TraceCounters { uint32_t nodes, tris; };
 
+// ---- stochastic alpha: the candidate filter of non-opaque triangles (generate_candidate_hit, pt_megakernel.glsl:153-211) ----
+// Only triangles whose material alpha texel is not 255 take part (tri_alpha8).  Closest hit: candidates are
+// judged front to back in (t, id) order with the path's own LCG -- rejected iff !(alpha > 0) || (alpha < 1 && u > alpha), one
+// draw per candidate with 0 < alpha < 1 -- which the traversal realises as "closest hit AFTER (after_t, after_id)" restarted
+// for every rejected candidate.  Visibility rays (:216-272): every candidate gets its own LCG seeded from
+// (primitive ^ frame_id, instance ^ frame_offset, pixel), so the verdict does not depend on the traversal order.
+struct AlphaFilter {
+    const GeomInst *ginst;
+    uint32_t frame_id, frame_offset; // view_params.frame_id / frame_offset of the frame (batch)
+    uint32_t pixel_linear;           // gl_GlobalInvocationID.x + y * frame_dims.x
+};
+RPTR_HD bool alpha_rejects(float alpha, uint32_t &lcg_state) { return !(alpha > 0.0f) || (alpha < 1.0f && lcg_randomf(lcg_state) > alpha); }
+RPTR_HD bool shadow_candidate_passes(const AlphaFilter &f, int32_t gi_alpha, int32_t prim) {
+    const int32_t a8 = (int32_t)(((uint32_t)gi_alpha) >> 24);
+    if (a8 == RPTR_TRI_OPAQUE) return true;
+    const GeomInst &g = f.ginst[gi_alpha & 0x00ffffff];
+    uint32_t st = lcg_seed((uint32_t)prim ^ f.frame_id, (uint32_t)g.instance ^ f.frame_offset, f.pixel_linear);
+    return !alpha_rejects(alpha8_to_float(a8), st);
+}
+
 RPTR_HD float slab_safe(float d) { return fabsf(d) > 1e-18f ? d : copysignf(1e-18f, d); }
 
 RPTR_HD float u2f_(uint32_t u) {
@@ -193,8 +213,11 @@ RPTR_HD void decode_child(const BvhNode &nd, int k, float *lo, float *hi) {
 
 // Reference traversal (host-executable statement of the contract; the GPU's persistent kernel in
 // rptr_trace_kernels.cuh visits the same tree in a different order with the same result).  Any = stop at the first hit.
+// Closest: only candidates strictly after (after_t, after_id) in (t, id) order count (after_t = tmin, after_id = INT_MAX: all).
+// Any: `filter` (may be null = every triangle opaque) decides whether a non-opaque candidate occludes.
 template <bool Any>
-RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float tmax, HitRec &best, TraceCounters &cnt) {
+RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float tmax, HitRec &best, TraceCounters &cnt, float after_t,
+                      int32_t after_id, const AlphaFilter *filter) {
     best.tri = -1;
     best.id = 0x7fffffff;
     best.t = tmax;
@@ -241,9 +264,11 @@ RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float 
                 if (!(t > tmin && t < tmax)) continue;
                 const int32_t id = f2i(c4.y);
                 if (Any) {
+                    if (filter && !shadow_candidate_passes(*filter, f2i(c4.z), f2i(c4.w))) continue;
                     best.t = t; best.u = u; best.v = v; best.tri = first + i; best.id = id;
                     return true;
                 }
+                if (!(t > after_t || (t == after_t && id > after_id))) continue;
                 if (best.tri < 0 || t < best.t || (t == best.t && id < best.id)) {
                     best.t = t; best.u = u; best.v = v; best.tri = first + i; best.id = id;
                 }
@@ -253,6 +278,24 @@ RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float 
             break;
     }
     return best.tri >= 0;
+}
+template <bool Any>
+RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float tmax, HitRec &best, TraceCounters &cnt) {
+    return trace_ray<Any>(bvh, o, d, tmin, tmax, best, cnt, tmin, 0x7fffffff, nullptr);
+}
+
+// Closest hit with the front-to-back candidate filter; lcg_state is the path's LCG (alpha_rng == rng for the LCG pointset,
+// pt_megakernel.glsl:354-355) and advances by one draw per candidate with 0 < alpha < 1.
+RPTR_HD bool closest_hit_filtered(const BvhDev &bvh, float3 o, float3 d, float tmin, float tmax, uint32_t &lcg_state, HitRec &best, TraceCounters &cnt) {
+    float after_t = tmin;
+    int32_t after_id = 0x7fffffff;
+    for (;;) {
+        if (!trace_ray<false>(bvh, o, d, tmin, tmax, best, cnt, after_t, after_id, nullptr)) return false;
+        const int32_t a8 = tri_alpha8(bvh.tris[best.tri]);
+        if (a8 == RPTR_TRI_OPAQUE || !alpha_rejects(alpha8_to_float(a8), lcg_state)) return true;
+        after_t = best.t;
+        after_id = best.id;
+    }
 }
 
 } // namespace rp

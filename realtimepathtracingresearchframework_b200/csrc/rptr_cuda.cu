@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                 uint32_t key = 0; // miss
                 if (tri >= 0) {
                     const Tri *tr = bvh.tris + tri;
-                    const GeomInst &g = sc.ginst[tr->geom_inst];
+                    const GeomInst &g = sc.ginst[tri_geom_inst(*tr)];
                     // key = code path of shade_vertex, not the material itself (keeps neighbouring pixels together):
                     // Lambert / GGX / thin or thick transmission, plus the emitter-MIS variant of each
                     const rptr_base_material &m = sc.materials[calc_hit_material_id(g, (uint32_t)tr->prim)];
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(128) k_ray_queries(BvhDev bvh, const rptr_rend
         HitRec h;
         const bool ok = trace_ray<false>(bvh, f3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), f3(q[i].dir[0], q[i].dir[1], q[i].dir[2]), 0.0f, q[i].t_max, h, cnt);
         int32_t gi = -1, prim = -1;
-        if (ok) { gi = bvh.tris[h.tri].geom_inst; prim = bvh.tris[h.tri].prim; }
+        if (ok) { gi = tri_geom_inst(bvh.tris[h.tri]); prim = bvh.tris[h.tri].prim; }
         results[i] = f4(ok ? h.u : 0.0f, ok ? h.v : 0.0f, __int_as_float(gi), __int_as_float(prim));
         if (hit_t) hit_t[i] = ok ? h.t : -1.0f;
     }

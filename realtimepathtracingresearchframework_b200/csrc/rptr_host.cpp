@@ -169,16 +169,71 @@ void equalize_emitter_bins(std::vector<Emitter> &emitters, std::vector<float> &r
 } // namespace
 
 // ---- scene flattening ---------------------------------------------------------------------------------------------------
+// ---- 1x1-texel mode: material parameters that carry texture handles are resolved on the host -----------------
+// The reference samples textures at the hit's uv (rendering/rt/material_textures.glsl:37-63); a 1 x 1 texture returns its only
+// texel for every uv and every LOD, so the lookup can be done once per material here and the kernels keep reading
+// constants.  UNORM8 -> v / 255 in float; colour channels of an sRGB image go through the sRGB transfer function evaluated in
+// double and rounded once (the texture unit's own table is not specified bit for bit; this is our statement of it).
+namespace {
+float srgb8_to_linear(int v) {
+    const double c = (double)v / 255.0;
+    return (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+}
+struct Texel { float c[4]; int a8; };
+Texel fetch_texel(const rptr_scene_desc &d, uint32_t handle) {
+    const uint32_t id = RPTR_GET_TEXTURE_ID(handle);
+    if (!d.textures || id >= (uint32_t)d.n_textures) throw std::runtime_error("material refers to texture " + std::to_string(id) + " which the scene does not have");
+    const rptr_texture_desc &t = d.textures[id];
+    if (t.width != 1 || t.height != 1)
+        throw std::runtime_error("texture " + std::to_string(id) + " is " + std::to_string(t.width) + " x " + std::to_string(t.height) +
+                                 ": only 1 x 1 textures are supported by this backend yet (1x1-texel mode)");
+    if (t.channels < 1 || t.channels > 4 || !t.texels) throw std::runtime_error("texture " + std::to_string(id) + " has no texels / bad channel count");
+    Texel x;
+    for (int k = 0; k < 3; ++k) {
+        const int v = k < t.channels ? t.texels[k] : 0;
+        x.c[k] = t.color_space == RPTR_COLOR_SPACE_SRGB ? srgb8_to_linear(v) : (float)v / 255.0f;
+    }
+    x.a8 = t.channels == 4 ? t.texels[3] : 255;
+    x.c[3] = alpha8_to_float(x.a8);
+    return x;
+}
+bool is_handle(float v) { return (f2u(v) & RPTR_TEXTURED_PARAM_MASK) != 0; }
+// textured_scalar_param (material_textures.glsl:50-63)
+float resolve_scalar(const rptr_scene_desc &d, float v) {
+    if (!is_handle(v)) return v;
+    return fetch_texel(d, f2u(v)).c[RPTR_GET_TEXTURE_CHANNEL(f2u(v))];
+}
+} // namespace
+
+// unpack_material's texture reads (material_textures.glsl:95-135, non-unrolled standard-texture semantics of
+// rendering/rt/materials.glsl:42-49) folded into the BaseMaterial; alpha8 = the texel get_material_alpha() would read.
+static void resolve_materials(const rptr_scene_desc &d, HostScene &s) {
+    s.materials.assign(d.materials, d.materials + d.n_materials);
+    s.material_alpha8.assign(d.n_materials, RPTR_TRI_OPAQUE);
+    for (int i = 0; i < d.n_materials; ++i) {
+        rptr_base_material &m = s.materials[i];
+        if (m.normal_map != -1) throw std::runtime_error("normal maps are not supported by this backend yet (normal_map must be -1)");
+        if (is_handle(m.base_color[0])) {
+            if (m.emission_intensity != 0.0f) throw std::runtime_error("emissive materials with a textured base colour are not supported by this backend yet");
+            const Texel x = fetch_texel(d, f2u(m.base_color[0]));
+            const float alpha = x.c[3];
+            for (int k = 0; k < 3; ++k) m.base_color[k] = alpha > 0.001f ? x.c[k] / alpha : x.c[k]; // PREMULTIPLIED_BASE_COLOR_ALPHA, :101-104
+            s.material_alpha8[i] = x.a8;
+        }
+        m.specular = resolve_scalar(d, m.specular);
+        m.roughness = resolve_scalar(d, m.roughness);
+        m.metallic = resolve_scalar(d, m.metallic);
+        m.ior = resolve_scalar(d, m.ior);
+        m.specular_transmission = resolve_scalar(d, m.specular_transmission);
+        m.clearcoat_gloss = resolve_scalar(d, m.clearcoat_gloss);
+        if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) s.material_alpha8[i] = RPTR_TRI_OPAQUE; // never alpha-tested (pt_megakernel.glsl:202)
+    }
+}
+
 void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config &ls, HostScene &s, bool with_bvh) {
     s = HostScene();
     if (d.n_materials <= 0 || !d.materials) throw std::runtime_error("scene has no materials");
-    s.materials.assign(d.materials, d.materials + d.n_materials);
-    for (const rptr_base_material &m : s.materials) {
-        const float scal[] = {m.base_color[0], m.roughness, m.specular, m.metallic, m.ior, m.specular_transmission, m.clearcoat_gloss};
-        for (float v : scal)
-            if (f2u(v) & 0x80000000u) throw std::runtime_error("textured material parameters are not supported by this backend yet (constants only)");
-        if (m.normal_map != -1) throw std::runtime_error("normal maps are not supported by this backend yet (normal_map must be -1)");
-    }
+    resolve_materials(d, s);
     s.qverts.resize(d.n_geometries);
     s.qnuv.resize(d.n_geometries);
     for (int g = 0; g < d.n_geometries; ++g) {
@@ -201,6 +256,11 @@ void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config
         for (int j = 0; j < mesh.n_geometries; ++j) total += (size_t)d.geometries[mesh.first_geometry + j].n_tris;
     }
     if (total > 0x1ffffff0u) throw std::runtime_error("too many triangles after instancing (limit 2^29)");
+    {
+        size_t n_gi = 0;
+        for (int i = 0; i < d.n_instances; ++i) n_gi += (size_t)d.meshes[d.pmeshes[d.instances[i].pmesh_id].mesh_id].n_geometries;
+        if (n_gi >= (1u << 24)) throw std::runtime_error("too many (instance, geometry) pairs (limit 2^24)");
+    }
     s.tris.reserve(total);
 
     std::vector<Emitter> emitters;
@@ -262,7 +322,9 @@ void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config
                 tr.e1x = e1.x; tr.e1y = e1.y; tr.e1z = e1.z;
                 tr.e2x = e2.x; tr.e2y = e2.y; tr.e2z = e2.z;
                 tr.id = (int32_t)s.tris.size();
-                tr.geom_inst = gi;
+                const int32_t a8 = no_alpha ? RPTR_TRI_OPAQUE : s.material_alpha8[per_tri ? mat_off + tm[t] : mat_off];
+                if (a8 != RPTR_TRI_OPAQUE) s.any_alpha_tested = true;
+                tr.gi_alpha = pack_gi_alpha(gi, a8);
                 tr.prim = t;
                 s.tris.push_back(tr);
                 if (!nonemissive[inst.pmesh_id]) { // collect_emitters, lights.cpp:33-73

@@ -22,7 +22,9 @@ struct HostScene {
     std::vector<std::vector<uint64_t>> qverts, qnuv;
     std::vector<std::vector<uint8_t>> tri_mat;
     std::vector<HostGeomInst> ginst;
-    std::vector<rptr_base_material> materials;
+    std::vector<rptr_base_material> materials;   // texture handles already resolved to constants (1x1-texel mode)
+    std::vector<int32_t> material_alpha8;       // per material: alpha texel (255 = opaque)
+    bool any_alpha_tested = false;              // some triangle has alpha8 != 255: traversal must run the candidate filter
     std::vector<rptr_tri_light_data> lights;
     std::vector<Tri> tris;      // flattened (instance, geometry, primitive) order; Tri::id == index
     std::vector<BvhNode> nodes; // node 0 = root

@@ -31,12 +31,20 @@ struct Tri { // 48 B traversal record (three 128-bit loads), world space
 #endif
     float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
     int32_t id;        // flattened (instance, geometry, primitive) index: the closest-hit tie-break key
-    int32_t geom_inst; // index into GeomInst[]
+    int32_t gi_alpha;  // index into GeomInst[] (low 24 bits) | 8-bit material alpha << 24; see tri_geom_inst / tri_alpha8
     int32_t prim;
 #ifdef RPTR_TRI64
     int32_t pad[4];
 #endif
 };
+
+// Alpha of the triangle's material as the 8-bit texel it comes from (1x1-texel mode, rptr_host.cpp resolve_materials):
+// 255 = opaque (NOALPHA flags, constant colour or alpha texel 255) -> traversal never draws for it.
+#define RPTR_TRI_OPAQUE 255
+RPTR_HD int32_t tri_geom_inst(const Tri &t) { return t.gi_alpha & 0x00ffffff; }
+RPTR_HD int32_t tri_alpha8(const Tri &t) { return (int32_t)(((uint32_t)t.gi_alpha) >> 24); }
+RPTR_HD int32_t pack_gi_alpha(int32_t geom_inst, int32_t alpha8) { return (int32_t)(((uint32_t)alpha8 << 24) | (uint32_t)geom_inst); }
+RPTR_HD float alpha8_to_float(int32_t a8) { return (float)a8 / 255.0f; } // UNORM8 texel
 
 struct SceneDev {
     const GeomInst *ginst;
@@ -747,7 +755,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
     const bool tr = (FEAT & RPTR_FEAT_TRANSMISSION) && fp.transmission != 0;
     const int output_channel = (FEAT & RPTR_FEAT_AOV) ? fp.output_channel : 0;
     ps.rng_dim = RPTR_DIM_CAMERA_END + ps.bounce * (RPTR_DIM_VERTEX_END + RPTR_DIM_LIGHT_END); // RANDOM_SET_DIM, pt_megakernel.glsl:423
-    const GeomInst &g = sc.ginst[tri->geom_inst];
+    const GeomInst &g = sc.ginst[tri_geom_inst(*tri)];
     RTHit h = calc_hit_attributes(g, hit_t, (uint32_t)tri->prim, hit_u, hit_v);
     float approx_sa = length(h.geo_normal);
     h.geo_normal = h.geo_normal / approx_sa;

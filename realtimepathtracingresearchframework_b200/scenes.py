@@ -146,6 +146,16 @@ class Scene:
             bl = (T.TriLightData * len(self.binned_lights))(*self.binned_lights)
             d.binned_lights, d.n_binned_lights = bl, len(self.binned_lights)
             keep.append(bl)
+        if getattr(self, "textures", None):
+            texs = (T.TextureDesc * len(self.textures))()
+            for i, (texels, color_space) in enumerate(self.textures):
+                px = np.ascontiguousarray(texels, np.uint8)
+                h, w, ch = px.shape
+                texs[i].width, texs[i].height, texs[i].channels, texs[i].color_space = w, h, ch, color_space
+                texs[i].texels = px.ctypes.data_as(C.POINTER(C.c_uint8))
+                keep.append(px)
+            d.textures, d.n_textures = texs, len(self.textures)
+            keep.append(texs)
         keep += [geoms, meshes, pms, insts, mats]
         self._keep = keep  # ctypes arrays must outlive the descriptor
         return d

@@ -104,11 +104,26 @@ class InstanceDesc(_Pod):
     _defaults_ = dict(transform=(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0))
 
 
+class TextureDesc(_Pod):
+    _fields_ = [("width", i32), ("height", i32), ("channels", i32), ("color_space", i32), ("texels", C.POINTER(C.c_uint8))]
+
+
+COLOR_SPACE_LINEAR, COLOR_SPACE_SRGB = 0, 1
+
+
+def texture_handle(texture_id, channel=0):
+    """A float material parameter that refers to a texture (rendering/bsdfs/texture_channel_mask.h:20-27): sign bit set,
+    bits 29-30 = channel, bits 0-28 = texture id."""
+    import struct
+    return struct.unpack("<f", struct.pack("<I", 0x80000000 | ((channel & 3) << 29) | (texture_id & 0x1fffffff)))[0]
+
+
 class SceneDesc(_Pod):
     _fields_ = [("geometries", C.POINTER(GeometryDesc)), ("n_geometries", i32), ("meshes", C.POINTER(MeshDesc)),
                 ("n_meshes", i32), ("pmeshes", C.POINTER(PMeshDesc)), ("n_pmeshes", i32),
                 ("instances", C.POINTER(InstanceDesc)), ("n_instances", i32), ("materials", C.POINTER(BaseMaterial)),
-                ("n_materials", i32), ("binned_lights", C.POINTER(TriLightData)), ("n_binned_lights", i32)]
+                ("n_materials", i32), ("binned_lights", C.POINTER(TriLightData)), ("n_binned_lights", i32),
+                ("textures", C.POINTER(TextureDesc)), ("n_textures", i32)]
 
 
 assert C.sizeof(BaseMaterial) == 80 and C.sizeof(RenderParams) == 80 and C.sizeof(LightSamplingConfig) == 16

@@ -1,5 +1,3 @@
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/t.log 2>&1; tail -5 gpurun_out/t.log
-timeout 600 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -c 600 gpurun_out/bench_full.json
-timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_trace_persistent -c 40 --csv \
-   --log-file gpurun_out/trace_dram.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/b_ncu4.log 2>&1
-tail -2 gpurun_out/trace_dram.csv
+N=$(nvidia-smi -L | wc -l); echo "gpus: $N"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; python -c "
+import json; j=json.load(open('gpurun_out/bench_${N}gpu.json')); print(j['n_gpus'], j['value'], j['e2e']['value'], j['ms_per_step'])"; tail -2 gpurun_out/bench_${N}gpu.err

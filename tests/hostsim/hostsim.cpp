@@ -91,12 +91,14 @@ int hostsim_render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_
             TraceCounters cnt{0, 0};
             for (;;) {
                 HitRec h;
-                bool found = trace_ray<false>(bvh, ps.o, ps.d, ps.tmin, ps.tmax, h, cnt);
+                // stochastic alpha draws come from the path's LCG (the LCG pointset; the QMC pointsets keep a separate one)
+                bool found = closest_hit_filtered(bvh, ps.o, ps.d, ps.tmin, ps.tmax, ps.rng, h, cnt);
                 ShadowRay sh;
                 ShadeResult r = shade_vertex(fp, sc, ps, h.t, h.u, h.v, found ? &bvh.tris[h.tri] : nullptr, sh);
                 if (sh.tmax > 0.0f) {
                     HitRec o;
-                    if (!trace_ray<true>(bvh, sh.o, sh.d, sh.tmin, sh.tmax, o, cnt)) ps.illum = ps.illum + sh.contrib;
+                    const AlphaFilter af{sc.ginst, fp.first_sample, fp.frame_offset, (uint32_t)x + (uint32_t)y * (uint32_t)fp.width};
+                    if (!trace_ray<true>(bvh, sh.o, sh.d, sh.tmin, sh.tmax, o, cnt, sh.tmin, 0x7fffffff, &af)) ps.illum = ps.illum + sh.contrib;
                 }
                 if (r == SHADE_TERMINATE) break;
             }
@@ -138,7 +140,7 @@ extern "C" int hostsim_trace(const hostsim_scene *s, const rptr_render_ray_query
         float3 o = f3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), d = f3(q[i].dir[0], q[i].dir[1], q[i].dir[2]);
         bool ok = any ? trace_ray<true>(bvh, o, d, 0.0f, q[i].t_max, h, cnt) : trace_ray<false>(bvh, o, d, 0.0f, q[i].t_max, h, cnt);
         int32_t gi = -1, prim = -1;
-        if (ok) { gi = bvh.tris[h.tri].geom_inst; prim = bvh.tris[h.tri].prim; }
+        if (ok) { gi = tri_geom_inst(bvh.tris[h.tri]); prim = bvh.tris[h.tri].prim; }
         results[4 * i + 0] = ok ? h.u : 0.0f;
         results[4 * i + 1] = ok ? h.v : 0.0f;
         memcpy(&results[4 * i + 2], &gi, 4);
