@@ -73,6 +73,7 @@ int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *params);
  *   "rng_variant"   RenderBackendOptions::rng_variant (librender/render_params.glsl.h:34-37,76): 0 UNIFORM (LCG), 1 BN, 2 SOBOL,
  *                   3 Z_SBL; 1-3 need their tables (rptr_cuda_set_pointset_table) before the next draw_frame
  *   "wave_paths"    max paths in flight per wavefront pass (memory/occupancy knob)
+ *   "aov_buffers"   0/1  write the fp16 AOV images (default 1: ENABLE_AOV_BUFFERS, vulkan/gpu_params.glsl:19)
  *   "stage_timing"  0/1  time each stage with CUDA events into rptr_counters.ms_*
  *   "bvh_builder"   0 = binned-SAH build on the host inside set_scene, 1 = LBVH build on the device (both replace the
  *                   driver's BLAS/TLAS build, vulkan/vulkanrt_utils.cpp:82-167; images are identical either way)
@@ -109,15 +110,23 @@ int rptr_cuda_frame_state(rptr_ctx *ctx, uint32_t *frame_id, uint32_t *frame_off
 int rptr_cuda_framebuffer_size(rptr_ctx *ctx, uint32_t *width, uint32_t *height, uint32_t *channels);
 size_t rptr_cuda_readback_f32(rptr_ctx *ctx, size_t n_elems, float *dst);
 size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst);
+/* RenderGraphic::readback_aov (util/display/render_graphic.h:39-43; vulkan/render_vulkan.cpp:2290-2294): the RGBA16F AOV
+ * images the megakernel stores for the first path vertex (vulkan/accumulate.glsl:89-103): aov_index 0 = albedo.rgb +
+ * roughness (AOVAlbedoRoughnessIndex), 1 = normal.xyz + depth (AOVNormalDepthIndex), as half-float bit patterns, RGBA,
+ * row-major, top row first.  Every sample layer overwrites them; they hold the frame's last layer.  Returns the number of
+ * elements written (width*height*4) or 0: buffer too small, option "aov_buffers" off, or aov_index 2
+ * (AOVMotionJitterIndex: needs the reprojection matrices, not produced by this backend). */
+size_t rptr_cuda_readback_aov(rptr_ctx *ctx, int32_t aov_index, size_t n_elems, uint16_t *dst);
 /* device address of the RGBA32F accumulator (for the multi-GPU reduce over NCCL); valid until initialize/destroy */
 int rptr_cuda_framebuffer_device_ptr(rptr_ctx *ctx, void **ptr);
 /* the cudaStream_t all work of this context is enqueued on (CommandStream of util/device_backend.h:14-22): lets a
  * caller bracket frames with its own events or order a collective after end_frame without a host sync */
 int rptr_cuda_stream_handle(rptr_ctx *ctx, void **stream);
 
-/* RaytraceBackend::trace_ray / RQ_CLOSEST (librender/raytrace_backend.h:18; vulkan/rt_intersect.comp:28-68):
- * results[i] = (bary.x, bary.y, bits(instance+geometry index), bits(primitive index)); miss = (0, 0, bits(-1), bits(-1)).
- * hit_t (optional) receives the hit distance or -1.  Host buffers. */
+/* RaytraceBackend::trace_ray / RQ_CLOSEST (librender/raytrace_backend.h:18; vulkan/rt_intersect.comp:30-68): opaque closest
+ * hit over (RAY_EPSILON * |origin|, t_max).  results[i] = (bary.x, bary.y, bits(instance+geometry index), bits(primitive
+ * index)); miss = (-1, -1, bits(-1), bits(-1)); a query with mode_or_data < 0 is skipped and its slot left as the caller
+ * passed it.  hit_t (optional) receives the hit distance or -1.  Host buffers. */
 int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, int32_t n, float *results, float *hit_t);
 
 /* util/write_image.cpp:34-66 (WriteImage::write_pfm): "<prefix>.pfm", RGB, bottom row first, little-endian.

@@ -38,6 +38,9 @@ extern "C" {
 #define RPTR_GEOMETRY_FLAGS_THIN 0x08u
 #define RPTR_GEOMETRY_FLAGS_DYNAMIC 0x10u
 
+/* vulkan/gpu_params.glsl:27-29 */
+#define RPTR_RAY_EPSILON 0.000005f
+
 /* librender/render_params.glsl.h:16-19 */
 #define RPTR_MAX_PATH_DEPTH 9
 #define RPTR_DEFAULT_RR_PATH_DEPTH 2

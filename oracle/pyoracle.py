@@ -55,6 +55,7 @@ def lib():
         L.oracle_view_params.argtypes = [C.POINTER(T.RenderCameraParams), C.c_int32, C.c_int32, f32p]
         L.oracle_render.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), f32p, C.POINTER(C.c_uint64)]
         L.oracle_render_sample.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_uint32, f32p]
+        L.oracle_render_aov.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_uint32, f32p, f32p]
         for n in ("oracle_trace_closest", "oracle_trace_closest_bruteforce"):
             getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_int32, f32p, f32p]
         L.oracle_pointset_replay.argtypes = [C.c_int, C.POINTER(C.c_void_p)] + [C.c_uint32] * 6 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -166,6 +167,14 @@ class OracleScene:
         img = np.zeros((height, width, 4), np.float32)
         lib().oracle_render_sample(self.h, C.byref(a), sample_index, _fp(img))
         return img
+
+    def render_aov(self, width, height, camera, scene_params, sample_index, **kw):
+        """Float values behind the fp16 AOV images (albedo+roughness, normal+depth) for one sample layer."""
+        a = self._args(width, height, camera, scene_params, **kw)
+        ar = np.zeros((height, width, 4), np.float32)
+        nd = np.zeros((height, width, 4), np.float32)
+        lib().oracle_render_aov(self.h, C.byref(a), sample_index, _fp(ar), _fp(nd))
+        return ar, nd
 
     def trace_closest(self, queries, bruteforce=False):
         """queries: structured (n, 8) float32 view of RenderRayQuery -> (results (n,4) float32 bits, t (n,))."""

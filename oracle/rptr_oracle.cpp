@@ -787,7 +787,11 @@ struct PathRng {
     void shift_dim(int d) { q.shift_dim(d); }
 };
 
-static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32_t view_frame_id, Counters &cnt) {
+// what the megakernel imageStore()s into aov_albedo_roughness_buffer / aov_normal_depth_buffer for the first path vertex
+// (vulkan/accumulate.glsl:89-103), as floats: [0..3] = albedo.rgb, roughness; [4..7] = normal.xyz, depth
+struct AovOut { float v[8]; };
+
+static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32_t view_frame_id, Counters &cnt, AovOut *aov = nullptr) {
     const oracle_render_args &a = *f.a;
     const Scene &s = *f.s;
     const rptr_scene_params &sp = f.sp;
@@ -843,6 +847,11 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         }
         if (!found) { // :480-489
             illum = illum + throughput * compute_sky_illum(sp, ray_dir, prev_bounce_pdf);
+            if (aov && bounce == 0) { // :482-486: store_geometry_aovs(vec3(0), vec3(2e32), vec3(0)); store_material_aovs(vec3(0), 1, 1)
+                const float far_depth = length(v3(2.e32f) - f.cam_pos); // accumulate.glsl:92
+                const float m[8] = {0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, far_depth};
+                std::memcpy(aov->v, m, sizeof(m));
+            }
             break;
         }
         cnt.vertices++;
@@ -884,6 +893,11 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         GltfMat mat;
         V3 emit;
         unpack_material(mat, emit, mp, f.tr, s.texset);
+        if (aov && bounce == 0) { // pt_megakernel.glsl:670-672 + shade_base_material.glsl:28-31
+            const V3 alb = throughput * mat.base_color;
+            const float m[8] = {alb.x, alb.y, alb.z, mat.ior != 1.0f ? mat.roughness : 1.0f, in_.x, in_.y, in_.z, length(ip - f.cam_pos)};
+            std::memcpy(aov->v, m, sizeof(m));
+        }
         if (a.params.output_channel == 0 && !is_zero(emit)) { // :33-39
             float light_pdf = (1.0f - p_sun) * (1.0f / ((float)f.n_bins * approx_sa));
             float w = nee_mis_heuristic(1.0f, prev_bounce_pdf, 1.0f, light_pdf);
@@ -1036,6 +1050,24 @@ int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rg
     return 0;
 }
 
+// The float values behind the two fp16 AOV images for sample `sample_index` (the last layer of a frame is what survives):
+// albedo_roughness and normal_depth are W*H*4 each.
+int oracle_render_aov(const oracle_scene *os, const oracle_render_args *a, uint32_t sample_index, float *albedo_roughness, float *normal_depth) {
+    Frame f = make_frame(os, a);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = a->y0; y < a->y1; ++y) {
+        Counters cnt;
+        for (int x = a->x0; x < a->x1; ++x) {
+            AovOut o;
+            std::memset(&o, 0, sizeof(o));
+            main_spp(f, x, y, sample_index, sample_index, cnt, &o);
+            std::memcpy(albedo_roughness + 4 * ((size_t)y * a->width + x), o.v, 16);
+            std::memcpy(normal_depth + 4 * ((size_t)y * a->width + x), o.v + 4, 16);
+        }
+    }
+    return 0;
+}
+
 // One un-averaged sample layer (the vec4 main_spp returns) for every pixel of the region: sample_rgba is W*H*4.
 int oracle_render_sample(const oracle_scene *os, const oracle_render_args *a, uint32_t sample_index, float *sample_rgba) {
     Frame f = make_frame(os, a);
@@ -1057,11 +1089,13 @@ int oracle_trace_closest(const oracle_scene *os, const rptr_render_ray_query *q,
     const Scene &s = os->s;
 #pragma omp parallel for schedule(dynamic, 256)
     for (int i = 0; i < n; ++i) {
+        if (q[i].mode_or_data < 0) continue; // rt_intersect.comp:44-45
         Hit h;
         V3 o = v3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), d = v3(q[i].dir[0], q[i].dir[1], q[i].dir[2]);
-        bool ok = closest_hit(s, o, d, 0.0f, q[i].t_max, 0.0f, 0x7fffffff, h);
+        const float tmin = RPTR_RAY_EPSILON * length(o); // :41
+        bool ok = closest_hit(s, o, d, tmin, q[i].t_max, tmin, 0x7fffffff, h);
         int32_t gi = -1, prim = -1;
-        float u = 0.0f, v = 0.0f;
+        float u = -1.0f, v = -1.0f; // :55-57
         if (ok) { gi = s.tris[h.tri].geom_inst; prim = s.tris[h.tri].prim; u = h.u; v = h.v; }
         results[4 * i + 0] = u;
         results[4 * i + 1] = v;
@@ -1077,19 +1111,21 @@ int oracle_trace_closest_bruteforce(const oracle_scene *os, const rptr_render_ra
     const Scene &s = os->s;
 #pragma omp parallel for schedule(dynamic, 64)
     for (int i = 0; i < n; ++i) {
+        if (q[i].mode_or_data < 0) continue;
         V3 o = v3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), d = v3(q[i].dir[0], q[i].dir[1], q[i].dir[2]);
+        const float tmin = RPTR_RAY_EPSILON * length(o);
         int best = -1;
         float bt = q[i].t_max, bu = 0.0f, bv = 0.0f;
         for (int id = 0; id < (int)s.tris.size(); ++id) {
             float t, u, v;
             if (!intersect_tri(s.tris[id], o, d, t, u, v)) continue;
-            if (!(t > 0.0f && t < q[i].t_max)) continue;
+            if (!(t > tmin && t < q[i].t_max)) continue;
             if (best < 0 || t < bt) { best = id; bt = t; bu = u; bv = v; }
         }
         int32_t gi = -1, prim = -1;
         if (best >= 0) { gi = s.tris[best].geom_inst; prim = s.tris[best].prim; }
-        results[4 * i + 0] = best >= 0 ? bu : 0.0f;
-        results[4 * i + 1] = best >= 0 ? bv : 0.0f;
+        results[4 * i + 0] = best >= 0 ? bu : -1.0f;
+        results[4 * i + 1] = best >= 0 ? bv : -1.0f;
         std::memcpy(&results[4 * i + 2], &gi, 4);
         std::memcpy(&results[4 * i + 3], &prim, 4);
         if (extra_t) extra_t[i] = best >= 0 ? bt : -1.0f;

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "rptr_cuda_begin_frame", "rptr_cuda_draw_frame", "rptr_cuda_end_frame", "rptr_cuda_stats", "rptr_cuda_flush",
     "rptr_cuda_get_counters", "rptr_cuda_reset_counters", "rptr_cuda_frame_state", "rptr_cuda_framebuffer_size",
     "rptr_cuda_readback_f32", "rptr_cuda_readback_u8", "rptr_cuda_framebuffer_device_ptr", "rptr_cuda_stream_handle",
-    "rptr_cuda_trace_rays", "rptr_cuda_set_pointset_table",
+    "rptr_cuda_trace_rays", "rptr_cuda_set_pointset_table", "rptr_cuda_readback_aov",
     "rptr_write_pfm",
 ]
 
@@ -85,6 +85,8 @@ def load_library(path=None):
     L.rptr_cuda_readback_f32.restype = C.c_size_t
     L.rptr_cuda_readback_u8.argtypes = [vp, C.c_size_t, vp]
     L.rptr_cuda_readback_u8.restype = C.c_size_t
+    L.rptr_cuda_readback_aov.argtypes = [vp, i32, C.c_size_t, vp]
+    L.rptr_cuda_readback_aov.restype = C.c_size_t
     L.rptr_cuda_framebuffer_device_ptr.argtypes = [vp, C.POINTER(vp)]
     L.rptr_cuda_stream_handle.argtypes = [vp, C.POINTER(vp)]
     L.rptr_cuda_trace_rays.argtypes = [vp, vp, i32, vp, vp]
@@ -263,6 +265,17 @@ class RenderCuda:
         if self.readback_framebuffer(out) != out.size:
             raise RptrError("readback failed: " + self._L.rptr_cuda_last_error(self._h).decode())
         return out
+
+    def readback_aov(self, aov_index, buffer):
+        """RenderGraphic::readback_aov: half-float RGBA into a uint16 / float16 array; returns the element count (0 = unavailable)."""
+        return self._L.rptr_cuda_readback_aov(self._h, int(aov_index), buffer.size, buffer.ctypes.data)
+
+    def aov(self, aov_index):
+        w, h, c = self.get_framebuffer_size()
+        a = np.zeros((h, w, c), np.float16)
+        if self.readback_aov(aov_index, a) != a.size:
+            raise RptrError("AOV %d is not available" % aov_index)
+        return a
 
     def framebuffer_device_ptr(self):
         p = C.c_void_p()

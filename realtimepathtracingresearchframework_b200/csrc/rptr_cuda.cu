@@ -8,6 +8,7 @@
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (RPTR-FP contract, see rptr_math.cuh).
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #include <chrono>
 #include <cstdarg>
@@ -52,6 +53,25 @@ struct TileMap {
 __host__ __device__ inline int32_t local_row_to_global(const TileMap &t, int32_t lr) {
     int32_t band = lr / t.rows;
     return (band * t.world + t.rank) * t.rows + lr % t.rows;
+}
+
+// The fp16 AOV images of the reference (aov_albedo_roughness_buffer, aov_normal_depth_buffer: vulkan/accumulate.glsl:19-23).
+// Every sample layer of a frame imageStore()s to them, last writer wins; with the sequential reading of a batch
+// (batch_spp = k == k frames of 1) that is the LAST layer of the frame, whose slots are [slot_lo, slot_lo + local_pixels).
+struct AovTarget {
+    ushort4 *albedo_roughness; // null: AOV images off
+    ushort4 *normal_depth;
+    uint32_t slot_lo;
+};
+__device__ __forceinline__ ushort4 to_half4(float x, float y, float z, float w) { // rgba16f store: round to nearest even
+    return make_ushort4(__half_as_ushort(__float2half_rn(x)), __half_as_ushort(__float2half_rn(y)), __half_as_ushort(__float2half_rn(z)),
+                        __half_as_ushort(__float2half_rn(w)));
+}
+__device__ __forceinline__ void store_aov(const AovTarget &t, const TileMap &tm, uint32_t slot, const AovSample &a) {
+    const uint32_t lp = slot - t.slot_lo;
+    const size_t px = (size_t)local_row_to_global(tm, (int32_t)(lp / (uint32_t)tm.width)) * tm.width + lp % (uint32_t)tm.width;
+    t.albedo_roughness[px] = to_half4(a.albedo.x, a.albedo.y, a.albedo.z, a.roughness);
+    t.normal_depth[px] = to_half4(a.normal.x, a.normal.y, a.normal.z, a.depth);
 }
 
 struct DevCounters {
@@ -107,7 +127,10 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
         const uint32_t slot = queue ? queue[i] : i;
         const float4 o = w.ray_o[slot], d = w.ray_d[slot];
         HitRec h;
-        trace_ray<false>(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h, cnt);
+        uint2 rb = w.rngb[slot];
+        const uint32_t before = rb.x;
+        closest_hit_filtered(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, rb.x, h, cnt);
+        if (rb.x != before) w.rngb[slot] = rb;
         w.hit[slot] = f4(h.t, h.u, h.v, __int_as_float(h.tri));
         rays++;
     }
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
 template <int FEAT>
 __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
                                                               const uint32_t *count, uint32_t *next_queue, uint32_t *next_count,
-                                                              uint32_t *shadow_count, DevCounters *dc) {
+                                                              uint32_t *shadow_count, DevCounters *dc, AovTarget aov, TileMap tm) {
     __shared__ uint32_t s_hist[RPTR_SHADE_KEYS], s_base[RPTR_SHADE_KEYS];
     __shared__ uint32_t s_sorted[RPTR_SHADE_TILE];
     const uint32_t n = *count;
@@ -199,7 +222,11 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                     ps.rng_b = ((FEAT & RPTR_FEAT_QMC) && fp.rng_variant != 0) ? w.rng2[slot] : 0u;
                     ps.rng_dim = 0;
                     verts++;
-                    ShadeResult r = shade_hit<FEAT>(fp, sc, ps, hit.x, hit.y, hit.z, &bvh.tris[tri], sh);
+                    // first vertex of a path of the frame's last sample layer: its attributes go to the AOV images
+                    const bool want_aov = aov.albedo_roughness && ps.bounce == 0 && slot - aov.slot_lo < (uint32_t)tm.local_pixels;
+                    AovSample as;
+                    ShadeResult r = shade_hit<FEAT>(fp, sc, ps, hit.x, hit.y, hit.z, &bvh.tris[tri], sh, want_aov ? &as : nullptr);
+                    if (want_aov) store_aov(aov, tm, slot, as);
                     cont = r == SHADE_CONTINUE;
                     shadow = sh.tmax > 0.0f;
                     w.illum[slot] = f4(ps.illum.x, ps.illum.y, ps.illum.z, ps.total_t);
@@ -227,18 +254,20 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
 }
 
 // any-hit visibility for the NEE samples of bounce d (vulkan/pt_megakernel.glsl:216-272); unoccluded -> illum += contrib
-__global__ void __launch_bounds__(128) k_shadow(BvhDev bvh, Wave w, const uint32_t *count, DevCounters *dc) {
+__global__ void __launch_bounds__(128) k_shadow(BvhDev bvh, Wave w, const uint32_t *count, DevCounters *dc, AlphaFilter af, TileMap tm) {
     const uint32_t n = *count;
     TraceCounters cnt{0, 0};
     unsigned long long rays = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o = w.sh_o[i], d = w.sh_d[i];
         HitRec h;
-        const bool occluded = trace_ray<true>(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h, cnt);
+        const float4 c = w.sh_c[i];
+        const uint32_t slot = __float_as_uint(c.w);
+        const uint32_t lp = slot % (uint32_t)tm.local_pixels;
+        af.pixel_linear = (uint32_t)local_row_to_global(tm, (int32_t)(lp / (uint32_t)tm.width)) * (uint32_t)tm.width + lp % (uint32_t)tm.width;
+        const bool occluded = trace_ray<true>(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h, cnt, o.w, 0x7fffffff, &af);
         rays++;
         if (!occluded) {
-            const float4 c = w.sh_c[i];
-            const uint32_t slot = __float_as_uint(c.w);
             float4 il = w.illum[slot];
             il.x = il.x + c.x; il.y = il.y + c.y; il.z = il.z + c.z;
             w.illum[slot] = il;
@@ -254,7 +283,7 @@ __global__ void __launch_bounds__(128) k_shadow(BvhDev bvh, Wave w, const uint32
 // Paths that ended with a miss (hit record still says "no triangle") get their sky / sun-disc term here, from the ray
 // direction, throughput and previous-bounce pdf they died with (shade_miss).
 __global__ void __launch_bounds__(256) k_resolve(rptr_scene_params sp, TileMap tm, Wave w, float4 *accum, uint32_t first_sample, int32_t n_layers,
-                                                 DevCounters *dc) {
+                                                 DevCounters *dc, AovTarget aov, float3 cam_pos) {
     unsigned long long samples = 0;
     for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < (uint32_t)tm.local_pixels; lp += gridDim.x * blockDim.x) {
         const int32_t px = (int32_t)(lp % (uint32_t)tm.width);
@@ -266,6 +295,10 @@ __global__ void __launch_bounds__(256) k_resolve(rptr_scene_params sp, TileMap t
             float4 il = w.illum[slot];
             const float alpha = w.rngb[slot].y == 0u ? 0.0f : 1.0f;
             if (__float_as_int(w.hit[slot].w) < 0) {
+                if (aov.albedo_roughness && alpha == 0.0f && slot - aov.slot_lo < (uint32_t)tm.local_pixels) { // primary ray left the scene
+                    const float c[3] = {cam_pos.x, cam_pos.y, cam_pos.z};
+                    store_aov(aov, tm, slot, aov_of_miss(c));
+                }
                 const float4 d = w.ray_d[slot], thr = w.thr[slot];
                 const float3 r = shade_miss(sp, f3(il.x, il.y, il.z), f3(thr.x, thr.y, thr.z), f3(d.x, d.y, d.z), thr.w);
                 il.x = r.x; il.y = r.y; il.z = r.z;
@@ -286,15 +319,19 @@ __global__ void __launch_bounds__(256) k_resolve(rptr_scene_params sp, TileMap t
     flush_counter(&dc->samples, samples);
 }
 
-// RQ_CLOSEST (vulkan/rt_intersect.comp:28-68)
+// RQ_CLOSEST (vulkan/rt_intersect.comp:30-68): opaque closest hit (gl_RayFlagsOpaqueEXT: no alpha test) over
+// (RAY_EPSILON * |origin|, t_max); mode < 0 leaves the result slot untouched; a miss stores (-1, -1, bits(-1), bits(-1)).
 __global__ void __launch_bounds__(128) k_ray_queries(BvhDev bvh, const rptr_render_ray_query *q, int32_t n, float4 *results, float *hit_t) {
     TraceCounters cnt{0, 0};
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (q[i].mode_or_data < 0) continue;
+        const float3 o = f3(q[i].origin[0], q[i].origin[1], q[i].origin[2]);
+        const float tmin = RPTR_RAY_EPSILON * length(o);
         HitRec h;
-        const bool ok = trace_ray<false>(bvh, f3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), f3(q[i].dir[0], q[i].dir[1], q[i].dir[2]), 0.0f, q[i].t_max, h, cnt);
+        const bool ok = trace_ray<false>(bvh, o, f3(q[i].dir[0], q[i].dir[1], q[i].dir[2]), tmin, q[i].t_max, h, cnt);
         int32_t gi = -1, prim = -1;
         if (ok) { gi = tri_geom_inst(bvh.tris[h.tri]); prim = bvh.tris[h.tri].prim; }
-        results[i] = f4(ok ? h.u : 0.0f, ok ? h.v : 0.0f, __int_as_float(gi), __int_as_float(prim));
+        results[i] = f4(ok ? h.u : -1.0f, ok ? h.v : -1.0f, __int_as_float(gi), __int_as_float(prim));
         if (hit_t) hit_t[i] = ok ? h.t : -1.0f;
     }
 }
@@ -328,6 +365,8 @@ struct rptr_ctx {
     int32_t width = 0, height = 0;
     float4 *accum = nullptr;
     uchar4 *ldr = nullptr;
+    ushort4 *aov_images[2] = {nullptr, nullptr}; // RGBA16F: albedo + roughness, normal + depth (RenderGraphic::AOVBufferIndex 0, 1)
+    int aov_buffers = 1;                         // option "aov_buffers": the reference always writes them (ENABLE_AOV_BUFFERS)
     // counters protocol (vulkan/render_vulkan.h:166-168)
     uint32_t frame_id = 0, frame_offset = 0, accumulated_spp = 0;
     bool freeze_frame = false;
@@ -337,6 +376,7 @@ struct rptr_ctx {
     SceneDev scene{};
     BvhDev bvh{};
     int32_t n_lights = 0;
+    bool any_alpha_tested = false; // some triangle needs the stochastic alpha candidate filter (Alpha variants of the trace kernels)
     std::vector<rptr_tri_light_data> lights_host;
     rptr_scene_params scene_params{};
     bool has_scene_params = false;
@@ -527,8 +567,10 @@ int rptr_cuda_create(int device_ordinal, rptr_ctx **out) {
     }
     cudaMemset(ctx->dcounters, 0, sizeof(DevCounters));
     const int top_bytes = (int)RPTR_TRACE_SMEM_BYTES;
-    if (cudaFuncSetAttribute(k_trace_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_trace_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_trace_persistent<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_trace_persistent<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_trace_persistent<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_trace_persistent<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, top_bytes) != cudaSuccess) {
         fail(nullptr, "cannot reserve %d bytes of shared memory for the trace kernel: %s", top_bytes, cudaGetErrorString(cudaGetLastError()));
         rptr_cuda_destroy(ctx);
         return 1;
@@ -548,6 +590,8 @@ void rptr_cuda_destroy(rptr_ctx *ctx) {
     for (uint32_t *t : ctx->pointset_tables) cudaFree(t);
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
+    cudaFree(ctx->aov_images[0]);
+    cudaFree(ctx->aov_images[1]);
     cudaFree(ctx->dcounters);
     cudaEventDestroy(ctx->ev_begin);
     cudaEventDestroy(ctx->ev_end);
@@ -564,14 +608,21 @@ int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height) {
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
+    cudaFree(ctx->aov_images[0]);
+    cudaFree(ctx->aov_images[1]);
     ctx->accum = nullptr;
     ctx->ldr = nullptr;
+    ctx->aov_images[0] = ctx->aov_images[1] = nullptr;
     ctx->width = width;
     ctx->height = height;
     const size_t n = (size_t)width * height;
     CU(cudaMalloc((void **)&ctx->accum, n * sizeof(float4)));
     CU(cudaMalloc((void **)&ctx->ldr, n * sizeof(uchar4)));
     CU(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc((void **)&ctx->aov_images[i], n * sizeof(ushort4)));
+        CU(cudaMemsetAsync(ctx->aov_images[i], 0, n * sizeof(ushort4), ctx->stream));
+    }
     ctx->frame_id = 0; // vulkan/render_vulkan.cpp:245-249
     ctx->frame_offset = 0;
     ctx->accumulated_spp = 0;
@@ -651,6 +702,7 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
         ctx->bvh = BvhDev{db.nodes, db.tris, db.n_nodes, db.n_tris, db.top, db.top_k};
         ctx->n_lights = (int32_t)hs.lights.size();
         ctx->lights_host = hs.lights;
+        ctx->any_alpha_tested = hs.any_alpha_tested;
         ctx->has_scene = true;
         ctx->frame_id = 0;
         return 0;
@@ -672,6 +724,7 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     ctx->bvh = BvhDev{d_nodes, d_tris, (int32_t)hs.nodes.size(), (int32_t)hs.leaf_tris.size(), d_top, top_k};
     ctx->n_lights = (int32_t)hs.lights.size();
     ctx->lights_host = hs.lights;
+    ctx->any_alpha_tested = hs.any_alpha_tested;
     ctx->has_scene = true;
     ctx->frame_id = 0; // vulkan/render_vulkan.cpp:1556
     return 0;
@@ -705,6 +758,7 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
         if (value < 1024) return fail(ctx, "wave_paths must be >= 1024");
         ctx->wave_paths = value;
     } else if (n == "stage_timing") ctx->stage_timing = value != 0;
+    else if (n == "aov_buffers") ctx->aov_buffers = value != 0;
     else if (n == "trace_kernel") ctx->trace_kernel = (int)value;
     else if (n == "bvh_builder") {
         if (value != 0 && value != 1) return fail(ctx, "bvh_builder must be 0 (host SAH) or 1 (device LBVH)");
@@ -798,6 +852,9 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         const bool ok = v == 0 || (v == 1 && ctx->pointset_tables[2] && ctx->pointset_tables[3]) || (v == 2 && ctx->pointset_tables[0]) ||
                         (v == 3 && ctx->pointset_tables[0] && ctx->pointset_tables[1]);
         if (!ok) return fail(ctx, "rng_variant %d needs its tables: call rptr_cuda_set_pointset_table first", v);
+        // with a QMC pointset the megakernel keeps a SEPARATE per-path LCG for stochastic alpha (pt_megakernel.glsl:354-358);
+        // the wavefront does not store that second state yet
+        if (v != 0 && ctx->any_alpha_tested) return fail(ctx, "rng_variant %d with alpha-tested (textured alpha) materials is not supported by this backend yet", v);
     }
     CU(cudaSetDevice(ctx->device));
     const TileMap tm = make_tilemap(ctx);
@@ -810,12 +867,17 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         if (layers_per_wave > fp.batch) layers_per_wave = fp.batch;
         if (ensure_wave(ctx, (size_t)layers_per_wave * tm.local_pixels, depth)) return 1;
         Wave &w = ctx->wave;
+        // per-candidate seeds of alpha-tested shadow rays: view_params.frame_id / frame_offset of this frame (pt_megakernel.glsl:252-254)
+        const AlphaFilter alpha_filter{ctx->scene.ginst, fp.first_sample, fp.frame_offset, 0u};
         // trace: one RPTR_TRACE_THREADS CTA per SM; dynamic smem = the staged top of the BVH + the shared stack part
         const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4), g_pt = grid_for(ctx, 1);
         const size_t top_smem = RPTR_TRACE_SMEM_BYTES; // staged BVH top (128 KB) + shared part of the traversal stacks (64 KB)
         for (int32_t first = 0; first < fp.batch; first += (int32_t)layers_per_wave) {
             const int32_t nl = (int32_t)((fp.batch - first) < layers_per_wave ? (fp.batch - first) : layers_per_wave);
             CU(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), ctx->stream));
+            // AOV images: written by the first vertex of the frame's last sample layer (last wave, last layer)
+            AovTarget aov{nullptr, nullptr, 0u};
+            if (ctx->aov_buffers && first + nl == fp.batch) aov = AovTarget{ctx->aov_images[0], ctx->aov_images[1], (uint32_t)(nl - 1) * (uint32_t)tm.local_pixels};
             {
                 StageTimer t(ctx, 3);
                 k_raygen<<<g_light, 256, 0, ctx->stream>>>(fp, tm, w, first, nl);
@@ -829,8 +891,9 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                 {
                     StageTimer t(ctx, 0);
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, nullptr, nullptr};
-                        k_trace_persistent<false><<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
+                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, nullptr, nullptr, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                        auto kernel = ctx->any_alpha_tested ? k_trace_persistent<false, true> : k_trace_persistent<false, false>;
+                        kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
                             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
                     } else
                         k_trace<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, q, cn, ctx->dcounters);
@@ -841,7 +904,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     // smallest compiled variant that covers the features this frame uses (rptr_shading.cuh, RPTR_FEAT_*)
                     const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
                                      (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0);
-#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, q, cn, nq, cn + 4, cn + 1, ctx->dcounters
+#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, q, cn, nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, 0u}), tm
                     if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else k_shade<RPTR_FEAT_ALL><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
@@ -851,17 +914,19 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                 if (fp.output_channel == 0 && d + 1 < depth) {
                     StageTimer t(ctx, 2);
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, w.sh_c, w.illum};
-                        k_trace_persistent<true><<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
+                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, w.sh_c, w.illum, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                        auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
+                        kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
                             ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
                     } else
-                        k_shadow<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, cn + 1, ctx->dcounters);
+                        k_shadow<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, cn + 1, ctx->dcounters, alpha_filter, tm);
                     ctx->launches++;
                 }
             }
             {
                 StageTimer t(ctx, 3);
-                k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp.sp, tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters);
+                k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp.sp, tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters, aov,
+                                                            make_float3(fp.cam_pos[0], fp.cam_pos[1], fp.cam_pos[2]));
                 ctx->launches++;
             }
         }
@@ -988,6 +1053,17 @@ size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst) {
     return size;
 }
 
+size_t rptr_cuda_readback_aov(rptr_ctx *ctx, int32_t aov_index, size_t n_elems, uint16_t *dst) {
+    if (!ctx || !dst || !ctx->accum) return 0;
+    if (aov_index < 0 || aov_index > 1 || !ctx->aov_buffers) return 0; // AOVMotionJitterIndex: not produced by this backend
+    const size_t n = (size_t)ctx->width * ctx->height * 4;
+    if (n_elems < n) return 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+    if (cudaMemcpyAsync(dst, ctx->aov_images[aov_index], n * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
+    return n;
+}
+
 int rptr_cuda_framebuffer_device_ptr(rptr_ctx *ctx, void **ptr) {
     if (!ctx || !ptr) return 1;
     if (!ctx->accum) return fail(ctx, "framebuffer_device_ptr before initialize");
@@ -1015,7 +1091,10 @@ int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, in
     CU(cudaMalloc((void **)&dr, sizeof(float4) * (size_t)n));
     CU(cudaMalloc((void **)&dt, sizeof(float) * (size_t)n));
     CU(cudaMemcpyAsync(dq, queries, sizeof(rptr_render_ray_query) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    k_ray_queries<<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->bvh, dq, n, dr, dt);
+    // slots of skipped queries (mode < 0) keep what the caller's buffers hold (rt_intersect.comp:44-45)
+    CU(cudaMemcpyAsync(dr, results, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (hit_t) CU(cudaMemcpyAsync(dt, hit_t, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    k_ray_queries<<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->bvh, dq, n, dr, hit_t ? dt : nullptr);
     ctx->launches++;
     CU(cudaMemcpyAsync(results, dr, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     if (hit_t) CU(cudaMemcpyAsync(hit_t, dt, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -693,6 +693,20 @@ struct ShadowRay {
     float3 contrib; // throughput * L * w * |cos| * f, added to illum iff unoccluded
 };
 enum ShadeResult { SHADE_TERMINATE = 0, SHADE_CONTINUE = 1 };
+// First-vertex attributes the megakernel stores into its fp16 AOV images (vulkan/accumulate.glsl:89-103;
+// pt_megakernel.glsl:482-486, 670-672; shade_base_material.glsl:28-31), as floats before the fp16 store
+struct AovSample {
+    float3 albedo;  // path_throughput * base_color (emitters: 0)
+    float roughness; // ior != 1 ? roughness : 1
+    float3 normal;  // interaction.n
+    float depth;    // |p - cam_pos|
+};
+RPTR_HD AovSample aov_of_miss(const float *cam_pos) { // store_geometry_aovs(0, vec3(2e32), 0) + store_material_aovs(0, 1, 1)
+    AovSample a;
+    a.albedo = f3(0.0f); a.roughness = 1.0f; a.normal = f3(0.0f);
+    a.depth = length(f3(2.e32f) - f3(cam_pos[0], cam_pos[1], cam_pos[2]));
+    return a;
+}
 
 // FEAT: code paths compiled in (the reference compiles its shader variants from #defines the same way, e.g.
 // GLTF_SUPPORT_TRANSMISSION, RBO_rng_variant); a kernel built without a feature must only be launched when the frame
@@ -749,7 +763,7 @@ RPTR_HD float3 shade_miss(const rptr_scene_params &sp, float3 illum, float3 thr,
 
 template <int FEAT = RPTR_FEAT_ALL>
 RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathState &ps, float hit_t, float hit_u, float hit_v, const Tri *tri,
-                             ShadowRay &sh) {
+                             ShadowRay &sh, AovSample *aov = nullptr) {
     sh.tmax = -1.0f;
     const rptr_scene_params &sp = fp.sp;
     const bool tr = (FEAT & RPTR_FEAT_TRANSMISSION) && fp.transmission != 0;
@@ -788,6 +802,12 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
     GltfMat mat;
     float3 emit;
     unpack_material(mat, emit, mp, tr);
+    if (aov && ps.bounce == 0) {
+        aov->normal = in_;
+        aov->depth = length(ip - ld3(fp.cam_pos));
+        aov->albedo = ps.thr * mat.base_color;
+        aov->roughness = mat.ior != 1.0f ? mat.roughness : 1.0f;
+    }
     const float p_sun = sp.sun_radiance[3];
     if (output_channel == 0 && !is_zero(emit)) {
         float light_pdf = (1.0f - p_sun) * (1.0f / ((float)fp.n_bins * approx_sa));
@@ -884,13 +904,14 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
 
 // One path vertex (hit or miss) -- the megakernel-order statement used by the host-side simulation and the unit tests.
 RPTR_HD ShadeResult shade_vertex(const FrameParams &fp, const SceneDev &sc, PathState &ps, float hit_t, float hit_u, float hit_v,
-                                const Tri *tri, ShadowRay &sh) {
+                                const Tri *tri, ShadowRay &sh, AovSample *aov = nullptr) {
     sh.tmax = -1.0f;
     if (!tri) {
+        if (aov && ps.bounce == 0) *aov = aov_of_miss(fp.cam_pos);
         ps.illum = shade_miss(fp.sp, ps.illum, ps.thr, ps.d, ps.prev_pdf);
         return SHADE_TERMINATE;
     }
-    return shade_hit(fp, sc, ps, hit_t, hit_u, hit_v, tri, sh);
+    return shade_hit(fp, sc, ps, hit_t, hit_u, hit_v, tri, sh, aov);
 }
 
 } // namespace rp

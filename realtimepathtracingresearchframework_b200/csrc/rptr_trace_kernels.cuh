@@ -39,6 +39,10 @@ struct TraceIO {
     float4 *hit;           // closest: (t,u,v,bits(tri)) per path slot
     const float4 *sh_c;    // shadow: (contribution.rgb, bits(path slot))
     float4 *illum;         // shadow: illum.rgb += contribution when unoccluded
+    // stochastic alpha (kernels instantiated with Alpha = true only; scenes without alpha-tested triangles never pay for it)
+    uint2 *rngb;           // closest: per path slot (LCG state, bounce) -- the candidate filter draws from the path's LCG
+    AlphaFilter alpha;     // shadow: per-candidate LCG seeds (pixel_linear is filled in per ray)
+    int32_t tm_width, tm_local_pixels, tm_rank, tm_world, tm_rows; // shadow: path slot -> global pixel (TileMap of rptr_cuda.cu)
 };
 
 
@@ -147,7 +151,11 @@ __device__ __forceinline__ float slab_k(const NodeSlab &n, uint32_t qnx, uint32_
     }
 #define RPTR_POP() (sp > 0 ? (--sp, sp < RPTR_SMEM_STACK ? lds32(sst + (uint32_t)sp * RPTR_STACK_STRIDE) : lstack[sp - RPTR_SMEM_STACK]) : RPTR_EMPTY)
 
-template <bool Any>
+// Alpha = true adds the candidate filter of non-opaque triangles (rptr_bvh.cuh, AlphaFilter).  Closest hit: a lane whose
+// traversal ended on an alpha-tested triangle draws from its path's LCG when it would retire; if the candidate is rejected
+// the lane restarts its traversal for the closest hit AFTER (t, id) of that candidate instead of retiring (front-to-back
+// order of DESIGN.md section 5 without a second wavefront pass).  Any hit: a candidate occludes iff its own seeded draw says so.
+template <bool Any, bool Alpha>
 __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhDev bvh, TraceIO io, unsigned long long *c_rays,
                                                                             unsigned long long *c_nodes, unsigned long long *c_tris) {
     extern __shared__ __align__(128) unsigned char smem_top[]; // four word planes of the top_k first nodes, then the stacks
@@ -187,6 +195,8 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     float tmin = 0.0f, tmax = 0.0f;
     float best_t = 0.0f, best_u = 0.0f, best_v = 0.0f;
     int32_t best_tri = -1, best_id = 0x7fffffff;
+    int32_t after_id = 0x7fffffff; // Alpha closest: candidates must come after (tmin, after_id) in (t, id) order; tmin doubles as after_t
+    uint32_t pixel_linear = 0;     // Alpha any-hit: global pixel of the path the shadow ray belongs to
     int32_t node = RPTR_EMPTY; // current item: inner node (>= 0), leaf reference (< 0) or RPTR_EMPTY
     int32_t leaf = 0;          // parked leaf reference (< 0) or 0 = none
     int32_t lstack[RPTR_STACK_SIZE - RPTR_SMEM_STACK]; // overflow part of the traversal stack (local memory)
@@ -206,7 +216,24 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     for (;;) {
         __syncwarp();
         // ---- retire + refill --------------------------------------------------------------------------------------
-        const bool done = have && node == RPTR_EMPTY && leaf == 0;
+        bool done = have && node == RPTR_EMPTY && leaf == 0;
+        if (Alpha && !Any && done && best_tri >= 0 && after_id != RPTR_EMPTY) {
+            const int32_t a8 = tri_alpha8(bvh.tris[best_tri]);
+            if (a8 != RPTR_TRI_OPAQUE) {
+                uint2 rb = io.rngb[slot];
+                const uint32_t before = rb.x;
+                const bool rejected = alpha_rejects(alpha8_to_float(a8), rb.x);
+                if (rb.x != before) io.rngb[slot] = rb;
+                if (rejected) { // look for the closest hit after this candidate
+                    tmin = best_t; after_id = best_id;
+                    best_t = tmax; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
+                    sp = 0;
+                    node = 0;
+                    done = false;
+                }
+            }
+            if (done) after_id = RPTR_EMPTY; // verdict reached: no second draw while the lane waits for the next refill
+        }
         const unsigned idle = __ballot_sync(FULL, !have || done);
         const unsigned inner0 = __ballot_sync(FULL, have && node >= 0);
         const unsigned parked0 = __ballot_sync(FULL, have && leaf != 0);
@@ -246,6 +273,12 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 inv = f3(1.0f / slab_safe(d.x), 1.0f / slab_safe(d.y), 1.0f / slab_safe(d.z));
                 ood = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
                 best_t = tmax; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
+                if (Alpha && !Any) after_id = 0x7fffffff;
+                if (Alpha && Any) { // global pixel of the path: slot -> local pixel -> row band of this rank
+                    const uint32_t lp = __float_as_uint(io.sh_c[ray_index].w) % (uint32_t)io.tm_local_pixels;
+                    const int32_t lr = (int32_t)(lp / (uint32_t)io.tm_width), band = lr / io.tm_rows;
+                    pixel_linear = (uint32_t)((band * io.tm_world + io.tm_rank) * io.tm_rows + lr % io.tm_rows) * (uint32_t)io.tm_width + lp % (uint32_t)io.tm_width;
+                }
                 sp = 0;
                 leaf = 0;
                 node = bvh.n_nodes > 0 ? 0 : RPTR_EMPTY;
@@ -339,11 +372,20 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             bool occluded = false;
             n_tris++;
             float t, u, v;
-            if (intersect_tri(f3(ta.x, ta.y, ta.z), f3(ta.w, tb.x, tb.y), f3(tb.z, tb.w, tc.x), o, d, t, u, v) && t > tmin && t < tmax) {
+            if (intersect_tri(f3(ta.x, ta.y, ta.z), f3(ta.w, tb.x, tb.y), f3(tb.z, tb.w, tc.x), o, d, t, u, v) && t < tmax &&
+                ((Alpha && !Any) ? (t > tmin || (t == tmin && f2i(tc.y) > after_id)) : t > tmin)) {
                 const int32_t id = f2i(tc.y);
                 if (Any) {
-                    best_tri = lf_first;
-                    occluded = true;
+                    bool passes = true;
+                    if (Alpha) {
+                        AlphaFilter af = io.alpha;
+                        af.pixel_linear = pixel_linear;
+                        passes = shadow_candidate_passes(af, f2i(tc.z), f2i(tc.w));
+                    }
+                    if (passes) {
+                        best_tri = lf_first;
+                        occluded = true;
+                    }
                 } else if (best_tri < 0 || t < best_t || (t == best_t && id < best_id)) {
                     best_t = t; best_u = u; best_v = v; best_tri = lf_first; best_id = id;
                 }
@@ -371,9 +413,14 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 n_tris++;
                 float t, u, v;
                 if (!intersect_tri(f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c4.x), o, d, t, u, v)) continue;
-                if (!(t > tmin && t < tmax)) continue;
+                if (!(t < tmax && ((Alpha && !Any) ? (t > tmin || (t == tmin && f2i(c4.y) > after_id)) : t > tmin))) continue;
                 const int32_t id = f2i(c4.y);
                 if (Any) {
+                    if (Alpha) {
+                        AlphaFilter af = io.alpha;
+                        af.pixel_linear = pixel_linear;
+                        if (!shadow_candidate_passes(af, f2i(c4.z), f2i(c4.w))) continue;
+                    }
                     best_tri = lf_first + i;
                     occluded = true;
                     break;

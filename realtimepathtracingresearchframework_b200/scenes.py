@@ -81,7 +81,14 @@ class Scene:
         self.instances = []    # (pmesh_id, 3x4 row-major transform)
         self.materials = []    # T.BaseMaterial
         self.binned_lights = None
+        self.textures = []     # (texels uint8[h, w, channels], T.COLOR_SPACE_*); only 1 x 1 is accepted by the backend yet
         self._keep = []
+
+    def add_texture(self, texel, color_space=T.COLOR_SPACE_LINEAR):
+        """1 x 1 texture from one texel (1-4 channels, 8 bit); returns the texture id for T.texture_handle()."""
+        px = np.asarray(texel, np.uint8).reshape(1, 1, -1)
+        self.textures.append((px, color_space))
+        return len(self.textures) - 1
 
     def add_mesh(self, geometries):
         first = len(self.geometries)
@@ -259,6 +266,29 @@ def random_triangles(n_tris=1_000_000, n_geometries=16, seed=0x5EED1A7B200, box=
     return s
 
 
+def alpha_tested_soup(n_tris=6000, seed=99):
+    """Random triangles whose materials exercise the 1x1-texel mode and the stochastic alpha candidate
+    filter (8a-4): cut-out (alpha 0), half transparent (alpha 128/255), faint (alpha 32/255), an opaque sRGB texel, a
+    material that reads roughness / metallic from texture channels, alpha-textured but flagged NOALPHA, and constants."""
+    s = random_triangles(n_tris, n_geometries=8, seed=seed, box=5.0, edge=0.9)
+    t_half = s.add_texture((200, 120, 60, 128), T.COLOR_SPACE_SRGB)
+    t_cut = s.add_texture((255, 255, 255, 0), T.COLOR_SPACE_SRGB)
+    t_faint = s.add_texture((40, 180, 220, 32), T.COLOR_SPACE_SRGB)
+    t_srgb = s.add_texture((188, 64, 230), T.COLOR_SPACE_SRGB)           # 3 channels: alpha reads 1
+    t_orm = s.add_texture((255, 90, 200, 255), T.COLOR_SPACE_LINEAR)     # (specular, roughness, metallic) like the glTF ORM slot
+    m = s.materials
+    m[0].base_color, m[0].flags = (T.texture_handle(t_half), 0.0, 0.0), 0
+    m[1].base_color, m[1].flags = (T.texture_handle(t_cut), 0.0, 0.0), 0
+    m[2].base_color, m[2].flags = (T.texture_handle(t_faint), 0.0, 0.0), 0
+    m[3].base_color, m[3].flags = (T.texture_handle(t_srgb), 0.0, 0.0), 0
+    m[4].roughness, m[4].metallic, m[4].flags = T.texture_handle(t_orm, 1), T.texture_handle(t_orm, 2), 0
+    m[5].base_color = (T.texture_handle(t_half), 0.0, 0.0)               # NOALPHA stays set: colour from the texel, never alpha-tested
+    m[6].flags = 0                                                        # constants without NOALPHA: alpha 1, no draw
+    s.camera = look_at_camera((0, 0, 16), (0, 0, 0), fovy=55.0)
+    s.name = "alpha_soup%d" % n_tris
+    return s
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # C4: one base mesh instanced many times; GGX + transmission (thick / thin) + emissive per-triangle materials
 # ---------------------------------------------------------------------------------------------------------------------
@@ -310,8 +340,10 @@ def instanced_scene(n_base_tris=100_000, n_instances=100, seed=0xC4C4C4, edge=No
         fl = na | T.BASE_MATERIAL_EXTENDED | (T.BASE_MATERIAL_ONESIDED if j < 2 else 0)
         mats.append(T.BaseMaterial(base_color=_PALETTE[8 + j], roughness=0.05 + 0.1 * j, ior=1.33 + 0.1 * j, specular_transmission=1.0,
                                    clearcoat_gloss=0.02 + 0.05 * j, flags=fl))
-    for j in range(2):  # stand-ins for the alpha-tested materials (alpha textures arrive with row f2): opaque, not flagged NOALPHA
-        mats.append(T.BaseMaterial(base_color=_PALETTE[12 + j], roughness=0.6, ior=1.5, flags=0))
+    for j in range(2):  # alpha-tested: 1 x 1 sRGB base-colour texture with alpha 128/255 -> stochastic candidates (SURVEY 8d, C4 input)
+        rgb8 = [int(round(255.0 * c ** (1.0 / 2.2))) for c in _PALETTE[12 + j]]
+        tex = s.add_texture(rgb8 + [128], T.COLOR_SPACE_SRGB)
+        mats.append(T.BaseMaterial(base_color=(T.texture_handle(tex), 0.0, 0.0), roughness=0.6, ior=1.5, flags=0))
     for j in range(2):  # emissive
         mats.append(T.BaseMaterial(base_color=(1.0, 0.8 - 0.3 * j, 0.5 + 0.4 * j), emission_intensity=20.0, flags=na))
     s.materials = mats

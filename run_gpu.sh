@@ -1,3 +1,1 @@
-N=$(nvidia-smi -L | wc -l); echo "gpus: $N"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; python -c "
-import json; j=json.load(open('gpurun_out/bench_${N}gpu.json')); print(j['n_gpus'], j['value'], j['e2e']['value'], j['ms_per_step'])"; tail -2 gpurun_out/bench_${N}gpu.err
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/t.log 2>&1; tail -5 gpurun_out/t.log

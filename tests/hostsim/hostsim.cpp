@@ -78,8 +78,9 @@ static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
     return fp;
 }
 
-// un-averaged sample layer `sample_index` for the region; rgba is W*H*4
-int hostsim_render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba) {
+// un-averaged sample layer `sample_index` for the region; rgba is W*H*4; aov (optional) = W*H*8 floats per pixel:
+// albedo.rgb, roughness, normal.xyz, depth of the first path vertex (the values behind the fp16 AOV images)
+static int render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba, float *aov_out) {
     FrameParams fp = make_frame(s, a);
     SceneDev sc{s->gi.data(), s->hs.materials.data(), s->hs.lights.data()};
     BvhDev bvh{s->hs.nodes.data(), s->hs.leaf_tris.data(), (int32_t)s->hs.nodes.size(), (int32_t)s->hs.leaf_tris.size()};
@@ -89,12 +90,14 @@ int hostsim_render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_
             PathState ps;
             generate_primary(fp, x, y, sample_index, ps);
             TraceCounters cnt{0, 0};
+            AovSample as;
+            memset(&as, 0, sizeof(as));
             for (;;) {
                 HitRec h;
                 // stochastic alpha draws come from the path's LCG (the LCG pointset; the QMC pointsets keep a separate one)
                 bool found = closest_hit_filtered(bvh, ps.o, ps.d, ps.tmin, ps.tmax, ps.rng, h, cnt);
                 ShadowRay sh;
-                ShadeResult r = shade_vertex(fp, sc, ps, h.t, h.u, h.v, found ? &bvh.tris[h.tri] : nullptr, sh);
+                ShadeResult r = shade_vertex(fp, sc, ps, h.t, h.u, h.v, found ? &bvh.tris[h.tri] : nullptr, sh, aov_out ? &as : nullptr);
                 if (sh.tmax > 0.0f) {
                     HitRec o;
                     const AlphaFilter af{sc.ginst, fp.first_sample, fp.frame_offset, (uint32_t)x + (uint32_t)y * (uint32_t)fp.width};
@@ -104,8 +107,18 @@ int hostsim_render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_
             }
             float *px = rgba + 4 * ((size_t)y * a->width + x);
             px[0] = ps.illum.x; px[1] = ps.illum.y; px[2] = ps.illum.z; px[3] = ps.bounce == 0 ? 0.0f : 1.0f;
+            if (aov_out) {
+                const float m[8] = {as.albedo.x, as.albedo.y, as.albedo.z, as.roughness, as.normal.x, as.normal.y, as.normal.z, as.depth};
+                memcpy(aov_out + 8 * ((size_t)y * a->width + x), m, sizeof(m));
+            }
         }
     return 0;
+}
+int hostsim_render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba) {
+    return render_sample(s, a, sample_index, rgba, nullptr);
+}
+int hostsim_render_sample_aov(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba, float *aov) {
+    return render_sample(s, a, sample_index, rgba, aov);
 }
 
 // sampler calls replayed through the product's rptr_pointsets.cuh (same protocol as oracle_pointset_replay)
@@ -137,12 +150,14 @@ extern "C" int hostsim_trace(const hostsim_scene *s, const rptr_render_ray_query
     for (int32_t i = 0; i < n; ++i) {
         HitRec h;
         TraceCounters cnt{0, 0};
+        if (q[i].mode_or_data < 0) continue;
         float3 o = f3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), d = f3(q[i].dir[0], q[i].dir[1], q[i].dir[2]);
-        bool ok = any ? trace_ray<true>(bvh, o, d, 0.0f, q[i].t_max, h, cnt) : trace_ray<false>(bvh, o, d, 0.0f, q[i].t_max, h, cnt);
+        const float tmin = RPTR_RAY_EPSILON * length(o);
+        bool ok = any ? trace_ray<true>(bvh, o, d, tmin, q[i].t_max, h, cnt) : trace_ray<false>(bvh, o, d, tmin, q[i].t_max, h, cnt);
         int32_t gi = -1, prim = -1;
         if (ok) { gi = tri_geom_inst(bvh.tris[h.tri]); prim = bvh.tris[h.tri].prim; }
-        results[4 * i + 0] = ok ? h.u : 0.0f;
-        results[4 * i + 1] = ok ? h.v : 0.0f;
+        results[4 * i + 0] = ok ? h.u : -1.0f;
+        results[4 * i + 1] = ok ? h.v : -1.0f;
         memcpy(&results[4 * i + 2], &gi, 4);
         memcpy(&results[4 * i + 3], &prim, 4);
         if (hit_t) hit_t[i] = ok ? h.t : -1.0f;

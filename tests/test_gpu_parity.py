@@ -191,10 +191,16 @@ def test_ray_query_service_matches_oracle_and_bruteforce(oracle):
     r = make_backend(s, 64, 64)
     o = oracle.OracleScene(s)
     q = random_queries(20000, 5, box=2.5)
+    q.view(np.int32)[::7, 3] = -1  # mode_or_data < 0: the query is skipped, its result slot keeps the caller's data (rt_intersect.comp:44-45)
     res, t = r.trace_ray(q)
     ores, ot = o.trace_closest(q)
     bres, bt = o.trace_closest(q, bruteforce=True)
     assert (t >= 0).mean() > 0.05
+    live = np.ones(len(q), bool)
+    live[::7] = False
+    assert (res[~live] == 0).all() and (t[~live] == 0).all()
+    miss = live & (t < 0)
+    assert miss.any() and (res[miss, :2] == -1.0).all() and (res[miss, 2:].view(np.int32) == -1).all()  # :55-57
     assert np.array_equal(ores.view(np.uint32), bres.view(np.uint32)) and np.array_equal(ot, bt)
     assert np.array_equal(res.view(np.uint32), ores.view(np.uint32))
     assert np.array_equal(t, ot)
@@ -400,7 +406,9 @@ def test_c4_full_size_properties():
     parts = []
     for rank in range(2):
         t = make_backend(s, W, H, sky, transmission=1, bvh_builder=1, tile_world=2, tile_rank=rank)
-        t.render_spp(s.camera, 2, batch_spp=1)
+        # same batch structure as the single-GPU frame: the alpha test of shadow rays is seeded with view_params.frame_id
+        # (pt_megakernel.glsl:252-254), which is the batch's, not the sample's
+        t.render_spp(s.camera, 2, batch_spp=2)
         parts.append(t.framebuffer())
     assert np.array_equal((parts[0] + parts[1]).view(np.uint32), img.view(np.uint32))
 
@@ -442,3 +450,67 @@ def test_low_discrepancy_samplers(oracle, variant):
     assert b.frame_state()[1] == 4  # reset_accumulation rolled frame_offset += frame_id (vulkan/render_vulkan.cpp:1937-1941)
     refu, _ = o.render(W, H, s.camera, sp, spp=2, frame_offset=4)
     assert_identical(b.framebuffer(), refu, "back to UNIFORM")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_alpha_tested_materials_and_1x1_textures(oracle):
+    """1x1-texel mode + stochastic alpha (generate_candidate_hit, pt_megakernel.glsl:153-272): the Alpha
+    variants of the persistent trace kernels (restart-after-rejection closest hit, per-candidate seeded any-hit) against the
+    oracle's front-to-back loop; progressive frames, a batch in several waves, and the one-ray-per-thread A/B kernels."""
+    s = scenes.alpha_tested_soup(20000)
+    W, H = 320, 180
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    sp = load_sky_fit(T.SceneConfig(**sky))
+    o = oracle.OracleScene(s)
+    r = make_backend(s, W, H, sky)
+    r.render_spp(s.camera, 3, batch_spp=1)
+    ref, _ = o.render(W, H, s.camera, sp, spp=3)
+    assert_identical(r.framebuffer(), ref, "alpha soup, 3 frames")
+    opaque = scenes.alpha_tested_soup(20000)
+    for m in opaque.materials:
+        m.flags |= T.BASE_MATERIAL_NOALPHA
+    ropq, _ = oracle.OracleScene(opaque).render(W, H, s.camera, sp, spp=3)
+    assert ref[..., 3].sum() < ropq[..., 3].sum(), "cut-outs must let primary rays through"
+    b = make_backend(s, W, H, sky, wave_paths=3 * W * H)
+    b.render_spp(s.camera, 4, batch_spp=4)  # shadow-ray seeds use the frame's frame_id for every layer of the batch
+    refb, _ = o.render(W, H, s.camera, sp, spp=4, batch_spp=4)
+    assert_identical(b.framebuffer(), refb, "alpha soup, batch of 4")
+    c = make_backend(s, W, H, sky, trace_kernel=1)
+    c.render_spp(s.camera, 3, batch_spp=1)
+    assert_identical(c.framebuffer(), ref, "alpha soup, one-ray-per-thread kernels")
+    # Sobol / blue-noise pointsets keep a separate alpha LCG per path: not stored by the wavefront yet -> loud error, not a wrong image
+    r.set_rng_variant(T.RNG_VARIANT_SOBOL)
+    with pytest.raises(RptrError):
+        r.render_spp(s.camera, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_aov_images_readback(oracle):
+    """readback_aov (a-16): RGBA16F albedo+roughness / normal+depth of the first vertex of the frame's LAST sample layer,
+    bit-identical to the oracle's float values rounded to half (numpy's IEEE round-to-nearest-even conversion)."""
+    s = scenes.alpha_tested_soup(20000)
+    W, H = 320, 180
+    sp = load_sky_fit()
+    o = oracle.OracleScene(s)
+    r = make_backend(s, W, H, wave_paths=2 * W * H)
+    r.render_spp(s.camera, 5, batch_spp=5)  # waves of 2 + 2 + 1 layers: the images hold sample 4
+    ar, nd = o.render_aov(W, H, s.camera, sp, 4, first_sample=0)
+    with np.errstate(over="ignore"):
+        want_ar, want_nd = ar.astype(np.float16), nd.astype(np.float16)
+    assert np.array_equal(r.aov(0).view(np.uint16), want_ar.view(np.uint16))
+    assert np.array_equal(r.aov(1).view(np.uint16), want_nd.view(np.uint16))
+    assert np.isinf(want_nd[..., 3]).any() and np.isfinite(want_nd[..., 3]).any()
+    # next frame overwrites them with its own last layer (sample 5 of the accumulation)
+    r.render_spp(s.camera, 1, batch_spp=1, reset=False)
+    ar2, nd2 = o.render_aov(W, H, s.camera, sp, 5, first_sample=5)
+    with np.errstate(over="ignore"):
+        assert np.array_equal(r.aov(1).view(np.uint16), nd2.astype(np.float16).view(np.uint16))
+        assert np.array_equal(r.aov(0).view(np.uint16), ar2.astype(np.float16).view(np.uint16))
+    # motion / jitter AOV is not produced; too-small buffers and the option switch return 0 like the reference's readback
+    assert r.readback_aov(2, np.zeros((H, W, 4), np.float16)) == 0
+    assert r.readback_aov(0, np.zeros(16, np.float16)) == 0
+    r.set_option("aov_buffers", 0)
+    assert r.readback_aov(0, np.zeros((H, W, 4), np.float16)) == 0
+    # the images do not disturb the beauty pass
+    ref, _ = o.render(W, H, s.camera, sp, spp=6, batch_spp=5)  # frames of 5 + 1 samples: view_params.frame_id = 0 x5, then 5
+    assert_identical(r.framebuffer(), ref, "beauty with AOV images on")

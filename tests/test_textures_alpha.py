@@ -1,0 +1,90 @@
+"""1x1-texel mode + stochastic alpha candidate filter (8a-4, generate_candidate_hit,
+vulkan/pt_megakernel.glsl:153-272): the product's host material resolution + traversal code (compiled for the CPU by
+tests/hostsim) against the oracle, which looks textures up at shading time like the reference does."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from realtimepathtracingresearchframework_b200 import load_sky_fit, scenes, types as T
+
+
+@pytest.fixture(scope="module")
+def H(hostsim, oracle):
+    lib = C.CDLL(hostsim)
+    lib.hostsim_scene_create.restype = C.c_void_p
+    lib.hostsim_scene_create.argtypes = [C.POINTER(T.SceneDesc), C.POINTER(T.LightSamplingConfig)]
+    lib.hostsim_scene_destroy.argtypes = [C.c_void_p]
+    lib.hostsim_render_sample.argtypes = [C.c_void_p, C.POINTER(oracle.OracleRenderArgs), C.c_uint32, oracle.f32p]
+    return lib
+
+
+def render_both(H, oracle, s, W, Hh, sample, sky=None, **kw):
+    sp = load_sky_fit(T.SceneConfig(**(sky or {})))
+    o = oracle.OracleScene(s)
+    ls = T.LightSamplingConfig()
+    d = s.desc()
+    hs = H.hostsim_scene_create(C.byref(d), C.byref(ls))
+    assert hs
+    try:
+        ref = o.render_sample(W, Hh, s.camera, sp, sample, **kw)
+        a = o._args(W, Hh, s.camera, sp, first_sample=sample, **kw)
+        img = np.zeros((Hh, W, 4), np.float32)
+        H.hostsim_render_sample(hs, C.byref(a), sample, oracle._fp(img))
+    finally:
+        H.hostsim_scene_destroy(hs)
+    return ref, img
+
+
+def test_texture_handle_encoding():
+    import struct
+    h = T.texture_handle(5, 2)
+    bits = struct.unpack("<I", struct.pack("<f", h))[0]
+    assert bits == 0x80000000 | (2 << 29) | 5  # rendering/bsdfs/texture_channel_mask.h:20-27
+    assert h < 0 or bits >> 31 == 1
+
+
+@pytest.mark.parametrize("sample,frame_offset", [(0, 0), (3, 7)])
+def test_alpha_tested_scene_matches_oracle_bit_for_bit(H, oracle, sample, frame_offset):
+    s = scenes.alpha_tested_soup()
+    ref, img = render_both(H, oracle, s, 200, 120, sample, sky=dict(sun_dir=(0.35, 0.8, 0.45)), frame_offset=frame_offset)
+    assert np.isfinite(ref).all() and ref[..., :3].max() > 0
+    assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), "%d pixels differ" % (ref != img).any(-1).sum()
+
+
+def test_alpha_changes_the_image_the_expected_way(H, oracle):
+    """cut-out triangles vanish, half-transparent ones let about half of the primary rays through"""
+    s = scenes.alpha_tested_soup()
+    opaque = scenes.alpha_tested_soup()
+    for m in opaque.materials:
+        m.flags |= T.BASE_MATERIAL_NOALPHA
+    W, Hh = 200, 120
+    a, _ = render_both(H, oracle, s, W, Hh, 0)
+    b, _ = render_both(H, oracle, opaque, W, Hh, 0)
+    assert not np.array_equal(a, b)
+    # alpha channel of the sample = "the path hit something" (pt_megakernel.glsl:736): fewer hits with cut-outs
+    assert a[..., 3].sum() < b[..., 3].sum()
+
+
+def test_textures_larger_than_one_texel_are_rejected(H, oracle):
+    s = scenes.alpha_tested_soup(500)
+    s.textures[0] = (np.zeros((2, 2, 4), np.uint8), T.COLOR_SPACE_SRGB)
+    ls = T.LightSamplingConfig()
+    d = s.desc()
+    assert not H.hostsim_scene_create(C.byref(d), C.byref(ls))  # build_host_scene throws: "only 1 x 1 textures are supported"
+
+
+def test_srgb_and_unorm_decoding_of_resolved_materials(H, oracle):
+    """AOV channel 1 (base colour * throughput at the first hit) shows the resolved texel colours exactly."""
+    s = scenes.alpha_tested_soup(3000)
+    p = T.RenderParams()
+    p.output_channel = 1
+    ref, img = render_both(H, oracle, s, 160, 90, 0, params=p)
+    assert np.array_equal(ref.view(np.uint32), img.view(np.uint32))
+
+    def srgb(v):
+        c = v / 255.0
+        return np.float32(c / 12.92 if c <= 0.04045 else ((c + 0.055) / 1.055) ** 2.4)
+    want = np.array([srgb(188), srgb(64), srgb(230)], np.float32)  # material 3: opaque sRGB texel, alpha 1
+    px = ref[..., :3].reshape(-1, 3)
+    assert (np.abs(px - want).max(axis=1) == 0).any(), "no pixel shows the decoded sRGB texel"
