@@ -101,7 +101,19 @@ void RenderCuda::set_scene(const Scene &scene) {
             for (int c = 0; c < 4; ++c) id.transform[4 * r + c] = m[c][r]; // 3x4 row-major, as handed to the TLAS (:1262-1268)
         instances.push_back(id);
     }
+    // Scene::textures (util/image.h:10-27).  The backend resolves 1 x 1 textures today and rejects larger ones with a
+    // readable error; block-compressed images would have to be decompressed first (Image::decompress).
+    std::vector<rptr_texture_desc> textures;
+    for (const Image &img : scene.textures) {
+        if (img.bcFormat != 0) throw_error("cuda backend: block-compressed texture '%s' is not supported yet", img.name.c_str());
+        rptr_texture_desc td{};
+        td.width = img.width; td.height = img.height; td.channels = img.channels;
+        td.color_space = img.color_space == SRGB ? RPTR_COLOR_SPACE_SRGB : RPTR_COLOR_SPACE_LINEAR;
+        td.texels = img.img.data();
+        textures.push_back(td);
+    }
     rptr_scene_desc d{};
+    d.textures = textures.data(); d.n_textures = (int32_t)textures.size();
     d.geometries = geoms.data(); d.n_geometries = (int32_t)geoms.size();
     d.meshes = meshes.data(); d.n_meshes = (int32_t)meshes.size();
     d.pmeshes = pmeshes.data(); d.n_pmeshes = (int32_t)pmeshes.size();
@@ -206,6 +218,9 @@ void RenderCuda::flush_pipeline() { check(rptr_cuda_flush(ctx)); }
 glm::uvec3 RenderCuda::get_framebuffer_size() const { return glm::uvec3(fb_width, fb_height, 4); }
 size_t RenderCuda::readback_framebuffer(size_t bufferSize, unsigned char *buffer, bool) { return rptr_cuda_readback_u8(ctx, bufferSize, buffer); }
 size_t RenderCuda::readback_framebuffer(size_t bufferSize, float *buffer, bool) { return rptr_cuda_readback_f32(ctx, bufferSize, buffer); }
+size_t RenderCuda::readback_aov(AOVBufferIndex aovIndex, size_t bufferSize, uint16_t *buffer, bool) {
+    return rptr_cuda_readback_aov(ctx, (int32_t)aovIndex, bufferSize, buffer);
+}
 
 int RenderCuda::trace_ray(const RenderRayQuery *queries, int num_queries, glm::vec4 *results) {
     check(rptr_cuda_trace_rays(ctx, (const rptr_render_ray_query *)queries, num_queries, (float *)results, nullptr));

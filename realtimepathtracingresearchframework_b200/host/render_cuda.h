@@ -37,6 +37,7 @@ struct RenderCuda : RenderBackend {
     glm::uvec3 get_framebuffer_size() const override;
     size_t readback_framebuffer(size_t bufferSize, unsigned char *buffer, bool force_refresh = false) override;
     size_t readback_framebuffer(size_t bufferSize, float *buffer, bool force_refresh = false) override;
+    size_t readback_aov(AOVBufferIndex aovIndex, size_t bufferSize, uint16_t *buffer, bool force_refresh = false) override;
 
     // RaytraceBackend::trace_ray with the RenderRayQuery wire format (librender/render_params.glsl.h:165-170,
     // vulkan/rt_intersect.comp:53-67); the rt_datacapture types of librender/raytrace_backend.h are not in the release
