@@ -97,7 +97,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def measured_traffic(args):
+def measured_traffic(args, overlap):
     """DRAM bytes per closest-hit launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the launches of a
     frame) from the committed ncu capture of this same command, or None when the workload is not the captured one."""
     p = os.path.join(ROOT, "profiles", "r01_trace_traffic.json")
@@ -108,7 +108,13 @@ def measured_traffic(args):
     w = t["workload"]
     same = (args.scene == w["scene"] and args.tris == w["tris"] and args.spp == w["spp"] and args.width == w["width"] and
             args.height == w["height"] and not args.wave_paths and not args.option and args.gpus == 1)
-    return (t["closest"]["avg_dram_bytes_per_launch"], "profiles/r01_trace_traffic.json") if same else (None, None)
+    if not same:
+        return None, None
+    if overlap:  # per launch over the closest-hit AND shadow launches, like `achieved`
+        n = t["closest"]["launches"] + t["shadow"]["launches"]
+        tot = t["closest"]["avg_dram_bytes_per_launch"] * t["closest"]["launches"] + t["shadow"]["avg_dram_bytes_per_launch"] * t["shadow"]["launches"]
+        return tot / n, "profiles/r01_trace_traffic.json (closest + shadow launches)"
+    return t["closest"]["avg_dram_bytes_per_launch"], "profiles/r01_trace_traffic.json"
 
 
 def make_scene(args):
@@ -298,17 +304,28 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (closest-hit trace): algorithmic bytes / event-timed duration ----
     peak, peak_src = peaks()
     node_b, tri_b = cnt["node_bytes"], cnt["tri_bytes"]
-    trace_bytes = cnt["closest_rays"] * (32 + 32) + cnt["closest_nodes"] * node_b + cnt["closest_tris"] * tri_b
+    closest_bytes = cnt["closest_rays"] * (32 + 32) + cnt["closest_nodes"] * node_b + cnt["closest_tris"] * tri_b
+    shadow_bytes = cnt["shadow_rays"] * (32 + 4) + cnt["shadow_nodes"] * node_b + cnt["shadow_tris"] * tri_b
+    # With option overlap_shadow (default) every shadow launch shares the GPU with the next closest-hit launch, so the two
+    # instantiations of the trace kernel are timed together (ms_trace = union of their intervals) and the roofline is
+    # stated for both: algorithmic bytes of closest-hit + shadow rays over that time.
+    overlap = bool(cnt.get("trace_overlap", 0))
+    trace_bytes = closest_bytes + (shadow_bytes if overlap else 0)
+    trace_rays = cnt["closest_rays"] + (cnt["shadow_rays"] if overlap else 0)
     ach = trace_bytes / (cnt["ms_trace"] * 1e-3) / 1e9 if cnt["ms_trace"] > 0 else None
     stage_ms = {k: cnt[k] for k in ("ms_trace", "ms_shade", "ms_shadow", "ms_other")}
     spl = max(1, cnt["samples"])
-    traffic, traffic_src = measured_traffic(args)
-    roofline = {"bound": "hbm", "kernel": "k_trace (closest hit)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+    traffic, traffic_src = measured_traffic(args, overlap)
+    kernel_name = "k_trace_persistent (closest-hit + any-hit launches, overlapped on two streams)" if overlap else "k_trace_persistent (closest hit)"
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "per_launch": {"launches": cnt["trace_launches"], "avg_ms": cnt["ms_trace"] / max(1, cnt["trace_launches"]),
                                "avg_algorithmic_bytes": trace_bytes / max(1, cnt["trace_launches"])},
-                "per_ray": {"nodes": cnt["closest_nodes"] / max(1, cnt["closest_rays"]), "tris": cnt["closest_tris"] / max(1, cnt["closest_rays"]),
-                            "bytes": trace_bytes / max(1, cnt["closest_rays"]), "node_bytes": node_b, "tri_bytes": tri_b},
+                "per_ray": {"closest": {"nodes": cnt["closest_nodes"] / max(1, cnt["closest_rays"]), "tris": cnt["closest_tris"] / max(1, cnt["closest_rays"]),
+                                        "bytes": closest_bytes / max(1, cnt["closest_rays"])},
+                            "shadow": {"nodes": cnt["shadow_nodes"] / max(1, cnt["shadow_rays"]), "tris": cnt["shadow_tris"] / max(1, cnt["shadow_rays"]),
+                                       "bytes": shadow_bytes / max(1, cnt["shadow_rays"])},
+                            "bytes": trace_bytes / max(1, trace_rays), "node_bytes": node_b, "tri_bytes": tri_b},
                 "per_sample": {"closest_rays": cnt["closest_rays"] / spl, "shadow_rays": cnt["shadow_rays"] / spl, "vertices": cnt["shaded_vertices"] / spl},
                 "stage_ms_rank0": stage_ms, "mrays_per_s": (cnt["closest_rays"] + cnt["shadow_rays"]) / (dev_ms * 1e-3) / 1e6 * world}
     line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -41,6 +41,8 @@ typedef struct rptr_counters {
     uint64_t tri_bytes;        /* size of one traversal triangle record fetched per triangle test */
     uint64_t bvh_nodes;        /* number of (4-wide) BVH nodes of the current scene */
     double bvh_build_ms;       /* wall time of the last BVH build (host SAH or device LBVH) */
+    uint64_t trace_overlap;    /* 1: option "overlap_shadow" is on -- ms_trace / trace_launches then cover closest-hit AND shadow
+                                  launches (each shadow launch shares the GPU with the next closest-hit launch) and ms_shadow is 0 */
 } rptr_counters;
 
 /* create_cuda_backend(Display&) / ~RenderBackend  (librender/render_backend.h:118-119, main.cpp:273-285).
@@ -74,6 +76,8 @@ int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *params);
  *                   3 Z_SBL; 1-3 need their tables (rptr_cuda_set_pointset_table) before the next draw_frame
  *   "wave_paths"    max paths in flight per wavefront pass (memory/occupancy knob)
  *   "aov_buffers"   0/1  write the fp16 AOV images (default 1: ENABLE_AOV_BUFFERS, vulkan/gpu_params.glsl:19)
+ *   "overlap_shadow" 0/1 (default 1) launch the shadow rays of bounce d on a second stream beside the closest-hit rays of bounce
+ *                   d + 1 (independent work; the persistent grids interleave SM by SM, hiding each other's tails)
  *   "stage_timing"  0/1  time each stage with CUDA events into rptr_counters.ms_*
  *   "bvh_builder"   0 = binned-SAH build on the host inside set_scene, 1 = LBVH build on the device (both replace the
  *                   driver's BLAS/TLAS build, vulkan/vulkanrt_utils.cpp:82-167; images are identical either way)

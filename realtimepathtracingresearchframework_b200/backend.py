@@ -34,7 +34,8 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("samples", "closest_rays", "shadow_rays", "shaded_vertices", "closest_nodes",
                                           "closest_tris", "shadow_nodes", "shadow_tris", "launches")] + \
                [(n, C.c_double) for n in ("ms_trace", "ms_shadow", "ms_shade", "ms_other")] + \
-               [(n, C.c_uint64) for n in ("trace_launches", "node_bytes", "tri_bytes", "bvh_nodes")] + [("bvh_build_ms", C.c_double)]
+               [(n, C.c_uint64) for n in ("trace_launches", "node_bytes", "tri_bytes", "bvh_nodes")] + [("bvh_build_ms", C.c_double),
+                                                                                                  ("trace_overlap", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
 template <int FEAT>
 __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
                                                               const uint32_t *count, uint32_t *next_queue, uint32_t *next_count,
-                                                              uint32_t *shadow_count, DevCounters *dc, AovTarget aov, TileMap tm) {
+                                                              uint32_t *shadow_count, DevCounters *dc, AovTarget aov, TileMap tm, int sort_tiles) {
     __shared__ uint32_t s_hist[RPTR_SHADE_KEYS], s_base[RPTR_SHADE_KEYS];
     __shared__ uint32_t s_sorted[RPTR_SHADE_TILE];
     const uint32_t n = *count;
@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t tile_base = tile * RPTR_SHADE_TILE;
         const uint32_t tile_count = min((uint32_t)RPTR_SHADE_TILE, n - tile_base);
+        if (sort_tiles) { // (every material of the scene takes the same code path otherwise: nothing to sort, rptr_cuda_draw_frame)
         if (threadIdx.x < RPTR_SHADE_KEYS) s_hist[threadIdx.x] = 0;
         __syncthreads();
         uint32_t my_slot[RPTR_SHADE_PER_THREAD], my_key[RPTR_SHADE_PER_THREAD], my_pos[RPTR_SHADE_PER_THREAD];
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
         for (int k = 0; k < RPTR_SHADE_PER_THREAD; ++k)
             if (my_key[k] != 0xffffffffu) s_sorted[s_base[my_key[k]] + my_pos[k]] = my_slot[k];
         __syncthreads();
+        }
         for (int k = 0; k < RPTR_SHADE_PER_THREAD; ++k) {
             const uint32_t j = k * RPTR_SHADE_THREADS + threadIdx.x;
             const bool active = j < tile_count;
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
             ShadowRay sh;
             sh.tmax = -1.0f;
             if (active) {
-                slot = s_sorted[j];
+                slot = sort_tiles ? s_sorted[j] : (queue ? queue[tile_base + j] : tile_base + j);
                 const float4 hit = w.hit[slot];
                 const int tri = __float_as_int(hit.w);
                 if (tri >= 0) { // a miss ends the path; its sky term is added by k_resolve from the untouched path state
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                 w.sh_c[si] = f4(sh.contrib.x, sh.contrib.y, sh.contrib.z, __uint_as_float(slot));
             }
         }
-        __syncthreads();
+        if (sort_tiles) __syncthreads();
     }
     flush_counter(&dc->shaded_vertices, verts);
 }
@@ -360,6 +362,9 @@ struct rptr_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr; // option "overlap_shadow": the shadow launch of bounce d runs beside the closest-hit launch of d + 1
+    cudaEvent_t ev_shade = nullptr, ev_shadow = nullptr;
+    int overlap_shadow = 1;
     std::string error;
     // framebuffer
     int32_t width = 0, height = 0;
@@ -376,6 +381,7 @@ struct rptr_ctx {
     SceneDev scene{};
     BvhDev bvh{};
     int32_t n_lights = 0;
+    std::vector<rptr_base_material> materials_host; // resolved materials (texture handles folded in), for per-frame host decisions
     bool any_alpha_tested = false; // some triangle needs the stochastic alpha candidate filter (Alpha variants of the trace kernels)
     std::vector<rptr_tri_light_data> lights_host;
     rptr_scene_params scene_params{};
@@ -409,7 +415,7 @@ struct rptr_ctx {
     float last_render_ms = 0.0f;
     uint64_t launches = 0, trace_launches = 0;
     double ms_trace = 0, ms_shadow = 0, ms_shade = 0, ms_other = 0;
-    struct Timed { cudaEvent_t a, b; int stage; };
+    struct Timed { cudaEvent_t a, b; int stage; int launches; };
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> event_pool;
     size_t bytes_now = 0, bytes_max = 0, bytes_total = 0;
@@ -508,7 +514,7 @@ struct StageTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     int stage;
     StageTimer(rptr_ctx *c, int s) : ctx(c), stage(s) {
-        if (ctx->stage_timing) {
+        if (ctx->stage_timing && s >= 0) {
             a = get_event(ctx);
             b = get_event(ctx);
             cudaEventRecord(a, ctx->stream);
@@ -517,7 +523,7 @@ struct StageTimer {
     ~StageTimer() {
         if (a) {
             cudaEventRecord(b, ctx->stream);
-            ctx->timed.push_back({a, b, stage});
+            ctx->timed.push_back({a, b, stage, 1});
         }
     }
 };
@@ -525,7 +531,7 @@ static void collect_timers(rptr_ctx *ctx) {
     for (auto &t : ctx->timed) {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
-            if (t.stage == 0) { ctx->ms_trace += ms; ctx->trace_launches++; }
+            if (t.stage == 0) { ctx->ms_trace += ms; ctx->trace_launches += (uint64_t)t.launches; }
             else if (t.stage == 1) ctx->ms_shade += ms;
             else if (t.stage == 2) ctx->ms_shadow += ms;
             else ctx->ms_other += ms;
@@ -559,7 +565,10 @@ int rptr_cuda_create(int device_ordinal, rptr_ctx **out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device_ordinal);
     ctx->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev_begin) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_shade, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_shadow, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev_begin) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_end) != cudaSuccess || cudaMalloc((void **)&ctx->dcounters, sizeof(DevCounters)) != cudaSuccess) {
         fail(nullptr, "CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
@@ -596,6 +605,9 @@ void rptr_cuda_destroy(rptr_ctx *ctx) {
     cudaEventDestroy(ctx->ev_begin);
     cudaEventDestroy(ctx->ev_end);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_shade) cudaEventDestroy(ctx->ev_shade);
+    if (ctx->ev_shadow) cudaEventDestroy(ctx->ev_shadow);
     delete ctx;
 }
 
@@ -703,6 +715,7 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
         ctx->n_lights = (int32_t)hs.lights.size();
         ctx->lights_host = hs.lights;
         ctx->any_alpha_tested = hs.any_alpha_tested;
+        ctx->materials_host = hs.materials;
         ctx->has_scene = true;
         ctx->frame_id = 0;
         return 0;
@@ -725,6 +738,7 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     ctx->n_lights = (int32_t)hs.lights.size();
     ctx->lights_host = hs.lights;
     ctx->any_alpha_tested = hs.any_alpha_tested;
+    ctx->materials_host = hs.materials;
     ctx->has_scene = true;
     ctx->frame_id = 0; // vulkan/render_vulkan.cpp:1556
     return 0;
@@ -759,6 +773,7 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
         ctx->wave_paths = value;
     } else if (n == "stage_timing") ctx->stage_timing = value != 0;
     else if (n == "aov_buffers") ctx->aov_buffers = value != 0;
+    else if (n == "overlap_shadow") ctx->overlap_shadow = value != 0;
     else if (n == "trace_kernel") ctx->trace_kernel = (int)value;
     else if (n == "bvh_builder") {
         if (value != 0 && value != 1) return fail(ctx, "bvh_builder must be 0 (host SAH) or 1 (device LBVH)");
@@ -867,6 +882,19 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         if (layers_per_wave > fp.batch) layers_per_wave = fp.batch;
         if (ensure_wave(ctx, (size_t)layers_per_wave * tm.local_pixels, depth)) return 1;
         Wave &w = ctx->wave;
+        // The shade kernel sorts queue tiles by shading code path; when every material of the scene takes the same path (C2:
+        // all GGX, no emitters) the sort pass -- four dependent loads per entry and three block barriers per tile -- is skipped.
+        int sort_tiles = 0;
+        {
+            int first_key = -1;
+            for (const rptr_base_material &m : ctx->materials_host) {
+                int key = m.ior > 1.0f ? 2 : 1;
+                if (fp.transmission && m.ior > 1.0f && m.specular_transmission > 0.0f) key = (m.flags & RPTR_BASE_MATERIAL_ONESIDED) ? 4 : 3;
+                if (m.emission_intensity != 0.0f) key += 5;
+                if (first_key < 0) first_key = key;
+                else if (key != first_key) { sort_tiles = 1; break; }
+            }
+        }
         // per-candidate seeds of alpha-tested shadow rays: view_params.frame_id / frame_offset of this frame (pt_megakernel.glsl:252-254)
         const AlphaFilter alpha_filter{ctx->scene.ginst, fp.first_sample, fp.frame_offset, 0u};
         // trace: one RPTR_TRACE_THREADS CTA per SM; dynamic smem = the staged top of the BVH + the shared stack part
@@ -883,13 +911,30 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                 k_raygen<<<g_light, 256, 0, ctx->stream>>>(fp, tm, w, first, nl);
                 ctx->launches++;
             }
+            bool shadow_pending = false;
+            cudaEvent_t union_a = nullptr; // stage_timing: start of the interval in which shadow(d) and closest(d + 1) share the GPU
+            int union_launches = 0;
+            auto join_shadow = [&]() -> int { // the main stream waits for the overlapped shadow launch; closes the union interval
+                if (!shadow_pending) return 0;
+                CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_shadow, 0));
+                shadow_pending = false;
+                if (union_a) {
+                    cudaEvent_t b = get_event(ctx);
+                    CU(cudaEventRecord(b, ctx->stream));
+                    ctx->timed.push_back({union_a, b, 0, union_launches});
+                    union_a = nullptr;
+                }
+                return 0;
+            };
             for (int d = 0; d < depth; ++d) {
                 // counts[4d] = live paths entering bounce d, [4d+1] = its shadow rays, [4d+2], [4d+3] = fetch cursors
                 const uint32_t *q = d == 0 ? nullptr : w.queue[d & 1];
                 uint32_t *nq = w.queue[(d + 1) & 1];
                 uint32_t *cn = w.counts + 4 * d;
                 {
-                    StageTimer t(ctx, 0);
+                    // inside a union interval the closest-hit launch is timed together with the shadow launch it overlaps
+                    StageTimer t(ctx, union_a ? -1 : 0);
+                    if (union_a) union_launches++;
                     if (ctx->trace_kernel == 0) {
                         TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, nullptr, nullptr, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<false, true> : k_trace_persistent<false, false>;
@@ -899,19 +944,38 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                         k_trace<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, q, cn, ctx->dcounters);
                     ctx->launches++;
                 }
+                if (join_shadow()) return 1; // shade reads illum and rewrites the shadow queue: the overlapped shadow launch must be done
                 {
                     StageTimer t(ctx, 1);
                     // smallest compiled variant that covers the features this frame uses (rptr_shading.cuh, RPTR_FEAT_*)
                     const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
                                      (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0);
-#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, q, cn, nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, 0u}), tm
+#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, q, cn, nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, 0u}), tm, sort_tiles
                     if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else k_shade<RPTR_FEAT_ALL><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
 #undef RPTR_SHADE_ARGS
                     ctx->launches++;
                 }
-                if (fp.output_channel == 0 && d + 1 < depth) {
+                if (fp.output_channel == 0 && d + 1 < depth && ctx->overlap_shadow && ctx->trace_kernel == 0) {
+                    // The shadow rays of bounce d and the closest-hit rays of bounce d + 1 are independent.  Both kernels are
+                    // persistent grids of one CTA per SM, so launched on two streams the second fills the SMs the first one
+                    // vacates: its head hides the first one's tail (the longest rays of the queue).
+                    if (ctx->stage_timing) {
+                        union_a = get_event(ctx);
+                        CU(cudaEventRecord(union_a, ctx->stream));
+                        union_launches = 1;
+                    }
+                    CU(cudaEventRecord(ctx->ev_shade, ctx->stream));
+                    CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_shade, 0));
+                    TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, w.sh_c, w.illum, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                    auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
+                    kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream2>>>(
+                        ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
+                    CU(cudaEventRecord(ctx->ev_shadow, ctx->stream2));
+                    shadow_pending = true;
+                    ctx->launches++;
+                } else if (fp.output_channel == 0 && d + 1 < depth) {
                     StageTimer t(ctx, 2);
                     if (ctx->trace_kernel == 0) {
                         TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, w.sh_c, w.illum, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
@@ -923,6 +987,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     ctx->launches++;
                 }
             }
+            if (join_shadow()) return 1;
             {
                 StageTimer t(ctx, 3);
                 k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp.sp, tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters, aov,
@@ -994,6 +1059,7 @@ int rptr_cuda_get_counters(rptr_ctx *ctx, rptr_counters *out) {
     out->ms_shade = ctx->ms_shade;
     out->ms_other = ctx->ms_other;
     out->trace_launches = ctx->trace_launches;
+    out->trace_overlap = (uint64_t)(ctx->overlap_shadow && ctx->trace_kernel == 0);
     out->node_bytes = sizeof(BvhNode);
     out->tri_bytes = sizeof(Tri);
     out->bvh_nodes = (uint64_t)ctx->bvh.n_nodes;

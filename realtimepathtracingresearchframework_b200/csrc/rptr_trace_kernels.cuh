@@ -57,6 +57,21 @@ __device__ __forceinline__ void ld256(const void *p, float4 &a, float4 &b) {
 
 // ---- TMA bulk copy (cp.async.bulk, SASS: UBLKCP) + mbarrier, raw PTX ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// the same, opaque to ptxas: the value is computed once and kept (S2R SR_CgaCtaId + LEA per use otherwise)
+__device__ __forceinline__ uint32_t smem_u32_pinned(const void *p) {
+    uint32_t r;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float slab_rcp(float x) {
+#if RPTR_FAST_RCP
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -92,6 +107,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #endif
 #ifndef RPTR_LEAF_ONE_PER_TRIP
 #define RPTR_LEAF_ONE_PER_TRIP 1 // leaf step tests one triangle of the parked leaf per trip instead of looping over it
+#endif
+#ifndef RPTR_FAST_RCP
+#define RPTR_FAST_RCP 1 // 1/d of the slab test through MUFU.RCP alone (boxes only prune and are padded far beyond 1 ulp of 1/d)
+#endif
+#ifndef RPTR_PIN_SMEM_BASE
+#define RPTR_PIN_SMEM_BASE 1 // compute the shared-window addresses once (asm volatile) instead of letting ptxas rematerialise them per node step
 #endif
 #ifndef RPTR_CHUNKS_PER_WARP
 #define RPTR_CHUNKS_PER_WARP 4 // target number of queue fetches per warp (tail balance) before the chunk is shortened
@@ -179,7 +200,11 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     }
     if (n > 0 && plane_bytes > 0) mbar_wait(&top_bar, 0);
     const int32_t top_k = bvh.top_k;
+#if RPTR_PIN_SMEM_BASE
+    const uint32_t top_base = smem_u32_pinned(smem_top);
+#else
     const uint32_t top_base = smem_u32(smem_top);
+#endif
     // Rays per queue fetch: RPTR_FETCH_CHUNK for long queues (few atomics, coherent warps); short queues (late bounces)
     // are cut finer so that every warp of the grid gets work instead of a few warps walking 256 rays 32 at a time.
     // Guided self-scheduling: the size is recomputed from what is left of the queue at every fetch.
@@ -200,7 +225,11 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     int32_t node = RPTR_EMPTY; // current item: inner node (>= 0), leaf reference (< 0) or RPTR_EMPTY
     int32_t leaf = 0;          // parked leaf reference (< 0) or 0 = none
     int32_t lstack[RPTR_STACK_SIZE - RPTR_SMEM_STACK]; // overflow part of the traversal stack (local memory)
+#if RPTR_PIN_SMEM_BASE
+    const uint32_t sst = top_base + (uint32_t)(RPTR_TOP_NODES_MAX * sizeof(BvhNode)) + threadIdx.x * (uint32_t)sizeof(int32_t);
+#else
     const uint32_t sst = smem_u32(smem_top + (size_t)RPTR_TOP_NODES_MAX * sizeof(BvhNode)) + threadIdx.x * (uint32_t)sizeof(int32_t);
+#endif
     // high bytes of the decoded box coordinates, kept opaque to ptxas so that it stays in a register and the selectors
     // become immediates (n is never 2^32 - 1)
 #if RPTR_HC_PER_THREAD
@@ -270,7 +299,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 const float4 ro = io.ray_o[Any ? ray_index : slot], rd = io.ray_d[Any ? ray_index : slot];
                 o = f3(ro.x, ro.y, ro.z); tmin = ro.w;
                 d = f3(rd.x, rd.y, rd.z); tmax = rd.w;
-                inv = f3(1.0f / slab_safe(d.x), 1.0f / slab_safe(d.y), 1.0f / slab_safe(d.z));
+                inv = f3(slab_rcp(slab_safe(d.x)), slab_rcp(slab_safe(d.y)), slab_rcp(slab_safe(d.z)));
                 ood = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
                 best_t = tmax; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
                 if (Alpha && !Any) after_id = 0x7fffffff;
