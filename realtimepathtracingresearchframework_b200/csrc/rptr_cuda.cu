@@ -40,6 +40,8 @@ struct Wave {
     float4 *sh_d;   //               dir.xyz, tmax
     float4 *sh_c;   //               contribution.rgb, bits(path slot)
     uint32_t *queue[2];
+    uint32_t *hitq;       // slots of the closest-hit rays of the current bounce that hit something (dense; input of the shade stage)
+    uint32_t *hit_counts; // per bounce
     uint32_t *counts; // per bounce d: [4d] live paths entering it, [4d+1] its shadow rays, [4d+2], [4d+3] fetch cursors
 };
 
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave
 }
 
 // closest hit for the live paths of bounce d
-__global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_t *queue, const uint32_t *count, DevCounters *dc) {
+__global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_t *queue, const uint32_t *count, DevCounters *dc, uint32_t *hit_count) {
     const uint32_t n = *count;
     TraceCounters cnt{0, 0};
     unsigned long long rays = 0;
@@ -132,6 +134,10 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
         closest_hit_filtered(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, rb.x, h, cnt);
         if (rb.x != before) w.rngb[slot] = rb;
         w.hit[slot] = f4(h.t, h.u, h.v, __int_as_float(h.tri));
+        if (hit_count) {
+            const uint32_t hi = warp_append(hit_count, h.tri >= 0);
+            if (h.tri >= 0) w.hitq[hi] = slot;
+        }
         rays++;
     }
     flush_counter(&dc->closest_rays, rays);
@@ -173,14 +179,13 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
             if (j < tile_count) {
                 const uint32_t slot = queue ? queue[tile_base + j] : tile_base + j;
                 const int tri = __float_as_int(w.hit[slot].w);
-                uint32_t key = 0; // miss
-                if (tri >= 0) {
+                uint32_t key = tri >= 0 ? 1u : 0u; // miss / hit
+                if (tri >= 0 && sort_tiles > 1) { // several code paths in the scene: look the material up
                     const Tri *tr = bvh.tris + tri;
                     const GeomInst &g = sc.ginst[tri_geom_inst(*tr)];
                     // key = code path of shade_vertex, not the material itself (keeps neighbouring pixels together):
                     // Lambert / GGX / thin or thick transmission, plus the emitter-MIS variant of each
                     const rptr_base_material &m = sc.materials[calc_hit_material_id(g, (uint32_t)tr->prim)];
-                    key = 1u;
                     if (m.ior > 1.0f) key = 2u;
                     if ((FEAT & RPTR_FEAT_TRANSMISSION) && fp.transmission && m.ior > 1.0f && m.specular_transmission > 0.0f) key = (m.flags & RPTR_BASE_MATERIAL_ONESIDED) ? 4u : 3u;
                     if (m.emission_intensity != 0.0f) key += 5u;
@@ -494,6 +499,8 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     CU(dev_alloc(ctx, &w.queue[0], n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.queue[1], n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.counts, (size_t)4 * (depth + 2), ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.hitq, n, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.hit_counts, (size_t)(depth + 2), ctx->wave_allocs));
     ctx->wave_capacity = paths;
     ctx->wave_depth = depth;
     return 0;
@@ -882,9 +889,12 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         if (layers_per_wave > fp.batch) layers_per_wave = fp.batch;
         if (ensure_wave(ctx, (size_t)layers_per_wave * tm.local_pixels, depth)) return 1;
         Wave &w = ctx->wave;
-        // The shade kernel sorts queue tiles by shading code path; when every material of the scene takes the same path (C2:
-        // all GGX, no emitters) the sort pass -- four dependent loads per entry and three block barriers per tile -- is skipped.
-        int sort_tiles = 0;
+        // Scenes whose materials take several shading code paths (C4: GGX, thick / thin transmission, emitters): the trace kernel
+        // hands the shade stage a dense queue of the paths that hit something, which the shade kernel then sorts tile by tile
+        // by code path (C4 shade: 27.1 -> 18.8 ms per 33 M samples).  Single-path scenes (C2: all GGX) keep the bounce queue
+        // in its screen / compaction order instead -- the tile sort then only moves the misses aside -- because the
+        // retire-order hit queue costs more in scattered path-state reads than the dropped misses save (C2: 1242 -> 1170).
+        int multi_path = 0;
         {
             int first_key = -1;
             for (const rptr_base_material &m : ctx->materials_host) {
@@ -892,9 +902,11 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                 if (fp.transmission && m.ior > 1.0f && m.specular_transmission > 0.0f) key = (m.flags & RPTR_BASE_MATERIAL_ONESIDED) ? 4 : 3;
                 if (m.emission_intensity != 0.0f) key += 5;
                 if (first_key < 0) first_key = key;
-                else if (key != first_key) { sort_tiles = 1; break; }
+                else if (key != first_key) { multi_path = 1; break; }
             }
         }
+        const int sort_tiles = multi_path ? 2 : 1; // 1: the tile sort only moves the misses aside (key = hit / miss, no material lookup)
+        uint32_t *const hitq = multi_path ? w.hitq : nullptr;
         // per-candidate seeds of alpha-tested shadow rays: view_params.frame_id / frame_offset of this frame (pt_megakernel.glsl:252-254)
         const AlphaFilter alpha_filter{ctx->scene.ginst, fp.first_sample, fp.frame_offset, 0u};
         // trace: one RPTR_TRACE_THREADS CTA per SM; dynamic smem = the staged top of the BVH + the shared stack part
@@ -903,6 +915,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         for (int32_t first = 0; first < fp.batch; first += (int32_t)layers_per_wave) {
             const int32_t nl = (int32_t)((fp.batch - first) < layers_per_wave ? (fp.batch - first) : layers_per_wave);
             CU(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), ctx->stream));
+            CU(cudaMemsetAsync(w.hit_counts, 0, sizeof(uint32_t) * (depth + 2), ctx->stream));
             // AOV images: written by the first vertex of the frame's last sample layer (last wave, last layer)
             AovTarget aov{nullptr, nullptr, 0u};
             if (ctx->aov_buffers && first + nl == fp.batch) aov = AovTarget{ctx->aov_images[0], ctx->aov_images[1], (uint32_t)(nl - 1) * (uint32_t)tm.local_pixels};
@@ -936,12 +949,12 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     StageTimer t(ctx, union_a ? -1 : 0);
                     if (union_a) union_launches++;
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, nullptr, nullptr, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, hitq, w.hit_counts + d, nullptr, nullptr, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<false, true> : k_trace_persistent<false, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
                             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
                     } else
-                        k_trace<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, q, cn, ctx->dcounters);
+                        k_trace<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, q, cn, ctx->dcounters, hitq ? w.hit_counts + d : nullptr);
                     ctx->launches++;
                 }
                 if (join_shadow()) return 1; // shade reads illum and rewrites the shadow queue: the overlapped shadow launch must be done
@@ -950,7 +963,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     // smallest compiled variant that covers the features this frame uses (rptr_shading.cuh, RPTR_FEAT_*)
                     const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
                                      (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0);
-#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, q, cn, nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, 0u}), tm, sort_tiles
+#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (hitq ? hitq : q), (hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, 0u}), tm, sort_tiles
                     if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else k_shade<RPTR_FEAT_ALL><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
@@ -968,7 +981,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     }
                     CU(cudaEventRecord(ctx->ev_shade, ctx->stream));
                     CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_shade, 0));
-                    TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, w.sh_c, w.illum, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                    TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
                     auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                     kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream2>>>(
                         ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
@@ -978,7 +991,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                 } else if (fp.output_channel == 0 && d + 1 < depth) {
                     StageTimer t(ctx, 2);
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, w.sh_c, w.illum, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
                             ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);

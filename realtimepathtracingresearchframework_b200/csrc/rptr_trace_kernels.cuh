@@ -37,6 +37,8 @@ struct TraceIO {
     const uint32_t *count; // number of rays (device resident)
     uint32_t *work;        // global fetch cursor (zeroed before launch)
     float4 *hit;           // closest: (t,u,v,bits(tri)) per path slot
+    uint32_t *hitq;        // closest, optional: compacted slots of the rays that hit something (input of the shade stage when set)
+    uint32_t *hit_count;
     const float4 *sh_c;    // shadow: (contribution.rgb, bits(path slot))
     float4 *illum;         // shadow: illum.rgb += contribution when unoccluded
     // stochastic alpha (kernels instantiated with Alpha = true only; scenes without alpha-tested triangles never pay for it)
@@ -278,6 +280,18 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                     }
                 } else {
                     io.hit[slot] = f4(best_t, best_u, best_v, __int_as_float(best_tri));
+                    // paths that left the scene end here (their sky term is added by the resolve kernel); the others
+                    // go to the shade stage through a dense queue: one atomic per warp and retire event
+                    if (io.hitq) { // warp-uniform
+                        const unsigned hits = __ballot_sync(__activemask(), best_tri >= 0);
+                        if (best_tri >= 0) {
+                            const int leader = __ffs(hits) - 1;
+                            uint32_t base = 0;
+                            if (lane == leader) base = atomicAdd(io.hit_count, (uint32_t)__popc(hits));
+                            base = __shfl_sync(hits, base, leader);
+                            io.hitq[base + __popc(hits & ((1u << lane) - 1u))] = slot;
+                        }
+                    }
                 }
                 have = false;
             }
