@@ -220,6 +220,9 @@ def gen_pointsets(n=384, seed=4321):
     mq[:, 3:5] = tiles[rng.integers(0, len(tiles), n)]
     mq[:, 5] = rng.integers(0, 2, n)
     mq[:, 6] = rng.integers(0, 2, n)
+    hal = np.zeros((R.ref_halton_23(None), 2), np.float32)
+    R.ref_halton_23(hal.ctypes.data_as(po.f32p))
+    out["halton_23"] = hal
     R.ref_morton_sample_id.restype = C.c_uint32
     out["morton_in"] = mq
     out["morton_out"] = np.array([R.ref_morton_sample_id(*[int(x) for x in row]) for row in mq], np.uint32)

@@ -60,6 +60,8 @@ def lib():
             getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_int32, f32p, f32p]
         L.oracle_pointset_replay.argtypes = [C.c_int, C.POINTER(C.c_void_p)] + [C.c_uint32] * 6 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                                                                        C.c_int, f32p, C.POINTER(C.c_uint32)]
+        L.oracle_screen_jitter.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, f32p]
+        L.oracle_halton_23.argtypes = [C.c_int32, f32p]
         L.oracle_morton_sample_id.restype = C.c_uint32
         L.oracle_morton_sample_id.argtypes = [C.c_uint32] * 5 + [C.c_int, C.c_int]
         L.oracle_lcg_seed.restype = C.c_uint32
@@ -105,6 +107,7 @@ def ref():
         R.ref_pointset_table.argtypes = [C.c_int, C.POINTER(C.c_uint32)]
         R.ref_pointset_replay.argtypes = [C.c_int] + [C.c_uint32] * 7 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, f32p,
                                                                         C.POINTER(C.c_uint32)]
+        R.ref_halton_23.argtypes = [f32p]
         R.ref_morton_sample_id.restype = C.c_uint32
         R.ref_morton_sample_id.argtypes = [C.c_uint32] * 5 + [C.c_int, C.c_int]
         _ref = R

@@ -9,6 +9,7 @@
 
 #include "rendering/pointsets/sobol_tables.h"
 #include "rendering/pointsets/bn_tables.h"
+#include "librender/halton.h"
 
 #define MAKE_RANDOM_TABLE(TYPE, NAME) static TYPE NAME;
 
@@ -118,6 +119,13 @@ int ref_pointset_replay(int variant, uint32_t sample_index, uint32_t frame_id, u
     } else
         return -1;
     return n_out;
+}
+
+// librender/halton.h:12-81: the table update_view_parameters reads for the raster-TAA screen jitter (render_vulkan.cpp:2917-2926)
+int ref_halton_23(float *out_) {
+    const int n = (int)halton_23_size;
+    if (out_) std::memcpy(out_, halton_23, sizeof(float) * 2 * n);
+    return n;
 }
 
 uint32_t ref_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, uint32_t tw, uint32_t th, int hash_tile_id, int hash_sample_id) {

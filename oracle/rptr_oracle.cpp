@@ -676,6 +676,27 @@ void oracle_view_params(const rptr_camera_params *cam, int32_t w, int32_t h, flo
 
 namespace {
 
+// Raster-TAA screen jitter (vulkan/render_vulkan.cpp:2917-2926): entry (frame_offset + frame_id) % RASTER_TAA_NUM_SAMPLES (16,
+// CMakeLists.txt:30) of the 2-3 Halton table of librender/halton.h, whose entries are 6-decimal literals:
+// halton_23[k] = (phi_2(k + 1), phi_3(k + 1)) rounded to 6 decimals, then to float.
+static float halton_literal(int index, int base) {
+    double f = 1.0, r = 0.0;
+    for (int i = index; i > 0; i /= base) {
+        f /= base;
+        r += f * (i % base);
+    }
+    // the table spells the value the way printf("%.6f") does (exact ties to even: phi_2(64) = 0.0078125 is listed as 0.007812)
+    char buf[32];
+    std::snprintf(buf, sizeof(buf), "%.6f", r);
+    return std::strtof(buf, nullptr);
+}
+static void screen_jitter(uint32_t frame_offset, uint32_t frame_id, int w, int h, float *out) {
+    const uint32_t idx = (frame_offset + frame_id) % 16u;
+    const float hx = halton_literal((int)idx + 1, 2), hy = halton_literal((int)idx + 1, 3);
+    out[0] = hx * 2.0f / (float)w - 1.0f / (float)w;
+    out[1] = hy * 2.0f / (float)h - 1.0f / (float)h;
+}
+
 struct Frame {
     const Scene *s;
     const oracle_render_args *a;
@@ -810,6 +831,12 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
     }
     ptx /= (float)a.width;
     pty /= (float)a.height;
+    if (a.params.enable_raster_taa != 0) { // pt_megakernel.glsl:319-320; screen_jitter belongs to the frame (view_params)
+        float sj[2];
+        screen_jitter(a.frame_offset, view_frame_id, a.width, a.height, sj);
+        ptx += 0.5f * sj[0];
+        pty += 0.5f * sj[1];
+    }
     V3 ray_origin = f.cam_pos;
     V3 ray_dir = normalize(f.du * ptx + f.dv * pty + f.tl);
     float t_min = 0.0f, t_max = 2.e32f;
@@ -1151,6 +1178,8 @@ int oracle_pointset_replay(int variant, const uint32_t *const *tables, uint32_t 
     }
     return n;
 }
+void oracle_screen_jitter(uint32_t frame_offset, uint32_t frame_id, int32_t w, int32_t h, float *out) { screen_jitter(frame_offset, frame_id, w, h, out); }
+void oracle_halton_23(int32_t k, float *out) { out[0] = halton_literal(k + 1, 2); out[1] = halton_literal(k + 1, 3); }
 uint32_t oracle_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, uint32_t tw, uint32_t th, int hash_tile, int hash_sample) {
     return oracle_ps::morton_sample_id(sample_id, px, py, tw, th, hash_tile != 0, hash_sample != 0);
 }

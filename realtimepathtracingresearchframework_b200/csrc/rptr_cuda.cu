@@ -850,6 +850,7 @@ static FrameParams make_frame_params(const rptr_ctx *ctx) {
     fp.output_channel = ctx->params.output_channel;
     fp.glossy_only_mode = ctx->params.glossy_only_mode;
     fp.enable_raster_taa = ctx->params.enable_raster_taa;
+    if (fp.enable_raster_taa > 0) screen_jitter(ctx->frame_offset, ctx->frame_id, ctx->width, ctx->height, fp.screen_jitter);
     fp.n_lights = ctx->n_lights;
     fp.bin_size = ctx->lighting.bin_size;
     fp.n_bins = (ctx->n_lights + fp.bin_size - 1) / fp.bin_size; // vulkan/pt_megakernel.glsl:102-103

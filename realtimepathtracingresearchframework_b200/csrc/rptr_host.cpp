@@ -5,7 +5,10 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <stdexcept>
+#include <string>
+#include <cstdlib>
 
 namespace rp {
 
@@ -169,6 +172,30 @@ void equalize_emitter_bins(std::vector<Emitter> &emitters, std::vector<float> &r
 } // namespace
 
 // ---- scene flattening ---------------------------------------------------------------------------------------------------
+// Raster-TAA screen jitter of update_view_parameters (vulkan/render_vulkan.cpp:2917-2926): halton_23[(frame_offset +
+// frame_id) % RASTER_TAA_NUM_SAMPLES] * 2 / dims - 1 / dims.  The table of librender/halton.h holds the 2-3 Halton points
+// of index k + 1 as 6-decimal literals, which is how they are rebuilt here (RASTER_TAA_NUM_SAMPLES = 16, CMakeLists.txt:30).
+void halton_23(int k, float *out) {
+    const int bases[2] = {2, 3};
+    for (int c = 0; c < 2; ++c) {
+        double r = 0.0, f = 1.0;
+        for (int i = k + 1; i > 0; i /= bases[c]) {
+            f /= bases[c];
+            r += f * (i % bases[c]);
+        }
+        // the literal "0.dddddd" the table spells out (printf rounding: exact ties to even), parsed to the nearest float
+        char lit[32];
+        std::snprintf(lit, sizeof(lit), "%.6f", r);
+        out[c] = std::strtof(lit, nullptr);
+    }
+}
+void screen_jitter(uint32_t frame_offset, uint32_t frame_id, int w, int h, float *out) {
+    float hp[2];
+    halton_23((int)((frame_offset + frame_id) % 16u), hp);
+    out[0] = hp[0] * 2.0f / (float)w - 1.0f / (float)w;
+    out[1] = hp[1] * 2.0f / (float)h - 1.0f / (float)h;
+}
+
 // ---- 1x1-texel mode: material parameters that carry texture handles are resolved on the host -----------------
 // The reference samples textures at the hit's uv (rendering/rt/material_textures.glsl:37-63); a 1 x 1 texture returns its only
 // texel for every uv and every LOD, so the lookup can be done once per material here and the kernels keep reading

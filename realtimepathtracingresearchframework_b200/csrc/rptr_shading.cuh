@@ -61,6 +61,7 @@ struct FrameParams {
     int32_t max_path_depth, rr_path_depth, output_channel, glossy_only_mode, enable_raster_taa;
     int32_t n_lights, n_bins, bin_size;
     int32_t transmission;
+    float screen_jitter[2]; // view_params.screen_jitter (raster TAA; zero unless enable_raster_taa)
     int32_t rng_variant;  // RenderBackendOptions::rng_variant (librender/render_params.glsl.h:34-37)
     PointsetTables pts;   // tables of the Sobol / blue-noise samplers (null unless rng_variant needs them)
     rptr_scene_params sp; // sun_radiance[3] already carries the light-count rule (vulkan/render_sky.cpp:67-70)
@@ -741,6 +742,10 @@ RPTR_HD void generate_primary(const FrameParams &fp, int px, int py, uint32_t sa
     }
     ptx /= (float)fp.width;
     pty /= (float)fp.height;
+    if (fp.enable_raster_taa != 0) { // pt_megakernel.glsl:319-320
+        ptx += 0.5f * fp.screen_jitter[0];
+        pty += 0.5f * fp.screen_jitter[1];
+    }
     ps.o = ld3(fp.cam_pos);
     ps.d = normalize(ld3(fp.du) * ptx + ld3(fp.dv) * pty + ld3(fp.tl));
     ps.tmin = 0.0f;

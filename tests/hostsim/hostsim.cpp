@@ -63,6 +63,7 @@ static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
     fp.output_channel = a->params.output_channel;
     fp.glossy_only_mode = a->params.glossy_only_mode;
     fp.enable_raster_taa = a->params.enable_raster_taa;
+    if (fp.enable_raster_taa > 0) screen_jitter(a->frame_offset, a->first_sample, a->width, a->height, fp.screen_jitter);
     fp.n_lights = (int)s->hs.lights.size();
     fp.bin_size = a->lighting.bin_size;
     fp.n_bins = fp.bin_size > 0 ? (fp.n_lights + fp.bin_size - 1) / fp.bin_size : 0;
@@ -138,6 +139,8 @@ int hostsim_pointset_replay(int variant, const uint32_t *const *tables, uint32_t
     }
     return n;
 }
+void hostsim_halton_23(int32_t k, float *out) { halton_23(k, out); }
+void hostsim_screen_jitter(uint32_t frame_offset, uint32_t frame_id, int32_t w, int32_t h, float *out) { screen_jitter(frame_offset, frame_id, w, h, out); }
 uint32_t hostsim_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, uint32_t tw, uint32_t th, int hash_tile, int hash_sample) {
     return morton_sample_id(sample_id, px, py, tw, th, hash_tile != 0, hash_sample != 0);
 }

@@ -514,3 +514,22 @@ def test_aov_images_readback(oracle):
     # the images do not disturb the beauty pass
     ref, _ = o.render(W, H, s.camera, sp, spp=6, batch_spp=5)  # frames of 5 + 1 samples: view_params.frame_id = 0 x5, then 5
     assert_identical(r.framebuffer(), ref, "beauty with AOV images on")
+
+
+def test_raster_taa_screen_jitter(oracle):
+    """RenderParams.enable_raster_taa: the pixel-filter draws are replaced by the frame's Halton jitter
+    (pt_megakernel.glsl:316-320; render_vulkan.cpp:2917-2926), frame by frame and inside a batch."""
+    s = scenes.random_triangles(5000)
+    W, H = 192, 108
+    p = T.RenderParams(enable_raster_taa=1)
+    r = make_backend(s, W, H)
+    r.params.enable_raster_taa = 1
+    r.render_spp(s.camera, 4, batch_spp=1)
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=4, params=p)
+    assert_identical(r.framebuffer(), ref, "raster TAA, 4 frames")
+    b = make_backend(s, W, H)
+    b.params.enable_raster_taa = 1
+    b.render_spp(s.camera, 4, batch_spp=4)  # one frame: every layer shares the frame's jitter
+    refb, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=4, params=p, batch_spp=4)
+    assert_identical(b.framebuffer(), refb, "raster TAA, batch of 4")
+    assert not np.array_equal(ref, refb)

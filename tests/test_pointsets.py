@@ -153,3 +153,49 @@ def test_product_code_with_each_sampler_matches_oracle_bit_for_bit(H, oracle, ta
         assert abs(ref[..., :3].mean() / uniform[..., :3].mean() - 1.0) < 0.15
     finally:
         H.hostsim_scene_destroy(hs)
+
+
+# ---- raster-TAA screen jitter (render_vulkan.cpp:2917-2926; librender/halton.h) -------------------------------------------
+def test_halton_table_and_screen_jitter(H, oracle, gold):
+    hal = gold["halton_23"]  # the reference's own table, all 64 entries
+    assert hal.shape == (64, 2) and hal[0, 0] == np.float32(0.5)
+    H.hostsim_halton_23.argtypes = [C.c_int32, oracle.f32p]
+    H.hostsim_screen_jitter.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, oracle.f32p]
+    for fn in (oracle.lib().oracle_halton_23, H.hostsim_halton_23):
+        got = np.zeros((64, 2), np.float32)
+        for k in range(64):
+            fn(k, got[k].ctypes.data_as(oracle.f32p))
+        assert np.array_equal(got.view(np.uint32), hal.view(np.uint32))
+    # jitter = halton_23[(frame_offset + frame_id) % 16] * 2 / dims - 1 / dims, in float, left to right
+    for fo, fid, w, h in ((0, 0, 1920, 1080), (7, 12, 333, 77), (2 ** 32 - 3, 9, 640, 480)):
+        k = ((fo + fid) & 0xFFFFFFFF) % 16
+        want = hal[k] * np.float32(2.0) / np.array([w, h], np.float32) - np.float32(1.0) / np.array([w, h], np.float32)
+        for fn in (oracle.lib().oracle_screen_jitter, H.hostsim_screen_jitter):
+            got = np.zeros(2, np.float32)
+            fn(fo, fid, w, h, got.ctypes.data_as(oracle.f32p))
+            assert np.array_equal(got.view(np.uint32), want.astype(np.float32).view(np.uint32))
+
+
+def test_raster_taa_frames_match_oracle(H, oracle):
+    """enable_raster_taa: no pixel-filter draws, the frame's Halton jitter instead (pt_megakernel.glsl:316-320)"""
+    s = scenes.random_triangles(5000)
+    sp = load_sky_fit()
+    o = oracle.OracleScene(s)
+    ls = T.LightSamplingConfig()
+    d = s.desc()
+    hs = H.hostsim_scene_create(C.byref(d), C.byref(ls))
+    W, Hh = 160, 90
+    p = T.RenderParams(enable_raster_taa=1)
+    imgs = []
+    for sample in (0, 5):
+        ref = o.render_sample(W, Hh, s.camera, sp, sample, params=p, frame_offset=3)
+        a = o._args(W, Hh, s.camera, sp, params=p, frame_offset=3, first_sample=sample)
+        img = np.zeros((Hh, W, 4), np.float32)
+        H.hostsim_render_sample(hs, C.byref(a), sample, oracle._fp(img))
+        assert np.array_equal(ref.view(np.uint32), img.view(np.uint32))
+        imgs.append(ref)
+    H.hostsim_scene_destroy(hs)
+    assert not np.array_equal(imgs[0], imgs[1])
+    # every pixel of a frame looks through the same sub-pixel offset: the hit mask of frame 0 equals the one rendered with the
+    # jitter folded into a pinhole without any draw -- here simply: it differs from the box-filtered frame
+    assert not np.array_equal(imgs[0], o.render_sample(W, Hh, s.camera, sp, 0, frame_offset=3))
