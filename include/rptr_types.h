@@ -38,6 +38,12 @@ extern "C" {
 #define RPTR_GEOMETRY_FLAGS_THIN 0x08u
 #define RPTR_GEOMETRY_FLAGS_DYNAMIC 0x10u
 
+/* rendering/postprocess/reprojection.h:11-13 (RenderParams::reprojection_mode); without ENABLE_REALTIME_RESOLVE only
+ * DISCARD_HISTORY changes the resolve: the frame's samples replace the history instead of being folded into it */
+#define RPTR_REPROJECTION_MODE_NONE 0
+#define RPTR_REPROJECTION_MODE_DISCARD_HISTORY 1
+#define RPTR_REPROJECTION_MODE_ACCUMULATE 2
+
 /* vulkan/gpu_params.glsl:27-29 */
 #define RPTR_RAY_EPSILON 0.000005f
 

@@ -1060,7 +1060,7 @@ int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rg
                 const uint32_t batch = a->batch_spp > 1 ? (uint32_t)a->batch_spp : 1u;
                 V4 c = main_spp(f, x, y, frame_id, a->first_sample + ((uint32_t)k / batch) * batch, cnt);
                 float xs[4] = {c.x, c.y, c.z, c.w};
-                if (frame_id > 0) {
+                if (frame_id > 0 && a->params.reprojection_mode != RPTR_REPROJECTION_MODE_DISCARD_HISTORY) { // process_samples.comp:116-127
                     float denom = (float)(frame_id + 1u);
                     for (int j = 0; j < 4; ++j) {
                         float m = px[j];

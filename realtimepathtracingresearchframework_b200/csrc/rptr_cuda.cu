@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(128) k_shadow(BvhDev bvh, Wave w, const uint32
 // Paths that ended with a miss (hit record still says "no triangle") get their sky / sun-disc term here, from the ray
 // direction, throughput and previous-bounce pdf they died with (shade_miss).
 __global__ void __launch_bounds__(256) k_resolve(rptr_scene_params sp, TileMap tm, Wave w, float4 *accum, uint32_t first_sample, int32_t n_layers,
-                                                 DevCounters *dc, AovTarget aov, float3 cam_pos) {
+                                                 DevCounters *dc, AovTarget aov, float3 cam_pos, int discard_history) {
     unsigned long long samples = 0;
     for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < (uint32_t)tm.local_pixels; lp += gridDim.x * blockDim.x) {
         const int32_t px = (int32_t)(lp % (uint32_t)tm.width);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) k_resolve(rptr_scene_params sp, TileMap t
                 il.x = r.x; il.y = r.y; il.z = r.z;
             }
             const uint32_t k = first_sample + (uint32_t)l;
-            if (k > 0) {
+            if (k > 0 && !discard_history) { // process_samples.comp:116-127: REPROJECTION_MODE_DISCARD_HISTORY keeps the new sample only
                 const float denom = (float)(k + 1u);
                 m.x += (il.x - m.x) / denom;
                 m.y += (il.y - m.y) / denom;
@@ -1005,7 +1005,8 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
             {
                 StageTimer t(ctx, 3);
                 k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp.sp, tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters, aov,
-                                                            make_float3(fp.cam_pos[0], fp.cam_pos[1], fp.cam_pos[2]));
+                                                            make_float3(fp.cam_pos[0], fp.cam_pos[1], fp.cam_pos[2]),
+                                                            ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_DISCARD_HISTORY);
                 ctx->launches++;
             }
         }

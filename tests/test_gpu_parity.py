@@ -516,6 +516,20 @@ def test_aov_images_readback(oracle):
     assert_identical(r.framebuffer(), ref, "beauty with AOV images on")
 
 
+def test_reprojection_mode_discard_history(oracle):
+    """RenderParams.reprojection_mode = DISCARD_HISTORY (process_samples.comp:116-127): the accumulator holds the last sample only."""
+    s = scenes.random_triangles(5000)
+    W, H = 128, 72
+    p = T.RenderParams(reprojection_mode=1)
+    r = make_backend(s, W, H)
+    r.params.reprojection_mode = 1
+    r.render_spp(s.camera, 3, batch_spp=1)
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=3, params=p)
+    assert_identical(r.framebuffer(), ref, "discard history")
+    last = oracle.OracleScene(s).render_sample(W, H, s.camera, load_sky_fit(), 2)
+    assert np.array_equal(ref.view(np.uint32), last.view(np.uint32))
+
+
 def test_raster_taa_screen_jitter(oracle):
     """RenderParams.enable_raster_taa: the pixel-filter draws are replaced by the frame's Halton jitter
     (pt_megakernel.glsl:316-320; render_vulkan.cpp:2917-2926), frame by frame and inside a batch."""
