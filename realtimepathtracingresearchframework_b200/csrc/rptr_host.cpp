@@ -404,6 +404,8 @@ struct Builder {
     std::vector<Prim> prims;
     std::vector<Node2> nodes;
     int sah_depth_limit = 32;
+    // cost of one traversal step in triangle tests (tuning: RPTR_SAH_TRAV_COST in the environment, profiles/r01_trace_sweep.md)
+    float trav_cost = std::getenv("RPTR_SAH_TRAV_COST") ? (float)std::atof(std::getenv("RPTR_SAH_TRAV_COST")) : 0.6f;
     static constexpr int NB = 16;
     static constexpr int MAX_LEAF = 4;
     static float half_area(const float *lo, const float *hi) {
@@ -483,8 +485,8 @@ struct Builder {
             std::nth_element(prims.begin() + lo, prims.begin() + mid, prims.begin() + hi, [ax](const Prim &a, const Prim &b) { return a.c[ax] < b.c[ax]; });
         } else {
             const float parent = half_area(blo, bhi);
-            // SAH termination: one traversal step costs about 1.2 triangle tests
-            if (n <= MAX_LEAF && (float)n * parent <= 1.2f * parent + best_cost) return leaf();
+            // SAH termination: one traversal step costs about `trav_cost` triangle tests
+            if (n <= MAX_LEAF && (float)n * parent <= trav_cost * parent + best_cost) return leaf();
             const float sc = (float)NB / (cmax[best_axis] - cmin[best_axis]);
             const float cm = cmin[best_axis];
             const int ax = best_axis, bb = best_bin;
