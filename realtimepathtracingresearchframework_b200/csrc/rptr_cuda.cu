@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                 const uint32_t slot = queue ? queue[tile_base + j] : tile_base + j;
                 const int tri = __float_as_int(w.hit[slot].w);
                 uint32_t key = tri >= 0 ? 1u : 0u; // miss / hit
+
                 if (tri >= 0 && sort_tiles > 1) { // several code paths in the scene: look the material up
                     const Tri *tr = bvh.tris + tri;
                     const GeomInst &g = sc.ginst[tri_geom_inst(*tr)];
