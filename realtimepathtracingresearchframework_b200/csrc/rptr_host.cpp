@@ -6,7 +6,9 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <atomic>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <cstdlib>
 
@@ -403,18 +405,26 @@ struct Node2 { // temporary binary node
 struct Builder {
     std::vector<Prim> prims;
     std::vector<Node2> nodes;
+    // sub-trees of at most `cutoff` primitives are left as placeholders by the serial top-down pass and built by worker
+    // threads afterwards (the primitive ranges are disjoint, the result does not depend on the thread count)
+    struct Job { int32_t node; int lo, hi, depth; };
     int sah_depth_limit = 32;
     // cost of one traversal step in triangle tests (tuning: RPTR_SAH_TRAV_COST in the environment, profiles/r01_trace_sweep.md)
     float trav_cost = std::getenv("RPTR_SAH_TRAV_COST") ? (float)std::atof(std::getenv("RPTR_SAH_TRAV_COST")) : 0.6f;
     static constexpr int NB = 16;
     static constexpr int MAX_LEAF = 4;
+    static constexpr int SWEEP_MAX = 8;
     static float half_area(const float *lo, const float *hi) {
         float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
         return dx * dy + dy * dz + dz * dx;
     }
-    int32_t build(int lo, int hi, int depth) {
+    int32_t build(std::vector<Node2> &nodes, int lo, int hi, int depth, std::vector<Job> *jobs, int cutoff) {
         const int32_t idx = (int32_t)nodes.size();
         nodes.push_back(Node2());
+        if (jobs && depth > 0 && hi - lo <= cutoff) {
+            jobs->push_back(Job{idx, lo, hi, depth});
+            return idx;
+        }
         float blo[3], bhi[3], cmin[3], cmax[3];
         for (int k = 0; k < 3; ++k) { blo[k] = 1e30f; bhi[k] = -1e30f; cmin[k] = 1e30f; cmax[k] = -1e30f; }
         for (int i = lo; i < hi; ++i)
@@ -432,6 +442,39 @@ struct Builder {
             return idx;
         };
         if (n == 1) return leaf();
+        if (n <= SWEEP_MAX && depth < sah_depth_limit) {
+            // few primitives: exact sweep SAH over the centroid order of each axis instead of 3 x 16 bins
+            int order[3][SWEEP_MAX];
+            float best = 1e30f;
+            int bax = -1, bsplit = -1;
+            for (int ax = 0; ax < 3; ++ax) {
+                int *o = order[ax];
+                for (int i = 0; i < n; ++i) o[i] = lo + i;
+                std::sort(o, o + n, [&](int a, int b) { return prims[a].c[ax] < prims[b].c[ax] || (prims[a].c[ax] == prims[b].c[ax] && prims[a].id < prims[b].id); });
+                float ra[SWEEP_MAX];
+                float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+                for (int i = n - 1; i > 0; --i) {
+                    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], prims[o[i]].lo[k]); mx[k] = fmaxf(mx[k], prims[o[i]].hi[k]); }
+                    ra[i] = half_area(mn, mx);
+                }
+                for (int k = 0; k < 3; ++k) { mn[k] = 1e30f; mx[k] = -1e30f; }
+                for (int i = 0; i < n - 1; ++i) {
+                    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], prims[o[i]].lo[k]); mx[k] = fmaxf(mx[k], prims[o[i]].hi[k]); }
+                    const float cost = half_area(mn, mx) * (float)(i + 1) + ra[i + 1] * (float)(n - i - 1);
+                    if (cost < best) { best = cost; bax = ax; bsplit = i + 1; }
+                }
+            }
+            const float parent = half_area(blo, bhi);
+            if (n <= MAX_LEAF && (float)n * parent <= trav_cost * parent + best) return leaf();
+            Prim tmp[SWEEP_MAX];
+            for (int i = 0; i < n; ++i) tmp[i] = prims[order[bax][i]];
+            for (int i = 0; i < n; ++i) prims[lo + i] = tmp[i];
+            const int32_t l = build(nodes, lo, lo + bsplit, depth + 1, jobs, cutoff);
+            const int32_t r = build(nodes, lo + bsplit, hi, depth + 1, jobs, cutoff);
+            nodes[idx].left = l;
+            nodes[idx].right = r;
+            return idx;
+        }
         int best_axis = -1, best_bin = -1;
         float best_cost = 1e30f;
         if (depth < sah_depth_limit) {
@@ -496,11 +539,45 @@ struct Builder {
             mid = (int)(it - prims.begin());
             if (mid == lo || mid == hi) mid = lo + n / 2;
         }
-        const int32_t l = build(lo, mid, depth + 1);
-        const int32_t r = build(mid, hi, depth + 1);
+        const int32_t l = build(nodes, lo, mid, depth + 1, jobs, cutoff);
+        const int32_t r = build(nodes, mid, hi, depth + 1, jobs, cutoff);
         nodes[idx].left = l;
         nodes[idx].right = r;
         return idx;
+    }
+    void build_all() {
+        const int n = (int)prims.size();
+        nodes.clear();
+        nodes.reserve(2 * (size_t)n);
+        std::vector<Job> jobs;
+        const int n_threads = std::getenv("RPTR_BUILD_THREADS") ? std::max(1, std::atoi(std::getenv("RPTR_BUILD_THREADS")))
+                                                                : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        build(nodes, 0, n, 0, n_threads > 1 && n > 65536 ? &jobs : nullptr, std::max(4096, n / (8 * n_threads)));
+        if (jobs.empty()) return;
+        if (std::getenv("RPTR_BUILD_VERBOSE")) fprintf(stderr, "bvh: top pass done, %zu jobs, %d threads\n", jobs.size(), n_threads);
+        std::vector<std::vector<Node2>> local(jobs.size());
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t j = next.fetch_add(1); j < jobs.size(); j = next.fetch_add(1)) {
+                local[j].reserve(2 * (size_t)(jobs[j].hi - jobs[j].lo));
+                build(local[j], jobs[j].lo, jobs[j].hi, jobs[j].depth, nullptr, 0);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+        work();
+        for (std::thread &t : pool) t.join();
+        if (std::getenv("RPTR_BUILD_VERBOSE")) fprintf(stderr, "bvh: workers joined\n");
+        // splice: local node 0 replaces the placeholder, local node i >= 1 lands at off + i
+        for (size_t j = 0; j < jobs.size(); ++j) {
+            const int32_t off = (int32_t)nodes.size() - 1;
+            auto fix = [&](Node2 nd) {
+                if (nd.left >= 0) { nd.left += off; nd.right += off; }
+                return nd;
+            };
+            nodes[jobs[j].node] = fix(local[j][0]);
+            for (size_t i = 1; i < local[j].size(); ++i) nodes.push_back(fix(local[j][i]));
+        }
     }
 };
 
@@ -599,12 +676,14 @@ void build_bvh(HostScene &s) {
     // median splits until the wide tree is at most RPTR_MAX_BVH_DEPTH deep (never needed for sane inputs).
     for (int limit = 32;; limit -= 8) {
         std::vector<Prim> keep = b.prims;
-        b.nodes.clear();
-        b.nodes.reserve(2 * s.tris.size());
         b.sah_depth_limit = limit;
-        b.build(0, (int)b.prims.size(), 0);
+        const auto tb0 = std::chrono::steady_clock::now();
+        b.build_all();
+        if (std::getenv("RPTR_BUILD_VERBOSE")) fprintf(stderr, "bvh: binary build %.0f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count());
         s.leaf_tris.reserve(s.tris.size());
+        const auto tc0 = std::chrono::steady_clock::now();
         const int depth = collapse(b, s);
+        if (std::getenv("RPTR_BUILD_VERBOSE")) fprintf(stderr, "bvh: collapse %.0f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
         if (depth <= RPTR_MAX_BVH_DEPTH || limit <= 0) {
             if (depth > RPTR_MAX_BVH_DEPTH) throw std::runtime_error("BVH too deep for the traversal stack");
             break;

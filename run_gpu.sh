@@ -1,6 +1,3 @@
-for v in base nopf base nopf; do RPTR_CUDA_LIB=variants/librptr_cuda_$v.so timeout 300 python bench.py --no-cpu-baseline --steps 2 --warmup 2 > gpurun_out/sweep_$v.json 2> gpurun_out/sweep_$v.err || tail -2 gpurun_out/sweep_$v.err; python -c "
-import json; j=json.load(open('gpurun_out/sweep_$v.json')); r=j['roofline']; print('var', '$v', round(j['value'],1), r['frac'], r['stage_ms_rank0'])"; done
-RPTR_CUDA_LIB=variants/librptr_cuda_base.so timeout 600 python bench.py --scene c4 --spp 16 --no-cpu-baseline --steps 2 --warmup 2 > gpurun_out/sweep_c4pf.json 2>/dev/null; python -c "
-import json; j=json.load(open('gpurun_out/sweep_c4pf.json')); print('var c4 prefetch', j['value'], j['roofline']['stage_ms_rank0'])"
-RPTR_CUDA_LIB=variants/librptr_cuda_nopf.so timeout 600 python bench.py --scene c4 --spp 16 --no-cpu-baseline --steps 2 --warmup 2 > gpurun_out/sweep_c4nopf.json 2>/dev/null; python -c "
-import json; j=json.load(open('gpurun_out/sweep_c4nopf.json')); print('var c4 no prefetch', j['value'], j['roofline']['stage_ms_rank0'])"
+N=$(nvidia-smi -L | wc -l); echo "gpus: $N"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; python -c "
+import json; j=json.load(open('gpurun_out/bench_${N}gpu.json')); print('scale', j['n_gpus'], j['value'], j['e2e']['value'], j['ms_per_step'], j['roofline']['stage_ms_rank0'])"; tail -2 gpurun_out/bench_${N}gpu.err | cut -c1-200
