@@ -905,7 +905,16 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
                 ign = -ign;
             }
         }
-        // normal mapping needs textures: normal_map must be -1 on this path (checked at scene creation)
+        if (mp.normal_map != -1) { // :634-654, the normal map read through the texture set (1 x 1: uv and LOD are irrelevant)
+            V3 t_y = normalize(cross(h.normal, h.tangent));
+            V3 t_x = cross(t_y, h.normal);
+            t_x = t_x * length(h.tangent);
+            t_y = t_y * h.bitangent_l;
+            TextureSet::RGBA tx = s.texset.texel((uint32_t)mp.normal_map);
+            V3 map_nrm = v3(2.0f * tx.r - 1.0f, 2.0f * tx.g - 1.0f, 1.0f * tx.b - 0.0f);
+            map_nrm.z = sqrtf(fmaxf(1.0f - map_nrm.x * map_nrm.x - map_nrm.y * map_nrm.y, 0.0f));
+            in_ = normalize(mat_mul(t_x, t_y, in_ * sp.normal_z_scale, map_nrm));
+        }
         { // :657-668
             float nw = dot(w_o, in_), gnw = dot(w_o, ign);
             if (nw * gnw <= 0.0f) {

@@ -388,6 +388,7 @@ struct rptr_ctx {
     BvhDev bvh{};
     int32_t n_lights = 0;
     std::vector<rptr_base_material> materials_host; // resolved materials (texture handles folded in), for per-frame host decisions
+    bool any_normal_map = false;
     bool any_alpha_tested = false; // some triangle needs the stochastic alpha candidate filter (Alpha variants of the trace kernels)
     std::vector<rptr_tri_light_data> lights_host;
     rptr_scene_params scene_params{};
@@ -697,6 +698,9 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     CU(cudaMemcpy(d_gi, gi.data(), gi.size() * sizeof(GeomInst), cudaMemcpyHostToDevice));
     CU(dev_alloc(ctx, &d_mat, hs.materials.size(), ctx->scene_allocs));
     CU(cudaMemcpy(d_mat, hs.materials.data(), hs.materials.size() * sizeof(rptr_base_material), cudaMemcpyHostToDevice));
+    float4 *d_ntex;
+    CU(dev_alloc(ctx, &d_ntex, hs.materials.size(), ctx->scene_allocs));
+    CU(cudaMemcpy(d_ntex, hs.normal_texels.data(), hs.materials.size() * sizeof(float4), cudaMemcpyHostToDevice));
     CU(dev_alloc(ctx, &d_lights, hs.lights.size(), ctx->scene_allocs));
     if (!hs.lights.empty()) CU(cudaMemcpy(d_lights, hs.lights.data(), hs.lights.size() * sizeof(rptr_tri_light_data), cudaMemcpyHostToDevice));
     if (ctx->bvh_builder == 1) { // device LBVH (rptr_bvh_build.cu)
@@ -718,11 +722,12 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
         ctx->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         for (void *p : {(void *)db.nodes, (void *)db.tris, (void *)db.top})
             if (p) ctx->scene_allocs.push_back(p);
-        ctx->scene = SceneDev{d_gi, d_mat, d_lights};
+        ctx->scene = SceneDev{d_gi, d_mat, d_lights, d_ntex};
         ctx->bvh = BvhDev{db.nodes, db.tris, db.n_nodes, db.n_tris, db.top, db.top_k};
         ctx->n_lights = (int32_t)hs.lights.size();
         ctx->lights_host = hs.lights;
         ctx->any_alpha_tested = hs.any_alpha_tested;
+        ctx->any_normal_map = hs.any_normal_map;
         ctx->materials_host = hs.materials;
         ctx->has_scene = true;
         ctx->frame_id = 0;
@@ -741,11 +746,12 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     float4 *d_top;
     CU(dev_alloc(ctx, &d_top, top.size(), ctx->scene_allocs));
     CU(cudaMemcpy(d_top, top.data(), top.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    ctx->scene = SceneDev{d_gi, d_mat, d_lights};
+    ctx->scene = SceneDev{d_gi, d_mat, d_lights, d_ntex};
     ctx->bvh = BvhDev{d_nodes, d_tris, (int32_t)hs.nodes.size(), (int32_t)hs.leaf_tris.size(), d_top, top_k};
     ctx->n_lights = (int32_t)hs.lights.size();
     ctx->lights_host = hs.lights;
     ctx->any_alpha_tested = hs.any_alpha_tested;
+    ctx->any_normal_map = hs.any_normal_map;
     ctx->materials_host = hs.materials;
     ctx->has_scene = true;
     ctx->frame_id = 0; // vulkan/render_vulkan.cpp:1556
@@ -964,7 +970,8 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     StageTimer t(ctx, 1);
                     // smallest compiled variant that covers the features this frame uses (rptr_shading.cuh, RPTR_FEAT_*)
                     const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
-                                     (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0);
+                                     (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0) |
+                                     (ctx->any_normal_map ? RPTR_FEAT_NORMAL_MAPS : 0);
 #define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (hitq ? hitq : q), (hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, 0u}), tm, sort_tiles
                     if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);

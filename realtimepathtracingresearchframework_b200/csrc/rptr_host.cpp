@@ -239,9 +239,14 @@ float resolve_scalar(const rptr_scene_desc &d, float v) {
 static void resolve_materials(const rptr_scene_desc &d, HostScene &s) {
     s.materials.assign(d.materials, d.materials + d.n_materials);
     s.material_alpha8.assign(d.n_materials, RPTR_TRI_OPAQUE);
+    s.normal_texels.assign(4 * (size_t)d.n_materials, 0.0f);
     for (int i = 0; i < d.n_materials; ++i) {
         rptr_base_material &m = s.materials[i];
-        if (m.normal_map != -1) throw std::runtime_error("normal maps are not supported by this backend yet (normal_map must be -1)");
+        if (m.normal_map != -1) { // the normal-map texel as textureLod(...).rgb returns it (pt_megakernel.glsl:647)
+            const Texel x = fetch_texel(d, (uint32_t)m.normal_map);
+            s.normal_texels[4 * i + 0] = x.c[0]; s.normal_texels[4 * i + 1] = x.c[1]; s.normal_texels[4 * i + 2] = x.c[2];
+            s.any_normal_map = true;
+        }
         if (is_handle(m.base_color[0])) {
             if (m.emission_intensity != 0.0f) throw std::runtime_error("emissive materials with a textured base colour are not supported by this backend yet");
             const Texel x = fetch_texel(d, f2u(m.base_color[0]));

@@ -24,6 +24,8 @@ struct HostScene {
     std::vector<HostGeomInst> ginst;
     std::vector<rptr_base_material> materials;   // texture handles already resolved to constants (1x1-texel mode)
     std::vector<int32_t> material_alpha8;       // per material: alpha texel (255 = opaque)
+    std::vector<float> normal_texels;           // per material: rgb (+ pad) of its 1 x 1 normal map, zeros without one
+    bool any_normal_map = false;
     bool any_alpha_tested = false;              // some triangle has alpha8 != 255: traversal must run the candidate filter
     std::vector<rptr_tri_light_data> lights;
     std::vector<Tri> tris;      // flattened (instance, geometry, primitive) order; Tri::id == index

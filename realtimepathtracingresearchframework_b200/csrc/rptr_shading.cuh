@@ -50,6 +50,7 @@ struct SceneDev {
     const GeomInst *ginst;
     const rptr_base_material *materials;
     const rptr_tri_light_data *lights;
+    const float4 *normal_texels; // per material: the texel of its (1 x 1) normal map, rgb as sampled; read only when normal_map != -1
 };
 
 struct FrameParams {
@@ -716,7 +717,8 @@ RPTR_HD AovSample aov_of_miss(const float *cam_pos) { // store_geometry_aovs(0, 
 #define RPTR_FEAT_TRI_LIGHTS 2   // the scene has binned triangle lights (p_sun < 1)
 #define RPTR_FEAT_AOV 4          // fp.output_channel may be non-zero
 #define RPTR_FEAT_QMC 8          // fp.rng_variant may select a Sobol / blue-noise sampler
-#define RPTR_FEAT_ALL 15
+#define RPTR_FEAT_NORMAL_MAPS 16 // some material has a normal map
+#define RPTR_FEAT_ALL 31
 // RANDOM_FLOAT1(rng, d) of the selected pointset (rendering/pointsets/selected_rng.glsl, rendering/defaults.glsl:23-28)
 template <int FEAT>
 RPTR_HD float path_rand(const FrameParams &fp, PathState &ps, int d) {
@@ -793,6 +795,16 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
             in_ = -in_;
             ign = -ign;
         }
+    }
+    if ((FEAT & RPTR_FEAT_NORMAL_MAPS) && mp.normal_map != -1) { // pt_megakernel.glsl:634-654 (1x1-texel mode: one texel per material)
+        float3 t_y = normalize(cross(h.normal, h.tangent));
+        float3 t_x = cross(t_y, h.normal);
+        t_x = t_x * length(h.tangent);
+        t_y = t_y * h.bitangent_l;
+        const float4 tx = sc.normal_texels[h.material_id];
+        float3 map_nrm = f3(2.0f * tx.x - 1.0f, 2.0f * tx.y - 1.0f, 1.0f * tx.z - 0.0f);
+        map_nrm.z = sqrtf(fmaxf(1.0f - map_nrm.x * map_nrm.x - map_nrm.y * map_nrm.y, 0.0f));
+        in_ = normalize(mat_mul(t_x, t_y, in_ * sp.normal_z_scale, map_nrm));
     }
     {
         float nw = dot(w_o, in_), gnw = dot(w_o, ign);

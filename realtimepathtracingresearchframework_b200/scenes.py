@@ -269,7 +269,8 @@ def random_triangles(n_tris=1_000_000, n_geometries=16, seed=0x5EED1A7B200, box=
 def alpha_tested_soup(n_tris=6000, seed=99):
     """Random triangles whose materials exercise the 1x1-texel mode and the stochastic alpha candidate
     filter (8a-4): cut-out (alpha 0), half transparent (alpha 128/255), faint (alpha 32/255), an opaque sRGB texel, a
-    material that reads roughness / metallic from texture channels, alpha-textured but flagged NOALPHA, and constants."""
+    material that reads roughness / metallic from texture channels, alpha-textured but flagged NOALPHA, constants, and
+    two materials with a (one-texel) normal map."""
     s = random_triangles(n_tris, n_geometries=8, seed=seed, box=5.0, edge=0.9)
     t_half = s.add_texture((200, 120, 60, 128), T.COLOR_SPACE_SRGB)
     t_cut = s.add_texture((255, 255, 255, 0), T.COLOR_SPACE_SRGB)
@@ -284,6 +285,9 @@ def alpha_tested_soup(n_tris=6000, seed=99):
     m[4].roughness, m[4].metallic, m[4].flags = T.texture_handle(t_orm, 1), T.texture_handle(t_orm, 2), 0
     m[5].base_color = (T.texture_handle(t_half), 0.0, 0.0)               # NOALPHA stays set: colour from the texel, never alpha-tested
     m[6].flags = 0                                                        # constants without NOALPHA: alpha 1, no draw
+    t_nrm = s.add_texture((170, 96, 255), T.COLOR_SPACE_LINEAR)          # tilted tangent-space normal
+    m[7].normal_map = t_nrm                                               # normal map (pt_megakernel.glsl:634-654), one texel
+    m[3].normal_map = t_nrm
     s.camera = look_at_camera((0, 0, 16), (0, 0, 0), fovy=55.0)
     s.name = "alpha_soup%d" % n_tris
     return s

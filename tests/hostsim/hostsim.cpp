@@ -83,7 +83,7 @@ static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
 // albedo.rgb, roughness, normal.xyz, depth of the first path vertex (the values behind the fp16 AOV images)
 static int render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba, float *aov_out) {
     FrameParams fp = make_frame(s, a);
-    SceneDev sc{s->gi.data(), s->hs.materials.data(), s->hs.lights.data()};
+    SceneDev sc{s->gi.data(), s->hs.materials.data(), s->hs.lights.data(), reinterpret_cast<const float4 *>(s->hs.normal_texels.data())};
     BvhDev bvh{s->hs.nodes.data(), s->hs.leaf_tris.data(), (int32_t)s->hs.nodes.size(), (int32_t)s->hs.leaf_tris.size()};
 #pragma omp parallel for schedule(dynamic, 1)
     for (int y = a->y0; y < a->y1; ++y)

@@ -88,3 +88,25 @@ def test_srgb_and_unorm_decoding_of_resolved_materials(H, oracle):
     want = np.array([srgb(188), srgb(64), srgb(230)], np.float32)  # material 3: opaque sRGB texel, alpha 1
     px = ref[..., :3].reshape(-1, 3)
     assert (np.abs(px - want).max(axis=1) == 0).any(), "no pixel shows the decoded sRGB texel"
+
+
+def test_normal_map_changes_shading_only_where_it_is_set(H, oracle):
+    """one-texel normal maps (pt_megakernel.glsl:634-654): bit-exact against the oracle (covered by the tests above, the soup
+    has two such materials) and really in effect: removing them changes pixels, but not the hit mask."""
+    s = scenes.alpha_tested_soup()
+    flat = scenes.alpha_tested_soup()
+    for m in flat.materials:
+        m.normal_map = -1
+    W, Hh = 200, 120
+    a, ia = render_both(H, oracle, s, W, Hh, 0)
+    b, ib = render_both(H, oracle, flat, W, Hh, 0)
+    assert np.array_equal(a.view(np.uint32), ia.view(np.uint32)) and np.array_equal(b.view(np.uint32), ib.view(np.uint32))
+    assert not np.array_equal(a[..., :3], b[..., :3])
+    assert np.array_equal(a[..., 3], b[..., 3])
+    # AOV channel 2 = shading normal of the first hit: differs exactly where a normal-mapped material is hit
+    p = T.RenderParams()
+    p.output_channel = 2
+    na, _ = render_both(H, oracle, s, W, Hh, 0, params=p)
+    nb, _ = render_both(H, oracle, flat, W, Hh, 0, params=p)
+    changed = (na[..., :3] != nb[..., :3]).any(-1)
+    assert 0.02 < changed.mean() < 0.5
