@@ -1,2 +1,3 @@
-for v in base pf; do for spp in 1 16 64; do RPTR_CUDA_LIB=variants/librptr_cuda_$v.so timeout 300 python bench.py --no-cpu-baseline --steps 3 --warmup 3 --spp $spp > gpurun_out/sweep_${v}_$spp.json 2> gpurun_out/sweep_$v.err || tail -2 gpurun_out/sweep_$v.err; python -c "
-import json; j=json.load(open('gpurun_out/sweep_${v}_$spp.json')); r=j['roofline']; print('var', '$v', $spp, round(j['value'],1), r['frac'], r['stage_ms_rank0'])"; done; done
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/t.log 2>&1; tail -2 gpurun_out/t.log
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; python -c "
+import json; j=json.load(open('gpurun_out/bench_c2.json')); r=j['roofline']; print('c2', j['value'], j['e2e']['value'], r['frac'])"

@@ -48,6 +48,17 @@ void hostsim_scene_destroy(hostsim_scene *s) { delete s; }
 int32_t hostsim_num_lights(const hostsim_scene *s) { return (int32_t)s->hs.lights.size(); }
 void hostsim_get_lights(const hostsim_scene *s, rptr_tri_light_data *out) { memcpy(out, s->hs.lights.data(), s->hs.lights.size() * sizeof(*out)); }
 int32_t hostsim_num_nodes(const hostsim_scene *s) { return (int32_t)s->hs.nodes.size(); }
+// FNV-1a over the 4-wide nodes and the leaf-ordered triangle records: the BVH must not depend on the builder's thread count
+uint64_t hostsim_bvh_hash(const hostsim_scene *s) {
+    uint64_t h = 1469598103934665603ull;
+    auto eat = [&](const void *p, size_t n) {
+        const unsigned char *b = (const unsigned char *)p;
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    eat(s->hs.nodes.data(), s->hs.nodes.size() * sizeof(BvhNode));
+    eat(s->hs.leaf_tris.data(), s->hs.leaf_tris.size() * sizeof(Tri));
+    return h;
+}
 
 static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
     FrameParams fp;

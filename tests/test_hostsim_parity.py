@@ -166,3 +166,25 @@ def test_c4_style_instanced_scene_matches_oracle(H, oracle):
     H.hostsim_scene_destroy(hs)
     assert (ref[..., 3] > 0).mean() > 0.02
     assert np.array_equal(ref.view(np.uint32), img.view(np.uint32))
+
+
+def test_host_bvh_does_not_depend_on_the_builder_thread_count(hostsim, monkeypatch):
+    """build_bvh (csrc/rptr_host.cpp) builds the top of the tree serially and the sub-trees on worker threads: the 4-wide
+    tree and the leaf order must be identical for any thread count (and the traversal result is independent of both)."""
+    lib = C.CDLL(hostsim)
+    lib.hostsim_scene_create.restype = C.c_void_p
+    lib.hostsim_scene_create.argtypes = [C.POINTER(T.SceneDesc), C.POINTER(T.LightSamplingConfig)]
+    lib.hostsim_scene_destroy.argtypes = [C.c_void_p]
+    lib.hostsim_bvh_hash.restype = C.c_uint64
+    lib.hostsim_bvh_hash.argtypes = [C.c_void_p]
+    lib.hostsim_num_nodes.argtypes = [C.c_void_p]
+    s = scenes.random_triangles(150000)  # large enough for the threaded path (> 65536 triangles)
+    ls = T.LightSamplingConfig()
+    seen = {}
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("RPTR_BUILD_THREADS", threads)
+        d = s.desc()
+        hs = lib.hostsim_scene_create(C.byref(d), C.byref(ls))
+        seen[threads] = (lib.hostsim_bvh_hash(hs), lib.hostsim_num_nodes(hs))
+        lib.hostsim_scene_destroy(hs)
+    assert seen["1"] == seen["3"] == seen["8"] and seen["1"][1] > 30000
