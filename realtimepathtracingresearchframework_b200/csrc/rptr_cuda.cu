@@ -344,16 +344,37 @@ __global__ void __launch_bounds__(128) k_ray_queries(BvhDev bvh, const rptr_rend
     }
 }
 
-// display path only (process_samples.comp:138-200 without tonemapping operators): exposure + sRGB, not part of .pfm parity
-__global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, uchar4 *out, uint32_t n, float exposure_scale) {
+// LDR framebuffer of the display path (process_samples.comp:138-200 with ENABLE_AOV_BUFFERS; not part of .pfm parity):
+// exposure for the colour channel, the AOV images for output_channel 1 / 2 (output_moment selects roughness / depth),
+// then linear_to_srgb (rendering/util.glsl:25-28) and the rgba8 store.  Tone-mapping operators (early_tone_mapping_mode >= 0)
+// and the motion / jitter image are not produced; pixels whose alpha is negative are left as they are (:139-140).
+__device__ __forceinline__ float4 half4_to_float4(ushort4 h) {
+    return f4(__half2float(__ushort_as_half(h.x)), __half2float(__ushort_as_half(h.y)), __half2float(__ushort_as_half(h.z)),
+              __half2float(__ushort_as_half(h.w)));
+}
+__global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, const ushort4 *aov_ar, const ushort4 *aov_nd, uchar4 *out, uint32_t n,
+                                                  float exposure_scale, int output_channel, int output_moment) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 c = accum[i];
-        float v[3] = {c.x * exposure_scale, c.y * exposure_scale, c.z * exposure_scale};
+        if (!(c.w >= 0.0f)) continue;
+        if (output_channel == 0) {
+            c.x *= exposure_scale; c.y *= exposure_scale; c.z *= exposure_scale;
+        } else if (output_channel == 1 && aov_ar) {
+            c = half4_to_float4(aov_ar[i]);
+            if (output_moment != 0) c.x = c.y = c.z = c.w;
+        } else if (output_channel == 2 && aov_nd) {
+            c = half4_to_float4(aov_nd[i]);
+            if (output_moment != 0) c.x = c.y = c.z = c.w * 0.05f;
+            else { c.x = c.x * 0.5f + 0.5f; c.y = c.y * 0.5f + 0.5f; c.z = c.z * 0.5f + 0.5f; }
+        } else if (output_channel == 3) {
+            c = f4(0.0f, 0.0f, 0.0f, 1.0f);
+        }
+        const float v[3] = {c.x, c.y, c.z};
         unsigned char o[3];
         for (int k = 0; k < 3; ++k) {
-            float x = v[k];
-            float s = (x <= 0.0031308f) ? 12.92f * x : 1.055f * powf(fmaxf(fabsf(x), 1.192092896e-07f), 1.0f / 2.4f) - 0.055f;
-            o[k] = (unsigned char)(fminf(fmaxf(s, 0.0f), 1.0f) * 255.0f + 0.5f);
+            const float x = v[k];
+            const float s = (x <= 0.0031308f) ? 12.92f * x : 1.055f * powf(fmaxf(fabsf(x), 1.192092896e-07f), 1.0f / 2.4f) - 0.055f;
+            o[k] = (unsigned char)(fminf(fmaxf(s, 0.0f), 1.0f) * 255.0f + 0.5f); // NaN (0 * inf of a far depth) stores 0
         }
         out[i] = make_uchar4(o[0], o[1], o[2], (unsigned char)(fminf(fmaxf(c.w, 0.0f), 1.0f) * 255.0f + 0.5f));
     }
@@ -1135,7 +1156,9 @@ size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst) {
     if (n_elems < size) return 0;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
     const float scale = exp2f(ctx->params.exposure);
-    k_to_srgb8<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->accum, ctx->ldr, (uint32_t)(size / 4), scale);
+    const bool aov_on = ctx->aov_buffers != 0;
+    k_to_srgb8<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->accum, aov_on ? ctx->aov_images[0] : nullptr, aov_on ? ctx->aov_images[1] : nullptr, ctx->ldr,
+                                                          (uint32_t)(size / 4), scale, ctx->params.output_channel, ctx->params.output_moment);
     ctx->launches++;
     if (cudaMemcpyAsync(dst, ctx->ldr, size, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;

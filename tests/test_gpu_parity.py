@@ -547,3 +547,58 @@ def test_raster_taa_screen_jitter(oracle):
     refb, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=4, params=p, batch_spp=4)
     assert_identical(b.framebuffer(), refb, "raster TAA, batch of 4")
     assert not np.array_equal(ref, refb)
+
+
+def test_c3_progressive_4096spp(oracle):
+    """BASELINE configs[2]: the 1 M-triangle scene accumulated to 4096 spp (reduced frame so that the oracle finishes in seconds):
+    one frame of batch_spp = 4096 split into waves == 64 frames of 64 spp, bit for bit, and a window of it == the oracle's
+    sequential running mean over all 4096 samples."""
+    s = scenes.random_triangles(1_000_000)
+    W, H = 384, 216
+    a = make_backend(s, W, H, wave_paths=96 * W * H)  # 4096 layers in waves of 96 (42 full waves + one of 64)
+    a.render_spp(s.camera, 4096, batch_spp=4096)
+    b = make_backend(s, W, H)
+    b.render_spp(s.camera, 4096, batch_spp=64)
+    fa_, fb = a.framebuffer(), b.framebuffer()
+    assert np.array_equal(fa_.view(np.uint32), fb.view(np.uint32))
+    assert a.stats().spp == 4096 and b.frame_state() == (4096, 0, 4096)
+    x0, y0, x1, y1 = 150, 100, 166, 108
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=4096, region=(x0, y0, x1, y1))
+    assert_identical(fa_[y0:y1, x0:x1], ref[y0:y1, x0:x1], "C3 window, 4096 spp")
+    # converged enough to be smooth where nothing is hit: the sky rows of the two halves of the accumulation agree to 1e-3
+    c = make_backend(s, W, H)
+    c.render_spp(s.camera, 2048, batch_spp=2048)
+    sky = fa_[..., 3] == 0
+    rel = np.abs(c.framebuffer()[sky][:, :3] - fa_[sky][:, :3]) / np.maximum(fa_[sky][:, :3], 1e-6)
+    assert sky.any() and np.median(rel) < 1e-3
+
+
+def test_ldr_framebuffer_readback(oracle):
+    """readback_framebuffer(uint8*): the display chain of process_samples.comp:138-200 -- exposure + sRGB for the colour
+    channel, the AOV images for output channels 1 / 2.  pow() is not part of the arithmetic contract: +-1 code value."""
+    s = scenes.random_triangles(20000)
+    W, H = 256, 144
+    r = make_backend(s, W, H)
+    r.params.exposure = 0.5
+    r.render_spp(s.camera, 4)
+    img = r.framebuffer()
+
+    def to_srgb8(rgb, alpha):
+        x = np.maximum(rgb.astype(np.float64), 0.0)
+        sr = np.where(x <= 0.0031308, 12.92 * x, 1.055 * np.power(np.maximum(x, 1e-12), 1 / 2.4) - 0.055)
+        out = np.zeros(rgb.shape[:2] + (4,), np.float64)
+        out[..., :3] = np.clip(sr, 0, 1) * 255 + 0.5
+        out[..., 3] = np.clip(alpha, 0, 1) * 255 + 0.5
+        return np.floor(out).astype(np.int32)
+    ldr = np.zeros((H, W, 4), np.uint8)
+    assert r.readback_framebuffer(ldr) == ldr.size
+    want = to_srgb8(img[..., :3] * np.float32(2.0 ** 0.5), img[..., 3])
+    assert np.abs(ldr.astype(np.int32) - want).max() <= 1
+    # normal / depth display from the AOV image
+    r.params.output_channel = 2
+    ldr2 = np.zeros((H, W, 4), np.uint8)
+    assert r.readback_framebuffer(ldr2) == ldr2.size
+    nd = r.aov(1).astype(np.float32)
+    want2 = to_srgb8(nd[..., :3] * 0.5 + 0.5, np.where(np.isfinite(nd[..., 3]), nd[..., 3], 1.0))
+    assert np.abs(ldr2[..., :3].astype(np.int32) - want2[..., :3]).max() <= 1
+    assert not np.array_equal(ldr, ldr2)
