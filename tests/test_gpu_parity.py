@@ -594,8 +594,9 @@ def test_ldr_framebuffer_readback(oracle):
     assert r.readback_framebuffer(ldr) == ldr.size
     want = to_srgb8(img[..., :3] * np.float32(2.0 ** 0.5), img[..., 3])
     assert np.abs(ldr.astype(np.int32) - want).max() <= 1
-    # normal / depth display from the AOV image
+    # normal / depth display from the AOV image (the parameters of the last frame decide, as in process_samples.comp)
     r.params.output_channel = 2
+    r.render_spp(s.camera, 1)
     ldr2 = np.zeros((H, W, 4), np.uint8)
     assert r.readback_framebuffer(ldr2) == ldr2.size
     nd = r.aov(1).astype(np.float32)
