@@ -149,8 +149,12 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
 // Divergence control: a CTA takes tiles of RPTR_SHADE_TILE queue entries, counting-sorts them in shared memory by
 // (miss | material id) and hands every warp a run of equal keys, so that sky evaluation, Lambert, GGX, transmissive and
 // emissive vertices do not share warps (the reference's megakernel pays that divergence inside every workgroup).
+#ifndef RPTR_SHADE_THREADS
 #define RPTR_SHADE_THREADS 128
+#endif
+#ifndef RPTR_SHADE_PER_THREAD
 #define RPTR_SHADE_PER_THREAD 4
+#endif
 #define RPTR_SHADE_TILE (RPTR_SHADE_THREADS * RPTR_SHADE_PER_THREAD)
 #define RPTR_SHADE_KEYS 16
 #ifndef RPTR_SHADE_MIN_BLOCKS
