@@ -156,6 +156,23 @@ def gen_vectors(n=512, seed=1234):
         assert m > 0
         out["bin_%s_in" % tag] = em
         out["bin_%s_out" % tag] = np.frombuffer(outl, np.float32).reshape(-1, 12)[:m].copy()
+    # --- sky model + sun sampling: rendering/lights/sky_model_arhosek/sky_model.glsl:40-59, rendering/lights/sun.glsl:9-20 ---
+    sky_dirs = unit(rng.normal(size=(n, 3))).astype(np.float32)
+    sky_dirs[: n // 2, 1] = np.abs(sky_dirs[: n // 2, 1])
+    sky_dirs[:8, 1] = np.array([0.0, 1e-4, 1.0, 0.999, 0.5, 0.01, 0.25, 0.75], np.float32)
+    sky_dirs = unit(sky_dirs).astype(np.float32)
+    for ci, kw in enumerate(SKY_CONFIGS):
+        sp = po.sky_fit(T.SceneConfig(**kw))
+        sd = np.array(list(sp.sun_dir), np.float32)
+        rad = np.zeros((n, 3), np.float32)
+        for i in range(n):
+            R.ref_skymodel_radiance(C.byref(sp), fa(*sd), fa(*sky_dirs[i]), rad[i].ctypes.data_as(po.f32p))
+        out["sky%d_radiance" % ci] = rad
+        sun = np.zeros((n, 4), np.float32)
+        for i in range(n):
+            R.ref_sample_sun_dir(fa(*sd), C.c_float(float(sp.sun_cos_angle)), fa(*u4[i, :2]), sun[i].ctypes.data_as(po.f32p))
+        out["sky%d_sun_samples" % ci] = sun
+    out["sky_dirs"] = sky_dirs
     path = os.path.join(ROOT, "tests", "golden", "ref_vectors.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})

@@ -1,0 +1,38 @@
+// oracle/ref_shim/ref_sky.cpp -- TEST INFRASTRUCTURE.
+// extern "C" wrappers around two more of the reference's own GLSL sources that compile as C++ with the shim, #included from
+// where they lie under REF: rendering/lights/sky_model_arhosek/sky_model.glsl (skymodel_radiance, the Hosek-Wilkie RGB
+// evaluation the miss shader calls) and rendering/lights/sun.glsl (sample_sun_dir / sample_sun_dir_pdf of the sun NEE).
+#include <glm/glm.hpp>
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/rptr_types.h"
+
+namespace refsky {
+using namespace glm;
+#include "rendering/language.hpp"
+#include "rendering/util.glsl"
+#include "rendering/lights/sky_model_arhosek/sky_model.glsl"
+#include "rendering/lights/sun.glsl"
+} // namespace refsky
+
+extern "C" {
+
+// skymodel_radiance(SkyModelParams{configs, radiances}, sun_dir, view_dir) with the fitted block of rptr_scene_params
+void ref_skymodel_radiance(const rptr_scene_params *sp, const float *sun_dir, const float *view_dir, float *out) {
+    refsky::SkyModelParams p;
+    for (int i = 0; i < 9; ++i) p.configs[i] = glm::vec4(sp->sky_configs[i][0], sp->sky_configs[i][1], sp->sky_configs[i][2], sp->sky_configs[i][3]);
+    p.radiances = glm::vec4(sp->sky_radiances[0], sp->sky_radiances[1], sp->sky_radiances[2], sp->sky_radiances[3]);
+    glm::vec3 r = refsky::skymodel_radiance(p, glm::vec3(sun_dir[0], sun_dir[1], sun_dir[2]), glm::vec3(view_dir[0], view_dir[1], view_dir[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+
+// sample_sun_dir(sun_dir, cos_radius, sample) -> out[0..2], sample_sun_dir_pdf -> out[3]
+void ref_sample_sun_dir(const float *sun_dir, float cos_radius, const float *u2, float *out) {
+    const glm::vec3 s(sun_dir[0], sun_dir[1], sun_dir[2]);
+    glm::vec3 d = refsky::sample_sun_dir(s, cos_radius, glm::vec2(u2[0], u2[1]));
+    out[0] = d.x; out[1] = d.y; out[2] = d.z;
+    out[3] = refsky::sample_sun_dir_pdf(s, cos_radius, d);
+}
+
+} // extern "C"

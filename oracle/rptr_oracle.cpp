@@ -1269,6 +1269,23 @@ void oracle_sample_tri_lights(const rptr_tri_light_data *lights, int32_t n_light
     out[3] = ld.x; out[4] = ld.y; out[5] = ld.z;
     out[6] = dist; out[7] = pdf; out[8] = mis;
 }
+void oracle_skymodel_radiance(const rptr_scene_params *sp, const float *sun_dir, const float *view, float *out) {
+    V3 r = skymodel_radiance(*sp, v3(sun_dir[0], sun_dir[1], sun_dir[2]), v3(view[0], view[1], view[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+// the sun branch of sample_direct_light as main_spp writes it (mc/lights_sun.glsl:8-17, lights/sun.glsl:9-20): direction + pdf
+void oracle_sample_sun_dir(const float *sun, float cos_radius, const float *u2, float *out) {
+    V3 sun_dir = v3(sun[0], sun[1], sun[2]);
+    float sn, cs;
+    sincos_pos(TWO_PI_F * u2[0], sn, cs);
+    float cosT = mix(1.0f, cos_radius, u2[1]);
+    float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
+    V3 fx, fy;
+    ortho_basis(fx, fy, sun_dir);
+    V3 d = mat_mul(fx, fy, sun_dir, v3(sinT * cs, sinT * sn, cosT));
+    out[0] = d.x; out[1] = d.y; out[2] = d.z;
+    out[3] = 1.0f / (TWO_PI_F * (1.0f - cos_radius));
+}
 void oracle_sky_illum(const rptr_scene_params *sp, const float *dir, float prev_pdf, float *out) {
     V3 r = compute_sky_illum(*sp, v3(dir[0], dir[1], dir[2]), prev_pdf);
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
