@@ -173,6 +173,47 @@ def gen_vectors(n=512, seed=1234):
             R.ref_sample_sun_dir(fa(*sd), C.c_float(float(sp.sun_cos_angle)), fa(*u4[i, :2]), sun[i].ctypes.data_as(po.f32p))
         out["sky%d_sun_samples" % ci] = sun
     out["sky_dirs"] = sky_dirs
+    # --- material decode with texture handles (rendering/rt/material_textures.glsl:95-145 + gltf_bsdf.glsl:38-62) ---
+    # The reference's unpack_material / get_material_alpha run on 1 x 1 textures; the sampler's return value for an 8-bit texel
+    # is OUR statement of the texture unit (UNORM8 -> v / 255 in float, sRGB colour channels through the transfer function in
+    # double, rounded once), so the fixture holds both the 8-bit texels and the floats handed to the reference.
+    n_tex, n_mat = 12, 320
+    tex8 = rng.integers(0, 256, (n_tex, 4)).astype(np.uint8)
+    tex8[0] = (255, 255, 255, 255)
+    tex8[1] = (10, 200, 30, 0)       # alpha 0: no premultiplied-alpha divide
+    tex8[2] = (128, 64, 32, 1)       # alpha 1/255 > 0.001: divide
+    tex_srgb = (np.arange(n_tex) % 2).astype(np.int32)
+    tex_ch = np.where(np.arange(n_tex) % 5 == 4, 3, 4).astype(np.int32)  # some RGB-only textures: alpha reads 1
+    texf = np.zeros((n_tex, 4), np.float32)
+    for t in range(n_tex):
+        for k in range(4):
+            v = int(tex8[t, k])
+            if k == 3:
+                texf[t, k] = np.float32(v) / np.float32(255.0) if tex_ch[t] == 4 else np.float32(1.0)
+            elif tex_srgb[t]:
+                c = v / 255.0
+                texf[t, k] = np.float32(c / 12.92 if c <= 0.04045 else ((c + 0.055) / 1.055) ** 2.4)
+            else:
+                texf[t, k] = np.float32(v) / np.float32(255.0)
+    mat_words = np.zeros((n_mat, 20), np.uint32)
+    res = np.zeros((2, n_mat, 17), np.float32)
+    for i in range(n_mat):
+        def scalar(lo, hi, p_tex=0.3):
+            if rng.random() < p_tex:
+                return T.texture_handle(int(rng.integers(0, n_tex)), int(rng.integers(0, 4)))
+            return float(np.float32(rng.uniform(lo, hi)))
+        bc = tuple(float(np.float32(x)) for x in rng.random(3))
+        if rng.random() < 0.5:
+            bc = (T.texture_handle(int(rng.integers(0, n_tex))), bc[1], bc[2])
+        m = T.BaseMaterial(base_color=bc, roughness=scalar(0.02, 1.0), metallic=scalar(0.0, 1.0), specular=scalar(0.0, 1.0),
+                           ior=(1.0 if rng.random() < 0.15 else scalar(1.05, 2.2, 0.1)),
+                           specular_transmission=(0.0 if rng.random() < 0.4 else scalar(0.0, 1.0)), clearcoat_gloss=scalar(0.0, 1.0),
+                           emission_intensity=(float(np.float32(rng.uniform(0.5, 30))) if rng.random() < 0.25 else 0.0),
+                           flags=int(rng.integers(0, 16)))
+        mat_words[i] = np.frombuffer(bytes(m), np.uint32)
+        for tr in (0, 1):
+            R.ref_unpack_material(C.byref(m), texf.ctypes.data_as(po.f32p), n_tex, tr, res[tr, i].ctypes.data_as(po.f32p))
+    out.update(mt_tex8=tex8, mt_tex_srgb=tex_srgb, mt_tex_channels=tex_ch, mt_tex_float=texf, mt_materials=mat_words, mt_unpacked=res)
     path = os.path.join(ROOT, "tests", "golden", "ref_vectors.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})

@@ -1269,6 +1269,24 @@ void oracle_sample_tri_lights(const rptr_tri_light_data *lights, int32_t n_light
     out[3] = ld.x; out[4] = ld.y; out[5] = ld.z;
     out[6] = dist; out[7] = pdf; out[8] = mis;
 }
+// unpack_material + get_material_alpha with 8-bit 1 x 1 textures; same output layout as ref_unpack_material
+void oracle_unpack_material(const rptr_base_material *p, const rptr_texture_desc *textures, int n_textures, int transmission, float *out) {
+    TextureSet ts;
+    ts.tex = textures;
+    ts.n = n_textures;
+    GltfMat m;
+    V3 e;
+    std::memset(out, 0, 17 * sizeof(float));
+    out[15] = unpack_material(m, e, *p, transmission != 0, ts);
+    out[16] = material_alpha(ts, *p);
+    out[0] = m.base_color.x; out[1] = m.base_color.y; out[2] = m.base_color.z;
+    out[3] = m.metallic; out[4] = m.specular; out[5] = m.roughness; out[6] = m.ior;
+    if (transmission) {
+        out[7] = m.specular_transmission; out[8] = m.transmission_roughness;
+        out[9] = m.transmission_color.x; out[10] = m.transmission_color.y; out[11] = m.transmission_color.z;
+    }
+    out[12] = e.x; out[13] = e.y; out[14] = e.z;
+}
 void oracle_skymodel_radiance(const rptr_scene_params *sp, const float *sun_dir, const float *view, float *out) {
     V3 r = skymodel_radiance(*sp, v3(sun_dir[0], sun_dir[1], sun_dir[2]), v3(view[0], view[1], view[2]));
     out[0] = r.x; out[1] = r.y; out[2] = r.z;

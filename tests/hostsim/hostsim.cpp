@@ -150,6 +150,22 @@ int hostsim_pointset_replay(int variant, const uint32_t *const *tables, uint32_t
     }
     return n;
 }
+// the product's view of material `mid`: resolve_materials (host, set_scene) followed by the device-side unpack_material;
+// same output layout as ref_unpack_material ([15] = alpha as unpack returns it for the resolved constants, [16] = alpha texel / 255)
+void hostsim_unpack_material(const hostsim_scene *s, int32_t mid, int32_t transmission, float *out) {
+    GltfMat m;
+    float3 e;
+    memset(out, 0, 17 * sizeof(float));
+    out[15] = unpack_material(m, e, s->hs.materials[mid], transmission != 0);
+    out[16] = alpha8_to_float(s->hs.material_alpha8[mid]);
+    out[0] = m.base_color.x; out[1] = m.base_color.y; out[2] = m.base_color.z;
+    out[3] = m.metallic; out[4] = m.specular; out[5] = m.roughness; out[6] = m.ior;
+    if (transmission) {
+        out[7] = m.specular_transmission; out[8] = m.transmission_roughness;
+        out[9] = m.transmission_color.x; out[10] = m.transmission_color.y; out[11] = m.transmission_color.z;
+    }
+    out[12] = e.x; out[13] = e.y; out[14] = e.z;
+}
 void hostsim_halton_23(int32_t k, float *out) { halton_23(k, out); }
 void hostsim_screen_jitter(uint32_t frame_offset, uint32_t frame_id, int32_t w, int32_t h, float *out) { screen_jitter(frame_offset, frame_id, w, h, out); }
 uint32_t hostsim_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, uint32_t tw, uint32_t th, int hash_tile, int hash_sample) {
