@@ -173,6 +173,34 @@ def gen_vectors(n=512, seed=1234):
             R.ref_sample_sun_dir(fa(*sd), C.c_float(float(sp.sun_cos_angle)), fa(*u4[i, :2]), sun[i].ctypes.data_as(po.f32p))
         out["sky%d_sun_samples" % ci] = sun
     out["sky_dirs"] = sky_dirs
+    # --- next-event estimation: rendering/mc/nee.glsl:32-90 (sample_direct_light) executed from the reference ---
+    n_nee = 768
+    nn = unit(rng.normal(size=(n_nee, 3))).astype(np.float32)
+    gnn = unit(nn + 0.25 * rng.normal(size=(n_nee, 3))).astype(np.float32)
+    woo = unit(nn + 0.9 * unit(rng.normal(size=(n_nee, 3)))).astype(np.float32)
+    hpp = (rng.normal(size=(n_nee, 3)) * 2).astype(np.float32)
+    uu = rng.random((n_nee, 4)).astype(np.float32)
+    nee_mats = np.zeros((n_nee, 20), np.uint32)
+    nee_frames = np.zeros((n_nee, 6), np.float32)
+    sp = po.sky_fit(T.SceneConfig(sun_dir=(0.35, 0.8, 0.45)))
+    sun_dir = np.array(list(sp.sun_dir), np.float32)
+    nee_out = np.zeros((2, n_nee, 16), np.float32)
+    for i in range(n_nee):
+        m = T.BaseMaterial(base_color=tuple(float(np.float32(x)) for x in rng.random(3)), roughness=float(np.float32(rng.uniform(0.03, 1.0))),
+                           metallic=float(rng.random() < 0.3) * float(np.float32(rng.random())),
+                           ior=float(1.0 if rng.random() < 0.2 else np.float32(1.05 + rng.random())), specular=float(np.float32(rng.random())),
+                           flags=T.BASE_MATERIAL_NOALPHA)
+        nee_mats[i] = np.frombuffer(bytes(m), np.uint32)
+        vx, vy = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        R.ref_ortho_basis(fa(*nn[i]), vx.ctypes.data_as(po.f32p), vy.ctypes.data_as(po.f32p))
+        nee_frames[i] = np.concatenate([vx, vy])
+        for mode, (p_sun, nl) in enumerate(((1.0, 0), (0.5, n_l))):
+            sr = np.array([sp.sun_radiance[0], sp.sun_radiance[1], sp.sun_radiance[2], p_sun], np.float32)
+            R.ref_sample_direct_light(C.byref(m), fa(*hpp[i]), fa(*gnn[i]), fa(*nn[i]), fa(*vx), fa(*vy), fa(*woo[i]), fa(*uu[i]), fa(*sun_dir),
+                                      C.c_float(float(sp.sun_cos_angle)), fa(*sr), C.cast(larr, C.c_void_p), nl, 16,
+                                      nee_out[mode, i].ctypes.data_as(po.f32p))
+    out.update(nee_mat=nee_mats, nee_p=hpp, nee_gn=gnn, nee_n=nn, nee_wo=woo, nee_u4=uu, nee_frames=nee_frames, nee_sun_dir=sun_dir,
+               nee_sun_cos=np.float32(sp.sun_cos_angle), nee_sun_rgb=np.array(list(sp.sun_radiance)[:3], np.float32), nee_out=nee_out)
     # --- material decode with texture handles (rendering/rt/material_textures.glsl:95-145 + gltf_bsdf.glsl:38-62) ---
     # The reference's unpack_material / get_material_alpha run on 1 x 1 textures; the sampler's return value for an 8-bit texel
     # is OUR statement of the texture unit (UNORM8 -> v / 255 in float, sRGB colour channels through the transfer function in

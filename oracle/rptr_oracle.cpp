@@ -796,6 +796,52 @@ static bool test_visibility(const Frame &f, V3 from, V3 dir, float dist, float g
 
 // main_spp: vulkan/pt_megakernel.glsl:310-737, shade_base_material (rendering/mc/shade_base_material.glsl:14-96),
 // sample_direct_light (rendering/mc/nee.glsl:32-90).  Returns vec4(illum, bounce == 0 ? 0 : 1).
+// sample_direct_light: rendering/mc/nee.glsl:32-90 with sample_sun_light (mc/lights_sun.glsl:8-17, lights/sun.glsl:9-20) and
+// sample_tri_lights; `visible(from, dir, dist)` is raytrace_test_visibility.  contrib excludes the path throughput.
+struct NeeSample { V3 contrib, light_dir; float light_dist, mis_pdf; };
+template <class Vis>
+static NeeSample sample_direct_light(const Frame &f, const GltfMat &mat, V3 ip, V3 ign, V3 in_, V3 w_o, V2 dir_sample, V2 sel_sample, Vis &&visible) {
+    const rptr_scene_params &sp = f.sp;
+    const float p_sun = sp.sun_radiance[3];
+    V3 sun_dir = v3(sp.sun_dir[0], sp.sun_dir[1], sp.sun_dir[2]);
+    V3 sun_rgb = v3(sp.sun_radiance[0], sp.sun_radiance[1], sp.sun_radiance[2]);
+    V3 li = v3(0.0f), light_dir = v3(0.0f);
+    float light_dist = 2.e16f, light_pdf = 0.0f, mis_pdf = 0.0f;
+    if (sel_sample.x <= p_sun) {
+        sel_sample.x /= p_sun;
+        float sn, cs;
+        sincos_pos(TWO_PI_F * dir_sample.x, sn, cs);
+        float cosT = mix(1.0f, sp.sun_cos_angle, dir_sample.y);
+        float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
+        V3 fx, fy;
+        ortho_basis(fx, fy, sun_dir);
+        light_dir = mat_mul(fx, fy, sun_dir, v3(sinT * cs, sinT * sn, cosT));
+        float pdf = 1.0f / (TWO_PI_F * (1.0f - sp.sun_cos_angle));
+        li = li + (v3(1.0f) / pdf) * (sun_rgb / p_sun);
+        light_pdf = pdf * p_sun;
+        mis_pdf = light_pdf;
+    } else {
+        sel_sample.x = (sel_sample.x - p_sun) / (1.0f - p_sun);
+        float tri_mis = 0.0f;
+        li = li + sample_tri_lights(f, ip, in_, dir_sample, sel_sample, light_dir, light_dist, light_pdf, tri_mis) / (1.0f - p_sun);
+        light_pdf *= 1.0f - p_sun;
+        mis_pdf = tri_mis * (1.0f - p_sun);
+    }
+    NeeSample r;
+    r.contrib = v3(0.0f); r.light_dir = light_dir; r.light_dist = light_dist; r.mis_pdf = 0.0f;
+    if (light_pdf > 0.0f && dot(light_dir, ign) * dot(light_dir, in_) > 0.0f) {
+        bool vis = visible(ip, light_dir, light_dist);
+        float bsdf_pdf = gltf_wpdf(mat, in_, w_o, light_dir, f.tr);
+        if (bsdf_pdf >= 0.0f && vis) {
+            V3 bsdf = gltf_bsdf(mat, in_, w_o, light_dir, f.tr);
+            float w = nee_mis_heuristic(1.0f, mis_pdf, 1.0f, bsdf_pdf);
+            r.contrib = li * (bsdf * (w * fabsf(dot(light_dir, in_))));
+            r.mis_pdf = mis_pdf;
+        }
+    }
+    return r;
+}
+
 // RANDOM_STATE of the selected pointset (rendering/pointsets/selected_rng.glsl) + the separate LCG the megakernel keeps
 // for stochastic alpha when the pointset is not the LCG (pt_megakernel.glsl:354-358)
 struct PathRng {
@@ -952,39 +998,10 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
             dir_sample.y = rng.draw(3);
             sel_sample.x = rng.draw(0); // DIM_LIGHT_SEL_1
             sel_sample.y = rng.draw(1);
-            V3 li = v3(0.0f), light_dir = v3(0.0f);
-            float light_dist = 2.e16f, light_pdf = 0.0f, mis_pdf = 0.0f;
-            if (sel_sample.x <= p_sun) {
-                sel_sample.x /= p_sun;
-                // sample_sun_light: mc/lights_sun.glsl:8-17, lights/sun.glsl:9-20
-                float sn, cs;
-                sincos_pos(TWO_PI_F * dir_sample.x, sn, cs);
-                float cosT = mix(1.0f, sp.sun_cos_angle, dir_sample.y);
-                float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
-                V3 fx, fy;
-                ortho_basis(fx, fy, sun_dir);
-                light_dir = mat_mul(fx, fy, sun_dir, v3(sinT * cs, sinT * sn, cosT));
-                float pdf = 1.0f / (TWO_PI_F * (1.0f - sp.sun_cos_angle));
-                li = li + (v3(1.0f) / pdf) * (sun_rgb / p_sun);
-                light_pdf = pdf * p_sun;
-                mis_pdf = light_pdf;
-            } else {
-                sel_sample.x = (sel_sample.x - p_sun) / (1.0f - p_sun);
-                float tri_mis = 0.0f;
-                li = li + sample_tri_lights(f, ip, in_, dir_sample, sel_sample, light_dir, light_dist, light_pdf, tri_mis) / (1.0f - p_sun);
-                light_pdf *= 1.0f - p_sun;
-                mis_pdf = tri_mis * (1.0f - p_sun);
-            }
-            V3 contrib = v3(0.0f);
-            if (light_pdf > 0.0f && dot(light_dir, ign) * dot(light_dir, in_) > 0.0f) {
-                bool vis = test_visibility(f, ip, light_dir, light_dist, geometry_scale, linear, view_frame_id, cnt);
-                float bsdf_pdf = gltf_wpdf(mat, in_, w_o, light_dir, f.tr);
-                if (bsdf_pdf >= 0.0f && vis) {
-                    V3 bsdf = gltf_bsdf(mat, in_, w_o, light_dir, f.tr);
-                    float w = nee_mis_heuristic(1.0f, mis_pdf, 1.0f, bsdf_pdf);
-                    contrib = li * (bsdf * (w * fabsf(dot(light_dir, in_))));
-                }
-            }
+            NeeSample ns = sample_direct_light(f, mat, ip, ign, in_, w_o, dir_sample, sel_sample, [&](V3 from, V3 dir, float dist) {
+                return test_visibility(f, from, dir, dist, geometry_scale, linear, view_frame_id, cnt);
+            });
+            V3 contrib = ns.contrib;
             illum = illum + throughput * contrib;
         }
         rng.shift_dim(4); // RANDOM_SHIFT_DIM(rng, DIM_LIGHT_END), shade_base_material.glsl:66
@@ -1268,6 +1285,45 @@ void oracle_sample_tri_lights(const rptr_tri_light_data *lights, int32_t n_light
     out[0] = L.x; out[1] = L.y; out[2] = L.z;
     out[3] = ld.x; out[4] = ld.y; out[5] = ld.z;
     out[6] = dist; out[7] = pdf; out[8] = mis;
+}
+// sample_direct_light for a constants-only material (no transmission); same argument / output layout as ref_sample_direct_light
+void oracle_sample_direct_light(const rptr_base_material *p, const float *hp, const float *gn, const float *n, const float *vx, const float *vy,
+                                const float *wo, const float *u4, const float *sun_dir, float sun_cos_angle, const float *sun_radiance,
+                                const rptr_tri_light_data *lights, int n_lights, int bin_size, float *out) {
+    (void)vx; (void)vy;
+    oracle_scene os;
+    if (n_lights > 0) os.s.lights.assign(lights, lights + n_lights);
+    oracle_render_args a;
+    std::memset(&a, 0, sizeof(a));
+    a.lighting.bin_size = bin_size;
+    Frame f;
+    f.s = &os.s;
+    f.a = &a;
+    std::memset(&f.sp, 0, sizeof(f.sp));
+    for (int k = 0; k < 3; ++k) f.sp.sun_dir[k] = sun_dir[k];
+    f.sp.sun_cos_angle = sun_cos_angle;
+    for (int k = 0; k < 4; ++k) f.sp.sun_radiance[k] = sun_radiance[k];
+    f.n_lights = n_lights;
+    f.n_bins = bin_size > 0 ? (n_lights + bin_size - 1) / bin_size : 0;
+    f.tr = false;
+    GltfMat m;
+    V3 e;
+    unpack_material(m, e, *p, false, TextureSet());
+    int queries = 0;
+    V3 qf = v3(0.0f), qd = v3(0.0f);
+    float qdist = 0.0f;
+    NeeSample r = sample_direct_light(f, m, v3(hp[0], hp[1], hp[2]), v3(gn[0], gn[1], gn[2]), v3(n[0], n[1], n[2]), v3(wo[0], wo[1], wo[2]),
+                                      V2{u4[0], u4[1]}, V2{u4[2], u4[3]}, [&](V3 from, V3 dir, float dist) {
+                                          ++queries; qf = from; qd = dir; qdist = dist;
+                                          return true;
+                                      });
+    std::memset(out, 0, 16 * sizeof(float));
+    out[0] = r.contrib.x; out[1] = r.contrib.y; out[2] = r.contrib.z;
+    if (r.mis_pdf != 0.0f) { // the reference fills aux_info only when it returns a contribution
+        out[3] = r.light_dir.x; out[4] = r.light_dir.y; out[5] = r.light_dir.z; out[6] = r.light_dist;
+    }
+    out[7] = r.mis_pdf; out[8] = (float)queries;
+    out[9] = qf.x; out[10] = qf.y; out[11] = qf.z; out[12] = qd.x; out[13] = qd.y; out[14] = qd.z; out[15] = qdist;
 }
 // unpack_material + get_material_alpha with 8-bit 1 x 1 textures; same output layout as ref_unpack_material
 void oracle_unpack_material(const rptr_base_material *p, const rptr_texture_desc *textures, int n_textures, int transmission, float *out) {
