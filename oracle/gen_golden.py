@@ -201,6 +201,42 @@ def gen_vectors(n=512, seed=1234):
                                       nee_out[mode, i].ctypes.data_as(po.f32p))
     out.update(nee_mat=nee_mats, nee_p=hpp, nee_gn=gnn, nee_n=nn, nee_wo=woo, nee_u4=uu, nee_frames=nee_frames, nee_sun_dir=sun_dir,
                nee_sun_cos=np.float32(sp.sun_cos_angle), nee_sun_rgb=np.array(list(sp.sun_radiance)[:3], np.float32), nee_out=nee_out)
+    # --- the whole per-vertex shading function: rendering/mc/shade_base_material.glsl:14-96 executed from the reference ---
+    n_sh = 1024
+    sh_n = unit(rng.normal(size=(n_sh, 3))).astype(np.float32)
+    sh_gn = unit(sh_n + 0.2 * rng.normal(size=(n_sh, 3))).astype(np.float32)
+    sh_wo = unit(sh_n + 0.9 * unit(rng.normal(size=(n_sh, 3)))).astype(np.float32)
+    sh_p = (rng.normal(size=(n_sh, 3)) * 2).astype(np.float32)
+    sh_ia = np.zeros((n_sh, 15), np.float32)
+    sh_mat = np.zeros((n_sh, 20), np.uint32)
+    sh_state = np.zeros((n_sh, 12), np.float32)   # bounce, output_channel, prev_pdf, illum3, thr3, approx_sa, max_depth, glossy_only
+    sh_rng = rng.integers(0, 2 ** 32, n_sh, dtype=np.uint64).astype(np.uint32)
+    sh_out = np.zeros((2, n_sh, 19), np.float32)
+    for i in range(n_sh):
+        emissive = rng.random() < 0.15
+        m = T.BaseMaterial(base_color=tuple(float(np.float32(x)) for x in rng.random(3)), roughness=float(np.float32(rng.uniform(0.03, 1.0))),
+                           metallic=float(rng.random() < 0.3) * float(np.float32(rng.random())),
+                           ior=float(1.0 if rng.random() < 0.2 else np.float32(1.05 + rng.random())), specular=float(np.float32(rng.random())),
+                           emission_intensity=float(np.float32(rng.uniform(1, 30))) if emissive else 0.0, flags=T.BASE_MATERIAL_NOALPHA)
+        sh_mat[i] = np.frombuffer(bytes(m), np.uint32)
+        vx, vy = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        R.ref_ortho_basis(fa(*sh_n[i]), vx.ctypes.data_as(po.f32p), vy.ctypes.data_as(po.f32p))
+        sh_ia[i] = np.concatenate([sh_p[i], sh_gn[i], sh_n[i], vx, vy])
+        bounce = int(rng.integers(0, 5))
+        channel = int(rng.integers(1, 4)) if rng.random() < 0.1 else 0
+        prev_pdf = float(np.float32(2.e16 if bounce == 0 else 10.0 ** rng.uniform(-2, 3)))
+        il = (rng.random(3) * (bounce > 0)).astype(np.float32)
+        thr = (rng.random(3) ** 2).astype(np.float32) if bounce else np.ones(3, np.float32)
+        sa = float(np.float32(10.0 ** rng.uniform(-5, -1)))
+        max_depth = int(rng.choice([9, 9, 9, bounce + 1, bounce + 2]))
+        glossy = int(rng.random() < 0.1)
+        sh_state[i] = [bounce, channel, prev_pdf, *il, *thr, sa, max_depth, glossy]
+        for mode, (p_sun, nl) in enumerate(((1.0, 0), (0.5, n_l))):
+            sr = np.array([sp.sun_radiance[0], sp.sun_radiance[1], sp.sun_radiance[2], p_sun], np.float32)
+            R.ref_shade_base_material(C.byref(m), bounce, channel, C.c_float(prev_pdf), fa(*il), fa(*thr), C.c_float(sa), fa(*sh_wo[i]), fa(*sh_ia[i]),
+                                      int(sh_rng[i]), max_depth, glossy, fa(*sun_dir), C.c_float(float(sp.sun_cos_angle)), fa(*sr),
+                                      C.cast(larr, C.c_void_p), nl, 16, sh_out[mode, i].ctypes.data_as(po.f32p))
+    out.update(sh_mat=sh_mat, sh_ia=sh_ia, sh_wo=sh_wo, sh_state=sh_state, sh_rng=sh_rng, sh_out=sh_out)
     # --- material decode with texture handles (rendering/rt/material_textures.glsl:95-145 + gltf_bsdf.glsl:38-62) ---
     # The reference's unpack_material / get_material_alpha run on 1 x 1 textures; the sampler's return value for an 8-bit texel
     # is OUR statement of the texture unit (UNORM8 -> v / 255 in float, sRGB colour channels through the transfer function in

@@ -75,6 +75,7 @@ def lib():
         L.oracle_gltf_wpdf.restype = C.c_float
         L.oracle_hit_attributes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, f32p]
         L.oracle_sky_illum.argtypes = [C.POINTER(T.SceneParams), f32p, C.c_float, f32p]
+        L.oracle_shade_base_material.argtypes = [C.POINTER(T.BaseMaterial), C.c_int, C.c_int, C.c_float, f32p, f32p, C.c_float, f32p, f32p, C.c_uint32, C.c_int, C.c_int, f32p, C.c_float, f32p, C.c_void_p, C.c_int, C.c_int, f32p]
         L.oracle_sample_direct_light.argtypes = [C.POINTER(T.BaseMaterial)] + [f32p] * 8 + [C.c_float, f32p, C.c_void_p, C.c_int, C.c_int, f32p]
         L.oracle_unpack_material.argtypes = [C.POINTER(T.BaseMaterial), C.POINTER(T.TextureDesc), C.c_int, C.c_int, f32p]
         L.oracle_skymodel_radiance.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, f32p]
@@ -108,6 +109,7 @@ def ref():
         R.ref_dequantize_normal.argtypes = [C.c_uint32, f32p]
         R.ref_dequantize_uv.argtypes = [C.c_uint32, f32p]
         R.ref_sky_fit.argtypes = [C.POINTER(T.SceneConfig), C.POINTER(T.SceneParams)]
+        R.ref_shade_base_material.argtypes = [C.POINTER(T.BaseMaterial), C.c_int, C.c_int, C.c_float, f32p, f32p, C.c_float, f32p, f32p, C.c_uint32, C.c_int, C.c_int, f32p, C.c_float, f32p, C.c_void_p, C.c_int, C.c_int, f32p]
         R.ref_sample_direct_light.argtypes = [C.POINTER(T.BaseMaterial)] + [f32p] * 8 + [C.c_float, f32p, C.c_void_p, C.c_int, C.c_int, f32p]
         R.ref_unpack_material.argtypes = [C.POINTER(T.BaseMaterial), f32p, C.c_int, C.c_int, f32p]
         R.ref_skymodel_radiance.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, f32p]

@@ -40,8 +40,7 @@ template <class T> struct tvec3 {
 template <class T> struct tvec4 {
     // .xy is the one GLSL swizzle the Z-order Sobol sampler needs (rendering/pointsets/sobol.glsl:174)
     union { struct { union { T x, r; }; union { T y, g; }; }; tvec2<T> xy; };
-    union { T z, b; };
-    union { T w, a; };
+    union { struct { union { T z, b; }; union { T w, a; }; }; tvec2<T> zw; }; // .zw: rendering/mc/shade_base_material.glsl:64
     tvec4() : x(0), y(0), z(0), w(0) {}
     tvec4(T s) : x(s), y(s), z(s), w(s) {}
     tvec4(T a_, T b_, T c, T d) : x(a_), y(b_), z(c), w(d) {}

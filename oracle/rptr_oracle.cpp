@@ -858,6 +858,60 @@ struct PathRng {
 // (vulkan/accumulate.glsl:89-103), as floats: [0..3] = albedo.rgb, roughness; [4..7] = normal.xyz, depth
 struct AovOut { float v[8]; };
 
+// shade_base_material: rendering/mc/shade_base_material.glsl:14-96 (material unpack, emitter MIS, AOV channels, path-length
+// cut, NEE, glossy-only cut, BSDF sampling with its draw order, bounce counting).  Returns SHADING_RESULT_*.
+enum { SHADING_RESULT_TERMINATE = -1, SHADING_RESULT_BOUNCE = 1 };
+template <class Vis>
+static int shade_base_material(const Frame &f, int &bounce, float &prev_bounce_pdf, V3 &illum, V3 &throughput, const rptr_base_material &mp,
+                               float approx_sa, V3 w_o, V3 ip, V3 ign, V3 in_, V3 v_x, V3 v_y, PathRng &rng, V3 &w_i, AovOut *aov, Vis &&visible) {
+    const oracle_render_args &a = *f.a;
+    const float p_sun = f.sp.sun_radiance[3];
+    GltfMat mat;
+    V3 emit;
+    unpack_material(mat, emit, mp, f.tr, f.s->texset);
+    if (aov && bounce == 0) { // pt_megakernel.glsl:670-672 + shade_base_material.glsl:28-31
+        const V3 alb = throughput * mat.base_color;
+        const float m[8] = {alb.x, alb.y, alb.z, mat.ior != 1.0f ? mat.roughness : 1.0f, in_.x, in_.y, in_.z, length(ip - f.cam_pos)};
+        std::memcpy(aov->v, m, sizeof(m));
+    }
+    if (a.params.output_channel == 0 && !is_zero(emit)) { // :33-39
+        float light_pdf = (1.0f - p_sun) * (1.0f / ((float)f.n_bins * approx_sa));
+        float w = nee_mis_heuristic(1.0f, prev_bounce_pdf, 1.0f, light_pdf);
+        illum = illum + throughput * w * emit;
+    }
+    if (a.params.output_channel != 0) { // AOV channels, :42-53; pow(0.25, bounce) is an exact power of two
+        float reliability = u2f((uint32_t)(127 - 2 * bounce) << 23);
+        if (a.params.output_channel == 1) illum = illum + throughput * mat.base_color * reliability;
+        else if (a.params.output_channel == 2) illum = illum + in_ * reliability;
+        else if (a.params.output_channel == 3) illum = illum + ip * reliability;
+    }
+    if (bounce + 1 >= a.params.max_path_depth) return SHADING_RESULT_TERMINATE; // :56-57
+    if (a.params.output_channel == 0) { // :59-65, nee.glsl:32-90
+        V2 dir_sample, sel_sample;
+        dir_sample.x = rng.draw(2); // DIM_POSITION_X
+        dir_sample.y = rng.draw(3);
+        sel_sample.x = rng.draw(0); // DIM_LIGHT_SEL_1
+        sel_sample.y = rng.draw(1);
+        NeeSample ns = sample_direct_light(f, mat, ip, ign, in_, w_o, dir_sample, sel_sample, visible);
+        illum = illum + throughput * ns.contrib;
+    }
+    rng.shift_dim(4); // RANDOM_SHIFT_DIM(rng, DIM_LIGHT_END), :66
+    if (a.params.glossy_only_mode != 0 && !(mat.roughness < RPTR_GLOSSY_MODE_ROUGHNESS_THRESHOLD && mat.ior != 1.0f)) return SHADING_RESULT_TERMINATE;
+    V2 lobe, dirs;
+    lobe.x = rng.draw(2); // DIM_LOBE
+    lobe.y = rng.draw(3);
+    dirs.x = rng.draw(0); // DIM_DIRECTION_X
+    dirs.y = rng.draw(1);
+    float sampling_pdf = 0.0f, mis_wpdf = 0.0f;
+    V3 bsdf = sample_gltf_brdf(mat, in_, w_o, w_i, sampling_pdf, mis_wpdf, dirs, lobe, v_x, v_y, f.tr);
+    rng.shift_dim(4); // DIM_VERTEX_END, :82
+    ++bounce;
+    if (mis_wpdf == 0.0f || is_zero(bsdf) || !(dot(w_i, in_) * dot(w_i, ign) > 0.0f)) return SHADING_RESULT_TERMINATE;
+    throughput = throughput * bsdf;
+    prev_bounce_pdf = mis_wpdf;
+    return SHADING_RESULT_BOUNCE;
+}
+
 static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32_t view_frame_id, Counters &cnt, AovOut *aov = nullptr) {
     const oracle_render_args &a = *f.a;
     const Scene &s = *f.s;
@@ -972,53 +1026,14 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         V3 v_x = cross(v_y, in_);
 
         // ---- shade_base_material ----
-        GltfMat mat;
-        V3 emit;
-        unpack_material(mat, emit, mp, f.tr, s.texset);
-        if (aov && bounce == 0) { // pt_megakernel.glsl:670-672 + shade_base_material.glsl:28-31
-            const V3 alb = throughput * mat.base_color;
-            const float m[8] = {alb.x, alb.y, alb.z, mat.ior != 1.0f ? mat.roughness : 1.0f, in_.x, in_.y, in_.z, length(ip - f.cam_pos)};
-            std::memcpy(aov->v, m, sizeof(m));
-        }
-        if (a.params.output_channel == 0 && !is_zero(emit)) { // :33-39
-            float light_pdf = (1.0f - p_sun) * (1.0f / ((float)f.n_bins * approx_sa));
-            float w = nee_mis_heuristic(1.0f, prev_bounce_pdf, 1.0f, light_pdf);
-            illum = illum + throughput * w * emit;
-        }
-        if (a.params.output_channel != 0) { // AOV channels, :42-53; pow(0.25, bounce) is an exact power of two
-            float reliability = u2f((uint32_t)(127 - 2 * bounce) << 23);
-            if (a.params.output_channel == 1) illum = illum + throughput * mat.base_color * reliability;
-            else if (a.params.output_channel == 2) illum = illum + in_ * reliability;
-            else if (a.params.output_channel == 3) illum = illum + ip * reliability;
-        }
-        if (bounce + 1 >= a.params.max_path_depth) break; // :56-57
-        if (a.params.output_channel == 0) { // :59-65, nee.glsl:32-90
-            V2 dir_sample, sel_sample;
-            dir_sample.x = rng.draw(2); // DIM_POSITION_X
-            dir_sample.y = rng.draw(3);
-            sel_sample.x = rng.draw(0); // DIM_LIGHT_SEL_1
-            sel_sample.y = rng.draw(1);
-            NeeSample ns = sample_direct_light(f, mat, ip, ign, in_, w_o, dir_sample, sel_sample, [&](V3 from, V3 dir, float dist) {
-                return test_visibility(f, from, dir, dist, geometry_scale, linear, view_frame_id, cnt);
-            });
-            V3 contrib = ns.contrib;
-            illum = illum + throughput * contrib;
-        }
-        rng.shift_dim(4); // RANDOM_SHIFT_DIM(rng, DIM_LIGHT_END), shade_base_material.glsl:66
-        if (a.params.glossy_only_mode != 0 && !(mat.roughness < RPTR_GLOSSY_MODE_ROUGHNESS_THRESHOLD && mat.ior != 1.0f)) break;
-        V2 lobe, dirs;
-        lobe.x = rng.draw(2); // DIM_LOBE
-        lobe.y = rng.draw(3);
-        dirs.x = rng.draw(0); // DIM_DIRECTION_X
-        dirs.y = rng.draw(1);
         V3 w_i;
-        float sampling_pdf = 0.0f, mis_wpdf = 0.0f;
-        V3 bsdf = sample_gltf_brdf(mat, in_, w_o, w_i, sampling_pdf, mis_wpdf, dirs, lobe, v_x, v_y, f.tr);
-        rng.shift_dim(4); // DIM_VERTEX_END, :82
-        ++bounce;
-        if (mis_wpdf == 0.0f || is_zero(bsdf) || !(dot(w_i, in_) * dot(w_i, ign) > 0.0f)) break;
-        throughput = throughput * bsdf;
-        prev_bounce_pdf = mis_wpdf;
+        {
+            const int result = shade_base_material(f, bounce, prev_bounce_pdf, illum, throughput, mp, approx_sa, w_o, ip, ign, in_, v_x, v_y, rng, w_i, aov,
+                                                   [&](V3 from, V3 dir, float dist) {
+                                                       return test_visibility(f, from, dir, dist, geometry_scale, linear, view_frame_id, cnt);
+                                                   });
+            if (result != SHADING_RESULT_BOUNCE) break;
+        }
         // next ray: pt_megakernel.glsl:703-709
         ray_dir = w_i;
         ray_origin = ip;
@@ -1285,6 +1300,55 @@ void oracle_sample_tri_lights(const rptr_tri_light_data *lights, int32_t n_light
     out[0] = L.x; out[1] = L.y; out[2] = L.z;
     out[3] = ld.x; out[4] = ld.y; out[5] = ld.z;
     out[6] = dist; out[7] = pdf; out[8] = mis;
+}
+// shade_base_material for a constants-only material with the LCG pointset; same argument / output layout as ref_shade_base_material
+void oracle_shade_base_material(const rptr_base_material *p, int bounce, int output_channel, float prev_bounce_pdf, const float *illum,
+                                const float *throughput, float approx_sa, const float *wo, const float *ia, uint32_t rng_state, int max_path_depth,
+                                int glossy_only_mode, const float *sun_dir, float sun_cos_angle, const float *sun_radiance,
+                                const rptr_tri_light_data *lights, int n_lights, int bin_size, float *out) {
+    oracle_scene os;
+    if (n_lights > 0) os.s.lights.assign(lights, lights + n_lights);
+    oracle_render_args a;
+    std::memset(&a, 0, sizeof(a));
+    a.lighting.bin_size = bin_size;
+    a.params.max_path_depth = max_path_depth;
+    a.params.glossy_only_mode = glossy_only_mode;
+    a.params.output_channel = output_channel;
+    Frame f;
+    f.s = &os.s;
+    f.a = &a;
+    std::memset(&f.sp, 0, sizeof(f.sp));
+    for (int k = 0; k < 3; ++k) f.sp.sun_dir[k] = sun_dir[k];
+    f.sp.sun_cos_angle = sun_cos_angle;
+    for (int k = 0; k < 4; ++k) f.sp.sun_radiance[k] = sun_radiance[k];
+    f.n_lights = n_lights;
+    f.n_bins = bin_size > 0 ? (n_lights + bin_size - 1) / bin_size : 0;
+    f.tr = false;
+    f.cam_pos = v3(0.0f);
+    PathRng rng;
+    rng.lcg.state = rng_state;
+    rng.alpha = rng.lcg;
+    rng.qmc = false;
+    V3 il = v3(illum[0], illum[1], illum[2]), thr = v3(throughput[0], throughput[1], throughput[2]), w_i = v3(0.0f);
+    int queries = 0;
+    V3 qd = v3(0.0f);
+    float qdist = 0.0f;
+    const float pdf_before = prev_bounce_pdf;
+    const int result = shade_base_material(f, bounce, prev_bounce_pdf, il, thr, *p, approx_sa, v3(wo[0], wo[1], wo[2]), v3(ia[0], ia[1], ia[2]),
+                                           v3(ia[3], ia[4], ia[5]), v3(ia[6], ia[7], ia[8]), v3(ia[9], ia[10], ia[11]), v3(ia[12], ia[13], ia[14]), rng,
+                                           w_i, nullptr, [&](V3, V3 dir, float dist) {
+                                               ++queries; qd = dir; qdist = dist;
+                                               return true;
+                                           });
+    std::memset(out, 0, 19 * sizeof(float));
+    out[0] = (float)result; out[1] = (float)bounce; out[2] = prev_bounce_pdf;
+    out[3] = il.x; out[4] = il.y; out[5] = il.z; out[6] = thr.x; out[7] = thr.y; out[8] = thr.z;
+    out[9] = w_i.x; out[10] = w_i.y; out[11] = w_i.z;
+    out[12] = result == SHADING_RESULT_BOUNCE ? prev_bounce_pdf : 0.0f; // aux.mis_pdf; (void)pdf_before
+    (void)pdf_before;
+    std::memcpy(&out[13], &rng.lcg.state, 4);
+    out[14] = (float)queries;
+    out[15] = qd.x; out[16] = qd.y; out[17] = qd.z; out[18] = qdist;
 }
 // sample_direct_light for a constants-only material (no transmission); same argument / output layout as ref_sample_direct_light
 void oracle_sample_direct_light(const rptr_base_material *p, const float *hp, const float *gn, const float *n, const float *vx, const float *vy,
