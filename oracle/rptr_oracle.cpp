@@ -2,12 +2,17 @@
 // tracing loop (PT_MEGAKERNEL with the LCG sampler).  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may load this library; the product (librptr_cuda.so) never does.
 //
-// PARITY STATUS: the reference ships no golden vectors, scenes or images for this path, and
-// its traversal/intersection and GLSL built-ins live in the Vulkan driver.  The functions the reference can
-// execute as C++ (BSDF, LCG, triangle lights, hit attributes, sky fit, light binning) are pinned against
-// oracle/_ref (the reference's own sources compiled from /root/reference, see oracle/Makefile) in
-// tests/test_oracle_vs_ref.py and through tests/golden/.  The GLSL-only driver loop below (pt_megakernel.glsl,
-// shade_base_material.glsl, nee.glsl) and the ray/triangle routine are restatements: "parity unpinned" for those.
+// PARITY STATUS: the reference ships no golden vectors, scenes or images for this path, and its
+// traversal/intersection and GLSL built-ins live in the Vulkan driver.  Everything the reference can execute as C++ is pinned
+// against oracle/_ref (the reference's own sources compiled from /root/reference, see oracle/Makefile and oracle/ref_shim/)
+// through the fixtures of tests/golden/ (tests/test_oracle_golden.py, tests/test_pointsets.py): LCG / murmur, the Sobol /
+// Z-order Sobol / blue-noise samplers and their tables, the Halton screen jitter, dequantisation, hit attributes, the glTF BSDF
+// (with and without transmission), triangle-light solid angles / sampling / binned RIS, host light binning, the sky fit and
+// skymodel_radiance, sun sampling, the material decode with texture handles, sample_direct_light (nee.glsl) and the complete
+// per-vertex shading function shade_base_material() with its LCG draw order.
+// "PARITY UNPINNED" (restated only, no reference-executed check possible): the loop of pt_megakernel.glsl around that function
+// (ray generation, normal fix-ups, ray epsilons, Russian roulette, sky on a miss), process_samples.comp / accumulate.glsl, the
+// texture unit (UNORM8 / sRGB decode of a texel), and the ray/triangle routine, which the reference does not contain at all.
 //
 // Structure follows the reference megakernel (one sequential loop per pixel sample), NOT the CUDA wavefront.
 #include "shading_oracle.h"
