@@ -1,2 +1,9 @@
-for v in base s256x2 s128x8 s128x2 s64x8 chunk128 chunk512 cpw8; do RPTR_CUDA_LIB=variants/librptr_cuda_$v.so timeout 300 python bench.py --no-cpu-baseline --steps 2 --warmup 2 > gpurun_out/sweep_$v.json 2> gpurun_out/sweep_$v.err || tail -2 gpurun_out/sweep_$v.err; python -c "
-import json; j=json.load(open('gpurun_out/sweep_$v.json')); r=j['roofline']; print('var', '$v', round(j['value'],1), {k: round(x,1) for k,x in r['stage_ms_rank0'].items()})"; done
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/t.log 2>&1; tail -2 gpurun_out/t.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 600 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; python -c "
+import json; j=json.load(open('gpurun_out/bench_full.json')); r=j['roofline']; print('c2', j['value'], j['e2e']['value'], r['frac'], r['traffic'], r['stage_ms_rank0'], j['cpu_baseline']['value'], j['config']['scene_setup_s'], j['gpu_launches'])"
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cut -c1-300 gpurun_out/bench_ref.json
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 2 -f -o gpurun_out/trace_full \
+    python bench.py --steps 1 --warmup 0 --spp 4 --no-cpu-baseline > gpurun_out/b_ncu2.log 2>&1
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_trace_persistent -c 40 --csv \
+   --log-file gpurun_out/trace_dram.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/b_ncu4.log 2>&1

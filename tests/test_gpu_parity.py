@@ -603,3 +603,25 @@ def test_ldr_framebuffer_readback(oracle):
     want2 = to_srgb8(nd[..., :3] * 0.5 + 0.5, np.where(np.isfinite(nd[..., 3]), nd[..., 3], 1.0))
     assert np.abs(ldr2[..., :3].astype(np.int32) - want2[..., :3]).max() <= 1
     assert not np.array_equal(ldr, ldr2)
+
+
+def test_resize_and_scene_swap_on_one_context(oracle):
+    """initialize() may be called again (window resize / upscale, libapp/shell.cpp:51-94) and set_scene() again (scene reload):
+    frame buffers, AOV images, wave buffers, BVH and the alpha / multi-path kernel selection all follow."""
+    a = scenes.random_triangles(20000)
+    b = scenes.alpha_tested_soup(8000)
+    sp = load_sky_fit()
+    r = make_backend(a, 160, 90)
+    r.render_spp(a.camera, 2)
+    assert_identical(r.framebuffer(), oracle.OracleScene(a).render(160, 90, a.camera, sp, spp=2)[0], "first size")
+    r.initialize(240, 100)  # larger: every per-pixel and per-path buffer grows
+    r.render_spp(a.camera, 2)
+    assert r.get_framebuffer_size() == (240, 100, 4)
+    assert_identical(r.framebuffer(), oracle.OracleScene(a).render(240, 100, a.camera, sp, spp=2)[0], "after resize")
+    assert r.aov(1).shape == (100, 240, 4)
+    r.set_scene(b)  # alpha-tested, textured, normal-mapped materials: other trace / shade variants on the same context
+    r.render_spp(b.camera, 2)
+    assert_identical(r.framebuffer(), oracle.OracleScene(b).render(240, 100, b.camera, sp, spp=2)[0], "after scene swap")  # set_scene zeroed frame_id
+    r.initialize(64, 64)  # smaller again
+    r.render_spp(b.camera, 1)
+    assert_identical(r.framebuffer(), oracle.OracleScene(b).render(64, 64, b.camera, sp, spp=1)[0], "after shrinking")
