@@ -25,6 +25,10 @@
 
 using namespace rp;
 
+#ifndef RPTR_IMPLIED_INITIAL_STATE
+#define RPTR_IMPLIED_INITIAL_STATE 0 // see k_raygen
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // device-side buffers
 // ---------------------------------------------------------------------------------------------------------------------
@@ -110,10 +114,15 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave
         const int32_t py = local_row_to_global(tm, lp / tm.width);
         PathState ps;
         generate_primary(fp, px, py, fp.first_sample + (uint32_t)(first_layer + layer), ps);
+        // RPTR_IMPLIED_INITIAL_STATE: thr = (1, 1, 1, prev_pdf = 2e16) and illum = 0 are implied for a path that has not been
+        // shaded yet (bounce counter 0): the first shade launch and the resolve kernel substitute them instead of reading 32
+        // bytes raygen would have to write
         w.ray_o[slot] = f4(ps.o.x, ps.o.y, ps.o.z, ps.tmin);
         w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
+#if !RPTR_IMPLIED_INITIAL_STATE
         w.thr[slot] = f4(1.0f, 1.0f, 1.0f, ps.prev_pdf);
         w.illum[slot] = f4(0.0f, 0.0f, 0.0f, 0.0f);
+#endif
         w.rngb[slot] = make_uint2(ps.rng, 0u);
         if (fp.rng_variant != 0) w.rng2[slot] = ps.rng_b;
     }
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
 template <int FEAT>
 __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
                                                               const uint32_t *count, uint32_t *next_queue, uint32_t *next_count,
-                                                              uint32_t *shadow_count, DevCounters *dc, AovTarget aov, TileMap tm, int sort_tiles) {
+                                                              uint32_t *shadow_count, DevCounters *dc, AovTarget aov, TileMap tm, int sort_tiles, int first_bounce) {
     __shared__ uint32_t s_hist[RPTR_SHADE_KEYS], s_base[RPTR_SHADE_KEYS];
     __shared__ uint32_t s_sorted[RPTR_SHADE_TILE];
     const uint32_t n = *count;
@@ -223,7 +232,10 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                 const float4 hit = w.hit[slot];
                 const int tri = __float_as_int(hit.w);
                 if (tri >= 0) { // a miss ends the path; its sky term is added by k_resolve from the untouched path state
-                    const float4 o = w.ray_o[slot], d = w.ray_d[slot], thr = w.thr[slot], il = w.illum[slot];
+                    const float4 o = w.ray_o[slot], d = w.ray_d[slot];
+                    const bool implied = RPTR_IMPLIED_INITIAL_STATE && first_bounce;
+                    const float4 thr = implied ? f4(1.0f, 1.0f, 1.0f, 2.e16f) : w.thr[slot]; // generate_primary's initial state
+                    const float4 il = implied ? f4(0.0f, 0.0f, 0.0f, 0.0f) : w.illum[slot];
                     const uint2 rb = w.rngb[slot];
                     PathState ps;
                     ps.o = f3(o.x, o.y, o.z); ps.tmin = o.w;
@@ -304,14 +316,17 @@ __global__ void __launch_bounds__(256) k_resolve(rptr_scene_params sp, TileMap t
         float4 m = *dst;
         for (int32_t l = 0; l < n_layers; ++l) {
             const uint32_t slot = (uint32_t)l * (uint32_t)tm.local_pixels + lp;
-            float4 il = w.illum[slot];
             const float alpha = w.rngb[slot].y == 0u ? 0.0f : 1.0f;
-            if (__float_as_int(w.hit[slot].w) < 0) {
+            const bool miss = __float_as_int(w.hit[slot].w) < 0;
+            const bool untouched = RPTR_IMPLIED_INITIAL_STATE && miss && alpha == 0.0f; // primary ray left the scene: never shaded
+            float4 il = untouched ? f4(0.0f, 0.0f, 0.0f, 0.0f) : w.illum[slot];
+            if (miss) {
                 if (aov.albedo_roughness && alpha == 0.0f && slot - aov.slot_lo < (uint32_t)tm.local_pixels) { // primary ray left the scene
                     const float c[3] = {cam_pos.x, cam_pos.y, cam_pos.z};
                     store_aov(aov, tm, slot, aov_of_miss(c));
                 }
-                const float4 d = w.ray_d[slot], thr = w.thr[slot];
+                const float4 d = w.ray_d[slot];
+                const float4 thr = untouched ? f4(1.0f, 1.0f, 1.0f, 2.e16f) : w.thr[slot];
                 const float3 r = shade_miss(sp, f3(il.x, il.y, il.z), f3(thr.x, thr.y, thr.z), f3(d.x, d.y, d.z), thr.w);
                 il.x = r.x; il.y = r.y; il.z = r.z;
             }
@@ -997,7 +1012,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
                                      (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0) |
                                      (ctx->any_normal_map ? RPTR_FEAT_NORMAL_MAPS : 0);
-#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (hitq ? hitq : q), (hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, 0u}), tm, sort_tiles
+#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (hitq ? hitq : q), (hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, 0u}), tm, sort_tiles, (d == 0 ? 1 : 0)
                     if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else k_shade<RPTR_FEAT_ALL><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
