@@ -9,3 +9,6 @@ timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
    --log-file gpurun_out/trace_dram.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/b_ncu4.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --spp 16 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
+RPTR_CUDA_LIB=variants/librptr_cuda_implied.so timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/t_implied.log 2>&1; tail -2 gpurun_out/t_implied.log
+for v in base implied base implied; do RPTR_CUDA_LIB=variants/librptr_cuda_$v.so timeout 300 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/sweep_$v.json 2>/dev/null; python -c "
+import json; j=json.load(open('gpurun_out/sweep_$v.json')); r=j['roofline']; print('var', '$v', round(j['value'],1), {k: round(x,1) for k,x in r['stage_ms_rank0'].items()})"; done
