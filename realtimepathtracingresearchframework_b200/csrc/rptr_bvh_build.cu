@@ -21,6 +21,10 @@
 
 #include "rptr_bvh_build.hpp"
 
+#ifndef RPTR_LBVH_LEAF_MAX
+#define RPTR_LBVH_LEAF_MAX 4 // sub-trees of at most this many triangles become leaves (1 = single-triangle leaves)
+#endif
+
 namespace rp {
 
 namespace {
@@ -160,7 +164,7 @@ __global__ void k_collapse(const int32_t *cur, int32_t cur_count, int32_t level_
                 for (int k = 0; k < nk; ++k) {
                     if (kids[k] < 0) continue;
                     const Node2 &c = nodes[kids[k]];
-                    if (c.last - c.first + 1 <= 4) continue; // becomes a leaf as a whole
+                    if (c.last - c.first + 1 <= RPTR_LBVH_LEAF_MAX) continue; // becomes a leaf as a whole
                     const float a = half_area(node_boxes[kids[k]]);
                     if (a > best) { best = a; pick = k; }
                 }
@@ -183,7 +187,7 @@ __global__ void k_collapse(const int32_t *cur, int32_t cur_count, int32_t level_
                 const Node2 &c = nodes[kids[k]];
                 b = node_boxes[kids[k]];
                 const int32_t cnt = c.last - c.first + 1;
-                if (cnt <= 4) ref = make_leaf_ref(c.first, cnt);
+                if (cnt <= RPTR_LBVH_LEAF_MAX) ref = make_leaf_ref(c.first, cnt);
                 else {
                     const uint32_t pos = atomicAdd(next_count, 1u);
                     next[pos] = kids[k];

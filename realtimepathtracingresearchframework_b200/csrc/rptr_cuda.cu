@@ -1215,12 +1215,16 @@ int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, in
     if (n < 0 || (n > 0 && (!queries || !results))) return fail(ctx, "trace_rays: invalid arguments");
     if (n == 0) return 0;
     CU(cudaSetDevice(ctx->device));
-    rptr_render_ray_query *dq = nullptr;
-    float4 *dr = nullptr;
-    float *dt = nullptr;
-    CU(cudaMalloc((void **)&dq, sizeof(rptr_render_ray_query) * (size_t)n));
-    CU(cudaMalloc((void **)&dr, sizeof(float4) * (size_t)n));
-    CU(cudaMalloc((void **)&dt, sizeof(float) * (size_t)n));
+    struct Scratch { // freed on every exit path
+        void *p[3] = {nullptr, nullptr, nullptr};
+        ~Scratch() { for (void *q : p) cudaFree(q); }
+    } scratch;
+    CU(cudaMalloc(&scratch.p[0], sizeof(rptr_render_ray_query) * (size_t)n));
+    CU(cudaMalloc(&scratch.p[1], sizeof(float4) * (size_t)n));
+    CU(cudaMalloc(&scratch.p[2], sizeof(float) * (size_t)n));
+    rptr_render_ray_query *dq = static_cast<rptr_render_ray_query *>(scratch.p[0]);
+    float4 *dr = static_cast<float4 *>(scratch.p[1]);
+    float *dt = static_cast<float *>(scratch.p[2]);
     CU(cudaMemcpyAsync(dq, queries, sizeof(rptr_render_ray_query) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     // slots of skipped queries (mode < 0) keep what the caller's buffers hold (rt_intersect.comp:44-45)
     CU(cudaMemcpyAsync(dr, results, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
@@ -1230,9 +1234,6 @@ int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, in
     CU(cudaMemcpyAsync(results, dr, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     if (hit_t) CU(cudaMemcpyAsync(hit_t, dt, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(dq);
-    cudaFree(dr);
-    cudaFree(dt);
     return 0;
 }
 

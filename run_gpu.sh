@@ -12,3 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 RPTR_CUDA_LIB=variants/librptr_cuda_implied.so timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/t_implied.log 2>&1; tail -2 gpurun_out/t_implied.log
 for v in base implied base implied; do RPTR_CUDA_LIB=variants/librptr_cuda_$v.so timeout 300 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/sweep_$v.json 2>/dev/null; python -c "
 import json; j=json.load(open('gpurun_out/sweep_$v.json')); r=j['roofline']; print('var', '$v', round(j['value'],1), {k: round(x,1) for k,x in r['stage_ms_rank0'].items()})"; done
+for v in base lbvh1 lbvh2; do RPTR_CUDA_LIB=variants/librptr_cuda_$v.so timeout 600 python bench.py --scene c4 --spp 16 --no-cpu-baseline --steps 2 --warmup 2 > gpurun_out/sweep_c4_$v.json 2>/dev/null; python -c "
+import json; j=json.load(open('gpurun_out/sweep_c4_$v.json')); r=j['roofline']; print('var c4', '$v', round(j['value'],1), r['per_ray']['closest'], {k: round(x,1) for k,x in r['stage_ms_rank0'].items()}, j['config']['scene_setup_s'])"; done
+for v in base lbvh1; do RPTR_CUDA_LIB=variants/librptr_cuda_$v.so timeout 600 python bench.py --no-cpu-baseline --steps 2 --warmup 2 --option bvh_builder=1 > gpurun_out/sweep_c2lbvh_$v.json 2>/dev/null; python -c "
+import json; j=json.load(open('gpurun_out/sweep_c2lbvh_$v.json')); r=j['roofline']; print('var c2 lbvh', '$v', round(j['value'],1), r['per_ray']['closest'], j['config']['scene_setup_s'])"; done
