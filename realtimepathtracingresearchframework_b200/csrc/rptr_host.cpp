@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <array>
 #include <atomic>
 #include <stdexcept>
 #include <thread>
@@ -419,6 +420,38 @@ struct Builder {
     static constexpr int NB = 16;
     static constexpr int MAX_LEAF = 4;
     static constexpr int SWEEP_MAX = 8;
+    // nodes of at least PAR_MIN primitives (the top levels) are processed by all threads: bounds and bins are reduced from
+    // per-thread partials (min / max / counts: the result does not depend on the split), and the primitives are partitioned
+    // STABLY -- by every path, whatever the thread count -- so that the tree is the same for any number of threads
+    static constexpr int PAR_MIN = 131072;
+    int par_threads = 1;
+    std::vector<Prim> scratch;
+    template <class F> void pfor(int T, int lo, int n, F &&body) { // body(t, i0, i1) over T contiguous slices of [lo, lo + n)
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back([&, t]() { body(t, lo + (int)((int64_t)n * t / T), lo + (int)((int64_t)n * (t + 1) / T)); });
+        body(0, lo, lo + (int)((int64_t)n / T));
+        for (std::thread &x : th) x.join();
+    }
+    struct Bins { float bl[3][NB][3], bh[3][NB][3]; int cnt[3][NB]; };
+    static void bins_clear(Bins &b) {
+        for (int ax = 0; ax < 3; ++ax)
+            for (int i = 0; i < NB; ++i) {
+                b.cnt[ax][i] = 0;
+                for (int k = 0; k < 3; ++k) { b.bl[ax][i][k] = 1e30f; b.bh[ax][i][k] = -1e30f; }
+            }
+    }
+    void bins_add(Bins &b, int i0, int i1, const float *cmin, const float *sc) const { // sc[ax] == 0: axis not binned
+        for (int i = i0; i < i1; ++i)
+            for (int ax = 0; ax < 3; ++ax) {
+                if (!(sc[ax] > 0.0f)) continue;
+                const int q = std::min(NB - 1, std::max(0, (int)((prims[i].c[ax] - cmin[ax]) * sc[ax])));
+                b.cnt[ax][q]++;
+                for (int k = 0; k < 3; ++k) {
+                    b.bl[ax][q][k] = fminf(b.bl[ax][q][k], prims[i].lo[k]);
+                    b.bh[ax][q][k] = fmaxf(b.bh[ax][q][k], prims[i].hi[k]);
+                }
+            }
+    }
     static float half_area(const float *lo, const float *hi) {
         float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
         return dx * dy + dy * dz + dz * dx;
@@ -430,17 +463,30 @@ struct Builder {
             jobs->push_back(Job{idx, lo, hi, depth});
             return idx;
         }
-        float blo[3], bhi[3], cmin[3], cmax[3];
-        for (int k = 0; k < 3; ++k) { blo[k] = 1e30f; bhi[k] = -1e30f; cmin[k] = 1e30f; cmax[k] = -1e30f; }
-        for (int i = lo; i < hi; ++i)
-            for (int k = 0; k < 3; ++k) {
-                blo[k] = fminf(blo[k], prims[i].lo[k]);
-                bhi[k] = fmaxf(bhi[k], prims[i].hi[k]);
-                cmin[k] = fminf(cmin[k], prims[i].c[k]);
-                cmax[k] = fmaxf(cmax[k], prims[i].c[k]);
-            }
-        for (int k = 0; k < 3; ++k) { nodes[idx].lo[k] = blo[k]; nodes[idx].hi[k] = bhi[k]; }
         const int n = hi - lo;
+        const int T = (jobs && n >= PAR_MIN) ? par_threads : 1; // threads working on THIS node
+        float blo[3], bhi[3], cmin[3], cmax[3];
+        {
+            std::vector<std::array<float, 12>> part((size_t)T);
+            pfor(T, lo, n, [&](int t, int i0, int i1) {
+                std::array<float, 12> &b = part[(size_t)t];
+                for (int k = 0; k < 3; ++k) { b[k] = 1e30f; b[3 + k] = -1e30f; b[6 + k] = 1e30f; b[9 + k] = -1e30f; }
+                for (int i = i0; i < i1; ++i)
+                    for (int k = 0; k < 3; ++k) {
+                        b[k] = fminf(b[k], prims[i].lo[k]);
+                        b[3 + k] = fmaxf(b[3 + k], prims[i].hi[k]);
+                        b[6 + k] = fminf(b[6 + k], prims[i].c[k]);
+                        b[9 + k] = fmaxf(b[9 + k], prims[i].c[k]);
+                    }
+            });
+            for (int k = 0; k < 3; ++k) { blo[k] = 1e30f; bhi[k] = -1e30f; cmin[k] = 1e30f; cmax[k] = -1e30f; }
+            for (const std::array<float, 12> &b : part)
+                for (int k = 0; k < 3; ++k) {
+                    blo[k] = fminf(blo[k], b[k]); bhi[k] = fmaxf(bhi[k], b[3 + k]);
+                    cmin[k] = fminf(cmin[k], b[6 + k]); cmax[k] = fmaxf(cmax[k], b[9 + k]);
+                }
+        }
+        for (int k = 0; k < 3; ++k) { nodes[idx].lo[k] = blo[k]; nodes[idx].hi[k] = bhi[k]; }
         auto leaf = [&]() {
             nodes[idx].left = ~lo;
             nodes[idx].right = n;
@@ -483,24 +529,31 @@ struct Builder {
         int best_axis = -1, best_bin = -1;
         float best_cost = 1e30f;
         if (depth < sah_depth_limit) {
+            float scs[3];
             for (int ax = 0; ax < 3; ++ax) {
                 const float ext = cmax[ax] - cmin[ax];
-                if (!(ext > 0.0f)) continue;
-                float bl[NB][3], bh[NB][3];
-                int cnt[NB];
-                for (int b = 0; b < NB; ++b) {
-                    cnt[b] = 0;
-                    for (int k = 0; k < 3; ++k) { bl[b][k] = 1e30f; bh[b][k] = -1e30f; }
-                }
-                const float sc = (float)NB / ext;
-                for (int i = lo; i < hi; ++i) {
-                    int b = std::min(NB - 1, std::max(0, (int)((prims[i].c[ax] - cmin[ax]) * sc)));
-                    cnt[b]++;
-                    for (int k = 0; k < 3; ++k) {
-                        bl[b][k] = fminf(bl[b][k], prims[i].lo[k]);
-                        bh[b][k] = fmaxf(bh[b][k], prims[i].hi[k]);
+                scs[ax] = ext > 0.0f ? (float)NB / ext : 0.0f;
+            }
+            std::vector<Bins> parts((size_t)T);
+            pfor(T, lo, n, [&](int t, int i0, int i1) {
+                bins_clear(parts[(size_t)t]);
+                bins_add(parts[(size_t)t], i0, i1, cmin, scs);
+            });
+            Bins &all = parts[0];
+            for (int t = 1; t < T; ++t)
+                for (int ax = 0; ax < 3; ++ax)
+                    for (int b = 0; b < NB; ++b) {
+                        all.cnt[ax][b] += parts[(size_t)t].cnt[ax][b];
+                        for (int k = 0; k < 3; ++k) {
+                            all.bl[ax][b][k] = fminf(all.bl[ax][b][k], parts[(size_t)t].bl[ax][b][k]);
+                            all.bh[ax][b][k] = fmaxf(all.bh[ax][b][k], parts[(size_t)t].bh[ax][b][k]);
+                        }
                     }
-                }
+            for (int ax = 0; ax < 3; ++ax) {
+                if (!(scs[ax] > 0.0f)) continue;
+                float(*bl)[3] = all.bl[ax];
+                float(*bh)[3] = all.bh[ax];
+                int *cnt = all.cnt[ax];
                 float ra[NB];
                 int rc[NB];
                 float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
@@ -538,10 +591,30 @@ struct Builder {
             const float sc = (float)NB / (cmax[best_axis] - cmin[best_axis]);
             const float cm = cmin[best_axis];
             const int ax = best_axis, bb = best_bin;
-            auto it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const Prim &q) {
-                return std::min(NB - 1, std::max(0, (int)((q.c[ax] - cm) * sc))) <= bb;
-            });
-            mid = (int)(it - prims.begin());
+            auto left = [&](const Prim &q) { return std::min(NB - 1, std::max(0, (int)((q.c[ax] - cm) * sc))) <= bb; };
+            if (n >= PAR_MIN) { // stable, by all threads of this node: counts per slice, then a scatter through the scratch array
+                if (scratch.size() < prims.size()) scratch.resize(prims.size());
+                std::vector<int> n_left((size_t)T + 1, 0);
+                pfor(T, lo, n, [&](int t, int i0, int i1) {
+                    int c = 0;
+                    for (int i = i0; i < i1; ++i) c += left(prims[i]) ? 1 : 0;
+                    n_left[(size_t)t + 1] = c;
+                });
+                for (int t = 0; t < T; ++t) n_left[(size_t)t + 1] += n_left[(size_t)t];
+                const int total_left = n_left[(size_t)T];
+                pfor(T, lo, n, [&](int t, int i0, int i1) {
+                    int l = lo + n_left[(size_t)t], r = lo + total_left + (i0 - lo) - n_left[(size_t)t];
+                    for (int i = i0; i < i1; ++i) {
+                        if (left(prims[i])) scratch[(size_t)l++] = prims[i];
+                        else scratch[(size_t)r++] = prims[i];
+                    }
+                });
+                pfor(T, lo, n, [&](int, int i0, int i1) { std::copy(scratch.begin() + i0, scratch.begin() + i1, prims.begin() + i0); });
+                mid = lo + total_left;
+            } else {
+                auto it = std::partition(prims.begin() + lo, prims.begin() + hi, left);
+                mid = (int)(it - prims.begin());
+            }
             if (mid == lo || mid == hi) mid = lo + n / 2;
         }
         const int32_t l = build(nodes, lo, mid, depth + 1, jobs, cutoff);
@@ -555,9 +628,12 @@ struct Builder {
         nodes.clear();
         nodes.reserve(2 * (size_t)n);
         std::vector<Job> jobs;
+        scratch.clear();
         const int n_threads = std::getenv("RPTR_BUILD_THREADS") ? std::max(1, std::atoi(std::getenv("RPTR_BUILD_THREADS")))
                                                                 : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        par_threads = n_threads;
         build(nodes, 0, n, 0, n_threads > 1 && n > 65536 ? &jobs : nullptr, std::max(4096, n / (8 * n_threads)));
+        par_threads = 1;
         if (jobs.empty()) return;
         if (std::getenv("RPTR_BUILD_VERBOSE")) fprintf(stderr, "bvh: top pass done, %zu jobs, %d threads\n", jobs.size(), n_threads);
         std::vector<std::vector<Node2>> local(jobs.size());
