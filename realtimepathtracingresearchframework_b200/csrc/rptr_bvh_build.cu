@@ -11,7 +11,7 @@
 //   sort          (key, triangle) pairs
 //   k_radix_tree  Karras 2012: one thread per internal node finds its key range and split
 //   k_refit       bottom-up boxes through atomic arrival counters
-//   k_collapse    level by level: opens the largest child until 4 are held, subtrees of <= 4 triangles become leaves
+//   k_collapse    level by level: opens the largest child until 4 are held; sub-trees of <= RPTR_LBVH_LEAF_MAX (1) triangles become leaves
 //                 (their triangles are contiguous in Morton order, so the leaf triangle array is just the sorted array)
 //   k_gather_tris / k_top_planes    leaf-order triangle records, shared-memory image of the first nodes
 #include <cub/device/device_radix_sort.cuh>
@@ -22,7 +22,7 @@
 #include "rptr_bvh_build.hpp"
 
 #ifndef RPTR_LBVH_LEAF_MAX
-#define RPTR_LBVH_LEAF_MAX 4 // sub-trees of at most this many triangles become leaves (1 = single-triangle leaves)
+#define RPTR_LBVH_LEAF_MAX 1 // sub-trees of at most this many triangles become leaves (1 = single-triangle leaves)
 #endif
 
 namespace rp {
