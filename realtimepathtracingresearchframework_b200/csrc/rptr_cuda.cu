@@ -40,6 +40,7 @@ struct Wave {
     float4 *illum;  // illum.rgb, total_t
     uint2 *rngb;    // sampler word that advances with the draws (LCG state), bounce
     uint32_t *rng2; // second sampler word (Sobol index / BN pixelID); allocated for rng_variant != UNIFORM only
+    uint32_t *rng3; // LCG of the stochastic alpha test when the pointset is not the LCG (pt_megakernel.glsl:354-358); with rng2
     float4 *sh_o;   // shadow queue: origin.xyz, tmin
     float4 *sh_d;   //               dir.xyz, tmax
     float4 *sh_c;   //               contribution.rgb, bits(path slot)
@@ -124,7 +125,10 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave
         w.illum[slot] = f4(0.0f, 0.0f, 0.0f, 0.0f);
 #endif
         w.rngb[slot] = make_uint2(ps.rng, 0u);
-        if (fp.rng_variant != 0) w.rng2[slot] = ps.rng_b;
+        if (fp.rng_variant != 0) {
+            w.rng2[slot] = ps.rng_b;
+            if (w.rng3) w.rng3[slot] = alpha_lcg_seed(fp, px, py, fp.first_sample + (uint32_t)(first_layer + layer));
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[0] = n;
 }
@@ -138,10 +142,11 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
         const uint32_t slot = queue ? queue[i] : i;
         const float4 o = w.ray_o[slot], d = w.ray_d[slot];
         HitRec h;
-        uint2 rb = w.rngb[slot];
-        const uint32_t before = rb.x;
-        closest_hit_filtered(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, rb.x, h, cnt);
-        if (rb.x != before) w.rngb[slot] = rb;
+        uint32_t *ap = w.rng3 ? w.rng3 + slot : &w.rngb[slot].x;
+        uint32_t st = *ap;
+        const uint32_t before = st;
+        closest_hit_filtered(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, st, h, cnt);
+        if (st != before) *ap = st;
         w.hit[slot] = f4(h.t, h.u, h.v, __int_as_float(h.tri));
         if (hit_count) {
             const uint32_t hi = warp_append(hit_count, h.tri >= 0);
@@ -534,7 +539,11 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     CU(dev_alloc(ctx, &w.illum, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.rngb, n, ctx->wave_allocs));
     w.rng2 = nullptr;
-    if (need_rng2) CU(dev_alloc(ctx, &w.rng2, n, ctx->wave_allocs));
+    w.rng3 = nullptr;
+    if (need_rng2) {
+        CU(dev_alloc(ctx, &w.rng2, n, ctx->wave_allocs));
+        CU(dev_alloc(ctx, &w.rng3, n, ctx->wave_allocs));
+    }
     CU(dev_alloc(ctx, &w.sh_o, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.sh_d, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.sh_c, n, ctx->wave_allocs));
@@ -922,9 +931,6 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         const bool ok = v == 0 || (v == 1 && ctx->pointset_tables[2] && ctx->pointset_tables[3]) || (v == 2 && ctx->pointset_tables[0]) ||
                         (v == 3 && ctx->pointset_tables[0] && ctx->pointset_tables[1]);
         if (!ok) return fail(ctx, "rng_variant %d needs its tables: call rptr_cuda_set_pointset_table first", v);
-        // with a QMC pointset the megakernel keeps a SEPARATE per-path LCG for stochastic alpha (pt_megakernel.glsl:354-358);
-        // the wavefront does not store that second state yet
-        if (v != 0 && ctx->any_alpha_tested) return fail(ctx, "rng_variant %d with alpha-tested (textured alpha) materials is not supported by this backend yet", v);
     }
     CU(cudaSetDevice(ctx->device));
     const TileMap tm = make_tilemap(ctx);
@@ -957,6 +963,9 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         uint32_t *const hitq = multi_path ? w.hitq : nullptr;
         // per-candidate seeds of alpha-tested shadow rays: view_params.frame_id / frame_offset of this frame (pt_megakernel.glsl:252-254)
         const AlphaFilter alpha_filter{ctx->scene.ginst, fp.first_sample, fp.frame_offset, 0u};
+        // closest-hit alpha draws: the path's LCG (UNIFORM), else the separate LCG of pt_megakernel.glsl:354-358
+        uint32_t *const alpha_lcg = ctx->rng_variant != 0 ? w.rng3 : reinterpret_cast<uint32_t *>(w.rngb);
+        const uint32_t alpha_stride = ctx->rng_variant != 0 ? 1u : 2u;
         // trace: one RPTR_TRACE_THREADS CTA per SM; dynamic smem = the staged top of the BVH + the shared stack part
         const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4), g_pt = grid_for(ctx, 1);
         const size_t top_smem = RPTR_TRACE_SMEM_BYTES; // staged BVH top (128 KB) + shared part of the traversal stacks (64 KB)
@@ -969,7 +978,9 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
             if (ctx->aov_buffers && first + nl == fp.batch) aov = AovTarget{ctx->aov_images[0], ctx->aov_images[1], (uint32_t)(nl - 1) * (uint32_t)tm.local_pixels};
             {
                 StageTimer t(ctx, 3);
-                k_raygen<<<g_light, 256, 0, ctx->stream>>>(fp, tm, w, first, nl);
+                Wave wr = w;
+                if (!ctx->any_alpha_tested) wr.rng3 = nullptr; // no alpha-tested triangle: nobody reads the alpha LCG
+                k_raygen<<<g_light, 256, 0, ctx->stream>>>(fp, tm, wr, first, nl);
                 ctx->launches++;
             }
             bool shadow_pending = false;
@@ -997,7 +1008,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     StageTimer t(ctx, union_a ? -1 : 0);
                     if (union_a) union_launches++;
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, hitq, w.hit_counts + d, nullptr, nullptr, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, hitq, w.hit_counts + d, nullptr, nullptr, alpha_lcg, alpha_stride, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<false, true> : k_trace_persistent<false, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
                             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
@@ -1030,7 +1041,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     }
                     CU(cudaEventRecord(ctx->ev_shade, ctx->stream));
                     CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_shade, 0));
-                    TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                    TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, alpha_lcg, alpha_stride, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
                     auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                     kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream2>>>(
                         ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
@@ -1040,7 +1051,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                 } else if (fp.output_channel == 0 && d + 1 < depth) {
                     StageTimer t(ctx, 2);
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, w.rngb, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, alpha_lcg, alpha_stride, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
                             ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);

@@ -730,6 +730,11 @@ RPTR_HD float path_rand(const FrameParams &fp, PathState &ps, int d) {
     return r;
 }
 
+// alpha_rng of a path when the pointset is not the LCG (pt_megakernel.glsl:354-358): the LCG the UNIFORM pointset would start from
+RPTR_HD uint32_t alpha_lcg_seed(const FrameParams &fp, int px, int py, uint32_t sample_index) {
+    return sampler_init(0, fp.pts, sample_index, fp.first_sample, fp.frame_offset, (uint32_t)px, (uint32_t)py, (uint32_t)fp.width).a;
+}
+
 // primary ray + path state (vulkan/pt_megakernel.glsl:310-365)
 RPTR_HD void generate_primary(const FrameParams &fp, int px, int py, uint32_t sample_index, PathState &ps) {
     const Sampler sm = sampler_init(fp.rng_variant, fp.pts, sample_index, fp.first_sample, fp.frame_offset, (uint32_t)px, (uint32_t)py,

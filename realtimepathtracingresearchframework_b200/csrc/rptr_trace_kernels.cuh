@@ -42,7 +42,8 @@ struct TraceIO {
     const float4 *sh_c;    // shadow: (contribution.rgb, bits(path slot))
     float4 *illum;         // shadow: illum.rgb += contribution when unoccluded
     // stochastic alpha (kernels instantiated with Alpha = true only; scenes without alpha-tested triangles never pay for it)
-    uint2 *rngb;           // closest: per path slot (LCG state, bounce) -- the candidate filter draws from the path's LCG
+    uint32_t *alpha_lcg;   // closest: LCG state the candidate filter draws from, word alpha_lcg[slot * alpha_stride]: the path's own
+    uint32_t alpha_stride; //          LCG with the UNIFORM pointset (stride 2: Wave::rngb), a separate one otherwise (stride 1: Wave::rng3)
     AlphaFilter alpha;     // shadow: per-candidate LCG seeds (pixel_linear is filled in per ray)
     int32_t tm_width, tm_local_pixels, tm_rank, tm_world, tm_rows; // shadow: path slot -> global pixel (TileMap of rptr_cuda.cu)
 };
@@ -251,10 +252,11 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         if (Alpha && !Any && done && best_tri >= 0 && after_id != RPTR_EMPTY) {
             const int32_t a8 = tri_alpha8(bvh.tris[best_tri]);
             if (a8 != RPTR_TRI_OPAQUE) {
-                uint2 rb = io.rngb[slot];
-                const uint32_t before = rb.x;
-                const bool rejected = alpha_rejects(alpha8_to_float(a8), rb.x);
-                if (rb.x != before) io.rngb[slot] = rb;
+                uint32_t *ap = io.alpha_lcg + (size_t)slot * io.alpha_stride;
+                uint32_t st = *ap;
+                const uint32_t before = st;
+                const bool rejected = alpha_rejects(alpha8_to_float(a8), st);
+                if (st != before) *ap = st;
                 if (rejected) { // look for the closest hit after this candidate
                     tmin = best_t; after_id = best_id;
                     best_t = tmax; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;

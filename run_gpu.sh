@@ -1,2 +1,5 @@
-for v in base t1024 t768; do RPTR_CUDA_LIB=variants/librptr_cuda_$v.so timeout 300 python bench.py --no-cpu-baseline --steps 2 --warmup 2 --option overlap_shadow=0 > gpurun_out/sweep_$v.json 2> gpurun_out/sweep_$v.err || tail -2 gpurun_out/sweep_$v.err; python -c "
-import json; j=json.load(open('gpurun_out/sweep_$v.json')); r=j['roofline']; print('var', '$v', round(j['value'],1), {k: round(x,1) for k,x in r['stage_ms_rank0'].items()})"; done
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t.log 2>&1; tail -5 gpurun_out/t.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_after_alpha_qmc.json 2> gpurun_out/bench_after_alpha_qmc.err; python -c "
+import json; j=json.load(open('gpurun_out/bench_after_alpha_qmc.json')); print(j['value'], j['e2e']['value'], j['roofline']['frac'])"

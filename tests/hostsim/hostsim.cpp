@@ -101,13 +101,14 @@ static int render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t
         for (int x = a->x0; x < a->x1; ++x) {
             PathState ps;
             generate_primary(fp, x, y, sample_index, ps);
+            uint32_t alpha_lcg = alpha_lcg_seed(fp, x, y, sample_index);
             TraceCounters cnt{0, 0};
             AovSample as;
             memset(&as, 0, sizeof(as));
             for (;;) {
                 HitRec h;
                 // stochastic alpha draws come from the path's LCG (the LCG pointset; the QMC pointsets keep a separate one)
-                bool found = closest_hit_filtered(bvh, ps.o, ps.d, ps.tmin, ps.tmax, ps.rng, h, cnt);
+                bool found = closest_hit_filtered(bvh, ps.o, ps.d, ps.tmin, ps.tmax, fp.rng_variant == 0 ? ps.rng : alpha_lcg, h, cnt);
                 ShadowRay sh;
                 ShadeResult r = shade_vertex(fp, sc, ps, h.t, h.u, h.v, found ? &bvh.tris[h.tri] : nullptr, sh, aov_out ? &as : nullptr);
                 if (sh.tmax > 0.0f) {

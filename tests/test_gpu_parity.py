@@ -478,10 +478,20 @@ def test_alpha_tested_materials_and_1x1_textures(oracle):
     c = make_backend(s, W, H, sky, trace_kernel=1)
     c.render_spp(s.camera, 3, batch_spp=1)
     assert_identical(c.framebuffer(), ref, "alpha soup, one-ray-per-thread kernels")
-    # Sobol / blue-noise pointsets keep a separate alpha LCG per path: not stored by the wavefront yet -> loud error, not a wrong image
-    r.set_rng_variant(T.RNG_VARIANT_SOBOL)
-    with pytest.raises(RptrError):
-        r.render_spp(s.camera, 1)
+    # Sobol / blue-noise pointsets: the closest-hit alpha test draws from a separate per-path LCG (pt_megakernel.glsl:354-358)
+    from realtimepathtracingresearchframework_b200 import load_pointset_tables
+    tables = load_pointset_tables()
+    for variant in (T.RNG_VARIANT_BN, T.RNG_VARIANT_SOBOL, T.RNG_VARIANT_Z_SBL):
+        q = make_backend(s, W, H, sky, wave_paths=3 * W * H)
+        q.set_rng_variant(variant, tables)
+        q.render_spp(s.camera, 4, batch_spp=4)
+        refq, _ = o.render(W, H, s.camera, sp, spp=4, batch_spp=4, rng_variant=variant, pointset_tables=tables)
+        assert_identical(q.framebuffer(), refq, "alpha soup, rng_variant %d, batch of 4" % variant)
+        q.close()
+    c.set_rng_variant(T.RNG_VARIANT_SOBOL, tables)  # same context, one-ray-per-thread kernels, progressive
+    c.render_spp(s.camera, 2, batch_spp=1, reset=True)
+    refc, _ = o.render(W, H, s.camera, sp, spp=2, rng_variant=T.RNG_VARIANT_SOBOL, pointset_tables=tables, frame_offset=3)
+    assert_identical(c.framebuffer(), refc, "alpha soup, Sobol, one-ray-per-thread kernels")
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from realtimepathtracingresearchframework_b200 import load_sky_fit, scenes, types as T
+from realtimepathtracingresearchframework_b200 import load_pointset_tables, load_sky_fit, scenes, types as T
 
 
 @pytest.fixture(scope="module")
@@ -50,6 +50,21 @@ def test_alpha_tested_scene_matches_oracle_bit_for_bit(H, oracle, sample, frame_
     ref, img = render_both(H, oracle, s, 200, 120, sample, sky=dict(sun_dir=(0.35, 0.8, 0.45)), frame_offset=frame_offset)
     assert np.isfinite(ref).all() and ref[..., :3].max() > 0
     assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), "%d pixels differ" % (ref != img).any(-1).sum()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_alpha_test_with_the_qmc_pointsets_draws_from_its_own_lcg(H, oracle, variant):
+    """RBO_rng_variant != UNIFORM: alpha_rng is a separate LCG seeded like the UNIFORM pointset (pt_megakernel.glsl:354-358),
+    so the path's BN / Sobol dimensions do not shift when a candidate is alpha-tested."""
+    s = scenes.alpha_tested_soup()
+    kw = dict(frame_offset=3, rng_variant=variant, pointset_tables=load_pointset_tables())
+    for sample in (0, 2):
+        ref, img = render_both(H, oracle, s, 300, 140, sample, sky=dict(sun_dir=(0.35, 0.8, 0.45)), **kw)
+        assert np.isfinite(ref).all() and ref[..., :3].max() > 0
+        assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), "%d pixels differ" % (ref != img).any(-1).sum()
+    # and the pointset is really in effect
+    uni, _ = render_both(H, oracle, s, 300, 140, 2, sky=dict(sun_dir=(0.35, 0.8, 0.45)), frame_offset=3)
+    assert not np.array_equal(ref[..., :3], uni[..., :3])
 
 
 def test_alpha_changes_the_image_the_expected_way(H, oracle):
