@@ -115,11 +115,12 @@ int rptr_cuda_framebuffer_size(rptr_ctx *ctx, uint32_t *width, uint32_t *height,
 size_t rptr_cuda_readback_f32(rptr_ctx *ctx, size_t n_elems, float *dst);
 size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst);
 /* RenderGraphic::readback_aov (util/display/render_graphic.h:39-43; vulkan/render_vulkan.cpp:2290-2294): the RGBA16F AOV
- * images the megakernel stores for the first path vertex (vulkan/accumulate.glsl:89-103): aov_index 0 = albedo.rgb +
- * roughness (AOVAlbedoRoughnessIndex), 1 = normal.xyz + depth (AOVNormalDepthIndex), as half-float bit patterns, RGBA,
+ * images the megakernel stores for the first path vertex (vulkan/accumulate.glsl:77-103): aov_index 0 = albedo.rgb +
+ * roughness (AOVAlbedoRoughnessIndex), 1 = normal.xyz + depth (AOVNormalDepthIndex), 2 = screen-space motion.xy against the
+ * previous begin_frame's view + screen_jitter.xy (AOVMotionJitterIndex; geometry is static, so the motion is the camera's;
+ * NaN before a second begin_frame exists, like the reference's zero VP_reference), as half-float bit patterns, RGBA,
  * row-major, top row first.  Every sample layer overwrites them; they hold the frame's last layer.  Returns the number of
- * elements written (width*height*4) or 0: buffer too small, option "aov_buffers" off, or aov_index 2
- * (AOVMotionJitterIndex: needs the reprojection matrices, not produced by this backend). */
+ * elements written (width*height*4) or 0: buffer too small, option "aov_buffers" off, or aov_index outside 0..2. */
 size_t rptr_cuda_readback_aov(rptr_ctx *ctx, int32_t aov_index, size_t n_elems, uint16_t *dst);
 /* device address of the RGBA32F accumulator (for the multi-GPU reduce over NCCL); valid until initialize/destroy */
 int rptr_cuda_framebuffer_device_ptr(rptr_ctx *ctx, void **ptr);

@@ -19,7 +19,8 @@ class OracleRenderArgs(C.Structure):
                 ("lighting", T.LightSamplingConfig), ("scene_params", T.SceneParams), ("frame_offset", C.c_uint32),
                 ("first_sample", C.c_uint32), ("n_samples", C.c_int32), ("x0", C.c_int32), ("y0", C.c_int32),
                 ("x1", C.c_int32), ("y1", C.c_int32), ("transmission", C.c_int32), ("n_threads", C.c_int32),
-                ("rng_variant", C.c_int32), ("batch_spp", C.c_int32), ("pointset_tables", C.c_void_p * 4)]
+                ("rng_variant", C.c_int32), ("batch_spp", C.c_int32), ("pointset_tables", C.c_void_p * 4),
+                ("vp_reference", C.c_float * 16)]
 
 
 def build(force=False):
@@ -56,6 +57,8 @@ def lib():
         L.oracle_render.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), f32p, C.POINTER(C.c_uint64)]
         L.oracle_render_sample.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_uint32, f32p]
         L.oracle_render_aov.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_uint32, f32p, f32p]
+        L.oracle_render_aov3.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_uint32, f32p, f32p, f32p]
+        L.oracle_view_projection.argtypes = [C.POINTER(T.RenderCameraParams), C.c_int32, C.c_int32, f32p]
         for n in ("oracle_trace_closest", "oracle_trace_closest_bruteforce"):
             getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_int32, f32p, f32p]
         L.oracle_pointset_replay.argtypes = [C.c_int, C.POINTER(C.c_void_p)] + [C.c_uint32] * 6 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -147,7 +150,7 @@ class OracleScene:
         return np.frombuffer(arr, dtype=np.float32).reshape(-1, 12)[:n].copy()
 
     def _args(self, width, height, camera, scene_params, params=None, frame_offset=0, first_sample=0, n_samples=1,
-              region=None, transmission=0, n_threads=0, rng_variant=0, batch_spp=1, pointset_tables=None):
+              region=None, transmission=0, n_threads=0, rng_variant=0, batch_spp=1, pointset_tables=None, vp_reference=None):
         a = OracleRenderArgs()
         a.width, a.height = width, height
         a.camera = camera
@@ -159,6 +162,8 @@ class OracleScene:
         a.x0, a.y0, a.x1, a.y1 = x0, y0, x1, y1
         a.transmission, a.n_threads = transmission, n_threads
         a.rng_variant, a.batch_spp = rng_variant, batch_spp
+        if vp_reference is not None:  # view_params.VP_reference (16 floats, column-major); zero = before the first frame
+            a.vp_reference[:] = [float(v) for v in np.asarray(vp_reference, np.float32).reshape(16)]
         if rng_variant != 0:
             if pointset_tables is None:
                 raise ValueError("rng_variant != 0 needs pointset_tables (four uint32 arrays)")
@@ -189,6 +194,16 @@ class OracleScene:
         lib().oracle_render_aov(self.h, C.byref(a), sample_index, _fp(ar), _fp(nd))
         return ar, nd
 
+    def render_aov3(self, width, height, camera, scene_params, sample_index, **kw):
+        """As render_aov plus the motion / jitter image; first_sample (kw) = frame_id of the frame the layer belongs to,
+        vp_reference (kw) = VP of the previous frame (view_projection of its camera)."""
+        a = self._args(width, height, camera, scene_params, **kw)
+        ar = np.zeros((height, width, 4), np.float32)
+        nd = np.zeros((height, width, 4), np.float32)
+        mj = np.zeros((height, width, 4), np.float32)
+        lib().oracle_render_aov3(self.h, C.byref(a), sample_index, _fp(ar), _fp(nd), _fp(mj))
+        return ar, nd, mj
+
     def trace_closest(self, queries, bruteforce=False):
         """queries: structured (n, 8) float32 view of RenderRayQuery -> (results (n,4) float32 bits, t (n,))."""
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, 8)
@@ -210,6 +225,13 @@ def table_ptrs(tables):
 def view_params(camera, w, h):
     out = np.zeros(9, np.float32)
     lib().oracle_view_params(C.byref(camera), w, h, _fp(out))
+    return out
+
+
+def view_projection(camera, w, h):
+    """view_params.VP (16 floats, column-major) for a camera and frame size."""
+    out = np.zeros(16, np.float32)
+    lib().oracle_view_projection(C.byref(camera), w, h, _fp(out))
     return out
 
 

@@ -522,6 +522,8 @@ typedef struct oracle_render_args {
     int32_t batch_spp;      // >= 1: view_params.frame_id of sample k is first_sample + (k / batch_spp) * batch_spp (the BN
                             // sampler seeds from frame_id, not from the sample index: bn_rng.glsl:112)
     const uint32_t *pointset_tables[4]; // SobolMatrix, SobolInversion_1_0, sobol_256spp_256d, scramblingTile_yx_d_1spp
+    float vp_reference[16];             // view_params.VP_reference (column-major): the VP of the previous begin_frame; all zero
+                                        // before the first one (the value-initialised ParameterCache, render_vulkan.cpp:103)
 } oracle_render_args;
 
 struct oracle_scene { Scene s; };
@@ -677,6 +679,68 @@ void oracle_view_params(const rptr_camera_params *cam, int32_t w, int32_t h, flo
     out[6] = tl.x; out[7] = tl.y; out[8] = tl.z;
 }
 
+// view_params.VP (vulkan/render_vulkan.cpp:2926-2930) = GLToVulkan * infinitePerspective(radians(fovy), aspect, 0.5) *
+// inverse(mat4(mat4x3(cross(dir, up), up, -dir, cam_pos))), out = 16 floats, column-major.  glm (0.9.9.8, fetched at
+// configure time by ext/CMakeLists.txt:18-21, absent from the reference tree) is restated from its published sources:
+// type_mat4x4.inl (operator*), func_matrix.inl (compute_inverse<4, 4>), ext/matrix_clip_space.inl (infinitePerspectiveRH).
+} // extern "C"
+namespace {
+struct M4 { V4 col[4]; };
+static inline V4 operator*(V4 a, float s) { return V4{a.x * s, a.y * s, a.z * s, a.w * s}; }
+static inline V4 operator*(V4 a, V4 b) { return V4{a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w}; }
+static inline V4 operator+(V4 a, V4 b) { return V4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+static inline V4 operator-(V4 a, V4 b) { return V4{a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w}; }
+static inline float comp(V4 v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+static M4 glm_mul(const M4 &a, const M4 &b) {
+    M4 r;
+    for (int j = 0; j < 4; ++j) r.col[j] = a.col[0] * b.col[j].x + a.col[1] * b.col[j].y + a.col[2] * b.col[j].z + a.col[3] * b.col[j].w;
+    return r;
+}
+static M4 glm_inverse(const M4 &m) {
+#define E(c, r) comp(m.col[c], r)
+    float Coef00 = E(2, 2) * E(3, 3) - E(3, 2) * E(2, 3), Coef02 = E(1, 2) * E(3, 3) - E(3, 2) * E(1, 3), Coef03 = E(1, 2) * E(2, 3) - E(2, 2) * E(1, 3);
+    float Coef04 = E(2, 1) * E(3, 3) - E(3, 1) * E(2, 3), Coef06 = E(1, 1) * E(3, 3) - E(3, 1) * E(1, 3), Coef07 = E(1, 1) * E(2, 3) - E(2, 1) * E(1, 3);
+    float Coef08 = E(2, 1) * E(3, 2) - E(3, 1) * E(2, 2), Coef10 = E(1, 1) * E(3, 2) - E(3, 1) * E(1, 2), Coef11 = E(1, 1) * E(2, 2) - E(2, 1) * E(1, 2);
+    float Coef12 = E(2, 0) * E(3, 3) - E(3, 0) * E(2, 3), Coef14 = E(1, 0) * E(3, 3) - E(3, 0) * E(1, 3), Coef15 = E(1, 0) * E(2, 3) - E(2, 0) * E(1, 3);
+    float Coef16 = E(2, 0) * E(3, 2) - E(3, 0) * E(2, 2), Coef18 = E(1, 0) * E(3, 2) - E(3, 0) * E(1, 2), Coef19 = E(1, 0) * E(2, 2) - E(2, 0) * E(1, 2);
+    float Coef20 = E(2, 0) * E(3, 1) - E(3, 0) * E(2, 1), Coef22 = E(1, 0) * E(3, 1) - E(3, 0) * E(1, 1), Coef23 = E(1, 0) * E(2, 1) - E(2, 0) * E(1, 1);
+    V4 Fac0{Coef00, Coef00, Coef02, Coef03}, Fac1{Coef04, Coef04, Coef06, Coef07}, Fac2{Coef08, Coef08, Coef10, Coef11};
+    V4 Fac3{Coef12, Coef12, Coef14, Coef15}, Fac4{Coef16, Coef16, Coef18, Coef19}, Fac5{Coef20, Coef20, Coef22, Coef23};
+    V4 Vec0{E(1, 0), E(0, 0), E(0, 0), E(0, 0)}, Vec1{E(1, 1), E(0, 1), E(0, 1), E(0, 1)};
+    V4 Vec2{E(1, 2), E(0, 2), E(0, 2), E(0, 2)}, Vec3{E(1, 3), E(0, 3), E(0, 3), E(0, 3)};
+#undef E
+    V4 Inv0 = Vec1 * Fac0 - Vec2 * Fac1 + Vec3 * Fac2;
+    V4 Inv1 = Vec0 * Fac0 - Vec2 * Fac3 + Vec3 * Fac4;
+    V4 Inv2 = Vec0 * Fac1 - Vec1 * Fac3 + Vec3 * Fac5;
+    V4 Inv3 = Vec0 * Fac2 - Vec1 * Fac4 + Vec2 * Fac5;
+    V4 SignA{+1.0f, -1.0f, +1.0f, -1.0f}, SignB{-1.0f, +1.0f, -1.0f, +1.0f};
+    M4 Inverse{{Inv0 * SignA, Inv1 * SignB, Inv2 * SignA, Inv3 * SignB}};
+    V4 Row0{Inverse.col[0].x, Inverse.col[1].x, Inverse.col[2].x, Inverse.col[3].x};
+    V4 Dot0 = m.col[0] * Row0;
+    float Dot1 = (Dot0.x + Dot0.y) + (Dot0.z + Dot0.w);
+    float OneOverDeterminant = 1.0f / Dot1;
+    for (int j = 0; j < 4; ++j) Inverse.col[j] = Inverse.col[j] * OneOverDeterminant;
+    return Inverse;
+}
+} // namespace
+extern "C" {
+void oracle_view_projection(const rptr_camera_params *cam, int32_t w, int32_t h, float *out) {
+    V3 dir = v3(cam->dir[0], cam->dir[1], cam->dir[2]), up = v3(cam->up[0], cam->up[1], cam->up[2]);
+    V3 right_ = cross(dir, up);
+    M4 frame{{V4{right_.x, right_.y, right_.z, 0.0f}, V4{up.x, up.y, up.z, 0.0f}, V4{-dir.x, -dir.y, -dir.z, 0.0f},
+              V4{cam->pos[0], cam->pos[1], cam->pos[2], 1.0f}}};
+    float fovy = cam->fovy * 0.01745329251994329576923690768489f; // glm::radians
+    float aspect = (float)w / (float)h;
+    float zNear = 0.5f;
+    float range = tanf(fovy / 2.0f) * zNear;
+    float left = -range * aspect, right = range * aspect, bottom = -range, top = range;
+    M4 P{{V4{(2.0f * zNear) / (right - left), 0.0f, 0.0f, 0.0f}, V4{0.0f, (2.0f * zNear) / (top - bottom), 0.0f, 0.0f}, V4{0.0f, 0.0f, -1.0f, -1.0f},
+          V4{0.0f, 0.0f, -2.0f * zNear, 0.0f}}};
+    M4 GLToVulkan{{V4{1.0f, 0.0f, 0.0f, 0.0f}, V4{0.0f, -1.0f, 0.0f, 0.0f}, V4{0.0f, 0.0f, 0.5f, 0.0f}, V4{0.0f, 0.0f, 0.5f, 1.0f}}};
+    M4 VP = glm_mul(glm_mul(GLToVulkan, P), glm_inverse(frame));
+    for (int j = 0; j < 4; ++j) { out[4 * j] = VP.col[j].x; out[4 * j + 1] = VP.col[j].y; out[4 * j + 2] = VP.col[j].z; out[4 * j + 3] = VP.col[j].w; }
+}
+
 } // extern "C"
 
 namespace {
@@ -707,6 +771,7 @@ struct Frame {
     const oracle_render_args *a;
     rptr_scene_params sp; // with the light-count rule applied to sun_radiance.w
     V3 cam_pos, du, dv, tl;
+    float VP[16]; // view_params.VP of this frame, column-major
     int n_lights, n_bins;
     bool tr;
 };
@@ -860,8 +925,33 @@ struct PathRng {
 };
 
 // what the megakernel imageStore()s into aov_albedo_roughness_buffer / aov_normal_depth_buffer for the first path vertex
-// (vulkan/accumulate.glsl:89-103), as floats: [0..3] = albedo.rgb, roughness; [4..7] = normal.xyz, depth
-struct AovOut { float v[8]; };
+// (vulkan/accumulate.glsl:77-103), as floats: [0..3] = albedo.rgb, roughness; [4..7] = normal.xyz, depth;
+// [8..11] = motion.xy, screen_jitter.xy (aov_motion_jitter_buffer)
+struct AovOut { float v[12]; uint32_t view_frame_id; };
+// store_motion_jitter_aovs: vulkan/accumulate.glsl:77-87.  mat4 * vec4 sums the columns left to right (RPTR-FP).
+static V4 mat_vec(const float *M, V4 v) {
+    V4 r;
+    r.x = ((M[0] * v.x + M[4] * v.y) + M[8] * v.z) + M[12] * v.w;
+    r.y = ((M[1] * v.x + M[5] * v.y) + M[9] * v.z) + M[13] * v.w;
+    r.z = ((M[2] * v.x + M[6] * v.y) + M[10] * v.z) + M[14] * v.w;
+    r.w = ((M[3] * v.x + M[7] * v.y) + M[11] * v.z) + M[15] * v.w;
+    return r;
+}
+static float glsl_max(float x, float y) { return x < y ? y : x; }
+static void store_motion_jitter_aovs(const Frame &f, V3 position, V3 motion_vector, AovOut *aov) {
+    const oracle_render_args &a = *f.a;
+    V3 moved = position + motion_vector;
+    V4 ref_proj = mat_vec(a.vp_reference, V4{moved.x, moved.y, moved.z, 1.0f});
+    float ref_w = glsl_max(ref_proj.w, 0.0f);
+    V4 cur_proj = mat_vec(f.VP, V4{position.x, position.y, position.z, 1.0f});
+    float cur_w = glsl_max(cur_proj.w, 0.0f);
+    float sj[2] = {0.0f, 0.0f}; // render_vulkan.cpp:2917-2926
+    if (a.params.enable_raster_taa > 0) screen_jitter(a.frame_offset, aov->view_frame_id, a.width, a.height, sj);
+    aov->v[8] = ref_proj.x / ref_w - cur_proj.x / cur_w;
+    aov->v[9] = ref_proj.y / ref_w - cur_proj.y / cur_w;
+    aov->v[10] = sj[0];
+    aov->v[11] = sj[1];
+}
 
 // shade_base_material: rendering/mc/shade_base_material.glsl:14-96 (material unpack, emitter MIS, AOV channels, path-length
 // cut, NEE, glossy-only cut, BSDF sampling with its draw order, bounce counting).  Returns SHADING_RESULT_*.
@@ -878,6 +968,7 @@ static int shade_base_material(const Frame &f, int &bounce, float &prev_bounce_p
         const V3 alb = throughput * mat.base_color;
         const float m[8] = {alb.x, alb.y, alb.z, mat.ior != 1.0f ? mat.roughness : 1.0f, in_.x, in_.y, in_.z, length(ip - f.cam_pos)};
         std::memcpy(aov->v, m, sizeof(m));
+        store_motion_jitter_aovs(f, ip, v3(0.0f), aov); // motion_vector = 0: static geometry (pt_megakernel.glsl:426)
     }
     if (a.params.output_channel == 0 && !is_zero(emit)) { // :33-39
         float light_pdf = (1.0f - p_sun) * (1.0f / ((float)f.n_bins * approx_sa));
@@ -983,6 +1074,7 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
                 const float far_depth = length(v3(2.e32f) - f.cam_pos); // accumulate.glsl:92
                 const float m[8] = {0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, far_depth};
                 std::memcpy(aov->v, m, sizeof(m));
+                store_motion_jitter_aovs(f, v3(2.e32f), v3(0.0f), aov);
             }
             break;
         }
@@ -1075,6 +1167,7 @@ static Frame make_frame(const oracle_scene *os, const oracle_render_args *a) {
     f.du = v3(vp[0], vp[1], vp[2]);
     f.dv = v3(vp[3], vp[4], vp[5]);
     f.tl = v3(vp[6], vp[7], vp[8]);
+    oracle_view_projection(&a->camera, a->width, a->height, f.VP);
     f.tr = a->transmission != 0;
     return f;
 }
@@ -1123,9 +1216,11 @@ int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rg
     return 0;
 }
 
-// The float values behind the two fp16 AOV images for sample `sample_index` (the last layer of a frame is what survives):
-// albedo_roughness and normal_depth are W*H*4 each.
-int oracle_render_aov(const oracle_scene *os, const oracle_render_args *a, uint32_t sample_index, float *albedo_roughness, float *normal_depth) {
+// The float values behind the fp16 AOV images for sample `sample_index` (the last layer of a frame is what survives):
+// albedo_roughness, normal_depth and motion_jitter (optional) are W*H*4 each.  view_params (frame_id for the raster-TAA
+// jitter) are those of the frame that starts at a->first_sample.
+int oracle_render_aov3(const oracle_scene *os, const oracle_render_args *a, uint32_t sample_index, float *albedo_roughness, float *normal_depth,
+                       float *motion_jitter) {
     Frame f = make_frame(os, a);
 #pragma omp parallel for schedule(dynamic, 1)
     for (int y = a->y0; y < a->y1; ++y) {
@@ -1133,12 +1228,19 @@ int oracle_render_aov(const oracle_scene *os, const oracle_render_args *a, uint3
         for (int x = a->x0; x < a->x1; ++x) {
             AovOut o;
             std::memset(&o, 0, sizeof(o));
-            main_spp(f, x, y, sample_index, sample_index, cnt, &o);
+            o.view_frame_id = a->first_sample;
+            main_spp(f, x, y, sample_index, a->first_sample, cnt, &o);
             std::memcpy(albedo_roughness + 4 * ((size_t)y * a->width + x), o.v, 16);
             std::memcpy(normal_depth + 4 * ((size_t)y * a->width + x), o.v + 4, 16);
+            if (motion_jitter) std::memcpy(motion_jitter + 4 * ((size_t)y * a->width + x), o.v + 8, 16);
         }
     }
     return 0;
+}
+int oracle_render_aov(const oracle_scene *os, const oracle_render_args *a, uint32_t sample_index, float *albedo_roughness, float *normal_depth) {
+    oracle_render_args b = *a;
+    b.first_sample = sample_index; // a frame of one sample
+    return oracle_render_aov3(os, &b, sample_index, albedo_roughness, normal_depth, nullptr);
 }
 
 // One un-averaged sample layer (the vec4 main_spp returns) for every pixel of the region: sample_rgba is W*H*4.

@@ -68,6 +68,7 @@ __host__ __device__ inline int32_t local_row_to_global(const TileMap &t, int32_t
 struct AovTarget {
     ushort4 *albedo_roughness; // null: AOV images off
     ushort4 *normal_depth;
+    ushort4 *motion_jitter;
     uint32_t slot_lo;
 };
 __device__ __forceinline__ ushort4 to_half4(float x, float y, float z, float w) { // rgba16f store: round to nearest even
@@ -79,6 +80,7 @@ __device__ __forceinline__ void store_aov(const AovTarget &t, const TileMap &tm,
     const size_t px = (size_t)local_row_to_global(tm, (int32_t)(lp / (uint32_t)tm.width)) * tm.width + lp % (uint32_t)tm.width;
     t.albedo_roughness[px] = to_half4(a.albedo.x, a.albedo.y, a.albedo.z, a.roughness);
     t.normal_depth[px] = to_half4(a.normal.x, a.normal.y, a.normal.z, a.depth);
+    t.motion_jitter[px] = to_half4(a.motion[0], a.motion[1], a.jitter[0], a.jitter[1]);
 }
 
 struct DevCounters {
@@ -311,8 +313,9 @@ __global__ void __launch_bounds__(128) k_shadow(BvhDev bvh, Wave w, const uint32
 // sample k (0-based since the last reset) is stored when k == 0 and folded as m += (x - m) / float(k + 1) otherwise.
 // Paths that ended with a miss (hit record still says "no triangle") get their sky / sun-disc term here, from the ray
 // direction, throughput and previous-bounce pdf they died with (shade_miss).
-__global__ void __launch_bounds__(256) k_resolve(rptr_scene_params sp, TileMap tm, Wave w, float4 *accum, uint32_t first_sample, int32_t n_layers,
-                                                 DevCounters *dc, AovTarget aov, float3 cam_pos, int discard_history) {
+__global__ void __launch_bounds__(256) k_resolve(FrameParams fp, TileMap tm, Wave w, float4 *accum, uint32_t first_sample, int32_t n_layers,
+                                                 DevCounters *dc, AovTarget aov, int discard_history) {
+    const rptr_scene_params &sp = fp.sp;
     unsigned long long samples = 0;
     for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < (uint32_t)tm.local_pixels; lp += gridDim.x * blockDim.x) {
         const int32_t px = (int32_t)(lp % (uint32_t)tm.width);
@@ -327,8 +330,7 @@ __global__ void __launch_bounds__(256) k_resolve(rptr_scene_params sp, TileMap t
             float4 il = untouched ? f4(0.0f, 0.0f, 0.0f, 0.0f) : w.illum[slot];
             if (miss) {
                 if (aov.albedo_roughness && alpha == 0.0f && slot - aov.slot_lo < (uint32_t)tm.local_pixels) { // primary ray left the scene
-                    const float c[3] = {cam_pos.x, cam_pos.y, cam_pos.z};
-                    store_aov(aov, tm, slot, aov_of_miss(c));
+                    store_aov(aov, tm, slot, aov_of_miss(fp));
                 }
                 const float4 d = w.ray_d[slot];
                 const float4 thr = untouched ? f4(1.0f, 1.0f, 1.0f, 2.e16f) : w.thr[slot];
@@ -421,7 +423,8 @@ struct rptr_ctx {
     int32_t width = 0, height = 0;
     float4 *accum = nullptr;
     uchar4 *ldr = nullptr;
-    ushort4 *aov_images[2] = {nullptr, nullptr}; // RGBA16F: albedo + roughness, normal + depth (RenderGraphic::AOVBufferIndex 0, 1)
+    ushort4 *aov_images[3] = {nullptr, nullptr, nullptr}; // RGBA16F: albedo + roughness, normal + depth, motion + jitter (RenderGraphic::AOVBufferIndex)
+    float vp[16] = {0.0f}, vp_reference[16] = {0.0f}; // view_params.VP of the current / previous begin_frame (zero before the first: render_vulkan.cpp:103)
     int aov_buffers = 1;                         // option "aov_buffers": the reference always writes them (ENABLE_AOV_BUFFERS)
     // counters protocol (vulkan/render_vulkan.h:166-168)
     uint32_t frame_id = 0, frame_offset = 0, accumulated_spp = 0;
@@ -657,8 +660,7 @@ void rptr_cuda_destroy(rptr_ctx *ctx) {
     for (uint32_t *t : ctx->pointset_tables) cudaFree(t);
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
-    cudaFree(ctx->aov_images[0]);
-    cudaFree(ctx->aov_images[1]);
+    for (ushort4 *im : ctx->aov_images) cudaFree(im);
     cudaFree(ctx->dcounters);
     cudaEventDestroy(ctx->ev_begin);
     cudaEventDestroy(ctx->ev_end);
@@ -678,18 +680,17 @@ int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height) {
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
-    cudaFree(ctx->aov_images[0]);
-    cudaFree(ctx->aov_images[1]);
+    for (ushort4 *im : ctx->aov_images) cudaFree(im);
     ctx->accum = nullptr;
     ctx->ldr = nullptr;
-    ctx->aov_images[0] = ctx->aov_images[1] = nullptr;
+    ctx->aov_images[0] = ctx->aov_images[1] = ctx->aov_images[2] = nullptr;
     ctx->width = width;
     ctx->height = height;
     const size_t n = (size_t)width * height;
     CU(cudaMalloc((void **)&ctx->accum, n * sizeof(float4)));
     CU(cudaMalloc((void **)&ctx->ldr, n * sizeof(uchar4)));
     CU(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         CU(cudaMalloc((void **)&ctx->aov_images[i], n * sizeof(ushort4)));
         CU(cudaMemsetAsync(ctx->aov_images[i], 0, n * sizeof(ushort4), ctx->stream));
     }
@@ -888,6 +889,10 @@ int rptr_cuda_begin_frame(rptr_ctx *ctx, const rptr_camera_params *camera, const
         if (!freeze_frame) ctx->frame_offset += ctx->frame_id;
         ctx->frame_id = 0;
     }
+    // update_view_parameters (:2880-2941): VP_reference = the VP of the previous begin_frame (:1986-1998 pass last frame's
+    // view_params in either reprojection mode), then this frame's VP
+    memcpy(ctx->vp_reference, ctx->vp, sizeof(ctx->vp));
+    view_projection(ctx->camera, ctx->width, ctx->height, ctx->vp);
     ctx->in_frame = true;
     return 0;
 }
@@ -907,6 +912,8 @@ static FrameParams make_frame_params(const rptr_ctx *ctx) {
     fp.glossy_only_mode = ctx->params.glossy_only_mode;
     fp.enable_raster_taa = ctx->params.enable_raster_taa;
     if (fp.enable_raster_taa > 0) screen_jitter(ctx->frame_offset, ctx->frame_id, ctx->width, ctx->height, fp.screen_jitter);
+    memcpy(fp.vp, ctx->vp, sizeof(fp.vp));
+    memcpy(fp.vp_reference, ctx->vp_reference, sizeof(fp.vp_reference));
     fp.n_lights = ctx->n_lights;
     fp.bin_size = ctx->lighting.bin_size;
     fp.n_bins = (ctx->n_lights + fp.bin_size - 1) / fp.bin_size; // vulkan/pt_megakernel.glsl:102-103
@@ -974,8 +981,8 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
             CU(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), ctx->stream));
             CU(cudaMemsetAsync(w.hit_counts, 0, sizeof(uint32_t) * (depth + 2), ctx->stream));
             // AOV images: written by the first vertex of the frame's last sample layer (last wave, last layer)
-            AovTarget aov{nullptr, nullptr, 0u};
-            if (ctx->aov_buffers && first + nl == fp.batch) aov = AovTarget{ctx->aov_images[0], ctx->aov_images[1], (uint32_t)(nl - 1) * (uint32_t)tm.local_pixels};
+            AovTarget aov{nullptr, nullptr, nullptr, 0u};
+            if (ctx->aov_buffers && first + nl == fp.batch) aov = AovTarget{ctx->aov_images[0], ctx->aov_images[1], ctx->aov_images[2], (uint32_t)(nl - 1) * (uint32_t)tm.local_pixels};
             {
                 StageTimer t(ctx, 3);
                 Wave wr = w;
@@ -1023,7 +1030,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
                                      (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0) |
                                      (ctx->any_normal_map ? RPTR_FEAT_NORMAL_MAPS : 0);
-#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (hitq ? hitq : q), (hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, 0u}), tm, sort_tiles, (d == 0 ? 1 : 0)
+#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (hitq ? hitq : q), (hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, nullptr, 0u}), tm, sort_tiles, (d == 0 ? 1 : 0)
                     if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
                     else k_shade<RPTR_FEAT_ALL><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
@@ -1063,8 +1070,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
             if (join_shadow()) return 1;
             {
                 StageTimer t(ctx, 3);
-                k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp.sp, tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters, aov,
-                                                            make_float3(fp.cam_pos[0], fp.cam_pos[1], fp.cam_pos[2]),
+                k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp, tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters, aov,
                                                             ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_DISCARD_HISTORY);
                 ctx->launches++;
             }
@@ -1197,7 +1203,7 @@ size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst) {
 
 size_t rptr_cuda_readback_aov(rptr_ctx *ctx, int32_t aov_index, size_t n_elems, uint16_t *dst) {
     if (!ctx || !dst || !ctx->accum) return 0;
-    if (aov_index < 0 || aov_index > 1 || !ctx->aov_buffers) return 0; // AOVMotionJitterIndex: not produced by this backend
+    if (aov_index < 0 || aov_index > 2 || !ctx->aov_buffers) return 0;
     const size_t n = (size_t)ctx->width * ctx->height * 4;
     if (n_elems < n) return 0;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;

@@ -47,6 +47,70 @@ void view_params(const rptr_camera_params &cam, int w, int h, float *du_, float 
     tl_[0] = tl.x; tl_[1] = tl.y; tl_[2] = tl.z;
 }
 
+// ---- view_params.VP: vulkan/render_vulkan.cpp:2926-2930 ----------------------------------------------------------------------
+// GLToVulkan * glm::infinitePerspective(radians(fovy), aspect, 0.5f) * inverse(mat4(mat4x3(cross(dir, up), up, -dir, cam_pos))).
+// glm 0.9.9.8 is a build-time download of the reference (ext/CMakeLists.txt:18-21), not in its tree: its published algorithms
+// (column-major storage; operator* accumulating A[k] * B[j][k] left to right; the cofactor inverse of
+// detail::compute_inverse<4, 4>; infinitePerspectiveRH) are restated here with their operation order.
+namespace {
+inline float &at(float *m, int col, int row) { return m[4 * col + row]; }
+inline float at(const float *m, int col, int row) { return m[4 * col + row]; }
+void mat_mul(const float *a, const float *b, float *out) {
+    for (int j = 0; j < 4; ++j)
+        for (int r = 0; r < 4; ++r)
+            at(out, j, r) = ((at(a, 0, r) * at(b, j, 0) + at(a, 1, r) * at(b, j, 1)) + at(a, 2, r) * at(b, j, 2)) + at(a, 3, r) * at(b, j, 3);
+}
+void mat_inverse(const float *m, float *out) {
+    // 2 x 2 sub-determinants, named by the row / column pairs they span
+    const float c00 = at(m, 2, 2) * at(m, 3, 3) - at(m, 3, 2) * at(m, 2, 3), c02 = at(m, 1, 2) * at(m, 3, 3) - at(m, 3, 2) * at(m, 1, 3),
+                c03 = at(m, 1, 2) * at(m, 2, 3) - at(m, 2, 2) * at(m, 1, 3), c04 = at(m, 2, 1) * at(m, 3, 3) - at(m, 3, 1) * at(m, 2, 3),
+                c06 = at(m, 1, 1) * at(m, 3, 3) - at(m, 3, 1) * at(m, 1, 3), c07 = at(m, 1, 1) * at(m, 2, 3) - at(m, 2, 1) * at(m, 1, 3),
+                c08 = at(m, 2, 1) * at(m, 3, 2) - at(m, 3, 1) * at(m, 2, 2), c10 = at(m, 1, 1) * at(m, 3, 2) - at(m, 3, 1) * at(m, 1, 2),
+                c11 = at(m, 1, 1) * at(m, 2, 2) - at(m, 2, 1) * at(m, 1, 2), c12 = at(m, 2, 0) * at(m, 3, 3) - at(m, 3, 0) * at(m, 2, 3),
+                c14 = at(m, 1, 0) * at(m, 3, 3) - at(m, 3, 0) * at(m, 1, 3), c15 = at(m, 1, 0) * at(m, 2, 3) - at(m, 2, 0) * at(m, 1, 3),
+                c16 = at(m, 2, 0) * at(m, 3, 2) - at(m, 3, 0) * at(m, 2, 2), c18 = at(m, 1, 0) * at(m, 3, 2) - at(m, 3, 0) * at(m, 1, 2),
+                c19 = at(m, 1, 0) * at(m, 2, 2) - at(m, 2, 0) * at(m, 1, 2), c20 = at(m, 2, 0) * at(m, 3, 1) - at(m, 3, 0) * at(m, 2, 1),
+                c22 = at(m, 1, 0) * at(m, 3, 1) - at(m, 3, 0) * at(m, 1, 1), c23 = at(m, 1, 0) * at(m, 2, 1) - at(m, 2, 0) * at(m, 1, 1);
+    const float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+    const float f3_[4] = {c12, c12, c14, c15}, f4_[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+    float adj[16];
+    for (int k = 0; k < 4; ++k) {
+        const int col = k == 0 ? 1 : 0; // (m[1][r], m[0][r], m[0][r], m[0][r])
+        const float v0 = at(m, col, 0), v1 = at(m, col, 1), v2 = at(m, col, 2), v3 = at(m, col, 3);
+        const float sa = (k & 1) ? -1.0f : 1.0f, sb = -sa;
+        at(adj, 0, k) = ((v1 * f0[k] - v2 * f1[k]) + v3 * f2[k]) * sa;
+        at(adj, 1, k) = ((v0 * f0[k] - v2 * f3_[k]) + v3 * f4_[k]) * sb;
+        at(adj, 2, k) = ((v0 * f1[k] - v1 * f3_[k]) + v3 * f5[k]) * sa;
+        at(adj, 3, k) = ((v0 * f2[k] - v1 * f4_[k]) + v2 * f5[k]) * sb;
+    }
+    const float d0 = at(m, 0, 0) * at(adj, 0, 0), d1 = at(m, 0, 1) * at(adj, 1, 0), d2 = at(m, 0, 2) * at(adj, 2, 0), d3 = at(m, 0, 3) * at(adj, 3, 0);
+    const float inv_det = 1.0f / ((d0 + d1) + (d2 + d3));
+    for (int i = 0; i < 16; ++i) out[i] = adj[i] * inv_det;
+}
+} // namespace
+
+void view_projection(const rptr_camera_params &cam, int w, int h, float *vp) {
+    const float3 dir = ld3(cam.dir), up = ld3(cam.up), side = cross(dir, up);
+    const float view[16] = {side.x, side.y, side.z, 0.0f, up.x, up.y, up.z, 0.0f, -dir.x, -dir.y, -dir.z, 0.0f, cam.pos[0], cam.pos[1], cam.pos[2], 1.0f};
+    float inv_view[16];
+    mat_inverse(view, inv_view);
+    // infinitePerspectiveRH(fovy, aspect, zNear)
+    const float fovy = cam.fovy * 0.01745329251994329576923690768489f, aspect = (float)w / (float)h, z_near = 0.5f;
+    const float range = tanf(fovy / 2.0f) * z_near;
+    const float left = -range * aspect, right = range * aspect, bottom = -range, top = range;
+    float proj[16] = {0.0f};
+    at(proj, 0, 0) = (2.0f * z_near) / (right - left);
+    at(proj, 1, 1) = (2.0f * z_near) / (top - bottom);
+    at(proj, 2, 2) = -1.0f;
+    at(proj, 2, 3) = -1.0f;
+    at(proj, 3, 2) = -2.0f * z_near;
+    float to_vulkan[16] = {0.0f};
+    at(to_vulkan, 0, 0) = 1.0f; at(to_vulkan, 1, 1) = -1.0f; at(to_vulkan, 2, 2) = 0.5f; at(to_vulkan, 3, 3) = 1.0f; at(to_vulkan, 3, 2) = 0.5f;
+    float clip[16];
+    mat_mul(to_vulkan, proj, clip);
+    mat_mul(clip, inv_view, vp);
+}
+
 // ---- emitters: librender/lights.cpp ---------------------------------------------------------------------------------------
 namespace {
 

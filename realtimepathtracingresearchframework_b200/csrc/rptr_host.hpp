@@ -43,6 +43,8 @@ void build_bvh(HostScene &s);
 
 // update_view_parameters (vulkan/render_vulkan.cpp:2880-2894): out = du, dv, top_left
 void view_params(const rptr_camera_params &cam, int w, int h, float *du, float *dv, float *tl);
+// view_params.VP (vulkan/render_vulkan.cpp:2926-2930), column-major 4 x 4
+void view_projection(const rptr_camera_params &cam, int w, int h, float *vp);
 
 // raster-TAA screen jitter of the frame (vulkan/render_vulkan.cpp:2917-2926); halton_23(k) = entry k of librender/halton.h
 void screen_jitter(uint32_t frame_offset, uint32_t frame_id, int w, int h, float *out);

@@ -63,6 +63,8 @@ struct FrameParams {
     int32_t n_lights, n_bins, bin_size;
     int32_t transmission;
     float screen_jitter[2]; // view_params.screen_jitter (raster TAA; zero unless enable_raster_taa)
+    float vp[16];           // view_params.VP, column-major (render_vulkan.cpp:2926-2930)
+    float vp_reference[16]; // view_params.VP_reference: the VP of the previous begin_frame (:1986-1998, :2911)
     int32_t rng_variant;  // RenderBackendOptions::rng_variant (librender/render_params.glsl.h:34-37)
     PointsetTables pts;   // tables of the Sobol / blue-noise samplers (null unless rng_variant needs them)
     rptr_scene_params sp; // sun_radiance[3] already carries the light-count rule (vulkan/render_sky.cpp:67-70)
@@ -702,11 +704,32 @@ struct AovSample {
     float roughness; // ior != 1 ? roughness : 1
     float3 normal;  // interaction.n
     float depth;    // |p - cam_pos|
+    float motion[2]; // screen-space motion of the vertex against the reference view (accumulate.glsl:77-87)
+    float jitter[2]; // view_params.screen_jitter
 };
-RPTR_HD AovSample aov_of_miss(const float *cam_pos) { // store_geometry_aovs(0, vec3(2e32), 0) + store_material_aovs(0, 1, 1)
+// mat4 * vec4(p, 1) in RPTR-FP order: columns accumulated left to right
+RPTR_HD void project_point(const float *m, float3 p, float &x, float &y, float &w) {
+    x = ((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12] * 1.0f;
+    y = ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13] * 1.0f;
+    w = ((m[3] * p.x + m[7] * p.y) + m[11] * p.z) + m[15] * 1.0f;
+}
+// store_motion_jitter_aovs (vulkan/accumulate.glsl:77-87) with motion_vector = 0 (static geometry)
+RPTR_HD void aov_motion_jitter(const FrameParams &fp, float3 position, AovSample &a) {
+    const float3 moved = position + f3(0.0f);
+    float rx, ry, rw, cx, cy, cw;
+    project_point(fp.vp_reference, moved, rx, ry, rw);
+    project_point(fp.vp, position, cx, cy, cw);
+    const float rd = rw < 0.0f ? 0.0f : rw, cd = cw < 0.0f ? 0.0f : cw; // max(w, 0)
+    a.motion[0] = rx / rd - cx / cd;
+    a.motion[1] = ry / rd - cy / cd;
+    a.jitter[0] = fp.screen_jitter[0];
+    a.jitter[1] = fp.screen_jitter[1];
+}
+RPTR_HD AovSample aov_of_miss(const FrameParams &fp) { // store_geometry_aovs(0, vec3(2e32), 0) + store_material_aovs(0, 1, 1)
     AovSample a;
     a.albedo = f3(0.0f); a.roughness = 1.0f; a.normal = f3(0.0f);
-    a.depth = length(f3(2.e32f) - f3(cam_pos[0], cam_pos[1], cam_pos[2]));
+    a.depth = length(f3(2.e32f) - ld3(fp.cam_pos));
+    aov_motion_jitter(fp, f3(2.e32f), a);
     return a;
 }
 
@@ -829,6 +852,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
         aov->depth = length(ip - ld3(fp.cam_pos));
         aov->albedo = ps.thr * mat.base_color;
         aov->roughness = mat.ior != 1.0f ? mat.roughness : 1.0f;
+        aov_motion_jitter(fp, ip, *aov);
     }
     const float p_sun = sp.sun_radiance[3];
     if (output_channel == 0 && !is_zero(emit)) {
@@ -929,7 +953,7 @@ RPTR_HD ShadeResult shade_vertex(const FrameParams &fp, const SceneDev &sc, Path
                                 const Tri *tri, ShadowRay &sh, AovSample *aov = nullptr) {
     sh.tmax = -1.0f;
     if (!tri) {
-        if (aov && ps.bounce == 0) *aov = aov_of_miss(fp.cam_pos);
+        if (aov && ps.bounce == 0) *aov = aov_of_miss(fp);
         ps.illum = shade_miss(fp.sp, ps.illum, ps.thr, ps.d, ps.prev_pdf);
         return SHADE_TERMINATE;
     }

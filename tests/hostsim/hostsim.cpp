@@ -22,6 +22,7 @@ struct hostsim_args { // same layout as oracle_render_args
     int32_t transmission, n_threads;
     int32_t rng_variant, batch_spp;
     const uint32_t *pointset_tables[4];
+    float vp_reference[16];
 };
 
 struct hostsim_scene { HostScene hs; std::vector<GeomInst> gi; };
@@ -84,6 +85,8 @@ static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
     fp.pts.sobol_tile_invert = a->pointset_tables[1];
     fp.pts.bn_sobol = a->pointset_tables[2];
     fp.pts.bn_scrambling = a->pointset_tables[3];
+    view_projection(a->camera, a->width, a->height, fp.vp);
+    memcpy(fp.vp_reference, a->vp_reference, sizeof(fp.vp_reference));
     fp.sp = a->scene_params;
     if (fp.n_lights > 0) fp.sp.sun_radiance[3] *= 0.5f;
     else fp.sp.sun_radiance[3] = 1.0f;
@@ -92,7 +95,7 @@ static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
 
 // un-averaged sample layer `sample_index` for the region; rgba is W*H*4; aov (optional) = W*H*8 floats per pixel:
 // albedo.rgb, roughness, normal.xyz, depth of the first path vertex (the values behind the fp16 AOV images)
-static int render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba, float *aov_out) {
+static int render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba, float *aov_out, int aov_stride = 8) {
     FrameParams fp = make_frame(s, a);
     SceneDev sc{s->gi.data(), s->hs.materials.data(), s->hs.lights.data(), reinterpret_cast<const float4 *>(s->hs.normal_texels.data())};
     BvhDev bvh{s->hs.nodes.data(), s->hs.leaf_tris.data(), (int32_t)s->hs.nodes.size(), (int32_t)s->hs.leaf_tris.size()};
@@ -121,8 +124,9 @@ static int render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t
             float *px = rgba + 4 * ((size_t)y * a->width + x);
             px[0] = ps.illum.x; px[1] = ps.illum.y; px[2] = ps.illum.z; px[3] = ps.bounce == 0 ? 0.0f : 1.0f;
             if (aov_out) {
-                const float m[8] = {as.albedo.x, as.albedo.y, as.albedo.z, as.roughness, as.normal.x, as.normal.y, as.normal.z, as.depth};
-                memcpy(aov_out + 8 * ((size_t)y * a->width + x), m, sizeof(m));
+                const float m[12] = {as.albedo.x, as.albedo.y, as.albedo.z, as.roughness, as.normal.x, as.normal.y, as.normal.z, as.depth,
+                                     as.motion[0], as.motion[1], as.jitter[0], as.jitter[1]};
+                memcpy(aov_out + (size_t)aov_stride * ((size_t)y * a->width + x), m, sizeof(float) * aov_stride);
             }
         }
     return 0;
@@ -133,6 +137,11 @@ int hostsim_render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_
 int hostsim_render_sample_aov(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba, float *aov) {
     return render_sample(s, a, sample_index, rgba, aov);
 }
+// aov = 12 floats per pixel: the 8 above + motion.xy, screen_jitter.xy (the motion / jitter image)
+int hostsim_render_sample_aov3(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba, float *aov) {
+    return render_sample(s, a, sample_index, rgba, aov, 12);
+}
+void hostsim_view_projection(const rptr_camera_params *cam, int32_t w, int32_t h, float *out) { view_projection(*cam, w, h, out); }
 
 // sampler calls replayed through the product's rptr_pointsets.cuh (same protocol as oracle_pointset_replay)
 int hostsim_pointset_replay(int variant, const uint32_t *const *tables, uint32_t sample_index, uint32_t frame_id, uint32_t frame_offset, uint32_t px,

@@ -516,14 +516,53 @@ def test_aov_images_readback(oracle):
     with np.errstate(over="ignore"):
         assert np.array_equal(r.aov(1).view(np.uint16), nd2.astype(np.float16).view(np.uint16))
         assert np.array_equal(r.aov(0).view(np.uint16), ar2.astype(np.float16).view(np.uint16))
-    # motion / jitter AOV is not produced; too-small buffers and the option switch return 0 like the reference's readback
-    assert r.readback_aov(2, np.zeros((H, W, 4), np.float16)) == 0
+    # an index outside AOVBufferIndex, too-small buffers and the option switch return 0 like the reference's readback
+    assert r.readback_aov(3, np.zeros((H, W, 4), np.float16)) == 0
     assert r.readback_aov(0, np.zeros(16, np.float16)) == 0
     r.set_option("aov_buffers", 0)
     assert r.readback_aov(0, np.zeros((H, W, 4), np.float16)) == 0
     # the images do not disturb the beauty pass
     ref, _ = o.render(W, H, s.camera, sp, spp=6, batch_spp=5)  # frames of 5 + 1 samples: view_params.frame_id = 0 x5, then 5
     assert_identical(r.framebuffer(), ref, "beauty with AOV images on")
+
+
+def test_motion_jitter_aov_image(oracle):
+    """AOVMotionJitterIndex (vulkan/accumulate.glsl:77-87): (projection on the previous frame's view - projection on this
+    frame's, screen_jitter) of the first vertex, RGBA16F.  VP_reference follows begin_frame (render_vulkan.cpp:1986-1998):
+    zero before the first frame (NaN motion), then the previous frame's VP.  NaN payloads of the half conversion are not
+    compared (imageStore of a NaN is implementation-defined), NaN positions are."""
+    def same_half(got16, want32, what):
+        with np.errstate(over="ignore", invalid="ignore"):
+            want16 = want32.astype(np.float16)
+        nan = np.isnan(want16)
+        assert np.array_equal(np.isnan(got16), nan), what
+        assert np.array_equal(got16.view(np.uint16)[~nan], want16.view(np.uint16)[~nan]), what
+
+    s = scenes.random_triangles(20000)
+    W, H = 320, 180
+    sp = load_sky_fit()
+    o = oracle.OracleScene(s)
+    r = make_backend(s, W, H)
+    r.render_spp(s.camera, 1)
+    _, nd, want = o.render_aov3(W, H, s.camera, sp, 0, first_sample=0)
+    same_half(r.aov(2), want, "first frame")
+    assert np.isnan(want[..., :2]).all()
+    cam2 = T.RenderCameraParams.from_buffer_copy(s.camera)
+    cam2.pos[0] += 0.05
+    taa = T.RenderParams()
+    taa.enable_raster_taa = 1
+    r.params.enable_raster_taa = 1
+    r.render_spp(cam2, 2, batch_spp=2, reset=False)  # frame_id 1: samples 1 and 2, the images keep sample 2
+    ar, nd, want = o.render_aov3(W, H, cam2, sp, 2, first_sample=1, params=taa, vp_reference=oracle.view_projection(s.camera, W, H))
+    same_half(r.aov(2), want, "moved camera + raster TAA")
+    same_half(r.aov(1), nd, "normal / depth beside it")
+    hit = np.isfinite(nd[..., 3])
+    assert (want[hit][:, 0] > 0).all() and (want[..., 2:] != 0).any()
+    r.params.enable_raster_taa = 0
+    r.render_spp(cam2, 1, reset=True)  # same camera again: static
+    _, nd, want = o.render_aov3(W, H, cam2, sp, 0, first_sample=0, frame_offset=3, vp_reference=oracle.view_projection(cam2, W, H))
+    same_half(r.aov(2), want, "static camera")
+    assert (r.aov(2)[np.isfinite(nd[..., 3])] == 0).all()
 
 
 def test_reprojection_mode_discard_history(oracle):
