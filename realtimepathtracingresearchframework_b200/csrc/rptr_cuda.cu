@@ -378,13 +378,27 @@ __device__ __forceinline__ float4 half4_to_float4(ushort4 h) {
     return f4(__half2float(__ushort_as_half(h.x)), __half2float(__ushort_as_half(h.y)), __half2float(__ushort_as_half(h.z)),
               __half2float(__ushort_as_half(h.w)));
 }
-__global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, const ushort4 *aov_ar, const ushort4 *aov_nd, uchar4 *out, uint32_t n,
-                                                  float exposure_scale, int output_channel, int output_moment) {
+// tonemap() of rendering/postprocess/tonemapping_utils.glsl:9-32 (modes: postprocess/tonemapping.h:7-9)
+__device__ __forceinline__ void tonemap(int mode, float4 &c) {
+    if (mode == 2) { // FAST_TONE_MAPPING
+        c.x = c.x / (1.0f + c.x); c.y = c.y / (1.0f + c.y); c.z = c.z / (1.0f + c.z);
+    } else if (mode == 1) { // NEUTRAL_TONE_MAPPING
+        const float level = fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, 1.0f));
+        const float a = 0.1f * log2f(level);
+        const float scale = (a * (1.0f - 0.8f) + 1.0f * 0.8f) / level; // mix(a, 1, 0.8) / level
+        c.x *= scale; c.y *= scale; c.z *= scale;
+    }
+}
+__global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, const ushort4 *aov_ar, const ushort4 *aov_nd, const ushort4 *aov_mj, uchar4 *out,
+                                                  uint32_t n, float exposure_scale, int output_channel, int output_moment, int tone_mapping_mode,
+                                                  float width, float height) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 c = accum[i];
+        c.w = fminf(c.w, 1.0f);
         if (!(c.w >= 0.0f)) continue;
         if (output_channel == 0) {
             c.x *= exposure_scale; c.y *= exposure_scale; c.z *= exposure_scale;
+            if (tone_mapping_mode >= 0) tonemap(tone_mapping_mode, c);
         } else if (output_channel == 1 && aov_ar) {
             c = half4_to_float4(aov_ar[i]);
             if (output_moment != 0) c.x = c.y = c.z = c.w;
@@ -392,6 +406,13 @@ __global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, const ush
             c = half4_to_float4(aov_nd[i]);
             if (output_moment != 0) c.x = c.y = c.z = c.w * 0.05f;
             else { c.x = c.x * 0.5f + 0.5f; c.y = c.y * 0.5f + 0.5f; c.z = c.z * 0.5f + 0.5f; }
+        } else if (output_channel == 3 && aov_mj) { // OUTPUT_CHANNEL_MOTION_JITTER (process_samples.comp:163-178)
+            const float4 m = half4_to_float4(aov_mj[i]);
+            if (output_moment == 0) c = f4(fabsf(10.0f * m.x), fabsf(10.0f * m.y), 0.0f, 1.0f);
+            else { // undo the scaling of update_view_parameters: back to the Halton point in [0, 1)
+                const float jx = (m.z + 1.0f / width) * (width / 2.0f), jy = (m.w + 1.0f / height) * (height / 2.0f);
+                c = f4(jx * 0.5f + 0.5f, jy * 0.5f + 0.5f, 0.0f, 1.0f);
+            }
         } else if (output_channel == 3) {
             c = f4(0.0f, 0.0f, 0.0f, 1.0f);
         }
@@ -1193,8 +1214,10 @@ size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst) {
     if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
     const float scale = exp2f(ctx->params.exposure);
     const bool aov_on = ctx->aov_buffers != 0;
-    k_to_srgb8<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->accum, aov_on ? ctx->aov_images[0] : nullptr, aov_on ? ctx->aov_images[1] : nullptr, ctx->ldr,
-                                                          (uint32_t)(size / 4), scale, ctx->params.output_channel, ctx->params.output_moment);
+    k_to_srgb8<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->accum, aov_on ? ctx->aov_images[0] : nullptr, aov_on ? ctx->aov_images[1] : nullptr,
+                                                          aov_on ? ctx->aov_images[2] : nullptr, ctx->ldr, (uint32_t)(size / 4), scale,
+                                                          ctx->params.output_channel, ctx->params.output_moment, ctx->params.early_tone_mapping_mode,
+                                                          (float)ctx->width, (float)ctx->height);
     ctx->launches++;
     if (cudaMemcpyAsync(dst, ctx->ldr, size, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;

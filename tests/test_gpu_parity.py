@@ -623,8 +623,9 @@ def test_c3_progressive_4096spp(oracle):
 
 
 def test_ldr_framebuffer_readback(oracle):
-    """readback_framebuffer(uint8*): the display chain of process_samples.comp:138-200 -- exposure + sRGB for the colour
-    channel, the AOV images for output channels 1 / 2.  pow() is not part of the arithmetic contract: +-1 code value."""
+    """readback_framebuffer(uint8*): the display chain of process_samples.comp:138-200 -- exposure, early tone mapping and
+    sRGB for the colour channel, the AOV images for output channels 1 / 2 / 3.  pow() / log2() are not part of the arithmetic
+    contract: +-1 code value."""
     s = scenes.random_triangles(20000)
     W, H = 256, 144
     r = make_backend(s, W, H)
@@ -643,6 +644,29 @@ def test_ldr_framebuffer_readback(oracle):
     assert r.readback_framebuffer(ldr) == ldr.size
     want = to_srgb8(img[..., :3] * np.float32(2.0 ** 0.5), img[..., 3])
     assert np.abs(ldr.astype(np.int32) - want).max() <= 1
+    # early_tone_mapping_mode (postprocess/tonemapping_utils.glsl): 0 none, 1 neutral, 2 fast (Reinhard)
+    for mode in (0, 1, 2):
+        r.params.early_tone_mapping_mode = mode
+        r.render_spp(s.camera, 4)
+        cur = r.framebuffer()
+        lin = cur[..., :3].astype(np.float64) * 2.0 ** 0.5
+        level = np.maximum(lin.max(-1), 1.0)[..., None]
+        want_lin = {0: lin, 1: lin * (0.1 * np.log2(level) * 0.2 + 0.8) / level, 2: lin / (1.0 + lin)}[mode]
+        got = np.zeros((H, W, 4), np.uint8)
+        assert r.readback_framebuffer(got) == got.size
+        assert np.abs(got.astype(np.int32) - to_srgb8(want_lin, cur[..., 3])).max() <= 1, "tone mapping mode %d" % mode
+    r.params.early_tone_mapping_mode = -1
+    # motion / jitter display (output_channel 3): |10 * motion| from the AOV image; moment 1 shows the Halton point
+    r.params.output_channel = 3
+    cam2 = T.RenderCameraParams.from_buffer_copy(s.camera)
+    cam2.pos[0] += 0.05
+    r.render_spp(cam2, 1)
+    mj = r.aov(2).astype(np.float32)
+    got = np.zeros((H, W, 4), np.uint8)
+    assert r.readback_framebuffer(got) == got.size
+    want3 = to_srgb8(np.nan_to_num(np.dstack([np.abs(10 * mj[..., 0]), np.abs(10 * mj[..., 1]), np.zeros((H, W), np.float32)]), posinf=1.0), np.ones((H, W)))
+    ok = np.isfinite(mj[..., :2]).all(-1)
+    assert ok.any() and np.abs(got.astype(np.int32) - want3)[ok].max() <= 1 and got[ok][:, 0].max() > 0
     # normal / depth display from the AOV image (the parameters of the last frame decide, as in process_samples.comp)
     r.params.output_channel = 2
     r.render_spp(s.camera, 1)
