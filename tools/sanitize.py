@@ -1,0 +1,88 @@
+"""A small tour of every kernel variant for compute-sanitizer (memcheck / racecheck / initcheck), sized to finish under the
+tool's 10-100x slow-down:
+
+    compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize.py
+
+Covers: persistent trace kernels (closest / any-hit, with and without the alpha filter), the one-ray-per-thread kernels,
+k_shade in its three feature variants (LCG, triangle lights, ALL = QMC + AOV + transmission + normal maps), raygen,
+resolve (progressive + discard-history), the tile sort of multi-material scenes, LDR / AOV read-backs, ray queries, the
+device LBVH builder and screen-space sharding (tile_rank / tile_world)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from realtimepathtracingresearchframework_b200 import RenderCuda, load_pointset_tables, scenes, types as T  # noqa: E402
+
+W, H = 96, 54
+
+
+def backend(scene, **options):
+    r = RenderCuda(device=0)
+    r.initialize(W, H)
+    for k, v in options.items():
+        r.set_option(k, v)
+    r.set_scene(scene)
+    r.update_config(T.SceneConfig(sun_dir=(0.35, 0.8, 0.45)))
+    return r
+
+
+def tour():
+    tables = load_pointset_tables()
+    n = 0
+    # LCG path, host SAH and device LBVH, persistent and one-ray-per-thread kernels, several waves per frame
+    for opts in (dict(), dict(bvh_builder=1), dict(trace_kernel=1), dict(wave_paths=W * H), dict(overlap_shadow=0, stage_timing=1)):
+        r = backend(scenes.random_triangles(3000), **opts)
+        r.render_spp(scenes.random_triangles(3000).camera, 3, batch_spp=3)
+        assert np.isfinite(r.framebuffer()).all()
+        r.close()
+        n += 1
+    # alpha-tested, textured, normal-mapped materials with every pointset; AOV + LDR read-backs
+    s = scenes.alpha_tested_soup(4000)
+    for variant in (0, 1, 2, 3):
+        r = backend(s, transmission=1)
+        if variant:
+            r.set_rng_variant(variant, tables)
+        r.params.enable_raster_taa = variant & 1
+        r.render_spp(s.camera, 2, batch_spp=2)
+        for i in range(3):
+            r.aov(i)
+        for channel in (0, 1, 2, 3):
+            r.params.output_channel = channel
+            r.params.early_tone_mapping_mode = channel - 1
+            r.render_spp(s.camera, 1, reset=False)
+            ldr = np.zeros((H, W, 4), np.uint8)
+            assert r.readback_framebuffer(ldr) == ldr.size
+        r.close()
+        n += 1
+    # triangle-light NEE (binned RIS), instancing, discard-history resolve, ray queries
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from test_hostsim_parity import emissive_soup
+    s = emissive_soup()
+    r = backend(s)
+    r.params.reprojection_mode = 1
+    r.render_spp(s.camera, 2)
+    rng = np.random.default_rng(1)
+    q = np.zeros((500, 8), np.float32)
+    q[:, 0:3] = rng.uniform(-2, 2, (500, 3))
+    d = rng.normal(size=(500, 3))
+    q[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    q[:, 7] = 1e20
+    q[::7, 3] = -1.0  # skipped queries
+    r.trace_ray(q)
+    r.close()
+    n += 1
+    # screen-space sharding: two ranks of the same frame
+    s = scenes.cornell_box()
+    for rank in (0, 1):
+        r = backend(s, tile_world=2, tile_rank=rank, tile_rows=8)
+        r.render_spp(s.camera, 2)
+        r.framebuffer()
+        r.close()
+        n += 1
+    return n
+
+
+if __name__ == "__main__":
+    print("sanitize tour: %d contexts ok" % tour())
