@@ -12,7 +12,10 @@
 // per-vertex shading function shade_base_material() with its LCG draw order.
 // "PARITY UNPINNED" (restated only, no reference-executed check possible): the loop of pt_megakernel.glsl around that function
 // (ray generation, normal fix-ups, ray epsilons, Russian roulette, sky on a miss), process_samples.comp / accumulate.glsl, the
-// texture unit (UNORM8 / sRGB decode of a texel), and the ray/triangle routine, which the reference does not contain at all.
+// texture unit (UNORM8 / sRGB decode of a texel), the ray/triangle routine, which the reference does not contain at all, and
+// view_params.VP / VP_reference behind the motion / jitter AOV image: built with glm 0.9.9.8, a configure-time download of
+// the reference (ext/CMakeLists.txt:18-21) that is not in its tree -- glm's published operator*, inverse and
+// infinitePerspective are restated (oracle_view_projection) and checked against the camera model only.
 //
 // Structure follows the reference megakernel (one sequential loop per pixel sample), NOT the CUDA wavefront.
 #include "shading_oracle.h"
