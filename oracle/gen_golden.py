@@ -172,6 +172,22 @@ def gen_vectors(n=512, seed=1234):
         for i in range(n):
             R.ref_sample_sun_dir(fa(*sd), C.c_float(float(sp.sun_cos_angle)), fa(*u4[i, :2]), sun[i].ctypes.data_as(po.f32p))
         out["sky%d_sun_samples" % ci] = sun
+        # compute_sky_illum (vulkan/pt_megakernel.glsl:113-149) executed from the reference: the sky dirs plus directions inside
+        # and around the sun disc, previous-bounce pdfs from "camera ray" (2e16) down to diffuse-like values, p_sun = 1 and 0.5
+        rs = np.random.default_rng(977 + ci)  # own stream: the sections below keep their inputs
+        dirs = sky_dirs.copy()
+        dirs[8:72] = unit(sd + 0.006 * rs.normal(size=(64, 3))).astype(np.float32)
+        dirs[72] = sd
+        pdfs = np.where(rs.random(n) < 0.25, 2.0e16, 10.0 ** rs.uniform(-2, 4, n)).astype(np.float32)
+        ill = np.zeros((2, n, 3), np.float32)
+        for k, p_sun in enumerate((1.0, 0.5)):
+            sp2 = T.SceneParams.from_buffer_copy(sp)
+            sp2.sun_radiance[3] = p_sun
+            for i in range(n):
+                R.ref_compute_sky_illum(C.byref(sp2), fa(0.0, 0.0, 0.0), fa(*dirs[i]), C.c_float(float(pdfs[i])), ill[k, i].ctypes.data_as(po.f32p))
+        out["sky%d_illum_dirs" % ci] = dirs
+        out["sky%d_illum_pdfs" % ci] = pdfs
+        out["sky%d_illum" % ci] = ill
     out["sky_dirs"] = sky_dirs
     # --- next-event estimation: rendering/mc/nee.glsl:32-90 (sample_direct_light) executed from the reference ---
     n_nee = 768

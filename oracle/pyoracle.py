@@ -82,6 +82,7 @@ def lib():
         L.oracle_sample_direct_light.argtypes = [C.POINTER(T.BaseMaterial)] + [f32p] * 8 + [C.c_float, f32p, C.c_void_p, C.c_int, C.c_int, f32p]
         L.oracle_unpack_material.argtypes = [C.POINTER(T.BaseMaterial), C.POINTER(T.TextureDesc), C.c_int, C.c_int, f32p]
         L.oracle_skymodel_radiance.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, f32p]
+        L.oracle_compute_sky_illum.argtypes = [C.POINTER(T.SceneParams), f32p, C.c_float, f32p]
         L.oracle_sample_sun_dir.argtypes = [f32p, C.c_float, f32p, f32p]
         L.oracle_dequantize_position.argtypes = [C.c_uint64, f32p, f32p, f32p]
         L.oracle_dequantize_normal.argtypes = [C.c_uint32, f32p]
@@ -116,6 +117,7 @@ def ref():
         R.ref_sample_direct_light.argtypes = [C.POINTER(T.BaseMaterial)] + [f32p] * 8 + [C.c_float, f32p, C.c_void_p, C.c_int, C.c_int, f32p]
         R.ref_unpack_material.argtypes = [C.POINTER(T.BaseMaterial), f32p, C.c_int, C.c_int, f32p]
         R.ref_skymodel_radiance.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, f32p]
+        R.ref_compute_sky_illum.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, C.c_float, f32p]
         R.ref_sample_sun_dir.argtypes = [f32p, C.c_float, f32p, f32p]
         R.ref_pointset_table.argtypes = [C.c_int, C.POINTER(C.c_uint32)]
         R.ref_pointset_replay.argtypes = [C.c_int] + [C.c_uint32] * 7 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, f32p,

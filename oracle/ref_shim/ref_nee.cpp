@@ -4,6 +4,9 @@
 // rendering/lights/{sun,tri}.glsl and the glTF BSDF registered as MATERIAL_TYPE, exactly as vulkan/pt_megakernel.glsl:22-109
 // assembles them.  Supplied here: the scene_params uniform block (sun + light count), the binned light buffer, and
 // raytrace_test_visibility(), which records the shadow-ray query and reports "visible" (visibility is the trace stage's job).
+// Also executed here: compute_sky_illum(), the miss shading of vulkan/pt_megakernel.glsl (the one self-contained function of
+// that file; the rest needs rayQueryEXT).  The Makefile cuts exactly that function out of the file where it lies into the
+// git-ignored build directory oracle/_ref/gen/ for the duration of the compile and deletes it afterwards.
 #include <glm/glm.hpp>
 #include <cstdint>
 #include <cstring>
@@ -19,11 +22,13 @@ typedef unsigned int uint;
 #include "rendering/bsdfs/base_material.h.glsl"
 #include "rendering/bsdfs/hit_point.glsl"
 #include "rendering/lights/tri.glsl"
+#include "rendering/lights/sky_model_arhosek/sky_model.glsl"
 
-struct SceneParamsStandIn { // the members of SceneParams (vulkan/gpu_params.glsl:120-131) that nee.glsl reads
+struct SceneParamsStandIn { // the members of SceneParams (vulkan/gpu_params.glsl:120-131) that nee.glsl / compute_sky_illum read
     vec3 sun_dir;
     float sun_cos_angle;
     vec4 sun_radiance;
+    SkyModelParams sky_params;
 };
 static SceneParamsStandIn scene_params;
 static const TriLightData *g_lights = nullptr;
@@ -47,6 +52,7 @@ inline bool raytrace_test_visibility(const vec3 from, const vec3 dir, float dist
     g_query_from = from; g_query_dir = dir; g_query_dist = dist; ++g_queries;
     return true;
 }
+#include "gen/compute_sky_illum.inc"
 }
 } // namespace refnee
 
@@ -89,6 +95,20 @@ void ref_sample_direct_light(const rptr_base_material *p, const float *hp, const
     out[6] = aux.light_dist; out[7] = aux.mis_pdf; out[8] = (float)g_queries;
     out[9] = g_query_from.x; out[10] = g_query_from.y; out[11] = g_query_from.z;
     out[12] = g_query_dir.x; out[13] = g_query_dir.y; out[14] = g_query_dir.z; out[15] = g_query_dist;
+}
+
+// compute_sky_illum(ray_origin, ray_dir, prev_bsdf_pdf) (vulkan/pt_megakernel.glsl:113-149) with the fitted sky block of sp;
+// sp->sun_radiance[3] = p_sun as the shader sees it (after the light-count rule of vulkan/render_sky.cpp:67-70).
+void ref_compute_sky_illum(const rptr_scene_params *sp, const float *ray_origin, const float *ray_dir, float prev_bsdf_pdf, float *out) {
+    using namespace refnee;
+    scene_params.sun_dir = glm::vec3(sp->sun_dir[0], sp->sun_dir[1], sp->sun_dir[2]);
+    scene_params.sun_cos_angle = sp->sun_cos_angle;
+    scene_params.sun_radiance = glm::vec4(sp->sun_radiance[0], sp->sun_radiance[1], sp->sun_radiance[2], sp->sun_radiance[3]);
+    for (int i = 0; i < 9; ++i)
+        scene_params.sky_params.configs[i] = glm::vec4(sp->sky_configs[i][0], sp->sky_configs[i][1], sp->sky_configs[i][2], sp->sky_configs[i][3]);
+    scene_params.sky_params.radiances = glm::vec4(sp->sky_radiances[0], sp->sky_radiances[1], sp->sky_radiances[2], sp->sky_radiances[3]);
+    glm::vec3 r = notr::compute_sky_illum(glm::vec3(ray_origin[0], ray_origin[1], ray_origin[2]), glm::vec3(ray_dir[0], ray_dir[1], ray_dir[2]), prev_bsdf_pdf);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
 
 } // extern "C"

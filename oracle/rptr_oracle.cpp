@@ -8,10 +8,10 @@
 // through the fixtures of tests/golden/ (tests/test_oracle_golden.py, tests/test_pointsets.py): LCG / murmur, the Sobol /
 // Z-order Sobol / blue-noise samplers and their tables, the Halton screen jitter, dequantisation, hit attributes, the glTF BSDF
 // (with and without transmission), triangle-light solid angles / sampling / binned RIS, host light binning, the sky fit and
-// skymodel_radiance, sun sampling, the material decode with texture handles, sample_direct_light (nee.glsl) and the complete
-// per-vertex shading function shade_base_material() with its LCG draw order.
+// skymodel_radiance, sun sampling, the material decode with texture handles, sample_direct_light (nee.glsl), the complete
+// per-vertex shading function shade_base_material() with its LCG draw order, and the miss shading compute_sky_illum().
 // "PARITY UNPINNED" (restated only, no reference-executed check possible): the loop of pt_megakernel.glsl around that function
-// (ray generation, normal fix-ups, ray epsilons, Russian roulette, sky on a miss), process_samples.comp / accumulate.glsl, the
+// (ray generation, normal fix-ups, ray epsilons, Russian roulette), process_samples.comp / accumulate.glsl, the
 // texture unit (UNORM8 / sRGB decode of a texel), the ray/triangle routine, which the reference does not contain at all, and
 // view_params.VP / VP_reference behind the motion / jitter AOV image: built with glm 0.9.9.8, a configure-time download of
 // the reference (ext/CMakeLists.txt:18-21) that is not in its tree -- glm's published operator*, inverse and
@@ -1516,6 +1516,11 @@ void oracle_unpack_material(const rptr_base_material *p, const rptr_texture_desc
         out[9] = m.transmission_color.x; out[10] = m.transmission_color.y; out[11] = m.transmission_color.z;
     }
     out[12] = e.x; out[13] = e.y; out[14] = e.z;
+}
+// compute_sky_illum (vulkan/pt_megakernel.glsl:113-149); sp->sun_radiance[3] = p_sun as the shader sees it
+void oracle_compute_sky_illum(const rptr_scene_params *sp, const float *dir, float prev_pdf, float *out) {
+    V3 r = compute_sky_illum(*sp, v3(dir[0], dir[1], dir[2]), prev_pdf);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
 void oracle_skymodel_radiance(const rptr_scene_params *sp, const float *sun_dir, const float *view, float *out) {
     V3 r = skymodel_radiance(*sp, v3(sun_dir[0], sun_dir[1], sun_dir[2]), v3(view[0], view[1], view[2]));

@@ -177,6 +177,11 @@ void hostsim_unpack_material(const hostsim_scene *s, int32_t mid, int32_t transm
     out[12] = e.x; out[13] = e.y; out[14] = e.z;
 }
 void hostsim_halton_23(int32_t k, float *out) { halton_23(k, out); }
+// the sky / sun-disc term of a missed path (k_resolve's shade_miss) with illum = 0, throughput = 1
+void hostsim_shade_miss(const rptr_scene_params *sp, const float *dir, float prev_pdf, float *out) {
+    const float3 r = shade_miss(*sp, f3(0.0f), f3(1.0f), f3(dir[0], dir[1], dir[2]), prev_pdf);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
 void hostsim_screen_jitter(uint32_t frame_offset, uint32_t frame_id, int32_t w, int32_t h, float *out) { screen_jitter(frame_offset, frame_id, w, h, out); }
 uint32_t hostsim_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, uint32_t tw, uint32_t th, int hash_tile, int hash_sample) {
     return morton_sample_id(sample_id, px, py, tw, th, hash_tile != 0, hash_sample != 0);
