@@ -189,6 +189,44 @@ def gen_vectors(n=512, seed=1234):
         out["sky%d_illum_pdfs" % ci] = pdfs
         out["sky%d_illum" % ci] = ill
     out["sky_dirs"] = sky_dirs
+    # --- two blocks of main_spp executed from the reference (oracle/ref_shim/ref_loop.cpp): bounce prologue + Russian roulette ---
+    rs = np.random.default_rng(4242)  # own stream: the sections below keep their inputs
+    n_pl = 1024
+    pl = np.zeros((n_pl, 20), np.float32)
+    gn = unit(rs.normal(size=(n_pl, 3)))
+    nrm = unit(gn + 0.4 * rs.normal(size=(n_pl, 3)))
+    tan = unit(np.cross(nrm, unit(rs.normal(size=(n_pl, 3))))) * rs.uniform(0.2, 3.0, (n_pl, 1))
+    pl[:, 0:3] = nrm
+    pl[:, 3] = 10.0 ** rs.uniform(-2, 2, n_pl)
+    pl[:, 4:7] = gn * 10.0 ** rs.uniform(-4, 1, (n_pl, 1))  # area-scaled geometric normal
+    pl[:, 7:10] = tan
+    pl[:, 10] = rs.uniform(0.2, 3.0, n_pl)
+    pl[:, 11:14] = rs.normal(size=(n_pl, 3)) * 3
+    rd = unit(-gn + 0.9 * unit(rs.normal(size=(n_pl, 3))))
+    rd[::3] = unit(rs.normal(size=(len(rd[::3]), 3)))  # back-facing and grazing hits, shading normal on the far side
+    pl[:, 14:17] = rd
+    tex8 = rs.integers(0, 256, (n_pl, 3)).astype(np.uint8)
+    tex8[::5] = (127, 127, 255)  # the loader's default normal texel (librender/scene.cpp:870-941)
+    pl[:, 17:20] = tex8.astype(np.float32) / np.float32(255.0)
+    flags = rs.choice([0, T.BASE_MATERIAL_ONESIDED, T.BASE_MATERIAL_VOLUME, T.BASE_MATERIAL_NOALPHA], n_pl).astype(np.uint32)
+    has_map = (rs.random(n_pl) < 0.5).astype(np.int32)
+    zscale = np.where(rs.random(n_pl) < 0.5, 1.0, rs.uniform(0.25, 4.0, n_pl)).astype(np.float32)
+    plo = np.zeros((n_pl, 17), np.float32)
+    for i in range(n_pl):
+        R.ref_bounce_prologue(pl[i].ctypes.data_as(po.f32p), int(flags[i]), 0 if has_map[i] else -1, C.c_float(float(zscale[i])), plo[i].ctypes.data_as(po.f32p))
+    out.update(pl_in=pl, pl_tex8=tex8, pl_flags=flags, pl_has_map=has_map, pl_zscale=zscale, pl_out=plo)
+    n_rr = 2048
+    thr = (10.0 ** rs.uniform(-3, 0.5, (n_rr, 3))).astype(np.float32)
+    thr[::7] = rs.uniform(0.9, 1.1, (len(thr[::7]), 3)).astype(np.float32)
+    rr_bounce = rs.integers(0, 12, n_rr).astype(np.int32)
+    rr_depth = rs.choice([0, 2, 5], n_rr).astype(np.int32)
+    rr_u = rs.random(n_rr).astype(np.float32)
+    rr_out = np.zeros((n_rr, 4), np.float32)
+    for i in range(n_rr):
+        t = thr[i].copy()
+        rr_out[i, 3] = R.ref_russian_roulette(int(rr_bounce[i]), int(rr_depth[i]), t.ctypes.data_as(po.f32p), C.c_float(float(rr_u[i])))
+        rr_out[i, :3] = t
+    out.update(rr_thr=thr, rr_bounce=rr_bounce, rr_depth=rr_depth, rr_u=rr_u, rr_out=rr_out)
     # --- next-event estimation: rendering/mc/nee.glsl:32-90 (sample_direct_light) executed from the reference ---
     n_nee = 768
     nn = unit(rng.normal(size=(n_nee, 3))).astype(np.float32)

@@ -83,6 +83,9 @@ def lib():
         L.oracle_unpack_material.argtypes = [C.POINTER(T.BaseMaterial), C.POINTER(T.TextureDesc), C.c_int, C.c_int, f32p]
         L.oracle_skymodel_radiance.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, f32p]
         L.oracle_compute_sky_illum.argtypes = [C.POINTER(T.SceneParams), f32p, C.c_float, f32p]
+        L.oracle_bounce_prologue.argtypes = [f32p, C.c_uint32, C.c_int32, C.c_void_p, C.c_float, f32p]
+        L.oracle_russian_roulette.restype = C.c_int32
+        L.oracle_russian_roulette.argtypes = [C.c_int32, C.c_int32, f32p, C.c_float]
         L.oracle_sample_sun_dir.argtypes = [f32p, C.c_float, f32p, f32p]
         L.oracle_dequantize_position.argtypes = [C.c_uint64, f32p, f32p, f32p]
         L.oracle_dequantize_normal.argtypes = [C.c_uint32, f32p]
@@ -118,6 +121,9 @@ def ref():
         R.ref_unpack_material.argtypes = [C.POINTER(T.BaseMaterial), f32p, C.c_int, C.c_int, f32p]
         R.ref_skymodel_radiance.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, f32p]
         R.ref_compute_sky_illum.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, C.c_float, f32p]
+        R.ref_bounce_prologue.argtypes = [f32p, C.c_uint32, C.c_int32, C.c_float, f32p]
+        R.ref_russian_roulette.restype = C.c_int32
+        R.ref_russian_roulette.argtypes = [C.c_int32, C.c_int32, f32p, C.c_float]
         R.ref_sample_sun_dir.argtypes = [f32p, C.c_float, f32p, f32p]
         R.ref_pointset_table.argtypes = [C.c_int, C.POINTER(C.c_uint32)]
         R.ref_pointset_replay.argtypes = [C.c_int] + [C.c_uint32] * 7 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, f32p,

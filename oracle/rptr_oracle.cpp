@@ -9,9 +9,10 @@
 // Z-order Sobol / blue-noise samplers and their tables, the Halton screen jitter, dequantisation, hit attributes, the glTF BSDF
 // (with and without transmission), triangle-light solid angles / sampling / binned RIS, host light binning, the sky fit and
 // skymodel_radiance, sun sampling, the material decode with texture handles, sample_direct_light (nee.glsl), the complete
-// per-vertex shading function shade_base_material() with its LCG draw order, and the miss shading compute_sky_illum().
+// per-vertex shading function shade_base_material() with its LCG draw order, the miss shading compute_sky_illum(), and two
+// blocks of main_spp cut out of pt_megakernel.glsl at build time: the bounce prologue and the Russian-roulette step.
 // "PARITY UNPINNED" (restated only, no reference-executed check possible): the loop of pt_megakernel.glsl around that function
-// (ray generation, normal fix-ups, ray epsilons, Russian roulette), process_samples.comp / accumulate.glsl, the
+// (ray generation, ray epsilons, loop control), process_samples.comp / accumulate.glsl, the
 // texture unit (UNORM8 / sRGB decode of a texel), the ray/triangle routine, which the reference does not contain at all, and
 // view_params.VP / VP_reference behind the motion / jitter AOV image: built with glm 0.9.9.8, a configure-time download of
 // the reference (ext/CMakeLists.txt:18-21) that is not in its tree -- glm's published operator*, inverse and
@@ -1011,6 +1012,61 @@ static int shade_base_material(const Frame &f, int &bounce, float &prev_bounce_p
     return SHADING_RESULT_BOUNCE;
 }
 
+// bounce prologue, pt_megakernel.glsl:578-580 and :609-678: approximate solid angle of the hit triangle, shading point,
+// face-forwarding (unless ONESIDED / VOLUME), one-texel normal map, "fix incident direction" blend, tangent frame
+static void bounce_prologue(RTHit &h, const rptr_base_material &mp, const TextureSet &texset, float normal_z_scale, V3 ray_origin, V3 ray_dir,
+                            float &approx_sa, V3 &ip, V3 &ign, V3 &in_, V3 &v_x, V3 &v_y) {
+    approx_sa = length(h.geo_normal); // :578-580
+    h.geo_normal = h.geo_normal / approx_sa;
+    approx_sa *= fabsf(dot(h.geo_normal, ray_dir)) / (h.dist * h.dist);
+
+    V3 w_o = -ray_dir;
+    ip = ray_origin + ray_dir * h.dist; // :613
+    ign = h.geo_normal;
+    in_ = h.normal;
+    if (dot(w_o, ign) < 0.0f) { // :622-633
+        if (mp.flags & RPTR_BASE_MATERIAL_VOLUME) {
+            ip = ray_origin;
+            h.dist = 0.0f;
+        } else if (!(mp.flags & RPTR_BASE_MATERIAL_ONESIDED)) {
+            in_ = -in_;
+            ign = -ign;
+        }
+    }
+    if (mp.normal_map != -1) { // :634-654, the normal map read through the texture set (1 x 1: uv and LOD are irrelevant)
+        V3 t_y = normalize(cross(h.normal, h.tangent));
+        V3 t_x = cross(t_y, h.normal);
+        t_x = t_x * length(h.tangent);
+        t_y = t_y * h.bitangent_l;
+        TextureSet::RGBA tx = texset.texel((uint32_t)mp.normal_map);
+        V3 map_nrm = v3(2.0f * tx.r - 1.0f, 2.0f * tx.g - 1.0f, 1.0f * tx.b - 0.0f);
+        map_nrm.z = sqrtf(fmaxf(1.0f - map_nrm.x * map_nrm.x - map_nrm.y * map_nrm.y, 0.0f));
+        in_ = normalize(mat_mul(t_x, t_y, in_ * normal_z_scale, map_nrm));
+    }
+    { // :657-668
+        float nw = dot(w_o, in_), gnw = dot(w_o, ign);
+        if (nw * gnw <= 0.0f) {
+            float blend = gnw / (gnw - nw);
+            in_ = normalize(mix(ign, in_, blend - 0.0001f));
+        }
+    }
+    v_y = normalize(cross(in_, h.tangent)); // :677-678
+    v_x = cross(v_y, in_);
+}
+
+// Russian roulette, pt_megakernel.glsl:715-729 (the caller draws rr_sample once bounce >= rr_path_depth); false = terminate
+static bool russian_roulette(int bounce, V3 &throughput, float rr_sample) {
+    float prefix = fmaxf(throughput.x, fmaxf(throughput.y, throughput.z));
+    float rr_prob = prefix;
+    if (bounce > 6) rr_prob = fminf(0.95f, rr_prob);
+    else rr_prob = fminf(1.0f, rr_prob);
+    if (rr_sample < rr_prob) {
+        throughput = throughput / rr_prob;
+        return true;
+    }
+    return false;
+}
+
 static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32_t view_frame_id, Counters &cnt, AovOut *aov = nullptr) {
     const oracle_render_args &a = *f.a;
     const Scene &s = *f.s;
@@ -1086,44 +1142,13 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         const GeomInst &g = s.ginst[tr.geom_inst];
         RTHit h = calc_hit_attributes(g, hit.t, (uint32_t)tr.prim, hit.u, hit.v);
 
-        float approx_sa = length(h.geo_normal); // :578-580
-        h.geo_normal = h.geo_normal / approx_sa;
-        approx_sa *= fabsf(dot(h.geo_normal, ray_dir)) / (h.dist * h.dist);
-        total_t += h.dist; // :585
+        total_t += h.dist; // :585 (before a VOLUME hit zeroes hit.dist)
         float geometry_scale = total_t;
-
-        V3 w_o = -ray_dir;
-        V3 ip = ray_origin + ray_dir * h.dist; // :613
-        V3 ign = h.geo_normal, in_ = h.normal;
         const rptr_base_material &mp = s.materials[h.material_id];
-        if (dot(w_o, ign) < 0.0f) { // :622-633
-            if (mp.flags & RPTR_BASE_MATERIAL_VOLUME) {
-                ip = ray_origin;
-                h.dist = 0.0f;
-            } else if (!(mp.flags & RPTR_BASE_MATERIAL_ONESIDED)) {
-                in_ = -in_;
-                ign = -ign;
-            }
-        }
-        if (mp.normal_map != -1) { // :634-654, the normal map read through the texture set (1 x 1: uv and LOD are irrelevant)
-            V3 t_y = normalize(cross(h.normal, h.tangent));
-            V3 t_x = cross(t_y, h.normal);
-            t_x = t_x * length(h.tangent);
-            t_y = t_y * h.bitangent_l;
-            TextureSet::RGBA tx = s.texset.texel((uint32_t)mp.normal_map);
-            V3 map_nrm = v3(2.0f * tx.r - 1.0f, 2.0f * tx.g - 1.0f, 1.0f * tx.b - 0.0f);
-            map_nrm.z = sqrtf(fmaxf(1.0f - map_nrm.x * map_nrm.x - map_nrm.y * map_nrm.y, 0.0f));
-            in_ = normalize(mat_mul(t_x, t_y, in_ * sp.normal_z_scale, map_nrm));
-        }
-        { // :657-668
-            float nw = dot(w_o, in_), gnw = dot(w_o, ign);
-            if (nw * gnw <= 0.0f) {
-                float blend = gnw / (gnw - nw);
-                in_ = normalize(mix(ign, in_, blend - 0.0001f));
-            }
-        }
-        V3 v_y = normalize(cross(in_, h.tangent)); // :677-678
-        V3 v_x = cross(v_y, in_);
+        float approx_sa;
+        V3 ip, ign, in_, v_x, v_y;
+        bounce_prologue(h, mp, s.texset, sp.normal_z_scale, ray_origin, ray_dir, approx_sa, ip, ign, in_, v_x, v_y);
+        V3 w_o = -ray_dir;
 
         // ---- shade_base_material ----
         V3 w_i;
@@ -1141,13 +1166,8 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         t_max = 1e20f;
         // Russian roulette: :715-729
         if (bounce >= a.params.rr_path_depth) {
-            float prefix = fmaxf(throughput.x, fmaxf(throughput.y, throughput.z));
-            float rr_prob = prefix;
             float rr_sample = rng.draw(-1); // DIM_RR = DIM_FREE_PATH - DIM_VERTEX_END
-            if (bounce > 6) rr_prob = fminf(0.95f, rr_prob);
-            else rr_prob = fminf(1.0f, rr_prob);
-            if (rr_sample < rr_prob) throughput = throughput / rr_prob;
-            else break;
+            if (!russian_roulette(bounce, throughput, rr_sample)) break;
         }
     }
     return V4{illum.x, illum.y, illum.z, bounce == 0 ? 0.0f : 1.0f};
@@ -1516,6 +1536,38 @@ void oracle_unpack_material(const rptr_base_material *p, const rptr_texture_desc
         out[9] = m.transmission_color.x; out[10] = m.transmission_color.y; out[11] = m.transmission_color.z;
     }
     out[12] = e.x; out[13] = e.y; out[14] = e.z;
+}
+// bounce prologue of main_spp; same in / out layout as ref_bounce_prologue (oracle/ref_shim/ref_loop.cpp), the normal-map
+// texel given as the three 8-bit values of a linear 1 x 1 texture
+void oracle_bounce_prologue(const float *in, uint32_t material_flags, int32_t has_normal_map, const uint8_t *texel8, float normal_z_scale, float *out) {
+    RTHit h;
+    std::memset(&h, 0, sizeof(h));
+    h.normal = v3(in[0], in[1], in[2]);
+    h.dist = in[3];
+    h.geo_normal = v3(in[4], in[5], in[6]);
+    h.tangent = v3(in[7], in[8], in[9]);
+    h.bitangent_l = in[10];
+    rptr_base_material mp;
+    std::memset(&mp, 0, sizeof(mp));
+    mp.flags = material_flags;
+    mp.normal_map = has_normal_map ? 0 : -1;
+    rptr_texture_desc td{1, 1, 3, RPTR_COLOR_SPACE_LINEAR, texel8};
+    TextureSet ts;
+    ts.tex = &td;
+    ts.n = 1;
+    float approx_sa;
+    V3 ip, ign, in_, v_x, v_y;
+    bounce_prologue(h, mp, ts, normal_z_scale, v3(in[11], in[12], in[13]), v3(in[14], in[15], in[16]), approx_sa, ip, ign, in_, v_x, v_y);
+    const float o[17] = {approx_sa, ip.x, ip.y, ip.z, ign.x, ign.y, ign.z, in_.x, in_.y, in_.z, v_x.x, v_x.y, v_x.z, v_y.x, v_y.y, v_y.z, h.dist};
+    std::memcpy(out, o, sizeof(o));
+}
+// Russian roulette of main_spp: 1 = survives (throughput divided by the survival probability), 0 = terminated
+int32_t oracle_russian_roulette(int32_t bounce, int32_t rr_path_depth, float *throughput, float rr_sample) {
+    if (!(bounce >= rr_path_depth)) return 1;
+    V3 t = v3(throughput[0], throughput[1], throughput[2]);
+    const bool alive = russian_roulette(bounce, t, rr_sample);
+    throughput[0] = t.x; throughput[1] = t.y; throughput[2] = t.z;
+    return alive ? 1 : 0;
 }
 // compute_sky_illum (vulkan/pt_megakernel.glsl:113-149); sp->sun_radiance[3] = p_sun as the shader sees it
 void oracle_compute_sky_illum(const rptr_scene_params *sp, const float *dir, float prev_pdf, float *out) {
