@@ -227,6 +227,45 @@ def gen_vectors(n=512, seed=1234):
         rr_out[i, 3] = R.ref_russian_roulette(int(rr_bounce[i]), int(rr_depth[i]), t.ctypes.data_as(po.f32p), C.c_float(float(rr_u[i])))
         rr_out[i, :3] = t
     out.update(rr_thr=thr, rr_bounce=rr_bounce, rr_depth=rr_depth, rr_u=rr_u, rr_out=rr_out)
+    # ray-generation head of main_spp, geometry_scale_to_tmin, the resolve's running mean (same shim, own stream)
+    from realtimepathtracingresearchframework_b200 import scenes
+    cam = scenes.random_triangles(16).camera
+    n_rg = 1024
+    Wd, Hd = 1920, 1080
+    vp = po.view_params(cam, Wd, Hd)  # du, dv, top_left (itself pinned by construction: SURVEY 8a-1)
+    camv = np.concatenate([np.array(list(cam.pos), np.float32), vp]).astype(np.float32)
+    rg = np.zeros((n_rg, 5), np.uint32)  # px, py, sample_index, frame_offset, enable_raster_taa
+    rg[:, 0] = rs.integers(0, Wd, n_rg)
+    rg[:, 1] = rs.integers(0, Hd, n_rg)
+    rg[:8, 0] = [0, Wd - 1, 0, Wd - 1, 1, 2, 3, 4]
+    rg[:8, 1] = [0, 0, Hd - 1, Hd - 1, 1, 2, 3, 4]
+    rg[:, 2] = rs.integers(0, 5000, n_rg)
+    rg[:, 3] = rs.integers(0, 100, n_rg)
+    rg[:, 4] = rs.random(n_rg) < 0.3
+    rg_j = np.zeros((n_rg, 2), np.float32)
+    rg_o = np.zeros((n_rg, 9), np.float32)
+    for i in range(n_rg):
+        if rg[i, 4]:
+            po.lib().oracle_screen_jitter(int(rg[i, 3]), int(rg[i, 2]), Wd, Hd, rg_j[i].ctypes.data_as(po.f32p))  # table pinned in ref_pointsets.npz
+        R.ref_camera_ray(camv.ctypes.data_as(po.f32p), Wd, Hd, int(rg[i, 0]), int(rg[i, 1]), int(rg[i, 2]), int(rg[i, 3]), int(rg[i, 4]),
+                         rg_j[i].ctypes.data_as(po.f32p), rg_o[i].ctypes.data_as(po.f32p))
+    out.update(rg_cam=camv, rg_in=rg, rg_jitter=rg_j, rg_out=rg_o)
+    n_tm = 512
+    tm_in = np.zeros((n_tm, 4), np.float32)
+    tm_in[:, :3] = rs.normal(size=(n_tm, 3)) * 10.0 ** rs.uniform(-2, 3, (n_tm, 1))
+    tm_in[:, 3] = 10.0 ** rs.uniform(-3, 3, n_tm)
+    tm_in[::9, 3] = 0.0
+    out["tmin_in"] = tm_in
+    out["tmin_out"] = np.array([R.ref_geometry_scale_to_tmin(tm_in[i, :3].copy().ctypes.data_as(po.f32p), C.c_float(float(tm_in[i, 3]))) for i in range(n_tm)],
+                               np.float32)
+    n_rm = 1024
+    rm_x = (10.0 ** rs.uniform(-3, 3, (n_rm, 4))).astype(np.float32)
+    rm_h = (10.0 ** rs.uniform(-3, 3, (n_rm, 4))).astype(np.float32)
+    rm_n = np.stack([rs.integers(1, 5000, n_rm), rs.choice([1, 1, 1, 4, 64], n_rm)], 1).astype(np.uint32)
+    rm_o = rm_h.copy()
+    for i in range(n_rm):
+        R.ref_running_mean(rm_x[i].ctypes.data_as(po.f32p), rm_o[i].ctypes.data_as(po.f32p), int(rm_n[i, 0]), int(rm_n[i, 1]))
+    out.update(rm_x=rm_x, rm_hist=rm_h, rm_n=rm_n, rm_out=rm_o)
     # --- next-event estimation: rendering/mc/nee.glsl:32-90 (sample_direct_light) executed from the reference ---
     n_nee = 768
     nn = unit(rng.normal(size=(n_nee, 3))).astype(np.float32)

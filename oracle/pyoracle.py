@@ -83,6 +83,10 @@ def lib():
         L.oracle_unpack_material.argtypes = [C.POINTER(T.BaseMaterial), C.POINTER(T.TextureDesc), C.c_int, C.c_int, f32p]
         L.oracle_skymodel_radiance.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, f32p]
         L.oracle_compute_sky_illum.argtypes = [C.POINTER(T.SceneParams), f32p, C.c_float, f32p]
+        L.oracle_camera_ray.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_int32, C.c_int32, C.c_uint32, f32p]
+        L.oracle_geometry_scale_to_tmin.restype = C.c_float
+        L.oracle_geometry_scale_to_tmin.argtypes = [f32p, C.c_float]
+        L.oracle_running_mean.argtypes = [f32p, f32p, C.c_uint32, C.c_uint32]
         L.oracle_bounce_prologue.argtypes = [f32p, C.c_uint32, C.c_int32, C.c_void_p, C.c_float, f32p]
         L.oracle_russian_roulette.restype = C.c_int32
         L.oracle_russian_roulette.argtypes = [C.c_int32, C.c_int32, f32p, C.c_float]
@@ -121,6 +125,10 @@ def ref():
         R.ref_unpack_material.argtypes = [C.POINTER(T.BaseMaterial), f32p, C.c_int, C.c_int, f32p]
         R.ref_skymodel_radiance.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, f32p]
         R.ref_compute_sky_illum.argtypes = [C.POINTER(T.SceneParams), f32p, f32p, C.c_float, f32p]
+        R.ref_camera_ray.argtypes = [f32p] + [C.c_uint32] * 6 + [C.c_int32, f32p, f32p]
+        R.ref_geometry_scale_to_tmin.restype = C.c_float
+        R.ref_geometry_scale_to_tmin.argtypes = [f32p, C.c_float]
+        R.ref_running_mean.argtypes = [f32p, f32p, C.c_uint32, C.c_uint32]
         R.ref_bounce_prologue.argtypes = [f32p, C.c_uint32, C.c_int32, C.c_float, f32p]
         R.ref_russian_roulette.restype = C.c_int32
         R.ref_russian_roulette.argtypes = [C.c_int32, C.c_int32, f32p, C.c_float]

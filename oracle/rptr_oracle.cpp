@@ -9,10 +9,11 @@
 // Z-order Sobol / blue-noise samplers and their tables, the Halton screen jitter, dequantisation, hit attributes, the glTF BSDF
 // (with and without transmission), triangle-light solid angles / sampling / binned RIS, host light binning, the sky fit and
 // skymodel_radiance, sun sampling, the material decode with texture handles, sample_direct_light (nee.glsl), the complete
-// per-vertex shading function shade_base_material() with its LCG draw order, the miss shading compute_sky_illum(), and two
-// blocks of main_spp cut out of pt_megakernel.glsl at build time: the bounce prologue and the Russian-roulette step.
-// "PARITY UNPINNED" (restated only, no reference-executed check possible): the loop of pt_megakernel.glsl around that function
-// (ray generation, ray epsilons, loop control), process_samples.comp / accumulate.glsl, the
+// per-vertex shading function shade_base_material() with its LCG draw order, the miss shading compute_sky_illum(), and blocks
+// cut out of the shader files at build time (oracle/ref_shim/ref_loop.cpp): the ray-generation head, the bounce prologue and
+// the Russian-roulette step of main_spp, geometry_scale_to_tmin, the running mean of process_samples.comp.
+// "PARITY UNPINNED" (restated only, no reference-executed check possible): the glue of pt_megakernel.glsl between those pieces
+// (loop control, the rayQueryEXT candidate loop with its alpha filter, the shadow-ray range test), accumulate.glsl, the
 // texture unit (UNORM8 / sRGB decode of a texel), the ray/triangle routine, which the reference does not contain at all, and
 // view_params.VP / VP_reference behind the motion / jitter AOV image: built with glm 0.9.9.8, a configure-time download of
 // the reference (ext/CMakeLists.txt:18-21) that is not in its tree -- glm's published operator*, inverse and
@@ -1067,16 +1068,10 @@ static bool russian_roulette(int bounce, V3 &throughput, float rr_sample) {
     return false;
 }
 
-static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32_t view_frame_id, Counters &cnt, AovOut *aov = nullptr) {
+// ray generation, head of main_spp (pt_megakernel.glsl:311-325): box pixel filter (two draws) unless raster TAA supplies
+// the frame's screen jitter
+static void camera_ray(const Frame &f, int px, int py, PathRng &rng, uint32_t view_frame_id, V3 &ray_origin, V3 &ray_dir) {
     const oracle_render_args &a = *f.a;
-    const Scene &s = *f.s;
-    const rptr_scene_params &sp = f.sp;
-    uint32_t linear = (uint32_t)px + (uint32_t)py * (uint32_t)a.width;
-    PathRng rng;
-    rng.lcg = lcg_seed(sample_index, a.frame_offset, linear);
-    rng.alpha = rng.lcg;
-    rng.qmc = a.rng_variant != 0;
-    if (rng.qmc) rng.q.seed(a.rng_variant, a.pointset_tables, sample_index, view_frame_id, a.frame_offset, (uint32_t)px, (uint32_t)py, (uint32_t)a.width);
     float ptx = (float)px + 0.5f, pty = (float)py + 0.5f;
     if (a.params.enable_raster_taa == 0) {
         float ux = rng.draw(0); // DIM_PIXEL_X, pathspace.h:13-14
@@ -1092,8 +1087,32 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         ptx += 0.5f * sj[0];
         pty += 0.5f * sj[1];
     }
-    V3 ray_origin = f.cam_pos;
-    V3 ray_dir = normalize(f.du * ptx + f.dv * pty + f.tl);
+    ray_origin = f.cam_pos;
+    ray_dir = normalize(f.du * ptx + f.dv * pty + f.tl);
+}
+
+// the running mean of the resolve pass (process_samples.comp:121-127): history += (x - history) / float(base + batch)
+static void fold_sample(float *history, const float *x, uint32_t sample_base_index, uint32_t sample_batch_size) {
+    float denom = (float)(sample_base_index + sample_batch_size);
+    for (int j = 0; j < 4; ++j) {
+        float m = history[j];
+        m += (x[j] - m) / denom;
+        history[j] = m;
+    }
+}
+
+static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32_t view_frame_id, Counters &cnt, AovOut *aov = nullptr) {
+    const oracle_render_args &a = *f.a;
+    const Scene &s = *f.s;
+    const rptr_scene_params &sp = f.sp;
+    uint32_t linear = (uint32_t)px + (uint32_t)py * (uint32_t)a.width;
+    PathRng rng;
+    rng.lcg = lcg_seed(sample_index, a.frame_offset, linear);
+    rng.alpha = rng.lcg;
+    rng.qmc = a.rng_variant != 0;
+    if (rng.qmc) rng.q.seed(a.rng_variant, a.pointset_tables, sample_index, view_frame_id, a.frame_offset, (uint32_t)px, (uint32_t)py, (uint32_t)a.width);
+    V3 ray_origin, ray_dir;
+    camera_ray(f, px, py, rng, view_frame_id, ray_origin, ray_dir);
     float t_min = 0.0f, t_max = 2.e32f;
     float total_t = 0.0f;
     V3 illum = v3(0.0f), throughput = v3(1.0f);
@@ -1222,14 +1241,9 @@ int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rg
                 const uint32_t batch = a->batch_spp > 1 ? (uint32_t)a->batch_spp : 1u;
                 V4 c = main_spp(f, x, y, frame_id, a->first_sample + ((uint32_t)k / batch) * batch, cnt);
                 float xs[4] = {c.x, c.y, c.z, c.w};
-                if (frame_id > 0 && a->params.reprojection_mode != RPTR_REPROJECTION_MODE_DISCARD_HISTORY) { // process_samples.comp:116-127
-                    float denom = (float)(frame_id + 1u);
-                    for (int j = 0; j < 4; ++j) {
-                        float m = px[j];
-                        m += (xs[j] - m) / denom;
-                        px[j] = m;
-                    }
-                } else
+                if (frame_id > 0 && a->params.reprojection_mode != RPTR_REPROJECTION_MODE_DISCARD_HISTORY) // process_samples.comp:116-127
+                    fold_sample(px, xs, frame_id, 1u);
+                else
                     for (int j = 0; j < 4; ++j) px[j] = xs[j];
             }
         }
@@ -1537,6 +1551,23 @@ void oracle_unpack_material(const rptr_base_material *p, const rptr_texture_desc
     }
     out[12] = e.x; out[13] = e.y; out[14] = e.z;
 }
+// head of main_spp for one pixel sample with the LCG pointset: out = origin(3), dir(3), bits(LCG state afterwards)
+void oracle_camera_ray(const oracle_scene *os, const oracle_render_args *a, int32_t px, int32_t py, uint32_t sample_index, float *out) {
+    Frame f = make_frame(os, a);
+    PathRng rng;
+    rng.lcg = lcg_seed(sample_index, a->frame_offset, (uint32_t)px + (uint32_t)py * (uint32_t)a->width);
+    rng.alpha = rng.lcg;
+    rng.qmc = false;
+    V3 o, d;
+    camera_ray(f, px, py, rng, a->first_sample, o, d);
+    out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = d.x; out[4] = d.y; out[5] = d.z;
+    std::memcpy(out + 6, &rng.lcg, 4);
+}
+void oracle_running_mean(const float *x, float *history, uint32_t sample_base_index, uint32_t sample_batch_size) {
+    fold_sample(history, x, sample_base_index, sample_batch_size);
+}
+// geometry_scale_to_tmin (vulkan/geometry.glsl:76-78)
+float oracle_geometry_scale_to_tmin(const float *orig, float geometry_scale) { return geometry_scale_to_tmin(v3(orig[0], orig[1], orig[2]), geometry_scale); }
 // bounce prologue of main_spp; same in / out layout as ref_bounce_prologue (oracle/ref_shim/ref_loop.cpp), the normal-map
 // texel given as the three 8-bit values of a linear 1 x 1 texture
 void oracle_bounce_prologue(const float *in, uint32_t material_flags, int32_t has_normal_map, const uint8_t *texel8, float normal_z_scale, float *out) {

@@ -177,6 +177,15 @@ void hostsim_unpack_material(const hostsim_scene *s, int32_t mid, int32_t transm
     out[12] = e.x; out[13] = e.y; out[14] = e.z;
 }
 void hostsim_halton_23(int32_t k, float *out) { halton_23(k, out); }
+// generate_primary for one pixel sample: out = origin(3), dir(3), bits(first sampler word afterwards), tmin, tmax
+void hostsim_primary_ray(const hostsim_scene *s, const hostsim_args *a, int32_t px, int32_t py, uint32_t sample_index, float *out) {
+    FrameParams fp = make_frame(s, a);
+    PathState ps;
+    generate_primary(fp, px, py, sample_index, ps);
+    out[0] = ps.o.x; out[1] = ps.o.y; out[2] = ps.o.z; out[3] = ps.d.x; out[4] = ps.d.y; out[5] = ps.d.z;
+    memcpy(out + 6, &ps.rng, 4);
+    out[7] = ps.tmin; out[8] = ps.tmax;
+}
 // the sky / sun-disc term of a missed path (k_resolve's shade_miss) with illum = 0, throughput = 1
 void hostsim_shade_miss(const rptr_scene_params *sp, const float *dir, float prev_pdf, float *out) {
     const float3 r = shade_miss(*sp, f3(0.0f), f3(1.0f), f3(dir[0], dir[1], dir[2]), prev_pdf);
