@@ -266,6 +266,42 @@ def gen_vectors(n=512, seed=1234):
     for i in range(n_rm):
         R.ref_running_mean(rm_x[i].ctypes.data_as(po.f32p), rm_o[i].ctypes.data_as(po.f32p), int(rm_n[i, 0]), int(rm_n[i, 1]))
     out.update(rm_x=rm_x, rm_hist=rm_h, rm_n=rm_n, rm_out=rm_o)
+    # raytrace_test_visibility over scripted ray queries + the alpha test of generate_candidate_hit
+    n_vis = 768
+    vis_in = np.zeros((n_vis, 14), np.float32)  # from3, dir3, dist, geometry_scale, frame_id, frame_offset, px, py, n_cands, opaque_hit
+    vis_c = np.zeros((n_vis, 6, 4), np.float32)  # (t, prim, inst, accept) per candidate
+    vis_o = np.zeros((n_vis, 5 + 6), np.float32)
+    vis_in[:, 0:3] = rs.normal(size=(n_vis, 3)) * 10.0 ** rs.uniform(-1, 2, (n_vis, 1))
+    vis_in[:, 3:6] = unit(rs.normal(size=(n_vis, 3)))
+    vis_in[:, 6] = 10.0 ** rs.uniform(-5, 3, n_vis)       # light distance, down to below the ray epsilon
+    vis_in[:, 7] = 10.0 ** rs.uniform(-2, 3, n_vis)       # geometry_scale (total_t)
+    vis_in[:, 8] = rs.integers(0, 5000, n_vis)
+    vis_in[:, 9] = rs.integers(0, 100, n_vis)
+    vis_in[:, 10] = rs.integers(0, Wd, n_vis)
+    vis_in[:, 11] = rs.integers(0, Hd, n_vis)
+    vis_in[:, 12] = rs.integers(0, 7, n_vis)
+    vis_in[:, 13] = rs.random(n_vis) < 0.15
+    for i in range(n_vis):
+        k = int(vis_in[i, 12])
+        vis_c[i, :k, 0] = np.sort(rs.uniform(0, 1, k)) * vis_in[i, 6]
+        vis_c[i, :k, 1] = rs.choice(100000, k, replace=False)
+        vis_c[i, :k, 2] = rs.integers(0, 100, k)
+        vis_c[i, :k, 3] = rs.random(k) < 0.25
+        R.ref_test_visibility(vis_in[i, 0:3].copy().ctypes.data_as(po.f32p), vis_in[i, 3:6].copy().ctypes.data_as(po.f32p), C.c_float(float(vis_in[i, 6])),
+                              C.c_float(float(vis_in[i, 7])), int(vis_in[i, 8]), int(vis_in[i, 9]), int(vis_in[i, 10]), int(vis_in[i, 11]), Wd, Hd,
+                              np.ascontiguousarray(vis_c[i]).ctypes.data_as(po.f32p), k, int(vis_in[i, 13]), vis_o[i].ctypes.data_as(po.f32p))
+    out.update(vis_in=vis_in, vis_cands=vis_c, vis_out=vis_o)
+    n_af = 1024
+    af_alpha = rs.choice([0.0, 1.0, 0.5, 0.25, 128.0 / 255.0, -0.0], n_af).astype(np.float32)
+    af_alpha[::3] = rs.random(len(af_alpha[::3])).astype(np.float32)
+    af_flags = rs.choice([0, T.BASE_MATERIAL_NOALPHA, T.BASE_MATERIAL_ONESIDED], n_af).astype(np.uint32)
+    af_state = rs.integers(0, 2 ** 32, n_af, dtype=np.uint64).astype(np.uint32)
+    af_out = np.zeros((n_af, 2), np.uint32)
+    for i in range(n_af):
+        st = C.c_uint32(int(af_state[i]))
+        af_out[i, 0] = R.ref_alpha_filter(C.c_float(float(af_alpha[i])), int(af_flags[i]), C.byref(st))
+        af_out[i, 1] = st.value
+    out.update(af_alpha=af_alpha, af_flags=af_flags, af_state=af_state, af_out=af_out)
     # --- next-event estimation: rendering/mc/nee.glsl:32-90 (sample_direct_light) executed from the reference ---
     n_nee = 768
     nn = unit(rng.normal(size=(n_nee, 3))).astype(np.float32)

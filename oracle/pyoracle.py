@@ -87,6 +87,12 @@ def lib():
         L.oracle_geometry_scale_to_tmin.restype = C.c_float
         L.oracle_geometry_scale_to_tmin.argtypes = [f32p, C.c_float]
         L.oracle_running_mean.argtypes = [f32p, f32p, C.c_uint32, C.c_uint32]
+        L.oracle_shadow_ray_range.restype = C.c_int32
+        L.oracle_shadow_ray_range.argtypes = [f32p, C.c_float, C.c_float, f32p]
+        L.oracle_shadow_alpha_seed.restype = C.c_uint32
+        L.oracle_shadow_alpha_seed.argtypes = [C.c_uint32] * 5
+        L.oracle_alpha_filter.restype = C.c_int32
+        L.oracle_alpha_filter.argtypes = [C.c_float, C.c_uint32, C.POINTER(C.c_uint32)]
         L.oracle_bounce_prologue.argtypes = [f32p, C.c_uint32, C.c_int32, C.c_void_p, C.c_float, f32p]
         L.oracle_russian_roulette.restype = C.c_int32
         L.oracle_russian_roulette.argtypes = [C.c_int32, C.c_int32, f32p, C.c_float]
@@ -129,6 +135,9 @@ def ref():
         R.ref_geometry_scale_to_tmin.restype = C.c_float
         R.ref_geometry_scale_to_tmin.argtypes = [f32p, C.c_float]
         R.ref_running_mean.argtypes = [f32p, f32p, C.c_uint32, C.c_uint32]
+        R.ref_test_visibility.argtypes = [f32p, f32p, C.c_float, C.c_float] + [C.c_uint32] * 6 + [f32p, C.c_int32, C.c_int32, f32p]
+        R.ref_alpha_filter.restype = C.c_int32
+        R.ref_alpha_filter.argtypes = [C.c_float, C.c_uint32, C.POINTER(C.c_uint32)]
         R.ref_bounce_prologue.argtypes = [f32p, C.c_uint32, C.c_int32, C.c_float, f32p]
         R.ref_russian_roulette.restype = C.c_int32
         R.ref_russian_roulette.argtypes = [C.c_int32, C.c_int32, f32p, C.c_float]

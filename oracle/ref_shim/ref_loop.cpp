@@ -36,7 +36,7 @@ struct { int rr_path_depth; int enable_raster_taa; } render_params;
 struct SwzU3 { uvec2 xy; };
 struct SwzU2 { uvec2 xy; operator vec2() const { return vec2(xy); } }; // uvec2 -> vec2 is implicit in GLSL
 struct SwzF3 { vec3 xyz; };
-struct { SwzU2 frame_dims; vec2 screen_jitter; SwzF3 cam_pos, cam_du, cam_dv, cam_dir_top_left; } view_params;
+struct { SwzU2 frame_dims; vec2 screen_jitter; SwzF3 cam_pos, cam_du, cam_dv, cam_dir_top_left; uint frame_id, frame_offset; } view_params;
 static SwzU3 gl_GlobalInvocationID;
 #define SAMPLE_PIXEL_FILTER(urand) (urand - vec2(0.5f)) // vulkan/gpu_params.glsl:42 (no PIXEL_FILTER_TENT_WINDOW in the build)
 #define RAY_EPSILON 0.000005f                           // vulkan/gpu_params.glsl:27-29
@@ -85,6 +85,57 @@ static vec4 running_mean(vec4 accum_color, vec4 history, uint sample_base_index,
     ivec2 fb_dims(1, 1);
 #include "gen/running_mean.inc"
     return accum_color;
+}
+
+// ---- raytrace_test_visibility (vulkan/pt_megakernel.glsl:216-272) over a scripted ray query ------------------------------
+// The GL_EXT_ray_query calls are answered from a list of non-opaque candidates (+ "an opaque triangle was hit", which the
+// traversal commits by itself); generate_candidate_hit() is replaced by a recorder that notes the alpha LCG it was handed
+// and answers from the script.  What runs from the reference: the epsilon / range / skip rule, the per-candidate seed,
+// the loop's termination and the final verdict.
+struct Candidate { float t; int prim, inst, geom, accept; };
+static const Candidate *g_cands = nullptr;
+static int g_ncands = 0, g_opaque_hit = 0;
+struct rayQueryEXT { int cursor; bool terminated; };
+static struct { vec3 from, dir; float tmin, tmax; int inits; } g_rq;
+static uint g_seeds[64];
+static int g_nseeds;
+static int scene;
+static float geometry_scale;
+enum { gl_RayFlagsTerminateOnFirstHitEXT = 4, gl_RayFlagsSkipClosestHitShaderEXT = 8, gl_RayQueryCandidateIntersectionTriangleEXT = 0 };
+inline void rayQueryInitializeEXT(rayQueryEXT &q, int, uint, uint, vec3 o, float tmin, vec3 d, float tmax) {
+    g_rq.from = o; g_rq.dir = d; g_rq.tmin = tmin; g_rq.tmax = tmax; ++g_rq.inits;
+    q.cursor = -1; q.terminated = false;
+}
+inline bool rayQueryProceedEXT(rayQueryEXT &q) { return !q.terminated && ++q.cursor < g_ncands; }
+inline void rayQueryTerminateEXT(rayQueryEXT &q) { q.terminated = true; }
+// committed == false: type of the current candidate (always a triangle); committed == true: 1 when an opaque triangle was hit
+inline uint rayQueryGetIntersectionTypeEXT(rayQueryEXT &, bool committed) { return committed ? (g_opaque_hit ? 1u : 0u) : 0u; }
+inline float rayQueryGetIntersectionTEXT(rayQueryEXT &q, bool) { return g_cands[q.cursor].t; }
+inline vec2 rayQueryGetIntersectionBarycentricsEXT(rayQueryEXT &, bool) { return vec2(0.25f); }
+inline int rayQueryGetIntersectionInstanceIdEXT(rayQueryEXT &q, bool) { return g_cands[q.cursor].inst; }
+inline int rayQueryGetIntersectionInstanceCustomIndexEXT(rayQueryEXT &q, bool) { return g_cands[q.cursor].geom; }
+inline int rayQueryGetIntersectionGeometryIndexEXT(rayQueryEXT &, bool) { return 0; }
+inline int rayQueryGetIntersectionPrimitiveIndexEXT(rayQueryEXT &q, bool) { return g_cands[q.cursor].prim; }
+inline vec3 rayQueryGetIntersectionObjectRayOriginEXT(rayQueryEXT &, bool) { return g_rq.from; }
+inline vec3 rayQueryGetIntersectionObjectRayDirectionEXT(rayQueryEXT &, bool) { return g_rq.dir; }
+static int g_candidate_cursor;
+inline bool generate_candidate_hit(float, vec2, int, int, int primitiveIdx, vec3, vec3, RTHit &, LCGRand &alpha_rng, bool) {
+    if (g_nseeds < 64) g_seeds[g_nseeds++] = alpha_rng.state;
+    for (int i = 0; i < g_ncands; ++i)
+        if (g_cands[i].prim == primitiveIdx) return !g_cands[i].accept; // true = candidate rejected (transparent)
+    return false;
+}
+#define IMPLICIT_INSTANCE_PARAMS // vulkan/gpu_params.glsl:16
+#include "gen/test_visibility.inc"
+
+// the alpha test at the end of generate_candidate_hit (:202-210)
+static float g_alpha;
+inline float get_material_alpha(int, const BaseMaterial &, const HitPoint &) { return g_alpha; }
+#define MATERIAL_PARAMS BaseMaterial
+static bool alpha_tail(RTHit hit, LCGRand &alpha_rng) {
+    vec3 local_ray_orig(0.0f), local_ray_dir(0.0f, 0.0f, 1.0f);
+    float dist = 1.0f;
+#include "gen/alpha_tail.inc"
 }
 
 static bool russian_roulette(vec3 &path_throughput) {
@@ -157,6 +208,40 @@ void ref_running_mean(const float *x, float *history, uint32_t sample_base_index
     glm::vec4 r = refloop::running_mean(glm::vec4(x[0], x[1], x[2], x[3]), glm::vec4(history[0], history[1], history[2], history[3]), sample_base_index,
                                         sample_batch_size);
     history[0] = r.x; history[1] = r.y; history[2] = r.z; history[3] = r.w;
+}
+
+// raytrace_test_visibility(from, dir, dist) with geometry_scale and the frame counters / pixel of the invocation, over the scripted
+// candidates cands[n] = (t, prim, inst, accept) and opaque_hit.  out: [0] visible, [1] number of ray queries started,
+// [2] tmin, [3] tmax, [4] number of candidates judged, [5..] bits of the alpha LCG state handed to each
+void ref_test_visibility(const float *from, const float *dir, float dist, float geom_scale, uint32_t frame_id, uint32_t frame_offset, uint32_t px,
+                         uint32_t py, uint32_t width, uint32_t height, const float *cands, int32_t n, int32_t opaque_hit, float *out) {
+    using namespace refloop;
+    static Candidate list[64];
+    for (int i = 0; i < n && i < 64; ++i) list[i] = Candidate{cands[4 * i], (int)cands[4 * i + 1], (int)cands[4 * i + 2], 0, (int)cands[4 * i + 3]};
+    g_cands = list; g_ncands = n < 64 ? n : 64; g_opaque_hit = opaque_hit;
+    g_rq.inits = 0; g_rq.tmin = 0.0f; g_rq.tmax = 0.0f; g_nseeds = 0;
+    geometry_scale = geom_scale;
+    view_params.frame_id = frame_id; view_params.frame_offset = frame_offset;
+    view_params.frame_dims.xy = glm::uvec2(width, height);
+    gl_GlobalInvocationID.xy = glm::uvec2(px, py);
+    const bool visible = raytrace_test_visibility(glm::vec3(from[0], from[1], from[2]), glm::vec3(dir[0], dir[1], dir[2]), dist);
+    out[0] = visible ? 1.0f : 0.0f; out[1] = (float)g_rq.inits; out[2] = g_rq.tmin; out[3] = g_rq.tmax; out[4] = (float)g_nseeds;
+    std::memcpy(out + 5, g_seeds, sizeof(uint) * g_nseeds);
+}
+
+// 1 = the candidate is rejected (the ray passes through); *lcg_state advances when a draw was needed
+int32_t ref_alpha_filter(float alpha, uint32_t material_flags, uint32_t *lcg_state) {
+    using namespace refloop;
+    RTHit hit;
+    std::memset(&hit, 0, sizeof(hit));
+    std::memset(&material_params[0], 0, sizeof(material_params[0]));
+    material_params[0].flags = material_flags;
+    g_alpha = alpha;
+    LCGRand rng;
+    rng.state = *lcg_state;
+    const bool rejected = alpha_tail(hit, rng);
+    *lcg_state = rng.state;
+    return rejected ? 1 : 0;
 }
 
 } // extern "C"

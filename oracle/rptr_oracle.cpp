@@ -11,9 +11,10 @@
 // skymodel_radiance, sun sampling, the material decode with texture handles, sample_direct_light (nee.glsl), the complete
 // per-vertex shading function shade_base_material() with its LCG draw order, the miss shading compute_sky_illum(), and blocks
 // cut out of the shader files at build time (oracle/ref_shim/ref_loop.cpp): the ray-generation head, the bounce prologue and
-// the Russian-roulette step of main_spp, geometry_scale_to_tmin, the running mean of process_samples.comp.
+// the Russian-roulette step of main_spp, the alpha test of generate_candidate_hit, raytrace_test_visibility over scripted ray
+// queries, geometry_scale_to_tmin, the running mean of process_samples.comp.
 // "PARITY UNPINNED" (restated only, no reference-executed check possible): the glue of pt_megakernel.glsl between those pieces
-// (loop control, the rayQueryEXT candidate loop with its alpha filter, the shadow-ray range test), accumulate.glsl, the
+// (loop control, the closest-hit rayQueryEXT candidate loop whose candidate order is the driver's), accumulate.glsl, the
 // texture unit (UNORM8 / sRGB decode of a texel), the ray/triangle routine, which the reference does not contain at all, and
 // view_params.VP / VP_reference behind the motion / jitter AOV image: built with glm 0.9.9.8, a configure-time download of
 // the reference (ext/CMakeLists.txt:18-21) that is not in its tree -- glm's published operator*, inverse and
@@ -846,23 +847,39 @@ static V3 sample_tri_lights(const Frame &f, V3 hit_p, V3 hit_n, V2 dir_sample, V
 static inline float geometry_scale_to_tmin(V3 orig, float scale) { return (length(orig) + scale) * 0.000005f; } // vulkan/geometry.glsl:76-78
 
 
+// pieces of raytrace_test_visibility / generate_candidate_hit (vulkan/pt_megakernel.glsl:216-272, 202-210)
+// range of a shadow ray: (eps, dist - eps) with eps = geometry_scale_to_tmin; not cast at all (= visible) when dist - 2 eps <= 0
+static bool shadow_ray_range(V3 from, float dist, float geometry_scale, float &tmin, float &tmax) {
+    float eps = geometry_scale_to_tmin(from, geometry_scale);
+    if (dist - 2.0f * eps > 0.0f) {
+        tmin = eps;
+        tmax = dist - eps;
+        return true;
+    }
+    return false;
+}
+// every candidate of a shadow ray gets its own LCG (:252-254)
+static Lcg shadow_alpha_rng(uint32_t prim, uint32_t instance, uint32_t frame_id, uint32_t frame_offset, uint32_t pixel_linear) {
+    return lcg_seed(prim ^ frame_id, instance ^ frame_offset, pixel_linear);
+}
+// stochastic alpha test of a candidate (:205-207): true = rejected, the ray passes
+static bool alpha_test_rejects(float alpha, Lcg &rng) { return !(alpha > 0.0f) || (alpha < 1.0f && lcg_randomf(rng) > alpha); }
+
 // raytrace_test_visibility: vulkan/pt_megakernel.glsl:216-272
 static bool test_visibility(const Frame &f, V3 from, V3 dir, float dist, float geometry_scale, uint32_t pixel_linear,
                             uint32_t frame_id, Counters &cnt) {
-    float eps = geometry_scale_to_tmin(from, geometry_scale);
-    if (dist - 2.0f * eps > 0.0f) {
+    float tmin, tmax;
+    if (shadow_ray_range(from, dist, geometry_scale, tmin, tmax)) {
         cnt.shadow_rays++;
         const Scene &s = *f.s;
-        bool occluded = any_hit(s, from, dir, eps, dist - eps, [&](int id, float, float, float) {
+        bool occluded = any_hit(s, from, dir, tmin, tmax, [&](int id, float, float, float) {
             const Tri &tr = s.tris[id];
             const GeomInst &g = s.ginst[tr.geom_inst];
             if (g.flags & RPTR_GEOMETRY_FLAGS_NOALPHA) return true;
             const rptr_base_material &m = s.materials[calc_hit_material_id(g, (uint32_t)tr.prim)];
             if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) return true;
-            Lcg arng = lcg_seed((uint32_t)tr.prim ^ frame_id, (uint32_t)g.instance ^ f.a->frame_offset, pixel_linear);
-            float alpha = material_alpha(s.texset, m);
-            if (!(alpha > 0.0f) || (alpha < 1.0f && lcg_randomf(arng) > alpha)) return false;
-            return true;
+            Lcg arng = shadow_alpha_rng((uint32_t)tr.prim, (uint32_t)g.instance, frame_id, f.a->frame_offset, pixel_linear);
+            return !alpha_test_rejects(material_alpha(s.texset, m), arng);
         });
         return !occluded;
     }
@@ -1562,6 +1579,21 @@ void oracle_camera_ray(const oracle_scene *os, const oracle_render_args *a, int3
     camera_ray(f, px, py, rng, a->first_sample, o, d);
     out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = d.x; out[4] = d.y; out[5] = d.z;
     std::memcpy(out + 6, &rng.lcg, 4);
+}
+// out = (tmin, tmax); returns 1 when the shadow ray is cast
+int32_t oracle_shadow_ray_range(const float *from, float dist, float geometry_scale, float *out) {
+    return shadow_ray_range(v3(from[0], from[1], from[2]), dist, geometry_scale, out[0], out[1]) ? 1 : 0;
+}
+uint32_t oracle_shadow_alpha_seed(uint32_t prim, uint32_t instance, uint32_t frame_id, uint32_t frame_offset, uint32_t pixel_linear) {
+    return shadow_alpha_rng(prim, instance, frame_id, frame_offset, pixel_linear).state;
+}
+// 1 = rejected; *lcg_state advances when a draw was needed.  material_flags: BASE_MATERIAL_NOALPHA skips the test (:204)
+int32_t oracle_alpha_filter(float alpha, uint32_t material_flags, uint32_t *lcg_state) {
+    if (material_flags & RPTR_BASE_MATERIAL_NOALPHA) return 0;
+    Lcg r{*lcg_state};
+    const bool rejected = alpha_test_rejects(alpha, r);
+    *lcg_state = r.state;
+    return rejected ? 1 : 0;
 }
 void oracle_running_mean(const float *x, float *history, uint32_t sample_base_index, uint32_t sample_batch_size) {
     fold_sample(history, x, sample_base_index, sample_batch_size);
