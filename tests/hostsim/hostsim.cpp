@@ -177,6 +177,16 @@ void hostsim_unpack_material(const hostsim_scene *s, int32_t mid, int32_t transm
     out[12] = e.x; out[13] = e.y; out[14] = e.z;
 }
 void hostsim_halton_23(int32_t k, float *out) { halton_23(k, out); }
+// the product's stochastic alpha test (csrc/rptr_bvh.cuh): closest-hit form (draws from the given LCG) and shadow-ray form
+// (own LCG per candidate); 1 = rejected / 1 = the candidate blocks the ray
+int32_t hostsim_alpha_rejects(float alpha, uint32_t *state) { return alpha_rejects(alpha, *state) ? 1 : 0; }
+int32_t hostsim_shadow_candidate_passes(int32_t alpha8, int32_t prim, int32_t instance, uint32_t frame_id, uint32_t frame_offset, uint32_t pixel_linear) {
+    GeomInst g;
+    memset(&g, 0, sizeof(g));
+    g.instance = instance;
+    const AlphaFilter af{&g, frame_id, frame_offset, pixel_linear};
+    return shadow_candidate_passes(af, pack_gi_alpha(0, alpha8), prim) ? 1 : 0;
+}
 // generate_primary for one pixel sample: out = origin(3), dir(3), bits(first sampler word afterwards), tmin, tmax
 void hostsim_primary_ray(const hostsim_scene *s, const hostsim_args *a, int32_t px, int32_t py, uint32_t sample_index, float *out) {
     FrameParams fp = make_frame(s, a);
