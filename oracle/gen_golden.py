@@ -266,6 +266,20 @@ def gen_vectors(n=512, seed=1234):
     for i in range(n_rm):
         R.ref_running_mean(rm_x[i].ctypes.data_as(po.f32p), rm_o[i].ctypes.data_as(po.f32p), int(rm_n[i, 0]), int(rm_n[i, 1]))
     out.update(rm_x=rm_x, rm_hist=rm_h, rm_n=rm_n, rm_out=rm_o)
+    # camera basis of update_view_parameters (vulkan/render_vulkan.cpp:2887-2895), cut out of the reference's host code
+    n_cb = 256
+    cb_in = np.zeros((n_cb, 12), np.float32)  # pos3, dir3, up3, fovy, w, h
+    cb_in[:, 0:3] = rs.normal(size=(n_cb, 3)) * 10
+    cb_in[:, 3:6] = unit(rs.normal(size=(n_cb, 3))) * rs.choice([1.0, 1.0, 0.5, 3.0], (n_cb, 1))  # dir is NOT normalised by the function
+    cb_in[:, 6:9] = unit(rs.normal(size=(n_cb, 3)))
+    cb_in[:, 9] = rs.uniform(10, 120, n_cb)
+    cb_in[:, 10:12] = np.array([(1920, 1080), (1280, 720), (640, 480), (333, 777)], np.float32)[rs.integers(0, 4, n_cb)]
+    cb_out = np.zeros((n_cb, 9), np.float32)
+    for i in range(n_cb):
+        c = T.RenderCameraParams()
+        c.pos[:], c.dir[:], c.up[:], c.fovy = cb_in[i, 0:3].tolist(), cb_in[i, 3:6].tolist(), cb_in[i, 6:9].tolist(), float(cb_in[i, 9])
+        R.ref_view_params(C.byref(c), int(cb_in[i, 10]), int(cb_in[i, 11]), cb_out[i].ctypes.data_as(po.f32p))
+    out.update(cb_in=cb_in, cb_out=cb_out)
     # raytrace_test_visibility over scripted ray queries + the alpha test of generate_candidate_hit
     n_vis = 768
     vis_in = np.zeros((n_vis, 14), np.float32)  # from3, dir3, dist, geometry_scale, frame_id, frame_offset, px, py, n_cands, opaque_hit

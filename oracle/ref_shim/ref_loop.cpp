@@ -245,3 +245,24 @@ int32_t ref_alpha_filter(float alpha, uint32_t material_flags, uint32_t *lcg_sta
 }
 
 } // extern "C"
+
+// ---- camera basis of RenderVulkan::update_view_parameters (vulkan/render_vulkan.cpp:2887-2895), host C++ of the reference ----
+// (the statements from `glm::vec2 img_plane_size;` to `dir_top_left`, cut out by the Makefile; glm calls go to the shim)
+namespace refcam {
+struct RenderTargetStandIn { glm::uvec2 d; glm::uvec2 dims() const { return d; } };
+static void camera_basis(const glm::vec3 &dir, const glm::vec3 &up, const float fovy, uint32_t w, uint32_t h, float *out) {
+    RenderTargetStandIn rt{glm::uvec2(w, h)};
+    RenderTargetStandIn *render_targets[1] = {&rt};
+#include "gen/camera_basis.inc"
+    out[0] = dir_du.x; out[1] = dir_du.y; out[2] = dir_du.z;
+    out[3] = dir_dv.x; out[4] = dir_dv.y; out[5] = dir_dv.z;
+    out[6] = dir_top_left.x; out[7] = dir_top_left.y; out[8] = dir_top_left.z;
+}
+} // namespace refcam
+
+extern "C" {
+// out = du(3), dv(3), top_left(3)
+void ref_view_params(const rptr_camera_params *cam, uint32_t w, uint32_t h, float *out) {
+    refcam::camera_basis(glm::vec3(cam->dir[0], cam->dir[1], cam->dir[2]), glm::vec3(cam->up[0], cam->up[1], cam->up[2]), cam->fovy, w, h, out);
+}
+} // extern "C"

@@ -12,7 +12,7 @@
 // per-vertex shading function shade_base_material() with its LCG draw order, the miss shading compute_sky_illum(), and blocks
 // cut out of the shader files at build time (oracle/ref_shim/ref_loop.cpp): the ray-generation head, the bounce prologue and
 // the Russian-roulette step of main_spp, the alpha test of generate_candidate_hit, raytrace_test_visibility over scripted ray
-// queries, geometry_scale_to_tmin, the running mean of process_samples.comp.
+// queries, geometry_scale_to_tmin, the running mean of process_samples.comp, the camera basis of update_view_parameters.
 // "PARITY UNPINNED" (restated only, no reference-executed check possible): the glue of pt_megakernel.glsl between those pieces
 // (loop control, the closest-hit rayQueryEXT candidate loop whose candidate order is the driver's), accumulate.glsl, the
 // texture unit (UNORM8 / sRGB decode of a texel), the ray/triangle routine, which the reference does not contain at all, and

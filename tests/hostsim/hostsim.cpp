@@ -141,6 +141,7 @@ int hostsim_render_sample_aov(const hostsim_scene *s, const hostsim_args *a, uin
 int hostsim_render_sample_aov3(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba, float *aov) {
     return render_sample(s, a, sample_index, rgba, aov, 12);
 }
+void hostsim_view_params(const rptr_camera_params *cam, int32_t w, int32_t h, float *out) { view_params(*cam, w, h, out, out + 3, out + 6); }
 void hostsim_view_projection(const rptr_camera_params *cam, int32_t w, int32_t h, float *out) { view_projection(*cam, w, h, out); }
 
 // sampler calls replayed through the product's rptr_pointsets.cuh (same protocol as oracle_pointset_replay)
