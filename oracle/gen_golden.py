@@ -488,6 +488,18 @@ def gen_pointsets(n=384, seed=4321):
     hal = np.zeros((R.ref_halton_23(None), 2), np.float32)
     R.ref_halton_23(hal.ctypes.data_as(po.f32p))
     out["halton_23"] = hal
+    # the screen-jitter statements of update_view_parameters executed from the reference's host code
+    rj = np.random.default_rng(611)
+    jin = np.zeros((256, 4), np.uint32)
+    jin[:, 0] = rj.integers(0, 2 ** 32, 256, dtype=np.uint64).astype(np.uint32)
+    jin[:64, 0] = np.arange(64)
+    jin[:, 1] = rj.integers(0, 5000, 256)
+    jin[:, 2:4] = np.array([(1920, 1080), (1280, 720), (333, 77), (640, 480)], np.uint32)[rj.integers(0, 4, 256)]
+    jout = np.zeros((256, 2), np.float32)
+    for i in range(256):
+        R.ref_screen_jitter(int(jin[i, 0]), int(jin[i, 1]), int(jin[i, 2]), int(jin[i, 3]), jout[i].ctypes.data_as(po.f32p))
+    out["jitter_in"] = jin
+    out["jitter_out"] = jout
     R.ref_morton_sample_id.restype = C.c_uint32
     out["morton_in"] = mq
     out["morton_out"] = np.array([R.ref_morton_sample_id(*[int(x) for x in row]) for row in mq], np.uint32)

@@ -128,6 +128,16 @@ int ref_halton_23(float *out_) {
     return n;
 }
 
+// the raster-TAA screen jitter statements of update_view_parameters (vulkan/render_vulkan.cpp:2922-2924), cut out of the
+// reference's host code by the Makefile; RASTER_TAA_NUM_SAMPLES = 16 is the build's definition (CMakeLists.txt:30)
+void ref_screen_jitter(uint32_t frame_offset, uint32_t frame_id, uint32_t w, uint32_t h, float *out_) {
+    constexpr size_t num_sample_offsets = 16;
+    struct { glm::uvec2 frame_dims; glm::vec2 screen_jitter; } viewParams;
+    viewParams.frame_dims = glm::uvec2(w, h);
+#include "gen/screen_jitter.inc"
+    out_[0] = viewParams.screen_jitter.x; out_[1] = viewParams.screen_jitter.y;
+}
+
 uint32_t ref_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, uint32_t tw, uint32_t th, int hash_tile_id, int hash_sample_id) {
     return refps::zorder::morton_sample_id(sample_id, glm::uvec2(px, py), glm::uvec2(tw, th), hash_tile_id != 0, hash_sample_id != 0);
 }

@@ -174,6 +174,12 @@ def test_halton_table_and_screen_jitter(H, oracle, gold):
             got = np.zeros(2, np.float32)
             fn(fo, fid, w, h, got.ctypes.data_as(oracle.f32p))
             assert np.array_equal(got.view(np.uint32), want.astype(np.float32).view(np.uint32))
+    # and against the statements of update_view_parameters themselves, executed from the reference's host code
+    for (fo, fid, w, h), want in zip(gold["jitter_in"].tolist(), gold["jitter_out"]):
+        for fn in (oracle.lib().oracle_screen_jitter, H.hostsim_screen_jitter):
+            got = np.zeros(2, np.float32)
+            fn(fo, fid, w, h, got.ctypes.data_as(oracle.f32p))
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (fo, fid, w, h)
 
 
 def test_raster_taa_frames_match_oracle(H, oracle):
