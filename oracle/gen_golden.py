@@ -280,6 +280,15 @@ def gen_vectors(n=512, seed=1234):
         c.pos[:], c.dir[:], c.up[:], c.fovy = cb_in[i, 0:3].tolist(), cb_in[i, 3:6].tolist(), cb_in[i, 6:9].tolist(), float(cb_in[i, 9])
         R.ref_view_params(C.byref(c), int(cb_in[i, 10]), int(cb_in[i, 11]), cb_out[i].ctypes.data_as(po.f32p))
     out.update(cb_in=cb_in, cb_out=cb_out)
+    # display chain: tonemap() + linear_to_srgb() executed from the reference (own stream)
+    rt = np.random.default_rng(90210)
+    tm_rgb = (10.0 ** rt.uniform(-4, 2, (768, 3))).astype(np.float32)
+    tm_rgb[::11] = 0.0
+    tm_mode = rt.integers(0, 3, 768).astype(np.int32)
+    tm_out = np.zeros((768, 6), np.float32)
+    for i in range(768):
+        R.ref_tonemap_srgb(int(tm_mode[i]), tm_rgb[i].ctypes.data_as(po.f32p), tm_out[i].ctypes.data_as(po.f32p))
+    out.update(tm_rgb=tm_rgb, tm_mode=tm_mode, tm_out=tm_out)
     # raytrace_test_visibility over scripted ray queries + the alpha test of generate_candidate_hit
     n_vis = 768
     vis_in = np.zeros((n_vis, 14), np.float32)  # from3, dir3, dist, geometry_scale, frame_id, frame_offset, px, py, n_cands, opaque_hit

@@ -139,6 +139,7 @@ def ref():
         R.ref_alpha_filter.restype = C.c_int32
         R.ref_alpha_filter.argtypes = [C.c_float, C.c_uint32, C.POINTER(C.c_uint32)]
         R.ref_screen_jitter.argtypes = [C.c_uint32] * 4 + [f32p]
+        R.ref_tonemap_srgb.argtypes = [C.c_int32, f32p, f32p]
         R.ref_view_params.argtypes = [C.POINTER(T.RenderCameraParams), C.c_uint32, C.c_uint32, f32p]
         R.ref_bounce_prologue.argtypes = [f32p, C.c_uint32, C.c_int32, C.c_float, f32p]
         R.ref_russian_roulette.restype = C.c_int32

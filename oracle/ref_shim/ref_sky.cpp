@@ -14,6 +14,7 @@ using namespace glm;
 #include "rendering/util.glsl"
 #include "rendering/lights/sky_model_arhosek/sky_model.glsl"
 #include "rendering/lights/sun.glsl"
+#include "rendering/postprocess/tonemapping_utils.glsl"
 } // namespace refsky
 
 extern "C" {
@@ -33,6 +34,14 @@ void ref_sample_sun_dir(const float *sun_dir, float cos_radius, const float *u2,
     glm::vec3 d = refsky::sample_sun_dir(s, cos_radius, glm::vec2(u2[0], u2[1]));
     out[0] = d.x; out[1] = d.y; out[2] = d.z;
     out[3] = refsky::sample_sun_dir_pdf(s, cos_radius, d);
+}
+
+// tonemap(mode, rgb) of rendering/postprocess/tonemapping_utils.glsl:16-32 followed by linear_to_srgb (rendering/util.glsl:25-28):
+// the display chain of process_samples.comp:148-149, 188.  out = tonemapped rgb (3), then its sRGB encoding (3)
+void ref_tonemap_srgb(int32_t mode, const float *rgb, float *out) {
+    glm::vec3 c = refsky::tonemap(mode, glm::vec3(rgb[0], rgb[1], rgb[2]));
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
+    out[3] = refsky::linear_to_srgb(c.x); out[4] = refsky::linear_to_srgb(c.y); out[5] = refsky::linear_to_srgb(c.z);
 }
 
 } // extern "C"
