@@ -289,6 +289,27 @@ def gen_vectors(n=512, seed=1234):
     for i in range(768):
         R.ref_tonemap_srgb(int(tm_mode[i]), tm_rgb[i].ctypes.data_as(po.f32p), tm_out[i].ctypes.data_as(po.f32p))
     out.update(tm_rgb=tm_rgb, tm_mode=tm_mode, tm_out=tm_out)
+    # rt_intersect.comp:main over scripted ray queries (own stream)
+    rq = np.random.default_rng(31337)
+    n_rq = 512
+    rq_q = np.zeros((n_rq, 8), np.float32)
+    rq_q[:, 0:3] = rq.normal(size=(n_rq, 3)) * 10.0 ** rq.uniform(-2, 3, (n_rq, 1))
+    rq_mode = rq.choice([0, 0, 0, 1, 7, -1, -5], n_rq).astype(np.int32)
+    rq_q[:, 3] = rq_mode.view(np.float32)
+    rq_q[:, 4:7] = unit(rq.normal(size=(n_rq, 3)))
+    rq_q[:, 7] = rq.choice([1e20, 5.0, 0.5], n_rq)
+    rq_hit = np.zeros((n_rq, 6), np.float32)  # hit, bary2, custom index, geometry index, prim
+    rq_hit[:, 0] = rq.random(n_rq) < 0.6
+    rq_hit[:, 1:3] = rq.random((n_rq, 2)) * 0.5
+    rq_hit[:, 3] = rq.integers(0, 1000, n_rq)
+    rq_hit[:, 4] = rq.integers(0, 8, n_rq)
+    rq_hit[:, 5] = rq.integers(0, 2 ** 24, n_rq)
+    rq_res = np.full((n_rq, 4), 123.0, np.float32)  # what the caller passed in: a skipped query must leave it alone
+    rq_info = np.zeros((n_rq, 4), np.float32)
+    for i in range(n_rq):
+        R.ref_ray_query(rq_q[i].ctypes.data_as(po.f32p), int(rq_hit[i, 0]), rq_hit[i, 1:3].copy().ctypes.data_as(po.f32p), int(rq_hit[i, 3]),
+                        int(rq_hit[i, 4]), int(rq_hit[i, 5]), rq_res[i].ctypes.data_as(po.f32p), rq_info[i].ctypes.data_as(po.f32p))
+    out.update(rq_q=rq_q, rq_hit=rq_hit, rq_res=rq_res, rq_info=rq_info)
     # raytrace_test_visibility over scripted ray queries + the alpha test of generate_candidate_hit
     n_vis = 768
     vis_in = np.zeros((n_vis, 14), np.float32)  # from3, dir3, dist, geometry_scale, frame_id, frame_offset, px, py, n_cands, opaque_hit

@@ -46,6 +46,7 @@ template <class T> struct tvec4 {
     tvec4(T a_, T b_, T c, T d) : x(a_), y(b_), z(c), w(d) {}
     tvec4(const tvec3<T> &v, T d) : x(v.x), y(v.y), z(v.z), w(d) {}
     tvec4(const tvec2<T> &u, const tvec2<T> &v) : x(u.x), y(u.y), z(v.x), w(v.y) {}
+    tvec4(T a_, T b_, const tvec2<T> &v) : x(a_), y(b_), z(v.x), w(v.y) {} // vulkan/rt_intersect.comp:56
     template <class U> explicit tvec4(const tvec4<U> &o) : x(T(o.x)), y(T(o.y)), z(T(o.z)), w(T(o.w)) {}
     T &operator[](int i) { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
     const T &operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }

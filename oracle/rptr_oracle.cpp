@@ -12,7 +12,8 @@
 // per-vertex shading function shade_base_material() with its LCG draw order, the miss shading compute_sky_illum(), and blocks
 // cut out of the shader files at build time (oracle/ref_shim/ref_loop.cpp): the ray-generation head, the bounce prologue and
 // the Russian-roulette step of main_spp, the alpha test of generate_candidate_hit, raytrace_test_visibility over scripted ray
-// queries, geometry_scale_to_tmin, the running mean of process_samples.comp, the camera basis of update_view_parameters.
+// queries, geometry_scale_to_tmin, the running mean of process_samples.comp, the camera basis of update_view_parameters,
+// the body of rt_intersect.comp.
 // "PARITY UNPINNED" (restated only, no reference-executed check possible): the glue of pt_megakernel.glsl between those pieces
 // (loop control, the closest-hit rayQueryEXT candidate loop whose candidate order is the driver's), accumulate.glsl, the
 // texture unit (UNORM8 / sRGB decode of a texel), the ray/triangle routine, which the reference does not contain at all, and
@@ -1312,6 +1313,20 @@ int oracle_render_sample(const oracle_scene *os, const oracle_render_args *a, ui
     return 0;
 }
 
+// pieces of rt_intersect.comp:main: t_min of a query (:41) and the packing of its result (:54-66); geom_inst = instance custom
+// index + geometry index, the flattened (instance, geometry) pair
+static inline float ray_query_tmin(V3 origin) { return RPTR_RAY_EPSILON * length(origin); }
+static inline void pack_ray_result(bool hit, float u, float v, int32_t geom_inst, int32_t prim, float *out) {
+    int32_t gi = -1, pr = -1;
+    float bu = -1.0f, bv = -1.0f;
+    if (hit) { gi = geom_inst; pr = prim; bu = u; bv = v; }
+    out[0] = bu;
+    out[1] = bv;
+    std::memcpy(&out[2], &gi, 4);
+    std::memcpy(&out[3], &pr, 4);
+}
+float oracle_ray_query_tmin(const float *origin) { return ray_query_tmin(v3(origin[0], origin[1], origin[2])); }
+void oracle_pack_ray_result(int32_t hit, float u, float v, int32_t geom_inst, int32_t prim, float *out) { pack_ray_result(hit != 0, u, v, geom_inst, prim, out); }
 // RQ_CLOSEST semantics (vulkan/rt_intersect.comp:28-68): result = (bary.x, bary.y, bits(instance+geometry), bits(prim)),
 // miss -> (0,0,bits(-1),bits(-1)); extra_t (optional) receives t.
 int oracle_trace_closest(const oracle_scene *os, const rptr_render_ray_query *q, int32_t n, float *results, float *extra_t) {
@@ -1321,15 +1336,10 @@ int oracle_trace_closest(const oracle_scene *os, const rptr_render_ray_query *q,
         if (q[i].mode_or_data < 0) continue; // rt_intersect.comp:44-45
         Hit h;
         V3 o = v3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), d = v3(q[i].dir[0], q[i].dir[1], q[i].dir[2]);
-        const float tmin = RPTR_RAY_EPSILON * length(o); // :41
+        const float tmin = ray_query_tmin(o);
         bool ok = closest_hit(s, o, d, tmin, q[i].t_max, tmin, 0x7fffffff, h);
-        int32_t gi = -1, prim = -1;
-        float u = -1.0f, v = -1.0f; // :55-57
-        if (ok) { gi = s.tris[h.tri].geom_inst; prim = s.tris[h.tri].prim; u = h.u; v = h.v; }
-        results[4 * i + 0] = u;
-        results[4 * i + 1] = v;
-        std::memcpy(&results[4 * i + 2], &gi, 4);
-        std::memcpy(&results[4 * i + 3], &prim, 4);
+        if (ok) pack_ray_result(true, h.u, h.v, s.tris[h.tri].geom_inst, s.tris[h.tri].prim, &results[4 * i]);
+        else pack_ray_result(false, 0.0f, 0.0f, 0, 0, &results[4 * i]);
         if (extra_t) extra_t[i] = ok ? h.t : -1.0f;
     }
     return 0;
