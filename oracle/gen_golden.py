@@ -289,6 +289,8 @@ def gen_vectors(n=512, seed=1234):
     for i in range(768):
         R.ref_tonemap_srgb(int(tm_mode[i]), tm_rgb[i].ctypes.data_as(po.f32p), tm_out[i].ctypes.data_as(po.f32p))
     out.update(tm_rgb=tm_rgb, tm_mode=tm_mode, tm_out=tm_out)
+    # the reference's srgb_to_linear over all 256 code values (cross-check of the texel decode)
+    out["srgb_decode"] = np.array([R.ref_srgb_to_linear(C.c_float(float(np.float32(v) / np.float32(255.0)))) for v in range(256)], np.float32)
     # rt_intersect.comp:main over scripted ray queries (own stream)
     rq = np.random.default_rng(31337)
     n_rq = 512

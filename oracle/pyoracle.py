@@ -96,6 +96,8 @@ def lib():
         L.oracle_ray_query_tmin.restype = C.c_float
         L.oracle_ray_query_tmin.argtypes = [f32p]
         L.oracle_pack_ray_result.argtypes = [C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32, f32p]
+        L.oracle_decode_texel.restype = C.c_float
+        L.oracle_decode_texel.argtypes = [C.c_int32, C.c_int32]
         L.oracle_bounce_prologue.argtypes = [f32p, C.c_uint32, C.c_int32, C.c_void_p, C.c_float, f32p]
         L.oracle_russian_roulette.restype = C.c_int32
         L.oracle_russian_roulette.argtypes = [C.c_int32, C.c_int32, f32p, C.c_float]
@@ -144,6 +146,8 @@ def ref():
         R.ref_screen_jitter.argtypes = [C.c_uint32] * 4 + [f32p]
         R.ref_tonemap_srgb.argtypes = [C.c_int32, f32p, f32p]
         R.ref_ray_query.argtypes = [f32p, C.c_int32, f32p, C.c_int32, C.c_int32, C.c_int32, f32p, f32p]
+        R.ref_srgb_to_linear.restype = C.c_float
+        R.ref_srgb_to_linear.argtypes = [C.c_float]
         R.ref_view_params.argtypes = [C.POINTER(T.RenderCameraParams), C.c_uint32, C.c_uint32, f32p]
         R.ref_bounce_prologue.argtypes = [f32p, C.c_uint32, C.c_int32, C.c_float, f32p]
         R.ref_russian_roulette.restype = C.c_int32

@@ -44,4 +44,8 @@ void ref_tonemap_srgb(int32_t mode, const float *rgb, float *out) {
     out[3] = refsky::linear_to_srgb(c.x); out[4] = refsky::linear_to_srgb(c.y); out[5] = refsky::linear_to_srgb(c.z);
 }
 
+// srgb_to_linear (rendering/util.glsl:39-42): the reference's own statement of the sRGB transfer function, the cross-check for
+// the texel decode the backend performs in place of the texture unit
+float ref_srgb_to_linear(float x) { return refsky::srgb_to_linear(x); }
+
 } // extern "C"

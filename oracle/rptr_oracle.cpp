@@ -1325,6 +1325,8 @@ static inline void pack_ray_result(bool hit, float u, float v, int32_t geom_inst
     std::memcpy(&out[2], &gi, 4);
     std::memcpy(&out[3], &pr, 4);
 }
+// one 8-bit texel channel as the texture unit returns it (UNORM8, or sRGB8 through the transfer function)
+float oracle_decode_texel(int32_t v, int32_t srgb) { return TextureSet::decode(v, srgb != 0); }
 float oracle_ray_query_tmin(const float *origin) { return ray_query_tmin(v3(origin[0], origin[1], origin[2])); }
 void oracle_pack_ray_result(int32_t hit, float u, float v, int32_t geom_inst, int32_t prim, float *out) { pack_ray_result(hit != 0, u, v, geom_inst, prim, out); }
 // RQ_CLOSEST semantics (vulkan/rt_intersect.comp:28-68): result = (bary.x, bary.y, bits(instance+geometry), bits(prim)),
