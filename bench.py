@@ -97,24 +97,33 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def measured_traffic(args, overlap):
-    """DRAM bytes per closest-hit launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the launches of a
-    frame) from the committed ncu capture of this same command, or None when the workload is not the captured one."""
-    p = os.path.join(ROOT, "profiles", "r01_trace_traffic.json")
-    if not os.path.exists(p):
-        return None, None
-    with open(p) as f:
-        t = json.load(f)
-    w = t["workload"]
-    same = (args.scene == w["scene"] and args.tris == w["tris"] and args.spp == w["spp"] and args.width == w["width"] and
-            args.height == w["height"] and not args.wave_paths and not args.option and args.gpus == 1)
-    if not same:
-        return None, None
-    if overlap:  # per launch over the closest-hit AND shadow launches, like `achieved`
-        n = t["closest"]["launches"] + t["shadow"]["launches"]
-        tot = t["closest"]["avg_dram_bytes_per_launch"] * t["closest"]["launches"] + t["shadow"]["avg_dram_bytes_per_launch"] * t["shadow"]["launches"]
-        return tot / n, "profiles/r01_trace_traffic.json (closest + shadow launches)"
-    return t["closest"]["avg_dram_bytes_per_launch"], "profiles/r01_trace_traffic.json"
+def measured_counters(args, overlap):
+    """Hardware counters of the trace kernel per launch -- DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum), warp and
+    thread instructions (smsp__inst_executed.sum, smsp__thread_inst_executed.sum) -- from the committed ncu capture of this same
+    command (tools/ncu_trace_metrics.py), or None when the workload is not a captured one.  Hardware counters need the profiler,
+    and nothing timed under a profiler is a bench value: the counters are deterministic for a fixed scene / seed, the time is
+    this run's."""
+    for name in ("r02_trace_metrics_%s.json" % args.scene, "r01_trace_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(p):
+            continue
+        with open(p) as f:
+            t = json.load(f)
+        w = t["workload"]
+        same = (args.scene == w["scene"] and args.tris == w["tris"] and args.spp == w["spp"] and args.width == w["width"] and
+                args.height == w["height"] and not args.wave_paths and not args.option and args.gpus == 1)
+        if not same:
+            continue
+        kinds = ["closest", "shadow"] if overlap else ["closest"]  # per launch over the same launches as `achieved`
+        n = sum(t[k]["launches"] for k in kinds)
+
+        def avg(key):
+            if any(key not in t[k] for k in kinds):
+                return None
+            return sum(t[k][key] * t[k]["launches"] for k in kinds) / n
+        return {"dram_bytes": avg("avg_dram_bytes_per_launch"), "warp_inst": avg("avg_warp_inst_per_launch"),
+                "thread_inst": avg("avg_thread_inst_per_launch"), "source": "profiles/%s (ncu, %s launches)" % (name, " + ".join(kinds))}
+    return None
 
 
 def make_scene(args):
@@ -133,39 +142,65 @@ def workload_name(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed on.  Passed to the oracle explicitly, so a launcher
+    that exports OMP_NUM_THREADS=1 (torch.distributed.run does) cannot throttle the baseline."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+class CpuArm:
+    """The restated reference megakernel (oracle/) on this box's host cores, on a bounded sample of the same workload:
+    the same scene, camera, frame size and samples per pixel as the GPU arm, on a subset of the frame's rows -- full-width
+    bands of 16 rows spread evenly over the frame so that sky and geometry rows are both represented.  Every pixel sample is
+    an independent path with its own seed, so Msamples/s of the subset is the rate of the whole frame."""
+
+    BAND = 16
+
+    def __init__(self, args, scene):
+        from oracle import pyoracle as po
+        from realtimepathtracingresearchframework_b200 import load_sky_fit
+        self.po, self.args, self.scene = po, args, scene
+        self.o = po.OracleScene(scene)
+        self.sp = load_sky_fit()
+        self.threads = host_threads()
+        self.img = np.zeros((args.height, args.width, 4), np.float32)
+        self.rate = None  # samples / s, refined by every run
+
+    def _render(self, ys, rows, spp):
+        a = self.args
+        t0 = time.perf_counter()
+        self.o.render(a.width, a.height, self.scene.camera, self.sp, spp=spp, region=(0, ys, a.width, min(ys + rows, a.height)), out=self.img,
+                      n_threads=self.threads)
+        return time.perf_counter() - t0
+
+    def run(self, seconds):
+        a = self.args
+        if self.rate is None:  # probe: one band in the middle of the frame, 1 spp
+            dt = self._render(a.height // 2 - self.BAND // 2, self.BAND, 1)
+            self.rate = a.width * self.BAND / dt
+        per_band = a.width * self.BAND * a.spp
+        bands = int(max(1, min(a.height // self.BAND, seconds * self.rate / per_band)))
+        step = a.height / bands
+        samples, t = 0, 0.0
+        for b in range(bands):
+            ys = min(int(b * step + 0.5 * (step - self.BAND)), a.height - self.BAND)
+            ys = max(ys, 0)
+            t += self._render(ys, self.BAND, a.spp)
+            samples += a.width * (min(ys + self.BAND, a.height) - ys) * a.spp
+        self.rate = samples / t
+        used = int(self.po.lib().oracle_last_threads())
+        return {"value": samples / t / 1e6, "unit": "Msamples/s", "cores": used, "kind": "port", "seconds": t,
+                "sample": "%d of %d rows (%d bands of %d rows spread over the frame) x %d px x %d spp = the GPU arm's scene, camera, "
+                          "frame size and spp on a subset of its pixels (samples are independent paths: the rate of the subset is the "
+                          "rate of the frame), %.1f s on %d OpenMP threads; restated reference megakernel (the reference has no CPU path)"
+                          % (bands * self.BAND, a.height, bands, self.BAND, a.width, a.spp, t, used)}
+
+
 def cpu_baseline(args, scene, seconds):
-    """The restated reference megakernel (oracle/) on this box's host cores, on a bounded sample of the same workload."""
-    from oracle import pyoracle as po
-    from realtimepathtracingresearchframework_b200 import load_sky_fit
-    o = po.OracleScene(scene)
-    sp = load_sky_fit()
-    cores = po.lib().oracle_num_threads()
-    # probe: a 1920 x 32 band in the middle of the frame, 1 spp
-    y0 = args.height // 2 - 16
-    t0 = time.perf_counter()
-    o.render(args.width, args.height, scene.camera, sp, spp=1, region=(0, y0, args.width, y0 + 32))
-    probe = time.perf_counter() - t0
-    rate = args.width * 32 / probe
-    # bounded sample: full-width bands spread over the frame so sky and geometry rows are both represented; once the
-    # whole frame fits the budget, more samples per pixel instead
-    rows = int(max(32, min(args.height, seconds * rate / args.width)))
-    rows -= rows % 8
-    spp = 1
-    if rows >= args.height - 8:
-        rows = args.height - args.height % 8
-        spp = int(max(1, min(args.spp, seconds * rate / (args.width * args.height))))
-    step = args.height / (rows / 8)
-    samples, t = 0, 0.0
-    img = np.zeros((args.height, args.width, 4), np.float32)
-    t0 = time.perf_counter()
-    for b in range(rows // 8):
-        ys = int(b * step)
-        o.render(args.width, args.height, scene.camera, sp, spp=spp, region=(0, ys, args.width, min(ys + 8, args.height)), out=img)
-        samples += args.width * (min(ys + 8, args.height) - ys) * spp
-    t = time.perf_counter() - t0
-    return {"value": samples / t / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
-            "sample": "%d rows (bands of 8 spread over the frame) x %d px x %d spp of the same scene/camera, %.1f s; "
-                      "restated reference megakernel, OpenMP" % (rows, args.width, spp, t)}
+    return CpuArm(args, scene).run(seconds)
 
 
 def run_reference(args):
@@ -173,18 +208,19 @@ def run_reference(args):
     if rank != 0:
         return
     scene = make_scene(args)
-    vals = []
+    arm = CpuArm(args, scene)
+    vals, secs = [], []
     base = None
+    budget = max(2.0, args.cpu_seconds * 4 / max(1, args.steps + args.warmup))  # whole run ~ a minute of CPU work
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(args, scene, max(2.0, args.cpu_seconds / max(1, args.steps)))
+        base = arm.run(budget)
         if i >= args.warmup:
             vals.append(base["value"])
-        if i == 0 and args.warmup > 1:
-            pass
+            secs.append(base["seconds"])
     v = float(np.mean(vals))
     base["value"] = v
     line = {"impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args)}, "cpu_baseline": base,
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
@@ -267,7 +303,13 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
+    # ---- hash frame: the very first frame after set_scene (frame_id = 0, frame_offset = 0) is the image the parity tests hold
+    # against the oracle (tests/test_gpu_parity.py::test_c2_bench_configuration_full_frame); its SHA-256 goes into the line and
+    # must be the same for every N (the sharded frame after the reduce is bit-identical to the 1-GPU frame)
+    import hashlib
+    step(True)
+    fb_sha = hashlib.sha256(host.numpy().tobytes()).hexdigest() if rank == 0 else None
+    for _ in range(max(0, args.warmup - 1)):
         step(True)
     # ---- device-timed region: K steps, inputs resident ----
     barrier()
@@ -315,10 +357,24 @@ def run_b200(args):
     ach = trace_bytes / (cnt["ms_trace"] * 1e-3) / 1e9 if cnt["ms_trace"] > 0 else None
     stage_ms = {k: cnt[k] for k in ("ms_trace", "ms_shade", "ms_shadow", "ms_other")}
     spl = max(1, cnt["samples"])
-    traffic, traffic_src = measured_traffic(args, overlap)
+    hw = measured_counters(args, overlap)
     kernel_name = "k_trace_persistent (closest-hit + any-hit launches, overlapped on two streams)" if overlap else "k_trace_persistent (closest hit)"
+    avg_s = cnt["ms_trace"] * 1e-3 / max(1, cnt["trace_launches"])
+    sm_hz = ((clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or 1965.0) * 1e6
+    issue_slots = avg_s * cnt["num_sms"] * 4 * sm_hz  # warp-instruction issue slots per launch: SMs x 4 schedulers x cycles
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "traffic": hw["dram_bytes"] if hw else None, "traffic_source": hw["source"] if hw else None, "peak_source": peak_src,
+                # what `achieved` is: ALGORITHMIC bytes (ray + hit records + 64 B per node visit + 48 B per triangle test) over
+                # the live launch time.  Scene + BVH fit the 126 MB L2, so most of those bytes never reach HBM: dram_frac is the
+                # measured DRAM rate (ncu dram__bytes per launch over the live launch time) against the same peak, and the limiter
+                # the profile shows is instruction issue: issue_frac = warp instructions per launch / issue slots of the launch,
+                # lane_adjusted_issue_frac = thread instructions / (32 x issue slots).
+                "achieved_is": "algorithmic bytes / live launch time (served mostly from L2, see dram_frac)",
+                "dram_frac": (hw["dram_bytes"] / avg_s / 1e9 / peak) if hw and hw["dram_bytes"] and avg_s > 0 else None,
+                "dram_gbs": (hw["dram_bytes"] / avg_s / 1e9) if hw and hw["dram_bytes"] and avg_s > 0 else None,
+                "issue_frac": (hw["warp_inst"] / issue_slots) if hw and hw["warp_inst"] and issue_slots > 0 else None,
+                "lane_adjusted_issue_frac": (hw["thread_inst"] / (32.0 * issue_slots)) if hw and hw["thread_inst"] and issue_slots > 0 else None,
+                "binding": "instruction issue (L2-resident scene; HBM traffic is the ray / hit records)",
                 "per_launch": {"launches": cnt["trace_launches"], "avg_ms": cnt["ms_trace"] / max(1, cnt["trace_launches"]),
                                "avg_algorithmic_bytes": trace_bytes / max(1, cnt["trace_launches"])},
                 "per_ray": {"closest": {"nodes": cnt["closest_nodes"] / max(1, cnt["closest_rays"]), "tris": cnt["closest_tris"] / max(1, cnt["closest_rays"]),
@@ -336,7 +392,8 @@ def run_b200(args):
                        "scene_setup_s": scene_s},
             "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(T.RenderCameraParams) + C.sizeof(T.RenderParams) + C.sizeof(T.LightSamplingConfig),
                     "d2h_bytes_per_step": n_px * 16, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(cnt["launches"]), "clocks": clk, "roofline": roofline}
+            "gpu_launches": int(cnt["launches"]), "clocks": clk, "roofline": roofline,
+            "framebuffer_sha256": fb_sha, "framebuffer_sha256_of": "first frame after set_scene (frame_id 0, frame_offset 0), RGBA32F as read back on rank 0"}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, scene, args.cpu_seconds)
     emit(line)

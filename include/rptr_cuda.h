@@ -43,6 +43,7 @@ typedef struct rptr_counters {
     double bvh_build_ms;       /* wall time of the last BVH build (host SAH or device LBVH) */
     uint64_t trace_overlap;    /* 1: option "overlap_shadow" is on -- ms_trace / trace_launches then cover closest-hit AND shadow
                                   launches (each shadow launch shares the GPU with the next closest-hit launch) and ms_shadow is 0 */
+    uint64_t num_sms;          /* streaming multiprocessors of the device (persistent grids are sized in multiples of it) */
 } rptr_counters;
 
 /* create_cuda_backend(Display&) / ~RenderBackend  (librender/render_backend.h:118-119, main.cpp:273-285).

@@ -1240,6 +1240,9 @@ extern "C" {
 // accumulate.glsl:68-73 + process_samples.comp:116-129: frame 0 stores x, frame k folds m += (x - m)/float(k+1).
 // If first_sample > 0 the buffer must hold the running mean of the previous frames.
 // stats (optional, 3 x uint64): closest rays, shadow rays, path vertices.
+static int g_last_threads = 1;
+// number of OpenMP threads the last oracle_render() call really ran on (bench.py reports it as cpu_baseline.cores)
+int oracle_last_threads(void) { return g_last_threads; }
 int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rgba, uint64_t *stats) {
     Frame f = make_frame(os, a);
     int nt = a->n_threads;
@@ -1249,10 +1252,19 @@ int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rg
     nt = 1;
 #endif
     uint64_t c0 = 0, c1 = 0, c2 = 0;
+    // work items are tiles of 16 x 4 pixels over the region (not scanlines: a band of 8 rows would keep 8 threads busy at most)
+    const int TW = 16, TH = 4;
+    const int tiles_x = (a->x1 - a->x0 + TW - 1) / TW, tiles_y = (a->y1 - a->y0 + TH - 1) / TH;
+    int used = 1;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(+ : c0, c1, c2)
-    for (int y = a->y0; y < a->y1; ++y) {
+    for (int tile = 0; tile < tiles_x * tiles_y; ++tile) {
+#ifdef _OPENMP
+        if (tile == 0) used = omp_get_num_threads();
+#endif
         Counters cnt;
-        for (int x = a->x0; x < a->x1; ++x) {
+        const int ty0 = a->y0 + (tile / tiles_x) * TH, tx0 = a->x0 + (tile % tiles_x) * TW;
+        for (int y = ty0; y < ty0 + TH && y < a->y1; ++y)
+        for (int x = tx0; x < tx0 + TW && x < a->x1; ++x) {
             float *px = rgba + 4 * ((size_t)y * a->width + x);
             for (int k = 0; k < a->n_samples; ++k) {
                 uint32_t frame_id = a->first_sample + (uint32_t)k;
@@ -1267,6 +1279,7 @@ int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rg
         }
         c0 += cnt.closest_rays; c1 += cnt.shadow_rays; c2 += cnt.vertices;
     }
+    g_last_threads = used;
     if (stats) { stats[0] = c0; stats[1] = c1; stats[2] = c2; }
     return 0;
 }

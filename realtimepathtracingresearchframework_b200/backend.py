@@ -35,7 +35,7 @@ class Counters(C.Structure):
                                           "closest_tris", "shadow_nodes", "shadow_tris", "launches")] + \
                [(n, C.c_double) for n in ("ms_trace", "ms_shadow", "ms_shade", "ms_other")] + \
                [(n, C.c_uint64) for n in ("trace_launches", "node_bytes", "tri_bytes", "bvh_nodes")] + [("bvh_build_ms", C.c_double),
-                                                                                                  ("trace_overlap", C.c_uint64)]
+                                                                                                  ("trace_overlap", C.c_uint64), ("num_sms", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/rptr_cuda.h"
@@ -455,6 +456,7 @@ struct rptr_ctx {
     std::vector<void *> scene_allocs;
     SceneDev scene{};
     BvhDev bvh{};
+    float scene_extent = 0.0f; // largest |coordinate| of the scene (box padding scale, range of admissible ray origins)
     int32_t n_lights = 0;
     std::vector<rptr_base_material> materials_host; // resolved materials (texture handles folded in), for per-frame host decisions
     bool any_normal_map = false;
@@ -495,6 +497,7 @@ struct rptr_ctx {
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> event_pool;
     size_t bytes_now = 0, bytes_max = 0, bytes_total = 0;
+    std::unordered_map<void *, size_t> alloc_sizes; // RenderStats::device_bytes_currently_allocated
 };
 
 static int fail(rptr_ctx *ctx, const char *fmt, ...) {
@@ -520,6 +523,7 @@ template <class T> static cudaError_t dev_alloc(rptr_ctx *ctx, T **p, size_t n, 
     cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
     if (e == cudaSuccess) {
         owner.push_back(*p);
+        ctx->alloc_sizes[*p] = n * sizeof(T);
         ctx->bytes_now += n * sizeof(T);
         ctx->bytes_total += n * sizeof(T);
         if (ctx->bytes_now > ctx->bytes_max) ctx->bytes_max = ctx->bytes_now;
@@ -527,9 +531,15 @@ template <class T> static cudaError_t dev_alloc(rptr_ctx *ctx, T **p, size_t n, 
     return e;
 }
 static void free_all(rptr_ctx *ctx, std::vector<void *> &owner) {
-    for (void *p : owner) cudaFree(p);
+    for (void *p : owner) {
+        auto it = ctx->alloc_sizes.find(p);
+        if (it != ctx->alloc_sizes.end()) {
+            ctx->bytes_now -= it->second;
+            ctx->alloc_sizes.erase(it);
+        }
+        cudaFree(p);
+    }
     owner.clear();
-    (void)ctx;
 }
 
 static TileMap make_tilemap(const rptr_ctx *ctx) {
@@ -552,8 +562,7 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     if (paths < ctx->wave_capacity) paths = ctx->wave_capacity;
     if (depth < ctx->wave_depth) depth = ctx->wave_depth;
     CU(cudaStreamSynchronize(ctx->stream));
-    for (void *p : ctx->wave_allocs) cudaFree(p);
-    ctx->wave_allocs.clear();
+    free_all(ctx, ctx->wave_allocs);
     Wave &w = ctx->wave;
     const size_t n = paths;
     CU(dev_alloc(ctx, &w.ray_o, n, ctx->wave_allocs));
@@ -722,35 +731,33 @@ int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height) {
     return 0;
 }
 
-int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_light_sampling_config *lighting) {
-    if (!ctx) return 1;
-    if (!desc) return fail(ctx, "set_scene: desc is NULL");
-    CU(cudaSetDevice(ctx->device));
-    rptr_light_sampling_config ls;
-    if (lighting) ls = *lighting;
-    else { ls.light_mis_angle = 0.0f; ls.bin_size = 16; ls.min_perceived_receiver_dist = 15.0f; ls.min_radiance = 0.0f; }
-    HostScene hs;
-    try {
-        build_host_scene(*desc, ls, hs, /*with_bvh=*/ctx->bvh_builder == 0);
-    } catch (const std::exception &e) {
-        return fail(ctx, "set_scene: %s", e.what());
-    }
-    CU(cudaStreamSynchronize(ctx->stream));
-    free_all(ctx, ctx->scene_allocs);
-    ctx->has_scene = false;
+// Everything set_scene puts on the device.  It is built completely before the previous scene is released, so a failure
+// (invalid input, out of memory, a BVH the traversal stack cannot hold) leaves the context with the scene it had.
+struct SceneUpload {
+    rptr_ctx *ctx;
+    std::vector<void *> allocs;
+    SceneDev scene{};
+    BvhDev bvh{};
+    double bvh_build_ms = 0.0;
+    float extent = 0.0f;
+    explicit SceneUpload(rptr_ctx *c) : ctx(c) {}
+    ~SceneUpload() { free_all(ctx, allocs); }
+};
+
+static int upload_scene(rptr_ctx *ctx, HostScene &hs, SceneUpload &up) {
     std::vector<uint64_t *> d_qv(hs.qverts.size(), nullptr), d_qn(hs.qnuv.size(), nullptr);
     std::vector<uint8_t *> d_tm(hs.tri_mat.size(), nullptr);
     for (size_t g = 0; g < hs.qverts.size(); ++g) {
-        CU(dev_alloc(ctx, &d_qv[g], hs.qverts[g].size(), ctx->scene_allocs));
+        CU(dev_alloc(ctx, &d_qv[g], hs.qverts[g].size(), up.allocs));
         CU(cudaMemcpy(d_qv[g], hs.qverts[g].data(), hs.qverts[g].size() * 8, cudaMemcpyHostToDevice));
         if (!hs.qnuv[g].empty()) {
-            CU(dev_alloc(ctx, &d_qn[g], hs.qnuv[g].size(), ctx->scene_allocs));
+            CU(dev_alloc(ctx, &d_qn[g], hs.qnuv[g].size(), up.allocs));
             CU(cudaMemcpy(d_qn[g], hs.qnuv[g].data(), hs.qnuv[g].size() * 8, cudaMemcpyHostToDevice));
         }
     }
     for (size_t p = 0; p < hs.tri_mat.size(); ++p)
         if (!hs.tri_mat[p].empty()) {
-            CU(dev_alloc(ctx, &d_tm[p], hs.tri_mat[p].size(), ctx->scene_allocs));
+            CU(dev_alloc(ctx, &d_tm[p], hs.tri_mat[p].size(), up.allocs));
             CU(cudaMemcpy(d_tm[p], hs.tri_mat[p].data(), hs.tri_mat[p].size(), cudaMemcpyHostToDevice));
         }
     std::vector<GeomInst> gi(hs.ginst.size());
@@ -763,51 +770,57 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     GeomInst *d_gi;
     rptr_base_material *d_mat;
     rptr_tri_light_data *d_lights;
-    BvhNode *d_nodes;
-    Tri *d_tris;
-    CU(dev_alloc(ctx, &d_gi, gi.size(), ctx->scene_allocs));
+    CU(dev_alloc(ctx, &d_gi, gi.size(), up.allocs));
     CU(cudaMemcpy(d_gi, gi.data(), gi.size() * sizeof(GeomInst), cudaMemcpyHostToDevice));
-    CU(dev_alloc(ctx, &d_mat, hs.materials.size(), ctx->scene_allocs));
+    CU(dev_alloc(ctx, &d_mat, hs.materials.size(), up.allocs));
     CU(cudaMemcpy(d_mat, hs.materials.data(), hs.materials.size() * sizeof(rptr_base_material), cudaMemcpyHostToDevice));
     float4 *d_ntex;
-    CU(dev_alloc(ctx, &d_ntex, hs.materials.size(), ctx->scene_allocs));
+    CU(dev_alloc(ctx, &d_ntex, hs.materials.size(), up.allocs));
     CU(cudaMemcpy(d_ntex, hs.normal_texels.data(), hs.materials.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    CU(dev_alloc(ctx, &d_lights, hs.lights.size(), ctx->scene_allocs));
+    CU(dev_alloc(ctx, &d_lights, hs.lights.size(), up.allocs));
     if (!hs.lights.empty()) CU(cudaMemcpy(d_lights, hs.lights.data(), hs.lights.size() * sizeof(rptr_tri_light_data), cudaMemcpyHostToDevice));
-    if (ctx->bvh_builder == 1) { // device LBVH (rptr_bvh_build.cu)
-        float extent = 0.0f, cmin[3] = {1e30f, 1e30f, 1e30f}, cmax[3] = {-1e30f, -1e30f, -1e30f};
-        for (const Tri &t : hs.tris) {
-            const float v[3][3] = {{t.v0x, t.v0y, t.v0z}, {t.v0x + t.e1x, t.v0y + t.e1y, t.v0z + t.e1z}, {t.v0x + t.e2x, t.v0y + t.e2y, t.v0z + t.e2z}};
-            extent = fmaxf(extent, fmaxf(fmaxf(fabsf(t.v0x), fabsf(t.v0y)), fabsf(t.v0z)) + fmaxf(fmaxf(fabsf(t.e1x), fabsf(t.e1y)), fabsf(t.e1z)) +
-                                       fmaxf(fmaxf(fabsf(t.e2x), fabsf(t.e2y)), fabsf(t.e2z)));
-            for (int k = 0; k < 3; ++k) {
-                const float c = 0.5f * (fminf(v[0][k], fminf(v[1][k], v[2][k])) + fmaxf(v[0][k], fmaxf(v[1][k], v[2][k])));
-                cmin[k] = fminf(cmin[k], c);
-                cmax[k] = fmaxf(cmax[k], c);
-            }
+    up.scene = SceneDev{d_gi, d_mat, d_lights, d_ntex};
+
+    // largest |coordinate| of the scene: scale of the conservative box padding (rptr_host.cpp build_bvh) and of the range of
+    // ray origins the slab test is guaranteed for (begin_frame / trace_rays check it)
+    float extent = 0.0f, cmin[3] = {1e30f, 1e30f, 1e30f}, cmax[3] = {-1e30f, -1e30f, -1e30f};
+    for (const Tri &t : hs.tris) {
+        const float v[3][3] = {{t.v0x, t.v0y, t.v0z}, {t.v0x + t.e1x, t.v0y + t.e1y, t.v0z + t.e1z}, {t.v0x + t.e2x, t.v0y + t.e2y, t.v0z + t.e2z}};
+        extent = fmaxf(extent, fmaxf(fmaxf(fabsf(t.v0x), fabsf(t.v0y)), fabsf(t.v0z)) + fmaxf(fmaxf(fabsf(t.e1x), fabsf(t.e1y)), fabsf(t.e1z)) +
+                                   fmaxf(fmaxf(fabsf(t.e2x), fabsf(t.e2y)), fabsf(t.e2z)));
+        for (int k = 0; k < 3; ++k) {
+            const float c = 0.5f * (fminf(v[0][k], fminf(v[1][k], v[2][k])) + fmaxf(v[0][k], fmaxf(v[1][k], v[2][k])));
+            cmin[k] = fminf(cmin[k], c);
+            cmax[k] = fmaxf(cmax[k], c);
         }
+    }
+    up.extent = extent;
+    if (ctx->bvh_builder == 1) { // device LBVH (rptr_bvh_build.cu)
         DeviceBvh db;
         std::string err;
         const auto t0 = std::chrono::steady_clock::now();
-        if (!build_bvh_device(hs.tris, extent, cmin, cmax, ctx->stream, ctx->num_sms, db, err)) return fail(ctx, "set_scene: %s", err.c_str());
-        ctx->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        for (void *p : {(void *)db.nodes, (void *)db.tris, (void *)db.top})
-            if (p) ctx->scene_allocs.push_back(p);
-        ctx->scene = SceneDev{d_gi, d_mat, d_lights, d_ntex};
-        ctx->bvh = BvhDev{db.nodes, db.tris, db.n_nodes, db.n_tris, db.top, db.top_k};
-        ctx->n_lights = (int32_t)hs.lights.size();
-        ctx->lights_host = hs.lights;
-        ctx->any_alpha_tested = hs.any_alpha_tested;
-        ctx->any_normal_map = hs.any_normal_map;
-        ctx->materials_host = hs.materials;
-        ctx->has_scene = true;
-        ctx->frame_id = 0;
-        return 0;
+        if (build_bvh_device(hs.tris, extent, cmin, cmax, ctx->stream, ctx->num_sms, db, err)) {
+            up.bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            for (void *p : {(void *)db.nodes, (void *)db.tris, (void *)db.top})
+                if (p) up.allocs.push_back(p);
+            up.bvh = BvhDev{db.nodes, db.tris, db.n_nodes, db.n_tris, db.top, db.top_k};
+            return 0;
+        }
+        // e.g. the collapsed Morton tree is deeper than the traversal stack allows (clustered or coincident centroids): the host
+        // SAH builder bounds the depth (it falls back to balanced median splits), so it takes over instead of failing set_scene
+        ctx->error = "device LBVH: " + err + "; fell back to the host SAH builder";
+        try {
+            build_bvh(hs);
+        } catch (const std::exception &e) {
+            return fail(ctx, "set_scene: device LBVH failed (%s) and so did the host builder (%s)", err.c_str(), e.what());
+        }
     }
-    ctx->bvh_build_ms = hs.bvh_build_ms;
-    CU(dev_alloc(ctx, &d_nodes, hs.nodes.size(), ctx->scene_allocs));
+    BvhNode *d_nodes;
+    Tri *d_tris;
+    up.bvh_build_ms = hs.bvh_build_ms;
+    CU(dev_alloc(ctx, &d_nodes, hs.nodes.size(), up.allocs));
     if (!hs.nodes.empty()) CU(cudaMemcpy(d_nodes, hs.nodes.data(), hs.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
-    CU(dev_alloc(ctx, &d_tris, hs.leaf_tris.size(), ctx->scene_allocs));
+    CU(dev_alloc(ctx, &d_tris, hs.leaf_tris.size(), up.allocs));
     if (!hs.leaf_tris.empty()) CU(cudaMemcpy(d_tris, hs.leaf_tris.data(), hs.leaf_tris.size() * sizeof(Tri), cudaMemcpyHostToDevice));
     // word planes of the top of the (breadth-first ordered) tree for the trace kernel's shared-memory stage
     const int32_t top_k = (int32_t)std::min<size_t>(hs.nodes.size(), RPTR_TOP_NODES_MAX);
@@ -815,10 +828,36 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     for (int32_t i = 0; i < top_k; ++i)
         for (int wd = 0; wd < 4; ++wd) memcpy(&top[(size_t)wd * RPTR_TOP_NODES_MAX + i], reinterpret_cast<const unsigned char *>(&hs.nodes[i]) + (wd << 4), 16);
     float4 *d_top;
-    CU(dev_alloc(ctx, &d_top, top.size(), ctx->scene_allocs));
+    CU(dev_alloc(ctx, &d_top, top.size(), up.allocs));
     CU(cudaMemcpy(d_top, top.data(), top.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    ctx->scene = SceneDev{d_gi, d_mat, d_lights, d_ntex};
-    ctx->bvh = BvhDev{d_nodes, d_tris, (int32_t)hs.nodes.size(), (int32_t)hs.leaf_tris.size(), d_top, top_k};
+    up.bvh = BvhDev{d_nodes, d_tris, (int32_t)hs.nodes.size(), (int32_t)hs.leaf_tris.size(), d_top, top_k};
+    return 0;
+}
+
+int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_light_sampling_config *lighting) {
+    if (!ctx) return 1;
+    if (!desc) return fail(ctx, "set_scene: desc is NULL");
+    if (ctx->in_frame) return fail(ctx, "set_scene inside begin_frame/end_frame");
+    CU(cudaSetDevice(ctx->device));
+    rptr_light_sampling_config ls;
+    if (lighting) ls = *lighting;
+    else { ls.light_mis_angle = 0.0f; ls.bin_size = 16; ls.min_perceived_receiver_dist = 15.0f; ls.min_radiance = 0.0f; }
+    HostScene hs;
+    try {
+        build_host_scene(*desc, ls, hs, /*with_bvh=*/ctx->bvh_builder == 0);
+    } catch (const std::exception &e) {
+        return fail(ctx, "set_scene: %s", e.what());
+    }
+    ctx->error.clear();
+    SceneUpload up(ctx);
+    if (upload_scene(ctx, hs, up)) return 1; // the previous scene stays in place
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_all(ctx, ctx->scene_allocs);
+    ctx->scene_allocs.swap(up.allocs); // `up` now owns nothing
+    ctx->scene = up.scene;
+    ctx->bvh = up.bvh;
+    ctx->bvh_build_ms = up.bvh_build_ms;
+    ctx->scene_extent = up.extent;
     ctx->n_lights = (int32_t)hs.lights.size();
     ctx->lights_host = hs.lights;
     ctx->any_alpha_tested = hs.any_alpha_tested;
@@ -854,7 +893,8 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
         if (value < 0 || value > 3) return fail(ctx, "rng_variant must be 0 (UNIFORM), 1 (BN), 2 (SOBOL) or 3 (Z_SBL)");
         ctx->rng_variant = (int)value;
     } else if (n == "wave_paths") {
-        if (value < 1024) return fail(ctx, "wave_paths must be >= 1024");
+        // path slots are 32-bit everywhere (k_raygen's slot loop, AovTarget::slot_lo, slots packed into float bits)
+        if (value < 1024 || value > 0x7fffffffll) return fail(ctx, "wave_paths must be in [1024, 2^31 - 1]");
         ctx->wave_paths = value;
     } else if (n == "stage_timing") ctx->stage_timing = value != 0;
     else if (n == "aov_buffers") ctx->aov_buffers = value != 0;
@@ -900,6 +940,15 @@ int rptr_cuda_begin_frame(rptr_ctx *ctx, const rptr_camera_params *camera, const
     if (params->batch_spp < 1) return fail(ctx, "batch_spp must be >= 1");
     if (params->max_path_depth < 1 || params->max_path_depth > 64) return fail(ctx, "max_path_depth out of range");
     if (ctx->tile_rank < 0 || ctx->tile_rank >= ctx->tile_world) return fail(ctx, "tile_rank %d outside tile_world %d", ctx->tile_rank, ctx->tile_world);
+    {   // The box tests of the traversal are conservative for ray origins within 8 scene extents of the world origin (padding of
+        // 2^-16 |coordinate| + 2^-17 extent against the cancellation in org / d - o / d, rptr_host.cpp build_bvh); farther out
+        // true hits could be culled silently, so such a camera is refused instead.
+        const float reach = 8.0f * fmaxf(ctx->scene_extent, 1e-3f);
+        for (int k = 0; k < 3; ++k)
+            if (!(fabsf(camera->pos[k]) <= reach))
+                return fail(ctx, "begin_frame: camera position (%g, %g, %g) is outside the supported range of %g (8 x the scene extent %g)",
+                            camera->pos[0], camera->pos[1], camera->pos[2], reach, ctx->scene_extent);
+    }
     ctx->camera = *camera;
     ctx->params = *params;
     if (lighting) ctx->lighting = *lighting;
@@ -1165,6 +1214,7 @@ int rptr_cuda_get_counters(rptr_ctx *ctx, rptr_counters *out) {
     out->tri_bytes = sizeof(Tri);
     out->bvh_nodes = (uint64_t)ctx->bvh.n_nodes;
     out->bvh_build_ms = ctx->bvh_build_ms;
+    out->num_sms = (uint64_t)ctx->num_sms;
     return 0;
 }
 
@@ -1254,6 +1304,12 @@ int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, in
     if (!ctx->has_scene) return fail(ctx, "trace_rays before set_scene");
     if (n < 0 || (n > 0 && (!queries || !results))) return fail(ctx, "trace_rays: invalid arguments");
     if (n == 0) return 0;
+    {
+        const float reach = 8.0f * fmaxf(ctx->scene_extent, 1e-3f); // see begin_frame
+        for (int32_t i = 0; i < n; ++i)
+            if (queries[i].mode_or_data >= 0 && !(fabsf(queries[i].origin[0]) <= reach && fabsf(queries[i].origin[1]) <= reach && fabsf(queries[i].origin[2]) <= reach))
+                return fail(ctx, "trace_rays: origin of query %d is outside the supported range of %g (8 x the scene extent)", i, reach);
+    }
     CU(cudaSetDevice(ctx->device));
     struct Scratch { // freed on every exit path
         void *p[3] = {nullptr, nullptr, nullptr};

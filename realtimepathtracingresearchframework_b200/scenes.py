@@ -368,3 +368,78 @@ def instanced_scene(n_base_tris=100_000, n_instances=100, seed=0xC4C4C4, edge=No
     s.camera = look_at_camera(centre + np.array([0.0, 0.2 * radius, 2.4 * radius], np.float32), centre, fovy=50.0)
     s.name = "instanced%dx%d" % (n_base_tris, n_instances)
     return s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Smooth-shaded, uv-mapped geometry (rendering/rt/hit.glsl:58-128): vertex normals, uvs, uv-derivative tangents
+# ---------------------------------------------------------------------------------------------------------------------
+def pack_qnormal_uv(normals, uvs):
+    """(..., 3) normals + (..., 2) uvs -> uint64 words: oct-encoded normal in the low half, quantised uv in the high half
+    (librender/quantize.h:21-42; librender/dequantize.glsl:23-48)."""
+    return quantize_normal(normals).astype(np.uint64) | (quantize_uv(uvs).astype(np.uint64) << np.uint64(32))
+
+
+def smooth_shaded_scene(n_u=24, n_v=12, n_soup=1500, seed=11):
+    """Tessellated unit spheres with smooth vertex normals and a spherical uv map (geometry 0: normals + uvs), a soup of
+    random triangles with arbitrary vertex normals -- many of them on the far side of the geometric normal, so the flip of
+    hit.glsl:71-72 and the incident-direction fix of pt_megakernel.glsl:657-668 are exercised -- and per-triangle constant
+    uvs (zero uv derivatives: the tangent falls back to cross(e2, gn), hit.glsl:117-121) (geometry 1: normals + uvs), and a
+    soup with uvs only (geometry 2) and normals only (geometry 3).  Instanced three times: identity, a rotation with
+    non-uniform scale (normals go through the inverse transpose) and a mirrored instance (negative determinant).
+    Half of the materials carry a one-texel normal map, whose tangent frame comes from the uv derivatives."""
+    s = Scene()
+    scale, base = 2.0 ** -19, -2.0
+    offset = (base + 2.0 ** -20,) * 3
+
+    def snap(p):
+        g = np.clip(np.floor((np.asarray(p, np.float64) - base) / scale), 0, 0x1FFFFF).astype(np.int64)
+        return g, (g.astype(np.float32) * np.float32(scale) + np.float32(offset[0]))
+
+    # lat-long sphere, unrolled vertices
+    iu, iv = np.meshgrid(np.arange(n_u), np.arange(n_v), indexing="ij")
+    quads = []
+    for du, dv in ((0, 0), (1, 0), (1, 1), (0, 0), (1, 1), (0, 1)):
+        quads.append(np.stack([(iu + du).ravel(), (iv + dv).ravel()], -1))
+    uvi = np.stack(quads, 1).reshape(-1, 2).astype(np.float64)  # (n_tris * 3, 2) lattice coordinates
+    phi, theta = uvi[:, 0] / n_u * 2 * np.pi, uvi[:, 1] / n_v * np.pi
+    pos = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta), np.sin(theta) * np.sin(phi)], -1)
+    g0, p0 = snap(pos)
+    nrm0 = p0 / np.maximum(np.linalg.norm(p0, axis=1, keepdims=True), 1e-9)
+    uv0 = np.stack([uvi[:, 0] / n_u * 3.0, uvi[:, 1] / n_v], -1)  # u repeats three times around the sphere
+    geo0 = Geometry(pack_qverts(g0), (scale,) * 3, offset, qnormal_uv=pack_qnormal_uv(nrm0, uv0), has_normals=True, has_uvs=True)
+
+    u = splitmix64_uniform(seed, n_soup * 3 * 14).reshape(n_soup, 3, 14)
+    c = (u[:, :1, 0:3] * 2.0 - 1.0) * 1.2
+    tri = c + (u[:, :, 3:6] * 2.0 - 1.0) * 0.25
+    g1, p1 = snap(tri.reshape(-1, 3))
+    rn = u[:, :, 6:9].reshape(-1, 3) * 2.0 - 1.0
+    rn = rn / np.maximum(np.linalg.norm(rn, axis=1, keepdims=True), 1e-9)
+    const_uv = np.repeat(u[:, :1, 9:11], 3, 1).reshape(-1, 2)         # one uv per triangle: zero derivatives
+    rand_uv = (u[:, :, 11:13].reshape(-1, 2) * 2.0)                   # arbitrary uvs
+    third = n_soup // 3
+    sl = [slice(0, 3 * third), slice(3 * third, 6 * third), slice(6 * third, 3 * n_soup)]
+    geo1 = Geometry(pack_qverts(g1[sl[0]]), (scale,) * 3, offset, qnormal_uv=pack_qnormal_uv(rn[sl[0]], const_uv[sl[0]]), has_normals=True, has_uvs=True)
+    geo2 = Geometry(pack_qverts(g1[sl[1]]), (scale,) * 3, offset, qnormal_uv=pack_qnormal_uv(rn[sl[1]], rand_uv[sl[1]]), has_normals=False, has_uvs=True)
+    geo3 = Geometry(pack_qverts(g1[sl[2]]), (scale,) * 3, offset, qnormal_uv=pack_qnormal_uv(rn[sl[2]], rand_uv[sl[2]]), has_normals=True, has_uvs=False)
+    mesh = s.add_mesh([geo0, geo1, geo2, geo3])
+    na = T.BASE_MATERIAL_NOALPHA
+    t_n0 = s.add_texture((170, 96, 255), T.COLOR_SPACE_LINEAR)
+    t_n1 = s.add_texture((90, 150, 255), T.COLOR_SPACE_LINEAR)
+    s.materials = [T.BaseMaterial(base_color=_PALETTE[1], roughness=0.35, ior=1.5, flags=na, normal_map=t_n0),
+                   T.BaseMaterial(base_color=_PALETTE[2], roughness=0.2, metallic=1.0, ior=1.5, flags=na),
+                   T.BaseMaterial(base_color=_PALETTE[3], roughness=0.6, ior=1.5, flags=na, normal_map=t_n1),
+                   T.BaseMaterial(base_color=_PALETTE[4], roughness=1.0, ior=1.0, flags=na)]
+    pm = s.add_pmesh(mesh, [0, 1, 2, 3])
+    s.add_instance(pm)
+    rot = np.array([[0.36, 0.48, -0.8], [-0.8, 0.6, 0.0], [0.48, 0.64, 0.6]], np.float32)  # orthonormal
+    t1 = np.zeros((3, 4), np.float32)
+    t1[:, :3] = rot * np.array([1.6, 0.7, 1.1], np.float32)  # columns scaled: non-uniform scale then rotation
+    t1[:, 3] = (3.2, 0.4, -0.5)
+    s.add_instance(pm, t1)
+    t2 = np.zeros((3, 4), np.float32)
+    t2[:, :3] = np.diag([-1.2, 1.0, 0.9]).astype(np.float32)  # mirrored
+    t2[:, 3] = (-3.1, -0.3, 0.4)
+    s.add_instance(pm, t2)
+    s.camera = look_at_camera((0.3, 1.5, 7.5), (0.0, 0.0, 0.0), fovy=50.0)
+    s.name = "smooth_shaded"
+    return s

@@ -50,6 +50,9 @@ CASES = {
     "random20k": (lambda: scenes.random_triangles(20000), dict()),
     "random20k_slanted_sun": (lambda: scenes.random_triangles(20000), dict(sun_dir=(0.35, 0.8, 0.45))),
     "emissive_instanced": (emissive_soup, dict(sun_dir=(0.35, 0.8, 0.45))),
+    # vertex normals + uvs (rendering/rt/hit.glsl:58-128): smooth shading, uv-derivative tangents under one-texel normal
+    # maps, normals on the far side of the geometric normal, instances with non-uniform scale and a mirrored instance
+    "smooth_shaded": (scenes.smooth_shaded_scene, dict(sun_dir=(0.35, 0.8, 0.45))),
 }
 
 
@@ -188,3 +191,35 @@ def test_host_bvh_does_not_depend_on_the_builder_thread_count(hostsim, monkeypat
         seen[threads] = (lib.hostsim_bvh_hash(hs), lib.hostsim_num_nodes(hs))
         lib.hostsim_scene_destroy(hs)
     assert seen["1"] == seen["3"] == seen["8"] and seen["1"][1] > 30000
+
+
+def test_vertex_normals_and_uvs_reach_the_shading(H, oracle):
+    """The smooth-shaded scene really exercises hit.glsl:58-128: dropping the vertex normals, the uvs or the normal maps each
+    changes the image, and the product code follows the oracle in every variant (has_normals / has_uvs combinations)."""
+    sp = load_sky_fit(T.SceneConfig(sun_dir=(0.35, 0.8, 0.45)))
+    W, Hh = 128, 72
+    ls = T.LightSamplingConfig()
+    images = {}
+    for variant in ("full", "no_normals", "no_uvs", "no_normal_maps"):
+        s = scenes.smooth_shaded_scene()
+        for g in s.geometries:
+            if variant == "no_normals":
+                g.has_normals = False
+            if variant == "no_uvs":
+                g.has_uvs = False
+        if variant == "no_normal_maps":
+            for m in s.materials:
+                m.normal_map = -1
+        d = s.desc()
+        hs = H.hostsim_scene_create(C.byref(d), C.byref(ls))
+        assert hs
+        o = oracle.OracleScene(s)
+        ref = o.render_sample(W, Hh, s.camera, sp, 1)
+        a = o._args(W, Hh, s.camera, sp)
+        img = np.zeros((Hh, W, 4), np.float32)
+        H.hostsim_render_sample(hs, C.byref(a), 1, oracle._fp(img))
+        H.hostsim_scene_destroy(hs)
+        assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), variant
+        images[variant] = ref
+    for variant in ("no_normals", "no_uvs", "no_normal_maps"):
+        assert (images[variant] != images["full"]).any(-1).mean() > 0.02, variant
