@@ -135,6 +135,41 @@ int rptr_cuda_stream_handle(rptr_ctx *ctx, void **stream);
  * passed it.  hit_t (optional) receives the hit distance or -1.  Host buffers. */
 int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, int32_t n, float *results, float *hit_t);
 
+/* RenderBackend::enable_ray_queries(max_queries, max_queries_per_pixel) (librender/render_backend.h:101;
+ * vulkan/render_vulkan.cpp:430-455; app.cpp:77-79 calls it with (DEFAULT_RAY_QUERY_BUDGET, 2)): sizes the device-side
+ * ray_query_buffer / ray_result_buffer for max(width * height * max_queries_per_pixel, max_queries) queries; initialize()
+ * re-sizes them for the new frame (:366-369).  The result buffer starts zeroed. */
+int rptr_cuda_enable_ray_queries(rptr_ctx *ctx, int32_t max_queries, int32_t max_queries_per_pixel);
+/* The reference keeps queries and results in device buffers that the producer of the queries fills (its data-capture module,
+ * which is not part of the tree): these are the device addresses (RenderRayQuery[capacity], vec4[capacity]) for a CUDA-side
+ * producer, and the host-side copies for everybody else.  Valid until enable_ray_queries / initialize / destroy. */
+int rptr_cuda_ray_query_buffers(rptr_ctx *ctx, void **queries, void **results, size_t *capacity);
+int rptr_cuda_write_ray_queries(rptr_ctx *ctx, const rptr_render_ray_query *queries, int32_t first, int32_t n);
+int rptr_cuda_read_ray_results(rptr_ctx *ctx, float *results /* 4 per query */, int32_t first, int32_t n);
+/* RenderBackend::render_ray_queries(num_queries, params, variant_idx, cmd_stream) (librender/render_backend.h:102;
+ * vulkan/render_vulkan.cpp:1867-1876, 2961-3060; vulkan/pt_megakernel.glsl:276-283, 297-301, 327-334): the path tracer on the
+ * first num_queries rays of the query buffer instead of camera rays -- origin, direction and t_max from the query, t_min = 0 --
+ * with the view (frame_dims, frame_id, frame_offset) and RenderParams of the last begin_frame; `params` is accepted and
+ * ignored exactly like the reference ignores it.  Query q is invocation gl_GlobalInvocationIndex = q of a 2-D dispatch of
+ * ceil(sqrt(n)) columns in 32 x 16 workgroups and is seeded like the (swizzled) pixel of that invocation
+ * (vulkan/setup_pixel_assignment.glsl:17-22).  batch_spp layers with sample indices 0 .. batch_spp - 1
+ * (accumulation_frame_offset = 0) are folded into ray_results[q] by accumulate_query (vulkan/accumulate.glsl:32-42) in sample
+ * order: layer 0 stores its sample, layer k > 0 ADDS the updated mean to the stored value (kept as the reference writes it;
+ * with the usual batch_spp = 1 the result is simply the sample).  Does not touch the frame counters.  Asynchronous.
+ * Not done: the reference's megakernel also writes the AOV images of the virtual pixels that fall inside the frame. */
+int rptr_cuda_render_ray_queries(rptr_ctx *ctx, int32_t num_queries, const rptr_render_params *params, int32_t variant);
+
+/* RenderBackend::normalize_options / configure_for (librender/render_backend.h:84-85; vulkan/render_vulkan.cpp:1878-1917;
+ * librender/render_backend.cpp:59-96).  normalize: options that do not apply to this backend's only integrator are reset to
+ * their defaults (for the reference's megakernel program every RenderBackendOptions member applies, so this is the identity
+ * but for range clamping of the enums).  configure_for: 0 = the backend now renders with these options (rng_variant is
+ * switched; its tables must have been handed over); non-zero = unsupported, with the reason in last_error, and
+ * *available (optional) receives the closest supported set -- the reference's "fallback exists" recovery path (app.cpp:400-431).
+ * Unsupported here: light_sampling_variant NONE (the reference's megakernel does not build with it either: wpdf_direct_light
+ * is undefined without lights_linear.glsl, rendering/mc/shade_base_material.glsl:36), render_upscale_factor != 1, enable_taa. */
+int rptr_cuda_normalize_options(rptr_ctx *ctx, rptr_backend_options *options, int32_t variant);
+int rptr_cuda_configure_for(rptr_ctx *ctx, const rptr_backend_options *options, int32_t variant, rptr_backend_options *available);
+
 /* util/write_image.cpp:34-66 (WriteImage::write_pfm): "<prefix>.pfm", RGB, bottom row first, little-endian.
  * Pure host helper so validation mode (libapp/app_state.cpp:362-388) can be replayed without the app. */
 int rptr_write_pfm(const char *prefix, uint32_t width, uint32_t height, uint32_t channels, const float *pixels);

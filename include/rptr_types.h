@@ -11,6 +11,7 @@
  *   rptr_tri_light_data       <- rendering/lights/tri.h.glsl:13-26            (48 B)
  *   rptr_camera_params        <- librender/render_backend.h:26-31             (40 B)
  *   rptr_render_stats         <- librender/render_backend.h:15-24
+ *   rptr_backend_options      <- librender/render_params.glsl.h:73-119        (32 B)
  *   rptr_scene_params         <- vulkan/gpu_params.glsl:113-131 (SceneParams, the fitted sky/sun block)
  *   rptr_geometry/mesh/pmesh/instance <- librender/mesh.h:10-41,78-121, librender/scene.h:48-72
  */
@@ -156,6 +157,23 @@ typedef struct rptr_render_stats {
     uint64_t max_device_bytes_allocated;
     uint64_t device_bytes_currently_allocated;
 } rptr_render_stats;
+
+/* RenderBackendOptions (librender/render_params.glsl.h:73-119), member for member; bool members are one byte like the C++ type */
+typedef struct rptr_backend_options {
+    int32_t rng_variant;                 /* RPTR_RNG_VARIANT_* */
+    int32_t light_sampling_variant;      /* RPTR_LIGHT_SAMPLING_VARIANT_* */
+    int32_t light_sampling_bucket_count; /* 16 */
+    uint8_t unroll_bounces;
+    uint8_t _pad0[3];
+    int32_t render_upscale_factor;       /* 1 */
+    uint8_t enable_rayqueries;
+    uint8_t force_bvh_rebuild;
+    uint8_t _pad1[2];
+    int32_t rebuild_triangle_budget;     /* 500000 */
+    uint8_t enable_taa;
+    uint8_t enable_raytraced_dof;        /* true */
+    uint8_t _pad2[2];
+} rptr_backend_options;
 
 /* The fitted sky/sun block the kernels read; produced on the host by update_sky_light
  * (vulkan/render_sky.cpp:25-72) from an rptr_scene_config. */

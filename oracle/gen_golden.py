@@ -540,10 +540,53 @@ def gen_pointsets(n=384, seed=4321):
     print("wrote", path, {k: v.shape for k, v in out.items()})
 
 
+def gen_queries(seed=77):
+    """render_ray_queries: the reference's dispatch size, invocation index / swizzled invocation id of every query of a few
+    dispatches, and accumulate_query chains -- all executed from the reference's files (oracle/ref_shim/ref_queries.cpp)."""
+    R = po.ref()
+    R.ref_query_invocation.argtypes = [C.c_uint32] * 5 + [C.POINTER(C.c_uint32)]
+    R.ref_accumulate_query.argtypes = [po.f32p, po.f32p, C.c_uint32]
+    R.ref_query_dispatch.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    out = {}
+    counts = np.array([1, 2, 31, 32, 33, 511, 512, 513, 1000, 1024, 1025, 4097, 65536, 250000, 262144, 1000003], np.int32)
+    disp = np.zeros((len(counts), 5), np.int32)
+    for i, n in enumerate(counts):
+        R.ref_query_dispatch(int(n), 3, disp[i].ctypes.data_as(C.POINTER(C.c_int32)))
+    out["q_counts"], out["q_dispatch"] = counts, disp
+    # every invocation of the dispatches of 513 and 4097 queries: (swizzled x, swizzled y, invocation index)
+    for n, tag in ((513, "513"), (4097, "4097")):
+        d = disp[list(counts).index(n)]
+        nwx, nwy = int(d[2]), int(d[3])
+        rows = np.zeros((nwx * nwy * 512, 3), np.uint32)
+        k = 0
+        for wy in range(nwy):
+            for wx in range(nwx):
+                for l in range(512):
+                    R.ref_query_invocation(wx, wy, nwx, nwy, l, rows[k].ctypes.data_as(C.POINTER(C.c_uint32)))
+                    k += 1
+        out["q_invocations_" + tag] = rows
+    rng = np.random.default_rng(seed)
+    xs = rng.uniform(0.0, 4.0, (64, 6, 4)).astype(np.float32)  # 64 chains of 6 layers
+    res = np.zeros((64, 6, 4), np.float32)
+    for c in range(64):
+        r = rng.uniform(-1, 1, 4).astype(np.float32)  # stale content of the result buffer: layer 0 must overwrite it
+        for k in range(6):
+            R.ref_accumulate_query(r.ctypes.data_as(po.f32p), xs[c, k].ctypes.data_as(po.f32p), k)
+            res[c, k] = r
+    out["q_accum_in"], out["q_accum_out"] = xs, res
+    path = os.path.join(ROOT, "tests", "golden", "ref_queries.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    if "--queries-only" in sys.argv:
+        gen_queries()
+        sys.exit(0)
     if po.ref() is None:
         sys.exit("oracle/_ref/libref.so missing: run `make -C oracle` in a container that has /root/reference")
     if "--pointsets-only" not in sys.argv:
         gen_sky()
         gen_vectors()
     gen_pointsets()
+    gen_queries()

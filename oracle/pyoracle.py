@@ -59,6 +59,7 @@ def lib():
         L.oracle_render_aov.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_uint32, f32p, f32p]
         L.oracle_render_aov3.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_uint32, f32p, f32p, f32p]
         L.oracle_view_projection.argtypes = [C.POINTER(T.RenderCameraParams), C.c_int32, C.c_int32, f32p]
+        L.oracle_render_ray_queries.argtypes = [C.c_void_p, C.POINTER(OracleRenderArgs), C.c_void_p, C.c_int32, f32p]
         for n in ("oracle_trace_closest", "oracle_trace_closest_bruteforce"):
             getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_int32, f32p, f32p]
         L.oracle_pointset_replay.argtypes = [C.c_int, C.POINTER(C.c_void_p)] + [C.c_uint32] * 6 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -239,6 +240,15 @@ class OracleScene:
         mj = np.zeros((height, width, 4), np.float32)
         lib().oracle_render_aov3(self.h, C.byref(a), sample_index, _fp(ar), _fp(nd), _fp(mj))
         return ar, nd, mj
+
+    def render_ray_queries(self, width, height, camera, scene_params, queries, view_frame_id=0, **kw):
+        """RenderBackend::render_ray_queries: (n, 8) RenderRayQuery rows -> (n, 4) results; kw as for render (batch_spp, params,
+        frame_offset, rng_variant, ...).  view_frame_id = view_params.frame_id of the last begin_frame."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, 8)
+        a = self._args(width, height, camera, scene_params, first_sample=view_frame_id, **kw)
+        res = np.zeros((q.shape[0], 4), np.float32)
+        lib().oracle_render_ray_queries(self.h, C.byref(a), q.ctypes.data, q.shape[0], _fp(res))
+        return res
 
     def trace_closest(self, queries, bruteforce=False):
         """queries: structured (n, 8) float32 view of RenderRayQuery -> (results (n,4) float32 bits, t (n,))."""

@@ -1119,7 +1119,8 @@ static void fold_sample(float *history, const float *x, uint32_t sample_base_ind
     }
 }
 
-static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32_t view_frame_id, Counters &cnt, AovOut *aov = nullptr) {
+static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32_t view_frame_id, Counters &cnt, AovOut *aov = nullptr,
+                   const rptr_render_ray_query *query = nullptr) {
     const oracle_render_args &a = *f.a;
     const Scene &s = *f.s;
     const rptr_scene_params &sp = f.sp;
@@ -1132,6 +1133,11 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
     V3 ray_origin, ray_dir;
     camera_ray(f, px, py, rng, view_frame_id, ray_origin, ray_dir);
     float t_min = 0.0f, t_max = 2.e32f;
+    if (query) { // pt_megakernel.glsl:327-334: the sampler is seeded and the pixel-filter draws are consumed as for a pixel
+        ray_origin = v3(query->origin[0], query->origin[1], query->origin[2]);
+        ray_dir = v3(query->dir[0], query->dir[1], query->dir[2]);
+        t_max = query->t_max;
+    }
     float total_t = 0.0f;
     V3 illum = v3(0.0f), throughput = v3(1.0f);
     int bounce = 0;
@@ -1281,6 +1287,55 @@ int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rg
     }
     g_last_threads = used;
     if (stats) { stats[0] = c0; stats[1] = c1; stats[2] = c2; }
+    return 0;
+}
+
+// render_ray_queries (vulkan/render_vulkan.cpp:1867-1876 -> record_frame :2961-3060): the megakernel dispatched over a "virtual
+// screen square" of ceil(sqrt(n)) x ceil(n / that) invocations in 32 x 16 workgroups, batch_spp layers with sample indices
+// 0 .. batch_spp - 1 (accumulation_frame_offset = 0).  Invocation index (setup_pixel_assignment.glsl:21-22) = query id;
+// gl_GlobalInvocationID.xy is swizzled inside the workgroup (:17-19) and is what seeds the samplers together with the REAL
+// frame width.  Results are folded by accumulate_query (vulkan/accumulate.glsl:32-42), layer after layer.
+// a->first_sample = view_params.frame_id of the last begin_frame, a->batch_spp = render_params.batch_spp.
+// out = invocations per row / rows of the virtual square, workgroups per row / column (record_frame + dispatch_rays)
+void oracle_query_dispatch(int32_t n, int32_t *out) {
+    out[0] = (int)std::ceil(std::sqrt((float)n));
+    out[1] = (n + out[0] - 1) / out[0];
+    out[2] = (out[0] + 31) / 32;
+    out[3] = (out[1] + 15) / 16;
+}
+// the pixel that seeds the samplers of query q (swizzled gl_GlobalInvocationID.xy of invocation index q)
+void oracle_query_pixel(uint32_t q, int32_t n, uint32_t *out) {
+    int32_t d[4];
+    oracle_query_dispatch(n, d);
+    const uint32_t groups_x = (uint32_t)d[2];
+    const uint32_t group = q / 512u, local = q % 512u; // gl_WorkGroupSize = 32 x 16
+    const uint32_t ix = (group % groups_x) * 32u + local % 32u, iy = (group / groups_x) * 16u + local / 32u;
+    out[0] = (ix & ~0x18u) + ((iy & 0x3u) << 3);
+    out[1] = (iy & ~0x3u) + ((ix & 0x18u) >> 3);
+}
+// accumulate_query (vulkan/accumulate.glsl:32-42) for one layer
+void oracle_accumulate_query(float *r, const float *x, uint32_t sample_index) {
+    for (int j = 0; j < 4; ++j) {
+        float accum = sample_index > 0 ? r[j] : 0.0f;
+        accum += (x[j] - accum) / (float)(sample_index + 1u);
+        if (sample_index == 0) r[j] = accum;
+        else r[j] += accum;
+    }
+}
+int oracle_render_ray_queries(const oracle_scene *os, const oracle_render_args *a, const rptr_render_ray_query *queries, int32_t n, float *results) {
+    Frame f = make_frame(os, a);
+    const int batch = a->batch_spp > 1 ? a->batch_spp : 1;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int q = 0; q < n; ++q) {
+        Counters cnt;
+        uint32_t pix[2];
+        oracle_query_pixel((uint32_t)q, n, pix);
+        for (int k = 0; k < batch; ++k) {
+            const V4 c = main_spp(f, (int)pix[0], (int)pix[1], (uint32_t)k, a->first_sample, cnt, nullptr, &queries[q]);
+            const float x[4] = {c.x, c.y, c.z, c.w};
+            oracle_accumulate_query(results + 4 * (size_t)q, x, (uint32_t)k);
+        }
+    }
     return 0;
 }
 

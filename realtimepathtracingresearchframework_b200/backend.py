@@ -26,6 +26,8 @@ ABI_SYMBOLS = [
     "rptr_cuda_get_counters", "rptr_cuda_reset_counters", "rptr_cuda_frame_state", "rptr_cuda_framebuffer_size",
     "rptr_cuda_readback_f32", "rptr_cuda_readback_u8", "rptr_cuda_framebuffer_device_ptr", "rptr_cuda_stream_handle",
     "rptr_cuda_trace_rays", "rptr_cuda_set_pointset_table", "rptr_cuda_readback_aov",
+    "rptr_cuda_enable_ray_queries", "rptr_cuda_ray_query_buffers", "rptr_cuda_write_ray_queries", "rptr_cuda_read_ray_results",
+    "rptr_cuda_render_ray_queries", "rptr_cuda_normalize_options", "rptr_cuda_configure_for",
     "rptr_write_pfm",
 ]
 
@@ -91,6 +93,13 @@ def load_library(path=None):
     L.rptr_cuda_framebuffer_device_ptr.argtypes = [vp, C.POINTER(vp)]
     L.rptr_cuda_stream_handle.argtypes = [vp, C.POINTER(vp)]
     L.rptr_cuda_trace_rays.argtypes = [vp, vp, i32, vp, vp]
+    L.rptr_cuda_enable_ray_queries.argtypes = [vp, i32, i32]
+    L.rptr_cuda_ray_query_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.rptr_cuda_write_ray_queries.argtypes = [vp, vp, i32, i32]
+    L.rptr_cuda_read_ray_results.argtypes = [vp, vp, i32, i32]
+    L.rptr_cuda_render_ray_queries.argtypes = [vp, i32, C.POINTER(T.RenderParams), i32]
+    L.rptr_cuda_normalize_options.argtypes = [vp, C.POINTER(T.RenderBackendOptions), i32]
+    L.rptr_cuda_configure_for.argtypes = [vp, C.POINTER(T.RenderBackendOptions), i32, C.POINTER(T.RenderBackendOptions)]
     L.rptr_write_pfm.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     if path is None:
         _lib = L
@@ -162,7 +171,7 @@ class RenderCuda:
         if self._L.rptr_cuda_create(int(device), C.byref(self._h)) != 0:
             raise RptrError(self._L.rptr_cuda_last_error(None).decode())
         # public members mutated by callers, as in the reference (librender/render_backend.h:69-76)
-        self.options = {"rng_variant": T.__dict__.get("RNG_VARIANT_UNIFORM", 0), "light_sampling_variant": 1}
+        self.options = T.RenderBackendOptions()
         self.params = T.RenderParams()
         self.lighting_params = T.LightSamplingConfig()
         self.camera = T.RenderCameraParams()
@@ -218,7 +227,7 @@ class RenderCuda:
             for i in {1: (2, 3), 2: (0,), 3: (0, 1)}[variant]:
                 self.set_pointset_table(i, tabs[i])
         self.set_option("rng_variant", variant)
-        self.options["rng_variant"] = variant
+        self.options.rng_variant = variant
 
     def begin_frame(self, cmd_stream, config):
         self.camera = config.camera
@@ -287,6 +296,46 @@ class RenderCuda:
         p = C.c_void_p()
         self._check(self._L.rptr_cuda_stream_handle(self._h, C.byref(p)))
         return p.value or 0
+
+    # -- options (librender/render_backend.h:84-85) ---------------------------------------------------------------------
+    def normalize_options(self, rbo, variant_idx=0):
+        self._check(self._L.rptr_cuda_normalize_options(self._h, C.byref(rbo), variant_idx))
+
+    def configure_for(self, rbo, variant_idx=0, available_recovery_options=None):
+        """True: the backend renders with `rbo` from now on.  False: unsupported (reason in last_error(); the closest supported
+        set is written to available_recovery_options when given) -- the caller falls back like app.cpp:400-431."""
+        avail = available_recovery_options if available_recovery_options is not None else T.RenderBackendOptions()
+        if self._L.rptr_cuda_configure_for(self._h, C.byref(rbo), variant_idx, C.byref(avail)) != 0:
+            return False
+        self.options = T.RenderBackendOptions.from_buffer_copy(rbo)
+        return True
+
+    def last_error(self):
+        return self._L.rptr_cuda_last_error(self._h).decode()
+
+    # -- ray queries through the integrator (librender/render_backend.h:101-102) -------------------------------------------
+    def enable_ray_queries(self, max_queries=T.DEFAULT_RAY_QUERY_BUDGET, max_queries_per_pixel=0):
+        self._check(self._L.rptr_cuda_enable_ray_queries(self._h, int(max_queries), int(max_queries_per_pixel)))
+
+    def ray_query_capacity(self):
+        cap = C.c_size_t()
+        self._check(self._L.rptr_cuda_ray_query_buffers(self._h, None, None, C.byref(cap)))
+        return cap.value
+
+    def write_ray_queries(self, queries, first=0):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, 8)
+        self._check(self._L.rptr_cuda_write_ray_queries(self._h, q.ctypes.data, int(first), q.shape[0]))
+        return q.shape[0]
+
+    def render_ray_queries(self, num_queries, params=None, variant_idx=0, cmd_stream=None):
+        p = params if params is not None else self.params
+        self._check(self._L.rptr_cuda_render_ray_queries(self._h, int(num_queries), C.byref(p), variant_idx))
+        return True
+
+    def read_ray_results(self, n, first=0):
+        res = np.zeros((n, 4), np.float32)
+        self._check(self._L.rptr_cuda_read_ray_results(self._h, res.ctypes.data, int(first), int(n)))
+        return res
 
     # -- RaytraceBackend ----------------------------------------------------------------------------------------------
     def trace_ray(self, queries):

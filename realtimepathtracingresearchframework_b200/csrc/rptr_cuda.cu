@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -50,18 +51,6 @@ struct Wave {
     uint32_t *hit_counts; // per bounce
     uint32_t *counts; // per bounce d: [4d] live paths entering it, [4d+1] its shadow rays, [4d+2], [4d+3] fetch cursors
 };
-
-struct TileMap {
-    int32_t width, height;
-    int32_t rank, world, rows; // interleaved bands of `rows` rows: band b belongs to rank b % world
-    int32_t local_rows;
-    int32_t local_pixels;
-};
-
-__host__ __device__ inline int32_t local_row_to_global(const TileMap &t, int32_t lr) {
-    int32_t band = lr / t.rows;
-    return (band * t.world + t.rank) * t.rows + lr % t.rows;
-}
 
 // The fp16 AOV images of the reference (aov_albedo_roughness_buffer, aov_normal_depth_buffer: vulkan/accumulate.glsl:19-23).
 // Every sample layer of a frame imageStore()s to them, last writer wins; with the sequential reading of a batch
@@ -108,16 +97,27 @@ __device__ __forceinline__ void flush_counter(unsigned long long *dst, unsigned 
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
 }
 
-// raygen (vulkan/pt_megakernel.glsl:310-365): one thread per path slot of the wave
-__global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave w, int32_t first_layer, int32_t n_layers) {
+// raygen (vulkan/pt_megakernel.glsl:310-365): one thread per path slot of the wave.  Sample index of layer l of the wave =
+// sample_base + first_layer + l (frames: sample_base = view_params.frame_id = fp.first_sample; ray queries: 0,
+// accumulation_frame_offset of record_frame, vulkan/render_vulkan.cpp:2982).  With `queries` the camera ray is replaced by the
+// caller's ray AFTER the sampler has been seeded and the pixel-filter draws consumed (:326-334).
+__global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave w, uint32_t sample_base, int32_t first_layer, int32_t n_layers,
+                                                const rptr_render_ray_query *queries) {
     const uint32_t n = (uint32_t)n_layers * (uint32_t)tm.local_pixels;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
         const int32_t layer = (int32_t)(slot / (uint32_t)tm.local_pixels);
-        const int32_t lp = (int32_t)(slot % (uint32_t)tm.local_pixels);
-        const int32_t px = lp % tm.width;
-        const int32_t py = local_row_to_global(tm, lp / tm.width);
+        const uint32_t lp = slot % (uint32_t)tm.local_pixels;
+        uint32_t upx, upy;
+        tile_pixel(tm, lp, upx, upy);
+        const int32_t px = (int32_t)upx, py = (int32_t)upy;
         PathState ps;
-        generate_primary(fp, px, py, fp.first_sample + (uint32_t)(first_layer + layer), ps);
+        generate_primary(fp, px, py, sample_base + (uint32_t)(first_layer + layer), ps);
+        if (queries) {
+            const rptr_render_ray_query q = queries[lp];
+            ps.o = f3(q.origin[0], q.origin[1], q.origin[2]);
+            ps.d = f3(q.dir[0], q.dir[1], q.dir[2]);
+            ps.tmax = q.t_max;
+        }
         // RPTR_IMPLIED_INITIAL_STATE: thr = (1, 1, 1, prev_pdf = 2e16) and illum = 0 are implied for a path that has not been
         // shaded yet (bounce counter 0): the first shade launch and the resolve kernel substitute them instead of reading 32
         // bytes raygen would have to write
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave
         w.rngb[slot] = make_uint2(ps.rng, 0u);
         if (fp.rng_variant != 0) {
             w.rng2[slot] = ps.rng_b;
-            if (w.rng3) w.rng3[slot] = alpha_lcg_seed(fp, px, py, fp.first_sample + (uint32_t)(first_layer + layer));
+            if (w.rng3) w.rng3[slot] = alpha_lcg_seed(fp, px, py, sample_base + (uint32_t)(first_layer + layer));
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) w.counts[0] = n;
@@ -295,8 +295,7 @@ __global__ void __launch_bounds__(128) k_shadow(BvhDev bvh, Wave w, const uint32
         HitRec h;
         const float4 c = w.sh_c[i];
         const uint32_t slot = __float_as_uint(c.w);
-        const uint32_t lp = slot % (uint32_t)tm.local_pixels;
-        af.pixel_linear = (uint32_t)local_row_to_global(tm, (int32_t)(lp / (uint32_t)tm.width)) * (uint32_t)tm.width + lp % (uint32_t)tm.width;
+        af.pixel_linear = tile_pixel_linear(tm, slot % (uint32_t)tm.local_pixels);
         const bool occluded = trace_ray<true>(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, h, cnt, o.w, 0x7fffffff, &af);
         rays++;
         if (!occluded) {
@@ -310,13 +309,28 @@ __global__ void __launch_bounds__(128) k_shadow(BvhDev bvh, Wave w, const uint32
     flush_counter(&dc->shadow_tris, cnt.tris);
 }
 
+// The vec4 main_spp returns for the path in `slot` (vulkan/pt_megakernel.glsl:736): paths that ended with a miss (hit record
+// still says "no triangle") get their sky / sun-disc term here, from the ray direction, throughput and previous-bounce pdf
+// they died with (shade_miss).  *primary_miss = the primary ray left the scene.
+__device__ __forceinline__ float4 path_sample(const FrameParams &fp, const Wave &w, uint32_t slot, bool *primary_miss) {
+    const float alpha = w.rngb[slot].y == 0u ? 0.0f : 1.0f;
+    const bool miss = __float_as_int(w.hit[slot].w) < 0;
+    const bool untouched = RPTR_IMPLIED_INITIAL_STATE && miss && alpha == 0.0f; // primary ray left the scene: never shaded
+    float4 il = untouched ? f4(0.0f, 0.0f, 0.0f, 0.0f) : w.illum[slot];
+    if (miss) {
+        const float4 d = w.ray_d[slot];
+        const float4 thr = untouched ? f4(1.0f, 1.0f, 1.0f, 2.e16f) : w.thr[slot];
+        const float3 r = shade_miss(fp.sp, f3(il.x, il.y, il.z), f3(thr.x, thr.y, thr.z), f3(d.x, d.y, d.z), thr.w);
+        il.x = r.x; il.y = r.y; il.z = r.z;
+    }
+    *primary_miss = miss && alpha == 0.0f;
+    return f4(il.x, il.y, il.z, alpha);
+}
+
 // accumulate.glsl:68-73 + process_samples.comp:116-129 replayed in sample order for the layers of this wave:
 // sample k (0-based since the last reset) is stored when k == 0 and folded as m += (x - m) / float(k + 1) otherwise.
-// Paths that ended with a miss (hit record still says "no triangle") get their sky / sun-disc term here, from the ray
-// direction, throughput and previous-bounce pdf they died with (shade_miss).
 __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, TileMap tm, Wave w, float4 *accum, uint32_t first_sample, int32_t n_layers,
                                                  DevCounters *dc, AovTarget aov, int discard_history) {
-    const rptr_scene_params &sp = fp.sp;
     unsigned long long samples = 0;
     for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < (uint32_t)tm.local_pixels; lp += gridDim.x * blockDim.x) {
         const int32_t px = (int32_t)(lp % (uint32_t)tm.width);
@@ -325,28 +339,18 @@ __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, TileMap tm, Wav
         float4 m = *dst;
         for (int32_t l = 0; l < n_layers; ++l) {
             const uint32_t slot = (uint32_t)l * (uint32_t)tm.local_pixels + lp;
-            const float alpha = w.rngb[slot].y == 0u ? 0.0f : 1.0f;
-            const bool miss = __float_as_int(w.hit[slot].w) < 0;
-            const bool untouched = RPTR_IMPLIED_INITIAL_STATE && miss && alpha == 0.0f; // primary ray left the scene: never shaded
-            float4 il = untouched ? f4(0.0f, 0.0f, 0.0f, 0.0f) : w.illum[slot];
-            if (miss) {
-                if (aov.albedo_roughness && alpha == 0.0f && slot - aov.slot_lo < (uint32_t)tm.local_pixels) { // primary ray left the scene
-                    store_aov(aov, tm, slot, aov_of_miss(fp));
-                }
-                const float4 d = w.ray_d[slot];
-                const float4 thr = untouched ? f4(1.0f, 1.0f, 1.0f, 2.e16f) : w.thr[slot];
-                const float3 r = shade_miss(sp, f3(il.x, il.y, il.z), f3(thr.x, thr.y, thr.z), f3(d.x, d.y, d.z), thr.w);
-                il.x = r.x; il.y = r.y; il.z = r.z;
-            }
+            bool primary_miss;
+            const float4 x = path_sample(fp, w, slot, &primary_miss);
+            if (primary_miss && aov.albedo_roughness && slot - aov.slot_lo < (uint32_t)tm.local_pixels) store_aov(aov, tm, slot, aov_of_miss(fp));
             const uint32_t k = first_sample + (uint32_t)l;
             if (k > 0 && !discard_history) { // process_samples.comp:116-127: REPROJECTION_MODE_DISCARD_HISTORY keeps the new sample only
                 const float denom = (float)(k + 1u);
-                m.x += (il.x - m.x) / denom;
-                m.y += (il.y - m.y) / denom;
-                m.z += (il.z - m.z) / denom;
-                m.w += (alpha - m.w) / denom;
+                m.x += (x.x - m.x) / denom;
+                m.y += (x.y - m.y) / denom;
+                m.z += (x.z - m.z) / denom;
+                m.w += (x.w - m.w) / denom;
             } else
-                m = f4(il.x, il.y, il.z, alpha);
+                m = x;
             samples++;
         }
         *dst = m;
@@ -354,8 +358,58 @@ __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, TileMap tm, Wav
     flush_counter(&dc->samples, samples);
 }
 
+// accumulate_query (vulkan/accumulate.glsl:32-42) replayed in sample order for the layers of this wave (the reference runs the
+// layers of a batch concurrently; one after the other is the race-free reading, as for frames).  Statement by statement:
+//   accum = sample_index > 0 ? ray_results[q] : 0;  accum += (x - accum) / (sample_index + 1);
+//   if (sample_index == 0) ray_results[q] = accum; else ray_results[q] += accum;
+// -- for sample_index > 0 the stored value is the OLD result PLUS the updated mean, not the mean: kept as written.
+__global__ void __launch_bounds__(256) k_resolve_queries(FrameParams fp, Wave w, float4 *results, uint32_t n_queries, uint32_t first_sample,
+                                                         int32_t n_layers, DevCounters *dc) {
+    unsigned long long samples = 0;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_queries; q += gridDim.x * blockDim.x) {
+        float4 r = results[q];
+        for (int32_t l = 0; l < n_layers; ++l) {
+            bool primary_miss;
+            const float4 x = path_sample(fp, w, (uint32_t)l * n_queries + q, &primary_miss);
+            const uint32_t k = first_sample + (uint32_t)l;
+            float4 a = k > 0 ? r : f4(0.0f, 0.0f, 0.0f, 0.0f);
+            const float denom = (float)(k + 1u);
+            a.x += (x.x - a.x) / denom; a.y += (x.y - a.y) / denom; a.z += (x.z - a.z) / denom; a.w += (x.w - a.w) / denom;
+            if (k == 0) r = a;
+            else { r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w; }
+            samples++;
+        }
+        results[q] = r;
+    }
+    flush_counter(&dc->samples, samples);
+}
+
 // RQ_CLOSEST (vulkan/rt_intersect.comp:30-68): opaque closest hit (gl_RayFlagsOpaqueEXT: no alpha test) over
 // (RAY_EPSILON * |origin|, t_max); mode < 0 leaves the result slot untouched; a miss stores (-1, -1, bits(-1), bits(-1)).
+// The rays go through the persistent traversal kernel like the path tracer's own (k_trace_persistent<false, false>):
+// k_rq_prepare turns the queries into its ray records, k_rq_pack its hit records into the result words.
+__global__ void __launch_bounds__(256) k_rq_prepare(const rptr_render_ray_query *q, int32_t n, float4 *ray_o, float4 *ray_d, uint32_t *counts) {
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float3 o = f3(q[i].origin[0], q[i].origin[1], q[i].origin[2]);
+        const bool skip = q[i].mode_or_data < 0;
+        ray_o[i] = f4(o.x, o.y, o.z, RPTR_RAY_EPSILON * length(o));
+        ray_d[i] = f4(q[i].dir[0], q[i].dir[1], q[i].dir[2], skip ? -1.0f : q[i].t_max); // empty range: a skipped query finds nothing
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counts[0] = (uint32_t)n; counts[1] = 0u; }
+}
+__global__ void __launch_bounds__(256) k_rq_pack(BvhDev bvh, const rptr_render_ray_query *q, int32_t n, const float4 *hit, float4 *results, float *hit_t) {
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (q[i].mode_or_data < 0) continue;
+        const float4 h = hit[i];
+        const int32_t tri = __float_as_int(h.w);
+        const bool ok = tri >= 0;
+        int32_t gi = -1, prim = -1;
+        if (ok) { gi = tri_geom_inst(bvh.tris[tri]); prim = bvh.tris[tri].prim; }
+        results[i] = f4(ok ? h.y : -1.0f, ok ? h.z : -1.0f, __int_as_float(gi), __int_as_float(prim));
+        if (hit_t) hit_t[i] = ok ? h.x : -1.0f;
+    }
+}
+// the same service with one ray per thread (option "trace_kernel" = 1: A/B reference)
 __global__ void __launch_bounds__(128) k_ray_queries(BvhDev bvh, const rptr_render_ray_query *q, int32_t n, float4 *results, float *hit_t) {
     TraceCounters cnt{0, 0};
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -498,6 +552,23 @@ struct rptr_ctx {
     std::vector<cudaEvent_t> event_pool;
     size_t bytes_now = 0, bytes_max = 0, bytes_total = 0;
     std::unordered_map<void *, size_t> alloc_sizes; // RenderStats::device_bytes_currently_allocated
+    // view_params.frame_id / frame_offset as the last begin_frame left them (update_view_parameters, render_vulkan.cpp:2907-2910):
+    // what the kernels of that frame -- and of ray queries rendered after it -- see, whatever end_frame does to the counters
+    uint32_t view_frame_id = 0, view_frame_offset = 0;
+    bool has_view = false;
+    // ray queries (enable_ray_queries / render_ray_queries, vulkan/render_vulkan.cpp:430-455, 1867-1876)
+    int rq_fixed_budget = 0, rq_per_pixel_budget = 0;
+    rptr_render_ray_query *rq_queries = nullptr; // ray_query_buffer
+    float4 *rq_results = nullptr;                // ray_result_buffer
+    size_t rq_capacity = 0;
+    std::vector<void *> rq_allocs;
+    // scratch of the RaytraceBackend service (rptr_cuda_trace_rays), grown on demand and kept
+    std::vector<void *> tr_allocs;
+    size_t tr_capacity = 0;
+    rptr_render_ray_query *tr_queries = nullptr;
+    float4 *tr_ray_o = nullptr, *tr_ray_d = nullptr, *tr_hit = nullptr, *tr_results = nullptr;
+    float *tr_t = nullptr;
+    uint32_t *tr_counts = nullptr;
 };
 
 static int fail(rptr_ctx *ctx, const char *fmt, ...) {
@@ -543,7 +614,7 @@ static void free_all(rptr_ctx *ctx, std::vector<void *> &owner) {
 }
 
 static TileMap make_tilemap(const rptr_ctx *ctx) {
-    TileMap t;
+    TileMap t{};
     t.width = ctx->width; t.height = ctx->height;
     t.rank = ctx->tile_rank; t.world = ctx->tile_world; t.rows = ctx->tile_rows;
     int32_t rows = 0;
@@ -687,6 +758,8 @@ void rptr_cuda_destroy(rptr_ctx *ctx) {
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     free_all(ctx, ctx->scene_allocs);
     free_all(ctx, ctx->wave_allocs);
+    free_all(ctx, ctx->rq_allocs);
+    free_all(ctx, ctx->tr_allocs);
     for (uint32_t *t : ctx->pointset_tables) cudaFree(t);
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
@@ -702,6 +775,8 @@ void rptr_cuda_destroy(rptr_ctx *ctx) {
 }
 
 const char *rptr_cuda_last_error(const rptr_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+static int ensure_ray_query_buffers(rptr_ctx *ctx);
 
 int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height) {
     if (!ctx) return 1;
@@ -728,6 +803,8 @@ int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height) {
     ctx->frame_offset = 0;
     ctx->accumulated_spp = 0;
     ctx->in_frame = false;
+    ctx->has_view = false;
+    if (ctx->rq_per_pixel_budget && ensure_ray_query_buffers(ctx)) return 1; // vulkan/render_vulkan.cpp:366-369
     return 0;
 }
 
@@ -963,6 +1040,9 @@ int rptr_cuda_begin_frame(rptr_ctx *ctx, const rptr_camera_params *camera, const
     // view_params in either reprojection mode), then this frame's VP
     memcpy(ctx->vp_reference, ctx->vp, sizeof(ctx->vp));
     view_projection(ctx->camera, ctx->width, ctx->height, ctx->vp);
+    ctx->view_frame_id = ctx->frame_id;
+    ctx->view_frame_offset = ctx->frame_offset;
+    ctx->has_view = true;
     ctx->in_frame = true;
     return 0;
 }
@@ -973,15 +1053,15 @@ static FrameParams make_frame_params(const rptr_ctx *ctx) {
     fp.width = ctx->width; fp.height = ctx->height;
     memcpy(fp.cam_pos, ctx->camera.pos, sizeof(fp.cam_pos));
     view_params(ctx->camera, ctx->width, ctx->height, fp.du, fp.dv, fp.tl);
-    fp.frame_offset = ctx->frame_offset;
-    fp.first_sample = ctx->frame_id;
+    fp.frame_offset = ctx->view_frame_offset;
+    fp.first_sample = ctx->view_frame_id;
     fp.batch = ctx->params.batch_spp;
     fp.max_path_depth = ctx->params.max_path_depth;
     fp.rr_path_depth = ctx->params.rr_path_depth;
     fp.output_channel = ctx->params.output_channel;
     fp.glossy_only_mode = ctx->params.glossy_only_mode;
     fp.enable_raster_taa = ctx->params.enable_raster_taa;
-    if (fp.enable_raster_taa > 0) screen_jitter(ctx->frame_offset, ctx->frame_id, ctx->width, ctx->height, fp.screen_jitter);
+    if (fp.enable_raster_taa > 0) screen_jitter(ctx->view_frame_offset, ctx->view_frame_id, ctx->width, ctx->height, fp.screen_jitter);
     memcpy(fp.vp, ctx->vp, sizeof(fp.vp));
     memcpy(fp.vp_reference, ctx->vp_reference, sizeof(fp.vp_reference));
     fp.n_lights = ctx->n_lights;
@@ -999,25 +1079,19 @@ static FrameParams make_frame_params(const rptr_ctx *ctx) {
     return fp;
 }
 
-int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
-    (void)variant;
-    if (!ctx) return 1;
-    if (!ctx->in_frame) return fail(ctx, "draw_frame outside begin_frame/end_frame");
-    {   // the Sobol / blue-noise samplers read the reference's tables (vulkan/pointsets/render_{sobol,bn}.cpp upload them)
-        const int v = ctx->rng_variant;
-        const bool ok = v == 0 || (v == 1 && ctx->pointset_tables[2] && ctx->pointset_tables[3]) || (v == 2 && ctx->pointset_tables[0]) ||
-                        (v == 3 && ctx->pointset_tables[0] && ctx->pointset_tables[1]);
-        if (!ok) return fail(ctx, "rng_variant %d needs its tables: call rptr_cuda_set_pointset_table first", v);
-    }
-    CU(cudaSetDevice(ctx->device));
-    const TileMap tm = make_tilemap(ctx);
-    FrameParams fp = make_frame_params(ctx);
+} // extern "C"
+
+// The wavefront: `batch` sample layers of the pixels (or ray queries) of `tm`, in waves of at most wave_paths paths:
+//   raygen -> [closest hit -> shade -> shadow] x max_path_depth -> resolve.
+// Frames resolve into the accumulator (queries == nullptr); ray queries (tm.query_wgs_x > 0) take their rays from `queries` and
+// resolve into `results` (both device arrays of tm.local_pixels entries).  sample_base = sample index of layer 0.
+static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm, int32_t batch, uint32_t sample_base,
+                        const rptr_render_ray_query *queries, float4 *results) {
     const int depth = fp.max_path_depth;
-    CU(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (tm.local_pixels > 0) {
         int64_t layers_per_wave = ctx->wave_paths / tm.local_pixels;
         if (layers_per_wave < 1) layers_per_wave = 1;
-        if (layers_per_wave > fp.batch) layers_per_wave = fp.batch;
+        if (layers_per_wave > batch) layers_per_wave = batch;
         if (ensure_wave(ctx, (size_t)layers_per_wave * tm.local_pixels, depth)) return 1;
         Wave &w = ctx->wave;
         // Scenes whose materials take several shading code paths (C4: GGX, thick / thin transmission, emitters): the trace kernel
@@ -1046,18 +1120,18 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
         // trace: one RPTR_TRACE_THREADS CTA per SM; dynamic smem = the staged top of the BVH + the shared stack part
         const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4), g_pt = grid_for(ctx, 1);
         const size_t top_smem = RPTR_TRACE_SMEM_BYTES; // staged BVH top (128 KB) + shared part of the traversal stacks (64 KB)
-        for (int32_t first = 0; first < fp.batch; first += (int32_t)layers_per_wave) {
-            const int32_t nl = (int32_t)((fp.batch - first) < layers_per_wave ? (fp.batch - first) : layers_per_wave);
+        for (int32_t first = 0; first < batch; first += (int32_t)layers_per_wave) {
+            const int32_t nl = (int32_t)((batch - first) < layers_per_wave ? (batch - first) : layers_per_wave);
             CU(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), ctx->stream));
             CU(cudaMemsetAsync(w.hit_counts, 0, sizeof(uint32_t) * (depth + 2), ctx->stream));
             // AOV images: written by the first vertex of the frame's last sample layer (last wave, last layer)
             AovTarget aov{nullptr, nullptr, nullptr, 0u};
-            if (ctx->aov_buffers && first + nl == fp.batch) aov = AovTarget{ctx->aov_images[0], ctx->aov_images[1], ctx->aov_images[2], (uint32_t)(nl - 1) * (uint32_t)tm.local_pixels};
+            if (ctx->aov_buffers && !queries && first + nl == batch) aov = AovTarget{ctx->aov_images[0], ctx->aov_images[1], ctx->aov_images[2], (uint32_t)(nl - 1) * (uint32_t)tm.local_pixels};
             {
                 StageTimer t(ctx, 3);
                 Wave wr = w;
                 if (!ctx->any_alpha_tested) wr.rng3 = nullptr; // no alpha-tested triangle: nobody reads the alpha LCG
-                k_raygen<<<g_light, 256, 0, ctx->stream>>>(fp, tm, wr, first, nl);
+                k_raygen<<<g_light, 256, 0, ctx->stream>>>(fp, tm, wr, sample_base, first, nl, queries);
                 ctx->launches++;
             }
             bool shadow_pending = false;
@@ -1085,7 +1159,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     StageTimer t(ctx, union_a ? -1 : 0);
                     if (union_a) union_launches++;
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, hitq, w.hit_counts + d, nullptr, nullptr, alpha_lcg, alpha_stride, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, hitq, w.hit_counts + d, nullptr, nullptr, alpha_lcg, alpha_stride, alpha_filter, tm};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<false, true> : k_trace_persistent<false, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
                             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
@@ -1118,7 +1192,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                     }
                     CU(cudaEventRecord(ctx->ev_shade, ctx->stream));
                     CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_shade, 0));
-                    TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, alpha_lcg, alpha_stride, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                    TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, alpha_lcg, alpha_stride, alpha_filter, tm};
                     auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                     kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream2>>>(
                         ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
@@ -1128,7 +1202,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
                 } else if (fp.output_channel == 0 && d + 1 < depth) {
                     StageTimer t(ctx, 2);
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, alpha_lcg, alpha_stride, alpha_filter, tm.width, tm.local_pixels, tm.rank, tm.world, tm.rows};
+                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, alpha_lcg, alpha_stride, alpha_filter, tm};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
                             ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
@@ -1140,12 +1214,35 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
             if (join_shadow()) return 1;
             {
                 StageTimer t(ctx, 3);
-                k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp, tm, w, ctx->accum, ctx->frame_id + (uint32_t)first, nl, ctx->dcounters, aov,
-                                                            ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_DISCARD_HISTORY);
+                if (queries)
+                    k_resolve_queries<<<g_light, 256, 0, ctx->stream>>>(fp, w, results, (uint32_t)tm.local_pixels, sample_base + (uint32_t)first, nl, ctx->dcounters);
+                else
+                    k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp, tm, w, ctx->accum, sample_base + (uint32_t)first, nl, ctx->dcounters, aov,
+                                                                ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_DISCARD_HISTORY);
                 ctx->launches++;
             }
         }
     }
+    return 0;
+}
+
+extern "C" {
+
+int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
+    (void)variant;
+    if (!ctx) return 1;
+    if (!ctx->in_frame) return fail(ctx, "draw_frame outside begin_frame/end_frame");
+    {   // the Sobol / blue-noise samplers read the reference's tables (vulkan/pointsets/render_{sobol,bn}.cpp upload them)
+        const int v = ctx->rng_variant;
+        const bool ok = v == 0 || (v == 1 && ctx->pointset_tables[2] && ctx->pointset_tables[3]) || (v == 2 && ctx->pointset_tables[0]) ||
+                        (v == 3 && ctx->pointset_tables[0] && ctx->pointset_tables[1]);
+        if (!ok) return fail(ctx, "rng_variant %d needs its tables: call rptr_cuda_set_pointset_table first", v);
+    }
+    CU(cudaSetDevice(ctx->device));
+    const TileMap tm = make_tilemap(ctx);
+    FrameParams fp = make_frame_params(ctx);
+    CU(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    if (render_waves(ctx, fp, tm, fp.batch, fp.first_sample, nullptr, nullptr)) return 1;
     CU(cudaGetLastError());
     return 0;
 }
@@ -1299,37 +1396,202 @@ int rptr_cuda_stream_handle(rptr_ctx *ctx, void **stream) {
     return 0;
 }
 
+static int origins_in_reach(rptr_ctx *ctx, const rptr_render_ray_query *queries, int32_t n, const char *who, bool honour_skip) {
+    const float reach = 8.0f * fmaxf(ctx->scene_extent, 1e-3f); // see begin_frame
+    for (int32_t i = 0; i < n; ++i)
+        if ((!honour_skip || queries[i].mode_or_data >= 0) &&
+            !(fabsf(queries[i].origin[0]) <= reach && fabsf(queries[i].origin[1]) <= reach && fabsf(queries[i].origin[2]) <= reach))
+            return fail(ctx, "%s: origin of query %d is outside the supported range of %g (8 x the scene extent)", who, i, reach);
+    return 0;
+}
+
 int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, int32_t n, float *results, float *hit_t) {
     if (!ctx) return 1;
     if (!ctx->has_scene) return fail(ctx, "trace_rays before set_scene");
     if (n < 0 || (n > 0 && (!queries || !results))) return fail(ctx, "trace_rays: invalid arguments");
     if (n == 0) return 0;
-    {
-        const float reach = 8.0f * fmaxf(ctx->scene_extent, 1e-3f); // see begin_frame
-        for (int32_t i = 0; i < n; ++i)
-            if (queries[i].mode_or_data >= 0 && !(fabsf(queries[i].origin[0]) <= reach && fabsf(queries[i].origin[1]) <= reach && fabsf(queries[i].origin[2]) <= reach))
-                return fail(ctx, "trace_rays: origin of query %d is outside the supported range of %g (8 x the scene extent)", i, reach);
-    }
+    if (origins_in_reach(ctx, queries, n, "trace_rays", true)) return 1;
     CU(cudaSetDevice(ctx->device));
-    struct Scratch { // freed on every exit path
-        void *p[3] = {nullptr, nullptr, nullptr};
-        ~Scratch() { for (void *q : p) cudaFree(q); }
-    } scratch;
-    CU(cudaMalloc(&scratch.p[0], sizeof(rptr_render_ray_query) * (size_t)n));
-    CU(cudaMalloc(&scratch.p[1], sizeof(float4) * (size_t)n));
-    CU(cudaMalloc(&scratch.p[2], sizeof(float) * (size_t)n));
-    rptr_render_ray_query *dq = static_cast<rptr_render_ray_query *>(scratch.p[0]);
-    float4 *dr = static_cast<float4 *>(scratch.p[1]);
-    float *dt = static_cast<float *>(scratch.p[2]);
+    if ((size_t)n > ctx->tr_capacity) { // scratch is kept between calls and only ever grows
+        CU(cudaStreamSynchronize(ctx->stream));
+        free_all(ctx, ctx->tr_allocs);
+        ctx->tr_capacity = 0;
+        const size_t cap = (size_t)n + (size_t)n / 4;
+        CU(dev_alloc(ctx, &ctx->tr_queries, cap, ctx->tr_allocs));
+        CU(dev_alloc(ctx, &ctx->tr_ray_o, cap, ctx->tr_allocs));
+        CU(dev_alloc(ctx, &ctx->tr_ray_d, cap, ctx->tr_allocs));
+        CU(dev_alloc(ctx, &ctx->tr_hit, cap, ctx->tr_allocs));
+        CU(dev_alloc(ctx, &ctx->tr_results, cap, ctx->tr_allocs));
+        CU(dev_alloc(ctx, &ctx->tr_t, cap, ctx->tr_allocs));
+        CU(dev_alloc(ctx, &ctx->tr_counts, 4, ctx->tr_allocs));
+        ctx->tr_capacity = cap;
+    }
+    rptr_render_ray_query *dq = ctx->tr_queries;
+    float4 *dr = ctx->tr_results;
+    float *dt = ctx->tr_t;
     CU(cudaMemcpyAsync(dq, queries, sizeof(rptr_render_ray_query) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     // slots of skipped queries (mode < 0) keep what the caller's buffers hold (rt_intersect.comp:44-45)
     CU(cudaMemcpyAsync(dr, results, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     if (hit_t) CU(cudaMemcpyAsync(dt, hit_t, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    k_ray_queries<<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->bvh, dq, n, dr, hit_t ? dt : nullptr);
-    ctx->launches++;
+    if (ctx->trace_kernel == 0) {
+        k_rq_prepare<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(dq, n, ctx->tr_ray_o, ctx->tr_ray_d, ctx->tr_counts);
+        TraceIO io{ctx->tr_ray_o, ctx->tr_ray_d, nullptr, ctx->tr_counts, ctx->tr_counts + 1, ctx->tr_hit, nullptr, nullptr, nullptr, nullptr, nullptr, 0u,
+                   AlphaFilter{nullptr, 0u, 0u, 0u}, TileMap{}};
+        k_trace_persistent<false, false><<<grid_for(ctx, 1), RPTR_TRACE_THREADS, RPTR_TRACE_SMEM_BYTES, ctx->stream>>>(
+            ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
+        k_rq_pack<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->bvh, dq, n, ctx->tr_hit, dr, hit_t ? dt : nullptr);
+        ctx->launches += 3;
+    } else {
+        k_ray_queries<<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->bvh, dq, n, dr, hit_t ? dt : nullptr);
+        ctx->launches++;
+    }
     CU(cudaMemcpyAsync(results, dr, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     if (hit_t) CU(cudaMemcpyAsync(hit_t, dt, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- ray queries through the integrator -------------------------------------------------------------------------------------
+static int ensure_ray_query_buffers(rptr_ctx *ctx) {
+    size_t budget = (size_t)(ctx->accum ? (size_t)ctx->width * ctx->height : 0) * (size_t)ctx->rq_per_pixel_budget;
+    if (budget < (size_t)ctx->rq_fixed_budget) budget = (size_t)ctx->rq_fixed_budget;
+    if (budget == ctx->rq_capacity) return 0;
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_all(ctx, ctx->rq_allocs);
+    ctx->rq_capacity = 0;
+    ctx->rq_queries = nullptr;
+    ctx->rq_results = nullptr;
+    if (budget == 0) return 0;
+    CU(dev_alloc(ctx, &ctx->rq_queries, budget, ctx->rq_allocs));
+    CU(dev_alloc(ctx, &ctx->rq_results, budget, ctx->rq_allocs));
+    CU(cudaMemsetAsync(ctx->rq_results, 0, budget * sizeof(float4), ctx->stream));
+    ctx->rq_capacity = budget;
+    return 0;
+}
+
+int rptr_cuda_enable_ray_queries(rptr_ctx *ctx, int32_t max_queries, int32_t max_queries_per_pixel) {
+    if (!ctx) return 1;
+    if (max_queries < 0 || max_queries_per_pixel < 0) return fail(ctx, "enable_ray_queries: negative budget");
+    CU(cudaSetDevice(ctx->device));
+    ctx->rq_fixed_budget = max_queries;
+    ctx->rq_per_pixel_budget = max_queries_per_pixel;
+    return ensure_ray_query_buffers(ctx); // before initialize() only the fixed budget counts; initialize() sizes them again (:366-369)
+}
+
+int rptr_cuda_ray_query_buffers(rptr_ctx *ctx, void **queries, void **results, size_t *capacity) {
+    if (!ctx) return 1;
+    if (queries) *queries = ctx->rq_queries;
+    if (results) *results = ctx->rq_results;
+    if (capacity) *capacity = ctx->rq_capacity;
+    return 0;
+}
+
+int rptr_cuda_write_ray_queries(rptr_ctx *ctx, const rptr_render_ray_query *queries, int32_t first, int32_t n) {
+    if (!ctx) return 1;
+    if (n < 0 || first < 0 || (n > 0 && !queries)) return fail(ctx, "write_ray_queries: invalid arguments");
+    if ((size_t)first + (size_t)n > ctx->rq_capacity)
+        return fail(ctx, "write_ray_queries: queries [%d, %d) exceed the budget of %zu set by enable_ray_queries", first, first + n, ctx->rq_capacity);
+    if (n == 0) return 0;
+    if (ctx->has_scene && origins_in_reach(ctx, queries, n, "write_ray_queries", false)) return 1;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->rq_queries + first, queries, sizeof(rptr_render_ray_query) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // the host buffer is only borrowed for the call
+    return 0;
+}
+
+int rptr_cuda_read_ray_results(rptr_ctx *ctx, float *results, int32_t first, int32_t n) {
+    if (!ctx) return 1;
+    if (n < 0 || first < 0 || (n > 0 && !results)) return fail(ctx, "read_ray_results: invalid arguments");
+    if ((size_t)first + (size_t)n > ctx->rq_capacity) return fail(ctx, "read_ray_results: range exceeds the ray-query budget of %zu", ctx->rq_capacity);
+    if (n == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(results, ctx->rq_results + first, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rptr_cuda_render_ray_queries(rptr_ctx *ctx, int32_t num_queries, const rptr_render_params *params, int32_t variant) {
+    (void)params; // the reference does not read it either: record_frame uses this->params (vulkan/render_vulkan.cpp:1867-1876, 2965)
+    (void)variant;
+    if (!ctx) return 1;
+    if (!ctx->has_scene) return fail(ctx, "render_ray_queries before set_scene");
+    if (!ctx->has_view) return fail(ctx, "render_ray_queries before the first begin_frame (it renders with that frame's view and render parameters)");
+    if (num_queries < 0) return fail(ctx, "render_ray_queries: negative query count");
+    if ((size_t)num_queries > ctx->rq_capacity)
+        return fail(ctx, "render_ray_queries: %d queries exceed the budget of %zu set by enable_ray_queries", num_queries, ctx->rq_capacity);
+    if (num_queries == 0) return 0; // record_frame then renders a normal frame; callers do not rely on that
+    {
+        const int v = ctx->rng_variant;
+        const bool ok = v == 0 || (v == 1 && ctx->pointset_tables[2] && ctx->pointset_tables[3]) || (v == 2 && ctx->pointset_tables[0]) ||
+                        (v == 3 && ctx->pointset_tables[0] && ctx->pointset_tables[1]);
+        if (!ok) return fail(ctx, "rng_variant %d needs its tables: call rptr_cuda_set_pointset_table first", v);
+    }
+    CU(cudaSetDevice(ctx->device));
+    FrameParams fp = make_frame_params(ctx);
+    TileMap tm{};
+    tm.width = ctx->width; tm.height = ctx->height;
+    tm.rank = 0; tm.world = 1; tm.rows = 1;
+    tm.local_rows = 0;
+    tm.local_pixels = num_queries;
+    // "dispatch ray queries into a virtual screen square" (record_frame, :3050-3056): ceil(sqrt(n)) invocations per row, in
+    // workgroups of 32 x 16 (ComputeRenderPipelineVulkan::dispatch_rays)
+    const int dim_x = (int)std::ceil(std::sqrt((float)num_queries));
+    tm.query_wgs_x = (dim_x + 31) / 32;
+    if (render_waves(ctx, fp, tm, fp.batch, 0u, ctx->rq_queries, ctx->rq_results)) return 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int rptr_cuda_normalize_options(rptr_ctx *ctx, rptr_backend_options *o, int32_t variant) {
+    (void)variant;
+    if (!ctx) return 1;
+    if (!o) return fail(ctx, "normalize_options: options is NULL");
+    if (o->rng_variant < 0 || o->rng_variant > RPTR_RNG_VARIANT_Z_SBL) o->rng_variant = RPTR_RNG_VARIANT_UNIFORM;
+    if (o->light_sampling_variant < 0 || o->light_sampling_variant > RPTR_LIGHT_SAMPLING_VARIANT_RIS) o->light_sampling_variant = RPTR_LIGHT_SAMPLING_VARIANT_RIS;
+    if (o->light_sampling_bucket_count < 1) o->light_sampling_bucket_count = 16;
+    if (o->render_upscale_factor < 1) o->render_upscale_factor = 1;
+    memset(o->_pad0, 0, sizeof(o->_pad0));
+    memset(o->_pad1, 0, sizeof(o->_pad1));
+    memset(o->_pad2, 0, sizeof(o->_pad2));
+    return 0;
+}
+
+int rptr_cuda_configure_for(rptr_ctx *ctx, const rptr_backend_options *o, int32_t variant, rptr_backend_options *available) {
+    if (!ctx) return 1;
+    if (!o) return fail(ctx, "configure_for: options is NULL");
+    if (ctx->in_frame) return fail(ctx, "configure_for inside begin_frame/end_frame");
+    rptr_backend_options ok = *o;
+    rptr_cuda_normalize_options(ctx, &ok, variant);
+    std::string why;
+    if (variant != 0) why += "variant index " + std::to_string(variant) + " does not exist (this backend has one integrator, PT_WAVEFRONT); ";
+    if (o->rng_variant < 0 || o->rng_variant > RPTR_RNG_VARIANT_Z_SBL) why += "unknown rng_variant; ";
+    if (o->light_sampling_variant != RPTR_LIGHT_SAMPLING_VARIANT_RIS) {
+        why += "light_sampling_variant must be RIS (binned triangle lights + sun); ";
+        ok.light_sampling_variant = RPTR_LIGHT_SAMPLING_VARIANT_RIS;
+    }
+    if (o->render_upscale_factor != 1) {
+        why += "render_upscale_factor " + std::to_string(o->render_upscale_factor) + " is not supported (no upscaling pass); ";
+        ok.render_upscale_factor = 1;
+    }
+    if (o->enable_taa) {
+        why += "enable_taa is not supported (no TAA pass); ";
+        ok.enable_taa = 0;
+    }
+    if (ok.rng_variant != RPTR_RNG_VARIANT_UNIFORM) {
+        const int v = ok.rng_variant;
+        const bool tables = (v == 1 && ctx->pointset_tables[2] && ctx->pointset_tables[3]) || (v == 2 && ctx->pointset_tables[0]) ||
+                            (v == 3 && ctx->pointset_tables[0] && ctx->pointset_tables[1]);
+        if (!tables) {
+            why += "rng_variant " + std::to_string(v) + " needs its tables (rptr_cuda_set_pointset_table) first; ";
+            ok.rng_variant = RPTR_RNG_VARIANT_UNIFORM;
+        }
+    }
+    if (available) *available = ok;
+    if (!why.empty()) return fail(ctx, "configure_for: %s", why.c_str());
+    ctx->rng_variant = ok.rng_variant;
+    // what the reference does at the end of a successful configure_for when built without ENABLE_REALTIME_RESOLVE
+    // (render_vulkan.cpp:1911-1915) -- params.reprojection_mode = NONE -- is left to the caller's RenderParams here
     return 0;
 }
 

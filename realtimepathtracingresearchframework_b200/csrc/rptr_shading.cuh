@@ -70,6 +70,43 @@ struct FrameParams {
     rptr_scene_params sp; // sun_radiance[3] already carries the light-count rule (vulkan/render_sky.cpp:67-70)
 };
 
+// ---- which pixel a path slot belongs to --------------------------------------------------------------------------------------
+// slot = layer * local_pixels + lp.  Frames: lp enumerates the rows this GPU owns (interleaved bands of `rows` rows: band b
+// belongs to rank b % world), row-major.  Ray queries (query_wgs_x > 0; render_ray_queries, vulkan/render_vulkan.cpp:1867-1876):
+// lp is the query index = gl_GlobalInvocationIndex of a 2-D dispatch of 32 x 16 workgroups, query_wgs_x of them per row
+// (record_frame, :3050-3056), and its "pixel" -- what seeds the samplers -- is the swizzled gl_GlobalInvocationID.xy of
+// vulkan/setup_pixel_assignment.glsl:17-22, linearised with the width of the real frame (rendering/pointsets/lcg_rng.glsl:36-39).
+struct TileMap {
+    int32_t width, height;
+    int32_t rank, world, rows;
+    int32_t local_rows;
+    int32_t local_pixels;
+    int32_t query_wgs_x; // 0: frame; > 0: ray queries
+};
+RPTR_HD int32_t local_row_to_global(const TileMap &t, int32_t lr) {
+    int32_t band = lr / t.rows;
+    return (band * t.world + t.rank) * t.rows + lr % t.rows;
+}
+RPTR_HD void query_pixel(uint32_t q, uint32_t wgs_x, uint32_t &px, uint32_t &py) {
+    const uint32_t wg = q >> 9, l = q & 511u; // WORKGROUP_SIZE 32 x 16 (vulkan/gpu_params.glsl, CMakeLists.txt:53-55)
+    const uint32_t gx = (wg % wgs_x) * 32u + (l & 31u), gy = (wg / wgs_x) * 16u + (l >> 5);
+    px = (gx & ~0x18u) + ((gy & 0x3u) << 3);
+    py = (gy & ~0x3u) + ((gx & 0x18u) >> 3);
+}
+RPTR_HD void tile_pixel(const TileMap &t, uint32_t lp, uint32_t &px, uint32_t &py) {
+    if (t.query_wgs_x > 0) {
+        query_pixel(lp, (uint32_t)t.query_wgs_x, px, py);
+        return;
+    }
+    px = lp % (uint32_t)t.width;
+    py = (uint32_t)local_row_to_global(t, (int32_t)(lp / (uint32_t)t.width));
+}
+RPTR_HD uint32_t tile_pixel_linear(const TileMap &t, uint32_t lp) {
+    uint32_t px, py;
+    tile_pixel(t, lp, px, py);
+    return px + py * (uint32_t)t.width;
+}
+
 // ---- RNG: rendering/pointsets/hashing.glsl:11-39, lcg_rng.glsl:15-39 ------------------------------------------------
 RPTR_HD uint32_t murmur_mix(uint32_t hash, uint32_t k) {
     k *= 0xcc9e2d51u;

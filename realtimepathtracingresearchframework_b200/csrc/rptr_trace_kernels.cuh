@@ -45,7 +45,7 @@ struct TraceIO {
     uint32_t *alpha_lcg;   // closest: LCG state the candidate filter draws from, word alpha_lcg[slot * alpha_stride]: the path's own
     uint32_t alpha_stride; //          LCG with the UNIFORM pointset (stride 2: Wave::rngb), a separate one otherwise (stride 1: Wave::rng3)
     AlphaFilter alpha;     // shadow: per-candidate LCG seeds (pixel_linear is filled in per ray)
-    int32_t tm_width, tm_local_pixels, tm_rank, tm_world, tm_rows; // shadow: path slot -> global pixel (TileMap of rptr_cuda.cu)
+    TileMap tm;            // shadow: path slot -> pixel that seeds the per-candidate LCG (frame pixel or ray-query invocation)
 };
 
 
@@ -320,9 +320,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 best_t = tmax; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
                 if (Alpha && !Any) after_id = 0x7fffffff;
                 if (Alpha && Any) { // global pixel of the path: slot -> local pixel -> row band of this rank
-                    const uint32_t lp = __float_as_uint(io.sh_c[ray_index].w) % (uint32_t)io.tm_local_pixels;
-                    const int32_t lr = (int32_t)(lp / (uint32_t)io.tm_width), band = lr / io.tm_rows;
-                    pixel_linear = (uint32_t)((band * io.tm_world + io.tm_rank) * io.tm_rows + lr % io.tm_rows) * (uint32_t)io.tm_width + lp % (uint32_t)io.tm_width;
+                    pixel_linear = tile_pixel_linear(io.tm, __float_as_uint(io.sh_c[ray_index].w) % (uint32_t)io.tm.local_pixels);
                 }
                 sp = 0;
                 leaf = 0;

@@ -13,6 +13,8 @@ GEOMETRY_FLAGS_NOALPHA = 0x01
 RNG_VARIANT_UNIFORM, RNG_VARIANT_BN, RNG_VARIANT_SOBOL, RNG_VARIANT_Z_SBL = 0, 1, 2, 3  # librender/render_params.glsl.h:34-37
 MAX_PATH_DEPTH = 9
 DEFAULT_RR_PATH_DEPTH = 2
+DEFAULT_RAY_QUERY_BUDGET = 512 * 512  # librender/render_params.glsl.h:172
+LIGHT_SAMPLING_VARIANT_NONE, LIGHT_SAMPLING_VARIANT_RIS = 0, 1  # rendering/mc/light_sampling.h:11-12
 
 f32, i32, u32 = C.c_float, C.c_int32, C.c_uint32
 
@@ -49,6 +51,16 @@ class RenderParams(_Pod):
     _defaults_ = dict(batch_spp=1, max_path_depth=MAX_PATH_DEPTH, rr_path_depth=DEFAULT_RR_PATH_DEPTH, focus_distance=2.5,
                       pixel_radius=1.0, variance_radius=4.0, early_tone_mapping_mode=-1, spp_accumulation_window=8,
                       render_upscale_factor=1, focal_length=35.0)
+
+
+class RenderBackendOptions(_Pod):
+    """librender/render_params.glsl.h:73-119"""
+    _fields_ = [("rng_variant", i32), ("light_sampling_variant", i32), ("light_sampling_bucket_count", i32), ("unroll_bounces", C.c_uint8),
+                ("_pad0", C.c_uint8 * 3), ("render_upscale_factor", i32), ("enable_rayqueries", C.c_uint8), ("force_bvh_rebuild", C.c_uint8),
+                ("_pad1", C.c_uint8 * 2), ("rebuild_triangle_budget", i32), ("enable_taa", C.c_uint8), ("enable_raytraced_dof", C.c_uint8),
+                ("_pad2", C.c_uint8 * 2)]
+    _defaults_ = dict(rng_variant=0, light_sampling_variant=1, light_sampling_bucket_count=16, render_upscale_factor=1,
+                      rebuild_triangle_budget=500000, enable_raytraced_dof=1)
 
 
 class LightSamplingConfig(_Pod):
@@ -128,4 +140,4 @@ class SceneDesc(_Pod):
 
 assert C.sizeof(BaseMaterial) == 80 and C.sizeof(RenderParams) == 80 and C.sizeof(LightSamplingConfig) == 16
 assert C.sizeof(SceneConfig) == 32 and C.sizeof(RenderRayQuery) == 32 and C.sizeof(TriLightData) == 48
-assert C.sizeof(RenderCameraParams) == 40 and C.sizeof(SceneParams) == 208
+assert C.sizeof(RenderCameraParams) == 40 and C.sizeof(SceneParams) == 208 and C.sizeof(RenderBackendOptions) == 32

@@ -4,6 +4,7 @@
 // tests/test_hostsim_parity.py can check -- without a GPU -- that the code the kernels execute agrees bit for bit with
 // the independent oracle.  The wavefront kernels themselves (queues, atomics, resolve) are covered by the -m gpu tests.
 #include "../../realtimepathtracingresearchframework_b200/csrc/rptr_host.hpp"
+#include <cmath>
 #include <cstring>
 
 using namespace rp;
@@ -208,6 +209,51 @@ uint32_t hostsim_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, 
 }
 
 } // extern "C"
+
+// render_ray_queries through the product's shared code: one sample layer (sample index `layer`, accumulation_frame_offset = 0)
+// of every query; the query's "pixel" comes from the product's TileMap in query mode (tile_pixel).  out = 4 floats per query.
+extern "C" int hostsim_ray_query_layer(const hostsim_scene *s, const hostsim_args *a, const rptr_render_ray_query *queries, int32_t n, uint32_t layer, float *out) {
+    FrameParams fp = make_frame(s, a);
+    SceneDev sc{s->gi.data(), s->hs.materials.data(), s->hs.lights.data(), reinterpret_cast<const float4 *>(s->hs.normal_texels.data())};
+    BvhDev bvh{s->hs.nodes.data(), s->hs.leaf_tris.data(), (int32_t)s->hs.nodes.size(), (int32_t)s->hs.leaf_tris.size()};
+    TileMap tm{};
+    tm.width = a->width; tm.height = a->height; tm.world = 1; tm.rows = 1; tm.local_pixels = n;
+    tm.query_wgs_x = ((int)ceilf(sqrtf((float)n)) + 31) / 32;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int32_t q = 0; q < n; ++q) {
+        uint32_t px, py;
+        tile_pixel(tm, (uint32_t)q, px, py);
+        PathState ps;
+        generate_primary(fp, (int)px, (int)py, layer, ps);
+        ps.o = f3(queries[q].origin[0], queries[q].origin[1], queries[q].origin[2]);
+        ps.d = f3(queries[q].dir[0], queries[q].dir[1], queries[q].dir[2]);
+        ps.tmax = queries[q].t_max;
+        uint32_t alpha_lcg = alpha_lcg_seed(fp, (int)px, (int)py, layer);
+        TraceCounters cnt{0, 0};
+        for (;;) {
+            HitRec h;
+            bool found = closest_hit_filtered(bvh, ps.o, ps.d, ps.tmin, ps.tmax, fp.rng_variant == 0 ? ps.rng : alpha_lcg, h, cnt);
+            ShadowRay sh;
+            ShadeResult r = shade_vertex(fp, sc, ps, h.t, h.u, h.v, found ? &bvh.tris[h.tri] : nullptr, sh, nullptr);
+            if (sh.tmax > 0.0f) {
+                HitRec o;
+                const AlphaFilter af{sc.ginst, fp.first_sample, fp.frame_offset, tile_pixel_linear(tm, (uint32_t)q)};
+                if (!trace_ray<true>(bvh, sh.o, sh.d, sh.tmin, sh.tmax, o, cnt, sh.tmin, 0x7fffffff, &af)) ps.illum = ps.illum + sh.contrib;
+            }
+            if (r == SHADE_TERMINATE) break;
+        }
+        out[4 * q + 0] = ps.illum.x; out[4 * q + 1] = ps.illum.y; out[4 * q + 2] = ps.illum.z; out[4 * q + 3] = ps.bounce == 0 ? 0.0f : 1.0f;
+    }
+    return 0;
+}
+
+// the product's query -> sampler pixel map (TileMap in query mode, csrc/rptr_shading.cuh); wgs_x as rptr_cuda_render_ray_queries computes it
+extern "C" void hostsim_query_pixel(uint32_t q, int32_t n, uint32_t *out) {
+    TileMap tm{};
+    tm.width = 1; tm.world = 1; tm.rows = 1; tm.local_pixels = n;
+    tm.query_wgs_x = ((int)std::ceil(std::sqrt((float)n)) + 31) / 32;
+    tile_pixel(tm, q, out[0], out[1]);
+}
 
 // RQ_CLOSEST through the product's traversal code (tmin = q.mode_or_data reinterpreted as float when any != 0)
 extern "C" int hostsim_trace(const hostsim_scene *s, const rptr_render_ray_query *q, int32_t n, float *results, float *hit_t, int32_t any) {

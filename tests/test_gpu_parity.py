@@ -730,7 +730,7 @@ def test_smooth_shaded_scene_vertex_normals_and_uvs(oracle):
         assert np.array_equal(r.aov(1).view(np.uint16), nd.astype(np.float16).view(np.uint16))
 
 
-C2_BENCH_FRAME_SHA256 = None  # filled in below once the oracle image of the bench configuration is known
+C2_BENCH_FRAME_SHA256 = "497d83b93ba10b4eadcc76aac15994af8f04c8636025b7dfc456ee91a7549545"  # oracle image of the bench configuration (computed on the CPU, 245 s on 8 cores); bench.py prints the same value as framebuffer_sha256
 
 
 def test_c2_bench_configuration_full_frame(oracle, c2_scene):
@@ -786,3 +786,131 @@ def test_c4_full_size_window_against_oracle(oracle):
     oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(T.SceneConfig(**sky)), spp=16, batch_spp=16, transmission=1, region=(x0, y0, x1, y1), out=ref)
     assert (ref[y0:y1, x0:x1, 3] > 0).mean() > 0.05
     assert_identical(img[y0:y1, x0:x1], ref[y0:y1, x0:x1], "C4 full size window, 16 spp")
+
+
+def test_render_ray_queries_through_the_integrator(oracle):
+    """RenderBackend::enable_ray_queries / render_ray_queries (librender/render_backend.h:101-102; SURVEY 3.5): the path tracer on
+    caller-supplied rays with the per-query fold of accumulate_query, against the oracle -- LCG and Sobol samplers, alpha-tested
+    occluders (per-candidate shadow seeds from the query's invocation id), emissive triangles, batches split into waves."""
+    from test_hostsim_parity import emissive_soup, random_path_queries
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    sp = load_sky_fit(T.SceneConfig(**sky))
+    W, H = 160, 90
+    for make, box, n in ((lambda: scenes.alpha_tested_soup(20000), 5.0, 20011), (emissive_soup, 4.0, 5000)):
+        s = make()
+        o = oracle.OracleScene(s)
+        r = make_backend(s, W, H, sky)
+        r.enable_ray_queries(32768, 0)
+        assert r.ray_query_capacity() == 32768
+        q = random_path_queries(n, 3, box)
+        r.write_ray_queries(q)
+        with pytest.raises(RptrError):
+            r.render_ray_queries(n)  # no view yet: it renders with the last begin_frame's view_params / RenderParams
+        r.render_spp(s.camera, 3)  # third frame began with frame_id 2
+        before = r.framebuffer()
+        r.render_ray_queries(n)
+        res = r.read_ray_results(n)
+        ref = o.render_ray_queries(W, H, s.camera, sp, q, view_frame_id=2, batch_spp=1)
+        assert np.isfinite(ref).all() and (ref[:, 3] > 0).mean() > 0.2
+        assert np.array_equal(res.view(np.uint32), ref.view(np.uint32)), "%d queries differ" % (res != ref).any(-1).sum()
+        assert r.frame_state() == (3, 0, 3) and np.array_equal(before, r.framebuffer())  # counters and accumulator untouched
+        # a batch of 5 layers in waves of 2 + 2 + 1: layer 0 stores, layers k > 0 add the updated mean (accumulate.glsl:32-42)
+        r.set_option("wave_paths", 2 * n)
+        r.render_spp(s.camera, 5, batch_spp=5)  # reset: frame_offset = 3, the frame began with frame_id 0
+        r.params.batch_spp = 5
+        r.render_ray_queries(n)
+        ref5 = o.render_ray_queries(W, H, s.camera, sp, q, view_frame_id=0, frame_offset=3, batch_spp=5)
+        assert np.array_equal(r.read_ray_results(n).view(np.uint32), ref5.view(np.uint32))
+        assert not np.array_equal(ref5, ref)
+        # a sub-range of the buffer, rewritten in place
+        r.params.batch_spp = 1
+        r.render_spp(s.camera, 1, batch_spp=1)  # frame_offset = 8
+        r.write_ray_queries(q[100:300][::-1], first=50)
+        r.render_ray_queries(250)
+        q2 = q.copy()
+        q2[50:250] = q[100:300][::-1]
+        ref2 = o.render_ray_queries(W, H, s.camera, sp, q2[:250], view_frame_id=0, frame_offset=8, batch_spp=1)
+        assert np.array_equal(r.read_ray_results(250).view(np.uint32), ref2.view(np.uint32))
+        with pytest.raises(RptrError):
+            r.write_ray_queries(q, first=32768 - 10)
+        with pytest.raises(RptrError):
+            r.render_ray_queries(32769)
+        r.close()
+    # Sobol sampler + the per-pixel budget, which follows the frame size (vulkan/render_vulkan.cpp:366-369, 440-441)
+    from realtimepathtracingresearchframework_b200 import load_pointset_tables
+    tables = load_pointset_tables()
+    s = scenes.alpha_tested_soup(20000)
+    o = oracle.OracleScene(s)
+    r = make_backend(s, W, H, sky)
+    r.enable_ray_queries(100, 2)
+    assert r.ray_query_capacity() == 2 * W * H
+    r.initialize(64, 48)
+    assert r.ray_query_capacity() == 2 * 64 * 48
+    r.set_rng_variant(T.RNG_VARIANT_SOBOL, tables)
+    r.render_spp(s.camera, 2)
+    q = random_path_queries(6000, 8, 5.0)
+    r.write_ray_queries(q)
+    r.render_ray_queries(6000)
+    ref = o.render_ray_queries(64, 48, s.camera, sp, q, view_frame_id=1, batch_spp=1, rng_variant=T.RNG_VARIANT_SOBOL, pointset_tables=tables)
+    assert np.array_equal(r.read_ray_results(6000).view(np.uint32), ref.view(np.uint32))
+
+
+def test_trace_rays_kernels_agree(oracle):
+    """RaytraceBackend::trace_ray through the persistent traversal kernel (default) and the one-ray-per-thread kernel
+    (option trace_kernel = 1): same bits, repeated calls reuse the cached scratch, larger calls grow it."""
+    s = scenes.random_triangles(100000)
+    a = make_backend(s, 64, 64)
+    b = make_backend(s, 64, 64, trace_kernel=1)
+    o = oracle.OracleScene(s)
+    for n, seed in ((1000, 1), (50000, 2), (700, 3), (120000, 4)):
+        q = random_queries(n, seed)
+        q.view(np.int32)[::11, 3] = -5
+        ra, ta = a.trace_ray(q)
+        rb, tb = b.trace_ray(q)
+        ro, to = o.trace_closest(q)
+        assert np.array_equal(ra.view(np.uint32), rb.view(np.uint32)) and np.array_equal(ta, tb)
+        assert np.array_equal(ra.view(np.uint32), ro.view(np.uint32)) and np.array_equal(ta, to)
+        assert (ra[::11] == 0).all()
+    far = random_queries(10, 5)
+    far[3, 0] = 1.0e4
+    with pytest.raises(RptrError):
+        a.trace_ray(far)  # outside the range the conservative box tests are guaranteed for: refused, not silently wrong
+
+
+def test_backend_options_normalize_and_configure(oracle):
+    """normalize_options / configure_for (librender/render_backend.h:84-85): unsupported RenderBackendOptions fail loudly with a
+    recovery set; supported ones switch the backend (rng_variant)."""
+    from realtimepathtracingresearchframework_b200 import load_pointset_tables
+    s = scenes.random_triangles(5000)
+    W, H = 96, 54
+    r = make_backend(s, W, H)
+    rbo = T.RenderBackendOptions()
+    assert r.configure_for(rbo)
+    for field, bad in (("light_sampling_variant", T.LIGHT_SAMPLING_VARIANT_NONE), ("render_upscale_factor", 2), ("enable_taa", 1)):
+        x = T.RenderBackendOptions()
+        setattr(x, field, bad)
+        avail = T.RenderBackendOptions()
+        assert not r.configure_for(x, 0, avail)
+        assert field in r.last_error()
+        assert getattr(avail, field) == getattr(T.RenderBackendOptions(), field)
+        assert r.configure_for(avail)
+    assert not r.configure_for(T.RenderBackendOptions(), variant_idx=3)
+    x = T.RenderBackendOptions(rng_variant=T.RNG_VARIANT_Z_SBL)
+    assert not r.configure_for(x) and "tables" in r.last_error()
+    tabs = load_pointset_tables()
+    for i in (0, 1):
+        r.set_pointset_table(i, tabs[i])
+    assert r.configure_for(x) and r.options.rng_variant == T.RNG_VARIANT_Z_SBL
+    r.render_spp(s.camera, 2)
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=2, rng_variant=T.RNG_VARIANT_Z_SBL, pointset_tables=tabs)
+    assert_identical(r.framebuffer(), ref, "configured for Z_SBL")
+    y = T.RenderBackendOptions(rng_variant=77, light_sampling_bucket_count=0)
+    r.normalize_options(y)
+    assert y.rng_variant == 0 and y.light_sampling_bucket_count == 16
+    # the camera must stay within the range the conservative box tests are guaranteed for
+    far = T.RenderCameraParams.from_buffer_copy(s.camera)
+    far.pos[2] = 1.0e4
+    with pytest.raises(RptrError):
+        r.begin_frame(None, RenderConfiguration(far, reset_accumulation=True))
+    with pytest.raises(RptrError):
+        r.set_option("wave_paths", 2 ** 31)

@@ -223,3 +223,70 @@ def test_vertex_normals_and_uvs_reach_the_shading(H, oracle):
         images[variant] = ref
     for variant in ("no_normals", "no_uvs", "no_normal_maps"):
         assert (images[variant] != images["full"]).any(-1).mean() > 0.02, variant
+
+
+def random_path_queries(n, seed, box):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((n, 8), np.float32)
+    q[:, 0:3] = rng.uniform(-box, box, (n, 3))
+    d = rng.uniform(-0.6 * box, 0.6 * box, (n, 3)) - q[:, 0:3]
+    q[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    q[:, 7] = rng.choice([1e20, 2.0 * box, 0.25 * box], n)
+    return q
+
+
+def fold_query_layers(layers):
+    """accumulate_query (vulkan/accumulate.glsl:32-42) applied layer after layer, float32."""
+    r = None
+    for k, x in enumerate(layers):
+        accum = r.copy() if k > 0 else np.zeros_like(x)
+        accum += (x - accum) / np.float32(k + 1)
+        r = accum if k == 0 else r + accum
+    return r
+
+
+def test_ray_queries_through_the_integrator(H, hostsim, oracle):
+    """render_ray_queries (vulkan/pt_megakernel.glsl:276-283, 327-334, accumulate.glsl:32-42): the product's shared
+    code -- TileMap in query mode, generate_primary + ray override, shade_vertex -- against the oracle's own statement of the
+    dispatch (virtual square, 32 x 16 workgroups, swizzled invocation id as the sampler's pixel), for a scene with alpha-tested
+    materials (per-candidate shadow seeds use the query's pixel) and emissive triangles."""
+    lib = C.CDLL(hostsim)
+    lib.hostsim_ray_query_layer.argtypes = [C.c_void_p, C.POINTER(oracle.OracleRenderArgs), C.c_void_p, C.c_int32, C.c_uint32, oracle.f32p]
+    sp = load_sky_fit(T.SceneConfig(sun_dir=(0.35, 0.8, 0.45)))
+    ls = T.LightSamplingConfig()
+    for make, box, n in ((lambda: scenes.alpha_tested_soup(6000), 5.0, 3000), (emissive_soup, 4.0, 1537)):
+        s = make()
+        o = oracle.OracleScene(s)
+        d = s.desc()
+        hs = H.hostsim_scene_create(C.byref(d), C.byref(ls))
+        q = random_path_queries(n, 21, box)
+        W, Hh = 97, 61  # the frame size only enters through the sampler's linear pixel index
+        a = o._args(W, Hh, s.camera, sp, frame_offset=5, first_sample=3)
+        layers = []
+        for k in range(3):
+            out = np.zeros((n, 4), np.float32)
+            lib.hostsim_ray_query_layer(hs, C.byref(a), q.ctypes.data, n, k, oracle._fp(out))
+            layers.append(out)
+        H.hostsim_scene_destroy(hs)
+        ref1 = o.render_ray_queries(W, Hh, s.camera, sp, q, view_frame_id=3, frame_offset=5, batch_spp=1)
+        assert np.isfinite(ref1).all() and (ref1[:, 3] > 0).mean() > 0.2 and (ref1[:, :3] > 0).any()
+        assert np.array_equal(ref1.view(np.uint32), layers[0].view(np.uint32))
+        ref3 = o.render_ray_queries(W, Hh, s.camera, sp, q, view_frame_id=3, frame_offset=5, batch_spp=3)
+        assert np.array_equal(ref3.view(np.uint32), fold_query_layers(layers).view(np.uint32))
+        # a query's sample is NOT the sample of the frame pixel with the same index: the invocation id is swizzled
+        assert not np.array_equal(ref1, ref3)
+
+
+def test_query_pixel_swizzle_is_a_permutation_of_the_dispatch():
+    """setup_pixel_assignment.glsl:17-22 maps the invocations of a 32 x 16 workgroup onto its own pixels one-to-one."""
+    lib_py = []
+    for n in (1, 511, 512, 513, 5000):
+        dim_x = int(np.ceil(np.sqrt(np.float32(n))))
+        gx_n = (dim_x + 31) // 32
+        q = np.arange(((n + 511) // 512) * 512, dtype=np.uint32)
+        wg, l = q >> 9, q & 511
+        ix, iy = (wg % gx_n) * 32 + (l & 31), (wg // gx_n) * 16 + (l >> 5)
+        sx, sy = (ix & ~np.uint32(0x18)) + ((iy & 3) << 3), (iy & ~np.uint32(3)) + ((ix & 0x18) >> 3)
+        assert len(set(zip(sx.tolist(), sy.tolist()))) == len(q)
+        assert (sx // 32 == ix // 32).all() and (sy // 16 == iy // 16).all()
+        lib_py.append((sx, sy))
