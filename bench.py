@@ -254,8 +254,13 @@ def run_b200(args):
         k, v = kv.split("=")
         r.set_option(k, int(v))
     if world > 1:
-        r.set_option("tile_world", world)
-        r.set_option("tile_rank", rank)
+        # the product's own communicator (NCCL inside librptr_cuda.so): rank 0's id travels over torch.distributed, which is
+        # plumbing here (barriers, the max over ranks of the timings)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(RenderCuda.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        r.comm_init_rank(world, rank, bytes(uid.cpu().numpy().tobytes()))  # sets tile_world / tile_rank
         r.set_option("tile_rows", 8)
     t0 = time.perf_counter()
     r.set_scene(scene)
@@ -266,14 +271,8 @@ def run_b200(args):
 
     stream = torch.cuda.ExternalStream(r.stream_handle(), device=torch.device("cuda", local))
     n_px = args.width * args.height
-    # framebuffer as a torch view of the library's accumulator (NCCL reduce) + pinned host buffer for the readback
-    fb_ptr = r.framebuffer_device_ptr()
-
-    class _Arr:
-        __cuda_array_interface__ = {"shape": (n_px * 4,), "typestr": "<f4", "data": (fb_ptr, False), "version": 3}
-    fb = torch.as_tensor(_Arr(), device=torch.device("cuda", local))
-    reduced = torch.empty_like(fb) if world > 1 else None
-    host = torch.empty(n_px * 4, dtype=torch.float32, pin_memory=True)
+    host = torch.empty(n_px * 4, dtype=torch.float32, pin_memory=True)  # pinned host buffer the framebuffer is read back into
+    host_np = host.numpy()
 
     def step(readback):
         cfg = RenderConfiguration(cam, reset_accumulation=True)
@@ -281,15 +280,13 @@ def run_b200(args):
         r.draw_frame()
         r.end_frame()
         if readback:
-            with torch.cuda.stream(stream):
-                src = fb
-                if world > 1:  # disjoint row bands: sum == gather, exact in fp32
-                    reduced.copy_(fb)
-                    dist.reduce(reduced, dst=0, op=dist.ReduceOp.SUM)
-                    src = reduced
-                if rank == 0:
-                    host.copy_(src, non_blocking=True)
-            stream.synchronize()
+            if world > 1:  # one NCCL reduce of the HDR accumulator to rank 0 (disjoint row bands: sum == gather, exact in fp32)
+                r.reduce_framebuffer(0)
+            if rank == 0:
+                if r.readback_framebuffer(host_np) != host_np.size:  # device -> pinned host, synchronises the stream
+                    raise RuntimeError("readback failed: " + r.last_error())
+            else:
+                r.flush_pipeline()
 
     def barrier():
         if world > 1:
@@ -308,7 +305,7 @@ def run_b200(args):
     # must be the same for every N (the sharded frame after the reduce is bit-identical to the 1-GPU frame)
     import hashlib
     step(True)
-    fb_sha = hashlib.sha256(host.numpy().tobytes()).hexdigest() if rank == 0 else None
+    fb_sha = hashlib.sha256(host_np.tobytes()).hexdigest() if rank == 0 else None
     for _ in range(max(0, args.warmup - 1)):
         step(True)
     # ---- device-timed region: K steps, inputs resident ----
@@ -387,7 +384,7 @@ def run_b200(args):
     line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "parallelism": "screen tiles x%d (interleaved 8-row bands), scene replicated" % world,
+            "config": {"workload": workload_name(args), "parallelism": "screen tiles x%d (interleaved 8-row bands), scene replicated, one NCCL reduce of the accumulator per readback inside librptr_cuda.so" % world,
                        "l2": "no explicit flush: per-wave path state (>1 GB) and scene+BVH (%.0f MB) exceed the 126 MB L2" % (args.tris * 110e-6),
                        "scene_setup_s": scene_s},
             "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(T.RenderCameraParams) + C.sizeof(T.RenderParams) + C.sizeof(T.LightSamplingConfig),

@@ -170,6 +170,27 @@ int rptr_cuda_render_ray_queries(rptr_ctx *ctx, int32_t num_queries, const rptr_
 int rptr_cuda_normalize_options(rptr_ctx *ctx, rptr_backend_options *options, int32_t variant);
 int rptr_cuda_configure_for(rptr_ctx *ctx, const rptr_backend_options *options, int32_t variant, rptr_backend_options *available);
 
+/* Multi-GPU (the reference has no multi-GPU path to mirror): one context per GPU, scene replicated, the frame
+ * sharded into interleaved bands of "tile_rows" rows (band b belongs to rank b % world; every rank seeds its pixels with the
+ * GLOBAL pixel id, so the image does not depend on the number of GPUs), and ONE collective per readback: a sum of the RGBA32F
+ * accumulators over NCCL -- ranks hold exact zeros outside their bands, so the sum is a gather, exact in fp32.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2": the copy the process already has, e.g. PyTorch's, else the system's;
+ * RPTR_NCCL_LIB overrides), so single-GPU users need none.
+ *   one process per GPU:  rank 0 calls rptr_cuda_comm_unique_id and ships the 128 bytes to the others (MPI, torch.distributed,
+ *                         a file ...); every rank calls rptr_cuda_comm_init_rank; per readback every rank calls
+ *                         rptr_cuda_reduce_framebuffer(root) and the root (every rank for root < 0 = all-reduce) reads the whole
+ *                         image with rptr_cuda_readback_f32.
+ *   one process, n GPUs:  (the reference's single render thread) rptr_cuda_comm_init_all over the n contexts, frames issued
+ *                         context by context (all calls are asynchronous), rptr_cuda_reduce_framebuffer_all per readback.
+ * comm_init sets the options tile_world / tile_rank; the reduce is enqueued on the context's stream (no host sync) and stays
+ * valid until the next draw_frame. */
+int rptr_cuda_comm_unique_id(void *id, size_t bytes);
+int rptr_cuda_comm_init_rank(rptr_ctx *ctx, int32_t world, int32_t rank, const void *id, size_t bytes);
+int rptr_cuda_comm_init_all(rptr_ctx **ctxs, int32_t n);
+int rptr_cuda_comm_destroy(rptr_ctx *ctx);
+int rptr_cuda_reduce_framebuffer(rptr_ctx *ctx, int32_t root);
+int rptr_cuda_reduce_framebuffer_all(rptr_ctx **ctxs, int32_t n, int32_t root);
+
 /* util/write_image.cpp:34-66 (WriteImage::write_pfm): "<prefix>.pfm", RGB, bottom row first, little-endian.
  * Pure host helper so validation mode (libapp/app_state.cpp:362-388) can be replayed without the app. */
 int rptr_write_pfm(const char *prefix, uint32_t width, uint32_t height, uint32_t channels, const float *pixels);

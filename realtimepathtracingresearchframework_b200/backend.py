@@ -28,6 +28,8 @@ ABI_SYMBOLS = [
     "rptr_cuda_trace_rays", "rptr_cuda_set_pointset_table", "rptr_cuda_readback_aov",
     "rptr_cuda_enable_ray_queries", "rptr_cuda_ray_query_buffers", "rptr_cuda_write_ray_queries", "rptr_cuda_read_ray_results",
     "rptr_cuda_render_ray_queries", "rptr_cuda_normalize_options", "rptr_cuda_configure_for",
+    "rptr_cuda_comm_unique_id", "rptr_cuda_comm_init_rank", "rptr_cuda_comm_init_all", "rptr_cuda_comm_destroy",
+    "rptr_cuda_reduce_framebuffer", "rptr_cuda_reduce_framebuffer_all",
     "rptr_write_pfm",
 ]
 
@@ -100,6 +102,12 @@ def load_library(path=None):
     L.rptr_cuda_render_ray_queries.argtypes = [vp, i32, C.POINTER(T.RenderParams), i32]
     L.rptr_cuda_normalize_options.argtypes = [vp, C.POINTER(T.RenderBackendOptions), i32]
     L.rptr_cuda_configure_for.argtypes = [vp, C.POINTER(T.RenderBackendOptions), i32, C.POINTER(T.RenderBackendOptions)]
+    L.rptr_cuda_comm_unique_id.argtypes = [vp, C.c_size_t]
+    L.rptr_cuda_comm_init_rank.argtypes = [vp, i32, i32, vp, C.c_size_t]
+    L.rptr_cuda_comm_init_all.argtypes = [C.POINTER(vp), i32]
+    L.rptr_cuda_comm_destroy.argtypes = [vp]
+    L.rptr_cuda_reduce_framebuffer.argtypes = [vp, i32]
+    L.rptr_cuda_reduce_framebuffer_all.argtypes = [C.POINTER(vp), i32, i32]
     L.rptr_write_pfm.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     if path is None:
         _lib = L
@@ -296,6 +304,37 @@ class RenderCuda:
         p = C.c_void_p()
         self._check(self._L.rptr_cuda_stream_handle(self._h, C.byref(p)))
         return p.value or 0
+
+    # -- multi-GPU: screen-space sharding + one NCCL reduce per readback (include/rptr_cuda.h) -----------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes from rank 0, to be shipped to every rank (torch.distributed, MPI, a file ...)."""
+        buf = C.create_string_buffer(128)
+        L = load_library()
+        if L.rptr_cuda_comm_unique_id(buf, 128) != 0:
+            raise RptrError(L.rptr_cuda_last_error(None).decode())
+        return buf.raw
+
+    def comm_init_rank(self, world, rank, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._L.rptr_cuda_comm_init_rank(self._h, int(world), int(rank), buf, 128))
+
+    @staticmethod
+    def comm_init_all(backends):
+        """One process driving several GPUs: a communicator over the given backends (rank = position in the list)."""
+        arr = (C.c_void_p * len(backends))(*[b._h for b in backends])
+        if backends[0]._L.rptr_cuda_comm_init_all(arr, len(backends)) != 0:
+            raise RptrError(backends[0].last_error())
+
+    def reduce_framebuffer(self, root=0):
+        """Collective: every rank calls it; afterwards readback on `root` (every rank for root < 0) returns the whole image."""
+        self._check(self._L.rptr_cuda_reduce_framebuffer(self._h, int(root)))
+
+    @staticmethod
+    def reduce_framebuffer_all(backends, root=0):
+        arr = (C.c_void_p * len(backends))(*[b._h for b in backends])
+        if backends[0]._L.rptr_cuda_reduce_framebuffer_all(arr, len(backends), int(root)) != 0:
+            raise RptrError(backends[0].last_error())
 
     # -- options (librender/render_backend.h:84-85) ---------------------------------------------------------------------
     def normalize_options(self, rbo, variant_idx=0):

@@ -9,6 +9,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (RPTR-FP contract, see rptr_math.cuh).
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <dlfcn.h>
 
 #include <chrono>
 #include <cmath>
@@ -562,6 +563,11 @@ struct rptr_ctx {
     float4 *rq_results = nullptr;                // ray_result_buffer
     size_t rq_capacity = 0;
     std::vector<void *> rq_allocs;
+    // multi-GPU: screen-space sharding + one NCCL reduce of the HDR accumulator per readback
+    void *comm = nullptr;          // ncclComm_t
+    int comm_world = 1, comm_rank = 0;
+    float4 *reduced = nullptr;     // result of the last reduce (the accumulator itself must keep this rank's partial image)
+    bool reduced_valid = false;    // a reduce has run since the last frame: readback_f32 then returns the whole image
     // scratch of the RaytraceBackend service (rptr_cuda_trace_rays), grown on demand and kept
     std::vector<void *> tr_allocs;
     size_t tr_capacity = 0;
@@ -761,8 +767,10 @@ void rptr_cuda_destroy(rptr_ctx *ctx) {
     free_all(ctx, ctx->rq_allocs);
     free_all(ctx, ctx->tr_allocs);
     for (uint32_t *t : ctx->pointset_tables) cudaFree(t);
+    rptr_cuda_comm_destroy(ctx);
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
+    cudaFree(ctx->reduced);
     for (ushort4 *im : ctx->aov_images) cudaFree(im);
     cudaFree(ctx->dcounters);
     cudaEventDestroy(ctx->ev_begin);
@@ -785,6 +793,9 @@ int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height) {
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
+    cudaFree(ctx->reduced);
+    ctx->reduced = nullptr;
+    ctx->reduced_valid = false;
     for (ushort4 *im : ctx->aov_images) cudaFree(im);
     ctx->accum = nullptr;
     ctx->ldr = nullptr;
@@ -1241,6 +1252,7 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
     CU(cudaSetDevice(ctx->device));
     const TileMap tm = make_tilemap(ctx);
     FrameParams fp = make_frame_params(ctx);
+    ctx->reduced_valid = false;
     CU(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (render_waves(ctx, fp, tm, fp.batch, fp.first_sample, nullptr, nullptr)) return 1;
     CU(cudaGetLastError());
@@ -1346,7 +1358,9 @@ size_t rptr_cuda_readback_f32(rptr_ctx *ctx, size_t n_elems, float *dst) {
     const size_t size = (size_t)ctx->width * ctx->height * 4;
     if (n_elems < size) return 0; // vulkan/render_vulkan.cpp:2262-2263
     if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
-    if (cudaMemcpyAsync(dst, ctx->accum, size * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
+    // sharded over several GPUs: after rptr_cuda_reduce_framebuffer the whole image, otherwise this rank's bands
+    const float4 *src = (ctx->reduced && ctx->reduced_valid) ? ctx->reduced : ctx->accum;
+    if (cudaMemcpyAsync(dst, src, size * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         fail(ctx, "readback failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 0;
@@ -1593,6 +1607,151 @@ int rptr_cuda_configure_for(rptr_ctx *ctx, const rptr_backend_options *o, int32_
     // what the reference does at the end of a successful configure_for when built without ENABLE_REALTIME_RESOLVE
     // (render_vulkan.cpp:1911-1915) -- params.reprojection_mode = NONE -- is left to the caller's RenderParams here
     return 0;
+}
+
+// ---- multi-GPU: NCCL, loaded at run time ---------------------------------------------------------------------------------------
+// The library does not link NCCL: a process that never shards a frame does not need it, and a host that already carries one
+// (PyTorch bundles its own libnccl.so.2) must not get a second copy.  dlopen("libnccl.so.2") returns the copy the process has
+// loaded, else the system's; RPTR_NCCL_LIB overrides the path.
+namespace {
+struct NcclId { char b[128]; }; // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed to ncclCommInitRank by value
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string error;
+};
+NcclApi g_nccl;
+bool load_nccl() {
+    if (g_nccl.lib) return true;
+    const char *names[] = {std::getenv("RPTR_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+        g_nccl.error = dlerror();
+    }
+    if (!g_nccl.lib) return false;
+    bool ok = true;
+    auto sym = [&](const char *name) {
+        void *p = dlsym(g_nccl.lib, name);
+        if (!p) { ok = false; g_nccl.error = std::string("missing symbol ") + name; }
+        return p;
+    };
+    *(void **)&g_nccl.GetUniqueId = sym("ncclGetUniqueId");
+    *(void **)&g_nccl.CommInitRank = sym("ncclCommInitRank");
+    *(void **)&g_nccl.CommInitAll = sym("ncclCommInitAll");
+    *(void **)&g_nccl.CommDestroy = sym("ncclCommDestroy");
+    *(void **)&g_nccl.Reduce = sym("ncclReduce");
+    *(void **)&g_nccl.AllReduce = sym("ncclAllReduce");
+    *(void **)&g_nccl.GroupStart = sym("ncclGroupStart");
+    *(void **)&g_nccl.GroupEnd = sym("ncclGroupEnd");
+    *(void **)&g_nccl.GetErrorString = sym("ncclGetErrorString");
+    if (!ok) { dlclose(g_nccl.lib); g_nccl.lib = nullptr; }
+    return ok;
+}
+const int kNcclFloat = 7, kNcclSum = 0; // ncclFloat32, ncclSum (nccl.h)
+int attach_comm(rptr_ctx *ctx, void *comm, int world, int rank) {
+    if (ctx->in_frame) return fail(ctx, "comm_init inside begin_frame/end_frame");
+    if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = comm;
+    ctx->comm_world = world;
+    ctx->comm_rank = rank;
+    ctx->tile_world = world; // interleaved bands of tile_rows rows: band b belongs to rank b % world
+    ctx->tile_rank = rank;
+    return 0;
+}
+int enqueue_reduce(rptr_ctx *ctx, int root) {
+    if (!ctx->accum) return fail(ctx, "reduce_framebuffer before initialize");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, "cudaSetDevice failed");
+    const size_t n = (size_t)ctx->width * ctx->height;
+    const bool receives = root < 0 || root == ctx->comm_rank;
+    if (receives && !ctx->reduced && cudaMalloc((void **)&ctx->reduced, n * sizeof(float4)) != cudaSuccess) return fail(ctx, "out of memory for the reduced framebuffer");
+    // ranks own disjoint bands and hold exact zeros elsewhere (initialize clears the accumulator, a rank only ever writes its
+    // own pixels): the sum over ranks is a gather, exact in fp32 whatever the reduction order
+    const int rc = root < 0 ? g_nccl.AllReduce(ctx->accum, ctx->reduced, 4 * n, kNcclFloat, kNcclSum, ctx->comm, ctx->stream)
+                            : g_nccl.Reduce(ctx->accum, receives ? ctx->reduced : nullptr, 4 * n, kNcclFloat, kNcclSum, root, ctx->comm, ctx->stream);
+    if (rc != 0) return fail(ctx, "NCCL reduce failed: %s", g_nccl.GetErrorString(rc));
+    ctx->reduced_valid = receives;
+    return 0;
+}
+} // namespace
+
+int rptr_cuda_comm_unique_id(void *id, size_t bytes) {
+    if (!id || bytes < 128) return fail(nullptr, "comm_unique_id: need a 128-byte buffer");
+    if (!load_nccl()) return fail(nullptr, "cannot load NCCL (%s)", g_nccl.error.c_str());
+    const int rc = g_nccl.GetUniqueId(id);
+    if (rc != 0) return fail(nullptr, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+    return 0;
+}
+
+int rptr_cuda_comm_init_rank(rptr_ctx *ctx, int32_t world, int32_t rank, const void *id, size_t bytes) {
+    if (!ctx) return 1;
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, "comm_init_rank: rank %d outside world %d", rank, world);
+    if (!id || bytes < 128) return fail(ctx, "comm_init_rank: need the 128-byte id of rptr_cuda_comm_unique_id");
+    if (!load_nccl()) return fail(ctx, "cannot load NCCL (%s)", g_nccl.error.c_str());
+    CU(cudaSetDevice(ctx->device));
+    NcclId nid;
+    memcpy(nid.b, id, 128);
+    void *comm = nullptr;
+    const int rc = g_nccl.CommInitRank(&comm, world, nid, rank);
+    if (rc != 0) return fail(ctx, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+    return attach_comm(ctx, comm, world, rank);
+}
+
+int rptr_cuda_comm_init_all(rptr_ctx **ctxs, int32_t n) {
+    if (!ctxs || n < 1) return 1;
+    for (int i = 0; i < n; ++i)
+        if (!ctxs[i]) return 1;
+    if (!load_nccl()) return fail(ctxs[0], "cannot load NCCL (%s)", g_nccl.error.c_str());
+    std::vector<int> devs(n);
+    std::vector<void *> comms(n, nullptr);
+    for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+    const int rc = g_nccl.CommInitAll(comms.data(), n, devs.data());
+    if (rc != 0) return fail(ctxs[0], "ncclCommInitAll: %s", g_nccl.GetErrorString(rc));
+    for (int i = 0; i < n; ++i)
+        if (attach_comm(ctxs[i], comms[i], n, i)) return 1;
+    return 0;
+}
+
+int rptr_cuda_comm_destroy(rptr_ctx *ctx) {
+    if (!ctx) return 1;
+    if (ctx->comm) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    ctx->comm_world = 1;
+    ctx->comm_rank = 0;
+    ctx->reduced_valid = false;
+    return 0;
+}
+
+int rptr_cuda_reduce_framebuffer(rptr_ctx *ctx, int32_t root) {
+    if (!ctx) return 1;
+    if (!ctx->comm) return fail(ctx, "reduce_framebuffer without a communicator (rptr_cuda_comm_init_rank / _all)");
+    if (root >= ctx->comm_world) return fail(ctx, "reduce_framebuffer: root %d outside world %d", root, ctx->comm_world);
+    return enqueue_reduce(ctx, root);
+}
+
+int rptr_cuda_reduce_framebuffer_all(rptr_ctx **ctxs, int32_t n, int32_t root) {
+    if (!ctxs || n < 1 || !ctxs[0]) return 1;
+    for (int i = 0; i < n; ++i)
+        if (!ctxs[i] || !ctxs[i]->comm || ctxs[i]->comm_world != n) return fail(ctxs[0], "reduce_framebuffer_all: context %d is not part of a communicator of %d", i, n);
+    g_nccl.GroupStart(); // one thread drives every device of the process
+    int bad = 0;
+    for (int i = 0; i < n; ++i) bad |= enqueue_reduce(ctxs[i], root);
+    const int rc = g_nccl.GroupEnd();
+    if (rc != 0) return fail(ctxs[0], "ncclGroupEnd: %s", g_nccl.GetErrorString(rc));
+    return bad;
 }
 
 int rptr_write_pfm(const char *prefix, uint32_t width, uint32_t height, uint32_t channels, const float *pixels) {

@@ -914,3 +914,42 @@ def test_backend_options_normalize_and_configure(oracle):
         r.begin_frame(None, RenderConfiguration(far, reset_accumulation=True))
     with pytest.raises(RptrError):
         r.set_option("wave_paths", 2 ** 31)
+
+
+def test_nccl_reduce_inside_the_library_two_devices():
+    """The multi-GPU path of the product itself (include/rptr_cuda.h, "Multi-GPU"): two contexts of ONE process on two GPUs, a
+    communicator from rptr_cuda_comm_init_all (NCCL loaded by the library), interleaved bands, one reduce per readback: the
+    root's readback is bit-identical to the single-GPU frame, for a reduce to rank 0, to rank 1 and an all-reduce; progressive
+    accumulation keeps working after a reduce (the reduce must not disturb the per-rank accumulators)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = scenes.random_triangles(20000)
+    W, H = 200, 117
+    full = make_backend(s, W, H)
+    full.render_spp(s.camera, 2)
+    want2 = full.framebuffer()
+    full.render_spp(s.camera, 2, reset=False)
+    want4 = full.framebuffer()
+    rs = []
+    for dev in range(2):
+        r = RenderCuda(device=dev)
+        r.initialize(W, H)
+        r.set_scene(s)
+        r.update_config()
+        rs.append(r)
+    RenderCuda.comm_init_all(rs)
+    for r in rs:
+        r.render_spp(s.camera, 2)
+    parts = [r.framebuffer() for r in rs]  # before any reduce: each rank's own bands
+    assert np.array_equal((parts[0] + parts[1]).view(np.uint32), want2.view(np.uint32))
+    RenderCuda.reduce_framebuffer_all(rs, root=0)
+    assert np.array_equal(rs[0].framebuffer().view(np.uint32), want2.view(np.uint32))
+    assert np.array_equal(rs[1].framebuffer().view(np.uint32), parts[1].view(np.uint32))  # not the root: still its own bands
+    RenderCuda.reduce_framebuffer_all(rs, root=1)
+    assert np.array_equal(rs[1].framebuffer().view(np.uint32), want2.view(np.uint32))
+    for r in rs:
+        r.render_spp(s.camera, 2, reset=False)  # two more samples on top: the accumulators were left alone by the reduces
+    RenderCuda.reduce_framebuffer_all(rs, root=-1)
+    for r in rs:
+        assert np.array_equal(r.framebuffer().view(np.uint32), want4.view(np.uint32))
