@@ -146,11 +146,13 @@ __device__ __forceinline__ float half_area(const Box &b) {
     return dx * dy + dy * dz + dz * dx;
 }
 
-// one wide node per queue entry; children that still hold more than 4 triangles go to the next level's queue
+// one wide node per queue entry: opens the largest inner child until eight are held, assigns slots, claims consecutive node
+// indices of the next level for its inner children and consecutive records of the leaf-order triangle array for its triangles
 __global__ void k_collapse(const int32_t *cur, int32_t cur_count, int32_t level_base, int32_t next_base, int32_t *next, uint32_t *next_count,
-                           const Node2 *nodes, const Box *node_boxes, const Box *boxes, const uint32_t *sorted, BvhNode *out, int32_t n) {
+                           uint32_t *tri_count, const Node2 *nodes, const Box *node_boxes, const Box *boxes, const uint32_t *sorted,
+                           const Tri *tris, Tri *leaf_tris, BvhNode *out, int32_t n) {
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cur_count; i += gridDim.x * blockDim.x) {
-        int32_t kids[RPTR_BVH_WIDTH];
+        int32_t kids[RPTR_BVH_WIDTH]; // >= 0: binary inner node, < 0: ~(position in the sorted triangle array)
         int nk = 0;
         const int32_t root = cur[i];
         if (n == 1) {
@@ -163,8 +165,6 @@ __global__ void k_collapse(const int32_t *cur, int32_t cur_count, int32_t level_
                 float best = -1.0f;
                 for (int k = 0; k < nk; ++k) {
                     if (kids[k] < 0) continue;
-                    const Node2 &c = nodes[kids[k]];
-                    if (c.last - c.first + 1 <= RPTR_LBVH_LEAF_MAX) continue; // becomes a leaf as a whole
                     const float a = half_area(node_boxes[kids[k]]);
                     if (a > best) { best = a; pick = k; }
                 }
@@ -174,42 +174,45 @@ __global__ void k_collapse(const int32_t *cur, int32_t cur_count, int32_t level_
                 kids[nk++] = nodes[open].right;
             }
         }
-        float clo[RPTR_BVH_WIDTH][3], chi[RPTR_BVH_WIDTH][3];
-        int32_t cref[RPTR_BVH_WIDTH];
+        float klo[RPTR_BVH_WIDTH][3], khi[RPTR_BVH_WIDTH][3];
+        int n_inner = 0, n_tri = 0;
         for (int k = 0; k < nk; ++k) {
-            Box b;
-            int32_t ref;
-            if (kids[k] < 0) { // single triangle
-                const int32_t leaf = ~kids[k];
-                b = boxes[sorted[leaf]];
-                ref = make_leaf_ref(leaf, 1);
-            } else {
-                const Node2 &c = nodes[kids[k]];
-                b = node_boxes[kids[k]];
-                const int32_t cnt = c.last - c.first + 1;
-                if (cnt <= RPTR_LBVH_LEAF_MAX) ref = make_leaf_ref(c.first, cnt);
-                else {
-                    const uint32_t pos = atomicAdd(next_count, 1u);
-                    next[pos] = kids[k];
-                    ref = next_base + (int32_t)pos;
-                }
-            }
-            for (int a = 0; a < 3; ++a) { clo[k][a] = b.lo[a]; chi[k][a] = b.hi[a]; }
-            cref[k] = ref;
+            const Box b = kids[k] < 0 ? boxes[sorted[~kids[k]]] : node_boxes[kids[k]];
+            for (int a = 0; a < 3; ++a) { klo[k][a] = b.lo[a]; khi[k][a] = b.hi[a]; }
+            if (kids[k] < 0) n_tri++;
+            else n_inner++;
         }
-        const BvhNode nd = encode_node(clo, chi, cref, nk);
-        out[level_base + i] = nd;
+        int slot_of[RPTR_BVH_WIDTH], kid_in[RPTR_BVH_WIDTH];
+        assign_slots(nk, klo, khi, slot_of);
+        for (int sl = 0; sl < RPTR_BVH_WIDTH; ++sl) kid_in[sl] = -1;
+        for (int k = 0; k < nk; ++k) kid_in[slot_of[k]] = k;
+        const uint32_t inner_pos = n_inner ? atomicAdd(next_count, (uint32_t)n_inner) : 0u;
+        const uint32_t tri_pos = n_tri ? atomicAdd(tri_count, (uint32_t)n_tri) : 0u;
+        float slo[RPTR_BVH_WIDTH][3], shi[RPTR_BVH_WIDTH][3];
+        int kind[RPTR_BVH_WIDTH];
+        uint32_t ri = 0, rt = 0;
+        for (int sl = 0; sl < RPTR_BVH_WIDTH; ++sl) {
+            const int k = kid_in[sl];
+            kind[sl] = 0;
+            for (int a = 0; a < 3; ++a) { slo[sl][a] = 0.0f; shi[sl][a] = 0.0f; }
+            if (k < 0) continue;
+            for (int a = 0; a < 3; ++a) { slo[sl][a] = klo[k][a]; shi[sl][a] = khi[k][a]; }
+            if (kids[k] >= 0) {
+                kind[sl] = 1;
+                next[inner_pos + ri++] = kids[k];
+            } else {
+                kind[sl] = 2;
+                leaf_tris[tri_pos + rt++] = tris[sorted[~kids[k]]];
+            }
+        }
+        out[level_base + i] = encode_node(slo, shi, kind, next_base + (int32_t)inner_pos, (int32_t)tri_pos);
     }
-}
-
-__global__ void k_gather_tris(const Tri *tris, const uint32_t *sorted, int32_t n, Tri *leaf_tris) {
-    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) leaf_tris[i] = tris[sorted[i]];
 }
 
 __global__ void k_top_planes(const BvhNode *nodes, int32_t top_k, float4 *planes) {
     // one thread per 16-byte word: word w of node i goes to plane w, slot i
-    for (int32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < top_k * 4; t += gridDim.x * blockDim.x) {
-        const int32_t i = t >> 2, w = t & 3;
+    for (int32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < top_k * RPTR_NODE_WORDS; t += gridDim.x * blockDim.x) {
+        const int32_t i = t / RPTR_NODE_WORDS, w = t % RPTR_NODE_WORDS;
         planes[w * RPTR_TOP_NODES_MAX + i] = reinterpret_cast<const float4 *>(nodes + i)[w];
     }
 }
@@ -230,7 +233,7 @@ bool build_bvh_device(const std::vector<Tri> &tris, float extent, const float *c
     Tri *d_tris = nullptr, *d_leaf = nullptr;
     Box *d_boxes = nullptr, *d_nboxes = nullptr;
     uint64_t *d_keys = nullptr, *d_keys2 = nullptr;
-    uint32_t *d_vals = nullptr, *d_sorted = nullptr, *d_arrivals = nullptr, *d_count = nullptr;
+    uint32_t *d_vals = nullptr, *d_sorted = nullptr, *d_arrivals = nullptr, *d_count = nullptr, *d_tri_count = nullptr;
     Node2 *d_nodes2 = nullptr;
     int32_t *d_leaf_parent = nullptr, *d_q[2] = {nullptr, nullptr};
     BvhNode *d_out = nullptr;
@@ -250,6 +253,8 @@ bool build_bvh_device(const std::vector<Tri> &tris, float extent, const float *c
     CUB_OK(cudaMalloc(&d_sorted, 4 * (size_t)n));
     CUB_OK(cudaMalloc(&d_arrivals, 4 * (size_t)n));
     CUB_OK(cudaMalloc(&d_count, 4));
+    CUB_OK(cudaMalloc(&d_tri_count, 4));
+    CUB_OK(cudaMemsetAsync(d_tri_count, 0, 4, stream));
     CUB_OK(cudaMalloc(&d_nodes2, sizeof(Node2) * n));
     CUB_OK(cudaMalloc(&d_leaf_parent, 4 * (size_t)n));
     CUB_OK(cudaMalloc(&d_q[0], 4 * (size_t)n));
@@ -273,7 +278,6 @@ bool build_bvh_device(const std::vector<Tri> &tris, float extent, const float *c
         k_radix_tree<<<grid, 256, 0, stream>>>(d_keys2, n, d_nodes2, d_leaf_parent);
         k_refit<<<grid, 256, 0, stream>>>(d_boxes, d_sorted, n, d_nodes2, d_leaf_parent, d_nboxes, d_arrivals);
     }
-    k_gather_tris<<<grid, 256, 0, stream>>>(d_tris, d_sorted, n, d_leaf);
     {
         // breadth-first collapse, one launch per level
         int32_t root = 0, cur_count = 1, level_base = 0, depth = 0;
@@ -284,8 +288,8 @@ bool build_bvh_device(const std::vector<Tri> &tris, float extent, const float *c
             CUB_OK(cudaMemsetAsync(d_count, 0, 4, stream));
             const int32_t next_base = level_base + cur_count;
             if ((size_t)next_base > max_nodes) { err = "device LBVH node overflow"; goto fail; }
-            k_collapse<<<grid, 128, 0, stream>>>(d_q[cur], cur_count, level_base, next_base, d_q[cur ^ 1], d_count, d_nodes2, d_nboxes, d_boxes,
-                                                 d_sorted, d_out, n);
+            k_collapse<<<grid, 128, 0, stream>>>(d_q[cur], cur_count, level_base, next_base, d_q[cur ^ 1], d_count, d_tri_count, d_nodes2, d_nboxes,
+                                                 d_boxes, d_sorted, d_tris, d_leaf, d_out, n);
             uint32_t next_count = 0;
             CUB_OK(cudaMemcpyAsync(&next_count, d_count, 4, cudaMemcpyDeviceToHost, stream));
             CUB_OK(cudaStreamSynchronize(stream));
@@ -297,8 +301,8 @@ bool build_bvh_device(const std::vector<Tri> &tris, float extent, const float *c
         out.depth = depth;
     }
     out.top_k = out.n_nodes < RPTR_TOP_NODES_MAX ? out.n_nodes : RPTR_TOP_NODES_MAX;
-    CUB_OK(cudaMalloc(&d_top, sizeof(float4) * 4 * RPTR_TOP_NODES_MAX));
-    CUB_OK(cudaMemsetAsync(d_top, 0, sizeof(float4) * 4 * RPTR_TOP_NODES_MAX, stream));
+    CUB_OK(cudaMalloc(&d_top, sizeof(float4) * RPTR_NODE_WORDS * RPTR_TOP_NODES_MAX));
+    CUB_OK(cudaMemsetAsync(d_top, 0, sizeof(float4) * RPTR_NODE_WORDS * RPTR_TOP_NODES_MAX, stream));
     if (out.top_k > 0) k_top_planes<<<64, 256, 0, stream>>>(d_out, out.top_k, d_top);
     CUB_OK(cudaStreamSynchronize(stream));
     CUB_OK(cudaGetLastError());
@@ -311,7 +315,7 @@ bool build_bvh_device(const std::vector<Tri> &tris, float extent, const float *c
     d_top = nullptr;
 fail:
     cudaFree(d_tris); cudaFree(d_leaf); cudaFree(d_boxes); cudaFree(d_nboxes); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals);
-    cudaFree(d_sorted); cudaFree(d_arrivals); cudaFree(d_count); cudaFree(d_nodes2); cudaFree(d_leaf_parent); cudaFree(d_q[0]); cudaFree(d_q[1]);
+    cudaFree(d_sorted); cudaFree(d_arrivals); cudaFree(d_count); cudaFree(d_tri_count); cudaFree(d_nodes2); cudaFree(d_leaf_parent); cudaFree(d_q[0]); cudaFree(d_q[1]);
     cudaFree(d_out); cudaFree(d_top); cudaFree(d_tmp);
     if (err) {
         error = err;

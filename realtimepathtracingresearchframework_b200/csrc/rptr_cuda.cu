@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, const ush
 // ---------------------------------------------------------------------------------------------------------------------
 static thread_local std::string g_create_error;
 
+#define RPTR_MAX_PIPES 4
 struct rptr_ctx {
     int device = 0;
     int num_sms = 0;
@@ -495,6 +496,12 @@ struct rptr_ctx {
     cudaStream_t stream2 = nullptr; // option "overlap_shadow": the shadow launch of bounce d runs beside the closest-hit launch of d + 1
     cudaEvent_t ev_shade = nullptr, ev_shadow = nullptr;
     int overlap_shadow = 1;
+    // sub-waves in flight side by side (render_waves): pipe 0 = stream / stream2 above
+    struct Pipe { cudaStream_t s_main = nullptr, s_shadow = nullptr; cudaEvent_t ev_shade = nullptr, ev_shadow = nullptr, ev_done = nullptr; };
+    Pipe pipes[RPTR_MAX_PIPES];
+    int n_pipes_ready = 0;
+    cudaEvent_t ev_round = nullptr;
+    int concurrent_waves = 1; // measured: two sub-waves side by side cost 3 % at 64 spp and 9 % at 8 spp on one GPU (profiles/r02_sweeps.md)
     std::string error;
     // framebuffer
     int32_t width = 0, height = 0;
@@ -659,11 +666,27 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     CU(dev_alloc(ctx, &w.sh_c, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.queue[0], n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.queue[1], n, ctx->wave_allocs));
-    CU(dev_alloc(ctx, &w.counts, (size_t)4 * (depth + 2), ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.counts, (size_t)4 * (depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs)); // per sub-wave
     CU(dev_alloc(ctx, &w.hitq, n, ctx->wave_allocs));
-    CU(dev_alloc(ctx, &w.hit_counts, (size_t)(depth + 2), ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.hit_counts, (size_t)(depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs));
     ctx->wave_capacity = paths;
     ctx->wave_depth = depth;
+    return 0;
+}
+
+static int ensure_pipes(rptr_ctx *ctx, int n) {
+    if (!ctx->ev_round) CU(cudaEventCreateWithFlags(&ctx->ev_round, cudaEventDisableTiming));
+    for (int k = ctx->n_pipes_ready; k < n; ++k) {
+        rptr_ctx::Pipe &p = ctx->pipes[k];
+        CU(cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming));
+        if (k > 0) {
+            CU(cudaStreamCreateWithFlags(&p.s_main, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithFlags(&p.s_shadow, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&p.ev_shade, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p.ev_shadow, cudaEventDisableTiming));
+        }
+        ctx->n_pipes_ready = k + 1;
+    }
     return 0;
 }
 
@@ -681,16 +704,17 @@ struct StageTimer {
     rptr_ctx *ctx;
     cudaEvent_t a = nullptr, b = nullptr;
     int stage;
-    StageTimer(rptr_ctx *c, int s) : ctx(c), stage(s) {
+    cudaStream_t stream;
+    StageTimer(rptr_ctx *c, int s, cudaStream_t st) : ctx(c), stage(s), stream(st) {
         if (ctx->stage_timing && s >= 0) {
             a = get_event(ctx);
             b = get_event(ctx);
-            cudaEventRecord(a, ctx->stream);
+            cudaEventRecord(a, stream);
         }
     }
     ~StageTimer() {
         if (a) {
-            cudaEventRecord(b, ctx->stream);
+            cudaEventRecord(b, stream);
             ctx->timed.push_back({a, b, stage, 1});
         }
     }
@@ -777,6 +801,14 @@ void rptr_cuda_destroy(rptr_ctx *ctx) {
     cudaEventDestroy(ctx->ev_end);
     cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (rptr_ctx::Pipe &p : ctx->pipes) {
+        if (p.s_main) cudaStreamDestroy(p.s_main);
+        if (p.s_shadow) cudaStreamDestroy(p.s_shadow);
+        if (p.ev_shade) cudaEventDestroy(p.ev_shade);
+        if (p.ev_shadow) cudaEventDestroy(p.ev_shadow);
+        if (p.ev_done) cudaEventDestroy(p.ev_done);
+    }
+    if (ctx->ev_round) cudaEventDestroy(ctx->ev_round);
     if (ctx->ev_shade) cudaEventDestroy(ctx->ev_shade);
     if (ctx->ev_shadow) cudaEventDestroy(ctx->ev_shadow);
     delete ctx;
@@ -912,9 +944,9 @@ static int upload_scene(rptr_ctx *ctx, HostScene &hs, SceneUpload &up) {
     if (!hs.leaf_tris.empty()) CU(cudaMemcpy(d_tris, hs.leaf_tris.data(), hs.leaf_tris.size() * sizeof(Tri), cudaMemcpyHostToDevice));
     // word planes of the top of the (breadth-first ordered) tree for the trace kernel's shared-memory stage
     const int32_t top_k = (int32_t)std::min<size_t>(hs.nodes.size(), RPTR_TOP_NODES_MAX);
-    std::vector<float4> top(4 * RPTR_TOP_NODES_MAX, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    std::vector<float4> top((size_t)RPTR_NODE_WORDS * RPTR_TOP_NODES_MAX, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     for (int32_t i = 0; i < top_k; ++i)
-        for (int wd = 0; wd < 4; ++wd) memcpy(&top[(size_t)wd * RPTR_TOP_NODES_MAX + i], reinterpret_cast<const unsigned char *>(&hs.nodes[i]) + (wd << 4), 16);
+        for (int wd = 0; wd < RPTR_NODE_WORDS; ++wd) memcpy(&top[(size_t)wd * RPTR_TOP_NODES_MAX + i], reinterpret_cast<const unsigned char *>(&hs.nodes[i]) + (wd << 4), 16);
     float4 *d_top;
     CU(dev_alloc(ctx, &d_top, top.size(), up.allocs));
     CU(cudaMemcpy(d_top, top.data(), top.size() * sizeof(float4), cudaMemcpyHostToDevice));
@@ -987,6 +1019,10 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
     } else if (n == "stage_timing") ctx->stage_timing = value != 0;
     else if (n == "aov_buffers") ctx->aov_buffers = value != 0;
     else if (n == "overlap_shadow") ctx->overlap_shadow = value != 0;
+    else if (n == "concurrent_waves") {
+        if (value < 1 || value > RPTR_MAX_PIPES) return fail(ctx, "concurrent_waves must be in [1, %d]", RPTR_MAX_PIPES);
+        ctx->concurrent_waves = (int)value;
+    }
     else if (n == "trace_kernel") ctx->trace_kernel = (int)value;
     else if (n == "bvh_builder") {
         if (value != 0 && value != 1) return fail(ctx, "bvh_builder must be 0 (host SAH) or 1 (device LBVH)");
@@ -1096,143 +1132,203 @@ static FrameParams make_frame_params(const rptr_ctx *ctx) {
 //   raygen -> [closest hit -> shade -> shadow] x max_path_depth -> resolve.
 // Frames resolve into the accumulator (queries == nullptr); ray queries (tm.query_wgs_x > 0) take their rays from `queries` and
 // resolve into `results` (both device arrays of tm.local_pixels entries).  sample_base = sample index of layer 0.
+//
+// Option "concurrent_waves" = k > 1 splits a wave into k SUB-WAVES of whole sample layers that are enqueued side by side, each on
+// its own pair of streams with its own queues and counters, resolved in sample order.  The idea: every launch of the bounce
+// loop ends with a tail (the longest rays of its queue) during which most SMs idle, and the persistent grids of the other
+// sub-wave could start on the SMs a kernel vacates.  Measured on the B200 it does not pay: the sub-waves double the number of
+// launches (each stages 96 KB of BVH per CTA) and halve their queues while the tails stay as long -- 64 spp: 1275 -> 1238
+// Msamples/s, 8 spp: 937 -> 851 (profiles/r02_sweeps.md).  The default is therefore 1; the option stays for experiments.
 static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm, int32_t batch, uint32_t sample_base,
                         const rptr_render_ray_query *queries, float4 *results) {
     const int depth = fp.max_path_depth;
-    if (tm.local_pixels > 0) {
-        int64_t layers_per_wave = ctx->wave_paths / tm.local_pixels;
-        if (layers_per_wave < 1) layers_per_wave = 1;
-        if (layers_per_wave > batch) layers_per_wave = batch;
-        if (ensure_wave(ctx, (size_t)layers_per_wave * tm.local_pixels, depth)) return 1;
-        Wave &w = ctx->wave;
-        // Scenes whose materials take several shading code paths (C4: GGX, thick / thin transmission, emitters): the trace kernel
-        // hands the shade stage a dense queue of the paths that hit something, which the shade kernel then sorts tile by tile
-        // by code path (C4 shade: 27.1 -> 18.8 ms per 33 M samples).  Single-path scenes (C2: all GGX) keep the bounce queue
-        // in its screen / compaction order instead -- the tile sort then only moves the misses aside -- because the
-        // retire-order hit queue costs more in scattered path-state reads than the dropped misses save (C2: 1242 -> 1170).
-        int multi_path = 0;
-        {
-            int first_key = -1;
-            for (const rptr_base_material &m : ctx->materials_host) {
-                int key = m.ior > 1.0f ? 2 : 1;
-                if (fp.transmission && m.ior > 1.0f && m.specular_transmission > 0.0f) key = (m.flags & RPTR_BASE_MATERIAL_ONESIDED) ? 4 : 3;
-                if (m.emission_intensity != 0.0f) key += 5;
-                if (first_key < 0) first_key = key;
-                else if (key != first_key) { multi_path = 1; break; }
-            }
+    if (tm.local_pixels <= 0) return 0;
+    int64_t layers_per_wave = ctx->wave_paths / tm.local_pixels;
+    if (layers_per_wave < 1) layers_per_wave = 1;
+    if (layers_per_wave > batch) layers_per_wave = batch;
+    int n_pipes = ctx->concurrent_waves < 1 ? 1 : (ctx->concurrent_waves > RPTR_MAX_PIPES ? RPTR_MAX_PIPES : ctx->concurrent_waves);
+    if (ctx->trace_kernel != 0) n_pipes = 1; // the one-ray-per-thread A/B kernels are not persistent grids: nothing to interleave
+    if (n_pipes > layers_per_wave) n_pipes = (int)layers_per_wave;
+    const int64_t layers_per_pipe = layers_per_wave / n_pipes; // whole layers per sub-wave
+    const size_t pipe_slots = (size_t)layers_per_pipe * tm.local_pixels;
+    if (ensure_wave(ctx, pipe_slots * n_pipes, depth)) return 1;
+    if (ensure_pipes(ctx, n_pipes)) return 1;
+    // Scenes whose materials take several shading code paths (C4: GGX, thick / thin transmission, emitters): the trace kernel
+    // hands the shade stage a dense queue of the paths that hit something, which the shade kernel then sorts tile by tile
+    // by code path (C4 shade: 27.1 -> 18.8 ms per 33 M samples).  Single-path scenes (C2: all GGX) keep the bounce queue
+    // in its screen / compaction order instead -- the tile sort then only moves the misses aside -- because the
+    // retire-order hit queue costs more in scattered path-state reads than the dropped misses save (C2: 1242 -> 1170).
+    int multi_path = 0;
+    {
+        int first_key = -1;
+        for (const rptr_base_material &m : ctx->materials_host) {
+            int key = m.ior > 1.0f ? 2 : 1;
+            if (fp.transmission && m.ior > 1.0f && m.specular_transmission > 0.0f) key = (m.flags & RPTR_BASE_MATERIAL_ONESIDED) ? 4 : 3;
+            if (m.emission_intensity != 0.0f) key += 5;
+            if (first_key < 0) first_key = key;
+            else if (key != first_key) { multi_path = 1; break; }
         }
-        const int sort_tiles = multi_path ? 2 : 1; // 1: the tile sort only moves the misses aside (key = hit / miss, no material lookup)
-        uint32_t *const hitq = multi_path ? w.hitq : nullptr;
-        // per-candidate seeds of alpha-tested shadow rays: view_params.frame_id / frame_offset of this frame (pt_megakernel.glsl:252-254)
-        const AlphaFilter alpha_filter{ctx->scene.ginst, fp.first_sample, fp.frame_offset, 0u};
-        // closest-hit alpha draws: the path's LCG (UNIFORM), else the separate LCG of pt_megakernel.glsl:354-358
-        uint32_t *const alpha_lcg = ctx->rng_variant != 0 ? w.rng3 : reinterpret_cast<uint32_t *>(w.rngb);
-        const uint32_t alpha_stride = ctx->rng_variant != 0 ? 1u : 2u;
-        // trace: one RPTR_TRACE_THREADS CTA per SM; dynamic smem = the staged top of the BVH + the shared stack part
-        const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4), g_pt = grid_for(ctx, 1);
-        const size_t top_smem = RPTR_TRACE_SMEM_BYTES; // staged BVH top (128 KB) + shared part of the traversal stacks (64 KB)
-        for (int32_t first = 0; first < batch; first += (int32_t)layers_per_wave) {
-            const int32_t nl = (int32_t)((batch - first) < layers_per_wave ? (batch - first) : layers_per_wave);
-            CU(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), ctx->stream));
-            CU(cudaMemsetAsync(w.hit_counts, 0, sizeof(uint32_t) * (depth + 2), ctx->stream));
-            // AOV images: written by the first vertex of the frame's last sample layer (last wave, last layer)
-            AovTarget aov{nullptr, nullptr, nullptr, 0u};
-            if (ctx->aov_buffers && !queries && first + nl == batch) aov = AovTarget{ctx->aov_images[0], ctx->aov_images[1], ctx->aov_images[2], (uint32_t)(nl - 1) * (uint32_t)tm.local_pixels};
-            {
-                StageTimer t(ctx, 3);
-                Wave wr = w;
-                if (!ctx->any_alpha_tested) wr.rng3 = nullptr; // no alpha-tested triangle: nobody reads the alpha LCG
-                k_raygen<<<g_light, 256, 0, ctx->stream>>>(fp, tm, wr, sample_base, first, nl, queries);
-                ctx->launches++;
+    }
+    const int sort_tiles = multi_path ? 2 : 1; // 1: the tile sort only moves the misses aside (key = hit / miss, no material lookup)
+    // per-candidate seeds of alpha-tested shadow rays: view_params.frame_id / frame_offset of this frame (pt_megakernel.glsl:252-254)
+    const AlphaFilter alpha_filter{ctx->scene.ginst, fp.first_sample, fp.frame_offset, 0u};
+    const uint32_t alpha_stride = ctx->rng_variant != 0 ? 1u : 2u;
+    // trace: one RPTR_TRACE_THREADS CTA per SM; dynamic smem = the staged top of the BVH + the LUT + the shared stack part
+    const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4), g_pt = grid_for(ctx, 1);
+    const size_t top_smem = RPTR_TRACE_SMEM_BYTES;
+    // smallest compiled shade variant that covers the features this frame uses (rptr_shading.cuh, RPTR_FEAT_*)
+    const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
+                     (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0) |
+                     (ctx->any_normal_map ? RPTR_FEAT_NORMAL_MAPS : 0);
+    const bool overlap = fp.output_channel == 0 && ctx->overlap_shadow && ctx->trace_kernel == 0;
+
+    struct Sub { // one sub-wave in flight
+        Wave w;
+        cudaStream_t s_main, s_shadow;
+        cudaEvent_t ev_shade, ev_shadow, ev_done;
+        int32_t first, nl;
+        AovTarget aov;
+        bool shadow_pending;
+        cudaEvent_t union_a; // stage_timing: start of the interval in which shadow(d) and closest(d + 1) of this sub-wave share the GPU
+        int union_launches;
+        uint32_t *hitq, *alpha_lcg;
+    };
+    for (int32_t round_first = 0; round_first < batch;) {
+        Sub subs[RPTR_MAX_PIPES];
+        int n_sub = 0;
+        for (int k = 0; k < n_pipes && round_first < batch; ++k) {
+            Sub &sb = subs[n_sub++];
+            sb.first = round_first;
+            sb.nl = (int32_t)((batch - round_first) < layers_per_pipe ? (batch - round_first) : layers_per_pipe);
+            round_first += sb.nl;
+            const size_t off = (size_t)k * pipe_slots;
+            const Wave &w0 = ctx->wave;
+            sb.w = w0;
+            sb.w.ray_o += off; sb.w.ray_d += off; sb.w.hit += off; sb.w.thr += off; sb.w.illum += off; sb.w.rngb += off;
+            if (w0.rng2) { sb.w.rng2 += off; sb.w.rng3 += off; }
+            sb.w.sh_o += off; sb.w.sh_d += off; sb.w.sh_c += off;
+            sb.w.queue[0] += off; sb.w.queue[1] += off; sb.w.hitq += off;
+            sb.w.counts += (size_t)k * 4 * (depth + 2);
+            sb.w.hit_counts += (size_t)k * (depth + 2);
+            sb.s_main = k == 0 ? ctx->stream : ctx->pipes[k].s_main;
+            sb.s_shadow = k == 0 ? ctx->stream2 : ctx->pipes[k].s_shadow;
+            sb.ev_shade = k == 0 ? ctx->ev_shade : ctx->pipes[k].ev_shade;
+            sb.ev_shadow = k == 0 ? ctx->ev_shadow : ctx->pipes[k].ev_shadow;
+            sb.ev_done = ctx->pipes[k].ev_done;
+            sb.shadow_pending = false;
+            sb.union_a = nullptr;
+            sb.union_launches = 0;
+            sb.hitq = multi_path ? sb.w.hitq : nullptr;
+            // closest-hit alpha draws: the path's LCG (UNIFORM), else the separate LCG of pt_megakernel.glsl:354-358
+            sb.alpha_lcg = ctx->rng_variant != 0 ? sb.w.rng3 : reinterpret_cast<uint32_t *>(sb.w.rngb);
+            // AOV images: written by the first vertex of the frame's last sample layer (last sub-wave, last layer)
+            sb.aov = AovTarget{nullptr, nullptr, nullptr, 0u};
+            if (ctx->aov_buffers && !queries && sb.first + sb.nl == batch)
+                sb.aov = AovTarget{ctx->aov_images[0], ctx->aov_images[1], ctx->aov_images[2], (uint32_t)(sb.nl - 1) * (uint32_t)tm.local_pixels};
+        }
+        if (n_sub > 1) { // the side streams start after everything enqueued on the context's stream so far
+            CU(cudaEventRecord(ctx->ev_round, ctx->stream));
+            for (int k = 1; k < n_sub; ++k) CU(cudaStreamWaitEvent(subs[k].s_main, ctx->ev_round, 0));
+        }
+        auto join_shadow = [&](Sub &sb) -> int { // the sub-wave's main stream waits for its overlapped shadow launch; closes the union interval
+            if (!sb.shadow_pending) return 0;
+            CU(cudaStreamWaitEvent(sb.s_main, sb.ev_shadow, 0));
+            sb.shadow_pending = false;
+            if (sb.union_a) {
+                cudaEvent_t e = get_event(ctx);
+                CU(cudaEventRecord(e, sb.s_main));
+                ctx->timed.push_back({sb.union_a, e, 0, sb.union_launches});
+                sb.union_a = nullptr;
             }
-            bool shadow_pending = false;
-            cudaEvent_t union_a = nullptr; // stage_timing: start of the interval in which shadow(d) and closest(d + 1) share the GPU
-            int union_launches = 0;
-            auto join_shadow = [&]() -> int { // the main stream waits for the overlapped shadow launch; closes the union interval
-                if (!shadow_pending) return 0;
-                CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_shadow, 0));
-                shadow_pending = false;
-                if (union_a) {
-                    cudaEvent_t b = get_event(ctx);
-                    CU(cudaEventRecord(b, ctx->stream));
-                    ctx->timed.push_back({union_a, b, 0, union_launches});
-                    union_a = nullptr;
-                }
-                return 0;
-            };
-            for (int d = 0; d < depth; ++d) {
+            return 0;
+        };
+        for (int k = 0; k < n_sub; ++k) {
+            Sub &sb = subs[k];
+            CU(cudaMemsetAsync(sb.w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), sb.s_main));
+            CU(cudaMemsetAsync(sb.w.hit_counts, 0, sizeof(uint32_t) * (depth + 2), sb.s_main));
+            StageTimer t(ctx, 3, sb.s_main);
+            Wave wr = sb.w;
+            if (!ctx->any_alpha_tested) wr.rng3 = nullptr; // no alpha-tested triangle: nobody reads the alpha LCG
+            k_raygen<<<g_light, 256, 0, sb.s_main>>>(fp, tm, wr, sample_base, sb.first, sb.nl, queries);
+            ctx->launches++;
+        }
+        for (int d = 0; d < depth; ++d)
+            for (int k = 0; k < n_sub; ++k) {
+                Sub &sb = subs[k];
+                Wave &w = sb.w;
                 // counts[4d] = live paths entering bounce d, [4d+1] = its shadow rays, [4d+2], [4d+3] = fetch cursors
                 const uint32_t *q = d == 0 ? nullptr : w.queue[d & 1];
                 uint32_t *nq = w.queue[(d + 1) & 1];
                 uint32_t *cn = w.counts + 4 * d;
                 {
                     // inside a union interval the closest-hit launch is timed together with the shadow launch it overlaps
-                    StageTimer t(ctx, union_a ? -1 : 0);
-                    if (union_a) union_launches++;
+                    StageTimer t(ctx, sb.union_a ? -1 : 0, sb.s_main);
+                    if (sb.union_a) sb.union_launches++;
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, hitq, w.hit_counts + d, nullptr, nullptr, alpha_lcg, alpha_stride, alpha_filter, tm};
+                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, sb.hitq, w.hit_counts + d, nullptr, nullptr, sb.alpha_lcg, alpha_stride, alpha_filter, tm};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<false, true> : k_trace_persistent<false, false>;
-                        kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
+                        kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_main>>>(
                             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
                     } else
-                        k_trace<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, q, cn, ctx->dcounters, hitq ? w.hit_counts + d : nullptr);
+                        k_trace<<<g_trace, 128, 0, sb.s_main>>>(ctx->bvh, w, q, cn, ctx->dcounters, sb.hitq ? w.hit_counts + d : nullptr);
                     ctx->launches++;
                 }
-                if (join_shadow()) return 1; // shade reads illum and rewrites the shadow queue: the overlapped shadow launch must be done
+                if (join_shadow(sb)) return 1; // shade reads illum and rewrites the shadow queue: the overlapped shadow launch must be done
                 {
-                    StageTimer t(ctx, 1);
-                    // smallest compiled variant that covers the features this frame uses (rptr_shading.cuh, RPTR_FEAT_*)
-                    const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
-                                     (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0) |
-                                     (ctx->any_normal_map ? RPTR_FEAT_NORMAL_MAPS : 0);
-#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (hitq ? hitq : q), (hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? aov : AovTarget{nullptr, nullptr, nullptr, 0u}), tm, sort_tiles, (d == 0 ? 1 : 0)
-                    if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
-                    else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
-                    else k_shade<RPTR_FEAT_ALL><<<g_trace, RPTR_SHADE_THREADS, 0, ctx->stream>>>(RPTR_SHADE_ARGS);
+                    StageTimer t(ctx, 1, sb.s_main);
+#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (sb.hitq ? sb.hitq : q), (sb.hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? sb.aov : AovTarget{nullptr, nullptr, nullptr, 0u}), tm, sort_tiles, (d == 0 ? 1 : 0)
+                    if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, sb.s_main>>>(RPTR_SHADE_ARGS);
+                    else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, sb.s_main>>>(RPTR_SHADE_ARGS);
+                    else k_shade<RPTR_FEAT_ALL><<<g_trace, RPTR_SHADE_THREADS, 0, sb.s_main>>>(RPTR_SHADE_ARGS);
 #undef RPTR_SHADE_ARGS
                     ctx->launches++;
                 }
-                if (fp.output_channel == 0 && d + 1 < depth && ctx->overlap_shadow && ctx->trace_kernel == 0) {
+                if (fp.output_channel != 0 || d + 1 >= depth) continue; // no next-event estimation: no shadow rays
+                TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, sb.alpha_lcg, alpha_stride, alpha_filter, tm};
+                if (overlap) {
                     // The shadow rays of bounce d and the closest-hit rays of bounce d + 1 are independent.  Both kernels are
                     // persistent grids of one CTA per SM, so launched on two streams the second fills the SMs the first one
                     // vacates: its head hides the first one's tail (the longest rays of the queue).
                     if (ctx->stage_timing) {
-                        union_a = get_event(ctx);
-                        CU(cudaEventRecord(union_a, ctx->stream));
-                        union_launches = 1;
+                        sb.union_a = get_event(ctx);
+                        CU(cudaEventRecord(sb.union_a, sb.s_main));
+                        sb.union_launches = 1;
                     }
-                    CU(cudaEventRecord(ctx->ev_shade, ctx->stream));
-                    CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_shade, 0));
-                    TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, alpha_lcg, alpha_stride, alpha_filter, tm};
+                    CU(cudaEventRecord(sb.ev_shade, sb.s_main));
+                    CU(cudaStreamWaitEvent(sb.s_shadow, sb.ev_shade, 0));
                     auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
-                    kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream2>>>(
+                    kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_shadow>>>(
                         ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
-                    CU(cudaEventRecord(ctx->ev_shadow, ctx->stream2));
-                    shadow_pending = true;
-                    ctx->launches++;
-                } else if (fp.output_channel == 0 && d + 1 < depth) {
-                    StageTimer t(ctx, 2);
+                    CU(cudaEventRecord(sb.ev_shadow, sb.s_shadow));
+                    sb.shadow_pending = true;
+                } else {
+                    StageTimer t(ctx, 2, sb.s_main);
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, alpha_lcg, alpha_stride, alpha_filter, tm};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
-                        kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, ctx->stream>>>(
+                        kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_main>>>(
                             ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
                     } else
-                        k_shadow<<<g_trace, 128, 0, ctx->stream>>>(ctx->bvh, w, cn + 1, ctx->dcounters, alpha_filter, tm);
-                    ctx->launches++;
+                        k_shadow<<<g_trace, 128, 0, sb.s_main>>>(ctx->bvh, w, cn + 1, ctx->dcounters, alpha_filter, tm);
                 }
-            }
-            if (join_shadow()) return 1;
-            {
-                StageTimer t(ctx, 3);
-                if (queries)
-                    k_resolve_queries<<<g_light, 256, 0, ctx->stream>>>(fp, w, results, (uint32_t)tm.local_pixels, sample_base + (uint32_t)first, nl, ctx->dcounters);
-                else
-                    k_resolve<<<g_light, 256, 0, ctx->stream>>>(fp, tm, w, ctx->accum, sample_base + (uint32_t)first, nl, ctx->dcounters, aov,
-                                                                ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_DISCARD_HISTORY);
                 ctx->launches++;
             }
+        // resolve in sample order: sub-wave k folds its layers after sub-wave k - 1 has
+        for (int k = 0; k < n_sub; ++k) {
+            Sub &sb = subs[k];
+            if (join_shadow(sb)) return 1;
+            if (k > 0) CU(cudaStreamWaitEvent(sb.s_main, subs[k - 1].ev_done, 0));
+            {
+                StageTimer t(ctx, 3, sb.s_main);
+                if (queries)
+                    k_resolve_queries<<<g_light, 256, 0, sb.s_main>>>(fp, sb.w, results, (uint32_t)tm.local_pixels, sample_base + (uint32_t)sb.first, sb.nl, ctx->dcounters);
+                else
+                    k_resolve<<<g_light, 256, 0, sb.s_main>>>(fp, tm, sb.w, ctx->accum, sample_base + (uint32_t)sb.first, sb.nl, ctx->dcounters, sb.aov,
+                                                              ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_DISCARD_HISTORY);
+                ctx->launches++;
+            }
+            if (n_sub > 1) CU(cudaEventRecord(sb.ev_done, sb.s_main));
         }
+        if (n_sub > 1) CU(cudaStreamWaitEvent(ctx->stream, subs[n_sub - 1].ev_done, 0)); // the context's stream continues after the whole round
     }
     return 0;
 }

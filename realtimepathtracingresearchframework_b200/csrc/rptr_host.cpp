@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <cmath>
 #include <cstdio>
 #include <array>
@@ -726,62 +727,150 @@ struct Builder {
     }
 };
 
-// collapse the binary tree into 4-wide nodes, emitted breadth-first; returns the depth of the wide tree
+// collapse the binary tree into 8-wide nodes (rptr_bvh.cuh), emitted breadth-first with the inner children and the triangles
+// of every node consecutive and in slot order; returns the depth of the wide tree
 int collapse(const Builder &b, HostScene &s) {
+    // a child under construction: a binary node (inner, or a leaf of several primitives) or one primitive of the builder's array
+    struct Kid { int32_t node2; int32_t prim; };
     struct Item { int32_t node2; int32_t depth; };
     std::vector<Item> queue;
     s.nodes.clear();
     s.leaf_tris.clear();
     s.sah_cost = 0.0f;
     auto is_leaf2 = [&](int32_t i) { return b.nodes[i].left < 0; };
-    auto area = [&](int32_t i) { return Builder::half_area(b.nodes[i].lo, b.nodes[i].hi); };
-    auto emit_leaf = [&](int32_t i) {
-        const int first_slot = ~b.nodes[i].left, n = b.nodes[i].right;
-        const int32_t first = (int32_t)s.leaf_tris.size();
-        for (int k = 0; k < n; ++k) s.leaf_tris.push_back(s.tris[b.prims[first_slot + k].id]);
-        return make_leaf_ref(first, n);
+    auto leaf_count = [&](int32_t i) { return b.nodes[i].right; };
+    auto leaf_first = [&](int32_t i) { return ~b.nodes[i].left; };
+    auto kid_area = [&](const Kid &k) {
+        return k.node2 >= 0 ? Builder::half_area(b.nodes[k.node2].lo, b.nodes[k.node2].hi) : Builder::half_area(b.prims[k.prim].lo, b.prims[k.prim].hi);
+    };
+    // SAH-optimal collapse by dynamic programming over the binary tree (after Ylitie et al. 2017, section 3): cost[n][i - 1] = the
+    // cheapest way to represent the sub-tree of binary node n as a forest of at most i roots (i = 1 .. 7), a root being a triangle
+    // slot (cost: its box area x c_tri) or a wide node (its box area x c_node + the best distribution of <= 8 roots over its two
+    // sub-trees).  Binary nodes are stored parent before children, so one backward sweep sees the children first.
+    const float c_node = std::getenv("RPTR_COLLAPSE_NODE_COST") ? (float)std::atof(std::getenv("RPTR_COLLAPSE_NODE_COST")) : 1.0f;
+    const float c_tri = std::getenv("RPTR_COLLAPSE_TRI_COST") ? (float)std::atof(std::getenv("RPTR_COLLAPSE_TRI_COST")) : 0.6f;
+    const bool greedy = std::getenv("RPTR_COLLAPSE_GREEDY") != nullptr; // A/B: open the largest child until eight are held
+    const size_t n2 = b.nodes.size();
+    struct Dp { float cost[7]; uint8_t split[8]; }; // split[i - 1]: 0 = as for i - 1 roots (i > 1) / one root (i == 1); k > 0 = k roots left, rest right; split[7] = the wide node's own split
+    std::vector<Dp> dp(greedy ? 0 : n2);
+    if (!greedy)
+        for (size_t idx = n2; idx-- > 0;) {
+            Dp &e = dp[idx];
+            const float area = Builder::half_area(b.nodes[idx].lo, b.nodes[idx].hi);
+            if (is_leaf2((int32_t)idx)) {
+                const int cnt = leaf_count((int32_t)idx);
+                float tris = 0.0f;
+                for (int k = 0; k < cnt; ++k) tris += Builder::half_area(b.prims[leaf_first((int32_t)idx) + k].lo, b.prims[leaf_first((int32_t)idx) + k].hi) * c_tri;
+                for (int i = 1; i <= 7; ++i) {
+                    e.cost[i - 1] = i >= cnt ? tris : area * c_node + tris; // fewer roots than triangles: one wide node of triangle slots
+                    e.split[i - 1] = 0;
+                }
+                e.split[7] = 0;
+                continue;
+            }
+            const Dp &l = dp[(size_t)b.nodes[idx].left], &r = dp[(size_t)b.nodes[idx].right];
+            // as a wide node: up to eight roots distributed over the two sub-trees
+            float wide = 1e30f;
+            int wide_k = 1;
+            for (int k = 1; k <= 7; ++k) {
+                const float c = l.cost[k - 1] + r.cost[8 - k - 1];
+                if (c < wide) { wide = c; wide_k = k; }
+            }
+            e.split[7] = (uint8_t)wide_k;
+            e.cost[0] = area * c_node + wide;
+            e.split[0] = 0;
+            for (int i = 2; i <= 7; ++i) {
+                float best = e.cost[i - 2];
+                int best_k = 0;
+                for (int k = 1; k < i; ++k) {
+                    const float c = l.cost[k - 1] + r.cost[i - k - 1];
+                    if (c < best) { best = c; best_k = k; }
+                }
+                e.cost[i - 1] = best;
+                e.split[i - 1] = (uint8_t)best_k;
+            }
+        }
+    // the roots of the cheapest forest of at most i roots for the sub-tree of binary node m
+    std::function<void(int32_t, int, Kid *, int &)> expand = [&](int32_t m, int i, Kid *kids, int &nk) {
+        if (is_leaf2(m)) {
+            const int cnt = leaf_count(m);
+            if (i >= cnt) for (int k = 0; k < cnt; ++k) kids[nk++] = Kid{-1, leaf_first(m) + k};
+            else kids[nk++] = Kid{m, -1};
+            return;
+        }
+        while (i > 1 && dp[(size_t)m].split[i - 1] == 0) --i;
+        if (i == 1) { kids[nk++] = Kid{m, -1}; return; }
+        const int k = dp[(size_t)m].split[i - 1];
+        expand(b.nodes[m].left, k, kids, nk);
+        expand(b.nodes[m].right, i - k, kids, nk);
     };
     int max_depth = 0;
-    if (is_leaf2(0)) { // a single leaf: one node with one used slot
-        queue.push_back(Item{-1, 0});
-    } else
-        queue.push_back(Item{0, 0});
+    queue.push_back(Item{0, 0});
     for (size_t head = 0; head < queue.size(); ++head) {
         const Item it = queue[head];
         max_depth = std::max(max_depth, (int)it.depth);
-        int32_t kids[RPTR_BVH_WIDTH];
+        Kid kids[RPTR_BVH_WIDTH];
         int nk = 0;
-        if (it.node2 < 0) {
-            kids[nk++] = 0;
+        if (is_leaf2(it.node2)) { // a leaf of the binary tree: its primitives are the slots
+            for (int k = 0; k < leaf_count(it.node2) && nk < RPTR_BVH_WIDTH; ++k) kids[nk++] = Kid{-1, leaf_first(it.node2) + k};
+        } else if (!greedy) {
+            const int k = dp[(size_t)it.node2].split[7];
+            expand(b.nodes[it.node2].left, k, kids, nk);
+            expand(b.nodes[it.node2].right, 8 - k, kids, nk);
         } else {
-            kids[nk++] = b.nodes[it.node2].left;
-            kids[nk++] = b.nodes[it.node2].right;
-            while (nk < RPTR_BVH_WIDTH) { // open the inner child with the largest surface area
+            kids[nk++] = Kid{b.nodes[it.node2].left, -1};
+            kids[nk++] = Kid{b.nodes[it.node2].right, -1};
+            for (;;) { // open the child with the largest surface area that still fits: an inner node -> its two children, a leaf -> its primitives
                 int pick = -1;
                 float best = -1.0f;
-                for (int k = 0; k < nk; ++k)
-                    if (!is_leaf2(kids[k]) && area(kids[k]) > best) { best = area(kids[k]); pick = k; }
+                for (int k = 0; k < nk; ++k) {
+                    if (kids[k].node2 < 0) continue;
+                    const int parts = is_leaf2(kids[k].node2) ? leaf_count(kids[k].node2) : 2;
+                    if (nk - 1 + parts > RPTR_BVH_WIDTH) continue;
+                    const float a = kid_area(kids[k]);
+                    if (a > best) { best = a; pick = k; }
+                }
                 if (pick < 0) break;
-                const int32_t open = kids[pick];
-                kids[pick] = b.nodes[open].left;
-                kids[nk++] = b.nodes[open].right;
+                const int32_t open = kids[pick].node2;
+                if (is_leaf2(open)) {
+                    kids[pick] = Kid{-1, leaf_first(open)};
+                    for (int k = 1; k < leaf_count(open); ++k) kids[nk++] = Kid{-1, leaf_first(open) + k};
+                } else {
+                    kids[pick] = Kid{b.nodes[open].left, -1};
+                    kids[nk++] = Kid{b.nodes[open].right, -1};
+                }
             }
         }
-        float clo[RPTR_BVH_WIDTH][3], chi[RPTR_BVH_WIDTH][3];
-        int32_t cref[RPTR_BVH_WIDTH];
-        // children of the queue items appended so far = index the child node will get
+        float klo[RPTR_BVH_WIDTH][3], khi[RPTR_BVH_WIDTH][3];
         for (int k = 0; k < nk; ++k) {
-            const Node2 &c = b.nodes[kids[k]];
-            for (int a = 0; a < 3; ++a) { clo[k][a] = c.lo[a]; chi[k][a] = c.hi[a]; }
-            if (is_leaf2(kids[k])) cref[k] = emit_leaf(kids[k]);
-            else {
-                cref[k] = (int32_t)queue.size();
-                queue.push_back(Item{kids[k], it.depth + 1});
-            }
-            s.sah_cost += area(kids[k]);
+            const float *lo = kids[k].node2 >= 0 ? b.nodes[kids[k].node2].lo : b.prims[kids[k].prim].lo;
+            const float *hi = kids[k].node2 >= 0 ? b.nodes[kids[k].node2].hi : b.prims[kids[k].prim].hi;
+            for (int a = 0; a < 3; ++a) { klo[k][a] = lo[a]; khi[k][a] = hi[a]; }
+            s.sah_cost += kid_area(kids[k]);
         }
-        const BvhNode nd = encode_node(clo, chi, cref, nk);
-        s.nodes.push_back(nd);
+        int slot_of[RPTR_BVH_WIDTH];
+        assign_slots(nk, klo, khi, slot_of);
+        int kid_in[RPTR_BVH_WIDTH];
+        for (int sl = 0; sl < RPTR_BVH_WIDTH; ++sl) kid_in[sl] = -1;
+        for (int k = 0; k < nk; ++k) kid_in[slot_of[k]] = k;
+        float slo[RPTR_BVH_WIDTH][3], shi[RPTR_BVH_WIDTH][3];
+        int kind[RPTR_BVH_WIDTH];
+        const int32_t child_base = (int32_t)queue.size(), tri_base = (int32_t)s.leaf_tris.size();
+        for (int sl = 0; sl < RPTR_BVH_WIDTH; ++sl) {
+            const int k = kid_in[sl];
+            kind[sl] = 0;
+            for (int a = 0; a < 3; ++a) { slo[sl][a] = 0.0f; shi[sl][a] = 0.0f; }
+            if (k < 0) continue;
+            for (int a = 0; a < 3; ++a) { slo[sl][a] = klo[k][a]; shi[sl][a] = khi[k][a]; }
+            if (kids[k].node2 >= 0) {
+                kind[sl] = 1;
+                queue.push_back(Item{kids[k].node2, it.depth + 1});
+            } else {
+                kind[sl] = 2;
+                s.leaf_tris.push_back(s.tris[b.prims[kids[k].prim].id]);
+            }
+        }
+        s.nodes.push_back(encode_node(slo, shi, kind, child_base, tri_base));
     }
     return max_depth + 1;
 }

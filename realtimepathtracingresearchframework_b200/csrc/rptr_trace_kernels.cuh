@@ -105,37 +105,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #ifndef RPTR_HC_PER_THREAD
 #define RPTR_HC_PER_THREAD 1
 #endif
-#ifndef RPTR_ANY_UNSORTED
-#define RPTR_ANY_UNSORTED 1 // shadow rays: skip the nearest-first sorting network (any hit terminates the ray)
-#endif
-#ifndef RPTR_LEAF_ONE_PER_TRIP
-#define RPTR_LEAF_ONE_PER_TRIP 1 // leaf step tests one triangle of the parked leaf per trip instead of looping over it
+#ifndef RPTR_NO_OOD
+#define RPTR_NO_OOD 1 // o / d is recomputed per node step (three multiplies on the idle FMA pipe) instead of living in three registers
 #endif
 #ifndef RPTR_FAST_RCP
 #define RPTR_FAST_RCP 1 // 1/d of the slab test through MUFU.RCP alone (boxes only prune and are padded far beyond 1 ulp of 1/d)
-#endif
-#ifndef RPTR_PIN_SMEM_BASE
-#define RPTR_PIN_SMEM_BASE 1 // compute the shared-window addresses once (asm volatile) instead of letting ptxas rematerialise them per node step
 #endif
 #ifndef RPTR_CHUNKS_PER_WARP
 #define RPTR_CHUNKS_PER_WARP 4 // target number of queue fetches per warp (tail balance) before the chunk is shortened
 #endif
 #ifndef RPTR_TRACE_THREADS
-#define RPTR_TRACE_THREADS 896 // one CTA per SM: 28 warps (<= 72 registers each) share one 64 KB image of the top of the BVH
+#define RPTR_TRACE_THREADS 896 // one CTA per SM: 28 warps share one 96 KB image of the top of the BVH
 #endif
 #define RPTR_TOP_PLANE_BYTES (RPTR_TOP_NODES_MAX * 16)
-// Traversal stack: the first RPTR_SMEM_STACK entries of every thread live in shared memory, laid out [entry][thread] so
-// that the bank only depends on the lane (any mix of stack depths in a warp is conflict free: one wavefront per push /
-// pop instead of up to 32 sectors through local memory); deeper entries spill to a local-memory array.
+#define RPTR_TOP_BYTES (RPTR_NODE_WORDS * RPTR_TOP_PLANE_BYTES)
+#define RPTR_LUT_BYTES 2048
+// Traversal stack of (base, masks) groups: the first RPTR_SMEM_STACK entries of every thread live in shared memory as two
+// planes of 32-bit words laid out [entry][thread], so that the bank only depends on the lane (any mix of stack depths in a
+// warp is conflict free); deeper entries spill to a local-memory array.
 #ifndef RPTR_SMEM_STACK
-#define RPTR_SMEM_STACK 16
+#define RPTR_SMEM_STACK 8
 #endif
-#define RPTR_TRACE_SMEM_BYTES ((size_t)RPTR_TOP_NODES_MAX * sizeof(BvhNode) + (size_t)RPTR_SMEM_STACK * RPTR_TRACE_THREADS * sizeof(int32_t))
+#define RPTR_STACK_PLANE_BYTES ((uint32_t)(RPTR_SMEM_STACK * RPTR_TRACE_THREADS * sizeof(uint32_t)))
+#define RPTR_TRACE_SMEM_BYTES ((size_t)RPTR_TOP_BYTES + RPTR_LUT_BYTES + 2 * (size_t)RPTR_STACK_PLANE_BYTES)
+#ifndef RPTR_TRI_BACKLOG
+#define RPTR_TRI_BACKLOG 6
+#endif
+#ifndef RPTR_NODE_REPS
+#define RPTR_NODE_REPS 2 // node steps per trip of the loop (the ballots / refill checks of a trip are paid once)
+#endif
 // shared-window accesses by 32-bit address (a generic pointer would cost a window-base computation per push / pop)
-__device__ __forceinline__ void sts32(uint32_t addr, int32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ int32_t lds32(uint32_t addr) {
-    int32_t v;
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 template <int OFF>
@@ -152,37 +160,37 @@ __device__ __forceinline__ float qfloat_k(uint32_t word, uint32_t hi_const) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(hi_const), "n"(0x7044 | (K << 8)));
     return __uint_as_float(r);
 }
-// slab test of child K against the per-node ray constants, branch free: returns the entry distance, or +inf on a miss.
+// slab test of the child in byte K of the six words, branch free: true when the padded box meets the ray inside (tmin, tmax].
 // qn* / qf* are the packed bounds on the near / far side of each axis (picked per node from the sign of the direction:
 // fma is monotonic, so this equals the min / max form of slab_q() bit for bit).
 template <int K>
-__device__ __forceinline__ float slab_k(const NodeSlab &n, uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx, uint32_t qfy,
-                                        uint32_t qfz, uint32_t hc, float tmin, float tmax, int32_t ref) {
+__device__ __forceinline__ bool slab_k(const NodeSlab &n, uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx, uint32_t qfy,
+                                       uint32_t qfz, uint32_t hc, float tmin, float tmax) {
     const float nx = fmaf(qfloat_k<K>(qnx, hc), n.ax, n.bx), fx = fmaf(qfloat_k<K>(qfx, hc), n.ax, n.bx);
     const float ny = fmaf(qfloat_k<K>(qny, hc), n.ay, n.by), fy = fmaf(qfloat_k<K>(qfy, hc), n.ay, n.by);
     const float nz = fmaf(qfloat_k<K>(qnz, hc), n.az, n.bz), fz = fmaf(qfloat_k<K>(qfz, hc), n.az, n.bz);
     float tf = fminf(fminf(fx, fy), fz);
-    float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
     tf = fminf(tf * 1.0000004f, tmax);
-    return (tn <= tf) & (ref != RPTR_EMPTY) ? tn : __int_as_float(0x7f800000);
+    return tn <= tf;
 }
-#define RPTR_STACK_STRIDE ((uint32_t)(RPTR_TRACE_THREADS * sizeof(int32_t)))
-#define RPTR_PUSH(v)                                                                  \
-    {                                                                                 \
-        if (sp < RPTR_SMEM_STACK) sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, (v)); \
-        else lstack[sp - RPTR_SMEM_STACK] = (v);                                      \
-        ++sp;                                                                         \
-    }
-#define RPTR_POP() (sp > 0 ? (--sp, sp < RPTR_SMEM_STACK ? lds32(sst + (uint32_t)sp * RPTR_STACK_STRIDE) : lstack[sp - RPTR_SMEM_STACK]) : RPTR_EMPTY)
 
 // Alpha = true adds the candidate filter of non-opaque triangles (rptr_bvh.cuh, AlphaFilter).  Closest hit: a lane whose
 // traversal ended on an alpha-tested triangle draws from its path's LCG when it would retire; if the candidate is rejected
 // the lane restarts its traversal for the closest hit AFTER (t, id) of that candidate instead of retiring (front-to-back
 // order of DESIGN.md section 5 without a second wavefront pass).  Any hit: a candidate occludes iff its own seeded draw says so.
+//
+// Per-lane state machine over the eight-wide tree (rptr_bvh.cuh).  A lane holds one NODE GROUP G = (child_base, imask << 8 |
+// pending inner hits in priority order) and one TRIANGLE GROUP T = (tri_base, lmask << 8 | pending triangle hits) in
+// registers and further groups on its stack.  One trip through the loop is at most one node step and one triangle step for
+// the warp: the node step takes the highest-priority pending child of G, slab-tests the eight slots of that node and
+// replaces G (the rest of the old group goes to the stack); triangle hits become T, or a stack entry while T is busy.  The
+// triangle step tests ONE pending triangle of T and runs only when at least RPTR_LEAF_LANES lanes hold one (warp ballot)
+// or no lane has node work, so that the triangle code runs at high lane utilisation too.
 template <bool Any, bool Alpha>
 __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhDev bvh, TraceIO io, unsigned long long *c_rays,
                                                                             unsigned long long *c_nodes, unsigned long long *c_tris) {
-    extern __shared__ __align__(128) unsigned char smem_top[]; // four word planes of the top_k first nodes, then the stacks
+    extern __shared__ __align__(128) unsigned char smem_top[]; // six word planes of the top_k first nodes, the LUT, the stacks
     __shared__ __align__(8) uint64_t top_bar;
     __shared__ uint32_t hc_word;
     const uint32_t n = *io.count;
@@ -194,20 +202,25 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         mbar_init(&top_bar, 1);
         hc_word = 0x3f000000u;
     }
+    // priority permutation of an 8-bit hit mask: lut[oct << 8 | m] has bit (s ^ oct) set iff bit s of m is set
+    for (uint32_t i = threadIdx.x; i < RPTR_LUT_BYTES; i += RPTR_TRACE_THREADS) {
+        const uint32_t oct = i >> 8, m = i & 0xffu;
+        uint32_t r = 0;
+#pragma unroll
+        for (uint32_t sl = 0; sl < 8; ++sl) r |= ((m >> sl) & 1u) << (sl ^ oct);
+        smem_top[RPTR_TOP_BYTES + i] = (unsigned char)r;
+    }
     __syncthreads();
     if (threadIdx.x == 0 && n > 0 && plane_bytes > 0) {
-        mbar_expect_tx(&top_bar, 4u * plane_bytes);
-        for (uint32_t w = 0; w < 4; ++w)
+        mbar_expect_tx(&top_bar, (uint32_t)RPTR_NODE_WORDS * plane_bytes);
+        for (uint32_t w = 0; w < RPTR_NODE_WORDS; ++w)
             tma_bulk_g2s(smem_top + w * RPTR_TOP_PLANE_BYTES, reinterpret_cast<const unsigned char *>(bvh.top_planes) + w * RPTR_TOP_PLANE_BYTES,
                          plane_bytes, &top_bar);
     }
     if (n > 0 && plane_bytes > 0) mbar_wait(&top_bar, 0);
     const int32_t top_k = bvh.top_k;
-#if RPTR_PIN_SMEM_BASE
     const uint32_t top_base = smem_u32_pinned(smem_top);
-#else
-    const uint32_t top_base = smem_u32(smem_top);
-#endif
+    const uint32_t lut_base = top_base + (uint32_t)RPTR_TOP_BYTES;
     // Rays per queue fetch: RPTR_FETCH_CHUNK for long queues (few atomics, coherent warps); short queues (late bounces)
     // are cut finer so that every warp of the grid gets work instead of a few warps walking 256 rays 32 at a time.
     // Guided self-scheduling: the size is recomputed from what is left of the queue at every fetch.
@@ -219,36 +232,65 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     // per-lane ray state
     bool have = false;
     uint32_t ray_index = 0, slot = 0;
-    float3 o = f3(0.0f), d = f3(0.0f), inv = f3(0.0f), ood = f3(0.0f);
-    float tmin = 0.0f, tmax = 0.0f;
+    float3 o = f3(0.0f), d = f3(0.0f), inv = f3(0.0f);
+#if !RPTR_NO_OOD
+    float3 ood = f3(0.0f); // o / d, kept per ray (RPTR_NO_OOD: recomputed per node step -- three multiplies for three registers)
+#endif
+    float tmin = 0.0f;
     float best_t = 0.0f, best_u = 0.0f, best_v = 0.0f;
     int32_t best_tri = -1, best_id = 0x7fffffff;
     int32_t after_id = 0x7fffffff; // Alpha closest: candidates must come after (tmin, after_id) in (t, id) order; tmin doubles as after_t
-    uint32_t pixel_linear = 0;     // Alpha any-hit: global pixel of the path the shadow ray belongs to
-    int32_t node = RPTR_EMPTY; // current item: inner node (>= 0), leaf reference (< 0) or RPTR_EMPTY
-    int32_t leaf = 0;          // parked leaf reference (< 0) or 0 = none
-    int32_t lstack[RPTR_STACK_SIZE - RPTR_SMEM_STACK]; // overflow part of the traversal stack (local memory)
-#if RPTR_PIN_SMEM_BASE
-    const uint32_t sst = top_base + (uint32_t)(RPTR_TOP_NODES_MAX * sizeof(BvhNode)) + threadIdx.x * (uint32_t)sizeof(int32_t);
-#else
-    const uint32_t sst = smem_u32(smem_top + (size_t)RPTR_TOP_NODES_MAX * sizeof(BvhNode)) + threadIdx.x * (uint32_t)sizeof(int32_t);
-#endif
-    // high bytes of the decoded box coordinates, kept opaque to ptxas so that it stays in a register and the selectors
-    // become immediates (n is never 2^32 - 1)
+    uint32_t pixel_linear = 0;     // Alpha any-hit: pixel of the path the shadow ray belongs to
+    uint32_t gx = 0, gy = 0;       // node group: first child node, imask << 8 | pending inner hits (priority order: bit p = slot ^ oct)
+    uint32_t tx = 0, ty = 0;       // triangle group: first triangle, lmask << 8 | pending triangle hits (slot order)
+    uint32_t oct = 0;              // ray octant (closest hit only: any-hit rays take the children in slot order)
+    uint32_t lstack_x[RPTR_MAX_BVH_DEPTH + 2 - RPTR_SMEM_STACK], lstack_y[RPTR_MAX_BVH_DEPTH + 2 - RPTR_SMEM_STACK]; // overflow part of the node-group stack (local memory)
+    // triangle groups that arrive while T is busy (local memory); a lane whose backlog is full pauses its node steps until the
+    // triangle step has caught up, so the backlog is bounded
+    uint32_t tstack_x[RPTR_TRI_BACKLOG], tstack_y[RPTR_TRI_BACKLOG];
+    int tsp = 0;
+    const uint32_t sst = lut_base + (uint32_t)RPTR_LUT_BYTES + threadIdx.x * (uint32_t)sizeof(uint32_t);
+    // high bytes of the decoded box coordinates: read back from shared memory on purpose -- a value ptxas can prove constant or
+    // warp-uniform takes the immediate / uniform-register slot of PRMT, and all 48 selectors of a node step are then
+    // materialised in registers instead
 #if RPTR_HC_PER_THREAD
-    // read back from shared memory on purpose: a value ptxas can prove constant or warp-uniform takes the immediate /
-    // uniform-register slot of PRMT, and all 24 selectors of a node step are then materialised in registers instead
-    const uint32_t hc = (uint32_t)lds32(smem_u32(&hc_word));
+    const uint32_t hc = lds32(smem_u32(&hc_word));
 #else
     const uint32_t hc = n == 0xffffffffu ? 0u : 0x3f000000u;
 #endif
     int sp = 0;
     uint32_t n_nodes = 0, n_tris = 0, n_rays = 0;
 
+#define RPTR_STACK_STRIDE ((uint32_t)(RPTR_TRACE_THREADS * sizeof(uint32_t)))
+#define RPTR_PUSH(vx, vy)                                                        \
+    {                                                                            \
+        if (sp < RPTR_SMEM_STACK) {                                              \
+            const uint32_t a_ = sst + (uint32_t)sp * RPTR_STACK_STRIDE;          \
+            sts32(a_, (vx));                                                     \
+            sts32(a_ + RPTR_STACK_PLANE_BYTES, (vy));                            \
+        } else {                                                                 \
+            lstack_x[sp - RPTR_SMEM_STACK] = (vx);                               \
+            lstack_y[sp - RPTR_SMEM_STACK] = (vy);                               \
+        }                                                                        \
+        ++sp;                                                                    \
+    }
+#define RPTR_POP(vx, vy)                                                         \
+    {                                                                            \
+        --sp;                                                                    \
+        if (sp < RPTR_SMEM_STACK) {                                              \
+            const uint32_t a_ = sst + (uint32_t)sp * RPTR_STACK_STRIDE;          \
+            (vx) = lds32(a_);                                                    \
+            (vy) = lds32(a_ + RPTR_STACK_PLANE_BYTES);                           \
+        } else {                                                                 \
+            (vx) = lstack_x[sp - RPTR_SMEM_STACK];                               \
+            (vy) = lstack_y[sp - RPTR_SMEM_STACK];                               \
+        }                                                                        \
+    }
+
     for (;;) {
         __syncwarp();
         // ---- retire + refill --------------------------------------------------------------------------------------
-        bool done = have && node == RPTR_EMPTY && leaf == 0;
+        bool done = have && (gy & 0xffu) == 0u && (ty & 0xffu) == 0u && sp == 0 && tsp == 0;
         if (Alpha && !Any && done && best_tri >= 0 && after_id != RPTR_EMPTY) {
             const int32_t a8 = tri_alpha8(bvh.tris[best_tri]);
             if (a8 != RPTR_TRI_OPAQUE) {
@@ -259,17 +301,16 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 if (st != before) *ap = st;
                 if (rejected) { // look for the closest hit after this candidate
                     tmin = best_t; after_id = best_id;
-                    best_t = tmax; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
-                    sp = 0;
-                    node = 0;
+                    best_t = io.ray_d[slot].w; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
+                    gx = 0u; gy = 0x100u | (1u << oct);
                     done = false;
                 }
             }
             if (done) after_id = RPTR_EMPTY; // verdict reached: no second draw while the lane waits for the next refill
         }
         const unsigned idle = __ballot_sync(FULL, !have || done);
-        const unsigned inner0 = __ballot_sync(FULL, have && node >= 0);
-        const unsigned parked0 = __ballot_sync(FULL, have && leaf != 0);
+        const unsigned inner0 = __ballot_sync(FULL, have && (gy & 0xffu) != 0u && tsp < RPTR_TRI_BACKLOG);
+        const unsigned parked0 = __ballot_sync(FULL, have && (ty & 0xffu) != 0u);
         if (__popc(idle) >= RPTR_REFILL_LANES || (inner0 == 0 && parked0 == 0)) {
             if (done) {
                 if (Any) {
@@ -314,175 +355,125 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 slot = (Any || !io.queue) ? ray_index : io.queue[ray_index];
                 const float4 ro = io.ray_o[Any ? ray_index : slot], rd = io.ray_d[Any ? ray_index : slot];
                 o = f3(ro.x, ro.y, ro.z); tmin = ro.w;
-                d = f3(rd.x, rd.y, rd.z); tmax = rd.w;
+                d = f3(rd.x, rd.y, rd.z);
                 inv = f3(slab_rcp(slab_safe(d.x)), slab_rcp(slab_safe(d.y)), slab_rcp(slab_safe(d.z)));
+#if !RPTR_NO_OOD
                 ood = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-                best_t = tmax; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
+#endif
+                best_t = rd.w; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
                 if (Alpha && !Any) after_id = 0x7fffffff;
-                if (Alpha && Any) { // global pixel of the path: slot -> local pixel -> row band of this rank
-                    pixel_linear = tile_pixel_linear(io.tm, __float_as_uint(io.sh_c[ray_index].w) % (uint32_t)io.tm.local_pixels);
-                }
+                if (Alpha && Any) pixel_linear = tile_pixel_linear(io.tm, __float_as_uint(io.sh_c[ray_index].w) % (uint32_t)io.tm.local_pixels);
+                oct = Any ? 0u : ray_octant(d);
                 sp = 0;
-                leaf = 0;
-                node = bvh.n_nodes > 0 ? 0 : RPTR_EMPTY;
+                tsp = 0;
+                tx = 0u; ty = 0u;
+                gx = 0u;
+                gy = bvh.n_nodes > 0 ? (0x100u | (1u << oct)) : 0u; // the root as the only child of a virtual group: slot 0, priority 0 ^ oct
                 have = true;
                 n_rays++;
             }
             pool_pos += min(avail, (uint32_t)__popc(idle));
             if (drained && !__any_sync(FULL, have)) break;
         }
-        // ---- issue every load of this trip up front: the node of lanes with node work AND the first triangle of lanes
-        //      whose parked leaf is processed in this trip, so the two dependent fetches overlap instead of queueing ----
+        // ---- the triangle of lanes whose triangle group is processed in this trip is requested first, so that its latency
+        //      hides behind the node step ----
         const bool leaf_turn = __popc(parked0) >= RPTR_LEAF_LANES || inner0 == 0;
-        const bool do_node = have && node >= 0;
-        const bool do_leaf = leaf_turn && have && leaf != 0;
-        float4 w0, w1, w2, w3, ta, tb, tc;
-        int32_t lf_first = 0, lf_cnt = 0;
+        const bool do_leaf = leaf_turn && have && (ty & 0xffu) != 0u;
+        float4 ta, tb, tc;
+        int32_t tri_index = 0;
         if (do_leaf) {
-            const int32_t ref = ~leaf;
-            lf_first = ref >> 2;
-            lf_cnt = (ref & 3) + 1;
-            const char *tp = reinterpret_cast<const char *>(bvh.tris + lf_first);
+            const uint32_t s = (uint32_t)__ffs((int)(ty & 0xffu)) - 1u;
+            tri_index = (int32_t)(tx + (uint32_t)__popc((ty >> 8) & ((1u << s) - 1u)));
+            ty &= ~(1u << s);
+            const char *tp = reinterpret_cast<const char *>(bvh.tris + tri_index);
             ta = ld128(tp); tb = ld128(tp + 16); tc = ld128(tp + 32);
         }
-        if (do_node) {
-            if (node < top_k) { // top of the tree: shared memory, one LDS.128 per word plane (address = base + 16 * node)
-                const uint32_t a = top_base + ((uint32_t)node << 4);
-                w0 = lds128<0>(a); w1 = lds128<RPTR_TOP_PLANE_BYTES>(a);
-                w2 = lds128<2 * RPTR_TOP_PLANE_BYTES>(a); w3 = lds128<3 * RPTR_TOP_PLANE_BYTES>(a);
-            } else { // 2 x 256-bit loads: both 32-byte sectors of the node pass through L1 once
-                const char *np = reinterpret_cast<const char *>(bvh.nodes + node);
-                ld256(np, w0, w1);
-                ld256(np + 32, w2, w3);
+        // ---- node steps ---------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int rep = 0; rep < RPTR_NODE_REPS; ++rep) {
+            if (have && (gy & 0xffu) != 0u && tsp < RPTR_TRI_BACKLOG) {
+                // the highest-priority pending child of the group; what is left of the group goes to the stack
+                const uint32_t p = 31u - (uint32_t)__clz((int)(gy & 0xffu));
+                gy &= ~(1u << p);
+                const uint32_t sl = Any ? p : (p ^ oct);
+                const int32_t node = (int32_t)(gx + (uint32_t)__popc((gy >> 8) & ((1u << sl) - 1u)));
+                if ((gy & 0xffu) != 0u) RPTR_PUSH(gx, gy);
+                float4 w0, w1, w2, w3, w4, w5;
+                if (node < top_k) { // top of the tree: shared memory, one LDS.128 per word plane (address = base + 16 * node)
+                    const uint32_t a = top_base + ((uint32_t)node << 4);
+                    w0 = lds128<0>(a); w1 = lds128<RPTR_TOP_PLANE_BYTES>(a); w2 = lds128<2 * RPTR_TOP_PLANE_BYTES>(a);
+                    w3 = lds128<3 * RPTR_TOP_PLANE_BYTES>(a); w4 = lds128<4 * RPTR_TOP_PLANE_BYTES>(a); w5 = lds128<5 * RPTR_TOP_PLANE_BYTES>(a);
+                } else { // 3 x 256-bit loads: every 32-byte sector of the node passes through L1 once
+                    const char *np = reinterpret_cast<const char *>(bvh.nodes + node);
+                    ld256(np, w0, w1);
+                    ld256(np + 32, w2, w3);
+                    ld256(np + 64, w4, w5);
+                }
+                n_nodes++;
+#if RPTR_NO_OOD
+                const float3 ood = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+#endif
+                const NodeSlab ns = node_slab(w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, inv, ood);
+                // packed bounds: qlo x / y / z = (w2.x w2.y) (w2.z w2.w) (w3.x w3.y), qhi x / y / z = (w3.z w3.w) (w4.x w4.y) (w4.z w4.w)
+                const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
+                const uint32_t lx0 = __float_as_uint(w2.x), lx1 = __float_as_uint(w2.y), ly0 = __float_as_uint(w2.z), ly1 = __float_as_uint(w2.w);
+                const uint32_t lz0 = __float_as_uint(w3.x), lz1 = __float_as_uint(w3.y), hx0 = __float_as_uint(w3.z), hx1 = __float_as_uint(w3.w);
+                const uint32_t hy0 = __float_as_uint(w4.x), hy1 = __float_as_uint(w4.y), hz0 = __float_as_uint(w4.z), hz1 = __float_as_uint(w4.w);
+                const uint32_t nx0 = sx ? hx0 : lx0, fx0 = sx ? lx0 : hx0, nx1 = sx ? hx1 : lx1, fx1 = sx ? lx1 : hx1;
+                const uint32_t ny0 = sy ? hy0 : ly0, fy0 = sy ? ly0 : hy0, ny1 = sy ? hy1 : ly1, fy1 = sy ? ly1 : hy1;
+                const uint32_t nz0 = sz ? hz0 : lz0, fz0 = sz ? lz0 : hz0, nz1 = sz ? hz1 : lz1, fz1 = sz ? lz1 : hz1;
+                uint32_t hit8 = 0u;
+                hit8 |= slab_k<0>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t) ? 0x01u : 0u;
+                hit8 |= slab_k<1>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t) ? 0x02u : 0u;
+                hit8 |= slab_k<2>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t) ? 0x04u : 0u;
+                hit8 |= slab_k<3>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t) ? 0x08u : 0u;
+                hit8 |= slab_k<0>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t) ? 0x10u : 0u;
+                hit8 |= slab_k<1>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t) ? 0x20u : 0u;
+                hit8 |= slab_k<2>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t) ? 0x40u : 0u;
+                hit8 |= slab_k<3>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t) ? 0x80u : 0u;
+                const uint32_t masks = __float_as_uint(w5.x);
+                const uint32_t ih = hit8 & masks, th = hit8 & (masks >> 8); // empty slots have neither bit
+                gx = __float_as_uint(w1.z);
+                gy = ((masks & 0xffu) << 8) | (Any ? ih : lds8(lut_base + ((oct << 8) | ih)));
+                if (th != 0u) {
+                    const uint32_t nty = (masks & 0xff00u) | th;
+                    if ((ty & 0xffu) != 0u) { tstack_x[tsp] = __float_as_uint(w1.w); tstack_y[tsp] = nty; ++tsp; }
+                    else { tx = __float_as_uint(w1.w); ty = nty; }
+                }
+                if ((gy & 0xffu) == 0u && sp > 0) RPTR_POP(gx, gy); // nothing hit: back to the closest pending group
             }
         }
-        // ---- node step ----------------------------------------------------------------------------------------------
-        if (do_node) {
-            n_nodes++;
-            // four slab tests on the quantised child boxes; a missed or unused child gets key +inf and reference EMPTY
-            const float INF = __int_as_float(0x7f800000);
-            const NodeSlab ns = node_slab(w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, inv, ood);
-            const uint32_t qlx = __float_as_uint(w1.z), qly = __float_as_uint(w1.w), qlz = __float_as_uint(w2.x);
-            const uint32_t qhx = __float_as_uint(w2.y), qhy = __float_as_uint(w2.z), qhz = __float_as_uint(w2.w);
-            const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
-            const uint32_t qnx = sx ? qhx : qlx, qfx = sx ? qlx : qhx;
-            const uint32_t qny = sy ? qhy : qly, qfy = sy ? qly : qhy;
-            const uint32_t qnz = sz ? qhz : qlz, qfz = sz ? qlz : qhz;
-            int32_t r0 = f2i(w3.x), r1 = f2i(w3.y), r2 = f2i(w3.z), r3 = f2i(w3.w);
-            float t0 = slab_k<0>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r0);
-            float t1 = slab_k<1>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r1);
-            float t2 = slab_k<2>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r2);
-            float t3 = slab_k<3>(ns, qnx, qny, qnz, qfx, qfy, qfz, hc, tmin, best_t, r3);
-            // 5-comparator sorting network on (t, ref): nearest first
-#define RPTR_CSWAP(ta_, ra, tb_, rb)                                 \
-    {                                                               \
-        const bool sw_ = tb_ < ta_;                                 \
-        const float tl_ = sw_ ? tb_ : ta_, th_ = sw_ ? ta_ : tb_;   \
-        const int32_t rl_ = sw_ ? rb : ra, rh_ = sw_ ? ra : rb;     \
-        ta_ = tl_; tb_ = th_; ra = rl_; rb = rh_;                   \
-    }
-            if (!(Any && RPTR_ANY_UNSORTED)) {
-                RPTR_CSWAP(t0, r0, t1, r1)
-                RPTR_CSWAP(t2, r2, t3, r3)
-                RPTR_CSWAP(t0, r0, t2, r2)
-                RPTR_CSWAP(t1, r1, t3, r3)
-                RPTR_CSWAP(t1, r1, t2, r2)
-            }
-#undef RPTR_CSWAP
-            // continue with the nearest hit, push the others farthest first (a key of +inf marks a missed / unused child)
-            if (sp + 3 <= RPTR_SMEM_STACK) { // common case, branch free: store unconditionally, advance when the entry is valid
-                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r3); sp += t3 < INF;
-                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r2); sp += t2 < INF;
-                sts32(sst + (uint32_t)sp * RPTR_STACK_STRIDE, r1); sp += t1 < INF;
-            } else {
-                if (t3 < INF) RPTR_PUSH(r3);
-                if (t2 < INF) RPTR_PUSH(r2);
-                if (t1 < INF) RPTR_PUSH(r1);
-            }
-            node = t0 < INF ? r0 : RPTR_POP();
-            // park a leaf and go on with whatever the stack holds (speculative traversal); when this lane's parked leaf
-            // is being processed in this trip the slot frees up below
-            if (node < 0 && node != RPTR_EMPTY && leaf == 0) {
-                leaf = node;
-                node = RPTR_POP();
-            }
-        }
-        // ---- leaf step ------------------------------------------------------------------------------------------------
-#if RPTR_LEAF_ONE_PER_TRIP
-        // one triangle of the parked leaf per trip (its words were requested at the top of the trip); the leaf reference
-        // is advanced in place: ~((first + 1) << 2 | (count - 2)) == leaf - 3
+        // ---- triangle step: one triangle of the group per trip (its words were requested at the top of the trip) -------------
         if (do_leaf) {
-            bool occluded = false;
             n_tris++;
             float t, u, v;
-            if (intersect_tri(f3(ta.x, ta.y, ta.z), f3(ta.w, tb.x, tb.y), f3(tb.z, tb.w, tc.x), o, d, t, u, v) && t < tmax &&
+            if (intersect_tri(f3(ta.x, ta.y, ta.z), f3(ta.w, tb.x, tb.y), f3(tb.z, tb.w, tc.x), o, d, t, u, v) &&
                 ((Alpha && !Any) ? (t > tmin || (t == tmin && f2i(tc.y) > after_id)) : t > tmin)) {
                 const int32_t id = f2i(tc.y);
                 if (Any) {
-                    bool passes = true;
-                    if (Alpha) {
-                        AlphaFilter af = io.alpha;
-                        af.pixel_linear = pixel_linear;
-                        passes = shadow_candidate_passes(af, f2i(tc.z), f2i(tc.w));
+                    if (t < best_t) { // best_t stays the ray's t_max for any-hit rays
+                        bool passes = true;
+                        if (Alpha) {
+                            AlphaFilter af = io.alpha;
+                            af.pixel_linear = pixel_linear;
+                            passes = shadow_candidate_passes(af, f2i(tc.z), f2i(tc.w));
+                        }
+                        if (passes) { // occluded: drop the rest of the traversal
+                            best_tri = tri_index;
+                            sp = 0;
+                            tsp = 0;
+                            gy = 0u; ty = 0u;
+                        }
                     }
-                    if (passes) {
-                        best_tri = lf_first;
-                        occluded = true;
-                    }
-                } else if (best_tri < 0 || t < best_t || (t == best_t && id < best_id)) {
-                    best_t = t; best_u = u; best_v = v; best_tri = lf_first; best_id = id;
+                } else if (best_tri < 0 ? t < best_t : (t < best_t || (t == best_t && id < best_id))) {
+                    best_t = t; best_u = u; best_v = v; best_tri = tri_index; best_id = id;
                 }
-            }
-            leaf = lf_cnt > 1 ? leaf - 3 : 0;
-            if (Any && occluded) { // drop the rest of the traversal
-                sp = 0;
-                leaf = 0;
-                node = RPTR_EMPTY;
-            } else if (leaf == 0 && node < 0 && node != RPTR_EMPTY) { // the current item was a second leaf waiting for the slot
-                leaf = node;
-                node = RPTR_POP();
             }
         }
-#else
-        // software-pipelined over the (<= 4, contiguous) triangles of the parked leaf
-        if (do_leaf) {
-            bool occluded = false;
-            for (int32_t i = 0; i < lf_cnt; ++i) {
-                const float4 a = ta, b = tb, c4 = tc;
-                if (i + 1 < lf_cnt) { // fetch the next triangle while this one is tested
-                    const char *tp = reinterpret_cast<const char *>(bvh.tris + lf_first + i + 1);
-                    ta = ld128(tp); tb = ld128(tp + 16); tc = ld128(tp + 32);
-                }
-                n_tris++;
-                float t, u, v;
-                if (!intersect_tri(f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c4.x), o, d, t, u, v)) continue;
-                if (!(t < tmax && ((Alpha && !Any) ? (t > tmin || (t == tmin && f2i(c4.y) > after_id)) : t > tmin))) continue;
-                const int32_t id = f2i(c4.y);
-                if (Any) {
-                    if (Alpha) {
-                        AlphaFilter af = io.alpha;
-                        af.pixel_linear = pixel_linear;
-                        if (!shadow_candidate_passes(af, f2i(c4.z), f2i(c4.w))) continue;
-                    }
-                    best_tri = lf_first + i;
-                    occluded = true;
-                    break;
-                }
-                if (best_tri < 0 || t < best_t || (t == best_t && id < best_id)) {
-                    best_t = t; best_u = u; best_v = v; best_tri = lf_first + i; best_id = id;
-                }
-            }
-            leaf = 0;
-            if (Any && occluded) { // drop the rest of the traversal
-                sp = 0;
-                node = RPTR_EMPTY;
-            } else if (node < 0 && node != RPTR_EMPTY) { // the current item was a second leaf waiting for the slot
-                leaf = node;
-                node = RPTR_POP();
-            }
-        }
-#endif
+        if (have && (ty & 0xffu) == 0u && tsp > 0) { --tsp; tx = tstack_x[tsp]; ty = tstack_y[tsp]; }
     }
+#undef RPTR_PUSH
+#undef RPTR_POP
     // ---- counters ----
     unsigned long long a = n_rays, b = n_nodes, c = n_tris;
     for (int s = 16; s > 0; s >>= 1) {

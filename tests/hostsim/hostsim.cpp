@@ -247,6 +247,21 @@ extern "C" int hostsim_ray_query_layer(const hostsim_scene *s, const hostsim_arg
     return 0;
 }
 
+// traversal statistics of the product's tree over a set of closest-hit queries: out = nodes visited, triangles tested (totals)
+extern "C" void hostsim_trace_stats(const hostsim_scene *s, const rptr_render_ray_query *q, int32_t n, uint64_t *out) {
+    BvhDev bvh{s->hs.nodes.data(), s->hs.leaf_tris.data(), (int32_t)s->hs.nodes.size(), (int32_t)s->hs.leaf_tris.size()};
+    uint64_t nodes = 0, tris = 0;
+#pragma omp parallel for reduction(+ : nodes, tris)
+    for (int32_t i = 0; i < n; ++i) {
+        HitRec h;
+        TraceCounters cnt{0, 0};
+        float3 o = f3(q[i].origin[0], q[i].origin[1], q[i].origin[2]), d = f3(q[i].dir[0], q[i].dir[1], q[i].dir[2]);
+        trace_ray<false>(bvh, o, d, RPTR_RAY_EPSILON * length(o), q[i].t_max, h, cnt);
+        nodes += cnt.nodes; tris += cnt.tris;
+    }
+    out[0] = nodes; out[1] = tris;
+}
+
 // the product's query -> sampler pixel map (TileMap in query mode, csrc/rptr_shading.cuh); wgs_x as rptr_cuda_render_ray_queries computes it
 extern "C" void hostsim_query_pixel(uint32_t q, int32_t n, uint32_t *out) {
     TileMap tm{};

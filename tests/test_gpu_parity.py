@@ -953,3 +953,20 @@ def test_nccl_reduce_inside_the_library_two_devices():
     RenderCuda.reduce_framebuffer_all(rs, root=-1)
     for r in rs:
         assert np.array_equal(r.framebuffer().view(np.uint32), want4.view(np.uint32))
+
+
+def test_concurrent_sub_waves_option_is_bit_identical(oracle):
+    """Option concurrent_waves (sub-waves of whole sample layers on their own streams, resolved in sample order) must not change
+    a bit, with waves that do not divide evenly, alpha-tested materials and the AOV images of the frame's last layer."""
+    s = scenes.alpha_tested_soup(20000)
+    W, H = 320, 180
+    a = make_backend(s, W, H)
+    a.render_spp(s.camera, 7, batch_spp=7)
+    want, want_nd = a.framebuffer(), a.aov(1)
+    for k, wave in ((2, 0), (3, 0), (4, 5 * W * H)):
+        b = make_backend(s, W, H, concurrent_waves=k, **({"wave_paths": wave} if wave else {}))
+        b.render_spp(s.camera, 7, batch_spp=7)
+        assert np.array_equal(b.framebuffer().view(np.uint32), want.view(np.uint32)), k
+        assert np.array_equal(b.aov(1).view(np.uint16), want_nd.view(np.uint16)), k
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=7, batch_spp=7)
+    assert_identical(want, ref, "7 layers in one frame")

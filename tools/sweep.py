@@ -21,8 +21,9 @@ for spec in sys.argv[1:]:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.exit(r.stderr[-3000:])
-    lines.append("RPTR_CUDA_LIB=variants/librptr_cuda_%s.so timeout 300 python bench.py --steps 2 --warmup 2 --spp 16 --no-cpu-baseline "
-                 "> gpurun_out/sweep_%s.json 2> gpurun_out/sweep_%s.err || tail -3 gpurun_out/sweep_%s.err" % (name, name, name, name))
+    lines.append("RPTR_CUDA_LIB=variants/librptr_cuda_%s.so timeout 300 python bench.py --steps 2 --warmup 2 %s --no-cpu-baseline "
+                 "> gpurun_out/sweep_%s.json 2> gpurun_out/sweep_%s.err || tail -3 gpurun_out/sweep_%s.err" % (name, os.environ.get("SWEEP_ARGS", "--spp 16"), name, name, name))
     print("built", name, defs)
+lines.append("python tools/sweep_report.py")
 with open(os.path.join(ROOT, "run_sweep.sh"), "w") as f:
-    f.write("\n".join(lines) + "\n")
+    f.write("mkdir -p gpurun_out\n" + "\n".join(lines) + "\n")
