@@ -75,8 +75,14 @@ static int g_queries;
 
 #include "rendering/rt/materials.glsl"
 #include "rendering/bsdfs/gltf_bsdf.glsl"
+static int (*g_visibility_cb)(void *, const float *, const float *, float) = nullptr; // set by the whole-path driver (ref_path.cpp)
+static void *g_visibility_user = nullptr;
 inline bool raytrace_test_visibility(const vec3 from, const vec3 dir, float dist) {
     g_query_from = from; g_query_dir = dir; g_query_dist = dist; ++g_queries;
+    if (g_visibility_cb) {
+        const float f[3] = {from.x, from.y, from.z}, d[3] = {dir.x, dir.y, dir.z};
+        return g_visibility_cb(g_visibility_user, f, d, dist) != 0;
+    }
     return true;
 }
 #include "rendering/rt/material_textures.glsl" // vulkan/pt_megakernel.glsl:106-109: textures, nee, then the shading function
@@ -85,6 +91,12 @@ inline bool raytrace_test_visibility(const vec3 from, const vec3 dir, float dist
 } // namespace refshade
 
 extern "C" {
+
+// the whole-path driver answers the shadow queries of sample_direct_light itself; null = record the query and say "visible"
+void ref_shade_set_visibility(int (*cb)(void *, const float *, const float *, float), void *user) {
+    refshade::g_visibility_cb = cb;
+    refshade::g_visibility_user = user;
+}
 
 // in : material, state (bounce, output_channel, prev_bounce_pdf), illum[3], throughput[3], approx solid angle of the hit triangle,
 //      w_o[3], interaction (p, gn, n, v_x, v_y: 15 floats), LCG state, render params (max_path_depth, glossy_only_mode),

@@ -1296,6 +1296,41 @@ int oracle_render(const oracle_scene *os, const oracle_render_args *a, float *rg
 // gl_GlobalInvocationID.xy is swizzled inside the workgroup (:17-19) and is what seeds the samplers together with the REAL
 // frame width.  Results are folded by accumulate_query (vulkan/accumulate.glsl:32-42), layer after layer.
 // a->first_sample = view_params.frame_id of the last begin_frame, a->batch_spp = render_params.batch_spp.
+// ---- intersection callbacks for the whole-path driver of oracle/_ref (ref_shim/ref_path.cpp): the reference leaves closest hit
+//      and occlusion to the Vulkan driver, the composed reference path takes them from here (opaque scenes) ----
+struct ref_path_hit { // mirror of the struct in ref_shim/ref_path.cpp
+    float t, u, v;
+    const uint64_t *qverts3;
+    const uint64_t *qnuv3;
+    float scale[3], offset[3];
+    int32_t has_normals, has_uvs;
+    float w2o[9];
+    int32_t material_id;
+    const uint32_t *id_4pack;
+    uint32_t prim;
+};
+int oracle_cb_closest(void *user, const float *o, const float *d, float tmin, float tmax, ref_path_hit *out) {
+    const Scene &s = static_cast<const oracle_scene *>(user)->s;
+    Hit h;
+    if (!closest_hit(s, v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), tmin, tmax, tmin, 0x7fffffff, h)) return 0;
+    const Tri &tr = s.tris[h.tri];
+    const GeomInst &g = s.ginst[tr.geom_inst];
+    out->t = h.t; out->u = h.u; out->v = h.v;
+    out->qverts3 = g.qverts + 3 * (size_t)tr.prim;
+    out->qnuv3 = g.qnuv ? g.qnuv + 3 * (size_t)tr.prim : nullptr;
+    for (int k = 0; k < 3; ++k) { out->scale[k] = g.scale[k]; out->offset[k] = g.offset[k]; }
+    out->has_normals = g.has_normals; out->has_uvs = g.has_uvs;
+    for (int r = 0; r < 3; ++r) { out->w2o[3 * r] = g.w2o_row[r].x; out->w2o[3 * r + 1] = g.w2o_row[r].y; out->w2o[3 * r + 2] = g.w2o_row[r].z; }
+    out->material_id = g.material_id;
+    out->id_4pack = reinterpret_cast<const uint32_t *>(g.tri_mat); // byte k of word i = id of triangle 4 i + k (little endian); must be 4-byte aligned
+    out->prim = (uint32_t)tr.prim;
+    return 1;
+}
+int oracle_cb_occluded(void *user, const float *o, const float *d, float tmin, float tmax) {
+    const Scene &s = static_cast<const oracle_scene *>(user)->s;
+    return any_hit(s, v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), tmin, tmax, [](int, float, float, float) { return true; }) ? 1 : 0;
+}
+
 // out = invocations per row / rows of the virtual square, workgroups per row / column (record_frame + dispatch_rays)
 void oracle_query_dispatch(int32_t n, int32_t *out) {
     out[0] = (int)std::ceil(std::sqrt((float)n));
