@@ -553,8 +553,8 @@ oracle_scene *oracle_scene_create(const rptr_scene_desc *d, const rptr_light_sam
     s.own_texels.resize(d->textures ? d->n_textures : 0);
     for (int t = 0; t < (int)s.own_texels.size(); ++t) {
         rptr_texture_desc td = d->textures[t];
-        if (td.width != 1 || td.height != 1) { delete os; return nullptr; } // 1x1-texel mode only
-        s.own_texels[t].assign(td.texels, td.texels + td.channels);
+        if (td.width < 1 || td.height < 1 || td.channels < 1 || td.channels > 4 || !td.texels) { delete os; return nullptr; }
+        s.own_texels[t].assign(td.texels, td.texels + (size_t)td.width * td.height * td.channels);
         td.texels = s.own_texels[t].data();
         s.textures.push_back(td);
     }
@@ -873,14 +873,16 @@ static bool test_visibility(const Frame &f, V3 from, V3 dir, float dist, float g
     if (shadow_ray_range(from, dist, geometry_scale, tmin, tmax)) {
         cnt.shadow_rays++;
         const Scene &s = *f.s;
-        bool occluded = any_hit(s, from, dir, tmin, tmax, [&](int id, float, float, float) {
+        bool occluded = any_hit(s, from, dir, tmin, tmax, [&](int id, float t, float bu, float bv) {
             const Tri &tr = s.tris[id];
             const GeomInst &g = s.ginst[tr.geom_inst];
             if (g.flags & RPTR_GEOMETRY_FLAGS_NOALPHA) return true;
             const rptr_base_material &m = s.materials[calc_hit_material_id(g, (uint32_t)tr.prim)];
             if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) return true;
             Lcg arng = shadow_alpha_rng((uint32_t)tr.prim, (uint32_t)g.instance, frame_id, f.a->frame_offset, pixel_linear);
-            return !alpha_test_rejects(material_alpha(s.texset, m), arng);
+            // generate_candidate_hit (:153-211): the candidate's own hit attributes give the uv of the alpha lookup
+            const V2 uv = TextureSet::is_handle(m.base_color[0]) ? calc_hit_attributes(g, t, (uint32_t)tr.prim, bu, bv).uv : V2{0.0f, 0.0f};
+            return !alpha_test_rejects(material_alpha(s.texset, m, uv), arng);
         });
         return !occluded;
     }
@@ -981,12 +983,12 @@ static void store_motion_jitter_aovs(const Frame &f, V3 position, V3 motion_vect
 enum { SHADING_RESULT_TERMINATE = -1, SHADING_RESULT_BOUNCE = 1 };
 template <class Vis>
 static int shade_base_material(const Frame &f, int &bounce, float &prev_bounce_pdf, V3 &illum, V3 &throughput, const rptr_base_material &mp,
-                               float approx_sa, V3 w_o, V3 ip, V3 ign, V3 in_, V3 v_x, V3 v_y, PathRng &rng, V3 &w_i, AovOut *aov, Vis &&visible) {
+                               float approx_sa, V3 w_o, V3 ip, V3 ign, V3 in_, V3 v_x, V3 v_y, PathRng &rng, V3 &w_i, AovOut *aov, V2 uv, Vis &&visible) {
     const oracle_render_args &a = *f.a;
     const float p_sun = f.sp.sun_radiance[3];
     GltfMat mat;
     V3 emit;
-    unpack_material(mat, emit, mp, f.tr, f.s->texset);
+    unpack_material(mat, emit, mp, f.tr, f.s->texset, uv);
     if (aov && bounce == 0) { // pt_megakernel.glsl:670-672 + shade_base_material.glsl:28-31
         const V3 alb = throughput * mat.base_color;
         const float m[8] = {alb.x, alb.y, alb.z, mat.ior != 1.0f ? mat.roughness : 1.0f, in_.x, in_.y, in_.z, length(ip - f.cam_pos)};
@@ -1057,7 +1059,7 @@ static void bounce_prologue(RTHit &h, const rptr_base_material &mp, const Textur
         V3 t_x = cross(t_y, h.normal);
         t_x = t_x * length(h.tangent);
         t_y = t_y * h.bitangent_l;
-        TextureSet::RGBA tx = texset.texel((uint32_t)mp.normal_map);
+        TextureSet::RGBA tx = texset.sample((uint32_t)mp.normal_map, h.uv); // textureLod(.., hit.uv, bounce): base level (single-level images)
         V3 map_nrm = v3(2.0f * tx.r - 1.0f, 2.0f * tx.g - 1.0f, 1.0f * tx.b - 0.0f);
         map_nrm.z = sqrtf(fmaxf(1.0f - map_nrm.x * map_nrm.x - map_nrm.y * map_nrm.y, 0.0f));
         in_ = normalize(mat_mul(t_x, t_y, in_ * normal_z_scale, map_nrm));
@@ -1162,7 +1164,8 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
             if (g.flags & RPTR_GEOMETRY_FLAGS_NOALPHA) break;
             const rptr_base_material &m = s.materials[calc_hit_material_id(g, (uint32_t)tr.prim)];
             if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) break;
-            float alpha = material_alpha(s.texset, m);
+            const V2 cuv = TextureSet::is_handle(m.base_color[0]) ? calc_hit_attributes(g, hit.t, (uint32_t)tr.prim, hit.u, hit.v).uv : V2{0.0f, 0.0f};
+            float alpha = material_alpha(s.texset, m, cuv);
             if (!(alpha > 0.0f) || (alpha < 1.0f && rng.draw_alpha() > alpha)) {
                 after_t = hit.t;
                 after_id = hit.tri;
@@ -1196,7 +1199,7 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         // ---- shade_base_material ----
         V3 w_i;
         {
-            const int result = shade_base_material(f, bounce, prev_bounce_pdf, illum, throughput, mp, approx_sa, w_o, ip, ign, in_, v_x, v_y, rng, w_i, aov,
+            const int result = shade_base_material(f, bounce, prev_bounce_pdf, illum, throughput, mp, approx_sa, w_o, ip, ign, in_, v_x, v_y, rng, w_i, aov, h.uv,
                                                    [&](V3 from, V3 dir, float dist) {
                                                        return test_visibility(f, from, dir, dist, geometry_scale, linear, view_frame_id, cnt);
                                                    });
@@ -1515,7 +1518,7 @@ float oracle_fast_positive_atan(float y) { return fast_positive_atan(y); }
 static GltfMat mat_from(const rptr_base_material *p, int tr) {
     GltfMat m;
     V3 e;
-    unpack_material(m, e, *p, tr != 0, TextureSet());
+    unpack_material(m, e, *p, tr != 0, TextureSet(), V2{0.0f, 0.0f});
     return m;
 }
 void oracle_gltf_bsdf(const rptr_base_material *p, const float *n, const float *wo, const float *wi, int tr, float *out) {
@@ -1612,7 +1615,7 @@ void oracle_shade_base_material(const rptr_base_material *p, int bounce, int out
     const float pdf_before = prev_bounce_pdf;
     const int result = shade_base_material(f, bounce, prev_bounce_pdf, il, thr, *p, approx_sa, v3(wo[0], wo[1], wo[2]), v3(ia[0], ia[1], ia[2]),
                                            v3(ia[3], ia[4], ia[5]), v3(ia[6], ia[7], ia[8]), v3(ia[9], ia[10], ia[11]), v3(ia[12], ia[13], ia[14]), rng,
-                                           w_i, nullptr, [&](V3, V3 dir, float dist) {
+                                           w_i, nullptr, V2{0.0f, 0.0f}, [&](V3, V3 dir, float dist) {
                                                ++queries; qd = dir; qdist = dist;
                                                return true;
                                            });
@@ -1648,7 +1651,7 @@ void oracle_sample_direct_light(const rptr_base_material *p, const float *hp, co
     f.tr = false;
     GltfMat m;
     V3 e;
-    unpack_material(m, e, *p, false, TextureSet());
+    unpack_material(m, e, *p, false, TextureSet(), V2{0.0f, 0.0f});
     int queries = 0;
     V3 qf = v3(0.0f), qd = v3(0.0f);
     float qdist = 0.0f;
@@ -1665,6 +1668,14 @@ void oracle_sample_direct_light(const rptr_base_material *p, const float *hp, co
     out[7] = r.mis_pdf; out[8] = (float)queries;
     out[9] = qf.x; out[10] = qf.y; out[11] = qf.z; out[12] = qd.x; out[13] = qd.y; out[14] = qd.z; out[15] = qdist;
 }
+// the texture unit (shading_oracle.h TextureSet::sample) on one texture: out = rgba
+void oracle_sample_texture(const rptr_texture_desc *t, float u, float v, float *out) {
+    TextureSet ts;
+    ts.tex = t;
+    ts.n = 1;
+    const TextureSet::RGBA c = ts.sample(0u, V2{u, v});
+    out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = c.a;
+}
 // unpack_material + get_material_alpha with 8-bit 1 x 1 textures; same output layout as ref_unpack_material
 void oracle_unpack_material(const rptr_base_material *p, const rptr_texture_desc *textures, int n_textures, int transmission, float *out) {
     TextureSet ts;
@@ -1673,8 +1684,8 @@ void oracle_unpack_material(const rptr_base_material *p, const rptr_texture_desc
     GltfMat m;
     V3 e;
     std::memset(out, 0, 17 * sizeof(float));
-    out[15] = unpack_material(m, e, *p, transmission != 0, ts);
-    out[16] = material_alpha(ts, *p);
+    out[15] = unpack_material(m, e, *p, transmission != 0, ts, V2{0.0f, 0.0f});
+    out[16] = material_alpha(ts, *p, V2{0.0f, 0.0f});
     out[0] = m.base_color.x; out[1] = m.base_color.y; out[2] = m.base_color.z;
     out[3] = m.metallic; out[4] = m.specular; out[5] = m.roughness; out[6] = m.ior;
     if (transmission) {

@@ -62,9 +62,12 @@ struct GltfMat {
 };
 static inline bool is_textured(float v) { return (f2u(v) & 0x80000000u) != 0; }
 
-// ---- textures: rendering/rt/material_textures.glsl:37-63 in 1x1-texel mode -------------------------------
-// A 1 x 1 texture returns its only texel whatever the uv / LOD.  UNORM8 -> v / 255; colour channels of an sRGB image through
-// the sRGB transfer function, evaluated in double and rounded once (our statement of the texture unit's table).
+// ---- textures: rendering/rt/material_textures.glsl:37-63 -----------------------------------------------------------------
+// The texture unit is hardware in the reference (VkSampler: LINEAR filters, REPEAT addressing, vulkan/render_vulkan.cpp:1655-1671);
+// this is the statement oracle and product share (RPTR-FP): base level, texel centres at (i + 0.5) / size, bilinear weights and
+// blends in binary32 as written, UNORM8 -> v / 255, colour channels of an sRGB image through the sRGB transfer function
+// (evaluated in double and rounded once) per texel before filtering.  A 1 x 1 texture returns its only texel for every uv.
+// Mip selection from ray differentials (textureGrad, 12x anisotropy) is hardware-defined and not restated: images are single-level.
 struct TextureSet {
     const rptr_texture_desc *tex = nullptr;
     int n = 0;
@@ -74,41 +77,58 @@ struct TextureSet {
         double c = (double)v / 255.0;
         return (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
     }
-    RGBA texel(uint32_t id) const {
-        const rptr_texture_desc &t = tex[id];
-        bool srgb = t.color_space == RPTR_COLOR_SPACE_SRGB;
+    static RGBA texel_at(const rptr_texture_desc &t, int x, int y) {
+        const bool srgb = t.color_space == RPTR_COLOR_SPACE_SRGB;
+        const uint8_t *px = t.texels + ((size_t)y * t.width + x) * t.channels;
         float ch[4] = {0.0f, 0.0f, 0.0f, 1.0f};
-        for (int k = 0; k < t.channels && k < 4; ++k) ch[k] = k == 3 ? (float)t.texels[3] / 255.0f : decode(t.texels[k], srgb);
+        for (int k = 0; k < t.channels && k < 4; ++k) ch[k] = k == 3 ? (float)px[3] / 255.0f : decode(px[k], srgb);
         return RGBA{ch[0], ch[1], ch[2], ch[3]};
+    }
+    RGBA texel(uint32_t id) const { return texel_at(tex[id], 0, 0); }
+    static int wrap(int i, int n) {
+        int r = i % n;
+        return r < 0 ? r + n : r;
+    }
+    static float blend(float a, float b, float t) { return a + (b - a) * t; }
+    RGBA sample(uint32_t id, V2 uv) const {
+        const rptr_texture_desc &t = tex[id];
+        float x = uv.x * (float)t.width - 0.5f, y = uv.y * (float)t.height - 0.5f;
+        if (!(fabsf(x) < 1.0e9f) || !(fabsf(y) < 1.0e9f)) { x = 0.0f; y = 0.0f; }
+        const float xf = floorf(x), yf = floorf(y);
+        const float wx = x - xf, wy = y - yf;
+        const int x0 = wrap((int)xf, t.width), x1 = wrap(x0 + 1, t.width), y0 = wrap((int)yf, t.height), y1 = wrap(y0 + 1, t.height);
+        const RGBA a = texel_at(t, x0, y0), b = texel_at(t, x1, y0), c = texel_at(t, x0, y1), d = texel_at(t, x1, y1);
+        return RGBA{blend(blend(a.r, b.r, wx), blend(c.r, d.r, wx), wy), blend(blend(a.g, b.g, wx), blend(c.g, d.g, wx), wy),
+                    blend(blend(a.b, b.b, wx), blend(c.b, d.b, wx), wy), blend(blend(a.a, b.a, wx), blend(c.a, d.a, wx), wy)};
     }
     static bool is_handle(float x) { return (f2u(x) & RPTR_TEXTURED_PARAM_MASK) != 0; }
     // textured_color_param(vec4(p.base_color, 1), hit)
-    RGBA color_param(const float *rgb) const {
-        if (is_handle(rgb[0])) return texel(RPTR_GET_TEXTURE_ID(f2u(rgb[0])));
+    RGBA color_param(const float *rgb, V2 uv) const {
+        if (is_handle(rgb[0])) return sample(RPTR_GET_TEXTURE_ID(f2u(rgb[0])), uv);
         return RGBA{rgb[0], rgb[1], rgb[2], 1.0f};
     }
     // textured_scalar_param(x, hit)
-    float scalar_param(float x) const {
+    float scalar_param(float x, V2 uv) const {
         if (!is_handle(x)) return x;
-        RGBA t = texel(RPTR_GET_TEXTURE_ID(f2u(x)));
+        RGBA t = sample(RPTR_GET_TEXTURE_ID(f2u(x)), uv);
         const float ch[4] = {t.r, t.g, t.b, t.a};
         return ch[RPTR_GET_TEXTURE_CHANNEL(f2u(x))];
     }
 };
 // get_material_alpha (material_textures.glsl:137-145)
-static inline float material_alpha(const TextureSet &ts, const rptr_base_material &p) { return ts.color_param(p.base_color).a; }
+static inline float material_alpha(const TextureSet &ts, const rptr_base_material &p, V2 uv) { return ts.color_param(p.base_color, uv).a; }
 
 // unpack_material (material_textures.glsl:95-135, non-unrolled standard-texture semantics of rendering/rt/materials.glsl:42-49);
 // returns alpha
-static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_material &p, bool transmission, const TextureSet &ts) {
-    TextureSet::RGBA texel = ts.color_param(p.base_color);
+static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_material &p, bool transmission, const TextureSet &ts, V2 uv) {
+    TextureSet::RGBA texel = ts.color_param(p.base_color, uv);
     float alpha = texel.a;
     m.base_color = v3(texel.r, texel.g, texel.b);
     if (alpha > 0.001f) m.base_color = m.base_color / alpha; // PREMULTIPLIED_BASE_COLOR_ALPHA
-    m.specular = ts.scalar_param(p.specular);
-    m.roughness = ts.scalar_param(p.roughness);
-    m.metallic = ts.scalar_param(p.metallic);
-    m.ior = ts.scalar_param(p.ior);
+    m.specular = ts.scalar_param(p.specular, uv);
+    m.roughness = ts.scalar_param(p.roughness, uv);
+    m.metallic = ts.scalar_param(p.metallic, uv);
+    m.ior = ts.scalar_param(p.ior, uv);
     emit = v3(p.base_color[0], p.base_color[1], p.base_color[2]) * p.emission_intensity;
     if (p.emission_intensity != 0.0f) {
         if (TextureSet::is_handle(p.base_color[0])) emit = m.base_color * p.emission_intensity;
@@ -119,7 +139,7 @@ static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_materi
     m.transmission_color = v3(0.0f);
     m.transmission_roughness = 0.0f;
     if (transmission) {
-        m.specular_transmission = ts.scalar_param(p.specular_transmission);
+        m.specular_transmission = ts.scalar_param(p.specular_transmission, uv);
         if (m.specular_transmission > 0.0f) {
             if (!(m.ior > 1.0f)) {
                 alpha *= 1.0f - m.specular_transmission;
@@ -127,7 +147,7 @@ static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_materi
             } else {
                 m.transmission_color = m.base_color;
                 m.transmission_roughness = m.roughness;
-                m.roughness = sqrtf(ts.scalar_param(p.clearcoat_gloss));
+                m.roughness = sqrtf(ts.scalar_param(p.clearcoat_gloss, uv));
             }
         }
     }

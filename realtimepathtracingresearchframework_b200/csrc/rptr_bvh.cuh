@@ -119,17 +119,18 @@ struct TraceCounters { uint32_t nodes, tris; };
 // for every rejected candidate.  Visibility rays (:216-272): every candidate gets its own LCG seeded from
 // (primitive ^ frame_id, instance ^ frame_offset, pixel), so the verdict does not depend on the traversal order.
 struct AlphaFilter {
-    const GeomInst *ginst;
+    SceneDev scene;                  // geometry instances (per-candidate seeds), materials + textures (alpha of textured candidates)
     uint32_t frame_id, frame_offset; // view_params.frame_id / frame_offset of the frame (batch)
     uint32_t pixel_linear;           // gl_GlobalInvocationID.x + y * frame_dims.x
 };
 RPTR_HD bool alpha_rejects(float alpha, uint32_t &lcg_state) { return !(alpha > 0.0f) || (alpha < 1.0f && lcg_randomf(lcg_state) > alpha); }
-RPTR_HD bool shadow_candidate_passes(const AlphaFilter &f, int32_t gi_alpha, int32_t prim) {
+// (u, v) = barycentrics of the candidate: only read when its alpha comes from a texture larger than 1 x 1
+RPTR_HD bool shadow_candidate_passes(const AlphaFilter &f, int32_t gi_alpha, int32_t prim, float u, float v) {
     const int32_t a8 = (int32_t)(((uint32_t)gi_alpha) >> 24);
-    if (a8 == RPTR_TRI_OPAQUE) return true;
-    const GeomInst &g = f.ginst[gi_alpha & 0x00ffffff];
+    if (a8 == RPTR_TRI_OPAQUE && !(gi_alpha & RPTR_TRI_TEXTURED_ALPHA)) return true;
+    const GeomInst &g = f.scene.ginst[gi_alpha & 0x007fffff];
     uint32_t st = lcg_seed((uint32_t)prim ^ f.frame_id, (uint32_t)g.instance ^ f.frame_offset, f.pixel_linear);
-    return !alpha_rejects(alpha8_to_float(a8), st);
+    return !alpha_rejects(candidate_alpha(f.scene, gi_alpha, prim, u, v), st);
 }
 
 RPTR_HD float slab_safe(float d) { return fabsf(d) > 1e-18f ? d : copysignf(1e-18f, d); }
@@ -317,7 +318,7 @@ RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float 
             if (!(t > tmin && t < tmax)) continue;
             const int32_t id = f2i(c4.y);
             if (Any) {
-                if (filter && !shadow_candidate_passes(*filter, f2i(c4.z), f2i(c4.w))) continue;
+                if (filter && !shadow_candidate_passes(*filter, f2i(c4.z), f2i(c4.w), u, v)) continue;
                 best.t = t; best.u = u; best.v = v; best.tri = ti; best.id = id;
                 return true;
             }
@@ -344,13 +345,15 @@ RPTR_HD bool trace_ray(const BvhDev &bvh, float3 o, float3 d, float tmin, float 
 
 // Closest hit with the front-to-back candidate filter; lcg_state is the path's LCG (alpha_rng == rng for the LCG pointset,
 // pt_megakernel.glsl:354-355) and advances by one draw per candidate with 0 < alpha < 1.
-RPTR_HD bool closest_hit_filtered(const BvhDev &bvh, float3 o, float3 d, float tmin, float tmax, uint32_t &lcg_state, HitRec &best, TraceCounters &cnt) {
+RPTR_HD bool closest_hit_filtered(const BvhDev &bvh, const SceneDev &sc, float3 o, float3 d, float tmin, float tmax, uint32_t &lcg_state, HitRec &best,
+                                 TraceCounters &cnt) {
     float after_t = tmin;
     int32_t after_id = 0x7fffffff;
     for (;;) {
         if (!trace_ray<false>(bvh, o, d, tmin, tmax, best, cnt, after_t, after_id, nullptr)) return false;
-        const int32_t a8 = tri_alpha8(bvh.tris[best.tri]);
-        if (a8 == RPTR_TRI_OPAQUE || !alpha_rejects(alpha8_to_float(a8), lcg_state)) return true;
+        const Tri &tr = bvh.tris[best.tri];
+        if (tri_alpha8(tr) == RPTR_TRI_OPAQUE && !(tr.gi_alpha & RPTR_TRI_TEXTURED_ALPHA)) return true;
+        if (!alpha_rejects(candidate_alpha(sc, tr.gi_alpha, tr.prim, best.u, best.v), lcg_state)) return true;
         after_t = best.t;
         after_id = best.id;
     }

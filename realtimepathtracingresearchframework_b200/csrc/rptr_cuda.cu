@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave
 }
 
 // closest hit for the live paths of bounce d
-__global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_t *queue, const uint32_t *count, DevCounters *dc, uint32_t *hit_count) {
+__global__ void __launch_bounds__(128) k_trace(BvhDev bvh, SceneDev sc, Wave w, const uint32_t *queue, const uint32_t *count, DevCounters *dc, uint32_t *hit_count) {
     const uint32_t n = *count;
     TraceCounters cnt{0, 0};
     unsigned long long rays = 0;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, Wave w, const uint32_
         uint32_t *ap = w.rng3 ? w.rng3 + slot : &w.rngb[slot].x;
         uint32_t st = *ap;
         const uint32_t before = st;
-        closest_hit_filtered(bvh, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, st, h, cnt);
+        closest_hit_filtered(bvh, sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, d.w, st, h, cnt);
         if (st != before) *ap = st;
         w.hit[slot] = f4(h.t, h.u, h.v, __int_as_float(h.tri));
         if (hit_count) {
@@ -522,6 +522,7 @@ struct rptr_ctx {
     int32_t n_lights = 0;
     std::vector<rptr_base_material> materials_host; // resolved materials (texture handles folded in), for per-frame host decisions
     bool any_normal_map = false;
+    bool any_textured = false;     // some material parameter refers to a texture larger than 1 x 1 (RPTR_FEAT_TEXTURES shade variant)
     bool any_alpha_tested = false; // some triangle needs the stochastic alpha candidate filter (Alpha variants of the trace kernels)
     std::vector<rptr_tri_light_data> lights_host;
     rptr_scene_params scene_params{};
@@ -899,7 +900,24 @@ static int upload_scene(rptr_ctx *ctx, HostScene &hs, SceneUpload &up) {
     CU(cudaMemcpy(d_ntex, hs.normal_texels.data(), hs.materials.size() * sizeof(float4), cudaMemcpyHostToDevice));
     CU(dev_alloc(ctx, &d_lights, hs.lights.size(), up.allocs));
     if (!hs.lights.empty()) CU(cudaMemcpy(d_lights, hs.lights.data(), hs.lights.size() * sizeof(rptr_tri_light_data), cudaMemcpyHostToDevice));
-    up.scene = SceneDev{d_gi, d_mat, d_lights, d_ntex};
+    // textures larger than 1 x 1 (the others were folded into the materials): RGBA8 texels + the table, and the sRGB decode table
+    std::vector<TexDev> tex(hs.textures.size());
+    for (size_t t = 0; t < hs.textures.size(); ++t) {
+        const HostTexture &ht = hs.textures[t];
+        tex[t] = TexDev{nullptr, ht.width, ht.height, ht.srgb, 0};
+        if (ht.rgba.empty()) continue;
+        uchar4 *d_px;
+        CU(dev_alloc(ctx, &d_px, ht.rgba.size() / 4, up.allocs));
+        CU(cudaMemcpy(d_px, ht.rgba.data(), ht.rgba.size(), cudaMemcpyHostToDevice));
+        tex[t].texels = d_px;
+    }
+    TexDev *d_tex;
+    float *d_lut;
+    CU(dev_alloc(ctx, &d_tex, tex.size(), up.allocs));
+    if (!tex.empty()) CU(cudaMemcpy(d_tex, tex.data(), tex.size() * sizeof(TexDev), cudaMemcpyHostToDevice));
+    CU(dev_alloc(ctx, &d_lut, 256, up.allocs));
+    CU(cudaMemcpy(d_lut, hs.srgb_lut, sizeof(hs.srgb_lut), cudaMemcpyHostToDevice));
+    up.scene = SceneDev{d_gi, d_mat, d_lights, d_ntex, d_tex, d_lut};
 
     // largest |coordinate| of the scene: scale of the conservative box padding (rptr_host.cpp build_bvh) and of the range of
     // ray origins the slab test is guaranteed for (begin_frame / trace_rays check it)
@@ -982,6 +1000,7 @@ int rptr_cuda_set_scene(rptr_ctx *ctx, const rptr_scene_desc *desc, const rptr_l
     ctx->lights_host = hs.lights;
     ctx->any_alpha_tested = hs.any_alpha_tested;
     ctx->any_normal_map = hs.any_normal_map;
+    ctx->any_textured = hs.any_textured;
     ctx->materials_host = hs.materials;
     ctx->has_scene = true;
     ctx->frame_id = 0; // vulkan/render_vulkan.cpp:1556
@@ -1171,7 +1190,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
     }
     const int sort_tiles = multi_path ? 2 : 1; // 1: the tile sort only moves the misses aside (key = hit / miss, no material lookup)
     // per-candidate seeds of alpha-tested shadow rays: view_params.frame_id / frame_offset of this frame (pt_megakernel.glsl:252-254)
-    const AlphaFilter alpha_filter{ctx->scene.ginst, fp.first_sample, fp.frame_offset, 0u};
+    const AlphaFilter alpha_filter{ctx->scene, fp.first_sample, fp.frame_offset, 0u};
     const uint32_t alpha_stride = ctx->rng_variant != 0 ? 1u : 2u;
     // trace: one RPTR_TRACE_THREADS CTA per SM; dynamic smem = the staged top of the BVH + the LUT + the shared stack part
     const int g_trace = grid_for(ctx, 8), g_light = grid_for(ctx, 4), g_pt = grid_for(ctx, 1);
@@ -1179,7 +1198,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
     // smallest compiled shade variant that covers the features this frame uses (rptr_shading.cuh, RPTR_FEAT_*)
     const int feat = (fp.transmission ? RPTR_FEAT_TRANSMISSION : 0) | (fp.n_lights > 0 ? RPTR_FEAT_TRI_LIGHTS : 0) |
                      (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0) |
-                     (ctx->any_normal_map ? RPTR_FEAT_NORMAL_MAPS : 0);
+                     (ctx->any_normal_map ? RPTR_FEAT_NORMAL_MAPS : 0) | (ctx->any_textured ? RPTR_FEAT_TEXTURES : 0);
     const bool overlap = fp.output_channel == 0 && ctx->overlap_shadow && ctx->trace_kernel == 0;
 
     struct Sub { // one sub-wave in flight
@@ -1270,7 +1289,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_main>>>(
                             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
                     } else
-                        k_trace<<<g_trace, 128, 0, sb.s_main>>>(ctx->bvh, w, q, cn, ctx->dcounters, sb.hitq ? w.hit_counts + d : nullptr);
+                        k_trace<<<g_trace, 128, 0, sb.s_main>>>(ctx->bvh, ctx->scene, w, q, cn, ctx->dcounters, sb.hitq ? w.hit_counts + d : nullptr);
                     ctx->launches++;
                 }
                 if (join_shadow(sb)) return 1; // shade reads illum and rewrites the shadow queue: the overlapped shadow launch must be done
@@ -1546,7 +1565,7 @@ int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, in
     if (ctx->trace_kernel == 0) {
         k_rq_prepare<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(dq, n, ctx->tr_ray_o, ctx->tr_ray_d, ctx->tr_counts);
         TraceIO io{ctx->tr_ray_o, ctx->tr_ray_d, nullptr, ctx->tr_counts, ctx->tr_counts + 1, ctx->tr_hit, nullptr, nullptr, nullptr, nullptr, nullptr, 0u,
-                   AlphaFilter{nullptr, 0u, 0u, 0u}, TileMap{}};
+                   AlphaFilter{SceneDev{}, 0u, 0u, 0u}, TileMap{}};
         k_trace_persistent<false, false><<<grid_for(ctx, 1), RPTR_TRACE_THREADS, RPTR_TRACE_SMEM_BYTES, ctx->stream>>>(
             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
         k_rq_pack<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->bvh, dq, n, ctx->tr_hit, dr, hit_t ? dt : nullptr);

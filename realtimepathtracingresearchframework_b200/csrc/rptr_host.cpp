@@ -275,14 +275,17 @@ float srgb8_to_linear(int v) {
     return (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
 }
 struct Texel { float c[4]; int a8; };
-Texel fetch_texel(const rptr_scene_desc &d, uint32_t handle) {
-    const uint32_t id = RPTR_GET_TEXTURE_ID(handle);
+const rptr_texture_desc &texture_of(const rptr_scene_desc &d, uint32_t handle_or_id) {
+    const uint32_t id = RPTR_GET_TEXTURE_ID(handle_or_id);
     if (!d.textures || id >= (uint32_t)d.n_textures) throw std::runtime_error("material refers to texture " + std::to_string(id) + " which the scene does not have");
     const rptr_texture_desc &t = d.textures[id];
-    if (t.width != 1 || t.height != 1)
-        throw std::runtime_error("texture " + std::to_string(id) + " is " + std::to_string(t.width) + " x " + std::to_string(t.height) +
-                                 ": only 1 x 1 textures are supported by this backend yet (1x1-texel mode)");
+    if (t.width < 1 || t.height < 1 || t.width > 32768 || t.height > 32768) throw std::runtime_error("texture " + std::to_string(id) + " has an invalid size");
     if (t.channels < 1 || t.channels > 4 || !t.texels) throw std::runtime_error("texture " + std::to_string(id) + " has no texels / bad channel count");
+    return t;
+}
+bool is_one_texel(const rptr_texture_desc &t) { return t.width == 1 && t.height == 1; }
+Texel fetch_texel(const rptr_scene_desc &d, uint32_t handle) { // the only texel of a 1 x 1 texture
+    const rptr_texture_desc &t = texture_of(d, handle);
     Texel x;
     for (int k = 0; k < 3; ++k) {
         const int v = k < t.channels ? t.texels[k] : 0;
@@ -293,40 +296,72 @@ Texel fetch_texel(const rptr_scene_desc &d, uint32_t handle) {
     return x;
 }
 bool is_handle(float v) { return (f2u(v) & RPTR_TEXTURED_PARAM_MASK) != 0; }
-// textured_scalar_param (material_textures.glsl:50-63)
-float resolve_scalar(const rptr_scene_desc &d, float v) {
+// textured_scalar_param (material_textures.glsl:50-63): folded when the texture has one texel, left as a handle otherwise
+float resolve_scalar(const rptr_scene_desc &d, float v, bool &kept_handle) {
     if (!is_handle(v)) return v;
+    if (!is_one_texel(texture_of(d, f2u(v)))) { kept_handle = true; return v; }
     return fetch_texel(d, f2u(v)).c[RPTR_GET_TEXTURE_CHANNEL(f2u(v))];
 }
 } // namespace
 
 // unpack_material's texture reads (material_textures.glsl:95-135, non-unrolled standard-texture semantics of
-// rendering/rt/materials.glsl:42-49) folded into the BaseMaterial; alpha8 = the texel get_material_alpha() would read.
+// rendering/rt/materials.glsl:42-49): parameters that refer to 1 x 1 textures are folded into the BaseMaterial (a 1 x 1 texture
+// returns its only texel for every uv and LOD), alpha8 = the texel get_material_alpha() would read; parameters that refer to
+// larger textures keep their handles and are sampled at the hit's uv on the device (rptr_shading.cuh: sample_texture).
 static void resolve_materials(const rptr_scene_desc &d, HostScene &s) {
     s.materials.assign(d.materials, d.materials + d.n_materials);
     s.material_alpha8.assign(d.n_materials, RPTR_TRI_OPAQUE);
+    s.material_alpha_textured.assign(d.n_materials, 0);
     s.normal_texels.assign(4 * (size_t)d.n_materials, 0.0f);
+    for (int v = 0; v < 256; ++v) s.srgb_lut[v] = srgb8_to_linear(v);
+    s.textures.assign(d.textures ? (size_t)d.n_textures : 0, HostTexture());
+    for (size_t t = 0; t < s.textures.size(); ++t) {
+        const rptr_texture_desc &td = texture_of(d, (uint32_t)t);
+        HostTexture &ht = s.textures[t];
+        ht.width = td.width; ht.height = td.height; ht.srgb = td.color_space == RPTR_COLOR_SPACE_SRGB;
+        if (is_one_texel(td)) continue;
+        const size_t n = (size_t)td.width * td.height;
+        ht.rgba.resize(4 * n);
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 4; ++k) ht.rgba[4 * i + k] = k < td.channels ? td.texels[i * td.channels + k] : (k == 3 ? 255 : 0);
+    }
     for (int i = 0; i < d.n_materials; ++i) {
         rptr_base_material &m = s.materials[i];
+        bool kept = false;
         if (m.normal_map != -1) { // the normal-map texel as textureLod(...).rgb returns it (pt_megakernel.glsl:647)
-            const Texel x = fetch_texel(d, (uint32_t)m.normal_map);
-            s.normal_texels[4 * i + 0] = x.c[0]; s.normal_texels[4 * i + 1] = x.c[1]; s.normal_texels[4 * i + 2] = x.c[2];
+            if (is_one_texel(texture_of(d, (uint32_t)m.normal_map))) {
+                const Texel x = fetch_texel(d, (uint32_t)m.normal_map);
+                s.normal_texels[4 * i + 0] = x.c[0]; s.normal_texels[4 * i + 1] = x.c[1]; s.normal_texels[4 * i + 2] = x.c[2];
+            } else {
+                s.normal_texels[4 * i + 3] = 1.0f; // sampled at the hit's uv
+                kept = true;
+            }
             s.any_normal_map = true;
         }
         if (is_handle(m.base_color[0])) {
             if (m.emission_intensity != 0.0f) throw std::runtime_error("emissive materials with a textured base colour are not supported by this backend yet");
-            const Texel x = fetch_texel(d, f2u(m.base_color[0]));
-            const float alpha = x.c[3];
-            for (int k = 0; k < 3; ++k) m.base_color[k] = alpha > 0.001f ? x.c[k] / alpha : x.c[k]; // PREMULTIPLIED_BASE_COLOR_ALPHA, :101-104
-            s.material_alpha8[i] = x.a8;
+            if (is_one_texel(texture_of(d, f2u(m.base_color[0])))) {
+                const Texel x = fetch_texel(d, f2u(m.base_color[0]));
+                const float alpha = x.c[3];
+                for (int k = 0; k < 3; ++k) m.base_color[k] = alpha > 0.001f ? x.c[k] / alpha : x.c[k]; // PREMULTIPLIED_BASE_COLOR_ALPHA, :101-104
+                s.material_alpha8[i] = x.a8;
+            } else {
+                kept = true;
+                // three- or fewer-channel images have alpha 1 everywhere: nothing to test during traversal
+                if (texture_of(d, f2u(m.base_color[0])).channels == 4) s.material_alpha_textured[i] = 1;
+            }
         }
-        m.specular = resolve_scalar(d, m.specular);
-        m.roughness = resolve_scalar(d, m.roughness);
-        m.metallic = resolve_scalar(d, m.metallic);
-        m.ior = resolve_scalar(d, m.ior);
-        m.specular_transmission = resolve_scalar(d, m.specular_transmission);
-        m.clearcoat_gloss = resolve_scalar(d, m.clearcoat_gloss);
-        if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) s.material_alpha8[i] = RPTR_TRI_OPAQUE; // never alpha-tested (pt_megakernel.glsl:202)
+        m.specular = resolve_scalar(d, m.specular, kept);
+        m.roughness = resolve_scalar(d, m.roughness, kept);
+        m.metallic = resolve_scalar(d, m.metallic, kept);
+        m.ior = resolve_scalar(d, m.ior, kept);
+        m.specular_transmission = resolve_scalar(d, m.specular_transmission, kept);
+        m.clearcoat_gloss = resolve_scalar(d, m.clearcoat_gloss, kept);
+        if (m.flags & RPTR_BASE_MATERIAL_NOALPHA) { // never alpha-tested (pt_megakernel.glsl:202)
+            s.material_alpha8[i] = RPTR_TRI_OPAQUE;
+            s.material_alpha_textured[i] = 0;
+        }
+        if (kept) s.any_textured = true;
     }
 }
 
@@ -359,7 +394,7 @@ void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config
     {
         size_t n_gi = 0;
         for (int i = 0; i < d.n_instances; ++i) n_gi += (size_t)d.meshes[d.pmeshes[d.instances[i].pmesh_id].mesh_id].n_geometries;
-        if (n_gi >= (1u << 24)) throw std::runtime_error("too many (instance, geometry) pairs (limit 2^24)");
+        if (n_gi >= (1u << 23)) throw std::runtime_error("too many (instance, geometry) pairs (limit 2^23)");
     }
     s.tris.reserve(total);
 
@@ -422,9 +457,12 @@ void build_host_scene(const rptr_scene_desc &d, const rptr_light_sampling_config
                 tr.e1x = e1.x; tr.e1y = e1.y; tr.e1z = e1.z;
                 tr.e2x = e2.x; tr.e2y = e2.y; tr.e2z = e2.z;
                 tr.id = (int32_t)s.tris.size();
-                const int32_t a8 = no_alpha ? RPTR_TRI_OPAQUE : s.material_alpha8[per_tri ? mat_off + tm[t] : mat_off];
-                if (a8 != RPTR_TRI_OPAQUE) s.any_alpha_tested = true;
-                tr.gi_alpha = pack_gi_alpha(gi, a8);
+                const int tri_material = per_tri ? mat_off + tm[t] : mat_off;
+                const int32_t a8 = no_alpha ? RPTR_TRI_OPAQUE : s.material_alpha8[tri_material];
+                const bool alpha_tex = !no_alpha && s.material_alpha_textured[tri_material] != 0;
+                if (a8 != RPTR_TRI_OPAQUE || alpha_tex) s.any_alpha_tested = true;
+                if (alpha_tex && !(gd.has_uvs && !s.qnuv[gidx].empty())) throw std::runtime_error("a material with an alpha texture is used on a geometry without uvs");
+                tr.gi_alpha = pack_gi_alpha(gi, a8, alpha_tex);
                 tr.prim = t;
                 s.tris.push_back(tr);
                 if (!nonemissive[inst.pmesh_id]) { // collect_emitters, lights.cpp:33-73

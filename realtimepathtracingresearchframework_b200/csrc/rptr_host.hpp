@@ -17,6 +17,11 @@ struct HostGeomInst {
     float o2w[12];
 };
 
+struct HostTexture { // one entry per texture of the scene; rgba is empty for 1 x 1 textures (folded into the materials)
+    int32_t width = 0, height = 0, srgb = 0;
+    std::vector<uint8_t> rgba; // four channels per texel: missing colour channels 0, missing alpha 255
+};
+
 struct HostScene {
     // owned copies of the input streams (the caller's Scene is only borrowed for set_scene, app.cpp:151-175)
     std::vector<std::vector<uint64_t>> qverts, qnuv;
@@ -24,6 +29,10 @@ struct HostScene {
     std::vector<HostGeomInst> ginst;
     std::vector<rptr_base_material> materials;   // texture handles already resolved to constants (1x1-texel mode)
     std::vector<int32_t> material_alpha8;       // per material: alpha texel (255 = opaque)
+    std::vector<char> material_alpha_textured;  // per material: alpha comes from a texture larger than 1 x 1 (looked up per candidate)
+    std::vector<HostTexture> textures;          // device image of Scene::textures
+    bool any_textured = false;                  // some parameter kept its handle (texture larger than 1 x 1)
+    float srgb_lut[256];                        // sRGB8 code value -> linear
     std::vector<float> normal_texels;           // per material: rgb (+ pad) of its 1 x 1 normal map, zeros without one
     bool any_normal_map = false;
     bool any_alpha_tested = false;              // some triangle has alpha8 != 255: traversal must run the candidate filter

@@ -31,27 +31,79 @@ struct Tri { // 48 B traversal record (three 128-bit loads), world space
 #endif
     float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
     int32_t id;        // flattened (instance, geometry, primitive) index: the closest-hit tie-break key
-    int32_t gi_alpha;  // index into GeomInst[] (low 24 bits) | 8-bit material alpha << 24; see tri_geom_inst / tri_alpha8
+    int32_t gi_alpha;  // index into GeomInst[] (low 23 bits) | RPTR_TRI_TEXTURED_ALPHA | 8-bit material alpha << 24; see tri_geom_inst / tri_alpha8
     int32_t prim;
 #ifdef RPTR_TRI64
     int32_t pad[4];
 #endif
 };
 
-// Alpha of the triangle's material as the 8-bit texel it comes from (1x1-texel mode, rptr_host.cpp resolve_materials):
-// 255 = opaque (NOALPHA flags, constant colour or alpha texel 255) -> traversal never draws for it.
+// Alpha of the triangle's material as the 8-bit texel it comes from when that is one number per material (constants, 1 x 1
+// textures: rptr_host.cpp resolve_materials): 255 = opaque (NOALPHA flags, constant colour or alpha texel 255) -> traversal
+// never draws for it.  Bit 23 (RPTR_TRI_TEXTURED_ALPHA) says the alpha comes from a texture larger than 1 x 1 and has to be
+// looked up at the candidate's uv (candidate_alpha below).
 #define RPTR_TRI_OPAQUE 255
-RPTR_HD int32_t tri_geom_inst(const Tri &t) { return t.gi_alpha & 0x00ffffff; }
+#define RPTR_TRI_TEXTURED_ALPHA 0x00800000
+RPTR_HD int32_t tri_geom_inst(const Tri &t) { return t.gi_alpha & 0x007fffff; }
 RPTR_HD int32_t tri_alpha8(const Tri &t) { return (int32_t)(((uint32_t)t.gi_alpha) >> 24); }
-RPTR_HD int32_t pack_gi_alpha(int32_t geom_inst, int32_t alpha8) { return (int32_t)(((uint32_t)alpha8 << 24) | (uint32_t)geom_inst); }
+RPTR_HD int32_t pack_gi_alpha(int32_t geom_inst, int32_t alpha8, bool textured = false) {
+    return (int32_t)(((uint32_t)alpha8 << 24) | (textured ? (uint32_t)RPTR_TRI_TEXTURED_ALPHA : 0u) | (uint32_t)geom_inst);
+}
 RPTR_HD float alpha8_to_float(int32_t a8) { return (float)a8 / 255.0f; } // UNORM8 texel
+
+// A texture on the device: base level only, always four 8-bit channels (missing colour channels 0, missing alpha 255).
+struct TexDev {
+    const uchar4 *texels;
+    int32_t width, height;
+    int32_t srgb; // colour channels go through the sRGB transfer function (SceneDev::srgb_lut), alpha never does
+    int32_t _pad;
+};
 
 struct SceneDev {
     const GeomInst *ginst;
     const rptr_base_material *materials;
     const rptr_tri_light_data *lights;
-    const float4 *normal_texels; // per material: the texel of its (1 x 1) normal map, rgb as sampled; read only when normal_map != -1
+    const float4 *normal_texels; // per material: rgb = the texel of its 1 x 1 normal map as sampled; w != 0: sample textures[normal_map] at the hit's uv instead
+    const TexDev *textures;      // Scene::textures (rptr_scene_desc::textures); parameters of the materials refer to them by handle
+    const float *srgb_lut;       // 256 entries: sRGB8 code value -> linear (evaluated in double on the host, rounded once)
 };
+
+// ---- the texture unit (RPTR-FP statement; the reference leaves it to the hardware: VkSampler of vulkan/render_vulkan.cpp:1655-1671) ----
+// REPEAT addressing, LINEAR filter, base level: texel centres at (i + 0.5) / size, UNORM8 -> v / 255, sRGB colour channels
+// decoded per texel BEFORE filtering (as a VK_FORMAT_*_SRGB image does), weights and blends in binary32 in the order written.
+// Level of detail: the base level.  The reference selects a mip level / anisotropic footprint from ray differentials
+// (textureGrad with hit.duvdxy, rendering/rt/material_textures.glsl:37-63); that stage is hardware-defined (12x anisotropy)
+// and is not restated -- images are taken as single-level, for which every LOD resolves to what is computed here.
+RPTR_HD float4 decode_texel(const SceneDev &sc, const TexDev &t, uchar4 c) {
+    if (t.srgb) return f4(sc.srgb_lut[c.x], sc.srgb_lut[c.y], sc.srgb_lut[c.z], (float)c.w / 255.0f);
+    return f4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+}
+RPTR_HD int32_t wrap_repeat(int32_t i, int32_t n) {
+    i %= n;
+    return i < 0 ? i + n : i;
+}
+RPTR_HD float lerp_tex(float a, float b, float t) { return a + (b - a) * t; }
+RPTR_HD float4 sample_texture(const SceneDev &sc, uint32_t id, float2 uv) {
+    const TexDev &t = sc.textures[id];
+    float x = uv.x * (float)t.width - 0.5f, y = uv.y * (float)t.height - 0.5f;
+    if (!(fabsf(x) < 1.0e9f) || !(fabsf(y) < 1.0e9f)) { x = 0.0f; y = 0.0f; } // NaN / out of the integer range: texel (0, 0)
+    const float x0 = floorf(x), y0 = floorf(y);
+    const float fx = x - x0, fy = y - y0;
+    const int32_t i0 = wrap_repeat((int32_t)x0, t.width), i1 = wrap_repeat(i0 + 1, t.width);
+    const int32_t j0 = wrap_repeat((int32_t)y0, t.height), j1 = wrap_repeat(j0 + 1, t.height);
+    const float4 c00 = decode_texel(sc, t, t.texels[(size_t)j0 * t.width + i0]), c10 = decode_texel(sc, t, t.texels[(size_t)j0 * t.width + i1]);
+    const float4 c01 = decode_texel(sc, t, t.texels[(size_t)j1 * t.width + i0]), c11 = decode_texel(sc, t, t.texels[(size_t)j1 * t.width + i1]);
+    return f4(lerp_tex(lerp_tex(c00.x, c10.x, fx), lerp_tex(c01.x, c11.x, fx), fy), lerp_tex(lerp_tex(c00.y, c10.y, fx), lerp_tex(c01.y, c11.y, fx), fy),
+              lerp_tex(lerp_tex(c00.z, c10.z, fx), lerp_tex(c01.z, c11.z, fx), fy), lerp_tex(lerp_tex(c00.w, c10.w, fx), lerp_tex(c01.w, c11.w, fx), fy));
+}
+RPTR_HD bool is_texture_handle(float v) { return (f2u(v) & RPTR_TEXTURED_PARAM_MASK) != 0; }
+// textured_scalar_param (rendering/rt/material_textures.glsl:50-63): handles that survived resolve_materials refer to textures larger than 1 x 1
+RPTR_HD float textured_scalar(const SceneDev &sc, float v, float2 uv) {
+    if (!is_texture_handle(v)) return v;
+    const float4 t = sample_texture(sc, RPTR_GET_TEXTURE_ID(f2u(v)), uv);
+    const uint32_t ch = RPTR_GET_TEXTURE_CHANNEL(f2u(v));
+    return ch == 0 ? t.x : ch == 1 ? t.y : ch == 2 ? t.z : t.w;
+}
 
 struct FrameParams {
     int32_t width, height;
@@ -156,22 +208,30 @@ struct GltfMat {
     uint32_t flags;
 };
 
-// constants-only unpack_material + load_material (rendering/rt/material_textures.glsl:95-135, gltf_bsdf.glsl:38-62)
-RPTR_HD float unpack_material(GltfMat &m, float3 &emit, const rptr_base_material &p, bool transmission) {
+// unpack_material + load_material (rendering/rt/material_textures.glsl:95-135, gltf_bsdf.glsl:38-62; non-unrolled standard-texture
+// semantics of rendering/rt/materials.glsl:42-49).  Parameters that refer to 1 x 1 textures were folded into constants on the
+// host; TEX = false compiles the lookups of larger textures out (scenes without any).
+template <bool TEX>
+RPTR_HD float unpack_material(GltfMat &m, float3 &emit, const rptr_base_material &p, bool transmission, const SceneDev &sc, float2 uv) {
     float alpha = 1.0f;
     m.base_color = f3(p.base_color[0], p.base_color[1], p.base_color[2]);
-    if (alpha > 0.001f) m.base_color = m.base_color / alpha;
-    m.specular = p.specular;
-    m.roughness = p.roughness;
-    m.metallic = p.metallic;
-    m.ior = p.ior;
+    if (TEX && is_texture_handle(p.base_color[0])) { // textured_color_param(vec4(base_color, 1), hit)
+        const float4 t = sample_texture(sc, RPTR_GET_TEXTURE_ID(f2u(p.base_color[0])), uv);
+        m.base_color = f3(t.x, t.y, t.z);
+        alpha = t.w;
+    }
+    if (alpha > 0.001f) m.base_color = m.base_color / alpha; // PREMULTIPLIED_BASE_COLOR_ALPHA
+    m.specular = TEX ? textured_scalar(sc, p.specular, uv) : p.specular;
+    m.roughness = TEX ? textured_scalar(sc, p.roughness, uv) : p.roughness;
+    m.metallic = TEX ? textured_scalar(sc, p.metallic, uv) : p.metallic;
+    m.ior = TEX ? textured_scalar(sc, p.ior, uv) : p.ior;
     emit = f3(p.base_color[0], p.base_color[1], p.base_color[2]) * p.emission_intensity;
-    if (p.emission_intensity != 0.0f) m.base_color = f3(0.0f);
+    if (p.emission_intensity != 0.0f) m.base_color = f3(0.0f); // (emitters with a textured colour are refused by set_scene)
     m.specular_transmission = 0.0f;
     m.transmission_color = f3(0.0f);
     m.transmission_roughness = 0.0f;
     if (transmission) {
-        m.specular_transmission = p.specular_transmission;
+        m.specular_transmission = TEX ? textured_scalar(sc, p.specular_transmission, uv) : p.specular_transmission;
         if (m.specular_transmission > 0.0f) {
             if (!(m.ior > 1.0f)) {
                 alpha *= 1.0f - m.specular_transmission;
@@ -179,12 +239,16 @@ RPTR_HD float unpack_material(GltfMat &m, float3 &emit, const rptr_base_material
             } else {
                 m.transmission_color = m.base_color;
                 m.transmission_roughness = m.roughness;
-                m.roughness = sqrtf(p.clearcoat_gloss);
+                m.roughness = sqrtf(TEX ? textured_scalar(sc, p.clearcoat_gloss, uv) : p.clearcoat_gloss);
             }
         }
     }
     m.flags = p.flags;
     return alpha;
+}
+// the constants-only form (no texture larger than 1 x 1 in reach)
+RPTR_HD float unpack_material(GltfMat &m, float3 &emit, const rptr_base_material &p, bool transmission) {
+    return unpack_material<false>(m, emit, p, transmission, SceneDev{}, f2(0.0f, 0.0f));
 }
 
 // ---- glTF BSDF (rendering/bsdfs/gltf_bsdf.glsl:172-645) -----------------------------------------------------------------
@@ -648,6 +712,23 @@ RPTR_HD float2 dequantize_uv(uint32_t w) {
 }
 
 // ---- hit attributes (rendering/rt/hit.glsl:49-128,162-203) -----------------------------------------------------------------
+RPTR_HD int calc_hit_material_id(const GeomInst &g, uint32_t prim);
+// the uv part of calc_hit_attributes (hit.glsl:75-84), also evaluated for alpha candidates during traversal (generate_candidate_hit)
+RPTR_HD float2 hit_uv(const GeomInst &g, uint32_t prim, float ax, float ay) {
+    if (!g.has_uvs) return f2(0.0f, 0.0f);
+    const uint64_t *qn = g.qnuv + 3 * (size_t)prim;
+    const float2 uva = dequantize_uv((uint32_t)(qn[0] >> 32)), uvb = dequantize_uv((uint32_t)(qn[1] >> 32)), uvc = dequantize_uv((uint32_t)(qn[2] >> 32));
+    const float bx = 1.0f - ax - ay;
+    return f2(fmaf(uvc.x, ay, fmaf(uvb.x, ax, uva.x * bx)), fmaf(uvc.y, ay, fmaf(uvb.y, ax, uva.y * bx)));
+}
+// get_material_alpha (material_textures.glsl:137-145) of a traversal candidate: the per-material texel packed into the triangle
+// record, or -- RPTR_TRI_TEXTURED_ALPHA -- the alpha channel of the material's base-colour texture at the candidate's uv
+RPTR_HD float candidate_alpha(const SceneDev &sc, int32_t gi_alpha, int32_t prim, float u, float v) {
+    if (!(gi_alpha & RPTR_TRI_TEXTURED_ALPHA)) return alpha8_to_float((int32_t)(((uint32_t)gi_alpha) >> 24));
+    const GeomInst &g = sc.ginst[gi_alpha & 0x007fffff];
+    const rptr_base_material &m = sc.materials[calc_hit_material_id(g, (uint32_t)prim)];
+    return sample_texture(sc, RPTR_GET_TEXTURE_ID(f2u(m.base_color[0])), hit_uv(g, (uint32_t)prim, u, v)).w;
+}
 struct RTHit {
     float3 normal; float dist; float3 geo_normal; int material_id; float3 tangent; float bitangent_l; float2 uv;
 };
@@ -778,7 +859,8 @@ RPTR_HD AovSample aov_of_miss(const FrameParams &fp) { // store_geometry_aovs(0,
 #define RPTR_FEAT_AOV 4          // fp.output_channel may be non-zero
 #define RPTR_FEAT_QMC 8          // fp.rng_variant may select a Sobol / blue-noise sampler
 #define RPTR_FEAT_NORMAL_MAPS 16 // some material has a normal map
-#define RPTR_FEAT_ALL 31
+#define RPTR_FEAT_TEXTURES 32    // some material parameter refers to a texture larger than 1 x 1
+#define RPTR_FEAT_ALL 63
 // RANDOM_FLOAT1(rng, d) of the selected pointset (rendering/pointsets/selected_rng.glsl, rendering/defaults.glsl:23-28)
 template <int FEAT>
 RPTR_HD float path_rand(const FrameParams &fp, PathState &ps, int d) {
@@ -866,7 +948,8 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
         float3 t_x = cross(t_y, h.normal);
         t_x = t_x * length(h.tangent);
         t_y = t_y * h.bitangent_l;
-        const float4 tx = sc.normal_texels[h.material_id];
+        float4 tx = sc.normal_texels[h.material_id];
+        if ((FEAT & RPTR_FEAT_TEXTURES) && tx.w != 0.0f) tx = sample_texture(sc, (uint32_t)mp.normal_map, h.uv); // textureLod(.., hit.uv, bounce): base level
         float3 map_nrm = f3(2.0f * tx.x - 1.0f, 2.0f * tx.y - 1.0f, 1.0f * tx.z - 0.0f);
         map_nrm.z = sqrtf(fmaxf(1.0f - map_nrm.x * map_nrm.x - map_nrm.y * map_nrm.y, 0.0f));
         in_ = normalize(mat_mul(t_x, t_y, in_ * sp.normal_z_scale, map_nrm));
@@ -883,7 +966,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
 
     GltfMat mat;
     float3 emit;
-    unpack_material(mat, emit, mp, tr);
+    unpack_material<(FEAT & RPTR_FEAT_TEXTURES) != 0>(mat, emit, mp, tr, sc, h.uv);
     if (aov && ps.bounce == 0) {
         aov->normal = in_;
         aov->depth = length(ip - ld3(fp.cam_pos));

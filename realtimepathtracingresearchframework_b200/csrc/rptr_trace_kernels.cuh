@@ -44,7 +44,7 @@ struct TraceIO {
     // stochastic alpha (kernels instantiated with Alpha = true only; scenes without alpha-tested triangles never pay for it)
     uint32_t *alpha_lcg;   // closest: LCG state the candidate filter draws from, word alpha_lcg[slot * alpha_stride]: the path's own
     uint32_t alpha_stride; //          LCG with the UNIFORM pointset (stride 2: Wave::rngb), a separate one otherwise (stride 1: Wave::rng3)
-    AlphaFilter alpha;     // shadow: per-candidate LCG seeds (pixel_linear is filled in per ray)
+    AlphaFilter alpha;     // scene tables for the alpha of textured candidates; shadow: per-candidate LCG seeds (pixel_linear is filled in per ray)
     TileMap tm;            // shadow: path slot -> pixel that seeds the per-candidate LCG (frame pixel or ray-query invocation)
 };
 
@@ -292,12 +292,12 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         // ---- retire + refill --------------------------------------------------------------------------------------
         bool done = have && (gy & 0xffu) == 0u && (ty & 0xffu) == 0u && sp == 0 && tsp == 0;
         if (Alpha && !Any && done && best_tri >= 0 && after_id != RPTR_EMPTY) {
-            const int32_t a8 = tri_alpha8(bvh.tris[best_tri]);
-            if (a8 != RPTR_TRI_OPAQUE) {
+            const int32_t ga = bvh.tris[best_tri].gi_alpha;
+            if ((((uint32_t)ga) >> 24) != RPTR_TRI_OPAQUE || (ga & RPTR_TRI_TEXTURED_ALPHA)) {
                 uint32_t *ap = io.alpha_lcg + (size_t)slot * io.alpha_stride;
                 uint32_t st = *ap;
                 const uint32_t before = st;
-                const bool rejected = alpha_rejects(alpha8_to_float(a8), st);
+                const bool rejected = alpha_rejects(candidate_alpha(io.alpha.scene, ga, bvh.tris[best_tri].prim, best_u, best_v), st);
                 if (st != before) *ap = st;
                 if (rejected) { // look for the closest hit after this candidate
                     tmin = best_t; after_id = best_id;
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                         if (Alpha) {
                             AlphaFilter af = io.alpha;
                             af.pixel_linear = pixel_linear;
-                            passes = shadow_candidate_passes(af, f2i(tc.z), f2i(tc.w));
+                            passes = shadow_candidate_passes(af, f2i(tc.z), f2i(tc.w), u, v);
                         }
                         if (passes) { // occluded: drop the rest of the traversal
                             best_tri = tri_index;

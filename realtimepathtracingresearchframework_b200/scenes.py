@@ -81,13 +81,14 @@ class Scene:
         self.instances = []    # (pmesh_id, 3x4 row-major transform)
         self.materials = []    # T.BaseMaterial
         self.binned_lights = None
-        self.textures = []     # (texels uint8[h, w, channels], T.COLOR_SPACE_*); only 1 x 1 is accepted by the backend yet
+        self.textures = []     # (texels uint8[h, w, channels], T.COLOR_SPACE_*): single-level images of any size
         self._keep = []
 
-    def add_texture(self, texel, color_space=T.COLOR_SPACE_LINEAR):
-        """1 x 1 texture from one texel (1-4 channels, 8 bit); returns the texture id for T.texture_handle()."""
-        px = np.asarray(texel, np.uint8).reshape(1, 1, -1)
-        self.textures.append((px, color_space))
+    def add_texture(self, texels, color_space=T.COLOR_SPACE_LINEAR):
+        """A texture from one texel (1-4 channels, 8 bit) or an (h, w, channels) image; returns the texture id for T.texture_handle()."""
+        px = np.asarray(texels, np.uint8)
+        px = px.reshape(1, 1, -1) if px.ndim == 1 else (px[..., None] if px.ndim == 2 else px)
+        self.textures.append((np.ascontiguousarray(px), color_space))
         return len(self.textures) - 1
 
     def add_mesh(self, geometries):
@@ -442,4 +443,46 @@ def smooth_shaded_scene(n_u=24, n_v=12, n_soup=1500, seed=11):
     s.add_instance(pm, t2)
     s.camera = look_at_camera((0.3, 1.5, 7.5), (0.0, 0.0, 0.0), fovy=50.0)
     s.name = "smooth_shaded"
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Textures larger than 1 x 1 (rendering/rt/material_textures.glsl:26-145): uv lookups at the hit and at alpha candidates
+# ---------------------------------------------------------------------------------------------------------------------
+def procedural_image(w, h, channels, seed):
+    """A deterministic 8-bit test image: smooth gradients + a checker + hashed noise, so that bilinear weights, wrap-around and
+    every channel matter."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.int64)
+    img = np.zeros((h, w, channels), np.uint8)
+    for c in range(channels):
+        v = (x * (37 + 11 * c) + y * (59 + 7 * c) + seed * 101) % 256
+        checker = (((x * 4 // max(w, 1)) + (y * 4 // max(h, 1)) + c) % 2) * 96
+        img[..., c] = ((v // 2) + checker + ((x * y + seed) % 23)) % 256
+    return img
+
+
+def textured_scene(seed=5):
+    """The smooth-shaded, uv-mapped scene with textures of several sizes on every textured parameter: an sRGB RGBA base colour whose
+    alpha channel cuts holes (stochastic alpha at candidates with interpolated uv: closest-hit and shadow rays), a linear
+    RGB(A) image read channel by channel for specular / roughness / metallic, a tangent-space normal map, a non-square image, a
+    1 x 1 texture beside them (folded on the host), and a NOALPHA material that reads colour but is never alpha-tested."""
+    s = smooth_shaded_scene()
+    t_color = s.add_texture(procedural_image(64, 32, 4, seed), T.COLOR_SPACE_SRGB)
+    alpha = t_color_img = s.textures[t_color][0]
+    yy, xx = np.mgrid[0:32, 0:64]
+    alpha[..., 3] = np.where(((xx // 8 + yy // 8) % 3) == 0, 0, np.where(((xx // 8 + yy // 8) % 3) == 1, 140, 255)).astype(np.uint8)
+    t_orm = s.add_texture(procedural_image(16, 16, 3, seed + 1), T.COLOR_SPACE_LINEAR)
+    nrm = procedural_image(32, 32, 3, seed + 2).astype(np.int32)
+    nrm = np.stack([128 + (nrm[..., 0] - 128) // 3, 128 + (nrm[..., 1] - 128) // 3, np.full(nrm.shape[:2], 255)], -1).astype(np.uint8)
+    t_nrm = s.add_texture(nrm, T.COLOR_SPACE_LINEAR)
+    t_gray = s.add_texture(procedural_image(5, 3, 1, seed + 3), T.COLOR_SPACE_SRGB)  # one channel: (r, 0, 0, 1)
+    t_one = s.add_texture((90, 200, 60, 255), T.COLOR_SPACE_SRGB)
+    m = s.materials
+    m[0].base_color, m[0].flags = (T.texture_handle(t_color), 0.0, 0.0), 0           # alpha-tested, textured colour, one-texel normal map stays
+    m[1].roughness, m[1].metallic, m[1].specular = T.texture_handle(t_orm, 1), T.texture_handle(t_orm, 2), T.texture_handle(t_orm, 0)
+    m[2].base_color, m[2].normal_map = (T.texture_handle(t_color), 0.0, 0.0), t_nrm  # NOALPHA stays set: colour from the image, no alpha test
+    m[3].base_color, m[3].ior = (T.texture_handle(t_gray), 0.0, 0.0), 1.5
+    m[3].roughness = T.texture_handle(t_orm, 0)
+    s.materials.append(T.BaseMaterial(base_color=(T.texture_handle(t_one), 0.0, 0.0), roughness=0.5, flags=0))
+    s.name = "textured"
     return s

@@ -26,7 +26,14 @@ struct hostsim_args { // same layout as oracle_render_args
     float vp_reference[16];
 };
 
-struct hostsim_scene { HostScene hs; std::vector<GeomInst> gi; };
+struct hostsim_scene {
+    HostScene hs;
+    std::vector<GeomInst> gi;
+    std::vector<TexDev> tex;
+    SceneDev dev() const { // the device-side scene tables, here with host pointers
+        return SceneDev{gi.data(), hs.materials.data(), hs.lights.data(), reinterpret_cast<const float4 *>(hs.normal_texels.data()), tex.data(), hs.srgb_lut};
+    }
+};
 
 hostsim_scene *hostsim_scene_create(const rptr_scene_desc *d, const rptr_light_sampling_config *ls) {
     hostsim_scene *s = new hostsim_scene();
@@ -44,6 +51,8 @@ hostsim_scene *hostsim_scene_create(const rptr_scene_desc *d, const rptr_light_s
         g.tri_mat = s->hs.tri_mat[h.pmesh].empty() ? nullptr : s->hs.tri_mat[h.pmesh].data() + h.prim_offset;
         s->gi.push_back(g);
     }
+    for (const HostTexture &t : s->hs.textures)
+        s->tex.push_back(TexDev{t.rgba.empty() ? nullptr : reinterpret_cast<const uchar4 *>(t.rgba.data()), t.width, t.height, t.srgb, 0});
     return s;
 }
 void hostsim_scene_destroy(hostsim_scene *s) { delete s; }
@@ -98,7 +107,7 @@ static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
 // albedo.rgb, roughness, normal.xyz, depth of the first path vertex (the values behind the fp16 AOV images)
 static int render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t sample_index, float *rgba, float *aov_out, int aov_stride = 8) {
     FrameParams fp = make_frame(s, a);
-    SceneDev sc{s->gi.data(), s->hs.materials.data(), s->hs.lights.data(), reinterpret_cast<const float4 *>(s->hs.normal_texels.data())};
+    const SceneDev sc = s->dev();
     BvhDev bvh{s->hs.nodes.data(), s->hs.leaf_tris.data(), (int32_t)s->hs.nodes.size(), (int32_t)s->hs.leaf_tris.size()};
 #pragma omp parallel for schedule(dynamic, 1)
     for (int y = a->y0; y < a->y1; ++y)
@@ -112,12 +121,12 @@ static int render_sample(const hostsim_scene *s, const hostsim_args *a, uint32_t
             for (;;) {
                 HitRec h;
                 // stochastic alpha draws come from the path's LCG (the LCG pointset; the QMC pointsets keep a separate one)
-                bool found = closest_hit_filtered(bvh, ps.o, ps.d, ps.tmin, ps.tmax, fp.rng_variant == 0 ? ps.rng : alpha_lcg, h, cnt);
+                bool found = closest_hit_filtered(bvh, sc, ps.o, ps.d, ps.tmin, ps.tmax, fp.rng_variant == 0 ? ps.rng : alpha_lcg, h, cnt);
                 ShadowRay sh;
                 ShadeResult r = shade_vertex(fp, sc, ps, h.t, h.u, h.v, found ? &bvh.tris[h.tri] : nullptr, sh, aov_out ? &as : nullptr);
                 if (sh.tmax > 0.0f) {
                     HitRec o;
-                    const AlphaFilter af{sc.ginst, fp.first_sample, fp.frame_offset, (uint32_t)x + (uint32_t)y * (uint32_t)fp.width};
+                    const AlphaFilter af{sc, fp.first_sample, fp.frame_offset, (uint32_t)x + (uint32_t)y * (uint32_t)fp.width};
                     if (!trace_ray<true>(bvh, sh.o, sh.d, sh.tmin, sh.tmax, o, cnt, sh.tmin, 0x7fffffff, &af)) ps.illum = ps.illum + sh.contrib;
                 }
                 if (r == SHADE_TERMINATE) break;
@@ -179,6 +188,11 @@ void hostsim_unpack_material(const hostsim_scene *s, int32_t mid, int32_t transm
     out[12] = e.x; out[13] = e.y; out[14] = e.z;
 }
 void hostsim_halton_23(int32_t k, float *out) { halton_23(k, out); }
+// the product's texture unit (csrc/rptr_shading.cuh sample_texture) on texture `id` of the scene: out = rgba
+void hostsim_sample_texture(const hostsim_scene *s, uint32_t id, float u, float v, float *out) {
+    const float4 c = sample_texture(s->dev(), id, f2(u, v));
+    out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
+}
 // the product's stochastic alpha test (csrc/rptr_bvh.cuh): closest-hit form (draws from the given LCG) and shadow-ray form
 // (own LCG per candidate); 1 = rejected / 1 = the candidate blocks the ray
 int32_t hostsim_alpha_rejects(float alpha, uint32_t *state) { return alpha_rejects(alpha, *state) ? 1 : 0; }
@@ -186,8 +200,10 @@ int32_t hostsim_shadow_candidate_passes(int32_t alpha8, int32_t prim, int32_t in
     GeomInst g;
     memset(&g, 0, sizeof(g));
     g.instance = instance;
-    const AlphaFilter af{&g, frame_id, frame_offset, pixel_linear};
-    return shadow_candidate_passes(af, pack_gi_alpha(0, alpha8), prim) ? 1 : 0;
+    SceneDev sc{};
+    sc.ginst = &g;
+    const AlphaFilter af{sc, frame_id, frame_offset, pixel_linear};
+    return shadow_candidate_passes(af, pack_gi_alpha(0, alpha8), prim, 0.0f, 0.0f) ? 1 : 0;
 }
 // generate_primary for one pixel sample: out = origin(3), dir(3), bits(first sampler word afterwards), tmin, tmax
 void hostsim_primary_ray(const hostsim_scene *s, const hostsim_args *a, int32_t px, int32_t py, uint32_t sample_index, float *out) {
@@ -214,7 +230,7 @@ uint32_t hostsim_morton_sample_id(uint32_t sample_id, uint32_t px, uint32_t py, 
 // of every query; the query's "pixel" comes from the product's TileMap in query mode (tile_pixel).  out = 4 floats per query.
 extern "C" int hostsim_ray_query_layer(const hostsim_scene *s, const hostsim_args *a, const rptr_render_ray_query *queries, int32_t n, uint32_t layer, float *out) {
     FrameParams fp = make_frame(s, a);
-    SceneDev sc{s->gi.data(), s->hs.materials.data(), s->hs.lights.data(), reinterpret_cast<const float4 *>(s->hs.normal_texels.data())};
+    const SceneDev sc = s->dev();
     BvhDev bvh{s->hs.nodes.data(), s->hs.leaf_tris.data(), (int32_t)s->hs.nodes.size(), (int32_t)s->hs.leaf_tris.size()};
     TileMap tm{};
     tm.width = a->width; tm.height = a->height; tm.world = 1; tm.rows = 1; tm.local_pixels = n;
@@ -232,12 +248,12 @@ extern "C" int hostsim_ray_query_layer(const hostsim_scene *s, const hostsim_arg
         TraceCounters cnt{0, 0};
         for (;;) {
             HitRec h;
-            bool found = closest_hit_filtered(bvh, ps.o, ps.d, ps.tmin, ps.tmax, fp.rng_variant == 0 ? ps.rng : alpha_lcg, h, cnt);
+            bool found = closest_hit_filtered(bvh, sc, ps.o, ps.d, ps.tmin, ps.tmax, fp.rng_variant == 0 ? ps.rng : alpha_lcg, h, cnt);
             ShadowRay sh;
             ShadeResult r = shade_vertex(fp, sc, ps, h.t, h.u, h.v, found ? &bvh.tris[h.tri] : nullptr, sh, nullptr);
             if (sh.tmax > 0.0f) {
                 HitRec o;
-                const AlphaFilter af{sc.ginst, fp.first_sample, fp.frame_offset, tile_pixel_linear(tm, (uint32_t)q)};
+                const AlphaFilter af{sc, fp.first_sample, fp.frame_offset, tile_pixel_linear(tm, (uint32_t)q)};
                 if (!trace_ray<true>(bvh, sh.o, sh.d, sh.tmin, sh.tmax, o, cnt, sh.tmin, 0x7fffffff, &af)) ps.illum = ps.illum + sh.contrib;
             }
             if (r == SHADE_TERMINATE) break;

@@ -970,3 +970,48 @@ def test_concurrent_sub_waves_option_is_bit_identical(oracle):
         assert np.array_equal(b.aov(1).view(np.uint16), want_nd.view(np.uint16)), k
     ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=7, batch_spp=7)
     assert_identical(want, ref, "7 layers in one frame")
+
+
+def test_textured_scene_uv_lookups(oracle):
+    """Textures larger than 1 x 1: bilinear REPEAT lookups of base colour + alpha, specular / roughness / metallic
+    channels, ior and the normal map at the hit's uv (k_shade<RPTR_FEAT_ALL>), and of the alpha channel at traversal candidates
+    with interpolated uv (k_trace_persistent<*, true>: closest hit at retire time, shadow rays per candidate) -- against the
+    oracle; persistent and one-ray-per-thread kernels, both BVH builders, a Sobol run (alpha draws from the separate LCG)."""
+    from realtimepathtracingresearchframework_b200 import load_pointset_tables
+    s = scenes.textured_scene()
+    W, H = 320, 180
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    sp = load_sky_fit(T.SceneConfig(**sky))
+    o = oracle.OracleScene(s)
+    ref, _ = o.render(W, H, s.camera, sp, spp=4, transmission=1)
+    r = make_backend(s, W, H, sky, transmission=1)
+    r.render_spp(s.camera, 4, batch_spp=1)
+    assert_identical(r.framebuffer(), ref, "textured, 4 frames")
+    b = make_backend(s, W, H, sky, transmission=1, wave_paths=3 * W * H, bvh_builder=1)
+    b.render_spp(s.camera, 4, batch_spp=4)
+    refb, _ = o.render(W, H, s.camera, sp, spp=4, batch_spp=4, transmission=1)
+    assert_identical(b.framebuffer(), refb, "textured, batch of 4, device LBVH")
+    c = make_backend(s, W, H, sky, transmission=1, trace_kernel=1)
+    c.render_spp(s.camera, 4, batch_spp=1)
+    assert_identical(c.framebuffer(), ref, "textured, one-ray-per-thread kernels")
+    tables = load_pointset_tables()
+    q = make_backend(s, W, H, sky)
+    q.set_rng_variant(T.RNG_VARIANT_SOBOL, tables)
+    q.render_spp(s.camera, 2, batch_spp=2)
+    refq, _ = o.render(W, H, s.camera, sp, spp=2, batch_spp=2, rng_variant=T.RNG_VARIANT_SOBOL, pointset_tables=tables)
+    assert_identical(q.framebuffer(), refq, "textured, Sobol")
+    # scene swap on one context: textured -> untextured -> textured (device texture tables follow)
+    plain = scenes.random_triangles(5000)
+    r.set_scene(plain)
+    r.render_spp(plain.camera, 1)
+    assert_identical(r.framebuffer(), oracle.OracleScene(plain).render(W, H, plain.camera, sp, spp=1, transmission=1)[0], "plain after textured")
+    r.set_scene(s)
+    r.render_spp(s.camera, 2)
+    assert_identical(r.framebuffer(), o.render(W, H, s.camera, sp, spp=2, transmission=1)[0], "textured again")
+    with pytest.raises(RptrError):
+        bad = scenes.textured_scene()
+        bad.materials[1].emission_intensity = 2.0
+        bad.materials[1].base_color = bad.materials[0].base_color
+        r.set_scene(bad)
+    r.render_spp(s.camera, 1)  # the failed set_scene left the previous scene in place
+    assert_identical(r.framebuffer(), o.render(W, H, s.camera, sp, spp=1, transmission=1, frame_offset=2)[0], "still the textured scene")

@@ -125,3 +125,79 @@ def test_normal_map_changes_shading_only_where_it_is_set(H, oracle):
     nb, _ = render_both(H, oracle, flat, W, Hh, 0, params=p)
     changed = (na[..., :3] != nb[..., :3]).any(-1)
     assert 0.02 < changed.mean() < 0.5
+
+
+# ---- textures larger than 1 x 1 ------------------------------------------------------------------------------
+def test_texture_unit_product_equals_oracle(H, hostsim, oracle):
+    """The bilinear REPEAT sampler (our statement of the VkSampler the reference leaves to the hardware): product
+    (csrc/rptr_shading.cuh sample_texture, RGBA8 device image) and oracle (TextureSet::sample on the caller's texels) bit for
+    bit over wrap-around, negative and huge coordinates, texel centres, 1-4 channels, sRGB and linear."""
+    lib = C.CDLL(hostsim)
+    lib.hostsim_sample_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, oracle.f32p]
+    L = oracle.lib()
+    L.oracle_sample_texture.argtypes = [C.POINTER(T.TextureDesc), C.c_float, C.c_float, oracle.f32p]
+    s = scenes.textured_scene()
+    d = s.desc()
+    ls = T.LightSamplingConfig()
+    hs = H.hostsim_scene_create(C.byref(d), C.byref(ls))
+    assert hs
+    rng = np.random.default_rng(4)
+    uvs = np.concatenate([rng.uniform(-3, 9, (300, 2)), rng.uniform(0, 1, (200, 2)), [[0, 0], [1, 1], [0.5, 0.5], [-0.0, 1e-9], [1e12, -1e12], [np.nan, 0.3],
+                                                                                       [0.5 / 64, 0.5 / 32], [1 - 1e-7, 1 - 1e-7]]]).astype(np.float32)
+    sizes = set()
+    for tid, (px, _) in enumerate(s.textures):
+        if px.shape[0] * px.shape[1] == 1:
+            continue  # folded into the materials by the product
+        sizes.add(px.shape)
+        for u, v in uvs:
+            a, b = np.zeros(4, np.float32), np.zeros(4, np.float32)
+            lib.hostsim_sample_texture(hs, tid, float(u), float(v), a.ctypes.data_as(oracle.f32p))
+            L.oracle_sample_texture(C.byref(d.textures[tid]), float(u), float(v), b.ctypes.data_as(oracle.f32p))
+            assert a.tobytes() == b.tobytes(), (tid, u, v, a, b)
+            assert np.isfinite(a).all() and (a >= 0).all() and (a <= 1).all()
+    H.hostsim_scene_destroy(hs)
+    assert len(sizes) >= 4
+    # texel centres return the texel itself, sRGB through the transfer function; the sample between two texels is their mean
+    img = np.array([[[0, 0, 0, 255], [255, 255, 255, 0]]], np.uint8)
+    td = T.TextureDesc(width=2, height=1, channels=4, color_space=T.COLOR_SPACE_SRGB)
+    td.texels = img.ctypes.data_as(C.POINTER(C.c_uint8))
+    out = np.zeros(4, np.float32)
+    L.oracle_sample_texture(C.byref(td), 0.25, 0.5, out.ctypes.data_as(oracle.f32p))
+    assert out.tolist() == [0.0, 0.0, 0.0, 1.0]
+    L.oracle_sample_texture(C.byref(td), 0.5, 0.5, out.ctypes.data_as(oracle.f32p))
+    assert out.tolist() == [0.5, 0.5, 0.5, 0.5]
+    L.oracle_sample_texture(C.byref(td), 1.0, 0.5, out.ctypes.data_as(oracle.f32p))  # REPEAT: half way between texel 1 and texel 0
+    assert out.tolist() == [0.5, 0.5, 0.5, 0.5]
+
+
+@pytest.mark.parametrize("sample,transmission", [(0, 0), (2, 1)])
+def test_textured_scene_matches_oracle_bit_for_bit(H, oracle, sample, transmission):
+    """uv lookups of base colour + alpha, specular / roughness / metallic channels, ior and the normal map at the hit, and of the
+    alpha channel at traversal candidates (closest hit: the path's LCG, front to back; shadow rays: per-candidate seeds)."""
+    s = scenes.textured_scene()
+    ref, img = render_both(H, oracle, s, 192, 108, sample, sky=dict(sun_dir=(0.35, 0.8, 0.45)), frame_offset=2, transmission=transmission)
+    assert np.isfinite(ref).all() and ref[..., :3].max() > 0
+    assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), "%d pixels differ" % (ref != img).any(-1).sum()
+    if sample == 0:
+        # the textures matter: constant materials give another image, and so do opaque ones (the alpha channel cuts holes)
+        flat = scenes.smooth_shaded_scene()
+        ref_flat, _ = render_both(H, oracle, flat, 192, 108, sample, sky=dict(sun_dir=(0.35, 0.8, 0.45)), frame_offset=2)
+        assert (ref_flat != ref).any(-1).mean() > 0.05
+        opaque = scenes.textured_scene()
+        for m in opaque.materials:
+            m.flags |= T.BASE_MATERIAL_NOALPHA
+        ref_opaque, _ = render_both(H, oracle, opaque, 192, 108, sample, sky=dict(sun_dir=(0.35, 0.8, 0.45)), frame_offset=2)
+        assert (ref_opaque != ref).any(-1).mean() > 0.01
+
+
+def test_textured_emitters_and_missing_uvs_are_refused(H):
+    s = scenes.textured_scene()
+    s.materials[1].emission_intensity = 3.0
+    s.materials[1].base_color = s.materials[0].base_color
+    d = s.desc()
+    ls = T.LightSamplingConfig()
+    assert not H.hostsim_scene_create(C.byref(d), C.byref(ls))  # the reference's own emitter collection reads the handle bits as a colour
+    s = scenes.textured_scene()
+    s.geometries[0].has_uvs = False  # alpha texture on a geometry without uvs
+    d = s.desc()
+    assert not H.hostsim_scene_create(C.byref(d), C.byref(ls))

@@ -84,5 +84,38 @@ def tour():
     return n
 
 
+def tiny_tour():
+    """racecheck-sized: 32 x 18 frames, a few hundred triangles -- the persistent closest-hit / any-hit kernels on their two streams
+    (the in-place illum update of the shadow kernel beside the next closest-hit launch), the alpha variants, sub-waves side by
+    side, ray queries through the integrator and the RaytraceBackend service.  Run against a build with small trace CTAs:
+        RPTR_CUDA_LIB=variants/librptr_cuda_t128.so compute-sanitizer --tool racecheck python tools/sanitize.py --tiny"""
+    global W, H
+    W, H = 32, 18
+    n = 0
+    for s, opts in ((scenes.random_triangles(400, box=3.0, edge=0.8), dict()), (scenes.alpha_tested_soup(600), dict()),
+                    (scenes.random_triangles(400, box=3.0, edge=0.8), dict(concurrent_waves=2))):
+        s.camera = scenes.look_at_camera((0, 0, 10), (0, 0, 0), fovy=50.0)
+        r = backend(s, **opts)
+        r.render_spp(s.camera, 4, batch_spp=4)
+        assert np.isfinite(r.framebuffer()).all()
+        r.enable_ray_queries(256, 0)
+        rng = np.random.default_rng(2)
+        q = np.zeros((200, 8), np.float32)
+        q[:, 0:3] = rng.uniform(-3, 3, (200, 3))
+        d = rng.normal(size=(200, 3))
+        q[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+        q[:, 7] = 1e20
+        r.write_ray_queries(q)
+        r.render_ray_queries(200)
+        r.read_ray_results(200)
+        r.trace_ray(q)
+        r.close()
+        n += 1
+    return n
+
+
 if __name__ == "__main__":
-    print("sanitize tour: %d contexts ok" % tour())
+    if "--tiny" in sys.argv:
+        print("sanitize tiny tour: %d contexts ok" % tiny_tour())
+    else:
+        print("sanitize tour: %d contexts ok" % tour())
