@@ -1,6 +1,7 @@
 // render_cuda.cpp -- see render_cuda.h.  Reference-side glue only; every arithmetic step of the hot path is behind the C ABI.
 #include "render_cuda.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "error_io.h"      // util/error_io.h: throw_error
@@ -22,6 +23,9 @@ static_assert(sizeof(rptr_render_params) == sizeof(RenderParams), "RenderParams 
 static_assert(sizeof(rptr_light_sampling_config) == sizeof(LightSamplingConfig), "LightSamplingConfig layout");
 static_assert(sizeof(rptr_render_ray_query) == sizeof(RenderRayQuery), "RenderRayQuery layout");
 static_assert(sizeof(rptr_camera_params) == sizeof(RenderCameraParams), "RenderCameraParams layout");
+static_assert(sizeof(rptr_backend_options) == sizeof(RenderBackendOptions), "RenderBackendOptions layout");
+static_assert(offsetof(rptr_backend_options, render_upscale_factor) == offsetof(RenderBackendOptions, render_upscale_factor), "RenderBackendOptions layout");
+static_assert(offsetof(rptr_backend_options, enable_raytraced_dof) == offsetof(RenderBackendOptions, enable_raytraced_dof), "RenderBackendOptions layout");
 static_assert(offsetof(rptr_base_material, emission_intensity) == offsetof(BaseMaterial, emission_intensity), "BaseMaterial layout");
 static_assert(offsetof(rptr_render_params, output_channel) == offsetof(RenderParams, output_channel), "RenderParams layout");
 
@@ -101,15 +105,22 @@ void RenderCuda::set_scene(const Scene &scene) {
             for (int c = 0; c < 4; ++c) id.transform[4 * r + c] = m[c][r]; // 3x4 row-major, as handed to the TLAS (:1262-1268)
         instances.push_back(id);
     }
-    // Scene::textures (util/image.h:10-27).  The backend resolves 1 x 1 textures today and rejects larger ones with a
-    // readable error; block-compressed images would have to be decompressed first (Image::decompress).
+    // Scene::textures (util/image.h:10-27): the base level of every image, 8 bits per channel.  Block-compressed images
+    // (BC1 / BC3 / BC5 of a .vks scene) go through the reference's own decoder (Image::decompress) first; mip levels stored
+    // behind the base level are not passed (the backend samples the base level, include/rptr_types.h).
     std::vector<rptr_texture_desc> textures;
+    std::vector<Image> decompressed;
+    decompressed.reserve(scene.textures.size());
     for (const Image &img : scene.textures) {
-        if (img.bcFormat != 0) throw_error("cuda backend: block-compressed texture '%s' is not supported yet", img.name.c_str());
+        const Image *src = &img;
+        if (img.bcFormat != 0) {
+            decompressed.push_back(img.decompress());
+            src = &decompressed.back();
+        }
         rptr_texture_desc td{};
-        td.width = img.width; td.height = img.height; td.channels = img.channels;
-        td.color_space = img.color_space == SRGB ? RPTR_COLOR_SPACE_SRGB : RPTR_COLOR_SPACE_LINEAR;
-        td.texels = img.img.data();
+        td.width = src->width; td.height = src->height; td.channels = src->channels;
+        td.color_space = src->color_space == SRGB ? RPTR_COLOR_SPACE_SRGB : RPTR_COLOR_SPACE_LINEAR;
+        td.texels = src->img.data();
         textures.push_back(td);
     }
     rptr_scene_desc d{};
@@ -160,6 +171,49 @@ void RenderCuda::update_config(SceneConfig const &config) {
     }
     sp.normal_z_scale = 1.0f / config.bump_scale;
     check(rptr_cuda_set_scene_params(ctx, &sp));
+}
+
+// normalize_options / configure_for (librender/render_backend.h:84-85; vulkan/render_vulkan.cpp:1878-1917): options the backend
+// cannot honour make configure_for return false with the recovery mask filled in, which sends the app through its fallback
+// (app.cpp:400-431) instead of rendering something else than was asked for.
+void RenderCuda::normalize_options(RenderBackendOptions &rbo, int variant_idx) const {
+    if (rptr_cuda_normalize_options(ctx, reinterpret_cast<rptr_backend_options *>(&rbo), variant_idx) != 0)
+        throw_error("cuda backend: %s", rptr_cuda_last_error(ctx));
+}
+bool RenderCuda::configure_for(RenderBackendOptions const &rbo, int variant_idx, AvailableRenderBackendOptions *available_recovery_options) {
+    if (rbo.rng_variant != RNG_VARIANT_UNIFORM) { // the tables have to be on the device before the variant can be selected
+        RenderBackendOptions saved = options;
+        options.rng_variant = rbo.rng_variant;
+        applied_rng_variant = -1;
+        apply_rng_variant();
+        options = saved;
+    }
+    rptr_backend_options closest;
+    const bool ok = rptr_cuda_configure_for(ctx, reinterpret_cast<const rptr_backend_options *>(&rbo), variant_idx, &closest) == 0;
+    if (available_recovery_options) { // an option is "available" when its requested value is one the backend renders with
+        const RenderBackendOptions &c = reinterpret_cast<const RenderBackendOptions &>(closest);
+#define RPTR_AVAILABLE(type, name, default_, flags) available_recovery_options->name = c.name == rbo.name;
+        RENDER_BACKEND_OPTIONS(RPTR_AVAILABLE)
+#undef RPTR_AVAILABLE
+    }
+    if (!ok) println(CLL::WARNING, "cuda backend: %s", rptr_cuda_last_error(ctx));
+    else applied_rng_variant = rbo.rng_variant;
+    return ok;
+}
+
+void RenderCuda::enable_ray_queries(const int max_queries, const int max_queries_per_pixel) {
+    check(rptr_cuda_enable_ray_queries(ctx, max_queries, max_queries_per_pixel));
+}
+bool RenderCuda::render_ray_queries(int num_queries, const RenderParams &params_, int variant_idx, CommandStream *) {
+    check(rptr_cuda_render_ray_queries(ctx, num_queries, (const rptr_render_params *)&params_, variant_idx));
+    return true;
+}
+void RenderCuda::write_ray_queries(const RenderRayQuery *queries, int first, int count) {
+    check(rptr_cuda_write_ray_queries(ctx, (const rptr_render_ray_query *)queries, first, count));
+}
+void RenderCuda::read_ray_results(glm::vec4 *results, int first, int count) { check(rptr_cuda_read_ray_results(ctx, (float *)results, first, count)); }
+void RenderCuda::ray_query_buffers(void **device_queries, void **device_results, size_t *capacity) {
+    check(rptr_cuda_ray_query_buffers(ctx, device_queries, device_results, capacity));
 }
 
 // options.rng_variant (librender/render_params.glsl.h:76) + the tables the reference's pointset extensions upload
@@ -227,4 +281,8 @@ int RenderCuda::trace_ray(const RenderRayQuery *queries, int num_queries, glm::v
     return num_queries;
 }
 
-RenderBackend *create_cuda_backend(Display &) { return new RenderCuda(0); }
+// the device is chosen like CUDA applications usually are: RPTR_CUDA_DEVICE (ordinal among the visible devices), default 0
+RenderBackend *create_cuda_backend(Display &) {
+    const char *dev = std::getenv("RPTR_CUDA_DEVICE");
+    return new RenderCuda(dev ? std::atoi(dev) : 0);
+}

@@ -27,12 +27,23 @@ struct RenderCuda : RenderBackend {
 
     void set_scene(const Scene &scene) override;
     void update_config(SceneConfig const &config) override;
+    void normalize_options(RenderBackendOptions &rbo, int variant_idx) const override;
+    bool configure_for(RenderBackendOptions const &rbo, int variant_idx, AvailableRenderBackendOptions *available_recovery_options = nullptr) override;
 
     void begin_frame(CommandStream *cmd_stream, const RenderConfiguration &config) override;
     void draw_frame(CommandStream *cmd_stream, int variant_idx = 0) override;
     void end_frame(CommandStream *cmd_stream, int variant_idx = 0) override;
     RenderStats stats() override;
     void flush_pipeline() override;
+
+    // path tracing on caller-supplied rays (librender/render_backend.h:101-102; app.cpp:77-79 enables it under ENABLE_CUDA).
+    // The reference keeps queries / results in device buffers its data-capture module fills; here they are reachable as
+    // device addresses (ray_query_buffers) or through the two host-side copies.
+    void enable_ray_queries(const int max_queries = DEFAULT_RAY_QUERY_BUDGET, const int max_queries_per_pixel = 0) override;
+    bool render_ray_queries(int num_queries, const RenderParams &params, int variant_idx = 0, CommandStream *cmd_stream = nullptr) override;
+    void write_ray_queries(const RenderRayQuery *queries, int first, int count);
+    void read_ray_results(glm::vec4 *results, int first, int count);
+    void ray_query_buffers(void **device_queries, void **device_results, size_t *capacity);
 
     glm::uvec3 get_framebuffer_size() const override;
     size_t readback_framebuffer(size_t bufferSize, unsigned char *buffer, bool force_refresh = false) override;
