@@ -247,7 +247,6 @@ def run_b200(args):
     r.set_option("stage_timing", 1)
     if args.scene == "c4":
         r.set_option("transmission", 1)
-        r.set_option("bvh_builder", 1)
     if args.wave_paths:
         r.set_option("wave_paths", args.wave_paths)
     for kv in args.option:

@@ -40,7 +40,7 @@ typedef struct rptr_counters {
     uint64_t node_bytes;       /* size of one BVH node record fetched per node visit */
     uint64_t tri_bytes;        /* size of one traversal triangle record fetched per triangle test */
     uint64_t bvh_nodes;        /* number of (4-wide) BVH nodes of the current scene */
-    double bvh_build_ms;       /* wall time of the last BVH build (host SAH or device LBVH) */
+    double bvh_build_ms;       /* wall time of the last BVH build (host SAH or device builder) */
     uint64_t trace_overlap;    /* 1: option "overlap_shadow" is on -- ms_trace / trace_launches then cover closest-hit AND shadow
                                   launches (each shadow launch shares the GPU with the next closest-hit launch) and ms_shadow is 0 */
     uint64_t num_sms;          /* streaming multiprocessors of the device (persistent grids are sized in multiples of it) */
@@ -80,8 +80,9 @@ int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *params);
  *   "overlap_shadow" 0/1 (default 1) launch the shadow rays of bounce d on a second stream beside the closest-hit rays of bounce
  *                   d + 1 (independent work; the persistent grids interleave SM by SM, hiding each other's tails)
  *   "stage_timing"  0/1  time each stage with CUDA events into rptr_counters.ms_*
- *   "bvh_builder"   0 = binned-SAH build on the host inside set_scene, 1 = LBVH build on the device (both replace the
- *                   driver's BLAS/TLAS build, vulkan/vulkanrt_utils.cpp:82-167; images are identical either way)
+ *   "bvh_builder"   1 (default) = binned-SAH build on the device, 0 = the same algorithm on the host inside set_scene, kept as
+ *                   the A/B (both replace the driver's BLAS/TLAS build, vulkan/vulkanrt_utils.cpp:82-167; images are identical
+ *                   either way; a device build that fails -- memory, depth -- falls back to the host builder)
  *   "trace_kernel"  0 = persistent speculative traversal kernel, 1 = one-ray-per-thread kernel (A/B reference)
  *   "tile_rank", "tile_world", "tile_rows": screen-space sharding across GPUs (interleaved bands of tile_rows rows)
  */

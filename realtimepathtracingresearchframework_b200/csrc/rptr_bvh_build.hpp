@@ -1,4 +1,4 @@
-// rptr_bvh_build.hpp -- device-side LBVH builder (rptr_bvh_build.cu)
+// rptr_bvh_build.hpp -- device-side binned-SAH builder (rptr_bvh_build.cu)
 #pragma once
 #include <cuda_runtime.h>
 
@@ -11,7 +11,7 @@ namespace rp {
 
 struct DeviceBvh { // device allocations owned by the caller after a successful build (cudaFree)
     BvhNode *nodes = nullptr;
-    Tri *tris = nullptr;     // leaf (= Morton) order
+    Tri *tris = nullptr;     // leaf order
     float4 *top = nullptr;   // word planes of the first top_k nodes (4 * RPTR_TOP_NODES_MAX words, BvhDev::top_planes)
     int32_t n_nodes = 0, n_tris = 0, top_k = 0, depth = 0;
 };

@@ -541,7 +541,7 @@ struct rptr_ctx {
     int64_t wave_paths = 128ll << 20;
     int stage_timing = 0;
     int trace_kernel = 0; // 0 = persistent while-while (rptr_trace_kernels.cuh), 1 = one ray per thread (A/B reference)
-    int bvh_builder = 0;  // 0 = binned SAH on the host (rptr_host.cpp), 1 = LBVH on the device (rptr_bvh_build.cu)
+    int bvh_builder = 1;  // 1 = binned SAH on the device (rptr_bvh_build.cu), 0 = the same algorithm on the host (rptr_host.cpp)
     double bvh_build_ms = 0.0;
     int tile_rank = 0, tile_world = 1, tile_rows = 8;
     // wave
@@ -933,7 +933,7 @@ static int upload_scene(rptr_ctx *ctx, HostScene &hs, SceneUpload &up) {
         }
     }
     up.extent = extent;
-    if (ctx->bvh_builder == 1) { // device LBVH (rptr_bvh_build.cu)
+    if (ctx->bvh_builder == 1) { // device builder (rptr_bvh_build.cu)
         DeviceBvh db;
         std::string err;
         const auto t0 = std::chrono::steady_clock::now();
@@ -946,11 +946,11 @@ static int upload_scene(rptr_ctx *ctx, HostScene &hs, SceneUpload &up) {
         }
         // e.g. the collapsed Morton tree is deeper than the traversal stack allows (clustered or coincident centroids): the host
         // SAH builder bounds the depth (it falls back to balanced median splits), so it takes over instead of failing set_scene
-        ctx->error = "device LBVH: " + err + "; fell back to the host SAH builder";
+        ctx->error = "device builder: " + err + "; fell back to the host SAH builder";
         try {
             build_bvh(hs);
         } catch (const std::exception &e) {
-            return fail(ctx, "set_scene: device LBVH failed (%s) and so did the host builder (%s)", err.c_str(), e.what());
+            return fail(ctx, "set_scene: device builder failed (%s) and so did the host builder (%s)", err.c_str(), e.what());
         }
     }
     BvhNode *d_nodes;
@@ -1044,7 +1044,7 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
     }
     else if (n == "trace_kernel") ctx->trace_kernel = (int)value;
     else if (n == "bvh_builder") {
-        if (value != 0 && value != 1) return fail(ctx, "bvh_builder must be 0 (host SAH) or 1 (device LBVH)");
+        if (value != 0 && value != 1) return fail(ctx, "bvh_builder must be 0 (host builder) or 1 (device builder)");
         ctx->bvh_builder = (int)value; // takes effect at the next set_scene
     }
     else if (n == "tile_rank") ctx->tile_rank = (int)value;

@@ -321,19 +321,19 @@ def test_c2_full_size_region_against_oracle_and_determinism(oracle, c2_scene):
     assert np.array_equal((parts[0] + parts[1]).view(np.uint32), img.view(np.uint32))
 
 
-def test_device_lbvh_builder_gives_identical_images(oracle):
-    """Option bvh_builder=1 builds the BVH on the GPU (Morton LBVH, rptr_bvh_build.cu).  The closest-hit contract does
-    not depend on the tree, so images and ray queries must not change by a single bit."""
+def test_device_builder_gives_identical_images(oracle):
+    """Option bvh_builder=1 (the default) builds the BVH on the GPU (binned SAH, rptr_bvh_build.cu), 0 on the host.  The
+    closest-hit contract does not depend on the tree, so images and ray queries must not change by a single bit."""
     for make, (W, H), spp in ((scenes.cornell_box, (160, 90), 2), (lambda: scenes.random_triangles(50000), (192, 108), 2)):
         s = make()
-        a = make_backend(s, W, H)
+        a = make_backend(s, W, H, bvh_builder=0)
         a.render_spp(s.camera, spp)
         b = make_backend(s, W, H, bvh_builder=1)
         b.render_spp(s.camera, spp)
         assert b.counters()["bvh_nodes"] > 0
         assert np.array_equal(a.framebuffer().view(np.uint32), b.framebuffer().view(np.uint32))
         ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=spp)
-        assert_identical(b.framebuffer(), ref, "device LBVH")
+        assert_identical(b.framebuffer(), ref, "device builder")
     big = scenes.random_triangles(300000)
     r = make_backend(big, 64, 64, bvh_builder=1)
     q = random_queries(100000, 9)
@@ -350,11 +350,15 @@ def test_device_lbvh_builder_gives_identical_images(oracle):
     many.materials = one.materials
     many.add_instance(many.add_pmesh(many.add_mesh([scenes.Geometry(scenes.pack_qverts(np.repeat(g, 300, 0).reshape(-1, 3)), (2.0 ** -12,) * 3, (-1.0,) * 3)]), [0]))
     many.camera = one.camera
-    for s in (one, many):
+    # ... and the sizes around the builder's phases: a root finished by the sweep (2, 5, 8), the smallest binned root (9)
+    few = [scenes.random_triangles(k, n_geometries=1, seed=77 + k, box=1.5, edge=0.8) for k in (2, 5, 8, 9, 70)]
+    for f in few:
+        f.camera = scenes.look_at_camera((0, 0, 5), (0, 0, 0), fovy=50.0)
+    for s in [one, many] + few:
         b = make_backend(s, 64, 48, bvh_builder=1)
         b.render_spp(s.camera, 1)
         ref, _ = oracle.OracleScene(s).render(64, 48, s.camera, load_sky_fit(), spp=1)
-        assert_identical(b.framebuffer(), ref, "degenerate LBVH")
+        assert_identical(b.framebuffer(), ref, "degenerate device build")
         assert (ref[..., 3] > 0).any()
 
 
@@ -380,7 +384,7 @@ def test_two_devices_when_available():
 
 def test_c4_instanced_transmission_emissive(oracle):
     """BASELINE configs[3] (instances + full BSDF set + area-light NEE): reduced size against the oracle with both BVH
-    builders, then the full 10 M instanced triangles (device LBVH) through size-independent properties."""
+    builders, then the full 10 M instanced triangles (device builder) through size-independent properties."""
     s = scenes.instanced_scene(1500, 25)
     W, H = 240, 135
     sky = dict(sun_dir=(0.35, 0.8, 0.45))
@@ -700,7 +704,7 @@ def test_smooth_shaded_scene_vertex_normals_and_uvs(oracle):
     """SURVEY 8a-6 on the CUDA path (rendering/rt/hit.glsl:58-128): geometries with quantised vertex normals and uvs --
     smooth shading with the geometric-normal flip, uv interpolation, the uv-derivative tangent under one-texel normal maps
     and its fallback for zero uv derivatives, has_normals / has_uvs in all four combinations, instances with non-uniform
-    scale and a mirrored instance.  Progressive frames, a batch in several waves, the device LBVH, and the A/B kernels."""
+    scale and a mirrored instance.  Progressive frames, a batch in several waves, the device builder, and the A/B kernels."""
     s = scenes.smooth_shaded_scene()
     W, H = 320, 180
     sky = dict(sun_dir=(0.35, 0.8, 0.45))
@@ -713,7 +717,7 @@ def test_smooth_shaded_scene_vertex_normals_and_uvs(oracle):
     assert_identical(r.framebuffer(), ref, "smooth shaded, 4 frames")
     b = make_backend(s, W, H, sky, wave_paths=3 * W * H, bvh_builder=1)
     b.render_spp(s.camera, 4, batch_spp=4)
-    assert_identical(b.framebuffer(), ref, "smooth shaded, batch of 4 in waves of 3 + 1, device LBVH")
+    assert_identical(b.framebuffer(), ref, "smooth shaded, batch of 4 in waves of 3 + 1, device builder")
     c = make_backend(s, W, H, sky, trace_kernel=1)
     c.render_spp(s.camera, 4, batch_spp=2)
     assert_identical(c.framebuffer(), ref, "smooth shaded, one-ray-per-thread kernels")
@@ -773,7 +777,7 @@ def test_c3_full_size_window_4096spp(oracle, c2_scene):
 
 def test_c4_full_size_window_against_oracle(oracle):
     """BASELINE configs[3] at its full size (10 M instanced triangles, 1920x1080, 16 spp, transmission, tri-light NEE, alpha-tested
-    materials; device LBVH): a window of the frame against the oracle."""
+    materials; device builder): a window of the frame against the oracle."""
     s = scenes.instanced_scene(100_000, 100)
     W, H = 1920, 1080
     sky = dict(sun_dir=(0.35, 0.8, 0.45))
@@ -990,7 +994,7 @@ def test_textured_scene_uv_lookups(oracle):
     b = make_backend(s, W, H, sky, transmission=1, wave_paths=3 * W * H, bvh_builder=1)
     b.render_spp(s.camera, 4, batch_spp=4)
     refb, _ = o.render(W, H, s.camera, sp, spp=4, batch_spp=4, transmission=1)
-    assert_identical(b.framebuffer(), refb, "textured, batch of 4, device LBVH")
+    assert_identical(b.framebuffer(), refb, "textured, batch of 4, device builder")
     c = make_backend(s, W, H, sky, transmission=1, trace_kernel=1)
     c.render_spp(s.camera, 4, batch_spp=1)
     assert_identical(c.framebuffer(), ref, "textured, one-ray-per-thread kernels")

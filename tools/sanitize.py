@@ -6,7 +6,7 @@ tool's 10-100x slow-down:
 Covers: persistent trace kernels (closest / any-hit, with and without the alpha filter), the one-ray-per-thread kernels,
 k_shade in its three feature variants (LCG, triangle lights, ALL = QMC + AOV + transmission + normal maps), raygen,
 resolve (progressive + discard-history), the tile sort of multi-material scenes, LDR / AOV read-backs, ray queries, the
-device LBVH builder and screen-space sharding (tile_rank / tile_world)."""
+device builder builder and screen-space sharding (tile_rank / tile_world)."""
 import os
 import sys
 
@@ -31,8 +31,8 @@ def backend(scene, **options):
 def tour():
     tables = load_pointset_tables()
     n = 0
-    # LCG path, host SAH and device LBVH, persistent and one-ray-per-thread kernels, several waves per frame
-    for opts in (dict(), dict(bvh_builder=1), dict(trace_kernel=1), dict(wave_paths=W * H), dict(overlap_shadow=0, stage_timing=1)):
+    # LCG path, host SAH and device builder, persistent and one-ray-per-thread kernels, several waves per frame
+    for opts in (dict(), dict(bvh_builder=0), dict(trace_kernel=1), dict(wave_paths=W * H), dict(overlap_shadow=0, stage_timing=1)):
         r = backend(scenes.random_triangles(3000), **opts)
         r.render_spp(scenes.random_triangles(3000).camera, 3, batch_spp=3)
         assert np.isfinite(r.framebuffer()).all()
