@@ -85,6 +85,13 @@ int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *params);
  *                   either way; a device build that fails -- memory, depth -- falls back to the host builder)
  *   "trace_kernel"  0 = persistent speculative traversal kernel, 1 = one-ray-per-thread kernel (A/B reference)
  *   "tile_rank", "tile_world", "tile_rows": screen-space sharding across GPUs (interleaved bands of tile_rows rows)
+ *   "render_upscale_factor" RenderBackendOptions::render_upscale_factor (also through rptr_cuda_configure_for): the LDR target is
+ *                   that many times the render size (vulkan/render_vulkan.cpp:255-263); takes effect at the next initialize
+ *   "realtime_resolve" 0/1 (default 0) the reference's ENABLE_REALTIME_RESOLVE build (CMakeLists.txt:98, OFF by default): with it
+ *                   reprojection_mode = ACCUMULATE runs reproject_and_accumulate (rendering/postprocess/reprojection.glsl) in place of
+ *                   the running mean -- the accumulator's alpha then holds 1 - sample weight -- and rptr_cuda_process_taa exists.
+ *                   Needs the AOV images and the whole frame on one GPU.  Without it ACCUMULATE is the running mean, as in the
+ *                   reference's default build (vulkan/render_vulkan.cpp:1911-1915).
  */
 int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value);
 
@@ -112,7 +119,10 @@ int rptr_cuda_frame_state(rptr_ctx *ctx, uint32_t *frame_id, uint32_t *frame_off
 
 /* RenderGraphic::get_framebuffer_size / readback_framebuffer(float*) / (unsigned char*)
  * (util/display/render_graphic.h:27-37; vulkan/render_vulkan.cpp:2250-2287): RGBA, row-major, top row first.
- * Return the number of elements written (width*height*4) or 0 when the buffer is too small. */
+ * Return the number of elements written or 0 when the buffer is too small.  As in the reference the float image has the
+ * render size (width*height*4 elements) while framebuffer_size and the 8-bit image are those of the LDR render target,
+ * render_upscale_factor times larger in x and y: factor 2 replicates every pixel 2 x 2, any other factor > 1 stores the pixels
+ * at their own coordinates and leaves the rest of the target untouched (vulkan/process_samples.comp:192-199, as written). */
 int rptr_cuda_framebuffer_size(rptr_ctx *ctx, uint32_t *width, uint32_t *height, uint32_t *channels);
 size_t rptr_cuda_readback_f32(rptr_ctx *ctx, size_t n_elems, float *dst);
 size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst);
@@ -167,8 +177,16 @@ int rptr_cuda_render_ray_queries(rptr_ctx *ctx, int32_t num_queries, const rptr_
  * switched; its tables must have been handed over); non-zero = unsupported, with the reason in last_error, and
  * *available (optional) receives the closest supported set -- the reference's "fallback exists" recovery path (app.cpp:400-431).
  * Unsupported here: light_sampling_variant NONE (the reference's megakernel does not build with it either: wpdf_direct_light
- * is undefined without lights_linear.glsl, rendering/mc/shade_base_material.glsl:36), render_upscale_factor != 1, enable_taa. */
+ * is undefined without lights_linear.glsl, rendering/mc/shade_base_material.glsl:36), enable_taa without option "realtime_resolve".
+ * render_upscale_factor is taken over for the next initialize. */
 int rptr_cuda_normalize_options(rptr_ctx *ctx, rptr_backend_options *options, int32_t variant);
+/* ProcessTAAVulkan::process (vulkan/processing/process_taa.cpp:93-136, process_taa.comp): the LDR post-process the application
+ * runs after end_frame when options.enable_taa && params.reprojection_mode != NONE (app.cpp:517-520): blends the frame's LDR
+ * target with the previous frame's (Lanczos-5 resampled along the motion image, weight 0.15) and clamps to the 3 x 3
+ * neighbourhood's spread; skipped while frame_id <= 1.  The next readback_u8 returns the processed target.  Needs option
+ * "realtime_resolve".  The shader updates the target in place while neighbouring invocations still read it; here every read
+ * sees the target as process_samples left it. */
+int rptr_cuda_process_taa(rptr_ctx *ctx);
 int rptr_cuda_configure_for(rptr_ctx *ctx, const rptr_backend_options *options, int32_t variant, rptr_backend_options *available);
 
 /* Multi-GPU (the reference has no multi-GPU path to mirror): one context per GPU, scene replicated, the frame

@@ -106,8 +106,33 @@ def lib():
         L.oracle_dequantize_position.argtypes = [C.c_uint64, f32p, f32p, f32p]
         L.oracle_dequantize_normal.argtypes = [C.c_uint32, f32p]
         L.oracle_dequantize_uv.argtypes = [C.c_uint32, f32p]
+        L.oracle_reproject_accumulate.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
+        L.oracle_process_taa.argtypes = [C.c_int32] * 5 + [C.c_void_p] * 4
         _lib = L
     return _lib
+
+
+def reproject_accumulate(accum_cur, history, nd_history, nd, mj, min_sample_weight, batch, fn=None):
+    """process_samples.comp:106-113 over a frame (reprojection.glsl).  accum_cur / history: (h, w, 4) float32; nd_history / nd / mj:
+    (h, w, 4) float16 or uint16 bit patterns.  Returns (stored accumulator, colour shown).  fn: the same entry point of another
+    library (tests/hostsim) instead of the oracle's."""
+    h, w = accum_cur.shape[:2]
+    arrs = [np.ascontiguousarray(accum_cur, np.float32), np.ascontiguousarray(history, np.float32)] + \
+           [np.ascontiguousarray(a).view(np.uint16) for a in (nd_history, nd, mj)]
+    stored, shown = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+    (fn or lib().oracle_reproject_accumulate)(w, h, *[a.ctypes.data for a in arrs], float(min_sample_weight), int(batch), stored.ctypes.data,
+                                              shown.ctypes.data)
+    return stored, shown
+
+
+def process_taa(current, history, mj, upscale=1, fn=None):
+    """process_taa.comp over the LDR target: current / history (h, w, 4) uint8, mj the (h / upscale, w / upscale, 4) motion image."""
+    h, w = current.shape[:2]
+    rh, rw = mj.shape[:2]
+    cur, his, m = np.ascontiguousarray(current, np.uint8), np.ascontiguousarray(history, np.uint8), np.ascontiguousarray(mj).view(np.uint16)
+    out = np.zeros((h, w, 4), np.uint8)
+    (fn or lib().oracle_process_taa)(w, h, int(upscale), rw, rh, cur.ctypes.data, his.ctypes.data, m.ctypes.data, out.ctypes.data)
+    return out
 
 
 def ref():

@@ -1831,3 +1831,33 @@ int32_t oracle_num_threads(void) {
 }
 
 } // extern "C"
+
+// ---- the temporal passes of the ENABLE_REALTIME_RESOLVE build (post_oracle.h), whole images -------------------------------------
+#include "post_oracle.h"
+extern "C" {
+// process_samples.comp:106-113 for every pixel: accum_cur = this frame's samples (RGBA32F); stored = accumulator after the pass,
+// shown = the colour handed on to the display chain
+void oracle_reproject_accumulate(int32_t w, int32_t h, const float *accum_cur, const float *history, const uint16_t *nd_history, const uint16_t *nd,
+                                 const uint16_t *mj, float min_sample_weight, int32_t batch, float *stored, float *shown) {
+    const post::ReprojectIn in{post::Image4f{history, w, h}, post::Image4h{nd_history, w, h}, post::Image4h{nd, w, h}, post::Image4h{mj, w, h}};
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int32_t y = 0; y < h; ++y)
+        for (int32_t x = 0; x < w; ++x) {
+            const size_t i = 4 * ((size_t)y * w + x);
+            V4 st;
+            const V4 sh = post::reproject_and_accumulate(in, V4{accum_cur[i], accum_cur[i + 1], accum_cur[i + 2], accum_cur[i + 3]}, post::IV2{x, y},
+                                                         post::IV2{w, h}, min_sample_weight, batch, &st);
+            stored[i] = st.x; stored[i + 1] = st.y; stored[i + 2] = st.z; stored[i + 3] = st.w;
+            shown[i] = sh.x; shown[i + 1] = sh.y; shown[i + 2] = sh.z; shown[i + 3] = sh.w;
+        }
+}
+// process_taa.comp main() for every pixel of the (w x h) LDR target; the motion image has the render size (rw x rh)
+void oracle_process_taa(int32_t w, int32_t h, int32_t upscale, int32_t rw, int32_t rh, const uint8_t *current, const uint8_t *history,
+                        const uint16_t *mj, uint8_t *out) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int32_t y = 0; y < h; ++y)
+        for (int32_t x = 0; x < w; ++x)
+            post::process_taa_main(post::Image4b{current, w, h}, post::Image4b{history, w, h}, post::Image4h{mj, rw, rh}, post::IV2{x, y}, post::IV2{w, h},
+                                   upscale, out + 4 * ((size_t)y * w + x));
+}
+} // extern "C"

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "rptr_cuda_readback_f32", "rptr_cuda_readback_u8", "rptr_cuda_framebuffer_device_ptr", "rptr_cuda_stream_handle",
     "rptr_cuda_trace_rays", "rptr_cuda_set_pointset_table", "rptr_cuda_readback_aov",
     "rptr_cuda_enable_ray_queries", "rptr_cuda_ray_query_buffers", "rptr_cuda_write_ray_queries", "rptr_cuda_read_ray_results",
-    "rptr_cuda_render_ray_queries", "rptr_cuda_normalize_options", "rptr_cuda_configure_for",
+    "rptr_cuda_render_ray_queries", "rptr_cuda_normalize_options", "rptr_cuda_configure_for", "rptr_cuda_process_taa",
     "rptr_cuda_comm_unique_id", "rptr_cuda_comm_init_rank", "rptr_cuda_comm_init_all", "rptr_cuda_comm_destroy",
     "rptr_cuda_reduce_framebuffer", "rptr_cuda_reduce_framebuffer_all",
     "rptr_write_pfm",
@@ -102,6 +102,7 @@ def load_library(path=None):
     L.rptr_cuda_render_ray_queries.argtypes = [vp, i32, C.POINTER(T.RenderParams), i32]
     L.rptr_cuda_normalize_options.argtypes = [vp, C.POINTER(T.RenderBackendOptions), i32]
     L.rptr_cuda_configure_for.argtypes = [vp, C.POINTER(T.RenderBackendOptions), i32, C.POINTER(T.RenderBackendOptions)]
+    L.rptr_cuda_process_taa.argtypes = [vp]
     L.rptr_cuda_comm_unique_id.argtypes = [vp, C.c_size_t]
     L.rptr_cuda_comm_init_rank.argtypes = [vp, i32, i32, vp, C.c_size_t]
     L.rptr_cuda_comm_init_all.argtypes = [C.POINTER(vp), i32]
@@ -209,6 +210,7 @@ class RenderCuda:
 
     def initialize(self, fb_width, fb_height):
         self._check(self._L.rptr_cuda_initialize(self._h, fb_width, fb_height))
+        self.render_width, self.render_height = int(fb_width), int(fb_height)
 
     def set_scene(self, scene):
         d = scene.desc()
@@ -278,19 +280,31 @@ class RenderCuda:
         raise TypeError("readback_framebuffer takes float32 or uint8 buffers")
 
     def framebuffer(self):
-        w, h, c = self.get_framebuffer_size()
-        out = np.empty((h, w, c), np.float32)
+        # the float image has the render size; get_framebuffer_size() is the (upscaled) LDR target's (render_vulkan.cpp:2250-2287)
+        out = np.empty((self.render_height, self.render_width, 4), np.float32)
         if self.readback_framebuffer(out) != out.size:
             raise RptrError("readback failed: " + self._L.rptr_cuda_last_error(self._h).decode())
         return out
+
+    def framebuffer_ldr(self):
+        """The sRGB8 render target (RGBA, upscaled by render_upscale_factor; after process_taa() the processed frame)."""
+        w, h, c = self.get_framebuffer_size()
+        out = np.empty((h, w, c), np.uint8)
+        if self.readback_framebuffer(out) != out.size:
+            raise RptrError("readback failed: " + self._L.rptr_cuda_last_error(self._h).decode())
+        return out
+
+    def process_taa(self):
+        """ProcessTAAVulkan::process (vulkan/processing/process_taa.cpp:93-136): after end_frame, when options.enable_taa and
+        params.reprojection_mode != NONE (app.cpp:517-520).  Needs option realtime_resolve."""
+        self._check(self._L.rptr_cuda_process_taa(self._h))
 
     def readback_aov(self, aov_index, buffer):
         """RenderGraphic::readback_aov: half-float RGBA into a uint16 / float16 array; returns the element count (0 = unavailable)."""
         return self._L.rptr_cuda_readback_aov(self._h, int(aov_index), buffer.size, buffer.ctypes.data)
 
     def aov(self, aov_index):
-        w, h, c = self.get_framebuffer_size()
-        a = np.zeros((h, w, c), np.float16)
+        a = np.zeros((self.render_height, self.render_width, 4), np.float16)
         if self.readback_aov(aov_index, a) != a.size:
             raise RptrError("AOV %d is not available" % aov_index)
         return a

@@ -25,6 +25,7 @@
 #include "rptr_host.hpp"
 #include "rptr_trace_kernels.cuh"
 #include "rptr_bvh_build.hpp"
+#include "rptr_post.cuh"
 
 using namespace rp;
 
@@ -445,11 +446,16 @@ __device__ __forceinline__ void tonemap(int mode, float4 &c) {
         c.x *= scale; c.y *= scale; c.z *= scale;
     }
 }
-__global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, const ushort4 *aov_ar, const ushort4 *aov_nd, const ushort4 *aov_mj, uchar4 *out,
-                                                  uint32_t n, float exposure_scale, int output_channel, int output_moment, int tone_mapping_mode,
-                                                  float width, float height) {
+// display_alpha: with the temporal resolve the accumulator's alpha holds the history weight and the display chain goes on with the
+// alpha of the frame's own sample (process_samples.comp:107-113: the return value of reproject_and_accumulate).
+// upscale: render_upscale_factor; the LDR target is upscale x larger, 2 replicates every pixel 2 x 2, any other factor stores the
+// pixel at its own coordinates (process_samples.comp:192-199, as written).
+__global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, const float *display_alpha, const ushort4 *aov_ar, const ushort4 *aov_nd,
+                                                  const ushort4 *aov_mj, uchar4 *out, uint32_t n, float exposure_scale, int output_channel,
+                                                  int output_moment, int tone_mapping_mode, float width, float height, int upscale) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 c = accum[i];
+        if (display_alpha) c.w = display_alpha[i];
         c.w = fminf(c.w, 1.0f);
         if (!(c.w >= 0.0f)) continue;
         if (output_channel == 0) {
@@ -479,8 +485,39 @@ __global__ void __launch_bounds__(256) k_to_srgb8(const float4 *accum, const ush
             const float s = (x <= 0.0031308f) ? 12.92f * x : 1.055f * powf(fmaxf(fabsf(x), 1.192092896e-07f), 1.0f / 2.4f) - 0.055f;
             o[k] = (unsigned char)(fminf(fmaxf(s, 0.0f), 1.0f) * 255.0f + 0.5f); // NaN (0 * inf of a far depth) stores 0
         }
-        out[i] = make_uchar4(o[0], o[1], o[2], (unsigned char)(fminf(fmaxf(c.w, 0.0f), 1.0f) * 255.0f + 0.5f));
+        const uchar4 px = make_uchar4(o[0], o[1], o[2], (unsigned char)(fminf(fmaxf(c.w, 0.0f), 1.0f) * 255.0f + 0.5f));
+        if (upscale == 1) {
+            out[i] = px;
+        } else {
+            const uint32_t w = (uint32_t)width, x = i % w, y = i / w, ow = w * (uint32_t)upscale;
+            if (upscale == 2) {
+                out[(size_t)(2 * y) * ow + 2 * x] = px;
+                out[(size_t)(2 * y + 1) * ow + 2 * x] = px;
+                out[(size_t)(2 * y) * ow + 2 * x + 1] = px;
+                out[(size_t)(2 * y + 1) * ow + 2 * x + 1] = px;
+            } else
+                out[(size_t)y * ow + x] = px;
+        }
     }
+}
+
+// process_samples.comp:106-113 for the frames after the first one since a reset, reprojection_mode == ACCUMULATE, temporal build
+__global__ void __launch_bounds__(256) k_reproject(ResolveImages im, float4 *accum, float *display_alpha, float min_sample_weight, int batch) {
+    const uint32_t n = (uint32_t)im.w * (uint32_t)im.h;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 stored;
+        const float4 shown = reproject_and_accumulate(im, accum[i], (int)(i % (uint32_t)im.w), (int)(i / (uint32_t)im.w), min_sample_weight, batch, &stored);
+        accum[i] = stored; // the pass reads the accumulator at its own pixel only: in place
+        display_alpha[i] = shown.w;
+    }
+}
+__global__ void __launch_bounds__(256) k_copy_alpha(const float4 *accum, float *display_alpha, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) display_alpha[i] = accum[i].w;
+}
+__global__ void __launch_bounds__(256) k_taa(TaaImages im, uchar4 *out) {
+    const uint32_t n = (uint32_t)im.w * (uint32_t)im.h;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = process_taa_pixel(im, (int)(i % (uint32_t)im.w), (int)(i / (uint32_t)im.w));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -506,7 +543,19 @@ struct rptr_ctx {
     // framebuffer
     int32_t width = 0, height = 0;
     float4 *accum = nullptr;
-    uchar4 *ldr = nullptr;
+    uchar4 *ldr = nullptr;       // the LDR target of this frame, (width * upscale) x (height * upscale)
+    // RenderBackendOptions::render_upscale_factor (configure_for / option "render_upscale_factor"); takes effect at the next initialize, as in
+    // the reference (render_vulkan.cpp:255-263 sizes the render targets there)
+    int upscale_option = 1, upscale = 1;
+    // the temporal build (ENABLE_REALTIME_RESOLVE, CMakeLists.txt:98): option "realtime_resolve"
+    int realtime_resolve = 0;
+    int enable_taa = 0;             // RenderBackendOptions::enable_taa
+    float4 *accum_history = nullptr; // accum_buffers[!active_accum_buffer]: the accumulator as the previous frame left it
+    ushort4 *nd_history = nullptr;   // aov_buffers[(!active) * AOVBufferCount + AOVNormalDepthIndex]
+    float *display_alpha = nullptr;
+    bool display_alpha_valid = false;
+    uchar4 *ldr_history = nullptr, *ldr_raw = nullptr; // render_targets[!active_render_target]; snapshot of the target before the TAA pass
+    bool ldr_valid = false;          // ctx->ldr holds this frame's image (process_taa ran): readback_u8 returns it as it is
     ushort4 *aov_images[3] = {nullptr, nullptr, nullptr}; // RGBA16F: albedo + roughness, normal + depth, motion + jitter (RenderGraphic::AOVBufferIndex)
     float vp[16] = {0.0f}, vp_reference[16] = {0.0f}; // view_params.VP of the current / previous begin_frame (zero before the first: render_vulkan.cpp:103)
     int aov_buffers = 1;                         // option "aov_buffers": the reference always writes them (ENABLE_AOV_BUFFERS)
@@ -739,6 +788,7 @@ static void collect_timers(rptr_ctx *ctx) {
 // C ABI
 // ---------------------------------------------------------------------------------------------------------------------
 extern "C" {
+static void free_temporal_buffers(rptr_ctx *ctx);
 
 const char *rptr_cuda_name(void) { return "CUDA wavefront path tracer (sm_100a)"; }
 
@@ -795,6 +845,7 @@ void rptr_cuda_destroy(rptr_ctx *ctx) {
     rptr_cuda_comm_destroy(ctx);
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
+    free_temporal_buffers(ctx);
     cudaFree(ctx->reduced);
     for (ushort4 *im : ctx->aov_images) cudaFree(im);
     cudaFree(ctx->dcounters);
@@ -819,6 +870,29 @@ const char *rptr_cuda_last_error(const rptr_ctx *ctx) { return ctx ? ctx->error.
 
 static int ensure_ray_query_buffers(rptr_ctx *ctx);
 
+static void free_temporal_buffers(rptr_ctx *ctx) {
+    cudaFree(ctx->accum_history); cudaFree(ctx->nd_history); cudaFree(ctx->display_alpha); cudaFree(ctx->ldr_history); cudaFree(ctx->ldr_raw);
+    ctx->accum_history = nullptr; ctx->nd_history = nullptr; ctx->display_alpha = nullptr; ctx->ldr_history = nullptr; ctx->ldr_raw = nullptr;
+    ctx->display_alpha_valid = false;
+    ctx->ldr_valid = false;
+}
+// history images of the temporal build, allocated when the option is first used with the current frame size
+static int ensure_temporal_buffers(rptr_ctx *ctx) {
+    if (ctx->accum_history) return 0;
+    const size_t n = (size_t)ctx->width * ctx->height, nl = n * ctx->upscale * ctx->upscale;
+    CU(cudaMalloc((void **)&ctx->accum_history, n * sizeof(float4)));
+    CU(cudaMalloc((void **)&ctx->nd_history, n * sizeof(ushort4)));
+    CU(cudaMalloc((void **)&ctx->display_alpha, n * sizeof(float)));
+    CU(cudaMalloc((void **)&ctx->ldr_history, nl * sizeof(uchar4)));
+    CU(cudaMalloc((void **)&ctx->ldr_raw, nl * sizeof(uchar4)));
+    CU(cudaMemsetAsync(ctx->accum_history, 0, n * sizeof(float4), ctx->stream));
+    CU(cudaMemsetAsync(ctx->nd_history, 0, n * sizeof(ushort4), ctx->stream));
+    CU(cudaMemsetAsync(ctx->display_alpha, 0, n * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(ctx->ldr_history, 0, nl * sizeof(uchar4), ctx->stream));
+    CU(cudaMemsetAsync(ctx->ldr_raw, 0, nl * sizeof(uchar4), ctx->stream));
+    return 0;
+}
+
 int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height) {
     if (!ctx) return 1;
     if (width <= 0 || height <= 0 || (int64_t)width * height > (1ll << 28)) return fail(ctx, "invalid framebuffer size %dx%d", width, height);
@@ -827,17 +901,20 @@ int rptr_cuda_initialize(rptr_ctx *ctx, int32_t width, int32_t height) {
     cudaFree(ctx->accum);
     cudaFree(ctx->ldr);
     cudaFree(ctx->reduced);
+    free_temporal_buffers(ctx);
     ctx->reduced = nullptr;
     ctx->reduced_valid = false;
     for (ushort4 *im : ctx->aov_images) cudaFree(im);
     ctx->accum = nullptr;
     ctx->ldr = nullptr;
+    ctx->upscale = ctx->upscale_option;
     ctx->aov_images[0] = ctx->aov_images[1] = ctx->aov_images[2] = nullptr;
     ctx->width = width;
     ctx->height = height;
     const size_t n = (size_t)width * height;
     CU(cudaMalloc((void **)&ctx->accum, n * sizeof(float4)));
-    CU(cudaMalloc((void **)&ctx->ldr, n * sizeof(uchar4)));
+    CU(cudaMalloc((void **)&ctx->ldr, n * sizeof(uchar4) * ctx->upscale * ctx->upscale));
+    CU(cudaMemsetAsync(ctx->ldr, 0, n * sizeof(uchar4) * ctx->upscale * ctx->upscale, ctx->stream));
     CU(cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
     for (int i = 0; i < 3; ++i) {
         CU(cudaMalloc((void **)&ctx->aov_images[i], n * sizeof(ushort4)));
@@ -1047,6 +1124,16 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
         if (value != 0 && value != 1) return fail(ctx, "bvh_builder must be 0 (host builder) or 1 (device builder)");
         ctx->bvh_builder = (int)value; // takes effect at the next set_scene
     }
+    else if (n == "realtime_resolve") {
+        if (value != 0 && value != 1) return fail(ctx, "realtime_resolve must be 0 or 1");
+        if (ctx->in_frame) return fail(ctx, "realtime_resolve cannot change inside a frame");
+        ctx->realtime_resolve = (int)value;
+        if (!value) free_temporal_buffers(ctx);
+    }
+    else if (n == "render_upscale_factor") {
+        if (value < 1 || value > 8) return fail(ctx, "render_upscale_factor must be in [1, 8]");
+        ctx->upscale_option = (int)value; // sizes the LDR target at the next initialize
+    }
     else if (n == "tile_rank") ctx->tile_rank = (int)value;
     else if (n == "tile_world") ctx->tile_world = (int)value;
     else if (n == "tile_rows") ctx->tile_rows = (int)value;
@@ -1083,6 +1170,13 @@ int rptr_cuda_begin_frame(rptr_ctx *ctx, const rptr_camera_params *camera, const
     if (params->batch_spp < 1) return fail(ctx, "batch_spp must be >= 1");
     if (params->max_path_depth < 1 || params->max_path_depth > 64) return fail(ctx, "max_path_depth out of range");
     if (ctx->tile_rank < 0 || ctx->tile_rank >= ctx->tile_world) return fail(ctx, "tile_rank %d outside tile_world %d", ctx->tile_rank, ctx->tile_world);
+    if (ctx->realtime_resolve) {
+        if (ctx->tile_world != 1) return fail(ctx, "option realtime_resolve needs the whole frame on one GPU (the passes read neighbouring pixels)");
+        if (params->reprojection_mode == RPTR_REPROJECTION_MODE_ACCUMULATE && params->spp_accumulation_window < 1)
+            return fail(ctx, "spp_accumulation_window must be >= 1");
+        CU(cudaSetDevice(ctx->device));
+        if (ensure_temporal_buffers(ctx)) return 1;
+    }
     {   // The box tests of the traversal are conservative for ray origins within 8 scene extents of the world origin (padding of
         // 2^-16 |coordinate| + 2^-17 extent against the cancellation in org / d - o / d, rptr_host.cpp build_bvh); farther out
         // true hits could be culled silently, so such a camera is refused instead.
@@ -1341,8 +1435,10 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                 if (queries)
                     k_resolve_queries<<<g_light, 256, 0, sb.s_main>>>(fp, sb.w, results, (uint32_t)tm.local_pixels, sample_base + (uint32_t)sb.first, sb.nl, ctx->dcounters);
                 else
+                    // the temporal build folds the history in k_reproject (draw_frame), from the frame's own sample
                     k_resolve<<<g_light, 256, 0, sb.s_main>>>(fp, tm, sb.w, ctx->accum, sample_base + (uint32_t)sb.first, sb.nl, ctx->dcounters, sb.aov,
-                                                              ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_DISCARD_HISTORY);
+                                                              ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_DISCARD_HISTORY ||
+                                                                  (ctx->realtime_resolve && ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_ACCUMULATE));
                 ctx->launches++;
             }
             if (n_sub > 1) CU(cudaEventRecord(sb.ev_done, sb.s_main));
@@ -1370,6 +1466,22 @@ int rptr_cuda_draw_frame(rptr_ctx *ctx, int32_t variant) {
     ctx->reduced_valid = false;
     CU(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (render_waves(ctx, fp, tm, fp.batch, fp.first_sample, nullptr, nullptr)) return 1;
+    ctx->ldr_valid = false;
+    ctx->display_alpha_valid = false;
+    if (ctx->realtime_resolve) {
+        const size_t n = (size_t)ctx->width * ctx->height;
+        if (ctx->params.reprojection_mode == RPTR_REPROJECTION_MODE_ACCUMULATE && fp.first_sample > 0) { // process_samples.comp:106-113
+            if (!ctx->aov_buffers) return fail(ctx, "reprojection_mode ACCUMULATE needs the AOV images (option aov_buffers)");
+            const ResolveImages im{ctx->width, ctx->height, ctx->accum_history, ctx->nd_history, ctx->aov_images[1], ctx->aov_images[2]};
+            k_reproject<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(im, ctx->accum, ctx->display_alpha,
+                                                                  1.0f / (float)ctx->params.spp_accumulation_window, ctx->params.batch_spp);
+            ctx->launches++;
+            ctx->display_alpha_valid = true;
+        }
+        // this frame's accumulator and normal / depth image are the next frame's history (the reference swaps two sets of images)
+        CU(cudaMemcpyAsync(ctx->accum_history, ctx->accum, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->nd_history, ctx->aov_images[1], n * sizeof(ushort4), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -1462,8 +1574,9 @@ int rptr_cuda_frame_state(rptr_ctx *ctx, uint32_t *frame_id, uint32_t *frame_off
 
 int rptr_cuda_framebuffer_size(rptr_ctx *ctx, uint32_t *width, uint32_t *height, uint32_t *channels) {
     if (!ctx) return 1;
-    if (width) *width = (uint32_t)ctx->width;
-    if (height) *height = (uint32_t)ctx->height;
+    // RenderVulkan::get_framebuffer_size (render_vulkan.cpp:2250-2254): the dimensions of the (upscaled) LDR render target
+    if (width) *width = (uint32_t)(ctx->width * ctx->upscale);
+    if (height) *height = (uint32_t)(ctx->height * ctx->upscale);
     if (channels) *channels = 4;
     return 0;
 }
@@ -1483,21 +1596,53 @@ size_t rptr_cuda_readback_f32(rptr_ctx *ctx, size_t n_elems, float *dst) {
     return size;
 }
 
-size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst) {
-    if (!ctx || !dst || !ctx->accum) return 0;
-    const size_t size = (size_t)ctx->width * ctx->height * 4;
-    if (n_elems < size) return 0;
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+// process_samples.comp:138-200 into the LDR target
+static void make_ldr(rptr_ctx *ctx) {
     const float scale = exp2f(ctx->params.exposure);
     const bool aov_on = ctx->aov_buffers != 0;
-    k_to_srgb8<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->accum, aov_on ? ctx->aov_images[0] : nullptr, aov_on ? ctx->aov_images[1] : nullptr,
-                                                          aov_on ? ctx->aov_images[2] : nullptr, ctx->ldr, (uint32_t)(size / 4), scale,
+    k_to_srgb8<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->accum, ctx->display_alpha_valid ? ctx->display_alpha : nullptr,
+                                                          aov_on ? ctx->aov_images[0] : nullptr, aov_on ? ctx->aov_images[1] : nullptr,
+                                                          aov_on ? ctx->aov_images[2] : nullptr, ctx->ldr, (uint32_t)((size_t)ctx->width * ctx->height), scale,
                                                           ctx->params.output_channel, ctx->params.output_moment, ctx->params.early_tone_mapping_mode,
-                                                          (float)ctx->width, (float)ctx->height);
+                                                          (float)ctx->width, (float)ctx->height, ctx->upscale);
     ctx->launches++;
+}
+
+size_t rptr_cuda_readback_u8(rptr_ctx *ctx, size_t n_elems, uint8_t *dst) {
+    if (!ctx || !dst || !ctx->accum) return 0;
+    const size_t size = (size_t)ctx->width * ctx->height * 4 * ctx->upscale * ctx->upscale; // render_vulkan.cpp:255-263: the targets are upscaled
+    if (n_elems < size) return 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+    if (!ctx->ldr_valid) make_ldr(ctx); // after process_taa the target already holds the frame
     if (cudaMemcpyAsync(dst, ctx->ldr, size, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
     return size;
+}
+
+// ProcessTAAVulkan::process (vulkan/processing/process_taa.cpp:93-136), run by the application after end_frame when
+// options.enable_taa && params.reprojection_mode != NONE (app.cpp:517-520).
+int rptr_cuda_process_taa(rptr_ctx *ctx) {
+    if (!ctx) return 1;
+    if (!ctx->accum) return fail(ctx, "process_taa before initialize");
+    if (ctx->in_frame) return fail(ctx, "process_taa inside begin_frame/end_frame (the pass runs after end_frame)");
+    if (!ctx->realtime_resolve) return fail(ctx, "process_taa needs option realtime_resolve (the reference builds the pass with ENABLE_REALTIME_RESOLVE only)");
+    if (!ctx->aov_buffers) return fail(ctx, "process_taa needs the motion image (option aov_buffers)");
+    CU(cudaSetDevice(ctx->device));
+    if (ensure_temporal_buffers(ctx)) return 1;
+    if (ctx->ldr_valid) return 0; // already run for this frame
+    const size_t nl = (size_t)ctx->width * ctx->height * ctx->upscale * ctx->upscale;
+    make_ldr(ctx);
+    if (ctx->frame_id > 1) { // process_taa.cpp:95-96
+        CU(cudaMemcpyAsync(ctx->ldr_raw, ctx->ldr, nl * sizeof(uchar4), cudaMemcpyDeviceToDevice, ctx->stream));
+        const TaaImages im{ctx->width * ctx->upscale, ctx->height * ctx->upscale, ctx->upscale, ctx->width, ctx->height, ctx->ldr_raw, ctx->ldr_history,
+                           ctx->aov_images[2]};
+        k_taa<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(im, ctx->ldr);
+        ctx->launches++;
+    }
+    CU(cudaMemcpyAsync(ctx->ldr_history, ctx->ldr, nl * sizeof(uchar4), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaGetLastError());
+    ctx->ldr_valid = true;
+    return 0;
 }
 
 size_t rptr_cuda_readback_aov(rptr_ctx *ctx, int32_t aov_index, size_t n_elems, uint16_t *dst) {
@@ -1699,12 +1844,12 @@ int rptr_cuda_configure_for(rptr_ctx *ctx, const rptr_backend_options *o, int32_
         why += "light_sampling_variant must be RIS (binned triangle lights + sun); ";
         ok.light_sampling_variant = RPTR_LIGHT_SAMPLING_VARIANT_RIS;
     }
-    if (o->render_upscale_factor != 1) {
-        why += "render_upscale_factor " + std::to_string(o->render_upscale_factor) + " is not supported (no upscaling pass); ";
-        ok.render_upscale_factor = 1;
+    if (ok.render_upscale_factor > 8) {
+        why += "render_upscale_factor " + std::to_string(o->render_upscale_factor) + " is out of range (1..8); ";
+        ok.render_upscale_factor = 8;
     }
-    if (o->enable_taa) {
-        why += "enable_taa is not supported (no TAA pass); ";
+    if (o->enable_taa && !ctx->realtime_resolve) {
+        why += "enable_taa needs option realtime_resolve (the reference compiles its TAA pass with ENABLE_REALTIME_RESOLVE only); ";
         ok.enable_taa = 0;
     }
     if (ok.rng_variant != RPTR_RNG_VARIANT_UNIFORM) {
@@ -1719,8 +1864,12 @@ int rptr_cuda_configure_for(rptr_ctx *ctx, const rptr_backend_options *o, int32_
     if (available) *available = ok;
     if (!why.empty()) return fail(ctx, "configure_for: %s", why.c_str());
     ctx->rng_variant = ok.rng_variant;
+    ctx->upscale_option = ok.render_upscale_factor; // the LDR target is sized by the next initialize (render_vulkan.cpp:255-263; the app
+                                                    // re-initialises when the factor changes, app.cpp:434-445)
+    ctx->enable_taa = ok.enable_taa;
     // what the reference does at the end of a successful configure_for when built without ENABLE_REALTIME_RESOLVE
-    // (render_vulkan.cpp:1911-1915) -- params.reprojection_mode = NONE -- is left to the caller's RenderParams here
+    // (render_vulkan.cpp:1911-1915) -- params.reprojection_mode = NONE -- is left to the caller's RenderParams here: without option
+    // realtime_resolve the modes NONE and ACCUMULATE are the same running mean
     return 0;
 }
 

@@ -50,8 +50,31 @@ int RenderCuda::variant_index(char const *name) { return std::strcmp(name, "PT_W
 void RenderCuda::initialize(const int w, const int h) {
     fb_width = w;
     fb_height = h;
+    // RenderVulkan::initialize sizes its LDR render targets by options.render_upscale_factor (vulkan/render_vulkan.cpp:255-263)
+    check(rptr_cuda_set_option(ctx, "render_upscale_factor", options.render_upscale_factor < 1 ? 1 : options.render_upscale_factor));
+#ifdef ENABLE_REALTIME_RESOLVE
+    check(rptr_cuda_set_option(ctx, "realtime_resolve", 1)); // the temporal build: reproject_and_accumulate + the TAA step
+#endif
     check(rptr_cuda_initialize(ctx, w, h));
 }
+
+// RenderBackend::create_processing_step (librender/render_backend.h:84; vulkan/render_vulkan_extensions.cpp:36-39): the application
+// asks for the TAA step under ENABLE_REALTIME_RESOLVE (app.cpp:97-99) and runs it after end_frame (app.cpp:517-520).
+namespace {
+struct ProcessTAACuda : RenderExtension {
+    RenderCuda *backend;
+    explicit ProcessTAACuda(RenderCuda *b) : backend(b) {}
+    std::string name() const override { return "CUDA TAA Processing Extension"; }
+    void initialize(const int, const int) override {}
+    void update_scene_from_backend(const Scene &) override {}
+    void process(CommandStream *, int) override { backend->process_taa(); }
+};
+} // namespace
+std::unique_ptr<RenderExtension> RenderCuda::create_processing_step(RenderProcessingStep step) {
+    if (step == RenderProcessingStep::TAA) return std::unique_ptr<RenderExtension>(new ProcessTAACuda(this));
+    return RenderBackend::create_processing_step(step);
+}
+void RenderCuda::process_taa() { check(rptr_cuda_process_taa(ctx)); }
 
 // Scene -> rptr_scene_desc.  Geometry must be unindexed with quantised positions, which is what the reference's own
 // backend requires as well (REQUIRE_UNROLLED_VERTICES / QUANTIZED_POSITIONS: vulkan/render_vulkan.cpp:575-596).
@@ -269,7 +292,11 @@ RenderStats RenderCuda::stats() {
 }
 void RenderCuda::flush_pipeline() { check(rptr_cuda_flush(ctx)); }
 
-glm::uvec3 RenderCuda::get_framebuffer_size() const { return glm::uvec3(fb_width, fb_height, 4); }
+glm::uvec3 RenderCuda::get_framebuffer_size() const { // the (upscaled) LDR target, as RenderVulkan::get_framebuffer_size
+    uint32_t w = 0, h = 0, c = 0;
+    check(rptr_cuda_framebuffer_size(ctx, &w, &h, &c));
+    return glm::uvec3(w, h, c);
+}
 size_t RenderCuda::readback_framebuffer(size_t bufferSize, unsigned char *buffer, bool) { return rptr_cuda_readback_u8(ctx, bufferSize, buffer); }
 size_t RenderCuda::readback_framebuffer(size_t bufferSize, float *buffer, bool) { return rptr_cuda_readback_f32(ctx, bufferSize, buffer); }
 size_t RenderCuda::readback_aov(AOVBufferIndex aovIndex, size_t bufferSize, uint16_t *buffer, bool) {

@@ -22,6 +22,8 @@ struct RenderCuda : RenderBackend {
 
     std::string name() const override;
     void initialize(const int fb_width, const int fb_height) override;
+    std::unique_ptr<RenderExtension> create_processing_step(RenderProcessingStep step) override;
+    void process_taa(); // ProcessTAAVulkan::process
     std::vector<std::string> const &variant_names() const override;
     int variant_index(char const *name) override;
 

@@ -11,6 +11,7 @@ BASE_MATERIAL_VOLUME = 0x04
 BASE_MATERIAL_EXTENDED = 0x08
 GEOMETRY_FLAGS_NOALPHA = 0x01
 RNG_VARIANT_UNIFORM, RNG_VARIANT_BN, RNG_VARIANT_SOBOL, RNG_VARIANT_Z_SBL = 0, 1, 2, 3  # librender/render_params.glsl.h:34-37
+REPROJECTION_MODE_NONE, REPROJECTION_MODE_DISCARD_HISTORY, REPROJECTION_MODE_ACCUMULATE = 0, 1, 2  # rendering/postprocess/reprojection.h:11-13
 MAX_PATH_DEPTH = 9
 DEFAULT_RR_PATH_DEPTH = 2
 DEFAULT_RAY_QUERY_BUDGET = 512 * 512  # librender/render_params.glsl.h:172

@@ -306,3 +306,29 @@ extern "C" int hostsim_trace(const hostsim_scene *s, const rptr_render_ray_query
     }
     return 0;
 }
+
+// ---- the temporal passes (csrc/rptr_post.cuh), image by image -----------------------------------------------------------------
+#include "../../realtimepathtracingresearchframework_b200/csrc/rptr_post.cuh"
+extern "C" {
+// process_samples.comp:106-113 over a whole frame; accum_cur = this frame's samples, stored / shown = accumulator and display colour
+void hostsim_reproject(int32_t w, int32_t h, const float *accum_cur, const float *history, const uint16_t *nd_history, const uint16_t *nd,
+                       const uint16_t *mj, float min_sample_weight, int32_t batch, float *stored, float *shown) {
+    const ResolveImages im{w, h, reinterpret_cast<const float4 *>(history), reinterpret_cast<const ushort4 *>(nd_history),
+                           reinterpret_cast<const ushort4 *>(nd), reinterpret_cast<const ushort4 *>(mj)};
+    for (int32_t y = 0; y < h; ++y)
+        for (int32_t x = 0; x < w; ++x) {
+            const size_t i = (size_t)y * w + x;
+            float4 st;
+            const float4 sh = reproject_and_accumulate(im, reinterpret_cast<const float4 *>(accum_cur)[i], x, y, min_sample_weight, batch, &st);
+            reinterpret_cast<float4 *>(stored)[i] = st;
+            reinterpret_cast<float4 *>(shown)[i] = sh;
+        }
+}
+void hostsim_taa(int32_t w, int32_t h, int32_t upscale, int32_t rw, int32_t rh, const uint8_t *current, const uint8_t *history, const uint16_t *mj,
+                 uint8_t *out) {
+    const TaaImages im{w, h, upscale, rw, rh, reinterpret_cast<const uchar4 *>(current), reinterpret_cast<const uchar4 *>(history),
+                       reinterpret_cast<const ushort4 *>(mj)};
+    for (int32_t y = 0; y < h; ++y)
+        for (int32_t x = 0; x < w; ++x) reinterpret_cast<uchar4 *>(out)[(size_t)y * w + x] = process_taa_pixel(im, x, y);
+}
+}

@@ -1019,3 +1019,91 @@ def test_textured_scene_uv_lookups(oracle):
         r.set_scene(bad)
     r.render_spp(s.camera, 1)  # the failed set_scene left the previous scene in place
     assert_identical(r.framebuffer(), o.render(W, H, s.camera, sp, spp=1, transmission=1, frame_offset=2)[0], "still the textured scene")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f3: render_upscale_factor and the temporal passes (ENABLE_REALTIME_RESOLVE build: reprojection accumulate + TAA)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_render_upscale_factor_ldr_target():
+    """render_upscale_factor sizes the LDR render target (vulkan/render_vulkan.cpp:255-263); process_samples.comp:192-199 replicates
+    every pixel 2 x 2 for factor 2 and stores the pixel at its own coordinates for any other factor."""
+    s = scenes.cornell_box()
+    W, H = 96, 54
+    base = make_backend(s, W, H)
+    base.render_spp(s.camera, 2)
+    ldr1 = base.framebuffer_ldr()
+    assert ldr1.shape == (H, W, 4)
+    for f in (2, 3):
+        r = RenderCuda(device=0)
+        rbo = T.RenderBackendOptions()
+        rbo.render_upscale_factor = f
+        assert r.configure_for(rbo), r.last_error()   # taken over for the next initialize, like the reference's re-initialisation
+        r.initialize(W, H)
+        r.set_scene(s)
+        r.update_config(T.SceneConfig())
+        r.render_spp(s.camera, 2)
+        assert r.get_framebuffer_size() == (W * f, H * f, 4)
+        assert np.array_equal(r.framebuffer().view(np.uint32), base.framebuffer().view(np.uint32))   # the float image keeps the render size
+        small = np.zeros((H, W, 4), np.uint8)
+        assert r.readback_framebuffer(small) == 0                                                      # buffer too small for the target
+        ldr = r.framebuffer_ldr()
+        if f == 2:
+            assert np.array_equal(ldr, np.repeat(np.repeat(ldr1, 2, 0), 2, 1))
+        else:
+            assert np.array_equal(ldr[:H, :W], ldr1) and not ldr[H:].any() and not ldr[:, W:].any()
+
+
+def test_realtime_resolve_reprojection_and_taa_against_the_oracle(oracle):
+    """Option realtime_resolve = the reference's ENABLE_REALTIME_RESOLVE build.  A camera dolly over six frames: context A renders
+    the frames' own samples (DISCARD_HISTORY) -- the inputs of the pass --, context B runs reprojection_mode = ACCUMULATE with the
+    temporal passes.  B's accumulator must equal the oracle's reproject_and_accumulate chained over A's frames bit for bit, and
+    B's TAA output the oracle's process_taa of B's own LDR target and the previous output."""
+    s = scenes.random_triangles(30000)
+    W, H = 160, 90
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    a = make_backend(s, W, H, sky)
+    a.params.reprojection_mode = T.REPROJECTION_MODE_DISCARD_HISTORY
+    b = make_backend(s, W, H, sky, realtime_resolve=1)
+    b.params.reprojection_mode = T.REPROJECTION_MODE_ACCUMULATE
+    b.params.spp_accumulation_window = 16
+    hist = hist_nd = ldr_hist = None
+    blended = 0
+    for k in range(6):
+        cam = T.RenderCameraParams.from_buffer_copy(s.camera)
+        cam.pos[0] += 0.04 * k
+        cam.pos[2] -= 0.05 * k
+        for r in (a, b):
+            r.params.batch_spp = 1
+            r.render(None, RenderConfiguration(cam, reset_accumulation=(k == 0)))
+        cur, nd, mj = a.framebuffer(), a.aov(1), a.aov(2)
+        assert np.array_equal(b.aov(1).view(np.uint16), nd.view(np.uint16)) and np.array_equal(b.aov(2).view(np.uint16), mj.view(np.uint16))
+        if k == 0:
+            stored, shown = cur, cur
+        else:
+            stored, shown = oracle.reproject_accumulate(cur, hist, hist_nd, nd, mj, 1.0 / 16, 1)
+            wgt = 1.0 - stored[..., 3]
+            blended += int(((wgt < 1.0) & (wgt > 1.0 / 16 + 1e-6)).sum())
+        got = b.framebuffer()
+        assert np.array_equal(got.view(np.uint32), stored.view(np.uint32)), "frame %d" % k
+        hist, hist_nd = stored, nd
+        # the LDR target of the frame shows the pass's return value: the resolved colour with the alpha of the frame's own sample
+        raw = b.framebuffer_ldr()
+        from display_chain import to_srgb8
+        assert np.abs(raw.astype(np.int32) - to_srgb8(shown[..., :3], shown[..., 3])).max() <= 1
+        b.process_taa()
+        out = b.framebuffer_ldr()
+        if k < 1:   # process_taa.cpp:95-96: skipped while frame_id <= 1, i.e. after the first one-sample frame only
+            assert np.array_equal(out, raw)
+        else:
+            assert np.array_equal(out, oracle.process_taa(raw, ldr_hist, mj, 1)), "TAA, frame %d" % k
+            assert not np.array_equal(out, raw)
+        ldr_hist = out
+    assert blended > 1000   # the history was actually used (not every pixel rejected it)
+    # without the option the mode is the running mean of the default build, and the TAA step does not exist
+    c = make_backend(s, W, H, sky)
+    with pytest.raises(RptrError):
+        c.process_taa()
+    rbo = T.RenderBackendOptions()
+    rbo.enable_taa = 1
+    assert not c.configure_for(rbo) and "realtime_resolve" in c.last_error()
+    assert b.configure_for(rbo), b.last_error()
