@@ -890,13 +890,15 @@ def test_backend_options_normalize_and_configure(oracle):
     r = make_backend(s, W, H)
     rbo = T.RenderBackendOptions()
     assert r.configure_for(rbo)
-    for field, bad in (("light_sampling_variant", T.LIGHT_SAMPLING_VARIANT_NONE), ("render_upscale_factor", 2), ("enable_taa", 1)):
+    # (render_upscale_factor is supported -- test_render_upscale_factor_ldr_target; enable_taa needs the temporal build, option
+    #  realtime_resolve -- test_realtime_resolve_reprojection_and_taa_against_the_oracle)
+    for field, bad in (("light_sampling_variant", T.LIGHT_SAMPLING_VARIANT_NONE), ("render_upscale_factor", 9), ("enable_taa", 1)):
         x = T.RenderBackendOptions()
         setattr(x, field, bad)
         avail = T.RenderBackendOptions()
         assert not r.configure_for(x, 0, avail)
         assert field in r.last_error()
-        assert getattr(avail, field) == getattr(T.RenderBackendOptions(), field)
+        assert getattr(avail, field) == (8 if field == "render_upscale_factor" else getattr(T.RenderBackendOptions(), field))
         assert r.configure_for(avail)
     assert not r.configure_for(T.RenderBackendOptions(), variant_idx=3)
     x = T.RenderBackendOptions(rng_variant=T.RNG_VARIANT_Z_SBL)
