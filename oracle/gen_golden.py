@@ -579,7 +579,40 @@ def gen_queries(seed=77):
     print("wrote", path, {k: v.shape for k, v in out.items()})
 
 
+POST_CASES = [(1, 1, 8), (2, 4, 32), (3, 1, 1)]   # (seed, batch, spp_accumulation_window) on 61 x 47 frames
+TAA_CASES = [(11, 1), (12, 2)]                     # (seed, upscale) on 40 x 30 render frames
+
+
+def gen_post():
+    """The temporal passes executed from the reference's shader sources (oracle/ref_shim/ref_post.cpp) on the synthetic frames of
+    tests/temporal_util.py: accumulator + display colour of reproject_and_accumulate, LDR target of process_taa."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from temporal_util import synthetic_frame
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref.so"))
+    R.ref_reproject_accumulate.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
+    R.ref_process_taa.argtypes = [C.c_int32] * 5 + [C.c_void_p] * 4
+    out = {}
+    for seed, batch, window in POST_CASES:
+        rng = np.random.default_rng(seed)
+        cur, hist, nd_hist, nd, mj = synthetic_frame(rng, 61, 47)
+        stored, shown = po.reproject_accumulate(cur, hist, nd_hist, nd, mj, 1.0 / window, batch, fn=R.ref_reproject_accumulate)
+        out["reproject_%d_stored" % seed], out["reproject_%d_shown" % seed] = stored, shown
+    for seed, upscale in TAA_CASES:
+        rng = np.random.default_rng(seed)
+        rw, rh = 40, 30
+        w, h = rw * upscale, rh * upscale
+        cur = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        his = np.clip(cur.astype(np.int32) + rng.integers(-40, 41, (h, w, 4)), 0, 255).astype(np.uint8)
+        _, _, _, _, mj = synthetic_frame(rng, rw, rh, motion_scale=0.03)
+        out["taa_%d" % seed] = po.process_taa(cur, his, mj, upscale, fn=R.ref_process_taa)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_post.npz"), **out)
+    print("wrote tests/golden/ref_post.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    if "--post-only" in sys.argv:
+        gen_post()
+        sys.exit(0)
     if "--queries-only" in sys.argv:
         gen_queries()
         sys.exit(0)
@@ -590,3 +623,4 @@ if __name__ == "__main__":
         gen_vectors()
     gen_pointsets()
     gen_queries()
+    gen_post()

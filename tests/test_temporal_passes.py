@@ -12,29 +12,10 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
-def synthetic_frame(rng, w, h, motion_scale=0.02, depth=5.0):
-    """accumulator sample, history (alpha = 1 - weight), normal / depth images and a smooth + noisy motion field"""
-    cur = rng.uniform(0.0, 2.0, (h, w, 4)).astype(np.float32)
-    cur[..., 3] = (rng.uniform(size=(h, w)) > 0.2).astype(np.float32)         # alpha of a sample: the primary ray hit something
-    cur[rng.uniform(size=(h, w)) > 0.97, 3] = 2.0                              # "non-accumulation object types" (alpha > 1)
-    hist = rng.uniform(0.0, 2.0, (h, w, 4)).astype(np.float32)
-    hist[..., 3] = rng.choice(np.array([0.0, 0.5, 0.75, 0.875, 1.0], np.float32), size=(h, w))
-    def nd_image():
-        n = rng.normal(size=(h, w, 3))
-        n /= np.linalg.norm(n, axis=-1, keepdims=True)
-        n = 0.3 * n + np.array([0.0, 0.0, 1.0])                                 # mostly facing the camera, some spread
-        n /= np.linalg.norm(n, axis=-1, keepdims=True)
-        d = depth * (1.0 + 0.02 * rng.normal(size=(h, w, 1)))
-        d[rng.uniform(size=(h, w, 1)) > 0.9] *= 3.0                             # depth edges
-        return np.concatenate([n, d], -1).astype(np.float16)
-    yy, xx = np.mgrid[0:h, 0:w]
-    mj = np.zeros((h, w, 4), np.float32)
-    mj[..., 0] = motion_scale * np.sin(xx / 7.0) + 0.3 * motion_scale * rng.normal(size=(h, w))
-    mj[..., 1] = motion_scale * np.cos(yy / 5.0) + 0.3 * motion_scale * rng.normal(size=(h, w))
-    mj[rng.uniform(size=(h, w)) > 0.98, :2] = 3.0                               # reprojects outside the frame
-    return cur, hist, nd_image(), nd_image(), mj.astype(np.float16)
+from temporal_util import synthetic_frame  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -120,3 +101,56 @@ def test_taa_of_a_constant_image_is_the_identity(passes):
     out = oracle.process_taa(img, img, mj, 1)
     inner = (slice(6, -6), slice(6, -6))   # away from the border, where the Lanczos window reads zeros outside the image
     assert np.array_equal(out[inner], img[inner])
+
+
+# ---- pin: the oracle against the passes EXECUTED from the reference's shader sources (oracle/ref_shim/ref_post.cpp compiles
+# rendering/postprocess/reprojection.glsl and vulkan/processing/process_taa.comp where they lie; outputs committed as
+# tests/golden/ref_post.npz by `python oracle/gen_golden.py --post-only`) -------------------------------------------------------
+@pytest.fixture(scope="module")
+def golden_post():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_post.npz"))
+
+
+@pytest.mark.parametrize("seed,batch,window", [(1, 1, 8), (2, 4, 32), (3, 1, 1)])
+def test_oracle_reprojection_matches_the_reference_shader(oracle, golden_post, seed, batch, window):
+    rng = np.random.default_rng(seed)
+    cur, hist, nd_hist, nd, mj = synthetic_frame(rng, 61, 47)
+    stored, shown = oracle.reproject_accumulate(cur, hist, nd_hist, nd, mj, 1.0 / window, batch)
+    want_stored, want_shown = golden_post["reproject_%d_stored" % seed], golden_post["reproject_%d_shown" % seed]
+    # libm exp / sqrt and unfused dot products on the reference side, RPTR-FP on ours: a few ulp, and no pixel takes another branch
+    assert np.abs(stored[..., 3] - want_stored[..., 3]).max() <= 4e-6          # 1 - sample weight
+    assert np.abs(stored[..., :3] - want_stored[..., :3]).max() <= 2e-6
+    assert np.array_equal(shown[..., 3], want_shown[..., 3]) and np.abs(shown[..., :3] - want_shown[..., :3]).max() <= 2e-6
+    assert np.array_equal(stored[..., 3] == 0.0, want_stored[..., 3] == 0.0)    # history rejected <=> weight exactly 1
+
+
+@pytest.mark.parametrize("seed,upscale", [(11, 1), (12, 2)])
+def test_oracle_taa_matches_the_reference_shader(oracle, golden_post, seed, upscale):
+    rng = np.random.default_rng(seed)
+    rw, rh = 40, 30
+    w, h = rw * upscale, rh * upscale
+    cur = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    his = np.clip(cur.astype(np.int32) + rng.integers(-40, 41, (h, w, 4)), 0, 255).astype(np.uint8)
+    _, _, _, _, mj = synthetic_frame(rng, rw, rh, motion_scale=0.03)
+    got = oracle.process_taa(cur, his, mj, upscale).astype(np.int32)
+    want = golden_post["taa_%d" % seed].astype(np.int32)
+    d = np.abs(got - want)
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3   # libm sin vs the RPTR-FP kernel: a value on a rounding boundary may move by one code
+
+
+def test_reference_executed_passes_reproduce_their_fixture(golden_post):
+    """When oracle/_ref is here (the authoring container), the fixture is what the reference's code returns now."""
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "libref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    R = C.CDLL(so)
+    if not hasattr(R, "ref_reproject_accumulate"):
+        pytest.skip("oracle/_ref predates ref_post.cpp")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import pyoracle as po
+    R.ref_reproject_accumulate.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(1)
+    cur, hist, nd_hist, nd, mj = synthetic_frame(rng, 61, 47)
+    stored, shown = po.reproject_accumulate(cur, hist, nd_hist, nd, mj, 1.0 / 8, 1, fn=R.ref_reproject_accumulate)
+    assert np.array_equal(stored.view(np.uint32), golden_post["reproject_1_stored"].view(np.uint32))
+    assert np.array_equal(shown.view(np.uint32), golden_post["reproject_1_shown"].view(np.uint32))
