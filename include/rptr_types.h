@@ -230,11 +230,18 @@ typedef struct rptr_instance_desc {
  * channels of an sRGB texture through the sRGB transfer function.  Larger textures are rejected with an error. */
 #define RPTR_COLOR_SPACE_LINEAR 0
 #define RPTR_COLOR_SPACE_SRGB 1
+/* One image of Scene::textures (util/image.h:10-27).  `texels` holds mip_levels levels back to back, the base level first,
+ * level k + 1 being (max(w / 2, 1), max(h / 2, 1)) of level k (Image::mip_levels, util/image.cpp:23-40).  bc_format is
+ * Image::bcFormat: 0 = `channels` bytes per texel; 1 = BC1 RGB, -1 = BC1 RGBA (1-bit alpha), 3 = BC3, 5 = BC5 UNORM (two
+ * channels: the normal maps of .vks scenes) -- the formats librender/scene.cpp:836-930 produces; 4 x 4 blocks, every level
+ * padded to whole blocks (vulkan/resource_utils.cpp:85-99).  Block-compressed levels are decoded to RGBA8 inside set_scene. */
 typedef struct rptr_texture_desc {
     int32_t width, height;
-    int32_t channels;    /* 1..4; missing colour channels read 0, missing alpha reads 255 */
+    int32_t channels;    /* 1..4; missing colour channels read 0, missing alpha reads 255 (bc_format 0 only) */
     int32_t color_space; /* RPTR_COLOR_SPACE_* */
     const uint8_t *texels;
+    int32_t bc_format;   /* 0, 1, -1, 3, 5 */
+    int32_t mip_levels;  /* levels stored in texels; 0 reads as 1 */
 } rptr_texture_desc;
 
 /* rendering/bsdfs/texture_channel_mask.h:20-27: a float material parameter with the sign bit set is a texture handle */

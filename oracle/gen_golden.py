@@ -579,6 +579,49 @@ def gen_queries(seed=77):
     print("wrote", path, {k: v.shape for k, v in out.items()})
 
 
+def gen_textures(n=1500, n_mats=300):
+    """f2: the footprint algebra of rendering/rt/footprint.glsl executed from the reference's file (oracle/ref_shim/ref_footprint.cpp), and
+    unpack_material / get_material_alpha of rendering/rt/material_textures.glsl in the USE_MIPMAPPING configuration (textureGrad) executed
+    from the reference's files (ref_shim/ref_materials.cpp) over OUR texture unit (the oracle's textureGrad on tests/texture_util.py's
+    texture set: the reference leaves that part to the hardware)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import texture_util as tu
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref.so"))
+    L = po.lib()
+    f32p = C.POINTER(C.c_float)
+    R.ref_footprint_op.argtypes = [C.c_int32, f32p, f32p]
+    L.oracle_footprint_op.argtypes = [C.c_int32, f32p, f32p]
+    out = {}
+    op0, d2 = tu.footprint_cases(n, 99)
+    F = np.zeros((n, 4), np.float32)
+    F2 = np.zeros((n, 4), np.float32)
+    dp = np.zeros((n, 6), np.float32)
+    for i in range(n):
+        R.ref_footprint_op(0, op0[i].ctypes.data_as(f32p), F[i].ctypes.data_as(f32p))
+        inp = np.concatenate([d2[i], op0[i, :3], F[i]]).astype(np.float32)
+        R.ref_footprint_op(1, inp.ctypes.data_as(f32p), F2[i].ctypes.data_as(f32p))
+        inp2 = np.concatenate([d2[i], F2[i]]).astype(np.float32)
+        R.ref_footprint_op(2, inp2.ctypes.data_as(f32p), dp[i].ctypes.data_as(f32p))
+    out["fp_to_footprint"], out["fp_reflect"], out["fp_to_dpdxy"] = F, F2, dp
+    # material glue over our texture unit
+    tset = tu.texture_set()
+    descs, keep = tu.texture_descs(tset)
+    L.oracle_sample_texture_grad.argtypes = [C.POINTER(T.TextureDesc), C.c_float, C.c_float, f32p, f32p, f32p]
+    UNIT = C.CFUNCTYPE(None, C.c_uint32, f32p, f32p, f32p, f32p)
+
+    def unit(tex_id, uv, dx, dy, rgba):
+        L.oracle_sample_texture_grad(C.byref(descs[tex_id]), uv[0], uv[1], dx, dy, rgba)
+    cb = UNIT(unit)
+    R.ref_unpack_material_grad.argtypes = [C.POINTER(T.BaseMaterial), f32p, f32p, UNIT, f32p]
+    mats, uv, duvdxy = tu.random_textured_materials(n_mats, len(tset), 123)
+    res = np.zeros((n_mats, 17), np.float32)
+    for i, m in enumerate(mats):
+        R.ref_unpack_material_grad(C.byref(m), uv[i].ctypes.data_as(f32p), duvdxy[i].ctypes.data_as(f32p), cb, res[i].ctypes.data_as(f32p))
+    out["mat_grad"] = res
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_textures.npz"), **out)
+    print("wrote tests/golden/ref_textures.npz:", {k: v.shape for k, v in out.items()})
+
+
 POST_CASES = [(1, 1, 8), (2, 4, 32), (3, 1, 1)]   # (seed, batch, spp_accumulation_window) on 61 x 47 frames
 TAA_CASES = [(11, 1), (12, 2)]                     # (seed, upscale) on 40 x 30 render frames
 
@@ -613,6 +656,9 @@ if __name__ == "__main__":
     if "--post-only" in sys.argv:
         gen_post()
         sys.exit(0)
+    if "--textures-only" in sys.argv:
+        gen_textures()
+        sys.exit(0)
     if "--queries-only" in sys.argv:
         gen_queries()
         sys.exit(0)
@@ -624,3 +670,4 @@ if __name__ == "__main__":
     gen_pointsets()
     gen_queries()
     gen_post()
+    gen_textures()

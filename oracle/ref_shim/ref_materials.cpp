@@ -54,9 +54,65 @@ namespace tr {
 #define MATERIAL_TYPE GLTFMaterial
 #include "rendering/rt/material_textures.glsl"
 }
+// third configuration: USE_MIPMAPPING as librender/render_params.glsl.h:8 defines it for the megakernel, i.e. the texture reads are
+// textureGrad(SCENE_GET_TEXTURE(id), hit.uv, hit.duvdxy[0], hit.duvdxy[1]) (material_textures.glsl:37-63).  The sampler object only
+// carries its index; textureGrad hands (index, uv, dPdx, dPdy) to a caller-supplied texture unit.
+#undef MATERIAL_DECODE_HEADER
+#undef MATERIAL_TEXTURE_DECODE_HEADER
+#undef HIT_POINT_H_GLSL
+#undef GLTF_BSDF_GLSL
+#undef GLTF_COMPONENT_COUNT
+#undef MATERIAL_TYPE
+#undef ENABLE_MATERIAL_DECODE
+#undef EmitterParams
+#undef textured_scalar_standard_param
+#undef textured_color_standard_param
+#undef get_standard_texture_sampler
+#undef get_base_material_alpha
+#undef NO_TEXTURE_GRAD
+#undef SCENE_GET_TEXTURE
+#define USE_MIPMAPPING
+struct SamplerIndex { uint32_t id; };
+typedef void (*texture_unit_fn)(uint32_t id, const float *uv, const float *dpdx, const float *dpdy, float *rgba);
+static texture_unit_fn g_texture_unit = nullptr;
+inline vec4 textureGrad(SamplerIndex s, vec2 uv, vec2 dpdx, vec2 dpdy) {
+    float rgba[4] = {0, 0, 0, 0};
+    const float a[2] = {uv.x, uv.y}, b[2] = {dpdx.x, dpdx.y}, c[2] = {dpdy.x, dpdy.y};
+    g_texture_unit(s.id, a, b, c, rgba);
+    return vec4(rgba[0], rgba[1], rgba[2], rgba[3]);
+}
+inline vec4 textureLod(SamplerIndex, vec2, float) { return vec4(0.0f); } // not reached with USE_MIPMAPPING
+#define SCENE_GET_TEXTURE(index) SamplerIndex{(uint32_t)(index)}
+namespace grad {
+#include "rendering/rt/materials.glsl"
+#include "rendering/bsdfs/gltf_bsdf.glsl"
+#define MATERIAL_TYPE GLTFMaterial
+#include "rendering/rt/material_textures.glsl"
+}
 } // namespace refmat
 
 extern "C" {
+// unpack_material + get_material_alpha in the USE_MIPMAPPING + transmission configuration with image textures: every texture read goes
+// to `unit` with the hit's uv and duvdxy (column-major 2 x 2: d(uv)/dx, d(uv)/dy).  Output layout as ref_unpack_material.
+void ref_unpack_material_grad(const rptr_base_material *p, const float *uv, const float *duvdxy, refmat::texture_unit_fn unit, float *out) {
+    using namespace refmat;
+    g_texture_unit = unit;
+    BaseMaterial bm;
+    std::memcpy(&bm, p, sizeof(bm));
+    std::memset(out, 0, 17 * sizeof(float));
+    grad::GLTFMaterial m;
+    std::memset(&m, 0, sizeof(m));
+    grad::EmitterInteraction e;
+    grad::HitPoint hit{glm::vec3(0.0f), glm::vec2(uv[0], uv[1]), glm::mat2(duvdxy[0], duvdxy[1], duvdxy[2], duvdxy[3]), glm::vec3(0.0f, 0.0f, 1.0f)};
+    out[15] = grad::unpack_material(m, e, 0u, bm, hit);
+    out[16] = grad::get_material_alpha(0u, bm, hit);
+    out[0] = m.base_color.x; out[1] = m.base_color.y; out[2] = m.base_color.z;
+    out[3] = m.metallic; out[4] = m.specular; out[5] = m.roughness; out[6] = m.ior;
+    out[7] = m.specular_transmission; out[8] = m.transmission_roughness;
+    out[9] = m.transmission_color.x; out[10] = m.transmission_color.y; out[11] = m.transmission_color.z;
+    out[12] = e.radiance.x; out[13] = e.radiance.y; out[14] = e.radiance.z;
+}
+
 
 // unpack_material(mat, emitter, material_id, params, hit) + get_material_alpha(...) for one BaseMaterial whose parameters may
 // carry texture handles into `texels` (n_textures x 4 floats, the value textureLod returns).

@@ -511,6 +511,85 @@ static void equalize_emitter_bins(std::vector<Emitter> &emitters, std::vector<fl
 // ================================================================================================================
 // C API (ctypes-callable)
 // ================================================================================================================
+// ---- texture ingestion (util/image.h:10-27: all mip levels of an image back to back; block formats of librender/scene.cpp:836-930) ----
+// S3TC / RGTC blocks after the Khronos Data Format Specification; interpolated palette entries are the specified rationals rounded
+// to the nearest 8-bit code.  Written independently of the product's decoder (csrc/rptr_host.cpp).
+static void palette_bc1(const uint8_t *blk, bool four_colour_always, bool punch_through, uint8_t pal[4][4]) {
+    const unsigned e0 = blk[0] + 256u * blk[1], e1 = blk[2] + 256u * blk[3];
+    const unsigned ends[2] = {e0, e1};
+    for (int k = 0; k < 2; ++k) {
+        const unsigned r5 = ends[k] >> 11, g6 = (ends[k] >> 5) & 0x3fu, b5 = ends[k] & 0x1fu;
+        pal[k][0] = (uint8_t)(r5 * 8 + r5 / 4); pal[k][1] = (uint8_t)(g6 * 4 + g6 / 16); pal[k][2] = (uint8_t)(b5 * 8 + b5 / 4); pal[k][3] = 255;
+    }
+    pal[2][3] = pal[3][3] = 255;
+    for (int c = 0; c < 3; ++c) {
+        const int a = pal[0][c], b = pal[1][c];
+        if (e0 > e1 || four_colour_always) {
+            pal[2][c] = (uint8_t)((2 * a + b + 1) / 3); // round(2a/3 + b/3)
+            pal[3][c] = (uint8_t)((a + 2 * b + 1) / 3);
+        } else {
+            pal[2][c] = (uint8_t)((a + b + 1) / 2);
+            pal[3][c] = 0;
+        }
+    }
+    if (!(e0 > e1 || four_colour_always) && punch_through) pal[3][3] = 0;
+}
+static void palette_bc4(const uint8_t *blk, uint8_t pal[8]) {
+    const int a = blk[0], b = blk[1];
+    pal[0] = (uint8_t)a; pal[1] = (uint8_t)b;
+    if (a > b) {
+        for (int k = 2; k < 8; ++k) pal[k] = (uint8_t)(((8 - k) * a + (k - 1) * b + 3) / 7);
+    } else {
+        for (int k = 2; k < 6; ++k) pal[k] = (uint8_t)(((6 - k) * a + (k - 1) * b + 2) / 5);
+        pal[6] = 0; pal[7] = 255;
+    }
+}
+static unsigned bc4_index(const uint8_t *blk, int texel) { // 3 bits per texel, little endian, starting at byte 2
+    const int bit = 3 * texel;
+    const unsigned lo = blk[2 + bit / 8], hi = bit / 8 + 1 < 6 ? blk[3 + bit / 8] : 0u;
+    return ((lo | (hi << 8)) >> (bit % 8)) & 7u;
+}
+static bool texture_levels_to_rgba8(const rptr_texture_desc &td, std::vector<uint8_t> &out) {
+    const int fmt = td.bc_format;
+    if (fmt != 0 && fmt != 1 && fmt != -1 && fmt != 3 && fmt != 5) return false;
+    const int levels = td.mip_levels > 0 ? td.mip_levels : 1;
+    out.clear();
+    const uint8_t *in = td.texels;
+    int w = td.width, h = td.height;
+    for (int level = 0; level < levels; ++level) {
+        if (fmt == 0) { // kept in its own channel count (the texture set reads `channels` bytes per texel)
+            out.insert(out.end(), in, in + (size_t)w * h * td.channels);
+            in += (size_t)w * h * td.channels;
+        } else {
+            const size_t at = out.size();
+            out.resize(at + (size_t)4 * w * h);
+            const int blocks_x = (w + 3) / 4, blocks_y = (h + 3) / 4, bytes = (fmt == 3 || fmt == 5) ? 16 : 8;
+            for (int y = 0; y < h; ++y)
+                for (int x = 0; x < w; ++x) {
+                    const uint8_t *blk = in + ((size_t)(y / 4) * blocks_x + x / 4) * bytes;
+                    const int texel = 4 * (y % 4) + x % 4;
+                    uint8_t *px = out.data() + at + 4 * ((size_t)y * w + x);
+                    if (fmt == 5) {
+                        uint8_t pr[8], pg[8];
+                        palette_bc4(blk, pr); palette_bc4(blk + 8, pg);
+                        px[0] = pr[bc4_index(blk, texel)]; px[1] = pg[bc4_index(blk + 8, texel)]; px[2] = 0; px[3] = 255;
+                    } else {
+                        const uint8_t *colour = fmt == 3 ? blk + 8 : blk;
+                        uint8_t pal[4][4];
+                        palette_bc1(colour, fmt == 3, fmt == -1, pal);
+                        const unsigned code = (colour[4 + texel / 4] >> (2 * (texel % 4))) & 3u;
+                        px[0] = pal[code][0]; px[1] = pal[code][1]; px[2] = pal[code][2]; px[3] = pal[code][3];
+                        if (fmt == 3) { uint8_t pa[8]; palette_bc4(blk, pa); px[3] = pa[bc4_index(blk, texel)]; }
+                    }
+                }
+            in += (size_t)blocks_x * blocks_y * bytes;
+        }
+        w = w > 1 ? w / 2 : 1;
+        h = h > 1 ? h / 2 : 1;
+    }
+    return true;
+}
+
 extern "C" {
 
 typedef struct oracle_render_args {
@@ -553,8 +632,9 @@ oracle_scene *oracle_scene_create(const rptr_scene_desc *d, const rptr_light_sam
     s.own_texels.resize(d->textures ? d->n_textures : 0);
     for (int t = 0; t < (int)s.own_texels.size(); ++t) {
         rptr_texture_desc td = d->textures[t];
-        if (td.width < 1 || td.height < 1 || td.channels < 1 || td.channels > 4 || !td.texels) { delete os; return nullptr; }
-        s.own_texels[t].assign(td.texels, td.texels + (size_t)td.width * td.height * td.channels);
+        if (td.width < 1 || td.height < 1 || !td.texels || (td.bc_format == 0 && (td.channels < 1 || td.channels > 4))) { delete os; return nullptr; }
+        if (!texture_levels_to_rgba8(td, s.own_texels[t])) { delete os; return nullptr; }
+        if (td.bc_format != 0) { td.bc_format = 0; td.channels = 4; } // decoded: RGBA8 levels back to back
         td.texels = s.own_texels[t].data();
         s.textures.push_back(td);
     }
@@ -983,12 +1063,13 @@ static void store_motion_jitter_aovs(const Frame &f, V3 position, V3 motion_vect
 enum { SHADING_RESULT_TERMINATE = -1, SHADING_RESULT_BOUNCE = 1 };
 template <class Vis>
 static int shade_base_material(const Frame &f, int &bounce, float &prev_bounce_pdf, V3 &illum, V3 &throughput, const rptr_base_material &mp,
-                               float approx_sa, V3 w_o, V3 ip, V3 ign, V3 in_, V3 v_x, V3 v_y, PathRng &rng, V3 &w_i, AovOut *aov, V2 uv, Vis &&visible) {
+                               float approx_sa, V3 w_o, V3 ip, V3 ign, V3 in_, V3 v_x, V3 v_y, PathRng &rng, V3 &w_i, AovOut *aov, V2 uv, V2 duvdx, V2 duvdy,
+                               Vis &&visible) {
     const oracle_render_args &a = *f.a;
     const float p_sun = f.sp.sun_radiance[3];
     GltfMat mat;
     V3 emit;
-    unpack_material(mat, emit, mp, f.tr, f.s->texset, uv);
+    unpack_material(mat, emit, mp, f.tr, f.s->texset, uv, duvdx, duvdy);
     if (aov && bounce == 0) { // pt_megakernel.glsl:670-672 + shade_base_material.glsl:28-31
         const V3 alb = throughput * mat.base_color;
         const float m[8] = {alb.x, alb.y, alb.z, mat.ior != 1.0f ? mat.roughness : 1.0f, in_.x, in_.y, in_.z, length(ip - f.cam_pos)};
@@ -1033,10 +1114,73 @@ static int shade_base_material(const Frame &f, int &bounce, float &prev_bounce_p
     return SHADING_RESULT_BOUNCE;
 }
 
+// ---- rendering/rt/footprint.glsl, with GLSL's matrices spelled out: Mat2 / Mat23 hold columns, (A * B)[c][r] = sum_k A[k][r] * B[c][k];
+// every sum of products is the contract's dot product (fma chain) ----
+struct Mat2 { V2 c[2]; };
+struct Mat23 { V3 c[2]; }; // mat2x3: two columns of three rows
+static inline Mat2 mul_t23_23(const Mat23 &a, const Mat23 &b) { // transpose(a) * b
+    Mat2 m;
+    for (int col = 0; col < 2; ++col) m.c[col] = V2{dot(a.c[0], b.c[col]), dot(a.c[1], b.c[col])};
+    return m;
+}
+static inline Mat2 transpose2(const Mat2 &a) { return Mat2{{V2{a.c[0].x, a.c[1].x}, V2{a.c[0].y, a.c[1].y}}}; }
+static inline Mat2 mul22(const Mat2 &a, const Mat2 &b) {
+    Mat2 m;
+    for (int col = 0; col < 2; ++col) {
+        const V2 row0{a.c[0].x, a.c[1].x}, row1{a.c[0].y, a.c[1].y};
+        m.c[col] = V2{dot(row0, b.c[col]), dot(row1, b.c[col])};
+    }
+    return m;
+}
+static inline Mat2 dpdxy_to_footprint(V3 ray_dir, V3 dpdx, V3 dpdy) { // footprint.glsl:10-15
+    V3 t, b;
+    ortho_basis(t, b, ray_dir);
+    const Mat2 F = mul_t23_23(Mat23{{t, b}}, Mat23{{dpdx, dpdy}});
+    return mul22(F, transpose2(F));
+}
+static inline Mat2 transform_footprint(V3 dst_ray_dir, V3 T0, V3 T1, V3 T2col, V3 src_ray_dir, const Mat2 &F) { // :28-35, T by columns
+    V3 t, b;
+    ortho_basis(t, b, src_ray_dir);
+    const Mat23 T2{{mat_mul(T0, T1, T2col, t), mat_mul(T0, T1, T2col, b)}};
+    ortho_basis(t, b, dst_ray_dir);
+    const Mat2 T3 = mul_t23_23(Mat23{{t, b}}, T2);
+    return mul22(mul22(T3, F), transpose2(T3));
+}
+static inline Mat2 reflect_footprint(V3 dst_ray_dir, V3 src_ray_dir, const Mat2 &F) { // :38-42
+    const V3 n = normalize(dst_ray_dir - src_ray_dir);
+    V3 R[3]; // mat3(1.0f) - 2.0f * outerProduct(n, n), column by column
+    const float nn[3] = {n.x, n.y, n.z};
+    for (int col = 0; col < 3; ++col) {
+        R[col] = v3((col == 0 ? 1.0f : 0.0f) - 2.0f * (n.x * nn[col]), (col == 1 ? 1.0f : 0.0f) - 2.0f * (n.y * nn[col]),
+                    (col == 2 ? 1.0f : 0.0f) - 2.0f * (n.z * nn[col]));
+    }
+    return transform_footprint(dst_ray_dir, R[0], R[1], R[2], src_ray_dir, F);
+}
+static inline void footprint_to_dpdxy(V3 &dpdx, V3 &dpdy, V3 ray_dir, const Mat2 &F) { // :44-61
+    const float B = F.c[0].x + F.c[1].y;
+    const float C = F.c[0].x * F.c[1].y - F.c[0].y * F.c[1].x;
+    const float D = sqrtf(B * B * 0.25f - C);
+    const V2 ev{0.5f * B - D, 0.5f * B + D};
+    Mat2 X{{V2{1.0f, 0.0f}, V2{0.0f, 1.0f}}};
+    if (fabsf(F.c[0].y) > 3.0e-39f) {
+        X.c[0] = V2{F.c[1].x, ev.x - F.c[0].x};
+        X.c[1] = V2{ev.y - F.c[1].y, F.c[0].y};
+    }
+    V3 t, b;
+    ortho_basis(t, b, ray_dir);
+    const V2 x0 = V2{X.c[0].x * (1.0f / sqrtf(dot(X.c[0], X.c[0]))), X.c[0].y * (1.0f / sqrtf(dot(X.c[0], X.c[0])))};
+    const V2 x1 = V2{X.c[1].x * (1.0f / sqrtf(dot(X.c[1], X.c[1]))), X.c[1].y * (1.0f / sqrtf(dot(X.c[1], X.c[1])))};
+    // mat2x3(t, b) * v = t * v.x + b * v.y, as the contract's matrix-vector product: fma(b, v.y, t * v.x)
+    const V3 wx = v3(fmaf(b.x, x0.y, t.x * x0.x), fmaf(b.y, x0.y, t.y * x0.x), fmaf(b.z, x0.y, t.z * x0.x));
+    const V3 wy = v3(fmaf(b.x, x1.y, t.x * x1.x), fmaf(b.y, x1.y, t.y * x1.x), fmaf(b.z, x1.y, t.z * x1.x));
+    dpdx = wx * sqrtf(ev.x);
+    dpdy = wy * sqrtf(ev.y);
+}
+
 // bounce prologue, pt_megakernel.glsl:578-580 and :609-678: approximate solid angle of the hit triangle, shading point,
 // face-forwarding (unless ONESIDED / VOLUME), one-texel normal map, "fix incident direction" blend, tangent frame
 static void bounce_prologue(RTHit &h, const rptr_base_material &mp, const TextureSet &texset, float normal_z_scale, V3 ray_origin, V3 ray_dir,
-                            float &approx_sa, V3 &ip, V3 &ign, V3 &in_, V3 &v_x, V3 &v_y) {
+                            float &approx_sa, V3 &ip, V3 &ign, V3 &in_, V3 &v_x, V3 &v_y, int bounce = 0) {
     approx_sa = length(h.geo_normal); // :578-580
     h.geo_normal = h.geo_normal / approx_sa;
     approx_sa *= fabsf(dot(h.geo_normal, ray_dir)) / (h.dist * h.dist);
@@ -1059,7 +1203,7 @@ static void bounce_prologue(RTHit &h, const rptr_base_material &mp, const Textur
         V3 t_x = cross(t_y, h.normal);
         t_x = t_x * length(h.tangent);
         t_y = t_y * h.bitangent_l;
-        TextureSet::RGBA tx = texset.sample((uint32_t)mp.normal_map, h.uv); // textureLod(.., hit.uv, bounce): base level (single-level images)
+        TextureSet::RGBA tx = texset.sample_lod((uint32_t)mp.normal_map, h.uv, bounce); // textureLod(.., hit.uv, float(shading_state.bounce)), :641-647
         V3 map_nrm = v3(2.0f * tx.r - 1.0f, 2.0f * tx.g - 1.0f, 1.0f * tx.b - 0.0f);
         map_nrm.z = sqrtf(fmaxf(1.0f - map_nrm.x * map_nrm.x - map_nrm.y * map_nrm.y, 0.0f));
         in_ = normalize(mat_mul(t_x, t_y, in_ * normal_z_scale, map_nrm));
@@ -1141,6 +1285,14 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         t_max = query->t_max;
     }
     float total_t = 0.0f;
+    // USE_MIPMAPPING (librender/render_params.glsl.h:8), pt_megakernel.glsl:338-351: the texture footprint of the pixel
+    Mat2 texture_footprint;
+    {
+        V3 dpdx = f.du / (float)a.width, dpdy = f.dv / (float)a.height;
+        dpdx = dpdx * a.params.pixel_radius;
+        dpdy = dpdy * a.params.pixel_radius;
+        texture_footprint = dpdxy_to_footprint(ray_dir, dpdx, dpdy);
+    }
     V3 illum = v3(0.0f), throughput = v3(1.0f);
     int bounce = 0;
     float prev_bounce_pdf = 2.e16f;
@@ -1193,18 +1345,34 @@ static V4 main_spp(const Frame &f, int px, int py, uint32_t sample_index, uint32
         const rptr_base_material &mp = s.materials[h.material_id];
         float approx_sa;
         V3 ip, ign, in_, v_x, v_y;
-        bounce_prologue(h, mp, s.texset, sp.normal_z_scale, ray_origin, ray_dir, approx_sa, ip, ign, in_, v_x, v_y);
+        const V3 tex_geo_normal = h.geo_normal / length(h.geo_normal); // hit.geo_normal as :579 leaves it (same operations as the prologue)
+        bounce_prologue(h, mp, s.texset, sp.normal_z_scale, ray_origin, ray_dir, approx_sa, ip, ign, in_, v_x, v_y, bounce);
         V3 w_o = -ray_dir;
+        V2 duvdx{0.0f, 0.0f}, duvdy{0.0f, 0.0f}; // hit.duvdxy, :583-605
+        {
+            V3 dpdx, dpdy;
+            footprint_to_dpdxy(dpdx, dpdy, ray_dir, texture_footprint);
+            const V3 dir_tangent_un = ray_dir - tex_geo_normal * dot(ray_dir, tex_geo_normal);
+            const float cosTheta2 = fmaxf(1.0f - dot(dir_tangent_un, dir_tangent_un), 0.0f);
+            const V3 dir_tangent_elong = dir_tangent_un / (sqrtf(cosTheta2) + cosTheta2);
+            const V3 dpdx_ = dpdx + dir_tangent_elong * dot(dpdx, dir_tangent_un);
+            const V3 dpdy_ = dpdy + dir_tangent_elong * dot(dpdy, dir_tangent_un);
+            const V3 bitangent = cross(tex_geo_normal, normalize(h.tangent)) * h.bitangent_l;
+            duvdx = V2{dot(h.tangent, dpdx_) * total_t, dot(bitangent, dpdx_) * total_t};
+            duvdy = V2{dot(h.tangent, dpdy_) * total_t, dot(bitangent, dpdy_) * total_t};
+        }
 
         // ---- shade_base_material ----
         V3 w_i;
         {
             const int result = shade_base_material(f, bounce, prev_bounce_pdf, illum, throughput, mp, approx_sa, w_o, ip, ign, in_, v_x, v_y, rng, w_i, aov, h.uv,
+                                                   duvdx, duvdy,
                                                    [&](V3 from, V3 dir, float dist) {
                                                        return test_visibility(f, from, dir, dist, geometry_scale, linear, view_frame_id, cnt);
                                                    });
             if (result != SHADING_RESULT_BOUNCE) break;
         }
+        if (dot(w_i, in_) * dot(w_o, in_) > -0.999f) texture_footprint = reflect_footprint(w_i, ray_dir, texture_footprint); // :698-702
         // next ray: pt_megakernel.glsl:703-709
         ray_dir = w_i;
         ray_origin = ip;
@@ -1615,7 +1783,7 @@ void oracle_shade_base_material(const rptr_base_material *p, int bounce, int out
     const float pdf_before = prev_bounce_pdf;
     const int result = shade_base_material(f, bounce, prev_bounce_pdf, il, thr, *p, approx_sa, v3(wo[0], wo[1], wo[2]), v3(ia[0], ia[1], ia[2]),
                                            v3(ia[3], ia[4], ia[5]), v3(ia[6], ia[7], ia[8]), v3(ia[9], ia[10], ia[11]), v3(ia[12], ia[13], ia[14]), rng,
-                                           w_i, nullptr, V2{0.0f, 0.0f}, [&](V3, V3 dir, float dist) {
+                                           w_i, nullptr, V2{0.0f, 0.0f}, V2{0.0f, 0.0f}, V2{0.0f, 0.0f}, [&](V3, V3 dir, float dist) {
                                                ++queries; qd = dir; qdist = dist;
                                                return true;
                                            });
@@ -1676,6 +1844,63 @@ void oracle_sample_texture(const rptr_texture_desc *t, float u, float v, float *
     const TextureSet::RGBA c = ts.sample(0u, V2{u, v});
     out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = c.a;
 }
+// textureGrad / textureLod on one texture description (block-compressed input is decoded first, like oracle_scene_create does)
+static bool decoded_copy(const rptr_texture_desc *t, rptr_texture_desc &td, std::vector<uint8_t> &store) {
+    td = *t;
+    if (!texture_levels_to_rgba8(td, store)) return false;
+    if (td.bc_format != 0) { td.bc_format = 0; td.channels = 4; }
+    td.texels = store.data();
+    return true;
+}
+void oracle_sample_texture_grad(const rptr_texture_desc *t, float u, float v, const float *ddx, const float *ddy, float *out) {
+    rptr_texture_desc td;
+    std::vector<uint8_t> store;
+    if (!decoded_copy(t, td, store)) return;
+    TextureSet ts;
+    ts.tex = &td;
+    ts.n = 1;
+    const TextureSet::RGBA c = ts.sample_grad(0u, V2{u, v}, V2{ddx[0], ddx[1]}, V2{ddy[0], ddy[1]});
+    out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = c.a;
+}
+void oracle_sample_texture_lod(const rptr_texture_desc *t, float u, float v, int32_t level, float *out) {
+    rptr_texture_desc td;
+    std::vector<uint8_t> store;
+    if (!decoded_copy(t, td, store)) return;
+    TextureSet ts;
+    ts.tex = &td;
+    ts.n = 1;
+    const TextureSet::RGBA c = ts.sample_lod(0u, V2{u, v}, level);
+    out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = c.a;
+}
+float oracle_log2(float x) { return TextureSet::log2_positive(x); }
+// all levels of a texture description as RGBA8 (missing channels: colour 0, alpha 255); returns the number of bytes
+int64_t oracle_decode_texture(const rptr_texture_desc *t, uint8_t *out, int64_t capacity) {
+    std::vector<uint8_t> store;
+    if (!texture_levels_to_rgba8(*t, store)) return -1;
+    if (t->bc_format != 0) {
+        if (out && (int64_t)store.size() <= capacity) std::memcpy(out, store.data(), store.size());
+        return (int64_t)store.size();
+    }
+    const int64_t texels = (int64_t)store.size() / t->channels;
+    if (out && 4 * texels <= capacity)
+        for (int64_t i = 0; i < texels; ++i)
+            for (int k = 0; k < 4; ++k) out[4 * i + k] = k < t->channels ? store[(size_t)i * t->channels + k] : (k == 3 ? 255 : 0);
+    return 4 * texels;
+}
+// rendering/rt/footprint.glsl: same operations and layouts as hostsim_footprint_op
+void oracle_footprint_op(int32_t op, const float *in, float *out) {
+    if (op == 0) {
+        const Mat2 F = dpdxy_to_footprint(v3(in[0], in[1], in[2]), v3(in[3], in[4], in[5]), v3(in[6], in[7], in[8]));
+        out[0] = F.c[0].x; out[1] = F.c[0].y; out[2] = F.c[1].x; out[3] = F.c[1].y;
+    } else if (op == 1) {
+        const Mat2 F = reflect_footprint(v3(in[0], in[1], in[2]), v3(in[3], in[4], in[5]), Mat2{{V2{in[6], in[7]}, V2{in[8], in[9]}}});
+        out[0] = F.c[0].x; out[1] = F.c[0].y; out[2] = F.c[1].x; out[3] = F.c[1].y;
+    } else {
+        V3 dx, dy;
+        footprint_to_dpdxy(dx, dy, v3(in[0], in[1], in[2]), Mat2{{V2{in[3], in[4]}, V2{in[5], in[6]}}});
+        out[0] = dx.x; out[1] = dx.y; out[2] = dx.z; out[3] = dy.x; out[4] = dy.y; out[5] = dy.z;
+    }
+}
 // unpack_material + get_material_alpha with 8-bit 1 x 1 textures; same output layout as ref_unpack_material
 void oracle_unpack_material(const rptr_base_material *p, const rptr_texture_desc *textures, int n_textures, int transmission, float *out) {
     TextureSet ts;
@@ -1692,6 +1917,28 @@ void oracle_unpack_material(const rptr_base_material *p, const rptr_texture_desc
         out[7] = m.specular_transmission; out[8] = m.transmission_roughness;
         out[9] = m.transmission_color.x; out[10] = m.transmission_color.y; out[11] = m.transmission_color.z;
     }
+    out[12] = e.x; out[13] = e.y; out[14] = e.z;
+}
+// unpack_material + get_material_alpha at a hit with image textures: uv, duvdxy = (d(uv)/dx, d(uv)/dy); transmission build; layout as above
+void oracle_unpack_material_at(const rptr_base_material *p, const rptr_texture_desc *textures, int n_textures, const float *uv, const float *duvdxy,
+                               float *out) {
+    std::vector<rptr_texture_desc> dec((size_t)n_textures);
+    std::vector<std::vector<uint8_t>> store((size_t)n_textures);
+    for (int i = 0; i < n_textures; ++i)
+        if (!decoded_copy(textures + i, dec[(size_t)i], store[(size_t)i])) return;
+    TextureSet ts;
+    ts.tex = dec.data();
+    ts.n = n_textures;
+    GltfMat m;
+    V3 e;
+    std::memset(out, 0, 17 * sizeof(float));
+    const V2 at{uv[0], uv[1]}, dx{duvdxy[0], duvdxy[1]}, dy{duvdxy[2], duvdxy[3]};
+    out[15] = unpack_material(m, e, *p, true, ts, at, dx, dy);
+    out[16] = ts.color_param(p->base_color, at, dx, dy).a;
+    out[0] = m.base_color.x; out[1] = m.base_color.y; out[2] = m.base_color.z;
+    out[3] = m.metallic; out[4] = m.specular; out[5] = m.roughness; out[6] = m.ior;
+    out[7] = m.specular_transmission; out[8] = m.transmission_roughness;
+    out[9] = m.transmission_color.x; out[10] = m.transmission_color.y; out[11] = m.transmission_color.z;
     out[12] = e.x; out[13] = e.y; out[14] = e.z;
 }
 // head of main_spp for one pixel sample with the LCG pointset: out = origin(3), dir(3), bits(LCG state afterwards)

@@ -63,11 +63,15 @@ struct GltfMat {
 static inline bool is_textured(float v) { return (f2u(v) & 0x80000000u) != 0; }
 
 // ---- textures: rendering/rt/material_textures.glsl:37-63 -----------------------------------------------------------------
-// The texture unit is hardware in the reference (VkSampler: LINEAR filters, REPEAT addressing, vulkan/render_vulkan.cpp:1655-1671);
-// this is the statement oracle and product share (RPTR-FP): base level, texel centres at (i + 0.5) / size, bilinear weights and
-// blends in binary32 as written, UNORM8 -> v / 255, colour channels of an sRGB image through the sRGB transfer function
-// (evaluated in double and rounded once) per texel before filtering.  A 1 x 1 texture returns its only texel for every uv.
-// Mip selection from ray differentials (textureGrad, 12x anisotropy) is hardware-defined and not restated: images are single-level.
+// The texture unit is hardware in the reference (VkSampler of vulkan/render_vulkan.cpp:1655-1671: LINEAR mag / min / mip filters,
+// REPEAT addressing, LOD range [0, 16], 12x anisotropy); this is the statement oracle and product share (RPTR-FP): texel centres
+// at (i + 0.5) / size, bilinear weights and blends in binary32 as written, UNORM8 -> v / 255, colour channels of an sRGB image
+// through the sRGB transfer function (evaluated in double and rounded once) per texel before filtering.  textureGrad follows the
+// Vulkan specification's formulas for scale factor, level of detail and anisotropic filtering (the part left to implementations):
+// rho_x / rho_y = lengths of the derivatives in base-level texels, eta = min(rho_max / rho_min, 12), N = ceil(eta) taps spread
+// along the major derivative at offsets i / (N + 1) - 1 / 2, lambda = log2(rho_max / eta) clamped to the stored levels, linear
+// blend of the two nearest levels.  The oracle's textures are RGBA8 with all mip levels back to back (block-compressed input is
+// decoded by oracle_scene_create).
 struct TextureSet {
     const rptr_texture_desc *tex = nullptr;
     int n = 0;
@@ -77,40 +81,101 @@ struct TextureSet {
         double c = (double)v / 255.0;
         return (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
     }
-    static RGBA texel_at(const rptr_texture_desc &t, int x, int y) {
+    static int levels_of(const rptr_texture_desc &t) { return t.mip_levels > 0 ? t.mip_levels : 1; }
+    struct Level { const uint8_t *px; int w, h; };
+    static Level level_of(const rptr_texture_desc &t, int level) {
+        Level L{t.texels, t.width, t.height};
+        for (int l = 0; l < level; ++l) {
+            L.px += (size_t)L.w * L.h * t.channels;
+            L.w = L.w > 1 ? L.w / 2 : 1;
+            L.h = L.h > 1 ? L.h / 2 : 1;
+        }
+        return L;
+    }
+    static RGBA texel_at(const rptr_texture_desc &t, const Level &L, int x, int y) {
         const bool srgb = t.color_space == RPTR_COLOR_SPACE_SRGB;
-        const uint8_t *px = t.texels + ((size_t)y * t.width + x) * t.channels;
+        const uint8_t *px = L.px + ((size_t)y * L.w + x) * t.channels;
         float ch[4] = {0.0f, 0.0f, 0.0f, 1.0f};
         for (int k = 0; k < t.channels && k < 4; ++k) ch[k] = k == 3 ? (float)px[3] / 255.0f : decode(px[k], srgb);
         return RGBA{ch[0], ch[1], ch[2], ch[3]};
     }
-    RGBA texel(uint32_t id) const { return texel_at(tex[id], 0, 0); }
+    RGBA texel(uint32_t id) const { return texel_at(tex[id], level_of(tex[id], 0), 0, 0); }
     static int wrap(int i, int n) {
         int r = i % n;
         return r < 0 ? r + n : r;
     }
     static float blend(float a, float b, float t) { return a + (b - a) * t; }
-    RGBA sample(uint32_t id, V2 uv) const {
-        const rptr_texture_desc &t = tex[id];
-        float x = uv.x * (float)t.width - 0.5f, y = uv.y * (float)t.height - 0.5f;
+    static RGBA blend(RGBA a, RGBA b, float t) { return RGBA{blend(a.r, b.r, t), blend(a.g, b.g, t), blend(a.b, b.b, t), blend(a.a, b.a, t)}; }
+    static RGBA bilinear(const rptr_texture_desc &t, int level, V2 uv) {
+        const Level L = level_of(t, level);
+        float x = uv.x * (float)L.w - 0.5f, y = uv.y * (float)L.h - 0.5f;
         if (!(fabsf(x) < 1.0e9f) || !(fabsf(y) < 1.0e9f)) { x = 0.0f; y = 0.0f; }
         const float xf = floorf(x), yf = floorf(y);
         const float wx = x - xf, wy = y - yf;
-        const int x0 = wrap((int)xf, t.width), x1 = wrap(x0 + 1, t.width), y0 = wrap((int)yf, t.height), y1 = wrap(y0 + 1, t.height);
-        const RGBA a = texel_at(t, x0, y0), b = texel_at(t, x1, y0), c = texel_at(t, x0, y1), d = texel_at(t, x1, y1);
-        return RGBA{blend(blend(a.r, b.r, wx), blend(c.r, d.r, wx), wy), blend(blend(a.g, b.g, wx), blend(c.g, d.g, wx), wy),
-                    blend(blend(a.b, b.b, wx), blend(c.b, d.b, wx), wy), blend(blend(a.a, b.a, wx), blend(c.a, d.a, wx), wy)};
+        const int x0 = wrap((int)xf, L.w), x1 = wrap(x0 + 1, L.w), y0 = wrap((int)yf, L.h), y1 = wrap(y0 + 1, L.h);
+        const RGBA a = texel_at(t, L, x0, y0), b = texel_at(t, L, x1, y0), c = texel_at(t, L, x0, y1), d = texel_at(t, L, x1, y1);
+        return blend(blend(a, b, wx), blend(c, d, wx), wy);
+    }
+    RGBA sample(uint32_t id, V2 uv) const { return bilinear(tex[id], 0, uv); }               // base level (alpha candidates: zero footprint)
+    RGBA sample_lod(uint32_t id, V2 uv, int level) const {                                      // textureLod with a whole level (normal maps)
+        const int top = levels_of(tex[id]) - 1;
+        return bilinear(tex[id], level < top ? level : top, uv);
+    }
+    static float log2_positive(float x) { // exponent + Cephes logf kernel, the contract's log2
+        uint32_t bits = f2u(x);
+        if (bits < 0x00800000u) return -127.0f;
+        int e = (int)(bits >> 23) - 127;
+        float m = u2f((bits & 0x007fffffu) | 0x3f800000u);
+        if (m > 1.41421356237f) { m *= 0.5f; e += 1; }
+        const float f = m - 1.0f, z = f * f;
+        const float c[9] = {7.0376836292e-2f, -1.1514610310e-1f, 1.1676998740e-1f, -1.2420140846e-1f, 1.4249322787e-1f,
+                            -1.6668057665e-1f, 2.0000714765e-1f, -2.4999993993e-1f, 3.3333331174e-1f};
+        float p = c[0];
+        for (int k = 1; k < 9; ++k) p = fmaf(f, p, c[k]);
+        const float y = fmaf(-0.5f, z, f * z * p);
+        return fmaf(f + y, 1.44269504088896341f, (float)e);
+    }
+    RGBA sample_grad(uint32_t id, V2 uv, V2 dx, V2 dy) const { // textureGrad(sampler, uv, dPdx, dPdy)
+        const rptr_texture_desc &t = tex[id];
+        if (t.width == 1 && t.height == 1) return bilinear(t, 0, uv); // one texel: every tap of every level is that texel (no averaging error)
+        const V2 mx{dx.x * (float)t.width, dx.y * (float)t.height}, my{dy.x * (float)t.width, dy.y * (float)t.height};
+        const float rho_x = sqrtf(dot(mx, mx)), rho_y = sqrtf(dot(my, my));
+        const float rho_max = fmaxf(rho_x, rho_y), rho_min = fminf(rho_x, rho_y);
+        if (!(rho_max > 0.0f) || !(rho_max < 1.0e18f) || rho_min != rho_min) return bilinear(t, 0, uv);
+        const float eta = rho_min > 0.0f ? fminf(rho_max / rho_min, 12.0f) : 12.0f;
+        const int taps = (int)ceilf(eta);
+        const int top = levels_of(t) - 1;
+        const float lambda = fminf(fmaxf(log2_positive(rho_max / eta), 0.0f), (float)top);
+        const float lo = floorf(lambda), w_hi = lambda - lo;
+        const int level_lo = (int)lo, level_hi = level_lo + 1 <= top ? level_lo + 1 : top;
+        const V2 major = rho_x >= rho_y ? dx : dy;
+        RGBA sum_lo{0, 0, 0, 0}, sum_hi{0, 0, 0, 0};
+        for (int i = 1; i <= taps; ++i) {
+            const float o = (float)i / (float)(taps + 1) - 0.5f;
+            const V2 at{uv.x + major.x * o, uv.y + major.y * o};
+            const RGBA a = bilinear(t, level_lo, at);
+            sum_lo.r += a.r; sum_lo.g += a.g; sum_lo.b += a.b; sum_lo.a += a.a;
+            if (w_hi > 0.0f) {
+                const RGBA b = bilinear(t, level_hi, at);
+                sum_hi.r += b.r; sum_hi.g += b.g; sum_hi.b += b.b; sum_hi.a += b.a;
+            }
+        }
+        const float nt = (float)taps;
+        const RGBA avg_lo{sum_lo.r / nt, sum_lo.g / nt, sum_lo.b / nt, sum_lo.a / nt};
+        if (!(w_hi > 0.0f)) return avg_lo;
+        const RGBA avg_hi{sum_hi.r / nt, sum_hi.g / nt, sum_hi.b / nt, sum_hi.a / nt};
+        return blend(avg_lo, avg_hi, w_hi);
     }
     static bool is_handle(float x) { return (f2u(x) & RPTR_TEXTURED_PARAM_MASK) != 0; }
     // textured_color_param(vec4(p.base_color, 1), hit)
-    RGBA color_param(const float *rgb, V2 uv) const {
-        if (is_handle(rgb[0])) return sample(RPTR_GET_TEXTURE_ID(f2u(rgb[0])), uv);
+    RGBA color_param(const float *rgb, V2 uv, V2 dx = V2{0.0f, 0.0f}, V2 dy = V2{0.0f, 0.0f}) const {
+        if (is_handle(rgb[0])) return sample_grad(RPTR_GET_TEXTURE_ID(f2u(rgb[0])), uv, dx, dy);
         return RGBA{rgb[0], rgb[1], rgb[2], 1.0f};
     }
     // textured_scalar_param(x, hit)
-    float scalar_param(float x, V2 uv) const {
+    float scalar_param(float x, V2 uv, V2 dx = V2{0.0f, 0.0f}, V2 dy = V2{0.0f, 0.0f}) const {
         if (!is_handle(x)) return x;
-        RGBA t = sample(RPTR_GET_TEXTURE_ID(f2u(x)), uv);
+        RGBA t = sample_grad(RPTR_GET_TEXTURE_ID(f2u(x)), uv, dx, dy);
         const float ch[4] = {t.r, t.g, t.b, t.a};
         return ch[RPTR_GET_TEXTURE_CHANNEL(f2u(x))];
     }
@@ -120,15 +185,16 @@ static inline float material_alpha(const TextureSet &ts, const rptr_base_materia
 
 // unpack_material (material_textures.glsl:95-135, non-unrolled standard-texture semantics of rendering/rt/materials.glsl:42-49);
 // returns alpha
-static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_material &p, bool transmission, const TextureSet &ts, V2 uv) {
-    TextureSet::RGBA texel = ts.color_param(p.base_color, uv);
+static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_material &p, bool transmission, const TextureSet &ts, V2 uv,
+                                    V2 dx = V2{0.0f, 0.0f}, V2 dy = V2{0.0f, 0.0f}) { // dx, dy: hit.duvdxy[0], hit.duvdxy[1]
+    TextureSet::RGBA texel = ts.color_param(p.base_color, uv, dx, dy);
     float alpha = texel.a;
     m.base_color = v3(texel.r, texel.g, texel.b);
     if (alpha > 0.001f) m.base_color = m.base_color / alpha; // PREMULTIPLIED_BASE_COLOR_ALPHA
-    m.specular = ts.scalar_param(p.specular, uv);
-    m.roughness = ts.scalar_param(p.roughness, uv);
-    m.metallic = ts.scalar_param(p.metallic, uv);
-    m.ior = ts.scalar_param(p.ior, uv);
+    m.specular = ts.scalar_param(p.specular, uv, dx, dy);
+    m.roughness = ts.scalar_param(p.roughness, uv, dx, dy);
+    m.metallic = ts.scalar_param(p.metallic, uv, dx, dy);
+    m.ior = ts.scalar_param(p.ior, uv, dx, dy);
     emit = v3(p.base_color[0], p.base_color[1], p.base_color[2]) * p.emission_intensity;
     if (p.emission_intensity != 0.0f) {
         if (TextureSet::is_handle(p.base_color[0])) emit = m.base_color * p.emission_intensity;
@@ -139,7 +205,7 @@ static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_materi
     m.transmission_color = v3(0.0f);
     m.transmission_roughness = 0.0f;
     if (transmission) {
-        m.specular_transmission = ts.scalar_param(p.specular_transmission, uv);
+        m.specular_transmission = ts.scalar_param(p.specular_transmission, uv, dx, dy);
         if (m.specular_transmission > 0.0f) {
             if (!(m.ior > 1.0f)) {
                 alpha *= 1.0f - m.specular_transmission;
@@ -147,7 +213,7 @@ static inline float unpack_material(GltfMat &m, V3 &emit, const rptr_base_materi
             } else {
                 m.transmission_color = m.base_color;
                 m.transmission_roughness = m.roughness;
-                m.roughness = sqrtf(ts.scalar_param(p.clearcoat_gloss, uv));
+                m.roughness = sqrtf(ts.scalar_param(p.clearcoat_gloss, uv, dx, dy));
             }
         }
     }

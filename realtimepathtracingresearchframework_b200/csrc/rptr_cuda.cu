@@ -45,6 +45,7 @@ struct Wave {
     uint2 *rngb;    // sampler word that advances with the draws (LCG state), bounce
     uint32_t *rng2; // second sampler word (Sobol index / BN pixelID); allocated for rng_variant != UNIFORM only
     uint32_t *rng3; // LCG of the stochastic alpha test when the pointset is not the LCG (pt_megakernel.glsl:354-358); with rng2
+    float4 *foot;   // texture_footprint (a GLSL mat2: m00, m01, m10, m11); allocated for scenes with image textures only
     float4 *sh_o;   // shadow queue: origin.xyz, tmin
     float4 *sh_d;   //               dir.xyz, tmax
     float4 *sh_c;   //               contribution.rgb, bits(path slot)
@@ -130,6 +131,10 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams fp, TileMap tm, Wave
         w.illum[slot] = f4(0.0f, 0.0f, 0.0f, 0.0f);
 #endif
         w.rngb[slot] = make_uint2(ps.rng, 0u);
+        if (w.foot) {
+            if (queries) init_footprint(fp, ps); // the footprint block runs on the ray actually traced (pt_megakernel.glsl:326-351)
+            w.foot[slot] = f4(ps.foot.m00, ps.foot.m01, ps.foot.m10, ps.foot.m11);
+        }
         if (fp.rng_variant != 0) {
             w.rng2[slot] = ps.rng_b;
             if (w.rng3) w.rng3[slot] = alpha_lcg_seed(fp, px, py, sample_base + (uint32_t)(first_layer + layer));
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                     ps.rng = rb.x; ps.bounce = (int)rb.y;
                     ps.rng_b = ((FEAT & RPTR_FEAT_QMC) && fp.rng_variant != 0) ? w.rng2[slot] : 0u;
                     ps.rng_dim = 0;
+                    if (FEAT & RPTR_FEAT_TEXTURES) { const float4 ft = w.foot[slot]; ps.foot = Footprint{ft.x, ft.y, ft.z, ft.w}; }
                     verts++;
                     // first vertex of a path of the frame's last sample layer: its attributes go to the AOV images
                     const bool want_aov = aov.albedo_roughness && ps.bounce == 0 && slot - aov.slot_lo < (uint32_t)tm.local_pixels;
@@ -269,6 +275,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                         w.ray_o[slot] = f4(ps.o.x, ps.o.y, ps.o.z, ps.tmin);
                         w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
                         w.thr[slot] = f4(ps.thr.x, ps.thr.y, ps.thr.z, ps.prev_pdf);
+                        if (FEAT & RPTR_FEAT_TEXTURES) w.foot[slot] = f4(ps.foot.m00, ps.foot.m01, ps.foot.m10, ps.foot.m11);
                     }
                 }
             }
@@ -692,7 +699,8 @@ static int grid_for(const rptr_ctx *ctx, int blocks_per_sm) { return ctx->num_sm
 
 static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     const bool need_rng2 = ctx->rng_variant != 0;
-    if (paths <= ctx->wave_capacity && depth <= ctx->wave_depth && (!need_rng2 || ctx->wave.rng2)) return 0;
+    const bool need_foot = ctx->any_textured; // texture footprints: scenes with image textures only
+    if (paths <= ctx->wave_capacity && depth <= ctx->wave_depth && (!need_rng2 || ctx->wave.rng2) && (!need_foot || ctx->wave.foot)) return 0;
     if (paths < ctx->wave_capacity) paths = ctx->wave_capacity;
     if (depth < ctx->wave_depth) depth = ctx->wave_depth;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -711,6 +719,8 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
         CU(dev_alloc(ctx, &w.rng2, n, ctx->wave_allocs));
         CU(dev_alloc(ctx, &w.rng3, n, ctx->wave_allocs));
     }
+    w.foot = nullptr;
+    if (need_foot) CU(dev_alloc(ctx, &w.foot, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.sh_o, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.sh_d, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.sh_c, n, ctx->wave_allocs));
@@ -981,7 +991,7 @@ static int upload_scene(rptr_ctx *ctx, HostScene &hs, SceneUpload &up) {
     std::vector<TexDev> tex(hs.textures.size());
     for (size_t t = 0; t < hs.textures.size(); ++t) {
         const HostTexture &ht = hs.textures[t];
-        tex[t] = TexDev{nullptr, ht.width, ht.height, ht.srgb, 0};
+        tex[t] = TexDev{nullptr, ht.width, ht.height, ht.srgb, ht.levels};
         if (ht.rgba.empty()) continue;
         uchar4 *d_px;
         CU(dev_alloc(ctx, &d_px, ht.rgba.size() / 4, up.allocs));
@@ -1221,6 +1231,7 @@ static FrameParams make_frame_params(const rptr_ctx *ctx) {
     fp.output_channel = ctx->params.output_channel;
     fp.glossy_only_mode = ctx->params.glossy_only_mode;
     fp.enable_raster_taa = ctx->params.enable_raster_taa;
+    fp.pixel_radius = ctx->params.pixel_radius;
     if (fp.enable_raster_taa > 0) screen_jitter(ctx->view_frame_offset, ctx->view_frame_id, ctx->width, ctx->height, fp.screen_jitter);
     memcpy(fp.vp, ctx->vp, sizeof(fp.vp));
     memcpy(fp.vp_reference, ctx->vp_reference, sizeof(fp.vp_reference));
@@ -1319,6 +1330,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
             sb.w = w0;
             sb.w.ray_o += off; sb.w.ray_d += off; sb.w.hit += off; sb.w.thr += off; sb.w.illum += off; sb.w.rngb += off;
             if (w0.rng2) { sb.w.rng2 += off; sb.w.rng3 += off; }
+            if (w0.foot) sb.w.foot += off;
             sb.w.sh_o += off; sb.w.sh_d += off; sb.w.sh_c += off;
             sb.w.queue[0] += off; sb.w.queue[1] += off; sb.w.hitq += off;
             sb.w.counts += (size_t)k * 4 * (depth + 2);

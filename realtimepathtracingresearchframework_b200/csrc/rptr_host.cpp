@@ -280,20 +280,26 @@ const rptr_texture_desc &texture_of(const rptr_scene_desc &d, uint32_t handle_or
     if (!d.textures || id >= (uint32_t)d.n_textures) throw std::runtime_error("material refers to texture " + std::to_string(id) + " which the scene does not have");
     const rptr_texture_desc &t = d.textures[id];
     if (t.width < 1 || t.height < 1 || t.width > 32768 || t.height > 32768) throw std::runtime_error("texture " + std::to_string(id) + " has an invalid size");
-    if (t.channels < 1 || t.channels > 4 || !t.texels) throw std::runtime_error("texture " + std::to_string(id) + " has no texels / bad channel count");
+    if (!t.texels) throw std::runtime_error("texture " + std::to_string(id) + " has no texels");
+    if (t.bc_format == 0 && (t.channels < 1 || t.channels > 4)) throw std::runtime_error("texture " + std::to_string(id) + " has a bad channel count");
+    if (t.bc_format != 0 && t.bc_format != 1 && t.bc_format != -1 && t.bc_format != 3 && t.bc_format != 5)
+        throw std::runtime_error("texture " + std::to_string(id) + ": block compression format " + std::to_string(t.bc_format) + " is not supported (BC1, BC3, BC5 UNORM are)");
+    if (t.mip_levels < 0 || t.mip_levels > 16) throw std::runtime_error("texture " + std::to_string(id) + " has an invalid number of mip levels");
     return t;
 }
 bool is_one_texel(const rptr_texture_desc &t) { return t.width == 1 && t.height == 1; }
 Texel fetch_texel(const rptr_scene_desc &d, uint32_t handle) { // the only texel of a 1 x 1 texture
     const rptr_texture_desc &t = texture_of(d, handle);
+    HostTexture ht;
+    decode_texture(t, ht);
     Texel x;
-    for (int k = 0; k < 3; ++k) {
-        const int v = k < t.channels ? t.texels[k] : 0;
-        x.c[k] = t.color_space == RPTR_COLOR_SPACE_SRGB ? srgb8_to_linear(v) : (float)v / 255.0f;
-    }
-    x.a8 = t.channels == 4 ? t.texels[3] : 255;
+    for (int k = 0; k < 3; ++k) x.c[k] = t.color_space == RPTR_COLOR_SPACE_SRGB ? srgb8_to_linear(ht.rgba[k]) : (float)ht.rgba[k] / 255.0f;
+    x.a8 = ht.rgba[3];
     x.c[3] = alpha8_to_float(x.a8);
     return x;
+}
+bool has_alpha_channel(const rptr_texture_desc &t) { // can a texel of this image have alpha != 1?
+    return t.bc_format == 0 ? t.channels == 4 : (t.bc_format == -1 || t.bc_format == 3);
 }
 bool is_handle(float v) { return (f2u(v) & RPTR_TEXTURED_PARAM_MASK) != 0; }
 // textured_scalar_param (material_textures.glsl:50-63): folded when the texture has one texel, left as a handle otherwise
@@ -303,6 +309,90 @@ float resolve_scalar(const rptr_scene_desc &d, float v, bool &kept_handle) {
     return fetch_texel(d, f2u(v)).c[RPTR_GET_TEXTURE_CHANNEL(f2u(v))];
 }
 } // namespace
+
+// ---- texture ingestion: every mip level to RGBA8 ----------------------------------------------------------------------------
+// Block formats as the Khronos Data Format Specification defines them (S3TC / RGTC sections); interpolated values are the exact
+// rationals of the specification rounded to the nearest 8-bit code, which is where hardware decoders are allowed to differ.
+namespace {
+void expand565(uint32_t c, int *rgb) {
+    const int r = (c >> 11) & 31, g = (c >> 5) & 63, b = c & 31;
+    rgb[0] = (r << 3) | (r >> 2); rgb[1] = (g << 2) | (g >> 4); rgb[2] = (b << 3) | (b >> 2);
+}
+// one BC1 colour block (8 bytes) into a 4 x 4 RGBA tile; mode: 0 = BC1 RGB (no transparency), 1 = BC1 RGBA (index 3 of the three-colour
+// mode is transparent black), 2 = the colour half of BC3 (always four colours, alpha untouched)
+void decode_bc1_block(const uint8_t *b, int mode, uint8_t tile[16][4]) {
+    const uint32_t c0 = b[0] | (b[1] << 8), c1 = b[2] | (b[3] << 8);
+    int pal[4][4];
+    expand565(c0, pal[0]); expand565(c1, pal[1]);
+    pal[0][3] = pal[1][3] = pal[2][3] = pal[3][3] = 255;
+    if (c0 > c1 || mode == 2) {
+        for (int k = 0; k < 3; ++k) { pal[2][k] = (2 * pal[0][k] + pal[1][k] + 1) / 3; pal[3][k] = (pal[0][k] + 2 * pal[1][k] + 1) / 3; }
+    } else {
+        for (int k = 0; k < 3; ++k) { pal[2][k] = (pal[0][k] + pal[1][k] + 1) / 2; pal[3][k] = 0; }
+        if (mode == 1) pal[3][3] = 0;
+    }
+    const uint32_t idx = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+    for (int i = 0; i < 16; ++i) {
+        const int *p = pal[(idx >> (2 * i)) & 3];
+        for (int k = 0; k < 3; ++k) tile[i][k] = (uint8_t)p[k];
+        if (mode != 2) tile[i][3] = (uint8_t)p[3];
+    }
+}
+// one BC4 UNORM block (8 bytes: two endpoints, 16 three-bit indices) into channel `ch` of the tile
+void decode_bc4_block(const uint8_t *b, int ch, uint8_t tile[16][4]) {
+    int pal[8];
+    pal[0] = b[0]; pal[1] = b[1];
+    if (pal[0] > pal[1]) for (int i = 1; i <= 6; ++i) pal[1 + i] = ((7 - i) * pal[0] + i * pal[1] + 3) / 7;
+    else {
+        for (int i = 1; i <= 4; ++i) pal[1 + i] = ((5 - i) * pal[0] + i * pal[1] + 2) / 5;
+        pal[6] = 0; pal[7] = 255;
+    }
+    uint64_t idx = 0;
+    for (int k = 0; k < 6; ++k) idx |= (uint64_t)b[2 + k] << (8 * k);
+    for (int i = 0; i < 16; ++i) tile[i][ch] = (uint8_t)pal[(idx >> (3 * i)) & 7];
+}
+} // namespace
+
+void decode_texture(const rptr_texture_desc &td, HostTexture &out) {
+    if (td.bc_format != 0 && td.bc_format != 1 && td.bc_format != -1 && td.bc_format != 3 && td.bc_format != 5)
+        throw std::runtime_error("block compression format " + std::to_string(td.bc_format) + " is not supported (BC1, BC3, BC5 UNORM are)");
+    out.width = td.width; out.height = td.height; out.srgb = td.color_space == RPTR_COLOR_SPACE_SRGB;
+    out.levels = td.mip_levels > 0 ? td.mip_levels : 1;
+    out.rgba.clear();
+    const uint8_t *src = td.texels;
+    int w = td.width, h = td.height;
+    for (int l = 0; l < out.levels; ++l) {
+        const size_t base = out.rgba.size();
+        out.rgba.resize(base + 4 * (size_t)w * h);
+        uint8_t *dst = out.rgba.data() + base;
+        if (td.bc_format == 0) {
+            for (size_t i = 0; i < (size_t)w * h; ++i)
+                for (int k = 0; k < 4; ++k) dst[4 * i + k] = k < td.channels ? src[i * td.channels + k] : (k == 3 ? 255 : 0);
+            src += (size_t)w * h * td.channels;
+        } else { // levels are padded to whole 4 x 4 blocks (vulkan/resource_utils.cpp:85-99)
+            const int bw = (w + 3) / 4, bh = (h + 3) / 4;
+            const int block_bytes = (td.bc_format == 1 || td.bc_format == -1) ? 8 : 16;
+            for (int by = 0; by < bh; ++by)
+                for (int bx = 0; bx < bw; ++bx) {
+                    const uint8_t *b = src + ((size_t)by * bw + bx) * block_bytes;
+                    uint8_t tile[16][4];
+                    for (int i = 0; i < 16; ++i) { tile[i][0] = tile[i][1] = tile[i][2] = 0; tile[i][3] = 255; }
+                    if (td.bc_format == 1) decode_bc1_block(b, 0, tile);
+                    else if (td.bc_format == -1) decode_bc1_block(b, 1, tile);
+                    else if (td.bc_format == 3) { decode_bc4_block(b, 3, tile); decode_bc1_block(b + 8, 2, tile); }
+                    else { decode_bc4_block(b, 0, tile); decode_bc4_block(b + 8, 1, tile); } // BC5 UNORM: red, green; blue 0, alpha 1
+                    for (int ty = 0; ty < 4; ++ty)
+                        for (int tx = 0; tx < 4; ++tx) {
+                            const int x = 4 * bx + tx, y = 4 * by + ty;
+                            if (x < w && y < h) memcpy(dst + 4 * ((size_t)y * w + x), tile[4 * ty + tx], 4);
+                        }
+                }
+            src += (size_t)bw * bh * block_bytes;
+        }
+        if (w > 1) w /= 2;
+        if (h > 1) h /= 2;
+    }
+}
 
 // unpack_material's texture reads (material_textures.glsl:95-135, non-unrolled standard-texture semantics of
 // rendering/rt/materials.glsl:42-49): parameters that refer to 1 x 1 textures are folded into the BaseMaterial (a 1 x 1 texture
@@ -320,10 +410,7 @@ static void resolve_materials(const rptr_scene_desc &d, HostScene &s) {
         HostTexture &ht = s.textures[t];
         ht.width = td.width; ht.height = td.height; ht.srgb = td.color_space == RPTR_COLOR_SPACE_SRGB;
         if (is_one_texel(td)) continue;
-        const size_t n = (size_t)td.width * td.height;
-        ht.rgba.resize(4 * n);
-        for (size_t i = 0; i < n; ++i)
-            for (int k = 0; k < 4; ++k) ht.rgba[4 * i + k] = k < td.channels ? td.texels[i * td.channels + k] : (k == 3 ? 255 : 0);
+        decode_texture(td, ht);
     }
     for (int i = 0; i < d.n_materials; ++i) {
         rptr_base_material &m = s.materials[i];
@@ -348,7 +435,7 @@ static void resolve_materials(const rptr_scene_desc &d, HostScene &s) {
             } else {
                 kept = true;
                 // three- or fewer-channel images have alpha 1 everywhere: nothing to test during traversal
-                if (texture_of(d, f2u(m.base_color[0])).channels == 4) s.material_alpha_textured[i] = 1;
+                if (has_alpha_channel(texture_of(d, f2u(m.base_color[0])))) s.material_alpha_textured[i] = 1;
             }
         }
         m.specular = resolve_scalar(d, m.specular, kept);

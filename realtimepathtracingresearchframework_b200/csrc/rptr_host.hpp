@@ -19,8 +19,11 @@ struct HostGeomInst {
 
 struct HostTexture { // one entry per texture of the scene; rgba is empty for 1 x 1 textures (folded into the materials)
     int32_t width = 0, height = 0, srgb = 0;
-    std::vector<uint8_t> rgba; // four channels per texel: missing colour channels 0, missing alpha 255
+    int32_t levels = 1;        // mip levels in rgba, base level first, level l = max(width >> l, 1) x max(height >> l, 1)
+    std::vector<uint8_t> rgba; // four channels per texel: missing colour channels 0, missing alpha 255; block-compressed input decoded
 };
+// decodes every level of a texture description (RGBA8 expansion, BC1 / BC3 / BC5 blocks) -- also used by the tests
+void decode_texture(const rptr_texture_desc &td, HostTexture &out);
 
 struct HostScene {
     // owned copies of the input streams (the caller's Scene is only borrowed for set_scene, app.cpp:151-175)

@@ -56,7 +56,7 @@ struct TexDev {
     const uchar4 *texels;
     int32_t width, height;
     int32_t srgb; // colour channels go through the sRGB transfer function (SceneDev::srgb_lut), alpha never does
-    int32_t _pad;
+    int32_t levels; // mip levels stored back to back behind the base level: level l is max(width >> l, 1) x max(height >> l, 1)
 };
 
 struct SceneDev {
@@ -68,12 +68,18 @@ struct SceneDev {
     const float *srgb_lut;       // 256 entries: sRGB8 code value -> linear (evaluated in double on the host, rounded once)
 };
 
-// ---- the texture unit (RPTR-FP statement; the reference leaves it to the hardware: VkSampler of vulkan/render_vulkan.cpp:1655-1671) ----
-// REPEAT addressing, LINEAR filter, base level: texel centres at (i + 0.5) / size, UNORM8 -> v / 255, sRGB colour channels
-// decoded per texel BEFORE filtering (as a VK_FORMAT_*_SRGB image does), weights and blends in binary32 in the order written.
-// Level of detail: the base level.  The reference selects a mip level / anisotropic footprint from ray differentials
-// (textureGrad with hit.duvdxy, rendering/rt/material_textures.glsl:37-63); that stage is hardware-defined (12x anisotropy)
-// and is not restated -- images are taken as single-level, for which every LOD resolves to what is computed here.
+// ---- the texture unit (RPTR-FP statement; the reference leaves it to the hardware: VkSampler of vulkan/render_vulkan.cpp:1655-1671:
+// LINEAR mag / min / mip filters, REPEAT addressing, minLod 0, maxLod 16, 12x anisotropy) ----
+// Texel centres at (i + 0.5) / size, UNORM8 -> v / 255, sRGB colour channels decoded per texel BEFORE filtering (as a
+// VK_FORMAT_*_SRGB image does), weights and blends in binary32 in the order written.  textureGrad (the megakernel's reads with
+// USE_MIPMAPPING, rendering/rt/material_textures.glsl:37-63) follows the formulas the Vulkan specification gives for the scale
+// factor, the level of detail and anisotropic filtering -- the part implementations are free to approximate, fixed here:
+//   m_x = (du/dx * w, dv/dx * h), m_y likewise; rho_x = |m_x|, rho_y = |m_y|; rho_max, rho_min their max / min
+//   eta = min(rho_max / rho_min, 12)  (12 when rho_min = 0);  N = ceil(eta);  lambda = log2(rho_max / eta), clamped to [0, levels - 1]
+//   tau(level) = 1 / N * sum_{i = 1..N} bilinear(level, uv + d_major * (i / (N + 1) - 1 / 2)),  d_major = the derivative with the larger rho
+//   result = tau(floor(lambda)) * (1 - frac) + tau(floor(lambda) + 1) * frac
+// A zero or non-finite footprint (alpha candidates pass mat2(0), vulkan/pt_megakernel.glsl:204) reads the base level with one tap.
+// A 1 x 1 image returns its texel whatever the footprint (the host folds such textures into the materials, rptr_host.cpp).
 RPTR_HD float4 decode_texel(const SceneDev &sc, const TexDev &t, uchar4 c) {
     if (t.srgb) return f4(sc.srgb_lut[c.x], sc.srgb_lut[c.y], sc.srgb_lut[c.z], (float)c.w / 255.0f);
     return f4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
@@ -83,24 +89,87 @@ RPTR_HD int32_t wrap_repeat(int32_t i, int32_t n) {
     return i < 0 ? i + n : i;
 }
 RPTR_HD float lerp_tex(float a, float b, float t) { return a + (b - a) * t; }
-RPTR_HD float4 sample_texture(const SceneDev &sc, uint32_t id, float2 uv) {
-    const TexDev &t = sc.textures[id];
-    float x = uv.x * (float)t.width - 0.5f, y = uv.y * (float)t.height - 0.5f;
+RPTR_HD float4 lerp_tex4(float4 a, float4 b, float t) { return f4(lerp_tex(a.x, b.x, t), lerp_tex(a.y, b.y, t), lerp_tex(a.z, b.z, t), lerp_tex(a.w, b.w, t)); }
+RPTR_HD float4 sample_texture_level(const SceneDev &sc, const TexDev &t, int level, float2 uv) {
+    int32_t w = t.width, h = t.height;
+    size_t off = 0;
+    for (int l = 0; l < level; ++l) {
+        off += (size_t)w * (size_t)h;
+        if (w > 1) w /= 2;
+        if (h > 1) h /= 2;
+    }
+    const uchar4 *px = t.texels + off;
+    float x = uv.x * (float)w - 0.5f, y = uv.y * (float)h - 0.5f;
     if (!(fabsf(x) < 1.0e9f) || !(fabsf(y) < 1.0e9f)) { x = 0.0f; y = 0.0f; } // NaN / out of the integer range: texel (0, 0)
     const float x0 = floorf(x), y0 = floorf(y);
     const float fx = x - x0, fy = y - y0;
-    const int32_t i0 = wrap_repeat((int32_t)x0, t.width), i1 = wrap_repeat(i0 + 1, t.width);
-    const int32_t j0 = wrap_repeat((int32_t)y0, t.height), j1 = wrap_repeat(j0 + 1, t.height);
-    const float4 c00 = decode_texel(sc, t, t.texels[(size_t)j0 * t.width + i0]), c10 = decode_texel(sc, t, t.texels[(size_t)j0 * t.width + i1]);
-    const float4 c01 = decode_texel(sc, t, t.texels[(size_t)j1 * t.width + i0]), c11 = decode_texel(sc, t, t.texels[(size_t)j1 * t.width + i1]);
-    return f4(lerp_tex(lerp_tex(c00.x, c10.x, fx), lerp_tex(c01.x, c11.x, fx), fy), lerp_tex(lerp_tex(c00.y, c10.y, fx), lerp_tex(c01.y, c11.y, fx), fy),
-              lerp_tex(lerp_tex(c00.z, c10.z, fx), lerp_tex(c01.z, c11.z, fx), fy), lerp_tex(lerp_tex(c00.w, c10.w, fx), lerp_tex(c01.w, c11.w, fx), fy));
+    const int32_t i0 = wrap_repeat((int32_t)x0, w), i1 = wrap_repeat(i0 + 1, w);
+    const int32_t j0 = wrap_repeat((int32_t)y0, h), j1 = wrap_repeat(j0 + 1, h);
+    const float4 c00 = decode_texel(sc, t, px[(size_t)j0 * w + i0]), c10 = decode_texel(sc, t, px[(size_t)j0 * w + i1]);
+    const float4 c01 = decode_texel(sc, t, px[(size_t)j1 * w + i0]), c11 = decode_texel(sc, t, px[(size_t)j1 * w + i1]);
+    return lerp_tex4(lerp_tex4(c00, c10, fx), lerp_tex4(c01, c11, fx), fy);
+}
+RPTR_HD float4 sample_texture(const SceneDev &sc, uint32_t id, float2 uv) { return sample_texture_level(sc, sc.textures[id], 0, uv); }
+// textureLod with a whole-numbered level (the normal map read of pt_megakernel.glsl:641-647: level = bounce)
+RPTR_HD float4 sample_texture_lod(const SceneDev &sc, uint32_t id, float2 uv, int level) {
+    const TexDev &t = sc.textures[id];
+    return sample_texture_level(sc, t, level < t.levels - 1 ? level : t.levels - 1, uv);
+}
+// log2 of a positive normal float: exponent + Cephes logf kernel on the mantissa in [sqrt(1/2), sqrt(2)), in +, -, x, fma only
+RPTR_HD float log2_pos(float x) {
+    const uint32_t u = f2u(x);
+    if (u < 0x00800000u) return -127.0f; // zero / subnormal: below every level
+    int e = (int)(u >> 23) - 127;
+    float m = u2f((u & 0x007fffffu) | 0x3f800000u);
+    if (m > 1.41421356237f) { m *= 0.5f; e += 1; }
+    const float f = m - 1.0f, z = f * f;
+    float p = fmaf(f, 7.0376836292e-2f, -1.1514610310e-1f);
+    p = fmaf(f, p, 1.1676998740e-1f);
+    p = fmaf(f, p, -1.2420140846e-1f);
+    p = fmaf(f, p, 1.4249322787e-1f);
+    p = fmaf(f, p, -1.6668057665e-1f);
+    p = fmaf(f, p, 2.0000714765e-1f);
+    p = fmaf(f, p, -2.4999993993e-1f);
+    p = fmaf(f, p, 3.3333331174e-1f);
+    const float y = fmaf(-0.5f, z, f * z * p);
+    return fmaf(f + y, 1.44269504088896341f, (float)e);
+}
+RPTR_HD float4 sample_texture_grad(const SceneDev &sc, uint32_t id, float2 uv, float2 ddx, float2 ddy) {
+    const TexDev &t = sc.textures[id];
+    if (t.width == 1 && t.height == 1) return sample_texture_level(sc, t, 0, uv);
+    const float mxx = ddx.x * (float)t.width, mxy = ddx.y * (float)t.height, myx = ddy.x * (float)t.width, myy = ddy.y * (float)t.height;
+    const float rx = sqrtf(fmaf(mxy, mxy, mxx * mxx)), ry = sqrtf(fmaf(myy, myy, myx * myx));
+    const float rmax = fmaxf(rx, ry), rmin = fminf(rx, ry);
+    if (!(rmax > 0.0f) || !(rmax < 1.0e18f) || !(rmin == rmin)) return sample_texture_level(sc, t, 0, uv);
+    const float eta = rmin > 0.0f ? fminf(rmax / rmin, 12.0f) : 12.0f;
+    const int n = (int)ceilf(eta);
+    float lambda = log2_pos(rmax / eta);
+    lambda = fminf(fmaxf(lambda, 0.0f), (float)(t.levels - 1));
+    const float l0f = floorf(lambda), frac = lambda - l0f;
+    const int l0 = (int)l0f, l1 = l0 + 1 < t.levels ? l0 + 1 : t.levels - 1;
+    const float2 major = rx >= ry ? ddx : ddy;
+    float4 a0 = f4(0.0f, 0.0f, 0.0f, 0.0f), a1 = f4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int i = 1; i <= n; ++i) {
+        const float s_ = (float)i / (float)(n + 1) - 0.5f;
+        const float2 p = f2(uv.x + major.x * s_, uv.y + major.y * s_);
+        const float4 c0 = sample_texture_level(sc, t, l0, p);
+        a0.x += c0.x; a0.y += c0.y; a0.z += c0.z; a0.w += c0.w;
+        if (frac > 0.0f) {
+            const float4 c1 = sample_texture_level(sc, t, l1, p);
+            a1.x += c1.x; a1.y += c1.y; a1.z += c1.z; a1.w += c1.w;
+        }
+    }
+    const float fn = (float)n;
+    a0 = f4(a0.x / fn, a0.y / fn, a0.z / fn, a0.w / fn);
+    if (!(frac > 0.0f)) return a0;
+    a1 = f4(a1.x / fn, a1.y / fn, a1.z / fn, a1.w / fn);
+    return lerp_tex4(a0, a1, frac);
 }
 RPTR_HD bool is_texture_handle(float v) { return (f2u(v) & RPTR_TEXTURED_PARAM_MASK) != 0; }
 // textured_scalar_param (rendering/rt/material_textures.glsl:50-63): handles that survived resolve_materials refer to textures larger than 1 x 1
-RPTR_HD float textured_scalar(const SceneDev &sc, float v, float2 uv) {
+RPTR_HD float textured_scalar(const SceneDev &sc, float v, float2 uv, float2 ddx, float2 ddy) {
     if (!is_texture_handle(v)) return v;
-    const float4 t = sample_texture(sc, RPTR_GET_TEXTURE_ID(f2u(v)), uv);
+    const float4 t = sample_texture_grad(sc, RPTR_GET_TEXTURE_ID(f2u(v)), uv, ddx, ddy);
     const uint32_t ch = RPTR_GET_TEXTURE_CHANNEL(f2u(v));
     return ch == 0 ? t.x : ch == 1 ? t.y : ch == 2 ? t.z : t.w;
 }
@@ -115,6 +184,7 @@ struct FrameParams {
     int32_t n_lights, n_bins, bin_size;
     int32_t transmission;
     float screen_jitter[2]; // view_params.screen_jitter (raster TAA; zero unless enable_raster_taa)
+    float pixel_radius;     // render_params.pixel_radius: scale of the texture footprint of a pixel (pt_megakernel.glsl:347-348)
     float vp[16];           // view_params.VP, column-major (render_vulkan.cpp:2926-2930)
     float vp_reference[16]; // view_params.VP_reference: the VP of the previous begin_frame (:1986-1998, :2911)
     int32_t rng_variant;  // RenderBackendOptions::rng_variant (librender/render_params.glsl.h:34-37)
@@ -212,26 +282,27 @@ struct GltfMat {
 // semantics of rendering/rt/materials.glsl:42-49).  Parameters that refer to 1 x 1 textures were folded into constants on the
 // host; TEX = false compiles the lookups of larger textures out (scenes without any).
 template <bool TEX>
-RPTR_HD float unpack_material(GltfMat &m, float3 &emit, const rptr_base_material &p, bool transmission, const SceneDev &sc, float2 uv) {
+RPTR_HD float unpack_material(GltfMat &m, float3 &emit, const rptr_base_material &p, bool transmission, const SceneDev &sc, float2 uv,
+                             float2 ddx = f2(0.0f, 0.0f), float2 ddy = f2(0.0f, 0.0f)) { // ddx / ddy: hit.duvdxy[0], [1] (textureGrad)
     float alpha = 1.0f;
     m.base_color = f3(p.base_color[0], p.base_color[1], p.base_color[2]);
     if (TEX && is_texture_handle(p.base_color[0])) { // textured_color_param(vec4(base_color, 1), hit)
-        const float4 t = sample_texture(sc, RPTR_GET_TEXTURE_ID(f2u(p.base_color[0])), uv);
+        const float4 t = sample_texture_grad(sc, RPTR_GET_TEXTURE_ID(f2u(p.base_color[0])), uv, ddx, ddy);
         m.base_color = f3(t.x, t.y, t.z);
         alpha = t.w;
     }
     if (alpha > 0.001f) m.base_color = m.base_color / alpha; // PREMULTIPLIED_BASE_COLOR_ALPHA
-    m.specular = TEX ? textured_scalar(sc, p.specular, uv) : p.specular;
-    m.roughness = TEX ? textured_scalar(sc, p.roughness, uv) : p.roughness;
-    m.metallic = TEX ? textured_scalar(sc, p.metallic, uv) : p.metallic;
-    m.ior = TEX ? textured_scalar(sc, p.ior, uv) : p.ior;
+    m.specular = TEX ? textured_scalar(sc, p.specular, uv, ddx, ddy) : p.specular;
+    m.roughness = TEX ? textured_scalar(sc, p.roughness, uv, ddx, ddy) : p.roughness;
+    m.metallic = TEX ? textured_scalar(sc, p.metallic, uv, ddx, ddy) : p.metallic;
+    m.ior = TEX ? textured_scalar(sc, p.ior, uv, ddx, ddy) : p.ior;
     emit = f3(p.base_color[0], p.base_color[1], p.base_color[2]) * p.emission_intensity;
     if (p.emission_intensity != 0.0f) m.base_color = f3(0.0f); // (emitters with a textured colour are refused by set_scene)
     m.specular_transmission = 0.0f;
     m.transmission_color = f3(0.0f);
     m.transmission_roughness = 0.0f;
     if (transmission) {
-        m.specular_transmission = TEX ? textured_scalar(sc, p.specular_transmission, uv) : p.specular_transmission;
+        m.specular_transmission = TEX ? textured_scalar(sc, p.specular_transmission, uv, ddx, ddy) : p.specular_transmission;
         if (m.specular_transmission > 0.0f) {
             if (!(m.ior > 1.0f)) {
                 alpha *= 1.0f - m.specular_transmission;
@@ -239,7 +310,7 @@ RPTR_HD float unpack_material(GltfMat &m, float3 &emit, const rptr_base_material
             } else {
                 m.transmission_color = m.base_color;
                 m.transmission_roughness = m.roughness;
-                m.roughness = sqrtf(TEX ? textured_scalar(sc, p.clearcoat_gloss, uv) : p.clearcoat_gloss);
+                m.roughness = sqrtf(TEX ? textured_scalar(sc, p.clearcoat_gloss, uv, ddx, ddy) : p.clearcoat_gloss);
             }
         }
     }
@@ -797,6 +868,69 @@ RPTR_HD RTHit calc_hit_attributes(const GeomInst &g, float ray_t, uint32_t prim,
 RPTR_HD float geometry_scale_to_tmin(float3 orig, float scale) { return (length(orig) + scale) * 0.000005f; }
 
 // ---- one path vertex ---------------------------------------------------------------------------------------------------------
+// ---- ray footprints for texture level of detail (USE_MIPMAPPING: rendering/rt/footprint.glsl, pt_megakernel.glsl:336-350, 583-605, 698-702) ----
+// A GLSL mat2 F, stored as the reference holds it (all four entries): mCR = F[C][R] = column C, row R.  Matrix products follow the
+// GLSL definition (A * B)[c][r] = sum_k A[k][r] * B[c][k], each sum as the RPTR-FP dot product (fma chain, last term innermost).
+struct Footprint { float m00, m01, m10, m11; };
+RPTR_HD float dot2f(float ax, float ay, float bx, float by) { return fmaf(ay, by, ax * bx); }
+// dpdxy_to_footprint (footprint.glsl:10-15)
+RPTR_HD Footprint dpdxy_to_footprint(float3 ray_dir, float3 dpdx, float3 dpdy) {
+    float3 t, b;
+    ortho_basis(t, b, ray_dir);
+    // M = transpose(mat2x3(t, b)) * mat2x3(dpdx, dpdy): M[0] = (t . dpdx, b . dpdx), M[1] = (t . dpdy, b . dpdy)
+    const float m00 = dot(t, dpdx), m01 = dot(b, dpdx), m10 = dot(t, dpdy), m11 = dot(b, dpdy);
+    Footprint f; // F = M * transpose(M): F[c][r] = M[0][r] * M[0][c] + M[1][r] * M[1][c]
+    f.m00 = dot2f(m00, m10, m00, m10);
+    f.m01 = dot2f(m01, m11, m00, m10);
+    f.m10 = dot2f(m00, m10, m01, m11);
+    f.m11 = dot2f(m01, m11, m01, m11);
+    return f;
+}
+// transform_footprint(dst_ray_dir, T, src_ray_dir, F) with T given by its columns (footprint.glsl:28-35)
+RPTR_HD Footprint transform_footprint(float3 dst_ray_dir, float3 tc0, float3 tc1, float3 tc2, float3 src_ray_dir, Footprint F) {
+    float3 t, b;
+    ortho_basis(t, b, src_ray_dir);
+    const float3 u0 = mat_mul(tc0, tc1, tc2, t), u1 = mat_mul(tc0, tc1, tc2, b); // T2 = T * mat2x3(t, b)
+    ortho_basis(t, b, dst_ray_dir);
+    const float a00 = dot(t, u0), a01 = dot(b, u0), a10 = dot(t, u1), a11 = dot(b, u1); // T3 = transpose(mat2x3(t, b)) * T2
+    // G = T3 * F: G[c][r] = T3[0][r] * F[c][0] + T3[1][r] * F[c][1]
+    const float g00 = dot2f(a00, a10, F.m00, F.m01), g01 = dot2f(a01, a11, F.m00, F.m01);
+    const float g10 = dot2f(a00, a10, F.m10, F.m11), g11 = dot2f(a01, a11, F.m10, F.m11);
+    Footprint h; // H = G * transpose(T3): H[c][r] = G[0][r] * T3[0][c] + G[1][r] * T3[1][c]
+    h.m00 = dot2f(g00, g10, a00, a10);
+    h.m01 = dot2f(g01, g11, a00, a10);
+    h.m10 = dot2f(g00, g10, a01, a11);
+    h.m11 = dot2f(g01, g11, a01, a11);
+    return h;
+}
+// reflect_footprint (footprint.glsl:38-42): R = mat3(1) - 2 * outerProduct(n, n), n = normalize(dst - src)
+RPTR_HD Footprint reflect_footprint(float3 dst_ray_dir, float3 src_ray_dir, Footprint F) {
+    const float3 n = normalize(dst_ray_dir - src_ray_dir);
+    const float3 c0 = f3(1.0f - 2.0f * (n.x * n.x), 0.0f - 2.0f * (n.y * n.x), 0.0f - 2.0f * (n.z * n.x));
+    const float3 c1 = f3(0.0f - 2.0f * (n.x * n.y), 1.0f - 2.0f * (n.y * n.y), 0.0f - 2.0f * (n.z * n.y));
+    const float3 c2 = f3(0.0f - 2.0f * (n.x * n.z), 0.0f - 2.0f * (n.y * n.z), 1.0f - 2.0f * (n.z * n.z));
+    return transform_footprint(dst_ray_dir, c0, c1, c2, src_ray_dir, F);
+}
+// footprint_to_dpdxy (footprint.glsl:44-61): the principal axes of F as world-space differentials
+RPTR_HD void footprint_to_dpdxy(float3 &dpdx, float3 &dpdy, float3 ray_dir, Footprint F) {
+    const float B = F.m00 + F.m11;
+    const float C = F.m00 * F.m11 - F.m01 * F.m10;
+    const float D = sqrtf(B * B * 0.25f - C);
+    const float ev0 = 0.5f * B - D, ev1 = 0.5f * B + D;
+    float x0x = 1.0f, x0y = 0.0f, x1x = 0.0f, x1y = 1.0f; // X = mat2(1)
+    if (fabsf(F.m01) > 3.0e-39f) {
+        x0x = F.m10; x0y = ev0 - F.m00;
+        x1x = ev1 - F.m11; x1y = F.m01;
+    }
+    float3 t, b;
+    ortho_basis(t, b, ray_dir);
+    const float i0 = 1.0f / sqrtf(dot2f(x0x, x0y, x0x, x0y)), i1 = 1.0f / sqrtf(dot2f(x1x, x1y, x1x, x1y));
+    const float n0x = x0x * i0, n0y = x0y * i0, n1x = x1x * i1, n1y = x1y * i1;
+    const float s0 = sqrtf(ev0), s1 = sqrtf(ev1);
+    dpdx = f3(fmaf(b.x, n0y, t.x * n0x), fmaf(b.y, n0y, t.y * n0x), fmaf(b.z, n0y, t.z * n0x)) * s0;
+    dpdy = f3(fmaf(b.x, n1y, t.x * n1x), fmaf(b.y, n1y, t.y * n1x), fmaf(b.z, n1y, t.z * n1x)) * s1;
+}
+
 struct PathState {
     float3 o, d;
     float tmin, tmax;
@@ -808,6 +942,7 @@ struct PathState {
     int bounce;
     uint32_t rng_b;   // second word, constant along the path (Sobol index / BN pixelID; unused by the LCG)
     int32_t rng_dim;  // RANDOM_SET_DIM / RANDOM_SHIFT_DIM cursor
+    Footprint foot;   // texture_footprint (pt_megakernel.glsl:338-350, 700): read by the texture lookups of textured scenes only
 };
 struct ShadowRay {
     float3 o, d;
@@ -877,6 +1012,11 @@ RPTR_HD uint32_t alpha_lcg_seed(const FrameParams &fp, int px, int py, uint32_t 
     return sampler_init(0, fp.pts, sample_index, fp.first_sample, fp.frame_offset, (uint32_t)px, (uint32_t)py, (uint32_t)fp.width).a;
 }
 
+// texture footprint of a pixel at the start of a path (pt_megakernel.glsl:341-351); ray queries run the same block on their own direction
+RPTR_HD void init_footprint(const FrameParams &fp, PathState &ps) {
+    const float3 dpdx = (ld3(fp.du) / (float)fp.width) * fp.pixel_radius, dpdy = (ld3(fp.dv) / (float)fp.height) * fp.pixel_radius;
+    ps.foot = dpdxy_to_footprint(ps.d, dpdx, dpdy);
+}
 // primary ray + path state (vulkan/pt_megakernel.glsl:310-365)
 RPTR_HD void generate_primary(const FrameParams &fp, int px, int py, uint32_t sample_index, PathState &ps) {
     const Sampler sm = sampler_init(fp.rng_variant, fp.pts, sample_index, fp.first_sample, fp.frame_offset, (uint32_t)px, (uint32_t)py,
@@ -904,6 +1044,7 @@ RPTR_HD void generate_primary(const FrameParams &fp, int px, int py, uint32_t sa
     ps.illum = f3(0.0f);
     ps.total_t = 0.0f;
     ps.bounce = 0;
+    init_footprint(fp, ps);
 }
 
 // Shades the vertex found by the closest-hit stage (tri < 0: miss).  On SHADE_CONTINUE ps holds the next ray.
@@ -949,7 +1090,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
         t_x = t_x * length(h.tangent);
         t_y = t_y * h.bitangent_l;
         float4 tx = sc.normal_texels[h.material_id];
-        if ((FEAT & RPTR_FEAT_TEXTURES) && tx.w != 0.0f) tx = sample_texture(sc, (uint32_t)mp.normal_map, h.uv); // textureLod(.., hit.uv, bounce): base level
+        if ((FEAT & RPTR_FEAT_TEXTURES) && tx.w != 0.0f) tx = sample_texture_lod(sc, (uint32_t)mp.normal_map, h.uv, ps.bounce); // textureLod(.., hit.uv, float(bounce)), :641-647
         float3 map_nrm = f3(2.0f * tx.x - 1.0f, 2.0f * tx.y - 1.0f, 1.0f * tx.z - 0.0f);
         map_nrm.z = sqrtf(fmaxf(1.0f - map_nrm.x * map_nrm.x - map_nrm.y * map_nrm.y, 0.0f));
         in_ = normalize(mat_mul(t_x, t_y, in_ * sp.normal_z_scale, map_nrm));
@@ -966,7 +1107,20 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
 
     GltfMat mat;
     float3 emit;
-    unpack_material<(FEAT & RPTR_FEAT_TEXTURES) != 0>(mat, emit, mp, tr, sc, h.uv);
+    float2 duvdx = f2(0.0f, 0.0f), duvdy = f2(0.0f, 0.0f);
+    if (FEAT & RPTR_FEAT_TEXTURES) { // hit.duvdxy, pt_megakernel.glsl:583-605 (total_t already includes this segment)
+        float3 dpdx, dpdy;
+        footprint_to_dpdxy(dpdx, dpdy, ps.d, ps.foot);
+        const float3 dir_tangent_un = ps.d - h.geo_normal * dot(ps.d, h.geo_normal);
+        const float cos_theta2 = fmaxf(1.0f - dot(dir_tangent_un, dir_tangent_un), 0.0f);
+        const float3 dir_tangent_elong = dir_tangent_un / (sqrtf(cos_theta2) + cos_theta2);
+        const float3 dpdx_ = dpdx + dir_tangent_elong * dot(dpdx, dir_tangent_un);
+        const float3 dpdy_ = dpdy + dir_tangent_elong * dot(dpdy, dir_tangent_un);
+        const float3 bitangent = cross(h.geo_normal, normalize(h.tangent)) * h.bitangent_l;
+        duvdx = f2(dot(h.tangent, dpdx_) * ps.total_t, dot(bitangent, dpdx_) * ps.total_t);
+        duvdy = f2(dot(h.tangent, dpdy_) * ps.total_t, dot(bitangent, dpdy_) * ps.total_t);
+    }
+    unpack_material<(FEAT & RPTR_FEAT_TEXTURES) != 0>(mat, emit, mp, tr, sc, h.uv, duvdx, duvdy);
     if (aov && ps.bounce == 0) {
         aov->normal = in_;
         aov->depth = length(ip - ld3(fp.cam_pos));
@@ -1052,6 +1206,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
     if (mis_wpdf == 0.0f || is_zero(bsdf) || !(dot(w_i, in_) * dot(w_i, ign) > 0.0f)) return SHADE_TERMINATE;
     ps.thr = ps.thr * bsdf;
     ps.prev_pdf = mis_wpdf;
+    if ((FEAT & RPTR_FEAT_TEXTURES) && dot(w_i, in_) * dot(w_o, in_) > -0.999f) ps.foot = reflect_footprint(w_i, ps.d, ps.foot); // :698-702
     ps.d = w_i;
     ps.o = ip;
     ps.tmin = geometry_scale_to_tmin(ps.o, ps.total_t);

@@ -128,22 +128,17 @@ void RenderCuda::set_scene(const Scene &scene) {
             for (int c = 0; c < 4; ++c) id.transform[4 * r + c] = m[c][r]; // 3x4 row-major, as handed to the TLAS (:1262-1268)
         instances.push_back(id);
     }
-    // Scene::textures (util/image.h:10-27): the base level of every image, 8 bits per channel.  Block-compressed images
-    // (BC1 / BC3 / BC5 of a .vks scene) go through the reference's own decoder (Image::decompress) first; mip levels stored
-    // behind the base level are not passed (the backend samples the base level, include/rptr_types.h).
+    // Scene::textures (util/image.h:10-27): every image as it is -- all mip levels back to back, raw RGBA8 or the block-compressed
+    // payload of a .vks scene (bcFormat 1 / -1 / 3 / 5, librender/scene.cpp:836-930); the backend decodes the blocks on upload and
+    // selects levels from the ray footprints like the megakernel's textureGrad reads (USE_MIPMAPPING)
     std::vector<rptr_texture_desc> textures;
-    std::vector<Image> decompressed;
-    decompressed.reserve(scene.textures.size());
     for (const Image &img : scene.textures) {
-        const Image *src = &img;
-        if (img.bcFormat != 0) {
-            decompressed.push_back(img.decompress());
-            src = &decompressed.back();
-        }
         rptr_texture_desc td{};
-        td.width = src->width; td.height = src->height; td.channels = src->channels;
-        td.color_space = src->color_space == SRGB ? RPTR_COLOR_SPACE_SRGB : RPTR_COLOR_SPACE_LINEAR;
-        td.texels = src->img.data();
+        td.width = img.width; td.height = img.height; td.channels = img.channels;
+        td.color_space = img.color_space == SRGB ? RPTR_COLOR_SPACE_SRGB : RPTR_COLOR_SPACE_LINEAR;
+        td.texels = img.img.data();
+        td.bc_format = img.bcFormat;
+        td.mip_levels = img.mip_levels();
         textures.push_back(td);
     }
     rptr_scene_desc d{};

@@ -71,6 +71,109 @@ class Geometry:
         return p.reshape(-1, 3, 3)
 
 
+def mip_chain(img):
+    """All mip levels of an (h, w, c) uint8 image down to 1 x 1: level k + 1 = (max(w // 2, 1), max(h // 2, 1)) of level k
+    (util/image.cpp:11-21), each texel the rounded mean of the texels it covers (a 2 x 2 box for even sizes)."""
+    levels = [np.ascontiguousarray(img, np.uint8)]
+    while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+        a = levels[-1].astype(np.float64)
+        h, w = a.shape[:2]
+        nh, nw = max(h // 2, 1), max(w // 2, 1)
+        ys = (np.arange(nh + 1) * h) // nh
+        xs = (np.arange(nw + 1) * w) // nw
+        out = np.zeros((nh, nw, a.shape[2]))
+        for j in range(nh):
+            for i in range(nw):
+                out[j, i] = a[ys[j]:ys[j + 1], xs[i]:xs[i + 1]].mean((0, 1))
+        levels.append(np.floor(out + 0.5).astype(np.uint8))
+    return levels
+
+
+def _bc1_block(tile, rgba_alpha):
+    """One 4 x 4 RGBA tile -> 8 bytes of BC1: endpoints = the tile's per-channel min / max quantised to 565, nearest palette entry per
+    texel.  rgba_alpha: three-colour mode with a transparent index for texels with alpha < 128 (BC1 RGBA)."""
+    px = tile.reshape(16, 4).astype(np.int32)
+    opaque = px[:, 3] >= 128 if rgba_alpha else np.ones(16, bool)
+    src = px[opaque][:, :3] if opaque.any() else px[:, :3]
+    lo, hi = src.min(0), src.max(0)
+    def q565(c):
+        return ((int(c[0]) * 31 + 127) // 255) << 11 | ((int(c[1]) * 63 + 127) // 255) << 5 | ((int(c[2]) * 31 + 127) // 255)
+    def expand(v):
+        r, g, b = v >> 11, (v >> 5) & 63, v & 31
+        return np.array([(r << 3) | (r >> 2), (g << 2) | (g >> 4), (b << 3) | (b >> 2)], np.int32)
+    c0, c1 = q565(hi), q565(lo)
+    punch = rgba_alpha and not opaque.all()
+    if punch:
+        if c0 > c1:
+            c0, c1 = c1, c0
+    else:
+        if c0 < c1:
+            c0, c1 = c1, c0
+        if c0 == c1:  # four-colour mode needs c0 > c1; with equal endpoints every index decodes to (nearly) the same colour anyway
+            if c0 == 0:
+                c0 = 1
+            else:
+                c1 = c0 - 1
+    e0, e1 = expand(c0), expand(c1)
+    if c0 > c1:
+        pal = [e0, e1, (2 * e0 + e1 + 1) // 3, (e0 + 2 * e1 + 1) // 3]
+    else:
+        pal = [e0, e1, (e0 + e1 + 1) // 2, np.zeros(3, np.int32)]
+    idx = 0
+    for i in range(16):
+        if punch and not opaque[i]:
+            k = 3
+        else:
+            cand = pal if c0 > c1 else pal[:3]
+            k = int(np.argmin([((px[i, :3] - p) ** 2).sum() for p in cand]))
+        idx |= k << (2 * i)
+    return bytes([c0 & 255, c0 >> 8, c1 & 255, c1 >> 8]) + int(idx).to_bytes(4, "little")
+
+
+def _bc4_block(vals):
+    """16 values -> 8 bytes of BC4 UNORM (eight-value mode: endpoints max / min, nearest palette entry)."""
+    v = vals.reshape(16).astype(np.int32)
+    a, b = int(v.max()), int(v.min())
+    if a == b:
+        pal = [a, b, 0, 0, 0, 0, 0, 255] if a <= b else None
+        pal = [a, b] + [((5 - i) * a + i * b + 2) // 5 for i in range(1, 5)] + [0, 255]
+    else:
+        pal = [a, b] + [((7 - i) * a + i * b + 3) // 7 for i in range(1, 7)]
+    idx = 0
+    for i in range(16):
+        k = int(np.argmin([abs(int(v[i]) - p) for p in pal]))
+        idx |= k << (3 * i)
+    return bytes([a, b]) + int(idx).to_bytes(6, "little")
+
+
+def encode_bc(img, bc_format):
+    """Block-compresses one mip level ((h, w, c) uint8, c expanded to RGBA) the way a .vks exporter would: 4 x 4 blocks, the level
+    padded to whole blocks by repeating its last row / column.  A simple encoder (endpoints = min / max), enough to produce valid
+    streams for the decoders."""
+    px = np.ascontiguousarray(img, np.uint8)
+    h, w, c = px.shape
+    rgba = np.zeros((h, w, 4), np.uint8)
+    rgba[..., 3] = 255
+    rgba[..., :c] = px
+    H, W = (h + 3) // 4 * 4, (w + 3) // 4 * 4
+    pad = np.pad(rgba, ((0, H - h), (0, W - w), (0, 0)), mode="edge")
+    out = bytearray()
+    for by in range(0, H, 4):
+        for bx in range(0, W, 4):
+            tile = pad[by:by + 4, bx:bx + 4]
+            if bc_format == 1:
+                out += _bc1_block(tile, False)
+            elif bc_format == -1:
+                out += _bc1_block(tile, True)
+            elif bc_format == 3:
+                out += _bc4_block(tile[..., 3]) + _bc1_block(tile, False)
+            elif bc_format == 5:
+                out += _bc4_block(tile[..., 0]) + _bc4_block(tile[..., 1])
+            else:
+                raise ValueError("bc_format %r" % bc_format)
+    return np.frombuffer(bytes(out), np.uint8)
+
+
 class Scene:
     """In-memory scene; `desc()` yields the rptr_scene_desc consumed by rptr_cuda_set_scene (and by the oracle)."""
 
@@ -84,11 +187,15 @@ class Scene:
         self.textures = []     # (texels uint8[h, w, channels], T.COLOR_SPACE_*): single-level images of any size
         self._keep = []
 
-    def add_texture(self, texels, color_space=T.COLOR_SPACE_LINEAR):
-        """A texture from one texel (1-4 channels, 8 bit) or an (h, w, channels) image; returns the texture id for T.texture_handle()."""
+    def add_texture(self, texels, color_space=T.COLOR_SPACE_LINEAR, mips=False, bc_format=0):
+        """A texture from one texel (1-4 channels, 8 bit) or an (h, w, channels) image; returns the texture id for T.texture_handle().
+        mips=True appends a box-filtered mip chain down to 1 x 1 (util/image.h: all levels of an Image back to back); bc_format != 0
+        block-compresses every level (BC1 RGB 1, BC1 RGBA -1, BC3 3, BC5 5: the formats of a .vks scene) with encode_bc()."""
         px = np.asarray(texels, np.uint8)
         px = px.reshape(1, 1, -1) if px.ndim == 1 else (px[..., None] if px.ndim == 2 else px)
-        self.textures.append((np.ascontiguousarray(px), color_space))
+        px = np.ascontiguousarray(px)
+        # entries: (base level, colour space) -- or, with a mip chain / block compression, (base level, colour space, levels, bc_format)
+        self.textures.append((px, color_space, mip_chain(px), bc_format) if (mips or bc_format) else (px, color_space))
         return len(self.textures) - 1
 
     def add_mesh(self, geometries):
@@ -156,12 +263,16 @@ class Scene:
             keep.append(bl)
         if getattr(self, "textures", None):
             texs = (T.TextureDesc * len(self.textures))()
-            for i, (texels, color_space) in enumerate(self.textures):
-                px = np.ascontiguousarray(texels, np.uint8)
-                h, w, ch = px.shape
-                texs[i].width, texs[i].height, texs[i].channels, texs[i].color_space = w, h, ch, color_space
-                texs[i].texels = px.ctypes.data_as(C.POINTER(C.c_uint8))
-                keep.append(px)
+            for i, t in enumerate(self.textures):
+                levels, bc = (t[2], t[3]) if len(t) == 4 else ([np.ascontiguousarray(t[0], np.uint8)], 0)
+                if len(t) == 4 and not np.array_equal(levels[0], t[0]):
+                    levels = mip_chain(t[0])  # the base level was edited after add_texture
+                h, w, ch = levels[0].shape
+                blob = np.concatenate([(encode_bc(l, bc) if bc else np.ascontiguousarray(l, np.uint8)).reshape(-1) for l in levels])
+                texs[i].width, texs[i].height, texs[i].channels, texs[i].color_space = w, h, ch, t[1]
+                texs[i].bc_format, texs[i].mip_levels = bc, len(levels)
+                texs[i].texels = blob.ctypes.data_as(C.POINTER(C.c_uint8))
+                keep.append(blob)
             d.textures, d.n_textures = texs, len(self.textures)
             keep.append(texs)
         keep += [geoms, meshes, pms, insts, mats]

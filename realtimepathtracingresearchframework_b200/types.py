@@ -118,7 +118,9 @@ class InstanceDesc(_Pod):
 
 
 class TextureDesc(_Pod):
-    _fields_ = [("width", i32), ("height", i32), ("channels", i32), ("color_space", i32), ("texels", C.POINTER(C.c_uint8))]
+    # texels: mip_levels levels back to back (0 reads as 1); bc_format = Image::bcFormat (0 raw, 1 / -1 BC1 RGB / RGBA, 3 BC3, 5 BC5)
+    _fields_ = [("width", i32), ("height", i32), ("channels", i32), ("color_space", i32), ("texels", C.POINTER(C.c_uint8)),
+                ("bc_format", i32), ("mip_levels", i32)]
 
 
 COLOR_SPACE_LINEAR, COLOR_SPACE_SRGB = 0, 1

@@ -52,7 +52,7 @@ hostsim_scene *hostsim_scene_create(const rptr_scene_desc *d, const rptr_light_s
         s->gi.push_back(g);
     }
     for (const HostTexture &t : s->hs.textures)
-        s->tex.push_back(TexDev{t.rgba.empty() ? nullptr : reinterpret_cast<const uchar4 *>(t.rgba.data()), t.width, t.height, t.srgb, 0});
+        s->tex.push_back(TexDev{t.rgba.empty() ? nullptr : reinterpret_cast<const uchar4 *>(t.rgba.data()), t.width, t.height, t.srgb, t.levels});
     return s;
 }
 void hostsim_scene_destroy(hostsim_scene *s) { delete s; }
@@ -85,6 +85,7 @@ static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
     fp.output_channel = a->params.output_channel;
     fp.glossy_only_mode = a->params.glossy_only_mode;
     fp.enable_raster_taa = a->params.enable_raster_taa;
+    fp.pixel_radius = a->params.pixel_radius;
     if (fp.enable_raster_taa > 0) screen_jitter(a->frame_offset, a->first_sample, a->width, a->height, fp.screen_jitter);
     fp.n_lights = (int)s->hs.lights.size();
     fp.bin_size = a->lighting.bin_size;
@@ -193,6 +194,38 @@ void hostsim_sample_texture(const hostsim_scene *s, uint32_t id, float u, float 
     const float4 c = sample_texture(s->dev(), id, f2(u, v));
     out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
 }
+// textureGrad / textureLod of the product's texture unit on texture `id` of the scene
+void hostsim_sample_texture_grad(const hostsim_scene *s, uint32_t id, float u, float v, const float *ddx, const float *ddy, float *out) {
+    const float4 c = sample_texture_grad(s->dev(), id, f2(u, v), f2(ddx[0], ddx[1]), f2(ddy[0], ddy[1]));
+    out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
+}
+void hostsim_sample_texture_lod(const hostsim_scene *s, uint32_t id, float u, float v, int32_t level, float *out) {
+    const float4 c = sample_texture_lod(s->dev(), id, f2(u, v), level);
+    out[0] = c.x; out[1] = c.y; out[2] = c.z; out[3] = c.w;
+}
+float hostsim_log2(float x) { return log2_pos(x); }
+// texture ingestion of the product (csrc/rptr_host.cpp decode_texture): all levels as RGBA8; returns the number of bytes (out may be NULL)
+int64_t hostsim_decode_texture(const rptr_texture_desc *td, uint8_t *out, int64_t capacity) {
+    HostTexture ht;
+    try { decode_texture(*td, ht); } catch (const std::exception &) { return -1; }
+    if (out && (int64_t)ht.rgba.size() <= capacity) memcpy(out, ht.rgba.data(), ht.rgba.size());
+    return (int64_t)ht.rgba.size();
+}
+// rendering/rt/footprint.glsl as the product states it: op 0 dpdxy_to_footprint(in: dir3, dpdx3, dpdy3) -> 4; op 1 reflect_footprint(in: dst3, src3,
+// F4) -> 4; op 2 footprint_to_dpdxy(in: dir3, F4) -> dpdx3, dpdy3.  F = m00, m01, m10, m11 (GLSL F[c][r])
+void hostsim_footprint_op(int32_t op, const float *in, float *out) {
+    if (op == 0) {
+        const Footprint f = dpdxy_to_footprint(f3(in[0], in[1], in[2]), f3(in[3], in[4], in[5]), f3(in[6], in[7], in[8]));
+        out[0] = f.m00; out[1] = f.m01; out[2] = f.m10; out[3] = f.m11;
+    } else if (op == 1) {
+        const Footprint f = reflect_footprint(f3(in[0], in[1], in[2]), f3(in[3], in[4], in[5]), Footprint{in[6], in[7], in[8], in[9]});
+        out[0] = f.m00; out[1] = f.m01; out[2] = f.m10; out[3] = f.m11;
+    } else {
+        float3 dx, dy;
+        footprint_to_dpdxy(dx, dy, f3(in[0], in[1], in[2]), Footprint{in[3], in[4], in[5], in[6]});
+        out[0] = dx.x; out[1] = dx.y; out[2] = dx.z; out[3] = dy.x; out[4] = dy.y; out[5] = dy.z;
+    }
+}
 // the product's stochastic alpha test (csrc/rptr_bvh.cuh): closest-hit form (draws from the given LCG) and shadow-ray form
 // (own LCG per candidate); 1 = rejected / 1 = the candidate blocks the ray
 int32_t hostsim_alpha_rejects(float alpha, uint32_t *state) { return alpha_rejects(alpha, *state) ? 1 : 0; }
@@ -244,6 +277,7 @@ extern "C" int hostsim_ray_query_layer(const hostsim_scene *s, const hostsim_arg
         ps.o = f3(queries[q].origin[0], queries[q].origin[1], queries[q].origin[2]);
         ps.d = f3(queries[q].dir[0], queries[q].dir[1], queries[q].dir[2]);
         ps.tmax = queries[q].t_max;
+        init_footprint(fp, ps); // the footprint block runs on the ray actually traced (pt_megakernel.glsl:326-351)
         uint32_t alpha_lcg = alpha_lcg_seed(fp, (int)px, (int)py, layer);
         TraceCounters cnt{0, 0};
         for (;;) {

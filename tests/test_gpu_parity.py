@@ -1109,3 +1109,40 @@ def test_realtime_resolve_reprojection_and_taa_against_the_oracle(oracle):
     rbo.enable_taa = 1
     assert not c.configure_for(rbo) and "realtime_resolve" in c.last_error()
     assert b.configure_for(rbo), b.last_error()
+
+
+def test_mip_mapped_block_compressed_textures(oracle):
+    """f2: mip chains + BC1 / BC3 / BC5 images (the formats of a .vks scene) through set_scene, ray-footprint level of detail
+    (rendering/rt/footprint.glsl) with anisotropic textureGrad on every textured parameter, normal maps at level = bounce.
+    Progressive frames, a batch in waves, another pixel_radius, and ray queries -- all bit-identical to the oracle."""
+    from test_texture_lod import textured_mip_scene
+    s = textured_mip_scene(True)
+    W, H = 192, 108
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    sp = load_sky_fit(T.SceneConfig(**sky))
+    o = oracle.OracleScene(s)
+    r = make_backend(s, W, H, sky, transmission=1)
+    r.render_spp(s.camera, 3)
+    ref, _ = o.render(W, H, s.camera, sp, spp=3, transmission=1)
+    assert_identical(r.framebuffer(), ref, "mip-mapped BC textures, 3 frames")
+    single = scenes.textured_scene()
+    ref_single, _ = oracle.OracleScene(single).render(W, H, single.camera, sp, spp=3, transmission=1)
+    assert (ref_single != ref).any(-1).mean() > 0.02   # mips + block compression are visible
+    b = make_backend(s, W, H, sky, transmission=1, wave_paths=3 * W * H, bvh_builder=0)
+    b.params.pixel_radius = 2.5
+    b.params.batch_spp = 4
+    b.render(None, RenderConfiguration(s.camera, reset_accumulation=True))
+    refb, _ = o.render(W, H, s.camera, sp, spp=4, transmission=1, batch_spp=4, params=T.RenderParams(pixel_radius=2.5, batch_spp=4))
+    assert_identical(b.framebuffer(), refb, "mip-mapped BC textures, batch of 4 in waves, pixel_radius 2.5")
+    assert not np.array_equal(refb, o.render(W, H, s.camera, sp, spp=4, transmission=1, batch_spp=4, params=T.RenderParams(batch_spp=4))[0])
+    # ray queries: the footprint starts from the query's own direction (third frame of r began with frame_id 2)
+    from test_hostsim_parity import random_path_queries
+    q = random_path_queries(4000, 5, 2.0)
+    r.enable_ray_queries(4096, 0)
+    r.write_ray_queries(q)
+    r.params.batch_spp = 1
+    r.render_ray_queries(len(q))
+    want = o.render_ray_queries(W, H, s.camera, sp, q, view_frame_id=2, batch_spp=1, transmission=1)
+    got = r.read_ray_results(len(q))
+    assert (want[:, 3] > 0).mean() > 0.1
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "%d queries differ" % (got != want).any(-1).sum()
