@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                     ps.rng = rb.x; ps.bounce = (int)rb.y;
                     ps.rng_b = ((FEAT & RPTR_FEAT_QMC) && fp.rng_variant != 0) ? w.rng2[slot] : 0u;
                     ps.rng_dim = 0;
-                    if (FEAT & RPTR_FEAT_TEXTURES) { const float4 ft = w.foot[slot]; ps.foot = Footprint{ft.x, ft.y, ft.z, ft.w}; }
+                    if ((FEAT & RPTR_FEAT_TEXTURES) && fp.image_textures) { const float4 ft = w.foot[slot]; ps.foot = Footprint{ft.x, ft.y, ft.z, ft.w}; }
                     verts++;
                     // first vertex of a path of the frame's last sample layer: its attributes go to the AOV images
                     const bool want_aov = aov.albedo_roughness && ps.bounce == 0 && slot - aov.slot_lo < (uint32_t)tm.local_pixels;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                         w.ray_o[slot] = f4(ps.o.x, ps.o.y, ps.o.z, ps.tmin);
                         w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
                         w.thr[slot] = f4(ps.thr.x, ps.thr.y, ps.thr.z, ps.prev_pdf);
-                        if (FEAT & RPTR_FEAT_TEXTURES) w.foot[slot] = f4(ps.foot.m00, ps.foot.m01, ps.foot.m10, ps.foot.m11);
+                        if ((FEAT & RPTR_FEAT_TEXTURES) && fp.image_textures) w.foot[slot] = f4(ps.foot.m00, ps.foot.m01, ps.foot.m10, ps.foot.m11);
                     }
                 }
             }
@@ -1232,6 +1232,7 @@ static FrameParams make_frame_params(const rptr_ctx *ctx) {
     fp.glossy_only_mode = ctx->params.glossy_only_mode;
     fp.enable_raster_taa = ctx->params.enable_raster_taa;
     fp.pixel_radius = ctx->params.pixel_radius;
+    fp.image_textures = ctx->any_textured ? 1 : 0;
     if (fp.enable_raster_taa > 0) screen_jitter(ctx->view_frame_offset, ctx->view_frame_id, ctx->width, ctx->height, fp.screen_jitter);
     memcpy(fp.vp, ctx->vp, sizeof(fp.vp));
     memcpy(fp.vp_reference, ctx->vp_reference, sizeof(fp.vp_reference));

@@ -185,6 +185,8 @@ struct FrameParams {
     int32_t transmission;
     float screen_jitter[2]; // view_params.screen_jitter (raster TAA; zero unless enable_raster_taa)
     float pixel_radius;     // render_params.pixel_radius: scale of the texture footprint of a pixel (pt_megakernel.glsl:347-348)
+    int32_t image_textures; // the scene has textures larger than 1 x 1: footprints are tracked and looked up (a feature-complete shade
+                            // variant also runs scenes without any)
     float vp[16];           // view_params.VP, column-major (render_vulkan.cpp:2926-2930)
     float vp_reference[16]; // view_params.VP_reference: the VP of the previous begin_frame (:1986-1998, :2911)
     int32_t rng_variant;  // RenderBackendOptions::rng_variant (librender/render_params.glsl.h:34-37)
@@ -1108,7 +1110,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
     GltfMat mat;
     float3 emit;
     float2 duvdx = f2(0.0f, 0.0f), duvdy = f2(0.0f, 0.0f);
-    if (FEAT & RPTR_FEAT_TEXTURES) { // hit.duvdxy, pt_megakernel.glsl:583-605 (total_t already includes this segment)
+    if ((FEAT & RPTR_FEAT_TEXTURES) && fp.image_textures) { // hit.duvdxy, pt_megakernel.glsl:583-605 (total_t already includes this segment)
         float3 dpdx, dpdy;
         footprint_to_dpdxy(dpdx, dpdy, ps.d, ps.foot);
         const float3 dir_tangent_un = ps.d - h.geo_normal * dot(ps.d, h.geo_normal);
@@ -1206,7 +1208,7 @@ RPTR_HD ShadeResult shade_hit(const FrameParams &fp, const SceneDev &sc, PathSta
     if (mis_wpdf == 0.0f || is_zero(bsdf) || !(dot(w_i, in_) * dot(w_i, ign) > 0.0f)) return SHADE_TERMINATE;
     ps.thr = ps.thr * bsdf;
     ps.prev_pdf = mis_wpdf;
-    if ((FEAT & RPTR_FEAT_TEXTURES) && dot(w_i, in_) * dot(w_o, in_) > -0.999f) ps.foot = reflect_footprint(w_i, ps.d, ps.foot); // :698-702
+    if ((FEAT & RPTR_FEAT_TEXTURES) && fp.image_textures && dot(w_i, in_) * dot(w_o, in_) > -0.999f) ps.foot = reflect_footprint(w_i, ps.d, ps.foot); // :698-702
     ps.d = w_i;
     ps.o = ip;
     ps.tmin = geometry_scale_to_tmin(ps.o, ps.total_t);

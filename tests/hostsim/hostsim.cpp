@@ -86,6 +86,7 @@ static FrameParams make_frame(const hostsim_scene *s, const hostsim_args *a) {
     fp.glossy_only_mode = a->params.glossy_only_mode;
     fp.enable_raster_taa = a->params.enable_raster_taa;
     fp.pixel_radius = a->params.pixel_radius;
+    fp.image_textures = s->hs.any_textured ? 1 : 0;
     if (fp.enable_raster_taa > 0) screen_jitter(a->frame_offset, a->first_sample, a->width, a->height, fp.screen_jitter);
     fp.n_lights = (int)s->hs.lights.size();
     fp.bin_size = a->lighting.bin_size;
