@@ -622,6 +622,52 @@ def gen_textures(n=1500, n_mats=300):
     print("wrote tests/golden/ref_textures.npz:", {k: v.shape for k, v in out.items()})
 
 
+def gen_vks():
+    """What the reference's own reader (ext/libvkr/src/vkr.c in oracle/_ref, through ref_shim/ref_vkr.c) reports for the .vks scene and
+    texture directory tests/vks_util.py writes with our writer."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import vks_util
+    from realtimepathtracingresearchframework_b200 import vks
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref.so"))
+    i64p, f32p = C.POINTER(C.c_int64), C.POINTER(C.c_float)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        path, _ = vks_util.write_test_scene(d)
+        p = path.encode()
+        counts = np.zeros(12, np.int64)
+        assert R.ref_vkr_scene_counts(p, counts.ctypes.data_as(i64p)) == 0, "vkr_open_scene refused the file"
+        out["counts"] = counts
+        n_meshes, n_inst, n_mat = int(counts[1]), int(counts[2]), int(counts[3])
+        ints, floats, segs, names = np.zeros((n_meshes, 10), np.int64), np.zeros((n_meshes, 6), np.float32), np.zeros((n_meshes, 16), np.int64), []
+        for i in range(n_meshes):
+            name = C.create_string_buffer(128)
+            assert R.ref_vkr_mesh(p, C.c_int64(i), ints[i].ctypes.data_as(i64p), floats[i].ctypes.data_as(f32p), segs[i].ctypes.data_as(i64p), C.c_int64(8), name) == 0
+            names.append(name.value.decode())
+        out["mesh_ints"], out["mesh_floats"], out["mesh_segs"], out["mesh_names"] = ints, floats, segs, np.array(names)
+        inst = np.zeros((n_inst, 3), np.int64)
+        for i in range(n_inst):
+            assert R.ref_vkr_instance(p, C.c_int64(i), inst[i].ctypes.data_as(i64p)) == 0
+        out["instances"] = inst
+        mf, mt, mn = np.zeros((n_mat, 8), np.float32), np.zeros((n_mat, 21), np.int64), []
+        for i in range(n_mat):
+            name = C.create_string_buffer(128)
+            assert R.ref_vkr_material(p, C.c_int64(i), name, mf[i].ctypes.data_as(f32p), mt[i].ctypes.data_as(i64p)) == 0
+            mn.append(name.value.decode())
+        out["material_floats"], out["material_tex"], out["material_names"] = mf, mt, np.array(mn)
+        c = vks.read_vks_container(path)
+        tr = np.zeros((int(counts[7]), 12), np.float32)
+        for k in range(len(tr)):
+            rec = np.ascontiguousarray(c["transform_table"][24 * k:24 * k + 24])
+            R.ref_vkr_dequantize_transform(rec.ctypes.data_as(C.POINTER(C.c_ubyte)), tr[k].ctypes.data_as(f32p))
+        out["transforms"] = tr
+        R.ref_vkr_transform_offset.restype = C.c_int64
+        R.ref_vkr_transform_offset.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64]
+        out["transform_offsets"] = np.array([R.ref_vkr_transform_offset(i, 3, 5, f) for i, f in ((0, 0), (2, 7), (3, 0), (4, 2), (7, 3))], np.int64)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_vks.npz"), **out)
+    print("wrote tests/golden/ref_vks.npz:", {k: v.shape for k, v in out.items()})
+
+
 POST_CASES = [(1, 1, 8), (2, 4, 32), (3, 1, 1)]   # (seed, batch, spp_accumulation_window) on 61 x 47 frames
 TAA_CASES = [(11, 1), (12, 2)]                     # (seed, upscale) on 40 x 30 render frames
 
@@ -659,6 +705,9 @@ if __name__ == "__main__":
     if "--textures-only" in sys.argv:
         gen_textures()
         sys.exit(0)
+    if "--vks-only" in sys.argv:
+        gen_vks()
+        sys.exit(0)
     if "--queries-only" in sys.argv:
         gen_queries()
         sys.exit(0)
@@ -671,3 +720,4 @@ if __name__ == "__main__":
     gen_queries()
     gen_post()
     gen_textures()
+    gen_vks()

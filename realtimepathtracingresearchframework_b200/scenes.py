@@ -264,13 +264,17 @@ class Scene:
         if getattr(self, "textures", None):
             texs = (T.TextureDesc * len(self.textures))()
             for i, t in enumerate(self.textures):
-                levels, bc = (t[2], t[3]) if len(t) == 4 else ([np.ascontiguousarray(t[0], np.uint8)], 0)
-                if len(t) == 4 and not np.array_equal(levels[0], t[0]):
-                    levels = mip_chain(t[0])  # the base level was edited after add_texture
-                h, w, ch = levels[0].shape
-                blob = np.concatenate([(encode_bc(l, bc) if bc else np.ascontiguousarray(l, np.uint8)).reshape(-1) for l in levels])
+                if len(t) == 4 and isinstance(t[0], str):  # ("vkt", colour space, vks.read_vkt() record, bcFormat): the file's bytes as they are
+                    blob, bc, w, h, ch, n_levels = np.ascontiguousarray(t[2]["blob"]), t[3], t[2]["width"], t[2]["height"], 4, len(t[2]["levels"])
+                else:
+                    levels, bc = (t[2], t[3]) if len(t) == 4 else ([np.ascontiguousarray(t[0], np.uint8)], 0)
+                    if len(t) == 4 and not np.array_equal(levels[0], t[0]):
+                        levels = mip_chain(t[0])  # the base level was edited after add_texture
+                    h, w, ch = levels[0].shape
+                    n_levels = len(levels)
+                    blob = np.concatenate([(encode_bc(l, bc) if bc else np.ascontiguousarray(l, np.uint8)).reshape(-1) for l in levels])
                 texs[i].width, texs[i].height, texs[i].channels, texs[i].color_space = w, h, ch, t[1]
-                texs[i].bc_format, texs[i].mip_levels = bc, len(levels)
+                texs[i].bc_format, texs[i].mip_levels = bc, n_levels
                 texs[i].texels = blob.ctypes.data_as(C.POINTER(C.c_uint8))
                 keep.append(blob)
             d.textures, d.n_textures = texs, len(self.textures)
@@ -408,7 +412,17 @@ def alpha_tested_soup(n_tris=6000, seed=99):
 # ---------------------------------------------------------------------------------------------------------------------
 # C4: one base mesh instanced many times; GGX + transmission (thick / thin) + emissive per-triangle materials
 # ---------------------------------------------------------------------------------------------------------------------
-def vks_instance_transform(translation, scaling, quat_codes):
+def vks_flip(m43):
+    """The vks axis flip of AnimationData::dequantize (librender/scene.cpp:36-40) applied to a float matrix[4][3] of vkr.c (column i of the
+    glm::mat4x3 = matrix[i]): 3 x 4 row-major object-to-world matrix."""
+    M = np.zeros((3, 4), np.float32)
+    for c in range(4):
+        M[:, c] = np.asarray(m43, np.float32)[c]
+    flip = np.array([[-1, 0, 0], [0, 0, 1], [0, 1, 0]], np.float32)  # (x, y, z) -> (-x, z, y)
+    return (flip @ M).astype(np.float32)
+
+
+def vks_instance_transform(translation, scaling, quat_codes, flip=True):
     """The 3x4 object-to-world matrix a .vks instance yields: vkr_dequantize_transform of the 24-byte record
     (translation 3 x f32, scaling f32, quaternion 4 x u16; ext/libvkr/src/vkr.c:1381-1408) followed by the vks axis
     flip of AnimationData::dequantize (librender/scene.cpp:22-41).  float32 arithmetic throughout."""
@@ -424,12 +438,7 @@ def vks_instance_transform(translation, scaling, quat_codes):
     m[2] = [f(2) * (xz - yw), f(2) * (yz + xw), f(1) - f(2) * (xx + yy)]
     m[:3] *= f(scaling)
     m[3] = np.asarray(translation, np.float32)
-    cols = m  # glm::mat4x3: column i = matrix[i][0..2]
-    M = np.zeros((3, 4), np.float32)
-    for c in range(4):
-        M[:, c] = cols[c]
-    flip = np.array([[-1, 0, 0], [0, 0, 1], [0, 1, 0]], np.float32)  # (x, y, z) -> (-x, z, y)
-    return (flip @ M).astype(np.float32)
+    return vks_flip(m) if flip else m
 
 
 def quantize_quaternion(q):

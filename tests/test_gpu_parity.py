@@ -1146,3 +1146,25 @@ def test_mip_mapped_block_compressed_textures(oracle):
     got = r.read_ray_results(len(q))
     assert (want[:, 3] > 0).mean() > 0.1
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "%d queries differ" % (got != want).any(-1).sum()
+
+
+def test_vks_scene_file_through_the_backend(oracle, tmp_path):
+    """f2: a `.vks` scene with its `.vkt` texture directory (BC1 / BC3 / BC5 / RGBA8 with mip chains, parameter files, LoD groups,
+    quantised instance transforms) loaded by vks.load_vks, rendered on the GPU and by the oracle; and the headless driver on the file."""
+    import vks_util
+    from realtimepathtracingresearchframework_b200 import read_pfm, render, vks
+    path, _ = vks_util.write_test_scene(str(tmp_path))
+    s = vks.load_vks(path)
+    cam = scenes.look_at_camera((0, 2, 14), (0, 0, 0), fovy=50.0)
+    sky = dict(sun_dir=(0.35, 0.8, 0.45))
+    sp = load_sky_fit(T.SceneConfig(**sky))
+    W, H = 160, 90
+    r = make_backend(s, W, H, sky, transmission=1)
+    r.render_spp(cam, 3)
+    ref, _ = oracle.OracleScene(s).render(W, H, cam, sp, spp=3, transmission=1)
+    assert (ref[..., 3] > 0).mean() > 0.05
+    assert_identical(r.framebuffer(), ref, ".vks scene")
+    prefix = str(tmp_path / "yard")
+    assert render.main([path, "--img", str(W), str(H), "--validation", prefix, "--validation-spp", "3", "--batch-spp", "1", "--eye", "0", "2", "14",
+                        "--fovy", "50", "--sun", "0.35", "0.8", "0.45", "--transmission"]) == 0
+    assert np.array_equal(read_pfm(prefix + "_0003.pfm"), ref[..., :3])
