@@ -41,7 +41,7 @@ def main(argv=None):
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args(argv)
     s = load_scene(a.scene)
-    cam = scenes.look_at_camera(tuple(a.eye), tuple(a.target), fovy=a.fovy) if a.eye else s.camera
+    cam = scenes.look_at_camera(tuple(a.eye), tuple(a.target), fovy=a.fovy) if a.eye else getattr(s, "camera", None)
     if cam is None:
         raise SystemExit("the scene file has no camera: pass --eye X Y Z [--target X Y Z] [--fovy F]")
     r = RenderCuda(device=a.device)
