@@ -1,5 +1,6 @@
 // render_cuda.cpp -- see render_cuda.h.  Reference-side glue only; every arithmetic step of the hot path is behind the C ABI.
 #include "render_cuda.h"
+#include "lights.h"            // librender/lights.h: collect_emitters, update_light_sampling
 
 #include <cstdlib>
 #include <cstring>
@@ -141,7 +142,18 @@ void RenderCuda::set_scene(const Scene &scene) {
         td.mip_levels = img.mip_levels();
         textures.push_back(td);
     }
+    // emitters: the reference's own collection and binning (RenderBinnedLightsVulkan::update_scene_from_backend + update_lights,
+    // vulkan/light_sampling/render_binned_lights.cpp:68-127, on librender/lights.cpp) -- the adapter links librender anyway, so the
+    // backend receives the binned buffer instead of re-deriving it (its own restatement serves hosts without librender)
+    BinnedLightSampling binned;
+    {
+        const std::vector<TriLight> emitters = collect_emitters(scene);
+        if (!emitters.empty()) update_light_sampling(binned, emitters, lighting_params);
+    }
+    static_assert(sizeof(TriLight) == sizeof(rptr_tri_light_data), "TriLightData layout");
     rptr_scene_desc d{};
+    d.binned_lights = binned.emitters.empty() ? nullptr : reinterpret_cast<const rptr_tri_light_data *>(binned.emitters.data());
+    d.n_binned_lights = (int32_t)binned.emitters.size();
     d.textures = textures.data(); d.n_textures = (int32_t)textures.size();
     d.geometries = geoms.data(); d.n_geometries = (int32_t)geoms.size();
     d.meshes = meshes.data(); d.n_meshes = (int32_t)meshes.size();
