@@ -370,7 +370,8 @@ def run_b200(args):
                 "dram_gbs": (hw["dram_bytes"] / avg_s / 1e9) if hw and hw["dram_bytes"] and avg_s > 0 else None,
                 "issue_frac": (hw["warp_inst"] / issue_slots) if hw and hw["warp_inst"] and issue_slots > 0 else None,
                 "lane_adjusted_issue_frac": (hw["thread_inst"] / (32.0 * issue_slots)) if hw and hw["thread_inst"] and issue_slots > 0 else None,
-                "binding": "instruction issue (L2-resident scene; HBM traffic is the ray / hit records)",
+                "binding": "L1 data-pipe wavefronts (one per scattered 32-byte sector: 70-84 % of peak) and the ALU pipe (64-68 %), ncu: "
+                           "profiles/r02_full_trace_*_final.txt; the scene is L2-resident, HBM traffic is the ray / hit records",
                 "per_launch": {"launches": cnt["trace_launches"], "avg_ms": cnt["ms_trace"] / max(1, cnt["trace_launches"]),
                                "avg_algorithmic_bytes": trace_bytes / max(1, cnt["trace_launches"])},
                 "per_ray": {"closest": {"nodes": cnt["closest_nodes"] / max(1, cnt["closest_rays"]), "tris": cnt["closest_tris"] / max(1, cnt["closest_rays"]),
