@@ -55,12 +55,14 @@ CLI = os.path.join(HERE, "host", "rptr_cuda_cli")
 def build_cli(force=False):
     """host/rptr_cuda_cli: the headless validation driver (C++ over the C ABI), linked against the in-tree librptr_cuda.so."""
     src = os.path.join(HERE, "host", "rptr_cuda_cli.cpp")
-    deps = [src, os.path.join(HERE, "host", "sky_fits.inc"), os.path.join(HERE, "..", "include", "rptr_cuda.h"), os.path.join(HERE, "..", "include", "rptr_types.h")]
+    loader = os.path.join(HERE, "host", "vks_loader.cpp")
+    deps = [src, loader, os.path.join(HERE, "host", "vks_loader.hpp"), os.path.join(HERE, "host", "sky_fits.inc"),
+            os.path.join(HERE, "..", "include", "rptr_cuda.h"), os.path.join(HERE, "..", "include", "rptr_types.h")]
     if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
         return CLI
     build()
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [host_cxx, "-O2", "-std=c++17", "-o", CLI, src, "-L" + HERE, "-l:librptr_cuda.so", "-Wl,-rpath,$ORIGIN/.."]
+    cmd = [host_cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", CLI, src, loader, "-L" + HERE, "-l:librptr_cuda.so", "-Wl,-rpath,$ORIGIN/.."]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building rptr_cuda_cli failed:\n" + r.stdout + r.stderr)

@@ -21,6 +21,7 @@
 
 #include "../../include/rptr_cuda.h"
 #include "sky_fits.inc"
+#include "vks_loader.hpp"
 
 namespace {
 
@@ -132,10 +133,12 @@ SceneData random_triangles(int64_t n_tris) {
 }
 
 const char *USAGE =
-    "usage: rptr_cuda_cli [--scene cornell|random:<triangles>] [--img <x> <y>] [--backend cuda] [--disable-ui]\n"
+    "usage: rptr_cuda_cli [--scene cornell|random:<triangles>|<file>.vks] [--img <x> <y>] [--backend cuda] [--disable-ui]\n"
+    "                     [--eye <x> <y> <z> --target <x> <y> <z> --fovy <deg>] [--transmission]\n"
     "                     --validation <prefix> [--validation-spp <n>] [--pfm] [--batch-spp <n>] [--profiling <name>]\n"
     "                     [--sky default|slanted] [--device <ordinal>] [--gpus <n>] [--bvh-builder 0|1]\n"
-    "Renders time 0 of a procedural scene to <prefix>_<spp>.pfm like `rptr --validation` (libapp/app_state.cpp:464-481);\n"
+    "Renders time 0 of a procedural scene or of a .vks scene file (with its <name>_textures/ directory; the file has no camera:\n"
+    "pass --eye) to <prefix>_<spp>.pfm like `rptr --validation` (libapp/app_state.cpp:464-481);\n"
     "--profiling writes the BenchmarkInfo columns of libapp/benchmark_info.cpp:69-124 to <name>.csv.  Needs a CUDA device:\n"
     "there is no CPU fallback.\n";
 
@@ -148,8 +151,9 @@ int die(const std::string &msg) {
 
 int main(int argc, char **argv) {
     std::string scene_name = "cornell", validation_prefix, profiling_name, sky = "default";
-    bool scene_hash = false;
-    int width = 1920, height = 1080, target_spp = -1, batch_spp = 1, device = 0, gpus = 1, bvh_builder = 0;
+    bool scene_hash = false, have_eye = false, transmission = false;
+    float eye[3] = {0.0f, 0.0f, 10.0f}, target[3] = {0.0f, 0.0f, 0.0f}, fovy = 65.0f;
+    int width = 1920, height = 1080, target_spp = -1, batch_spp = 1, device = 0, gpus = 1, bvh_builder = 1;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&](const char *what) -> const char * {
@@ -170,6 +174,10 @@ int main(int argc, char **argv) {
         else if (a == "--device") device = atoi(next("--device"));
         else if (a == "--gpus") gpus = atoi(next("--gpus"));
         else if (a == "--bvh-builder") bvh_builder = atoi(next("--bvh-builder"));
+        else if (a == "--eye") { for (float &v : eye) v = (float)atof(next("--eye")); have_eye = true; }
+        else if (a == "--target") { for (float &v : target) v = (float)atof(next("--target")); }
+        else if (a == "--fovy") fovy = (float)atof(next("--fovy"));
+        else if (a == "--transmission") transmission = true; // the GLTF_SUPPORT_TRANSMISSION build (option "transmission")
         else if (a == "--scene-hash") scene_hash = true; // FNV-1a of the generated scene (tests: equals scenes.py), no device needed
         else return die("unknown argument " + a + "\n" + USAGE);
     }
@@ -182,7 +190,19 @@ int main(int argc, char **argv) {
     if (!fit) return die("unknown --sky " + sky);
 
     SceneData sd;
-    if (scene_name == "cornell") sd = cornell_box();
+    rptr_host::VksScene vks;
+    const bool from_file = scene_name.size() > 4 && (scene_name.rfind(".vks") == scene_name.size() - 4 || scene_name.rfind(".vkrs") == scene_name.size() - 5);
+    if (from_file) { // librender/scene.cpp:61-62 dispatches on the extension
+        try {
+            rptr_host::load_vks(scene_name, vks);
+        } catch (const std::exception &e) {
+            return die(e.what());
+        }
+        if (scene_hash) { printf("%016llx\n", (unsigned long long)vks.hash()); return 0; }
+        if (!have_eye) return die("a .vks file has no camera: pass --eye <x> <y> <z> [--target <x> <y> <z>] [--fovy <deg>]");
+        sd.camera = look_at(eye, target, fovy);
+    }
+    else if (scene_name == "cornell") sd = cornell_box();
     else if (scene_name.rfind("random:", 0) == 0) sd = random_triangles(atoll(scene_name.c_str() + 7));
     else return die("unknown --scene " + scene_name);
     if (scene_hash) {
@@ -224,6 +244,8 @@ int main(int argc, char **argv) {
     desc.pmeshes = &pmesh; desc.n_pmeshes = 1;
     desc.instances = &inst; desc.n_instances = 1;
     desc.materials = sd.materials.data(); desc.n_materials = (int32_t)sd.materials.size();
+    if (from_file) desc = vks.desc();
+    else if (have_eye) sd.camera = look_at(eye, target, fovy);
 
     // one context per GPU; with several, a communicator over them (the reference's single render thread drives all devices)
     std::vector<rptr_ctx *> ctxs((size_t)gpus, nullptr);
@@ -236,6 +258,7 @@ int main(int argc, char **argv) {
     for (rptr_ctx *c : ctxs) {
         CHECK(rptr_cuda_initialize(c, width, height), c);
         CHECK(rptr_cuda_set_option(c, "bvh_builder", bvh_builder), c);
+        if (transmission) CHECK(rptr_cuda_set_option(c, "transmission", 1), c);
         CHECK(rptr_cuda_set_scene(c, &desc, &lighting), c);
         CHECK(rptr_cuda_set_scene_params(c, &fit->params), c);
     }
