@@ -13,7 +13,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from realtimepathtracingresearchframework_b200 import RenderCuda, load_pointset_tables, scenes, types as T  # noqa: E402
+from realtimepathtracingresearchframework_b200 import RenderConfiguration, RenderCuda, load_pointset_tables, scenes, types as T  # noqa: E402
 
 W, H = 96, 54
 
@@ -71,6 +71,36 @@ def tour():
     q[:, 7] = 1e20
     q[::7, 3] = -1.0  # skipped queries
     r.trace_ray(q)
+    r.close()
+    n += 1
+    # round 2: image textures with mip chains and block compression (footprint level of detail, anisotropic taps), the temporal passes
+    # (reprojection accumulate + TAA on an upscaled LDR target) over a moving camera, a .vks scene file
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from test_texture_lod import textured_mip_scene
+    s = textured_mip_scene(True)
+    r = backend(s, transmission=1, realtime_resolve=1, render_upscale_factor=2)
+    r.initialize(W, H)   # the upscale factor sizes the LDR target at initialize
+    r.set_scene(s)
+    r.update_config(T.SceneConfig(sun_dir=(0.35, 0.8, 0.45)))
+    r.params.reprojection_mode = T.REPROJECTION_MODE_ACCUMULATE
+    for k in range(4):
+        cam = T.RenderCameraParams.from_buffer_copy(s.camera)
+        cam.pos[0] += 0.05 * k
+        r.params.batch_spp = 1
+        r.render(None, RenderConfiguration(cam, reset_accumulation=(k == 0)))
+        r.process_taa()
+        assert r.framebuffer_ldr().shape == (2 * H, 2 * W, 4)
+    r.close()
+    n += 1
+    import tempfile
+    import vks_util
+    from realtimepathtracingresearchframework_b200 import vks
+    with tempfile.TemporaryDirectory() as d:
+        path, _ = vks_util.write_test_scene(d)
+        s = vks.load_vks(path)
+    r = backend(s, transmission=1)
+    r.render_spp(scenes.look_at_camera((0, 2, 14), (0, 0, 0), fovy=50.0), 2)
+    assert np.isfinite(r.framebuffer()).all()
     r.close()
     n += 1
     # screen-space sharding: two ranks of the same frame
