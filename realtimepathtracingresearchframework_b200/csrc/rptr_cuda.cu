@@ -24,6 +24,7 @@
 #include "../../include/rptr_cuda.h"
 #include "rptr_host.hpp"
 #include "rptr_trace_kernels.cuh"
+#include "rptr_reorder.cuh"
 #include "rptr_bvh_build.hpp"
 #include "rptr_post.cuh"
 
@@ -53,6 +54,11 @@ struct Wave {
     uint32_t *hitq;       // slots of the closest-hit rays of the current bounce that hit something (dense; input of the shade stage)
     uint32_t *hit_counts; // per bounce
     uint32_t *counts; // per bounce d: [4d] live paths entering it, [4d+1] its shadow rays, [4d+2], [4d+3] fetch cursors
+    // ray reordering (rptr_reorder.cuh; allocated when option reorder_bounce / reorder_shadow is on)
+    uint16_t *keys_b, *keys_s; // bin keys of the next bounce queue's entries / of the shadow rays, written by the shade stage
+    uint32_t *queue_sorted;    // the bounce queue in bin order (what the trace stage reads; the shade stage keeps the screen order)
+    uint32_t *sh_perm;         // shadow-ray indices in bin order
+    uint32_t *bin_hist;        // per bounce d: RPTR_BINS counters / cursors of the bounce queue, then of the shadow queue
 };
 
 // The fp16 AOV images of the reference (aov_albedo_roughness_buffer, aov_normal_depth_buffer: vulkan/accumulate.glsl:19-23).
@@ -187,7 +193,8 @@ __global__ void __launch_bounds__(128) k_trace(BvhDev bvh, SceneDev sc, Wave w, 
 template <int FEAT>
 __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_shade(FrameParams fp, SceneDev sc, BvhDev bvh, Wave w, const uint32_t *queue,
                                                               const uint32_t *count, uint32_t *next_queue, uint32_t *next_count,
-                                                              uint32_t *shadow_count, DevCounters *dc, AovTarget aov, TileMap tm, int sort_tiles, int first_bounce) {
+                                                              uint32_t *shadow_count, DevCounters *dc, AovTarget aov, TileMap tm, int sort_tiles, int first_bounce,
+                                                              ReorderKeys rk) {
     __shared__ uint32_t s_hist[RPTR_SHADE_KEYS], s_base[RPTR_SHADE_KEYS];
     __shared__ uint32_t s_sorted[RPTR_SHADE_TILE];
     const uint32_t n = *count;
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
             const uint32_t j = k * RPTR_SHADE_THREADS + threadIdx.x;
             const bool active = j < tile_count;
             bool cont = false, shadow = false;
-            uint32_t slot = 0;
+            uint32_t slot = 0, key_b = 0;
             ShadowRay sh;
             sh.tmax = -1.0f;
             if (active) {
@@ -276,17 +283,22 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                         w.ray_d[slot] = f4(ps.d.x, ps.d.y, ps.d.z, ps.tmax);
                         w.thr[slot] = f4(ps.thr.x, ps.thr.y, ps.thr.z, ps.prev_pdf);
                         if ((FEAT & RPTR_FEAT_TEXTURES) && fp.image_textures) w.foot[slot] = f4(ps.foot.m00, ps.foot.m01, ps.foot.m10, ps.foot.m11);
+                        if (rk.keys_b) key_b = ray_key(rk, rk.mode_b, ps.o, ps.d);
                     }
                 }
             }
             __syncwarp();
             const uint32_t qi = warp_append(next_count, cont);
-            if (cont) next_queue[qi] = slot;
+            if (cont) {
+                next_queue[qi] = slot;
+                if (rk.keys_b) rk.keys_b[qi] = (uint16_t)key_b;
+            }
             const uint32_t si = warp_append(shadow_count, shadow);
             if (shadow) {
                 w.sh_o[si] = f4(sh.o.x, sh.o.y, sh.o.z, sh.tmin);
                 w.sh_d[si] = f4(sh.d.x, sh.d.y, sh.d.z, sh.tmax);
                 w.sh_c[si] = f4(sh.contrib.x, sh.contrib.y, sh.contrib.z, __uint_as_float(slot));
+                if (rk.keys_s) rk.keys_s[si] = (uint16_t)ray_key(rk, rk.mode_s, sh.o, sh.d);
             }
         }
         if (sort_tiles) __syncthreads();
@@ -545,6 +557,8 @@ struct rptr_ctx {
     Pipe pipes[RPTR_MAX_PIPES];
     int n_pipes_ready = 0;
     cudaEvent_t ev_round = nullptr;
+    // ray reordering between shade and trace (rptr_reorder.cuh): key mode of the bounce queue / the shadow queue; 0 = off, -1 = chosen per scene
+    int reorder_bounce = 0, reorder_shadow = 0;
     int concurrent_waves = 1; // measured: two sub-waves side by side cost 3 % at 64 spp and 9 % at 8 spp on one GPU (profiles/r02_sweeps.md)
     std::string error;
     // framebuffer
@@ -700,7 +714,10 @@ static int grid_for(const rptr_ctx *ctx, int blocks_per_sm) { return ctx->num_sm
 static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     const bool need_rng2 = ctx->rng_variant != 0;
     const bool need_foot = ctx->any_textured; // texture footprints: scenes with image textures only
-    if (paths <= ctx->wave_capacity && depth <= ctx->wave_depth && (!need_rng2 || ctx->wave.rng2) && (!need_foot || ctx->wave.foot)) return 0;
+    const bool need_reorder = ctx->reorder_bounce != 0 || ctx->reorder_shadow != 0;
+    if (paths <= ctx->wave_capacity && depth <= ctx->wave_depth && (!need_rng2 || ctx->wave.rng2) && (!need_foot || ctx->wave.foot) &&
+        (!need_reorder || ctx->wave.bin_hist))
+        return 0;
     if (paths < ctx->wave_capacity) paths = ctx->wave_capacity;
     if (depth < ctx->wave_depth) depth = ctx->wave_depth;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -729,6 +746,15 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     CU(dev_alloc(ctx, &w.counts, (size_t)4 * (depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs)); // per sub-wave
     CU(dev_alloc(ctx, &w.hitq, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.hit_counts, (size_t)(depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs));
+    w.keys_b = w.keys_s = nullptr;
+    w.queue_sorted = w.sh_perm = w.bin_hist = nullptr;
+    if (need_reorder) {
+        CU(dev_alloc(ctx, &w.keys_b, n, ctx->wave_allocs));
+        CU(dev_alloc(ctx, &w.keys_s, n, ctx->wave_allocs));
+        CU(dev_alloc(ctx, &w.queue_sorted, n, ctx->wave_allocs));
+        CU(dev_alloc(ctx, &w.sh_perm, n, ctx->wave_allocs));
+        CU(dev_alloc(ctx, &w.bin_hist, (size_t)2 * RPTR_BINS * (depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs));
+    }
     ctx->wave_capacity = paths;
     ctx->wave_depth = depth;
     return 0;
@@ -1129,6 +1155,10 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
         if (value < 1 || value > RPTR_MAX_PIPES) return fail(ctx, "concurrent_waves must be in [1, %d]", RPTR_MAX_PIPES);
         ctx->concurrent_waves = (int)value;
     }
+    else if (n == "reorder_bounce" || n == "reorder_shadow") {
+        if (value < -1 || value > 4) return fail(ctx, "%s must be -1 (chosen per scene), 0 (off) or a key mode 1..4", name);
+        (n == "reorder_bounce" ? ctx->reorder_bounce : ctx->reorder_shadow) = (int)value;
+    }
     else if (n == "trace_kernel") ctx->trace_kernel = (int)value;
     else if (n == "bvh_builder") {
         if (value != 0 && value != 1) return fail(ctx, "bvh_builder must be 0 (host builder) or 1 (device builder)");
@@ -1306,6 +1336,30 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                      (fp.output_channel != 0 ? RPTR_FEAT_AOV : 0) | (fp.rng_variant != 0 ? RPTR_FEAT_QMC : 0) |
                      (ctx->any_normal_map ? RPTR_FEAT_NORMAL_MAPS : 0) | (ctx->any_textured ? RPTR_FEAT_TEXTURES : 0);
     const bool overlap = fp.output_channel == 0 && ctx->overlap_shadow && ctx->trace_kernel == 0;
+    // ray reordering (rptr_reorder.cuh).  Chosen per scene (-1): bounce rays by origin cell and octant; shadow rays by beam when the
+    // sun is the only light NEE samples (parallel rays), by origin cell and octant otherwise.
+    ReorderKeys rk0{};
+    if (ctx->trace_kernel == 0 && ctx->wave.bin_hist) {
+        rk0.mode_b = ctx->reorder_bounce < 0 ? RPTR_KEY_OCTANT_ORIGIN : ctx->reorder_bounce;
+        rk0.mode_s = ctx->reorder_shadow < 0 ? (fp.n_lights == 0 ? RPTR_KEY_BEAM : RPTR_KEY_OCTANT_ORIGIN) : ctx->reorder_shadow;
+        rk0.center[0] = rk0.center[1] = rk0.center[2] = 0.0f;
+        rk0.inv_half = 1.0f / fmaxf(ctx->scene_extent, 1e-20f);
+        const float *sd = fp.sp.sun_dir; // beam basis: any orthonormal pair perpendicular to the sun direction
+        const int a = fabsf(sd[0]) <= fabsf(sd[1]) && fabsf(sd[0]) <= fabsf(sd[2]) ? 0 : (fabsf(sd[1]) <= fabsf(sd[2]) ? 1 : 2);
+        float e[3] = {0.0f, 0.0f, 0.0f};
+        e[a] = 1.0f;
+        float u[3] = {sd[1] * e[2] - sd[2] * e[1], sd[2] * e[0] - sd[0] * e[2], sd[0] * e[1] - sd[1] * e[0]};
+        const float ul = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (ul > 0.0f) {
+            for (int k = 0; k < 3; ++k) u[k] /= ul;
+            const float v[3] = {sd[1] * u[2] - sd[2] * u[1], sd[2] * u[0] - sd[0] * u[2], sd[0] * u[1] - sd[1] * u[0]};
+            const float vl = fmaxf(sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e-20f);
+            for (int k = 0; k < 3; ++k) { rk0.bu[k] = u[k]; rk0.bv[k] = v[k] / vl; }
+        } else if (rk0.mode_s == RPTR_KEY_BEAM)
+            rk0.mode_s = RPTR_KEY_OCTANT_ORIGIN;
+    }
+    const bool sort_b = rk0.mode_b != RPTR_KEY_NONE && fp.output_channel == 0, sort_s = rk0.mode_s != RPTR_KEY_NONE && fp.output_channel == 0;
+    const int g_bin = grid_for(ctx, 4);
 
     struct Sub { // one sub-wave in flight
         Wave w;
@@ -1334,6 +1388,10 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
             if (w0.foot) sb.w.foot += off;
             sb.w.sh_o += off; sb.w.sh_d += off; sb.w.sh_c += off;
             sb.w.queue[0] += off; sb.w.queue[1] += off; sb.w.hitq += off;
+            if (w0.bin_hist) {
+                sb.w.keys_b += off; sb.w.keys_s += off; sb.w.queue_sorted += off; sb.w.sh_perm += off;
+                sb.w.bin_hist += (size_t)k * 2 * RPTR_BINS * (depth + 2);
+            }
             sb.w.counts += (size_t)k * 4 * (depth + 2);
             sb.w.hit_counts += (size_t)k * (depth + 2);
             sb.s_main = k == 0 ? ctx->stream : ctx->pipes[k].s_main;
@@ -1372,6 +1430,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
             Sub &sb = subs[k];
             CU(cudaMemsetAsync(sb.w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), sb.s_main));
             CU(cudaMemsetAsync(sb.w.hit_counts, 0, sizeof(uint32_t) * (depth + 2), sb.s_main));
+            if (sort_b || sort_s) CU(cudaMemsetAsync(sb.w.bin_hist, 0, sizeof(uint32_t) * 2 * RPTR_BINS * (depth + 2), sb.s_main));
             StageTimer t(ctx, 3, sb.s_main);
             Wave wr = sb.w;
             if (!ctx->any_alpha_tested) wr.rng3 = nullptr; // no alpha-tested triangle: nobody reads the alpha LCG
@@ -1384,14 +1443,18 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                 Wave &w = sb.w;
                 // counts[4d] = live paths entering bounce d, [4d+1] = its shadow rays, [4d+2], [4d+3] = fetch cursors
                 const uint32_t *q = d == 0 ? nullptr : w.queue[d & 1];
+                const uint32_t *q_trace = d > 0 && sort_b ? w.queue_sorted : q; // same entries, bin order
                 uint32_t *nq = w.queue[(d + 1) & 1];
                 uint32_t *cn = w.counts + 4 * d;
+                ReorderKeys rk = rk0;
+                rk.keys_b = sort_b && d + 1 < depth ? w.keys_b : nullptr;
+                rk.keys_s = sort_s ? w.keys_s : nullptr;
                 {
                     // inside a union interval the closest-hit launch is timed together with the shadow launch it overlaps
                     StageTimer t(ctx, sb.union_a ? -1 : 0, sb.s_main);
                     if (sb.union_a) sb.union_launches++;
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.ray_o, w.ray_d, q, cn, cn + 2, w.hit, sb.hitq, w.hit_counts + d, nullptr, nullptr, sb.alpha_lcg, alpha_stride, alpha_filter, tm};
+                        TraceIO io{w.ray_o, w.ray_d, q_trace, cn, cn + 2, w.hit, sb.hitq, w.hit_counts + d, nullptr, nullptr, sb.alpha_lcg, alpha_stride, alpha_filter, tm};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<false, true> : k_trace_persistent<false, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_main>>>(
                             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
@@ -1402,7 +1465,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                 if (join_shadow(sb)) return 1; // shade reads illum and rewrites the shadow queue: the overlapped shadow launch must be done
                 {
                     StageTimer t(ctx, 1, sb.s_main);
-#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (sb.hitq ? sb.hitq : q), (sb.hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? sb.aov : AovTarget{nullptr, nullptr, nullptr, 0u}), tm, sort_tiles, (d == 0 ? 1 : 0)
+#define RPTR_SHADE_ARGS fp, ctx->scene, ctx->bvh, w, (sb.hitq ? sb.hitq : q), (sb.hitq ? w.hit_counts + d : cn), nq, cn + 4, cn + 1, ctx->dcounters, (d == 0 ? sb.aov : AovTarget{nullptr, nullptr, nullptr, 0u}), tm, sort_tiles, (d == 0 ? 1 : 0), rk
                     if (feat == 0) k_shade<0><<<g_trace, RPTR_SHADE_THREADS, 0, sb.s_main>>>(RPTR_SHADE_ARGS);
                     else if (feat == RPTR_FEAT_TRI_LIGHTS) k_shade<RPTR_FEAT_TRI_LIGHTS><<<g_trace, RPTR_SHADE_THREADS, 0, sb.s_main>>>(RPTR_SHADE_ARGS);
                     else k_shade<RPTR_FEAT_ALL><<<g_trace, RPTR_SHADE_THREADS, 0, sb.s_main>>>(RPTR_SHADE_ARGS);
@@ -1410,7 +1473,13 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                     ctx->launches++;
                 }
                 if (fp.output_channel != 0 || d + 1 >= depth) continue; // no next-event estimation: no shadow rays
-                TraceIO io{w.sh_o, w.sh_d, nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, sb.alpha_lcg, alpha_stride, alpha_filter, tm};
+                auto bin_pass = [&](const uint16_t *keys, const uint32_t *values, const uint32_t *count, uint32_t *hist, uint32_t *out, cudaStream_t st) {
+                    k_bin_count<<<g_bin, RPTR_BIN_THREADS, 0, st>>>(keys, count, hist);
+                    k_bin_scan<<<1, 1024, 0, st>>>(hist);
+                    k_bin_scatter<<<g_bin, RPTR_BIN_THREADS, 0, st>>>(keys, values, count, hist, out);
+                    ctx->launches += 3;
+                };
+                TraceIO io{w.sh_o, w.sh_d, sort_s ? w.sh_perm : nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, sb.alpha_lcg, alpha_stride, alpha_filter, tm};
                 if (overlap) {
                     // The shadow rays of bounce d and the closest-hit rays of bounce d + 1 are independent.  Both kernels are
                     // persistent grids of one CTA per SM, so launched on two streams the second fills the SMs the first one
@@ -1422,6 +1491,8 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                     }
                     CU(cudaEventRecord(sb.ev_shade, sb.s_main));
                     CU(cudaStreamWaitEvent(sb.s_shadow, sb.ev_shade, 0));
+                    if (sort_s) bin_pass(w.keys_s, nullptr, cn + 1, w.bin_hist + (size_t)(2 * d + 1) * RPTR_BINS, w.sh_perm, sb.s_shadow);
+                    if (sort_b) bin_pass(w.keys_b, nq, cn + 4, w.bin_hist + (size_t)(2 * d) * RPTR_BINS, w.queue_sorted, sb.s_main);
                     auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                     kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_shadow>>>(
                         ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
@@ -1429,6 +1500,8 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                     sb.shadow_pending = true;
                 } else {
                     StageTimer t(ctx, 2, sb.s_main);
+                    if (sort_s) bin_pass(w.keys_s, nullptr, cn + 1, w.bin_hist + (size_t)(2 * d + 1) * RPTR_BINS, w.sh_perm, sb.s_main);
+                    if (sort_b) bin_pass(w.keys_b, nq, cn + 4, w.bin_hist + (size_t)(2 * d) * RPTR_BINS, w.queue_sorted, sb.s_main);
                     if (ctx->trace_kernel == 0) {
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_main>>>(

@@ -33,7 +33,7 @@ struct TraceIO {
     // rays: closest -> Wave ray_o/ray_d indexed by path slot through `queue` (or identity); shadow -> sh_o/sh_d by index
     const float4 *ray_o;
     const float4 *ray_d;
-    const uint32_t *queue; // may be nullptr (identity)
+    const uint32_t *queue; // order in which the rays are fetched (path slots / shadow-ray indices); may be nullptr (identity)
     const uint32_t *count; // number of rays (device resident)
     uint32_t *work;        // global fetch cursor (zeroed before launch)
     float4 *hit;           // closest: (t,u,v,bits(tri)) per path slot
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             if (done) {
                 if (Any) {
                     if (best_tri < 0) { // unoccluded: add the pending NEE contribution (one shadow ray per path and bounce)
-                        const float4 c = io.sh_c[ray_index];
+                        const float4 c = io.sh_c[slot];
                         const uint32_t ps = __float_as_uint(c.w);
                         float4 il = io.illum[ps];
                         il.x = il.x + c.x; il.y = il.y + c.y; il.z = il.z + c.z;
@@ -352,8 +352,8 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
             if (!have && rank < avail) {
                 ray_index = pool_pos + rank;
-                slot = (Any || !io.queue) ? ray_index : io.queue[ray_index];
-                const float4 ro = io.ray_o[Any ? ray_index : slot], rd = io.ray_d[Any ? ray_index : slot];
+                slot = io.queue ? io.queue[ray_index] : ray_index; // closest: path slot; shadow: index of the shadow ray
+                const float4 ro = io.ray_o[slot], rd = io.ray_d[slot];
                 o = f3(ro.x, ro.y, ro.z); tmin = ro.w;
                 d = f3(rd.x, rd.y, rd.z);
                 inv = f3(slab_rcp(slab_safe(d.x)), slab_rcp(slab_safe(d.y)), slab_rcp(slab_safe(d.z)));
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
 #endif
                 best_t = rd.w; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
                 if (Alpha && !Any) after_id = 0x7fffffff;
-                if (Alpha && Any) pixel_linear = tile_pixel_linear(io.tm, __float_as_uint(io.sh_c[ray_index].w) % (uint32_t)io.tm.local_pixels);
+                if (Alpha && Any) pixel_linear = tile_pixel_linear(io.tm, __float_as_uint(io.sh_c[slot].w) % (uint32_t)io.tm.local_pixels);
                 oct = Any ? 0u : ray_octant(d);
                 sp = 0;
                 tsp = 0;

@@ -978,6 +978,24 @@ def test_concurrent_sub_waves_option_is_bit_identical(oracle):
     assert_identical(want, ref, "7 layers in one frame")
 
 
+def test_ray_reordering_options_are_bit_identical():
+    """Options reorder_bounce / reorder_shadow (rptr_reorder.cuh: the bounce and shadow queues binned by origin / direction keys
+    before they are traced) change the ORDER of the trace stage only: every key mode must give the image of the screen order bit
+    for bit -- sun NEE and triangle-light NEE, alpha-tested shadow rays (their seeds come from the pixel, not from the order)."""
+    from test_hostsim_parity import emissive_soup
+    W, H = 320, 180
+    for s, opts in ((scenes.alpha_tested_soup(20000), {}), (emissive_soup(), {"transmission": 1})):
+        a = make_backend(s, W, H, **opts)
+        a.render_spp(s.camera, 5, batch_spp=5)
+        want = a.framebuffer()
+        for mb, ms in ((1, 1), (2, 3), (4, 2), (-1, -1), (0, 3), (2, 0)):
+            b = make_backend(s, W, H, reorder_bounce=mb, reorder_shadow=ms, **opts)
+            b.render_spp(s.camera, 5, batch_spp=5)
+            assert np.array_equal(b.framebuffer().view(np.uint32), want.view(np.uint32)), (s.name, mb, ms)
+            b.close()
+        a.close()
+
+
 def test_textured_scene_uv_lookups(oracle):
     """Textures larger than 1 x 1: bilinear REPEAT lookups of base colour + alpha, specular / roughness / metallic
     channels, ior and the normal map at the hit's uv (k_shade<RPTR_FEAT_ALL>), and of the alpha channel at traversal candidates
