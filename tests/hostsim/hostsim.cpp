@@ -342,6 +342,53 @@ extern "C" int hostsim_trace(const hostsim_scene *s, const rptr_render_ray_query
     return 0;
 }
 
+// Structure and conservativeness of the wide tree (rptr_bvh.cuh): every node and every leaf-order triangle is referenced exactly
+// once, no slot is both an inner child and a triangle, and the vertices of every triangle lie strictly inside the decoded box of its own slot and of every
+// ancestor slot on the way down from the root (what culling relies on).  out = {nodes, triangles, violations, deepest level}.
+#include <functional>
+extern "C" void hostsim_validate_bvh(const hostsim_scene *s, int64_t *out) {
+    const std::vector<BvhNode> &nodes = s->hs.nodes;
+    const std::vector<Tri> &tris = s->hs.leaf_tris;
+    std::vector<int> seen_node(nodes.size(), 0), seen_tri(tris.size(), 0);
+    int64_t bad = 0, depth = 0;
+    struct Bx { float lo[3], hi[3]; };
+    std::vector<Bx> path;
+    std::function<void(int32_t)> walk = [&](int32_t ni) {
+        depth = std::max<int64_t>(depth, (int64_t)path.size() + 1);
+        const BvhNode &nd = nodes[ni];
+        const uint32_t im = node_imask(nd), lm = node_lmask(nd);
+        if (im & lm) bad++;
+        for (int k = 0; k < RPTR_BVH_WIDTH; ++k) {
+            if (!(((im | lm) >> k) & 1u)) continue;
+            Bx bx;
+            decode_child(nd, k, bx.lo, bx.hi);
+            path.push_back(bx);
+            if ((lm >> k) & 1u) {
+                const int32_t ti = nd.tri_base + popc8(lm & ((1u << k) - 1u));
+                if (ti < 0 || ti >= (int32_t)tris.size()) bad++;
+                else {
+                    seen_tri[ti]++;
+                    const Tri &t = tris[ti];
+                    const float v[3][3] = {{t.v0x, t.v0y, t.v0z}, {t.v0x + t.e1x, t.v0y + t.e1y, t.v0z + t.e1z}, {t.v0x + t.e2x, t.v0y + t.e2y, t.v0z + t.e2z}};
+                    for (const Bx &anc : path)
+                        for (int c = 0; c < 3; ++c)
+                            for (int a = 0; a < 3; ++a)
+                                if (!(anc.lo[a] < v[c][a] && v[c][a] < anc.hi[a])) bad++;
+                }
+            } else {
+                const int32_t ci = nd.child_base + popc8(im & ((1u << k) - 1u));
+                if (ci <= ni || ci >= (int32_t)nodes.size()) bad++;
+                else { seen_node[ci]++; walk(ci); }
+            }
+            path.pop_back();
+        }
+    };
+    if (!nodes.empty()) { seen_node[0] = 1; walk(0); }
+    for (int c : seen_node) bad += c != 1;
+    for (int c : seen_tri) bad += c != 1;
+    out[0] = (int64_t)nodes.size(); out[1] = (int64_t)tris.size(); out[2] = bad; out[3] = depth;
+}
+
 // ---- the temporal passes (csrc/rptr_post.cuh), image by image -----------------------------------------------------------------
 #include "../../realtimepathtracingresearchframework_b200/csrc/rptr_post.cuh"
 extern "C" {

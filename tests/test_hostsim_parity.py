@@ -193,6 +193,29 @@ def test_host_bvh_does_not_depend_on_the_builder_thread_count(hostsim, monkeypat
     assert seen["1"] == seen["3"] == seen["8"] and seen["1"][1] > 30000
 
 
+def test_wide_bvh_structure_and_conservative_boxes(hostsim):
+    """The eight-wide nodes (csrc/rptr_bvh.cuh: 7-bit bounds on the node's own grid) as the traversal decodes them: every node
+    and triangle referenced once, and every triangle strictly inside the decoded boxes of all its ancestors -- on a soup, on
+    instances with large offsets, and on a scene whose triangles are tiny against its extent."""
+    lib = C.CDLL(hostsim)
+    lib.hostsim_scene_create.restype = C.c_void_p
+    lib.hostsim_scene_create.argtypes = [C.POINTER(T.SceneDesc), C.POINTER(T.LightSamplingConfig)]
+    lib.hostsim_scene_destroy.argtypes = [C.c_void_p]
+    lib.hostsim_validate_bvh.argtypes = [C.c_void_p, C.c_void_p]
+    ls = T.LightSamplingConfig()
+    cases = [scenes.random_triangles(60000), scenes.instanced_scene(3000, 12), scenes.random_triangles(20000, box=10.0, edge=0.0008),
+             scenes.cornell_box(), scenes.smooth_shaded_scene()]
+    for s in cases:
+        d = s.desc()
+        hs = lib.hostsim_scene_create(C.byref(d), C.byref(ls))
+        assert hs
+        out = (C.c_int64 * 4)()
+        lib.hostsim_validate_bvh(hs, out)
+        lib.hostsim_scene_destroy(hs)
+        nodes, tris, bad, depth = list(out)
+        assert tris > 0 and nodes > 0 and bad == 0 and depth <= 32, (s.name, nodes, tris, bad, depth)
+
+
 def test_vertex_normals_and_uvs_reach_the_shading(H, oracle):
     """The smooth-shaded scene really exercises hit.glsl:58-128: dropping the vertex normals, the uvs or the normal maps each
     changes the image, and the product code follows the oracle in every variant (has_normals / has_uvs combinations)."""
