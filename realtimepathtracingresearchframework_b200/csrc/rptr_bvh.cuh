@@ -74,7 +74,7 @@ struct BvhDev {
 };
 
 #ifndef RPTR_TOP_NODES_MAX
-#define RPTR_TOP_NODES_MAX 1024 // 96 KB of shared memory per CTA
+#define RPTR_TOP_NODES_MAX 832 // 78 KB of shared memory per CTA
 #endif
 
 struct HitRec {

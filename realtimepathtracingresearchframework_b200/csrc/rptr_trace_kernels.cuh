@@ -111,6 +111,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #ifndef RPTR_FAST_RCP
 #define RPTR_FAST_RCP 1 // 1/d of the slab test through MUFU.RCP alone (boxes only prune and are padded far beyond 1 ulp of 1/d)
 #endif
+#ifndef RPTR_SIGN_MASK
+#define RPTR_SIGN_MASK 1 // hit mask of a node step from the sign bits of (tfar - tnear)
+#endif
+#ifndef RPTR_NO_WIDEN
+#define RPTR_NO_WIDEN 0 // 1: tfar is not widened by 4 ulp (the builder's padding alone keeps the slab test conservative)
+#endif
 #ifndef RPTR_CHUNKS_PER_WARP
 #define RPTR_CHUNKS_PER_WARP 4 // target number of queue fetches per warp (tail balance) before the chunk is shortened
 #endif
@@ -127,10 +133,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #define RPTR_SMEM_STACK 8
 #endif
 #define RPTR_STACK_PLANE_BYTES ((uint32_t)(RPTR_SMEM_STACK * RPTR_TRACE_THREADS * sizeof(uint32_t)))
-#define RPTR_TRACE_SMEM_BYTES ((size_t)RPTR_TOP_BYTES + RPTR_LUT_BYTES + 2 * (size_t)RPTR_STACK_PLANE_BYTES)
 #ifndef RPTR_TRI_BACKLOG
-#define RPTR_TRI_BACKLOG 6
+#define RPTR_TRI_BACKLOG 3 // with 832 staged nodes the CTA stays inside the 164 KB shared-memory configuration: 92 KB of L1 remain (profiles/r02_sweeps.md)
 #endif
+// the backlog of triangle groups: shared memory as well, same [entry][thread] layout (it lived in local memory first: every pop
+// was an L1 / L2 round trip the whole warp waited for at the top of the next trip -- 6 % of all stall samples, profiles/r02_trace_source_stalls.md)
+#define RPTR_TRI_PLANE_BYTES ((uint32_t)(RPTR_TRI_BACKLOG * RPTR_TRACE_THREADS * sizeof(uint32_t)))
+#define RPTR_TRACE_SMEM_BYTES ((size_t)RPTR_TOP_BYTES + RPTR_LUT_BYTES + 2 * (size_t)RPTR_STACK_PLANE_BYTES + 2 * (size_t)RPTR_TRI_PLANE_BYTES)
 #ifndef RPTR_NODE_REPS
 #define RPTR_NODE_REPS 2 // node steps per trip of the loop (the ballots / refill checks of a trip are paid once)
 #endif
@@ -160,20 +169,32 @@ __device__ __forceinline__ float qfloat_k(uint32_t word, uint32_t hi_const) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(hi_const), "n"(0x7044 | (K << 8)));
     return __uint_as_float(r);
 }
-// slab test of the child in byte K of the six words, branch free: true when the padded box meets the ray inside (tmin, tmax].
+// slab test of the child in byte K of the six words, branch free: a value whose sign bit is CLEAR when the padded box meets the
+// ray inside (tmin, tmax].  The caller collects the eight sign bits with one funnel shift each (instead of a compare, a select
+// and a third of an add per slot: the kernel is bound by instruction issue, and the subtraction runs on the idle FMA pipe).
 // qn* / qf* are the packed bounds on the near / far side of each axis (picked per node from the sign of the direction:
 // fma is monotonic, so this equals the min / max form of slab_q() bit for bit).
 template <int K>
-__device__ __forceinline__ bool slab_k(const NodeSlab &n, uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx, uint32_t qfy,
-                                       uint32_t qfz, uint32_t hc, float tmin, float tmax) {
+__device__ __forceinline__ float slab_k(const NodeSlab &n, uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx, uint32_t qfy,
+                                        uint32_t qfz, uint32_t hc, float tmin, float tmax) {
     const float nx = fmaf(qfloat_k<K>(qnx, hc), n.ax, n.bx), fx = fmaf(qfloat_k<K>(qfx, hc), n.ax, n.bx);
     const float ny = fmaf(qfloat_k<K>(qny, hc), n.ay, n.by), fy = fmaf(qfloat_k<K>(qfy, hc), n.ay, n.by);
     const float nz = fmaf(qfloat_k<K>(qnz, hc), n.az, n.bz), fz = fmaf(qfloat_k<K>(qfz, hc), n.az, n.bz);
     float tf = fminf(fminf(fx, fy), fz);
     const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+#if RPTR_NO_WIDEN
+    tf = fminf(tf, tmax);
+#else
     tf = fminf(tf * 1.0000004f, tmax);
-    return tn <= tf;
+#endif
+#if RPTR_SIGN_MASK
+    return tf - tn; // hit <=> tn <= tf <=> the sign bit of tf - tn is clear (all operands are finite; x - x = +0)
+#else
+    return tn <= tf ? 0.0f : -1.0f;
+#endif
 }
+// the sign bit of x shifted into m from the right (one funnel shift)
+__device__ __forceinline__ uint32_t shift_in_sign(uint32_t m, float x) { return __funnelshift_l(__float_as_uint(x), m, 1); }
 
 // Alpha = true adds the candidate filter of non-opaque triangles (rptr_bvh.cuh, AlphaFilter).  Closest hit: a lane whose
 // traversal ended on an alpha-tested triangle draws from its path's LCG when it would retire; if the candidate is rejected
@@ -193,6 +214,8 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     extern __shared__ __align__(128) unsigned char smem_top[]; // six word planes of the top_k first nodes, the LUT, the stacks
     __shared__ __align__(8) uint64_t top_bar;
     __shared__ uint32_t hc_word;
+    __shared__ uint32_t s_cnt[RPTR_TRACE_THREADS / 32][4]; // per warp: rays, node steps, triangle tests
+    if (threadIdx.x < RPTR_TRACE_THREADS / 32) s_cnt[threadIdx.x][0] = s_cnt[threadIdx.x][1] = s_cnt[threadIdx.x][2] = 0u;
     const uint32_t n = *io.count;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -231,7 +254,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
 
     // per-lane ray state
     bool have = false;
-    uint32_t ray_index = 0, slot = 0;
+    uint32_t slot = 0;
     float3 o = f3(0.0f), d = f3(0.0f), inv = f3(0.0f);
 #if !RPTR_NO_OOD
     float3 ood = f3(0.0f); // o / d, kept per ray (RPTR_NO_OOD: recomputed per node step -- three multiplies for three registers)
@@ -245,11 +268,11 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     uint32_t tx = 0, ty = 0;       // triangle group: first triangle, lmask << 8 | pending triangle hits (slot order)
     uint32_t oct = 0;              // ray octant (closest hit only: any-hit rays take the children in slot order)
     uint32_t lstack_x[RPTR_MAX_BVH_DEPTH + 2 - RPTR_SMEM_STACK], lstack_y[RPTR_MAX_BVH_DEPTH + 2 - RPTR_SMEM_STACK]; // overflow part of the node-group stack (local memory)
-    // triangle groups that arrive while T is busy (local memory); a lane whose backlog is full pauses its node steps until the
-    // triangle step has caught up, so the backlog is bounded
-    uint32_t tstack_x[RPTR_TRI_BACKLOG], tstack_y[RPTR_TRI_BACKLOG];
+    // triangle groups that arrive while T is busy (shared memory, two planes [entry][thread]); a lane whose backlog is full pauses
+    // its node steps until the triangle step has caught up, so the backlog is bounded
     int tsp = 0;
     const uint32_t sst = lut_base + (uint32_t)RPTR_LUT_BYTES + threadIdx.x * (uint32_t)sizeof(uint32_t);
+    const uint32_t tst = sst + 2u * RPTR_STACK_PLANE_BYTES;
     // high bytes of the decoded box coordinates: read back from shared memory on purpose -- a value ptxas can prove constant or
     // warp-uniform takes the immediate / uniform-register slot of PRMT, and all 48 selectors of a node step are then
     // materialised in registers instead
@@ -259,7 +282,14 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
     const uint32_t hc = n == 0xffffffffu ? 0u : 0x3f000000u;
 #endif
     int sp = 0;
-    uint32_t n_nodes = 0, n_tris = 0, n_rays = 0;
+    // statistics (rays, node steps, triangle tests): ballot counts added to per-warp words in shared memory by lane 0 (reductions
+    // without a return value: nothing waits for them) -- per-lane counters in registers were spilled to local memory by the
+    // register allocator and every increment stalled the warp on a local-memory round trip (7 % of all stall samples)
+#define RPTR_COUNT(k, v)                                                          \
+    {                                                                            \
+        const uint32_t v_ = (uint32_t)(v); /* evaluated by the whole warp (ballots) */ \
+        if (lane == 0) atomicAdd(&s_cnt[threadIdx.x >> 5][k], v_);                \
+    }
 
 #define RPTR_STACK_STRIDE ((uint32_t)(RPTR_TRACE_THREADS * sizeof(uint32_t)))
 #define RPTR_PUSH(vx, vy)                                                        \
@@ -351,7 +381,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             const uint32_t avail = pool_end > pool_pos ? pool_end - pool_pos : 0u;
             const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
             if (!have && rank < avail) {
-                ray_index = pool_pos + rank;
+                const uint32_t ray_index = pool_pos + rank;
                 slot = io.queue ? io.queue[ray_index] : ray_index; // closest: path slot; shadow: index of the shadow ray
                 const float4 ro = io.ray_o[slot], rd = io.ray_d[slot];
                 o = f3(ro.x, ro.y, ro.z); tmin = ro.w;
@@ -370,8 +400,8 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 gx = 0u;
                 gy = bvh.n_nodes > 0 ? (0x100u | (1u << oct)) : 0u; // the root as the only child of a virtual group: slot 0, priority 0 ^ oct
                 have = true;
-                n_rays++;
             }
+            RPTR_COUNT(0, min(avail, (uint32_t)__popc(idle)));
             pool_pos += min(avail, (uint32_t)__popc(idle));
             if (drained && !__any_sync(FULL, have)) break;
         }
@@ -379,6 +409,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         //      hides behind the node step ----
         const bool leaf_turn = __popc(parked0) >= RPTR_LEAF_LANES || inner0 == 0;
         const bool do_leaf = leaf_turn && have && (ty & 0xffu) != 0u;
+        if (leaf_turn && parked0 != 0u) RPTR_COUNT(2, __popc(parked0));
         float4 ta, tb, tc;
         int32_t tri_index = 0;
         if (do_leaf) {
@@ -391,6 +422,7 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         // ---- node steps ---------------------------------------------------------------------------------------------
 #pragma unroll
         for (int rep = 0; rep < RPTR_NODE_REPS; ++rep) {
+            RPTR_COUNT(1, __popc(__ballot_sync(FULL, have && (gy & 0xffu) != 0u && tsp < RPTR_TRI_BACKLOG)));
             if (have && (gy & 0xffu) != 0u && tsp < RPTR_TRI_BACKLOG) {
                 // the highest-priority pending child of the group; what is left of the group goes to the stack
                 const uint32_t p = 31u - (uint32_t)__clz((int)(gy & 0xffu));
@@ -409,7 +441,6 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                     ld256(np + 32, w2, w3);
                     ld256(np + 64, w4, w5);
                 }
-                n_nodes++;
 #if RPTR_NO_OOD
                 const float3 ood = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
 #endif
@@ -422,22 +453,28 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 const uint32_t nx0 = sx ? hx0 : lx0, fx0 = sx ? lx0 : hx0, nx1 = sx ? hx1 : lx1, fx1 = sx ? lx1 : hx1;
                 const uint32_t ny0 = sy ? hy0 : ly0, fy0 = sy ? ly0 : hy0, ny1 = sy ? hy1 : ly1, fy1 = sy ? ly1 : hy1;
                 const uint32_t nz0 = sz ? hz0 : lz0, fz0 = sz ? lz0 : hz0, nz1 = sz ? hz1 : lz1, fz1 = sz ? lz1 : hz1;
-                uint32_t hit8 = 0u;
-                hit8 |= slab_k<0>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t) ? 0x01u : 0u;
-                hit8 |= slab_k<1>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t) ? 0x02u : 0u;
-                hit8 |= slab_k<2>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t) ? 0x04u : 0u;
-                hit8 |= slab_k<3>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t) ? 0x08u : 0u;
-                hit8 |= slab_k<0>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t) ? 0x10u : 0u;
-                hit8 |= slab_k<1>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t) ? 0x20u : 0u;
-                hit8 |= slab_k<2>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t) ? 0x40u : 0u;
-                hit8 |= slab_k<3>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t) ? 0x80u : 0u;
+                uint32_t miss8 = 0u; // slot 7 first: bit k of the result belongs to slot k
+                miss8 = shift_in_sign(miss8, slab_k<3>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t));
+                miss8 = shift_in_sign(miss8, slab_k<2>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t));
+                miss8 = shift_in_sign(miss8, slab_k<1>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t));
+                miss8 = shift_in_sign(miss8, slab_k<0>(ns, nx1, ny1, nz1, fx1, fy1, fz1, hc, tmin, best_t));
+                miss8 = shift_in_sign(miss8, slab_k<3>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t));
+                miss8 = shift_in_sign(miss8, slab_k<2>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t));
+                miss8 = shift_in_sign(miss8, slab_k<1>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t));
+                miss8 = shift_in_sign(miss8, slab_k<0>(ns, nx0, ny0, nz0, fx0, fy0, fz0, hc, tmin, best_t));
+                const uint32_t hit8 = ~miss8 & 0xffu;
                 const uint32_t masks = __float_as_uint(w5.x);
                 const uint32_t ih = hit8 & masks, th = hit8 & (masks >> 8); // empty slots have neither bit
                 gx = __float_as_uint(w1.z);
                 gy = ((masks & 0xffu) << 8) | (Any ? ih : lds8(lut_base + ((oct << 8) | ih)));
                 if (th != 0u) {
                     const uint32_t nty = (masks & 0xff00u) | th;
-                    if ((ty & 0xffu) != 0u) { tstack_x[tsp] = __float_as_uint(w1.w); tstack_y[tsp] = nty; ++tsp; }
+                    if ((ty & 0xffu) != 0u) {
+                        const uint32_t a_ = tst + (uint32_t)tsp * RPTR_STACK_STRIDE;
+                        sts32(a_, __float_as_uint(w1.w));
+                        sts32(a_ + RPTR_TRI_PLANE_BYTES, nty);
+                        ++tsp;
+                    }
                     else { tx = __float_as_uint(w1.w); ty = nty; }
                 }
                 if ((gy & 0xffu) == 0u && sp > 0) RPTR_POP(gx, gy); // nothing hit: back to the closest pending group
@@ -445,7 +482,6 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
         }
         // ---- triangle step: one triangle of the group per trip (its words were requested at the top of the trip) -------------
         if (do_leaf) {
-            n_tris++;
             float t, u, v;
             if (intersect_tri(f3(ta.x, ta.y, ta.z), f3(ta.w, tb.x, tb.y), f3(tb.z, tb.w, tc.x), o, d, t, u, v) &&
                 ((Alpha && !Any) ? (t > tmin || (t == tmin && f2i(tc.y) > after_id)) : t > tmin)) {
@@ -470,21 +506,22 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                 }
             }
         }
-        if (have && (ty & 0xffu) == 0u && tsp > 0) { --tsp; tx = tstack_x[tsp]; ty = tstack_y[tsp]; }
+        if (have && (ty & 0xffu) == 0u && tsp > 0) {
+            --tsp;
+            const uint32_t a_ = tst + (uint32_t)tsp * RPTR_STACK_STRIDE;
+            tx = lds32(a_);
+            ty = lds32(a_ + RPTR_TRI_PLANE_BYTES);
+        }
     }
 #undef RPTR_PUSH
 #undef RPTR_POP
     // ---- counters ----
-    unsigned long long a = n_rays, b = n_nodes, c = n_tris;
-    for (int s = 16; s > 0; s >>= 1) {
-        a += __shfl_down_sync(FULL, a, s);
-        b += __shfl_down_sync(FULL, b, s);
-        c += __shfl_down_sync(FULL, c, s);
-    }
+#undef RPTR_COUNT
     if (lane == 0) {
-        if (a) atomicAdd(c_rays, a);
-        if (b) atomicAdd(c_nodes, b);
-        if (c) atomicAdd(c_tris, c);
+        const uint32_t *c = s_cnt[threadIdx.x >> 5];
+        if (c[0]) atomicAdd(c_rays, (unsigned long long)c[0]);
+        if (c[1]) atomicAdd(c_nodes, (unsigned long long)c[1]);
+        if (c[2]) atomicAdd(c_tris, (unsigned long long)c[2]);
     }
 }
 
