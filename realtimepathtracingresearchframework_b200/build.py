@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librptr_cuda.so")
 SOURCES = ["rptr_cuda.cu", "rptr_bvh_build.cu", "rptr_host.cpp"]
-HEADERS = ["rptr_math.cuh", "rptr_shading.cuh", "rptr_bvh.cuh", "rptr_trace_kernels.cuh", "rptr_reorder.cuh", "rptr_post.cuh", "rptr_pointsets.cuh", "rptr_host.hpp", "rptr_bvh_build.hpp",
+HEADERS = ["rptr_math.cuh", "rptr_shading.cuh", "rptr_bvh.cuh", "rptr_trace_kernels.cuh", "rptr_reorder.cuh", "rptr_trace_tail.cuh", "rptr_post.cuh", "rptr_pointsets.cuh", "rptr_host.hpp", "rptr_bvh_build.hpp",
            "../../include/rptr_cuda.h", "../../include/rptr_types.h"]
 
 # RPTR-FP contract (csrc/rptr_math.cuh): no FMA contraction on either side, IEEE division and square root.

@@ -25,6 +25,7 @@
 #include "rptr_host.hpp"
 #include "rptr_trace_kernels.cuh"
 #include "rptr_reorder.cuh"
+#include "rptr_trace_tail.cuh"
 #include "rptr_bvh_build.hpp"
 #include "rptr_post.cuh"
 
@@ -59,6 +60,9 @@ struct Wave {
     uint32_t *queue_sorted;    // the bounce queue in bin order (what the trace stage reads; the shade stage keeps the screen order)
     uint32_t *sh_perm;         // shadow-ray indices in bin order
     uint32_t *bin_hist;        // per bounce d: RPTR_BINS counters / cursors of the bounce queue, then of the shadow queue
+    // tail hand-over (rptr_trace_tail.cuh): records of the closest-hit launch, then of the shadow launch; counters per bounce d: [2d], [2d+1]
+    TailRec *tail;
+    uint32_t *tail_counts;
 };
 
 // The fp16 AOV images of the reference (aov_albedo_roughness_buffer, aov_normal_depth_buffer: vulkan/accumulate.glsl:19-23).
@@ -559,6 +563,7 @@ struct rptr_ctx {
     cudaEvent_t ev_round = nullptr;
     // ray reordering between shade and trace (rptr_reorder.cuh): key mode of the bounce queue / the shadow queue; 0 = off, -1 = chosen per scene
     int reorder_bounce = 0, reorder_shadow = 0;
+    int tail_kernel = 1; // the last rays of every trace launch go to k_trace_tail, one warp per ray (rptr_trace_tail.cuh)
     int concurrent_waves = 1; // measured: two sub-waves side by side cost 3 % at 64 spp and 9 % at 8 spp on one GPU (profiles/r02_sweeps.md)
     std::string error;
     // framebuffer
@@ -746,6 +751,8 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     CU(dev_alloc(ctx, &w.counts, (size_t)4 * (depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs)); // per sub-wave
     CU(dev_alloc(ctx, &w.hitq, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.hit_counts, (size_t)(depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.tail, (size_t)2 * RPTR_TAIL_CAPACITY(ctx->num_sms) * RPTR_MAX_PIPES, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.tail_counts, (size_t)2 * (depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs));
     w.keys_b = w.keys_s = nullptr;
     w.queue_sorted = w.sh_perm = w.bin_hist = nullptr;
     if (need_reorder) {
@@ -1159,6 +1166,7 @@ int rptr_cuda_set_option(rptr_ctx *ctx, const char *name, int64_t value) {
         if (value < -1 || value > 4) return fail(ctx, "%s must be -1 (chosen per scene), 0 (off) or a key mode 1..4", name);
         (n == "reorder_bounce" ? ctx->reorder_bounce : ctx->reorder_shadow) = (int)value;
     }
+    else if (n == "tail_kernel") ctx->tail_kernel = value != 0;
     else if (n == "trace_kernel") ctx->trace_kernel = (int)value;
     else if (n == "bvh_builder") {
         if (value != 0 && value != 1) return fail(ctx, "bvh_builder must be 0 (host builder) or 1 (device builder)");
@@ -1358,6 +1366,8 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
         } else if (rk0.mode_s == RPTR_KEY_BEAM)
             rk0.mode_s = RPTR_KEY_OCTANT_ORIGIN;
     }
+    const bool use_tail = ctx->tail_kernel && ctx->trace_kernel == 0;
+    const int g_tail = grid_for(ctx, 8);
     const bool sort_b = rk0.mode_b != RPTR_KEY_NONE && fp.output_channel == 0, sort_s = rk0.mode_s != RPTR_KEY_NONE && fp.output_channel == 0;
     const int g_bin = grid_for(ctx, 4);
 
@@ -1392,6 +1402,8 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                 sb.w.keys_b += off; sb.w.keys_s += off; sb.w.queue_sorted += off; sb.w.sh_perm += off;
                 sb.w.bin_hist += (size_t)k * 2 * RPTR_BINS * (depth + 2);
             }
+            sb.w.tail += (size_t)k * 2 * RPTR_TAIL_CAPACITY(ctx->num_sms);
+            sb.w.tail_counts += (size_t)k * 2 * (depth + 2);
             sb.w.counts += (size_t)k * 4 * (depth + 2);
             sb.w.hit_counts += (size_t)k * (depth + 2);
             sb.s_main = k == 0 ? ctx->stream : ctx->pipes[k].s_main;
@@ -1430,6 +1442,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
             Sub &sb = subs[k];
             CU(cudaMemsetAsync(sb.w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), sb.s_main));
             CU(cudaMemsetAsync(sb.w.hit_counts, 0, sizeof(uint32_t) * (depth + 2), sb.s_main));
+            CU(cudaMemsetAsync(sb.w.tail_counts, 0, sizeof(uint32_t) * 2 * (depth + 2), sb.s_main));
             if (sort_b || sort_s) CU(cudaMemsetAsync(sb.w.bin_hist, 0, sizeof(uint32_t) * 2 * RPTR_BINS * (depth + 2), sb.s_main));
             StageTimer t(ctx, 3, sb.s_main);
             Wave wr = sb.w;
@@ -1454,10 +1467,16 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                     StageTimer t(ctx, sb.union_a ? -1 : 0, sb.s_main);
                     if (sb.union_a) sb.union_launches++;
                     if (ctx->trace_kernel == 0) {
-                        TraceIO io{w.ray_o, w.ray_d, q_trace, cn, cn + 2, w.hit, sb.hitq, w.hit_counts + d, nullptr, nullptr, sb.alpha_lcg, alpha_stride, alpha_filter, tm};
+                        TraceIO io{w.ray_o, w.ray_d, q_trace, cn, cn + 2, w.hit, sb.hitq, w.hit_counts + d, nullptr, nullptr, sb.alpha_lcg, alpha_stride, alpha_filter, tm,
+                                   use_tail ? w.tail : nullptr, w.tail_counts + 2 * d};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<false, true> : k_trace_persistent<false, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_main>>>(
                             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
+                        if (use_tail) {
+                            auto tail = ctx->any_alpha_tested ? k_trace_tail<false, true> : k_trace_tail<false, false>;
+                            tail<<<g_tail, RPTR_TAIL_WARPS * 32, 0, sb.s_main>>>(ctx->bvh, io, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
+                            ctx->launches++;
+                        }
                     } else
                         k_trace<<<g_trace, 128, 0, sb.s_main>>>(ctx->bvh, ctx->scene, w, q, cn, ctx->dcounters, sb.hitq ? w.hit_counts + d : nullptr);
                     ctx->launches++;
@@ -1479,7 +1498,14 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                     k_bin_scatter<<<g_bin, RPTR_BIN_THREADS, 0, st>>>(keys, values, count, hist, out);
                     ctx->launches += 3;
                 };
-                TraceIO io{w.sh_o, w.sh_d, sort_s ? w.sh_perm : nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, sb.alpha_lcg, alpha_stride, alpha_filter, tm};
+                TraceIO io{w.sh_o, w.sh_d, sort_s ? w.sh_perm : nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, sb.alpha_lcg, alpha_stride, alpha_filter, tm,
+                           use_tail ? w.tail + RPTR_TAIL_CAPACITY(ctx->num_sms) : nullptr, w.tail_counts + 2 * d + 1};
+                auto shadow_tail = [&](cudaStream_t st) {
+                    if (!use_tail) return;
+                    auto tail = ctx->any_alpha_tested ? k_trace_tail<true, true> : k_trace_tail<true, false>;
+                    tail<<<g_tail, RPTR_TAIL_WARPS * 32, 0, st>>>(ctx->bvh, io, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
+                    ctx->launches++;
+                };
                 if (overlap) {
                     // The shadow rays of bounce d and the closest-hit rays of bounce d + 1 are independent.  Both kernels are
                     // persistent grids of one CTA per SM, so launched on two streams the second fills the SMs the first one
@@ -1496,6 +1522,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                     auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                     kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_shadow>>>(
                         ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
+                    shadow_tail(sb.s_shadow);
                     CU(cudaEventRecord(sb.ev_shadow, sb.s_shadow));
                     sb.shadow_pending = true;
                 } else {
@@ -1506,6 +1533,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<true, true> : k_trace_persistent<true, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_main>>>(
                             ctx->bvh, io, &ctx->dcounters->shadow_rays, &ctx->dcounters->shadow_nodes, &ctx->dcounters->shadow_tris);
+                        shadow_tail(sb.s_main);
                     } else
                         k_shadow<<<g_trace, 128, 0, sb.s_main>>>(ctx->bvh, w, cn + 1, ctx->dcounters, alpha_filter, tm);
                 }
@@ -1796,7 +1824,7 @@ int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, in
     if (ctx->trace_kernel == 0) {
         k_rq_prepare<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(dq, n, ctx->tr_ray_o, ctx->tr_ray_d, ctx->tr_counts);
         TraceIO io{ctx->tr_ray_o, ctx->tr_ray_d, nullptr, ctx->tr_counts, ctx->tr_counts + 1, ctx->tr_hit, nullptr, nullptr, nullptr, nullptr, nullptr, 0u,
-                   AlphaFilter{SceneDev{}, 0u, 0u, 0u}, TileMap{}};
+                   AlphaFilter{SceneDev{}, 0u, 0u, 0u}, TileMap{}, nullptr, nullptr};
         k_trace_persistent<false, false><<<grid_for(ctx, 1), RPTR_TRACE_THREADS, RPTR_TRACE_SMEM_BYTES, ctx->stream>>>(
             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
         k_rq_pack<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->bvh, dq, n, ctx->tr_hit, dr, hit_t ? dt : nullptr);

@@ -29,6 +29,15 @@ namespace rp {
 #define RPTR_LEAF_LANES 8
 #endif
 
+// A ray the persistent kernel hands over to the tail kernel (rptr_trace_tail.cuh): where it is read from and what is known so far
+struct TailRec {
+    uint32_t slot;    // closest: path slot; shadow: index of the shadow ray
+    float tmin;       // closest with the alpha filter: t of the last rejected candidate
+    int32_t after_id; //                                its id
+    float best_t, best_u, best_v;
+    int32_t best_tri, best_id;
+};
+
 struct TraceIO {
     // rays: closest -> Wave ray_o/ray_d indexed by path slot through `queue` (or identity); shadow -> sh_o/sh_d by index
     const float4 *ray_o;
@@ -46,6 +55,9 @@ struct TraceIO {
     uint32_t alpha_stride; //          LCG with the UNIFORM pointset (stride 2: Wave::rngb), a separate one otherwise (stride 1: Wave::rng3)
     AlphaFilter alpha;     // scene tables for the alpha of textured candidates; shadow: per-candidate LCG seeds (pixel_linear is filled in per ray)
     TileMap tm;            // shadow: path slot -> pixel that seeds the per-candidate LCG (frame pixel or ray-query invocation)
+    // tail hand-over (nullptr: the persistent kernel finishes every ray itself)
+    TailRec *tail;
+    uint32_t *tail_count;
 };
 
 
@@ -116,6 +128,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #endif
 #ifndef RPTR_NO_WIDEN
 #define RPTR_NO_WIDEN 0 // 1: tfar is not widened by 4 ulp (the builder's padding alone keeps the slab test conservative)
+#endif
+#ifndef RPTR_TAIL_LIVE
+#define RPTR_TAIL_LIVE 8 // a drained warp hands its rays over to the tail kernel once at most this many are alive (sweep: profiles/r02_sweeps.md)
 #endif
 #ifndef RPTR_CHUNKS_PER_WARP
 #define RPTR_CHUNKS_PER_WARP 4 // target number of queue fetches per warp (tail balance) before the chunk is shortened
@@ -404,6 +419,20 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
             RPTR_COUNT(0, min(avail, (uint32_t)__popc(idle)));
             pool_pos += min(avail, (uint32_t)__popc(idle));
             if (drained && !__any_sync(FULL, have)) break;
+        }
+        // ---- the tail of the launch: the queue is empty and this warp is down to its last rays -> they go to the tail kernel, where
+        //      a whole warp works on each (rptr_trace_tail.cuh), and the warp's slot on the SM is free for the next launch ----
+        if (io.tail && drained) { // warp-uniform
+            const unsigned live = __ballot_sync(FULL, have);
+            if (__popc(live) <= RPTR_TAIL_LIVE) {
+                if (have) {
+                    TailRec tr;
+                    tr.slot = slot; tr.tmin = tmin; tr.after_id = (Alpha && !Any) ? after_id : 0x7fffffff;
+                    tr.best_t = best_t; tr.best_u = best_u; tr.best_v = best_v; tr.best_tri = best_tri; tr.best_id = best_id;
+                    io.tail[atomicAdd(io.tail_count, 1u)] = tr;
+                }
+                break;
+            }
         }
         // ---- the triangle of lanes whose triangle group is processed in this trip is requested first, so that its latency
         //      hides behind the node step ----

@@ -996,6 +996,28 @@ def test_ray_reordering_options_are_bit_identical():
         a.close()
 
 
+def test_tail_kernel_is_bit_identical(oracle):
+    """Option tail_kernel (default on; csrc/rptr_trace_tail.cuh): the last rays of every trace launch are handed to a kernel that
+    walks each with a whole warp, four nodes per step, restarting at the root with the best hit found so far.  Small frames make
+    the tail a large share of every launch: closest-hit and any-hit rays, the alpha filter's restarts and per-candidate seeds,
+    triangle-light NEE, transmission, ray queries -- same bits with the hand-over on and off, and equal to the oracle."""
+    from test_hostsim_parity import emissive_soup
+    W, H = 160, 90
+    for s, opts in ((scenes.alpha_tested_soup(20000), {}), (emissive_soup(), {"transmission": 1}), (scenes.random_triangles(50000), {})):
+        imgs = []
+        for tail in (0, 1):
+            r = make_backend(s, W, H, tail_kernel=tail, **opts)
+            r.render_spp(s.camera, 6, batch_spp=3)
+            imgs.append(r.framebuffer())
+            c = r.counters()
+            assert c["closest_rays"] > 0 and c["closest_nodes"] > c["closest_rays"]
+            r.close()
+        assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), s.name
+    s = scenes.random_triangles(50000)
+    ref, _ = oracle.OracleScene(s).render(W, H, s.camera, load_sky_fit(), spp=6, batch_spp=3)
+    assert_identical(imgs[1], ref, "tail kernel on")
+
+
 def test_textured_scene_uv_lookups(oracle):
     """Textures larger than 1 x 1: bilinear REPEAT lookups of base colour + alpha, specular / roughness / metallic
     channels, ior and the normal map at the hit's uv (k_shade<RPTR_FEAT_ALL>), and of the alpha channel at traversal candidates
