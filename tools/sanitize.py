@@ -123,7 +123,9 @@ def tiny_tour():
     W, H = 32, 18
     n = 0
     for s, opts in ((scenes.random_triangles(400, box=3.0, edge=0.8), dict()), (scenes.alpha_tested_soup(600), dict()),
-                    (scenes.random_triangles(400, box=3.0, edge=0.8), dict(concurrent_waves=2))):
+                    (scenes.random_triangles(400, box=3.0, edge=0.8), dict(concurrent_waves=2)),
+                    (scenes.alpha_tested_soup(600), dict(reorder_bounce=2, reorder_shadow=3)),  # binned queues (rptr_reorder.cuh)
+                    (scenes.random_triangles(400, box=3.0, edge=0.8), dict(tail_kernel=0))):   # every other context hands its tails to k_trace_tail
         s.camera = scenes.look_at_camera((0, 0, 10), (0, 0, 0), fovy=50.0)
         r = backend(s, **opts)
         r.render_spp(s.camera, 4, batch_spp=4)
