@@ -60,7 +60,8 @@ struct Wave {
     uint32_t *queue_sorted;    // the bounce queue in bin order (what the trace stage reads; the shade stage keeps the screen order)
     uint32_t *sh_perm;         // shadow-ray indices in bin order
     uint32_t *bin_hist;        // per bounce d: RPTR_BINS counters / cursors of the bounce queue, then of the shadow queue
-    // tail hand-over (rptr_trace_tail.cuh): records of the closest-hit launch, then of the shadow launch; counters per bounce d: [2d], [2d+1]
+    // tail hand-over (rptr_trace_tail.cuh): records of the closest-hit launch, then of the shadow launch; per bounce d: [4d], [4d+1] record
+    // counts of the two launches, [4d+2], [4d+3] the cursors of their tail kernels
     TailRec *tail;
     uint32_t *tail_counts;
 };
@@ -752,7 +753,7 @@ static int ensure_wave(rptr_ctx *ctx, size_t paths, int depth) {
     CU(dev_alloc(ctx, &w.hitq, n, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.hit_counts, (size_t)(depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs));
     CU(dev_alloc(ctx, &w.tail, (size_t)2 * RPTR_TAIL_CAPACITY(ctx->num_sms) * RPTR_MAX_PIPES, ctx->wave_allocs));
-    CU(dev_alloc(ctx, &w.tail_counts, (size_t)2 * (depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs));
+    CU(dev_alloc(ctx, &w.tail_counts, (size_t)4 * (depth + 2) * RPTR_MAX_PIPES, ctx->wave_allocs));
     w.keys_b = w.keys_s = nullptr;
     w.queue_sorted = w.sh_perm = w.bin_hist = nullptr;
     if (need_reorder) {
@@ -1367,7 +1368,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
             rk0.mode_s = RPTR_KEY_OCTANT_ORIGIN;
     }
     const bool use_tail = ctx->tail_kernel && ctx->trace_kernel == 0;
-    const int g_tail = grid_for(ctx, 8);
+    const int g_tail = grid_for(ctx, 16); // 4 warps x 4 rays per CTA
     const bool sort_b = rk0.mode_b != RPTR_KEY_NONE && fp.output_channel == 0, sort_s = rk0.mode_s != RPTR_KEY_NONE && fp.output_channel == 0;
     const int g_bin = grid_for(ctx, 4);
 
@@ -1403,7 +1404,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                 sb.w.bin_hist += (size_t)k * 2 * RPTR_BINS * (depth + 2);
             }
             sb.w.tail += (size_t)k * 2 * RPTR_TAIL_CAPACITY(ctx->num_sms);
-            sb.w.tail_counts += (size_t)k * 2 * (depth + 2);
+            sb.w.tail_counts += (size_t)k * 4 * (depth + 2);
             sb.w.counts += (size_t)k * 4 * (depth + 2);
             sb.w.hit_counts += (size_t)k * (depth + 2);
             sb.s_main = k == 0 ? ctx->stream : ctx->pipes[k].s_main;
@@ -1442,7 +1443,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
             Sub &sb = subs[k];
             CU(cudaMemsetAsync(sb.w.counts, 0, sizeof(uint32_t) * 4 * (depth + 2), sb.s_main));
             CU(cudaMemsetAsync(sb.w.hit_counts, 0, sizeof(uint32_t) * (depth + 2), sb.s_main));
-            CU(cudaMemsetAsync(sb.w.tail_counts, 0, sizeof(uint32_t) * 2 * (depth + 2), sb.s_main));
+            CU(cudaMemsetAsync(sb.w.tail_counts, 0, sizeof(uint32_t) * 4 * (depth + 2), sb.s_main));
             if (sort_b || sort_s) CU(cudaMemsetAsync(sb.w.bin_hist, 0, sizeof(uint32_t) * 2 * RPTR_BINS * (depth + 2), sb.s_main));
             StageTimer t(ctx, 3, sb.s_main);
             Wave wr = sb.w;
@@ -1468,7 +1469,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                     if (sb.union_a) sb.union_launches++;
                     if (ctx->trace_kernel == 0) {
                         TraceIO io{w.ray_o, w.ray_d, q_trace, cn, cn + 2, w.hit, sb.hitq, w.hit_counts + d, nullptr, nullptr, sb.alpha_lcg, alpha_stride, alpha_filter, tm,
-                                   use_tail ? w.tail : nullptr, w.tail_counts + 2 * d};
+                                   use_tail ? w.tail : nullptr, w.tail_counts + 4 * d, w.tail_counts + 4 * d + 2};
                         auto kernel = ctx->any_alpha_tested ? k_trace_persistent<false, true> : k_trace_persistent<false, false>;
                         kernel<<<g_pt, RPTR_TRACE_THREADS, top_smem, sb.s_main>>>(
                             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
@@ -1499,7 +1500,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
                     ctx->launches += 3;
                 };
                 TraceIO io{w.sh_o, w.sh_d, sort_s ? w.sh_perm : nullptr, cn + 1, cn + 3, nullptr, nullptr, nullptr, w.sh_c, w.illum, sb.alpha_lcg, alpha_stride, alpha_filter, tm,
-                           use_tail ? w.tail + RPTR_TAIL_CAPACITY(ctx->num_sms) : nullptr, w.tail_counts + 2 * d + 1};
+                           use_tail ? w.tail + RPTR_TAIL_CAPACITY(ctx->num_sms) : nullptr, w.tail_counts + 4 * d + 1, w.tail_counts + 4 * d + 3};
                 auto shadow_tail = [&](cudaStream_t st) {
                     if (!use_tail) return;
                     auto tail = ctx->any_alpha_tested ? k_trace_tail<true, true> : k_trace_tail<true, false>;
@@ -1824,7 +1825,7 @@ int rptr_cuda_trace_rays(rptr_ctx *ctx, const rptr_render_ray_query *queries, in
     if (ctx->trace_kernel == 0) {
         k_rq_prepare<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(dq, n, ctx->tr_ray_o, ctx->tr_ray_d, ctx->tr_counts);
         TraceIO io{ctx->tr_ray_o, ctx->tr_ray_d, nullptr, ctx->tr_counts, ctx->tr_counts + 1, ctx->tr_hit, nullptr, nullptr, nullptr, nullptr, nullptr, 0u,
-                   AlphaFilter{SceneDev{}, 0u, 0u, 0u}, TileMap{}, nullptr, nullptr};
+                   AlphaFilter{SceneDev{}, 0u, 0u, 0u}, TileMap{}, nullptr, nullptr, nullptr};
         k_trace_persistent<false, false><<<grid_for(ctx, 1), RPTR_TRACE_THREADS, RPTR_TRACE_SMEM_BYTES, ctx->stream>>>(
             ctx->bvh, io, &ctx->dcounters->closest_rays, &ctx->dcounters->closest_nodes, &ctx->dcounters->closest_tris);
         k_rq_pack<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->bvh, dq, n, ctx->tr_hit, dr, hit_t ? dt : nullptr);

@@ -58,6 +58,7 @@ struct TraceIO {
     // tail hand-over (nullptr: the persistent kernel finishes every ray itself)
     TailRec *tail;
     uint32_t *tail_count;
+    uint32_t *tail_cursor; // next record the tail kernel hands to a group of lanes (zero at launch)
 };
 
 
