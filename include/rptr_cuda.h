@@ -79,6 +79,12 @@ int rptr_cuda_set_scene_params(rptr_ctx *ctx, const rptr_scene_params *params);
  *   "aov_buffers"   0/1  write the fp16 AOV images (default 1: ENABLE_AOV_BUFFERS, vulkan/gpu_params.glsl:19)
  *   "overlap_shadow" 0/1 (default 1) launch the shadow rays of bounce d on a second stream beside the closest-hit rays of bounce
  *                   d + 1 (independent work; the persistent grids interleave SM by SM, hiding each other's tails)
+ *   "tail_kernel"   0/1 (default 1) a drained warp of the persistent trace kernel hands its last rays to k_trace_tail, which walks each
+ *                   with eight lanes breadth-wise (csrc/rptr_trace_tail.cuh); images are identical either way
+ *   "reorder_bounce", "reorder_shadow"  0 (default) = trace the queues in screen order; 1..4 = bin the bounce / shadow queue by a
+ *                   12-bit key of ray origin and direction first (csrc/rptr_reorder.cuh), -1 = key chosen per scene.  Images are
+ *                   identical either way; measured without gain on the target scenes (profiles/r02_sweeps.md)
+ *   "concurrent_waves" 1..4 (default 1) sub-waves of whole sample layers side by side on their own streams
  *   "stage_timing"  0/1  time each stage with CUDA events into rptr_counters.ms_*
  *   "bvh_builder"   1 (default) = binned-SAH build on the device, 0 = the same algorithm on the host inside set_scene, kept as
  *                   the A/B (both replace the driver's BLAS/TLAS build, vulkan/vulkanrt_utils.cpp:82-167; images are identical

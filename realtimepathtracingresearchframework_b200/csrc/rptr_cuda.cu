@@ -1368,7 +1368,7 @@ static int render_waves(rptr_ctx *ctx, const FrameParams &fp, const TileMap &tm,
             rk0.mode_s = RPTR_KEY_OCTANT_ORIGIN;
     }
     const bool use_tail = ctx->tail_kernel && ctx->trace_kernel == 0;
-    const int g_tail = grid_for(ctx, 16); // 4 warps x 4 rays per CTA
+    const int g_tail = grid_for(ctx, 64 / RPTR_TAIL_WARPS); // 4 warps x 4 rays per CTA
     const bool sort_b = rk0.mode_b != RPTR_KEY_NONE && fp.output_channel == 0, sort_s = rk0.mode_s != RPTR_KEY_NONE && fp.output_channel == 0;
     const int g_bin = grid_for(ctx, 4);
 

@@ -20,8 +20,10 @@
 
 namespace rp {
 
-#define RPTR_TAIL_WARPS 4         // warps per CTA of the tail kernel
+#ifndef RPTR_TAIL_GROUP
 #define RPTR_TAIL_GROUP 8         // lanes per ray
+#endif
+#define RPTR_TAIL_WARPS (RPTR_TAIL_GROUP >= 8 ? 4 : 2) // warps per CTA of the tail kernel (32 KB of frontiers)
 #define RPTR_TAIL_FRONTIER 512    // node indices per ray, shared memory
 #define RPTR_TAIL_RESERVE (7 * (RPTR_MAX_BVH_DEPTH + 2) + 8 * RPTR_TAIL_GROUP)
 // records one launch can hand over: every warp of the persistent grid, RPTR_TAIL_LIVE rays each
