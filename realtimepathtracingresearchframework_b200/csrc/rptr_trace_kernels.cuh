@@ -30,12 +30,17 @@ namespace rp {
 #endif
 
 // A ray the persistent kernel hands over to the tail kernel (rptr_trace_tail.cuh): where it is read from and what is known so far
+#define RPTR_TAIL_GROUPS 16 // >= 2 + RPTR_SMEM_STACK + RPTR_TRI_BACKLOG: what a lane can have pending without its local-memory overflow stack
 struct TailRec {
     uint32_t slot;    // closest: path slot; shadow: index of the shadow ray
     float tmin;       // closest with the alpha filter: t of the last rejected candidate
     int32_t after_id; //                                its id
     float best_t, best_u, best_v;
     int32_t best_tri, best_id;
+    // where the traversal stood: node groups (bottom of the stack first, the lane's current group last), then triangle groups, as
+    // (base, masks) pairs of the persistent kernel.  n_node_groups < 0: not recorded (deep stack) -- the tail kernel restarts at the root
+    int32_t n_node_groups, n_tri_groups;
+    uint32_t gx[RPTR_TAIL_GROUPS], gy[RPTR_TAIL_GROUPS];
 };
 
 struct TraceIO {
@@ -155,6 +160,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // the backlog of triangle groups: shared memory as well, same [entry][thread] layout (it lived in local memory first: every pop
 // was an L1 / L2 round trip the whole warp waited for at the top of the next trip -- 6 % of all stall samples, profiles/r02_trace_source_stalls.md)
 #define RPTR_TRI_PLANE_BYTES ((uint32_t)(RPTR_TRI_BACKLOG * RPTR_TRACE_THREADS * sizeof(uint32_t)))
+static_assert(2 + RPTR_SMEM_STACK + RPTR_TRI_BACKLOG <= RPTR_TAIL_GROUPS, "TailRec holds the node-group stack, the backlog and the two current groups");
 #define RPTR_TRACE_SMEM_BYTES ((size_t)RPTR_TOP_BYTES + RPTR_LUT_BYTES + 2 * (size_t)RPTR_STACK_PLANE_BYTES + 2 * (size_t)RPTR_TRI_PLANE_BYTES)
 #ifndef RPTR_NODE_REPS
 #define RPTR_NODE_REPS 2 // node steps per trip of the loop (the ballots / refill checks of a trip are paid once)
@@ -430,7 +436,27 @@ __global__ void __launch_bounds__(RPTR_TRACE_THREADS, 1) k_trace_persistent(BvhD
                     TailRec tr;
                     tr.slot = slot; tr.tmin = tmin; tr.after_id = (Alpha && !Any) ? after_id : 0x7fffffff;
                     tr.best_t = best_t; tr.best_u = best_u; tr.best_v = best_v; tr.best_tri = best_tri; tr.best_id = best_id;
-                    io.tail[atomicAdd(io.tail_count, 1u)] = tr;
+                    TailRec *out = io.tail + atomicAdd(io.tail_count, 1u);
+                    int ng = 0, nt = 0;
+                    if (sp > RPTR_SMEM_STACK) ng = -1; // part of the stack is in local memory: restart at the root
+                    else {
+                        for (int i = 0; i < sp; ++i) {
+                            out->gx[ng] = lds32(sst + (uint32_t)i * RPTR_STACK_STRIDE);
+                            out->gy[ng] = lds32(sst + (uint32_t)i * RPTR_STACK_STRIDE + RPTR_STACK_PLANE_BYTES);
+                            ++ng;
+                        }
+                        if ((gy & 0xffu) != 0u) { out->gx[ng] = gx; out->gy[ng] = gy; ++ng; }
+                        for (int i = 0; i < tsp; ++i) {
+                            out->gx[ng + nt] = lds32(tst + (uint32_t)i * RPTR_STACK_STRIDE);
+                            out->gy[ng + nt] = lds32(tst + (uint32_t)i * RPTR_STACK_STRIDE + RPTR_TRI_PLANE_BYTES);
+                            ++nt;
+                        }
+                        if ((ty & 0xffu) != 0u) { out->gx[ng + nt] = tx; out->gy[ng + nt] = ty; ++nt; }
+                    }
+                    tr.n_node_groups = ng; tr.n_tri_groups = nt;
+                    // header only (the groups were written in place)
+                    out->slot = tr.slot; out->tmin = tr.tmin; out->after_id = tr.after_id; out->best_t = tr.best_t; out->best_u = tr.best_u;
+                    out->best_v = tr.best_v; out->best_tri = tr.best_tri; out->best_id = tr.best_id; out->n_node_groups = ng; out->n_tri_groups = nt;
                 }
                 break;
             }

@@ -31,6 +31,14 @@ namespace rp {
 
 #if defined(__CUDACC__)
 
+// priority permutation of an 8-bit hit mask (the LUT of the persistent kernel, computed; an involution): bit (s ^ oct) <-> bit s
+__device__ __forceinline__ uint32_t order_hits(uint32_t m, uint32_t oct) {
+    if (oct & 1u) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
+    if (oct & 2u) m = ((m & 0x33u) << 2) | ((m >> 2) & 0x33u);
+    if (oct & 4u) m = ((m & 0x0fu) << 4) | ((m >> 4) & 0x0fu);
+    return m;
+}
+
 template <bool Any, bool Alpha>
 __global__ void __launch_bounds__(RPTR_TAIL_WARPS * 32) k_trace_tail(BvhDev bvh, TraceIO io, unsigned long long *c_nodes, unsigned long long *c_tris) {
     constexpr int G = RPTR_TAIL_GROUP, NG = 32 / G;
@@ -54,6 +62,11 @@ __global__ void __launch_bounds__(RPTR_TAIL_WARPS * 32) k_trace_tail(BvhDev bvh,
     float tmin = 0.0f, tmax = 0.0f, best_t = 0.0f, best_u = 0.0f, best_v = 0.0f;
     int32_t after_id = 0x7fffffff, best_tri = -1, best_id = 0x7fffffff;
     int32_t cs = 0; // nodes on the group's frontier
+    // a ray that was handed over with its pending groups resumes: while resume_at < resume_n the lanes take record entries
+    // (node groups -> their pending children go onto the frontier; triangle groups -> their pending triangles are tested)
+    // instead of nodes
+    const TailRec *resume_rec = nullptr;
+    int32_t resume_at = 0, resume_n = 0, resume_nodes = 0;
     for (;;) {
         // ---- groups without a ray take the next record of the tail list ----
         if (__any_sync(FULL, !active && !exhausted)) {
@@ -72,8 +85,17 @@ __global__ void __launch_bounds__(RPTR_TAIL_WARPS * 32) k_trace_tail(BvhDev bvh,
                     tmin = tr.tmin; tmax = rd.w; after_id = tr.after_id;
                     best_t = tr.best_t; best_u = tr.best_u; best_v = tr.best_v; best_tri = tr.best_tri; best_id = tr.best_id;
                     if (Alpha && Any) pixel_linear = tile_pixel_linear(io.tm, __float_as_uint(io.sh_c[slot].w) % (uint32_t)io.tm.local_pixels);
-                    cs = bvh.n_nodes > 0 ? 1 : 0;
-                    if (sub == 0) frontier[0] = 0;
+                    if (tr.n_node_groups < 0) { // not recorded: from the root
+                        cs = bvh.n_nodes > 0 ? 1 : 0;
+                        if (sub == 0) frontier[0] = 0;
+                        resume_n = 0;
+                    } else {
+                        cs = 0;
+                        resume_rec = io.tail + rec;
+                        resume_nodes = tr.n_node_groups;
+                        resume_n = tr.n_node_groups + tr.n_tri_groups;
+                    }
+                    resume_at = 0;
                     active = true;
                 }
             }
@@ -82,14 +104,30 @@ __global__ void __launch_bounds__(RPTR_TAIL_WARPS * 32) k_trace_tail(BvhDev bvh,
         __syncwarp(); // pushes of the previous step before the reads below
         // ---- one step: every lane of a group takes one node off the top of the group's frontier (one lane only while the frontier
         //      is nearly full: a depth-first walk adds at most seven entries per level of the tree, and that much is kept in reserve) ----
+        const bool resuming = active && resume_at < resume_n;
         const int width = cs > RPTR_TAIL_FRONTIER - RPTR_TAIL_RESERVE ? 1 : G;
-        const int take = !active ? 0 : (cs < width ? cs : width);
+        const int take = (!active || resuming) ? 0 : (cs < width ? cs : width);
         const int32_t node = sub < take ? frontier[cs - 1 - sub] : -1;
         cs -= take;
         __syncwarp();
         if (sub == 0) n_nodes += (unsigned long long)take;
         uint32_t ih = 0u, th = 0u, imask = 0u, lmask = 0u;
         int32_t child_base = 0, tri_base = 0;
+        if (resuming) { // lane `sub` takes entry resume_at + sub of the record
+            const int32_t e = resume_at + sub;
+            if (e < resume_n) {
+                const uint32_t ex = resume_rec->gx[e], ey = resume_rec->gy[e];
+                if (e < resume_nodes) { // pending inner children, in priority order for closest-hit rays
+                    const uint32_t oct = Any ? 0u : ray_octant(d);
+                    imask = (ey >> 8) & 0xffu; ih = Any ? (ey & 0xffu) : order_hits(ey & 0xffu, oct);
+                    child_base = (int32_t)ex;
+                } else { // pending triangles
+                    lmask = (ey >> 8) & 0xffu; th = ey & 0xffu;
+                    tri_base = (int32_t)ex;
+                }
+            }
+            resume_at += G;
+        }
         if (node >= 0) {
             const bool sx = inv.x < 0.0f, sy = inv.y < 0.0f, sz = inv.z < 0.0f;
             const char *np = reinterpret_cast<const char *>(bvh.nodes + node);
@@ -184,7 +222,7 @@ __global__ void __launch_bounds__(RPTR_TAIL_WARPS * 32) k_trace_tail(BvhDev bvh,
             }
         }
         // ---- a ray whose frontier is empty (or that is occluded) is finished ----
-        if (active && (cs == 0 || occluded)) {
+        if (active && ((cs == 0 && resume_at >= resume_n) || occluded)) {
             bool again = false;
             if (Alpha && !Any && best_tri >= 0) { // the verdict of the alpha filter on the closest candidate (as at the retire step of the persistent kernel)
                 const int32_t ga = bvh.tris[best_tri].gi_alpha;
@@ -200,6 +238,7 @@ __global__ void __launch_bounds__(RPTR_TAIL_WARPS * 32) k_trace_tail(BvhDev bvh,
                         best_t = tmax; best_u = 0.0f; best_v = 0.0f; best_tri = -1; best_id = 0x7fffffff;
                         cs = 1;
                         if (sub == 0) frontier[0] = 0;
+                        resume_n = 0; resume_at = 0;
                         again = true;
                     }
                 }
