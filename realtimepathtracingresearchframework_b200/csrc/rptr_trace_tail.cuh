@@ -1,20 +1,23 @@
-// rptr_trace_tail.cuh -- the tail of a trace launch: the last rays of a queue, one WARP per ray.
+// rptr_trace_tail.cuh -- the tail of a trace launch: the last rays of a queue, eight lanes per ray.
 //
 // A launch of the persistent kernel (rptr_trace_kernels.cuh) cannot end before its longest ray has, and in the per-lane state
 // machine that ray advances one node at a time at the latency of a lone warp (~0.9 us per node step: a dependent L2 fetch plus
 // several hundred instructions issued back to back) while 31 lanes idle -- a floor of 0.23-0.29 ms per launch, 17 launches per
 // frame, which is what caps strong scaling over GPUs (profiles/r02_sweeps.md).  So a warp of the persistent kernel that finds the
-// queue drained and is down to its last RPTR_TAIL_LIVE rays hands them over instead of finishing them: it appends (slot, best hit
-// so far, alpha state) records to the launch's tail list and exits.  k_trace_tail runs right behind it on the same stream and
-// takes eight lanes per record, four rays per warp, records claimed from a cursor: the ray restarts at the root -- with the best hit found so far as its t_max, so what was pruned
-// stays pruned -- and the group walks the tree breadth-wise: every step each of its lanes takes one node off the ray's frontier
-// (eight nodes per step instead of one), tests its eight slots with the node step of the persistent kernel, the inner children that were hit go
-// back onto the frontier (prefix sum over the group), the triangle slots that were hit are intersected by the lane that found
-// them, and one arg-min by (t, id) over the group per step shortens the ray.  (One WARP per ray, 32 nodes per step, was the
-// version before: 12-14 lanes active, most steps of a ray have fewer than a dozen nodes on the frontier.)  Same box
-// tests, same intersect_tri, same tie-break, and the closest-hit / any-hit result does not depend on the order of the walk
-// (culling only prunes): bit-identical images with the tail kernel on or off (tests/test_gpu_parity.py).  (A first version
-// that tested four nodes per step, eight lanes per node, was no faster than the state machine it relieved.)
+// queue drained and is down to its last RPTR_TAIL_LIVE rays hands them over instead of finishing them: it appends a record per
+// ray -- slot, best hit so far, alpha-filter state, and the (base, masks) groups the lane still had pending: its node-group stack,
+// its triangle backlog, its two current groups -- to the launch's tail list and exits.  k_trace_tail runs right behind it on the
+// same stream and gives every record eight lanes (four rays per warp, records claimed from a cursor).  The ray RESUMES: the
+// lanes first take the record's groups (the pending children of the node groups go onto the ray's frontier in shared memory,
+// the pending triangles are tested), then walk on breadth-wise -- every step each lane takes one node off the frontier (eight
+// nodes per step instead of one), tests its eight slots with the node step of the persistent kernel, the inner children that
+// were hit go back onto the frontier (prefix sum over the group), the triangle slots that were hit are intersected by the lane
+// that found them, and one arg-min by (t, id) over the group per step shortens the ray.  Same box tests, same intersect_tri,
+// same tie-break, and the closest-hit / any-hit result does not depend on the order of the walk (culling only prunes):
+// bit-identical images with the tail kernel on or off (tests/test_gpu_parity.py).
+// Versions measured on the way (profiles/r02_sweeps.md): four nodes per step with eight lanes per NODE (no faster than the state
+// machine it relieved); one warp per ray, 32 nodes per step (12-14 lanes active: most steps of a ray have fewer than a dozen
+// nodes on the frontier); eight lanes per ray restarting at the root (every handed-over ray paid its whole walk again).
 #pragma once
 #include "rptr_trace_kernels.cuh"
 
