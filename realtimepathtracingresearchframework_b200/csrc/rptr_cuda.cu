@@ -212,13 +212,21 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
         if (threadIdx.x < RPTR_SHADE_KEYS) s_hist[threadIdx.x] = 0;
         __syncthreads();
         uint32_t my_slot[RPTR_SHADE_PER_THREAD], my_key[RPTR_SHADE_PER_THREAD], my_pos[RPTR_SHADE_PER_THREAD];
+        // the two dependent gathers of the key (queue word, then the hit record) are issued for all of the thread's entries before
+        // any of them is consumed: two memory round trips per tile instead of eight (profiles/r02_shade_source_stalls.md)
+        int my_tri[RPTR_SHADE_PER_THREAD];
 #pragma unroll
         for (int k = 0; k < RPTR_SHADE_PER_THREAD; ++k) {
             const uint32_t j = k * RPTR_SHADE_THREADS + threadIdx.x;
+            my_slot[k] = j < tile_count ? (queue ? queue[tile_base + j] : tile_base + j) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < RPTR_SHADE_PER_THREAD; ++k) my_tri[k] = my_slot[k] != 0xffffffffu ? __float_as_int(w.hit[my_slot[k]].w) : -1;
+#pragma unroll
+        for (int k = 0; k < RPTR_SHADE_PER_THREAD; ++k) {
             my_key[k] = 0xffffffffu;
-            if (j < tile_count) {
-                const uint32_t slot = queue ? queue[tile_base + j] : tile_base + j;
-                const int tri = __float_as_int(w.hit[slot].w);
+            if (my_slot[k] != 0xffffffffu) {
+                const int tri = my_tri[k];
                 uint32_t key = tri >= 0 ? 1u : 0u; // miss / hit
 
                 if (tri >= 0 && sort_tiles > 1) { // several code paths in the scene: look the material up
@@ -231,7 +239,6 @@ __global__ void __launch_bounds__(RPTR_SHADE_THREADS, RPTR_SHADE_MIN_BLOCKS) k_s
                     if ((FEAT & RPTR_FEAT_TRANSMISSION) && fp.transmission && m.ior > 1.0f && m.specular_transmission > 0.0f) key = (m.flags & RPTR_BASE_MATERIAL_ONESIDED) ? 4u : 3u;
                     if (m.emission_intensity != 0.0f) key += 5u;
                 }
-                my_slot[k] = slot;
                 my_key[k] = key;
                 my_pos[k] = atomicAdd(&s_hist[key], 1u);
             }
